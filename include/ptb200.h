@@ -1,0 +1,256 @@
+/*
+ * ptb200.h — C ABI of the B200-native path-tracing backend ("ptb200") for
+ * nonl4331/raytracing-rust.
+ *
+ * This header is the drop-in boundary: it is exactly what a Rust `build.rs` +
+ * `extern "C"` shim (see ffi/rust/) binds when the frontend is
+ * started with `--backend cuda`.  All citations are file:line into the reference
+ * tree (crates/<name>/src/... abbreviated as <name>/...).
+ *
+ * Conventions
+ *   - every entry point returns an int32 status (PTB_OK == 0); no C++ exception
+ *     or Rust panic ever crosses the boundary; ptb_last_error() gives the text;
+ *   - the caller owns all host buffers; the library copies on upload;
+ *   - one ptb_ctx per GPU; a ctx is not thread-safe, distinct ctxs are independent;
+ *   - plain pointers and sizes only; every struct below is #[repr(C)]-mirrorable POD;
+ *   - primitive ids are indices into the reference's primitive array order:
+ *     all spheres first, then all mesh triangles (loader/lib.rs:234-240);
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry
+ *     point fails with PTB_ERR_CUDA.
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_ABI_VERSION 1u
+
+/* ---------------------------------------------------------------- status -- */
+enum {
+  PTB_OK = 0,
+  PTB_ERR_INVALID = 1,   /* bad argument / bad state (e.g. render before commit)   */
+  PTB_ERR_CUDA = 2,      /* CUDA runtime error or no device                          */
+  PTB_ERR_OOM = 3,       /* host or device allocation failed                         */
+  PTB_ERR_PARSE = 4,     /* .ssml / .obj syntax error     (loader LoadErr::ParseError, lib.rs:180-194) */
+  PTB_ERR_IO = 5,        /* file could not be read/written (LoadErr::FileNotRead)    */
+  PTB_ERR_MISSING = 6,   /* required key/object missing   (LoadErr::MissingRequired, MissingCamera) */
+  PTB_ERR_ABORTED = 7,   /* progress callback asked to stop (random_sampler.rs:84-86) */
+  PTB_ERR_UNSUPPORTED = 8
+};
+
+/* ------------------------------------------------------------------- POD -- */
+/* rt_core/vec.rs:108-114 — `#[repr(C)] struct Vec3 { x, y, z }` with Float = f32 (rt_core/lib.rs:23-29) */
+typedef struct ptb_vec3 { float x, y, z; } ptb_vec3;
+
+/* implementations/primitives/sphere.rs:8-13 (material reference -> index into the material array) */
+typedef struct ptb_sphere {
+  ptb_vec3 center;
+  float    radius;
+  uint32_t material;
+} ptb_sphere;
+
+/* implementations/primitives/triangle.rs:9-14 / :30-36 — Triangle and MeshTriangle both flatten to this:
+ * three positions, three vertex normals (MeshData indirection resolved by the host), one material. */
+typedef struct ptb_triangle {
+  ptb_vec3 p[3];
+  ptb_vec3 n[3];
+  uint32_t material;
+} ptb_triangle;
+
+/* enum order == tag order: implementations/materials/mod.rs:19-25 */
+enum {
+  PTB_MAT_EMIT = 0,             /* emissive.rs:7-10      param = strength */
+  PTB_MAT_LAMBERTIAN = 1,       /* lambertian.rs:6-9     param = albedo   */
+  PTB_MAT_TROWBRIDGE_REITZ = 2, /* trowbridge_reitz.rs:6-11  param = alpha (already squared), ior, metallic */
+  PTB_MAT_REFLECT = 3,          /* reflect.rs:8-11       param = fuzz     */
+  PTB_MAT_REFRACT = 4           /* refract.rs:9-12       param = eta      */
+};
+typedef struct ptb_material {
+  uint32_t kind;
+  uint32_t texture;   /* index into the texture array */
+  float    param;
+  ptb_vec3 ior;       /* TrowbridgeReitz only */
+  float    metallic;  /* TrowbridgeReitz only */
+} ptb_material;
+
+/* enum order == tag order: implementations/textures/mod.rs:17-24 */
+enum {
+  PTB_TEX_CHECKERED = 0, /* textures/mod.rs:26-30,61-73   a = colour_one, b = colour_two */
+  PTB_TEX_SOLID = 1,     /* textures/mod.rs:182-200       a = colour                     */
+  PTB_TEX_IMAGE = 2,     /* textures/mod.rs:202-266       (not supported by the device path yet) */
+  PTB_TEX_LERP = 3,      /* textures/mod.rs:268-291       a = colour_one, b = colour_two */
+  PTB_TEX_PERLIN = 4     /* textures/mod.rs:75-180        (not supported by the device path yet) */
+};
+typedef struct ptb_texture {
+  uint32_t kind;
+  ptb_vec3 a;
+  ptb_vec3 b;
+} ptb_texture;
+
+/* implementations/camera.rs:6-17 — only the four vectors get_ray() reads (camera.rs:57-63) */
+typedef struct ptb_camera {
+  ptb_vec3 origin;
+  ptb_vec3 lower_left;
+  ptb_vec3 horizontal;
+  ptb_vec3 vertical;
+} ptb_camera;
+
+/* implementations/sky.rs:12-18 — material is always Emit(texture, 1.0) (loader/misc.rs:26);
+ * sampler_res (0,0) disables importance sampling (sky.rs:61-63). The library builds the
+ * Distribution2D table itself (sky.rs:20-37, textures/mod.rs:32-50, distributions.rs:82-99). */
+typedef struct ptb_sky {
+  uint32_t texture;
+  uint32_t sampler_res_x;
+  uint32_t sampler_res_y;
+} ptb_sky;
+
+/* rt_core/ray.rs:4-11 — the caller passes origin + (un-normalised) direction; the library derives
+ * direction/|direction|, d_inverse and shear exactly as Ray::new does (ray.rs:13-46). 2 x 16 B. */
+typedef struct ptb_ray {
+  float ox, oy, oz, _pad0;
+  float dx, dy, dz, _pad1;
+} ptb_ray;
+
+/* what AccelerationStructure::check_hit returns (implementations/acceleration/mod.rs:265-298), reduced
+ * to the comparable part: t, primitive id in the ORIGINAL (pre-BVH) order, barycentrics b1,b2 of
+ * triangle.rs:149-151 (0 for spheres). Miss: prim = PTB_MISS, t = 0 (sky.rs:79-91). 16 B. */
+#define PTB_MISS 0xFFFFFFFFu
+typedef struct ptb_hit {
+  float    t;
+  uint32_t prim;
+  float    u, v;
+} ptb_hit;
+
+/* implementations/samplers/mod.rs:43-47 */
+enum { PTB_METHOD_NAIVE = 0, PTB_METHOD_MIS = 1 };
+
+/* implementations/samplers/mod.rs:22-29 + the constants of integrators/mod.rs:7-8 made explicit,
+ * plus what a deterministic, shardable device renderer needs (seed, sample_offset). */
+typedef struct ptb_render_opts {
+  uint32_t width;
+  uint32_t height;
+  uint32_t samples_per_pixel; /* samples rendered by THIS call                                  */
+  uint32_t sample_offset;     /* absolute index of the first sample (rank r renders [off, off+spp)) */
+  uint32_t method;            /* PTB_METHOD_*; reference default is MIS (parameters.rs:34-35)   */
+  uint32_t max_depth;         /* 0 -> 50  (integrators/mod.rs:7)                                */
+  uint32_t rr_threshold;      /* 0xFFFFFFFF -> 3 (integrators/mod.rs:8); RR applies when depth > threshold */
+  uint32_t flags;             /* reserved, 0                                                    */
+  uint64_t seed;              /* counter-based RNG key; same seed + same sample range == same image */
+} ptb_render_opts;
+#define PTB_RR_DEFAULT 0xFFFFFFFFu
+
+/* BVH2 node as exported for bit-exact tests: both children's boxes live in the parent (64 B).
+ * child ref: bit31 set -> leaf, low bits = position in the Morton-sorted primitive order. */
+#define PTB_LEAF_BIT 0x80000000u
+typedef struct ptb_bvh_node {
+  float    lmin[3], lmax[3];
+  float    rmin[3], rmax[3];
+  uint32_t left, right;
+  uint32_t parent;  /* 0xFFFFFFFF for the root */
+  uint32_t _pad;
+} ptb_bvh_node;
+
+typedef struct ptb_stats {
+  uint64_t rays_camera;        /* traversals launched for camera rays                         */
+  uint64_t rays_bounce;        /* ... for BSDF-sampled bounce rays                            */
+  uint64_t rays_shadow_light;  /* ... for NEE rays towards a light primitive (check_hit_index) */
+  uint64_t rays_shadow_sky;    /* ... for NEE rays towards the sky                            */
+  uint64_t rays_reference;     /* the reference's own counter: naive = 1 per check_hit (integrators/mod.rs:34),
+                                  MIS = 1 per bounce iteration (mis.rs:38)                     */
+  uint64_t paths;              /* camera paths finished                                       */
+  uint64_t wavefront_iterations;
+  uint64_t kernel_launches;    /* kernels of this library launched since the last ptb_stats_reset */
+  double   build_ms;           /* last ptb_scene_commit: device LBVH build time               */
+  double   render_ms;          /* last ptb_render: device time (CUDA events)                  */
+} ptb_stats;
+
+typedef struct ptb_ctx ptb_ctx;
+
+/* called between wavefront iterations; return non-zero to abort (random_sampler.rs:82-88 contract,
+ * carrying counters only — the per-pass image is replaced by the device accumulator). */
+typedef int32_t (*ptb_progress_fn)(void* user, uint64_t samples_completed, uint64_t rays_shot);
+
+/* ------------------------------------------------------------ lifecycle -- */
+uint32_t    ptb_abi_version(void);
+int32_t     ptb_device_count(int32_t* count);
+int32_t     ptb_create(int32_t device, ptb_ctx** out);
+int32_t     ptb_destroy(ptb_ctx* ctx);
+const char* ptb_last_error(const ptb_ctx* ctx);           /* ctx may be NULL: last error of ptb_create */
+int32_t     ptb_set_stream(ptb_ctx* ctx, void* cuda_stream); /* optional: run on the caller's cudaStream_t */
+int32_t     ptb_synchronize(ptb_ctx* ctx);
+
+/* ---------------------------------------------------------------- scene -- */
+/* Replaces what loader::load_file_full returns (loader/lib.rs:196-243) + Bvh::new's input
+ * (implementations/acceleration/mod.rs:58-93). Host pointers; copied. n may be 0. */
+int32_t ptb_scene_set_spheres(ptb_ctx* ctx, const ptb_sphere* spheres, size_t n);
+int32_t ptb_scene_set_triangles(ptb_ctx* ctx, const ptb_triangle* triangles, size_t n);
+int32_t ptb_scene_set_materials(ptb_ctx* ctx, const ptb_material* materials, size_t n);
+int32_t ptb_scene_set_textures(ptb_ctx* ctx, const ptb_texture* textures, size_t n);
+int32_t ptb_scene_set_camera(ptb_ctx* ctx, const ptb_camera* camera);
+int32_t ptb_scene_set_sky(ptb_ctx* ctx, const ptb_sky* sky);
+
+/* Replaces Bvh::new (acceleration/mod.rs:58-93): uploads the scene and builds the LBVH on the device. */
+enum { PTB_BUILD_DEFAULT = 0 };
+int32_t ptb_scene_commit(ptb_ctx* ctx, uint32_t build_flags);
+
+/* Bit-exact test hooks: n_prims Morton codes and primitive ids in sorted order, n_prims-1 nodes
+ * (1 node when n_prims == 1). Any pointer may be NULL. */
+int32_t ptb_bvh_info(ptb_ctx* ctx, uint64_t* n_prims, uint64_t* n_nodes);
+int32_t ptb_bvh_export(ptb_ctx* ctx, uint32_t* morton_sorted, uint32_t* prim_sorted, ptb_bvh_node* nodes);
+
+/* ---------------------------------------------------------- closest hit -- */
+/* Replaces AccelerationStructure::check_hit (acceleration/mod.rs:265-298) for a batch of rays.
+ * Host buffers; H2D + kernel + D2H. */
+int32_t ptb_closest_hit(ptb_ctx* ctx, const ptb_ray* rays, size_t n, ptb_hit* hits);
+/* Same, buffers already resident in device memory (kernel only; used for roofline timing). */
+int32_t ptb_closest_hit_device(ptb_ctx* ctx, const void* d_rays, size_t n, void* d_hits);
+
+/* --------------------------------------------------------------- render -- */
+/* Replaces Sampler::sample_image (samplers/mod.rs:7-20, random_sampler.rs:10-99) + the running mean of
+ * src/main.rs:175-191: adds opts->samples_per_pixel samples per pixel into the device accumulator (sums). */
+int32_t ptb_render(ptb_ctx* ctx, const ptb_render_opts* opts, ptb_progress_fn progress, void* user);
+int32_t ptb_accum_clear(ptb_ctx* ctx);
+/* Reads back width*height*3 floats, row-major, top row first, RGB (the layout of
+ * SamplerProgress.current_image, samplers/mod.rs:49-63). normalise != 0 divides by the samples accumulated. */
+int32_t ptb_accum_read(ptb_ctx* ctx, float* rgb, size_t n_floats, int32_t normalise);
+/* Device pointer of the width*height*3 float sums (for the NCCL reduce) and its element count. */
+int32_t ptb_accum_device_ptr(ptb_ctx* ctx, void** d_ptr, size_t* n_floats);
+/* After an external reduce wrote sums of `total_samples` samples into the accumulator. */
+int32_t ptb_accum_set_samples(ptb_ctx* ctx, uint64_t total_samples);
+
+int32_t ptb_stats_get(ptb_ctx* ctx, ptb_stats* out);
+int32_t ptb_stats_reset(ptb_ctx* ctx);
+
+/* ------------------------------------------------------------- host side -- */
+/* C++ restatement of the `loader` crate (loader/lib.rs:196-243, parser.rs:112-197, misc.rs, materials.rs,
+ * primitives.rs, meshes.rs, obj.rs, textures.rs): parses a .ssml file (and the OBJ files it names) into the
+ * POD arrays above. No GPU needed. */
+typedef struct ptb_host_scene ptb_host_scene;
+int32_t ptb_ssml_load_file(const char* path, ptb_host_scene** out);
+int32_t ptb_ssml_load_str(const char* text, const char* base_dir, ptb_host_scene** out);
+void    ptb_host_scene_free(ptb_host_scene* s);
+const char* ptb_host_last_error(void);
+size_t  ptb_host_scene_spheres(const ptb_host_scene* s, const ptb_sphere** out);
+size_t  ptb_host_scene_triangles(const ptb_host_scene* s, const ptb_triangle** out);
+size_t  ptb_host_scene_materials(const ptb_host_scene* s, const ptb_material** out);
+size_t  ptb_host_scene_textures(const ptb_host_scene* s, const ptb_texture** out);
+int32_t ptb_host_scene_camera(const ptb_host_scene* s, ptb_camera* out);
+int32_t ptb_host_scene_sky(const ptb_host_scene* s, ptb_sky* out);
+/* SimpleCamera::new (camera.rs:20-53); aspect is 16/9 in the loader (loader/misc.rs:15). */
+int32_t ptb_camera_make(ptb_vec3 origin, ptb_vec3 lookat, ptb_vec3 vup, float hfov_deg, float aspect,
+                        float aperture, float focus_dist, ptb_camera* out);
+/* ptb_scene_set_* for every array of a loaded scene. */
+int32_t ptb_scene_upload(ptb_ctx* ctx, const ptb_host_scene* s);
+
+/* output::save_data_to_image (output/lib.rs:74-113): gamma + 8-bit for ppm/bmp/png, linear f32 for pfm. */
+int32_t ptb_image_save(const char* filename, uint32_t width, uint32_t height, const float* rgb, float gamma);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H */

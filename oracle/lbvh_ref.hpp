@@ -1,0 +1,214 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ref_math.hpp header).
+// CPU statement of the device LBVH (the reference has no Morton/LBVH code: its builder is the top-down SAH
+// of acceleration/mod.rs:97-160, restated in ref_bvh.hpp). This file defines, operation by operation, the
+// tree the device must reproduce BIT-EXACTLY (Morton keys, sorted order, child/parent links, boxes), and the
+// ordered, t-culled stack traversal whose mean node/triangle counts define the algorithmic bytes per ray
+// (B_ray = 32 + 16 + V*64 + T*48).
+//
+// Build (Karras 2012, "Maximizing parallelism in the construction of BVHs, octrees, and k-d trees"):
+//   1. per primitive: AABB (sphere.rs:175-181 / triangle.rs:285-307), centroid = 0.5*(min+max)
+//      (acceleration/mod.rs:29-41);
+//   2. scene bounds over the centroids; q_axis = (uint)clamp((c-cmin)/(cmax-cmin)*1024, 0, 1023)
+//      (0 when the extent is 0); 30-bit Morton code, x in the most significant interleave position;
+//   3. stable sort by code (ties keep primitive-index order);
+//   4. hierarchy with delta(i,j) = clz(code_i ^ code_j), ties broken by 32 + clz(i ^ j);
+//   5. bottom-up refit: box(node) = union of its children's boxes; each node stores BOTH children's boxes.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <vector>
+
+#include "ref_scene.hpp"
+
+namespace ref {
+
+static inline uint32_t expand_bits10(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+static inline uint32_t quantise10(Float c, Float cmin, Float ext) {
+  Float n = ext > 0.0f ? (c - cmin) / ext : 0.0f;
+  Float s = fmin_(fmax_(n * 1024.0f, 0.0f), 1023.0f);
+  return (uint32_t)s;
+}
+static inline int clz32(uint32_t x) { return x == 0 ? 32 : __builtin_clz(x); }
+
+struct Lbvh {
+  std::vector<Prim> prims;          // original (loader) order
+  std::vector<uint32_t> morton;     // sorted
+  std::vector<uint32_t> prim_sorted;  // sorted position -> original primitive id
+  std::vector<ptb_bvh_node> nodes;  // n-1 internal nodes (1 when n == 1), root = 0
+  Vec3 cmin, cmax;
+
+  int delta(int64_t i, int64_t j) const {
+    int64_t n = (int64_t)morton.size();
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = morton[i], b = morton[j];
+    if (a == b) return 32 + clz32((uint32_t)i ^ (uint32_t)j);
+    return clz32(a ^ b);
+  }
+
+  void build(const std::vector<Prim>& in) {
+    prims = in;
+    const size_t n = prims.size();
+    morton.assign(n, 0);
+    prim_sorted.assign(n, 0);
+    nodes.clear();
+    if (n == 0) return;
+    std::vector<Vec3> bmin(n), bmax(n), cen(n);
+    for (size_t i = 0; i < n; ++i) {
+      prims[i].aabb(bmin[i], bmax[i]);
+      cen[i] = 0.5f * (bmin[i] + bmax[i]);
+    }
+    cmin = cen[0]; cmax = cen[0];
+    for (size_t i = 1; i < n; ++i) { cmin = cmin.min_by_component(cen[i]); cmax = cmax.max_by_component(cen[i]); }
+    Vec3 ext = cmax - cmin;
+    std::vector<uint32_t> code(n);
+    for (size_t i = 0; i < n; ++i) {
+      uint32_t qx = quantise10(cen[i].x, cmin.x, ext.x);
+      uint32_t qy = quantise10(cen[i].y, cmin.y, ext.y);
+      uint32_t qz = quantise10(cen[i].z, cmin.z, ext.z);
+      code[i] = (expand_bits10(qx) << 2) | (expand_bits10(qy) << 1) | expand_bits10(qz);
+    }
+    std::vector<uint32_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return code[a] < code[b]; });
+    for (size_t i = 0; i < n; ++i) { morton[i] = code[order[i]]; prim_sorted[i] = order[i]; }
+
+    auto set_box = [](float* mn, float* mx, const Vec3& a, const Vec3& b) {
+      mn[0] = a.x; mn[1] = a.y; mn[2] = a.z; mx[0] = b.x; mx[1] = b.y; mx[2] = b.z;
+    };
+    if (n == 1) {  // single primitive: both child slots reference leaf 0
+      ptb_bvh_node nd{};
+      set_box(nd.lmin, nd.lmax, bmin[order[0]], bmax[order[0]]);
+      set_box(nd.rmin, nd.rmax, bmin[order[0]], bmax[order[0]]);
+      nd.left = PTB_LEAF_BIT | 0u;
+      nd.right = PTB_LEAF_BIT | 0u;
+      nd.parent = 0xFFFFFFFFu;
+      nodes.push_back(nd);
+      return;
+    }
+    nodes.assign(n - 1, ptb_bvh_node{});
+    std::vector<uint32_t> leaf_parent(n, 0xFFFFFFFFu);
+    nodes[0].parent = 0xFFFFFFFFu;
+    for (int64_t i = 0; i < (int64_t)n - 1; ++i) {
+      int d = (delta(i, i + 1) - delta(i, i - 1)) < 0 ? -1 : 1;
+      int dmin = delta(i, i - d);
+      int64_t lmax = 2;
+      while (delta(i, i + lmax * d) > dmin) lmax *= 2;
+      int64_t l = 0;
+      for (int64_t t = lmax / 2; t >= 1; t /= 2)
+        if (delta(i, i + (l + t) * d) > dmin) l += t;
+      int64_t j = i + l * d;
+      int dnode = delta(i, j);
+      int64_t s = 0;
+      for (int64_t t = (l + 1) / 2;; t = (t + 1) / 2) {
+        if (delta(i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+      }
+      int64_t gam = i + s * d + (d < 0 ? -1 : 0);
+      int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+      if (lo == gam) { nodes[i].left = PTB_LEAF_BIT | (uint32_t)gam; leaf_parent[gam] = (uint32_t)i; }
+      else { nodes[i].left = (uint32_t)gam; nodes[gam].parent = (uint32_t)i; }
+      if (hi == gam + 1) { nodes[i].right = PTB_LEAF_BIT | (uint32_t)(gam + 1); leaf_parent[gam + 1] = (uint32_t)i; }
+      else { nodes[i].right = (uint32_t)(gam + 1); nodes[gam + 1].parent = (uint32_t)i; }
+    }
+    // bottom-up refit (post-order recursion is equivalent to the device's atomic-flag walk: min/max are exact)
+    std::vector<Vec3> nmin(n - 1), nmax(n - 1);
+    std::vector<int> state(n - 1, 0);
+    std::vector<uint32_t> stack;
+    stack.push_back(0);
+    while (!stack.empty()) {
+      uint32_t i = stack.back();
+      ptb_bvh_node& nd = nodes[i];
+      bool ready = true;
+      if (!(nd.left & PTB_LEAF_BIT) && state[nd.left] == 0) { stack.push_back(nd.left); ready = false; }
+      if (!(nd.right & PTB_LEAF_BIT) && state[nd.right] == 0) { stack.push_back(nd.right); ready = false; }
+      if (!ready) continue;
+      Vec3 lmn, lmx, rmn, rmx;
+      if (nd.left & PTB_LEAF_BIT) { uint32_t p = order[nd.left & ~PTB_LEAF_BIT]; lmn = bmin[p]; lmx = bmax[p]; }
+      else { lmn = nmin[nd.left]; lmx = nmax[nd.left]; }
+      if (nd.right & PTB_LEAF_BIT) { uint32_t p = order[nd.right & ~PTB_LEAF_BIT]; rmn = bmin[p]; rmx = bmax[p]; }
+      else { rmn = nmin[nd.right]; rmx = nmax[nd.right]; }
+      set_box(nd.lmin, nd.lmax, lmn, lmx);
+      set_box(nd.rmin, nd.rmax, rmn, rmx);
+      nmin[i] = lmn.min_by_component(rmn);
+      nmax[i] = lmx.max_by_component(rmx);
+      state[i] = 1;
+      stack.pop_back();
+    }
+  }
+
+  // Slab test of aabb.rs:22-57 with the device's additions: entry distance returned, culled against best t.
+  static inline bool box_hit(const float* mn, const float* mx, const Ray& ray, Float best_t, Float& tnear) {
+    const Float k = 1.0f + 2.0f * gamma(3);
+    Float t1 = (mn[0] - ray.origin.x) * ray.d_inverse.x;
+    Float t2 = (mx[0] - ray.origin.x) * ray.d_inverse.x;
+    Float tmin = fmin_(t1, t2);
+    Float tmax = fmax_(t1, t2) * k;
+    t1 = (mn[1] - ray.origin.y) * ray.d_inverse.y;
+    t2 = (mx[1] - ray.origin.y) * ray.d_inverse.y;
+    tmin = fmax_(tmin, fmin_(t1, t2));
+    tmax = fmin_(tmax, fmax_(t1, t2) * k);
+    t1 = (mn[2] - ray.origin.z) * ray.d_inverse.z;
+    t2 = (mx[2] - ray.origin.z) * ray.d_inverse.z;
+    tmin = fmax_(tmin, fmin_(t1, t2));
+    tmax = fmin_(tmax, fmax_(t1, t2) * k);
+    tnear = tmin;
+    return tmax > fmax_(tmin, 0.0f) && tmin <= best_t;
+  }
+
+  // Ordered (near child first), t-culled closest hit. Ties on t go to the lower ORIGINAL primitive id.
+  // nodes_fetched / prims_tested feed the algorithmic-bytes-per-ray figure.
+  bool closest_hit(const Ray& ray, Hit& best, uint32_t& best_prim, uint64_t* nodes_fetched, uint64_t* prims_tested) const {
+    best_prim = PTB_MISS;
+    if (nodes.empty()) return false;
+    Float best_t = INF_F;
+    uint32_t stack[128];
+    Float stack_t[128];  // entry distance of the deferred child: re-checked against best_t when popped
+    int sp = 0;
+    uint32_t cur = 0;
+    Hit h;
+    auto pop = [&](uint32_t& out) -> bool {
+      while (sp > 0) {
+        --sp;
+        if (stack_t[sp] <= best_t) { out = stack[sp]; return true; }
+      }
+      return false;
+    };
+    for (;;) {
+      if (cur & PTB_LEAF_BIT) {
+        uint32_t slot = cur & ~PTB_LEAF_BIT;
+        uint32_t pid = prim_sorted[slot];
+        if (prims_tested) ++*prims_tested;
+        if (prims[pid].get_int(ray, h) && h.t > 0.0f) {
+          if (h.t < best_t || (h.t == best_t && pid < best_prim)) { best_t = h.t; best = h; best_prim = pid; }
+        }
+        if (!pop(cur)) break;
+        continue;
+      }
+      const ptb_bvh_node& nd = nodes[cur];
+      if (nodes_fetched) ++*nodes_fetched;
+      Float tl, tr;
+      bool hl = box_hit(nd.lmin, nd.lmax, ray, best_t, tl);
+      bool hr = box_hit(nd.rmin, nd.rmax, ray, best_t, tr);
+      if (hl && hr) {
+        uint32_t nearc = nd.left, farc = nd.right;
+        Float tfar = tr;
+        if (tr < tl) { nearc = nd.right; farc = nd.left; tfar = tl; }
+        stack[sp] = farc;
+        stack_t[sp] = tfar;
+        ++sp;
+        cur = nearc;
+      } else if (hl) cur = nd.left;
+      else if (hr) cur = nd.right;
+      else if (!pop(cur)) break;
+    }
+    return best_prim != PTB_MISS;
+  }
+};
+
+}  // namespace ref

@@ -1,0 +1,384 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see ref_math.hpp header).
+// C entry points (ctypes-friendly) over the CPU restatement. Used by tests/, smoke() and bench.py's CPU legs.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <thread>
+#include <vector>
+
+#include "lbvh_ref.hpp"
+#include "ref_integrators.hpp"
+
+namespace ref {
+thread_local RngCursor g_rng;
+}
+
+using namespace ref;
+
+struct orc_scene {
+  std::vector<Texture> textures;
+  std::vector<Material> materials;
+  std::vector<Prim> prims_original;  // loader order: spheres first, then triangles
+  Bvh bvh;
+  Camera camera;
+  Lbvh lbvh;
+  bool lbvh_built = false;
+  double build_seconds = 0.0;
+};
+
+static inline Vec3 v3(const ptb_vec3& v) { return Vec3(v.x, v.y, v.z); }
+
+template <class F>
+static void parallel_for(size_t n, int threads, F f) {
+  unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
+  if (nt == 0) nt = 1;
+  if (nt == 1 || n < 1024) {
+    f(0, (size_t)0, n);
+    return;
+  }
+  std::atomic<size_t> next(0);
+  const size_t grain = 4096;
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < nt; ++t)
+    pool.emplace_back([&, t]() {
+      for (;;) {
+        size_t b = next.fetch_add(grain);
+        if (b >= n) break;
+        size_t e = b + grain < n ? b + grain : n;
+        f(t, b, e);
+      }
+    });
+  for (auto& th : pool) th.join();
+}
+
+extern "C" {
+
+orc_scene* orc_scene_create(const ptb_sphere* spheres, size_t ns, const ptb_triangle* tris, size_t nt,
+                            const ptb_material* mats, size_t nm, const ptb_texture* texs, size_t ntex,
+                            const ptb_camera* cam, const ptb_sky* sky, int split_type) {
+  orc_scene* s = new orc_scene();
+  s->textures.resize(ntex);
+  for (size_t i = 0; i < ntex; ++i) {
+    s->textures[i].kind = texs[i].kind;
+    s->textures[i].a = v3(texs[i].a);
+    s->textures[i].b = v3(texs[i].b);
+  }
+  s->materials.resize(nm);
+  for (size_t i = 0; i < nm; ++i) {
+    s->materials[i].kind = mats[i].kind;
+    s->materials[i].texture = &s->textures[mats[i].texture];
+    s->materials[i].param = mats[i].param;
+  }
+  s->prims_original.reserve(ns + nt);
+  for (size_t i = 0; i < ns; ++i) {
+    Prim p{};
+    p.is_sphere = 1;
+    p.orig_id = (uint32_t)i;
+    p.material = &s->materials[spheres[i].material];
+    p.center = v3(spheres[i].center);
+    p.radius = spheres[i].radius;
+    s->prims_original.push_back(p);
+  }
+  for (size_t i = 0; i < nt; ++i) {
+    Prim p{};
+    p.is_sphere = 0;
+    p.orig_id = (uint32_t)(ns + i);
+    p.material = &s->materials[tris[i].material];
+    for (int k = 0; k < 3; ++k) { p.p[k] = v3(tris[i].p[k]); p.n[k] = v3(tris[i].n[k]); }
+    s->prims_original.push_back(p);
+  }
+  if (cam) {
+    s->camera.origin = v3(cam->origin);
+    s->camera.lower_left = v3(cam->lower_left);
+    s->camera.horizontal = v3(cam->horizontal);
+    s->camera.vertical = v3(cam->vertical);
+  }
+  if (sky) s->bvh.sky.init(&s->textures[sky->texture], sky->sampler_res_x, sky->sampler_res_y);
+  if (split_type >= 0) {
+    auto t0 = std::chrono::steady_clock::now();
+    s->bvh.build(s->prims_original, (SplitType)split_type);
+    s->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  return s;
+}
+
+void orc_scene_destroy(orc_scene* s) { delete s; }
+size_t orc_bvh_num_nodes(const orc_scene* s) { return s->bvh.nodes.size(); }
+size_t orc_bvh_depth(const orc_scene* s) { return s->bvh.max_depth_seen; }
+double orc_bvh_build_seconds(const orc_scene* s) { return s->build_seconds; }
+size_t orc_num_lights(const orc_scene* s) { return s->bvh.lights.size(); }
+// BVH-order -> original primitive id (the permutation the reference discards, acceleration/mod.rs:79-82)
+void orc_bvh_order(const orc_scene* s, uint32_t* out) {
+  for (size_t i = 0; i < s->bvh.primitives.size(); ++i) out[i] = s->bvh.primitives[i].orig_id;
+}
+
+static inline void fill_hit(ptb_hit& o, bool have, const Hit& h, uint32_t prim) {
+  if (have) { o.t = h.t; o.prim = prim; o.u = h.b1; o.v = h.b2; }
+  else { o.t = 0.0f; o.prim = PTB_MISS; o.u = 0.0f; o.v = 0.0f; }
+}
+
+// check_hit with the reference's SAH tree + BFS candidates (acceleration/mod.rs:265-298)
+void orc_closest_hit(const orc_scene* s, const ptb_ray* rays, size_t n, ptb_hit* out, int threads, uint64_t* counts2) {
+  unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
+  std::vector<uint64_t> nv(nt ? nt : 1, 0), pt(nt ? nt : 1, 0);
+  parallel_for(n, threads, [&](unsigned tid, size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      Ray ray(Vec3(rays[i].ox, rays[i].oy, rays[i].oz), Vec3(rays[i].dx, rays[i].dy, rays[i].dz), 0.0f);
+      Hit h;
+      const Material* m;
+      size_t idx = s->bvh.check_hit(ray, h, m, &nv[tid], &pt[tid]);
+      fill_hit(out[i], idx != Bvh::MISS, h, idx != Bvh::MISS ? s->bvh.primitives[idx].orig_id : PTB_MISS);
+    }
+  });
+  if (counts2) {
+    counts2[0] = counts2[1] = 0;
+    for (size_t i = 0; i < nv.size(); ++i) { counts2[0] += nv[i]; counts2[1] += pt[i]; }
+  }
+}
+
+// every primitive, no acceleration structure: the f32 ground truth of "min t over all primitives"
+void orc_closest_hit_brute(const orc_scene* s, const ptb_ray* rays, size_t n, ptb_hit* out, int threads) {
+  parallel_for(n, threads, [&](unsigned, size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      Ray ray(Vec3(rays[i].ox, rays[i].oy, rays[i].oz), Vec3(rays[i].dx, rays[i].dy, rays[i].dz), 0.0f);
+      Hit best, h;
+      uint32_t bp = PTB_MISS;
+      for (const Prim& p : s->prims_original) {
+        if (p.get_int(ray, h) && h.t > 0.0f && (bp == PTB_MISS || h.t < best.t)) { best = h; bp = p.orig_id; }
+      }
+      fill_hit(out[i], bp != PTB_MISS, best, bp);
+    }
+  });
+}
+
+// full hit record of one ray against the reference tree (point, normal, error, out) for unit tests
+int orc_hit_record(const orc_scene* s, const ptb_ray* r, float out[12]) {
+  Ray ray(Vec3(r->ox, r->oy, r->oz), Vec3(r->dx, r->dy, r->dz), 0.0f);
+  Hit h;
+  const Material* m;
+  size_t idx = s->bvh.check_hit(ray, h, m);
+  out[0] = h.t;
+  out[1] = h.point.x; out[2] = h.point.y; out[3] = h.point.z;
+  out[4] = h.normal.x; out[5] = h.normal.y; out[6] = h.normal.z;
+  out[7] = h.error.x; out[8] = h.error.y; out[9] = h.error.z;
+  out[10] = h.out ? 1.0f : 0.0f;
+  out[11] = idx == Bvh::MISS ? -1.0f : (float)s->bvh.primitives[idx].orig_id;
+  return idx != Bvh::MISS;
+}
+
+// RandomSampler::sample_image restated as a SUM into accum (W*H*3). counts: reference, camera, bounce,
+// shadow_light, shadow_sky, nodes_visited, prims_tested. Returns wall seconds.
+double orc_render(const orc_scene* s, const ptb_render_opts* o, float* accum, int threads, uint64_t counts[7]) {
+  RenderOpts ro;
+  ro.width = o->width;
+  ro.height = o->height;
+  ro.spp = o->samples_per_pixel;
+  ro.sample_offset = o->sample_offset;
+  ro.method = o->method;
+  ro.seed = o->seed;
+  ro.integ.max_depth = o->max_depth ? o->max_depth : MAX_DEPTH;
+  ro.integ.rr_threshold = o->rr_threshold == PTB_RR_DEFAULT ? RUSSIAN_ROULETTE_THRESHOLD : o->rr_threshold;
+  ro.threads = threads > 0 ? (unsigned)threads : 0;
+  auto t0 = std::chrono::steady_clock::now();
+  RayCounts rc = sample_image(s->camera, s->bvh, ro, accum);
+  double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (counts) {
+    counts[0] = rc.reference; counts[1] = rc.camera; counts[2] = rc.bounce; counts[3] = rc.shadow_light;
+    counts[4] = rc.shadow_sky; counts[5] = rc.nodes_visited; counts[6] = rc.prims_tested;
+  }
+  return dt;
+}
+
+// Mean radiance of ONE fixed ray over n samples (the shape of the reference's disabled furnace / MIS tests,
+// implementations/tests/sampling.rs:181-297). Sample k uses the RNG path (pixel = k mod 2^20, sample = k >> 20).
+void orc_radiance(const orc_scene* s, const ptb_ray* r, uint32_t method, uint64_t n, uint64_t seed, int threads,
+                  double out[3]) {
+  unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
+  if (nt == 0) nt = 1;
+  std::vector<double> acc(3 * (size_t)nt, 0.0);
+  IntegratorOpts io;
+  parallel_for((size_t)n, threads, [&](unsigned tid, size_t b, size_t e) {
+    g_rng.seed(seed);
+    RayCounts rc;
+    for (size_t k = b; k < e; ++k) {
+      g_rng.path((uint32_t)(k & 0xFFFFFu), (uint32_t)(k >> 20));
+      Ray ray(Vec3(r->ox, r->oy, r->oz), Vec3(r->dx, r->dy, r->dz), 0.0f);
+      Vec3 c = method == PTB_METHOD_NAIVE ? naive_get_colour(ray, s->bvh, io, rc) : mis_get_colour(ray, s->bvh, io, rc);
+      acc[3 * tid + 0] += c.x; acc[3 * tid + 1] += c.y; acc[3 * tid + 2] += c.z;
+    }
+  });
+  out[0] = out[1] = out[2] = 0.0;
+  for (unsigned t = 0; t < nt; ++t) { out[0] += acc[3 * t]; out[1] += acc[3 * t + 1]; out[2] += acc[3 * t + 2]; }
+  out[0] /= (double)n; out[1] /= (double)n; out[2] /= (double)n;
+}
+
+// ------------------------------------------------------------------ LBVH
+int orc_lbvh_build(orc_scene* s) {
+  s->lbvh.build(s->prims_original);
+  s->lbvh_built = true;
+  return 0;
+}
+size_t orc_lbvh_num_nodes(const orc_scene* s) { return s->lbvh.nodes.size(); }
+void orc_lbvh_export(const orc_scene* s, uint32_t* morton, uint32_t* prim_sorted, ptb_bvh_node* nodes) {
+  const Lbvh& l = s->lbvh;
+  if (morton) for (size_t i = 0; i < l.morton.size(); ++i) morton[i] = l.morton[i];
+  if (prim_sorted) for (size_t i = 0; i < l.prim_sorted.size(); ++i) prim_sorted[i] = l.prim_sorted[i];
+  if (nodes) for (size_t i = 0; i < l.nodes.size(); ++i) nodes[i] = l.nodes[i];
+}
+// counts2: nodes fetched, primitives tested (summed over the batch)
+void orc_lbvh_closest_hit(const orc_scene* s, const ptb_ray* rays, size_t n, ptb_hit* out, int threads, uint64_t* counts2) {
+  unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
+  std::vector<uint64_t> nv(nt ? nt : 1, 0), pt(nt ? nt : 1, 0);
+  parallel_for(n, threads, [&](unsigned tid, size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      Ray ray(Vec3(rays[i].ox, rays[i].oy, rays[i].oz), Vec3(rays[i].dx, rays[i].dy, rays[i].dz), 0.0f);
+      Hit h;
+      uint32_t prim;
+      bool have = s->lbvh.closest_hit(ray, h, prim, &nv[tid], &pt[tid]);
+      fill_hit(out[i], have, h, prim);
+    }
+  });
+  if (counts2) {
+    counts2[0] = counts2[1] = 0;
+    for (size_t i = 0; i < nv.size(); ++i) { counts2[0] += nv[i]; counts2[1] += pt[i]; }
+  }
+}
+
+// ------------------------------------------------------------- KAT hooks
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { Philox::block(ctr, key, out); }
+void orc_sort_by_indices_u32(uint32_t* values, const uint64_t* indices, size_t n) {
+  std::vector<uint32_t> v(values, values + n);
+  std::vector<size_t> idx(indices, indices + n);
+  sort_by_indices(v, idx);
+  for (size_t i = 0; i < n; ++i) values[i] = v[i];
+}
+float orc_next_float(float f) { return next_float(f); }
+float orc_previous_float(float f) { return previous_float(f); }
+float orc_gamma(uint32_t n) { return gamma(n); }
+void orc_offset_ray(const float o[3], const float nrm[3], const float err[3], int is_brdf, float out[3]) {
+  Vec3 r = offset_ray(Vec3(o[0], o[1], o[2]), Vec3(nrm[0], nrm[1], nrm[2]), Vec3(err[0], err[1], err[2]), is_brdf != 0);
+  out[0] = r.x; out[1] = r.y; out[2] = r.z;
+}
+// Ray::new: out = direction(3), d_inverse(3), shear(3)
+void orc_ray_new(const float o[3], const float d[3], float out[9]) {
+  Ray r(Vec3(o[0], o[1], o[2]), Vec3(d[0], d[1], d[2]), 0.0f);
+  out[0] = r.direction.x; out[1] = r.direction.y; out[2] = r.direction.z;
+  out[3] = r.d_inverse.x; out[4] = r.d_inverse.y; out[5] = r.d_inverse.z;
+  out[6] = r.shear.x; out[7] = r.shear.y; out[8] = r.shear.z;
+}
+// Coordinate: out1 = from(to(v)), out2 = to(from(v))   (utility/coord.rs:39-49)
+void orc_coord_roundtrip(const float z[3], const float v[3], float out1[3], float out2[3]) {
+  Coordinate to = Coordinate::new_from_z(Vec3(z[0], z[1], z[2]));
+  Coordinate from = to.create_inverse();
+  Vec3 vv(v[0], v[1], v[2]);
+  Vec3 a = from.to_coord(to.to_coord(vv)), b = to.to_coord(from.to_coord(vv));
+  out1[0] = a.x; out1[1] = a.y; out1[2] = a.z;
+  out2[0] = b.x; out2[1] = b.y; out2[2] = b.z;
+}
+void orc_camera_make(const float origin[3], const float lookat[3], const float vup[3], float fov, float aspect,
+                     float aperture, float focus, ptb_camera* out) {
+  Camera c = make_camera(Vec3(origin[0], origin[1], origin[2]), Vec3(lookat[0], lookat[1], lookat[2]),
+                         Vec3(vup[0], vup[1], vup[2]), fov, aspect, aperture, focus);
+  out->origin = {c.origin.x, c.origin.y, c.origin.z};
+  out->lower_left = {c.lower_left.x, c.lower_left.y, c.lower_left.z};
+  out->horizontal = {c.horizontal.x, c.horizontal.y, c.horizontal.z};
+  out->vertical = {c.vertical.x, c.vertical.y, c.vertical.z};
+}
+// camera ray for pixel coordinates (u, v): out = origin(3), normalised direction(3)
+void orc_camera_ray(const orc_scene* s, float u, float v, float out[6]) {
+  Ray r = s->camera.get_ray(u, v);
+  out[0] = r.origin.x; out[1] = r.origin.y; out[2] = r.origin.z;
+  out[3] = r.direction.x; out[4] = r.direction.y; out[5] = r.direction.z;
+}
+// lambertian::sample / pdf (statistics/bxdfs/lambertian.rs:5-22); sample k uses RNG path (k, 0), test stream
+void orc_lambertian_sample(const float normal[3], uint64_t seed, size_t n, int local, float* dirs) {
+  g_rng.seed(seed);
+  Vec3 nn(normal[0], normal[1], normal[2]);
+  for (size_t k = 0; k < n; ++k) {
+    g_rng.path((uint32_t)k, (uint32_t)(k >> 32));
+    g_rng.select(0, RNG_TEST);
+    Vec3 d = local ? lambertian::sample_local() : lambertian::sample(nn);
+    dirs[3 * k] = d.x; dirs[3 * k + 1] = d.y; dirs[3 * k + 2] = d.z;
+  }
+}
+void orc_lambertian_pdf(const float normal[3], const float* dirs, size_t n, int local, float* pdf) {
+  Vec3 nn(normal[0], normal[1], normal[2]);
+  for (size_t k = 0; k < n; ++k) {
+    Vec3 d(dirs[3 * k], dirs[3 * k + 1], dirs[3 * k + 2]);
+    pdf[k] = local ? lambertian::pdf_local(d) : lambertian::pdf(d, nn);
+  }
+}
+void orc_random_unit_vectors(uint64_t seed, size_t n, float* dirs) {
+  g_rng.seed(seed);
+  for (size_t k = 0; k < n; ++k) {
+    g_rng.path((uint32_t)k, (uint32_t)(k >> 32));
+    g_rng.select(0, RNG_TEST);
+    Vec3 d = random_unit_vector();
+    dirs[3 * k] = d.x; dirs[3 * k + 1] = d.y; dirs[3 * k + 2] = d.z;
+  }
+}
+// Distribution1D (statistics/distributions.rs:11-72)
+void orc_dist1d(const float* values, size_t n, float* pdf_out, float* cdf_out, uint64_t seed, size_t nsamples, uint64_t* counts) {
+  Distribution1D d(values, n);
+  if (pdf_out) for (size_t i = 0; i < n; ++i) pdf_out[i] = d.pdf[i];
+  if (cdf_out) for (size_t i = 0; i <= n; ++i) cdf_out[i] = d.cdf[i];
+  if (counts) {
+    g_rng.seed(seed);
+    for (size_t k = 0; k < nsamples; ++k) {
+      g_rng.path((uint32_t)k, (uint32_t)(k >> 32));
+      g_rng.select(0, RNG_TEST);
+      counts[d.sample()] += 1;
+    }
+  }
+}
+// Distribution2D (statistics/distributions.rs:75-113): counts is dim_y x dim_x row-major, pdf_out likewise
+void orc_dist2d(const float* values, size_t n, size_t width, float* pdf_out, uint64_t seed, size_t nsamples, uint64_t* counts) {
+  std::vector<Float> v(values, values + n);
+  Distribution2D d(v, width);
+  if (pdf_out)
+    for (size_t y = 0; y < d.dim_y; ++y)
+      for (size_t x = 0; x < d.dim_x; ++x)
+        pdf_out[y * width + x] = d.pdf(((Float)x + 0.5f) / (Float)d.dim_x, ((Float)y + 0.5f) / (Float)d.dim_y);
+  if (counts) {
+    g_rng.seed(seed);
+    for (size_t k = 0; k < nsamples; ++k) {
+      g_rng.path((uint32_t)k, (uint32_t)(k >> 32));
+      g_rng.select(0, RNG_TEST);
+      size_t u, vv;
+      d.sample(u, vv);
+      counts[vv * width + u] += 1;
+    }
+  }
+}
+// Sky::sample / Sky::pdf (sky.rs:43-78)
+void orc_sky_sample(const orc_scene* s, uint64_t seed, size_t n, float* dirs) {
+  g_rng.seed(seed);
+  for (size_t k = 0; k < n; ++k) {
+    g_rng.path((uint32_t)k, (uint32_t)(k >> 32));
+    g_rng.select(0, RNG_TEST);
+    Vec3 d = s->bvh.sky.sample();
+    dirs[3 * k] = d.x; dirs[3 * k + 1] = d.y; dirs[3 * k + 2] = d.z;
+  }
+}
+void orc_sky_pdf(const orc_scene* s, const float* dirs, size_t n, float* pdf) {
+  for (size_t k = 0; k < n; ++k) pdf[k] = s->bvh.sky.pdf(Vec3(dirs[3 * k], dirs[3 * k + 1], dirs[3 * k + 2]));
+}
+void orc_texture_colour(const orc_scene* s, uint32_t tex, const float dir[3], const float point[3], float out[3]) {
+  Vec3 c = s->textures[tex].colour_value(Vec3(dir[0], dir[1], dir[2]), Vec3(point[0], point[1], point[2]));
+  out[0] = c.x; out[1] = c.y; out[2] = c.z;
+}
+// the sky table as the device must hold it: y cdf (ry+1), x cdfs (ry*(rx+1)), y pdf (ry), x pdfs (ry*rx)
+void orc_sky_table(const orc_scene* s, float* ycdf, float* xcdf, float* ypdf, float* xpdf) {
+  const Sky& sky = s->bvh.sky;
+  if (!sky.has_distribution) return;
+  const Distribution2D& d = sky.distribution;
+  for (size_t i = 0; i <= d.dim_y; ++i) ycdf[i] = d.y_distribution.cdf[i];
+  for (size_t i = 0; i < d.dim_y; ++i) ypdf[i] = d.y_distribution.pdf[i];
+  for (size_t y = 0; y < d.dim_y; ++y) {
+    for (size_t x = 0; x <= d.dim_x; ++x) xcdf[y * (d.dim_x + 1) + x] = d.x_distributions[y].cdf[x];
+    for (size_t x = 0; x < d.dim_x; ++x) xpdf[y * d.dim_x + x] = d.x_distributions[y].pdf[x];
+  }
+}
+unsigned orc_hardware_threads(void) { return std::thread::hardware_concurrency(); }
+
+}  // extern "C"

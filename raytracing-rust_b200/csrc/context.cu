@@ -1,0 +1,332 @@
+// ptb200 — C ABI (include/ptb200.h): context lifecycle, scene upload, closest-hit batches, render, accumulator.
+// No CPU fallback: every compute entry point needs a CUDA device and fails with PTB_ERR_CUDA otherwise.
+#include <cstdarg>
+#include <cstring>
+#include <new>
+
+#include "ptb_internal.h"
+
+namespace ptb {
+
+static thread_local std::string g_create_error;
+
+int32_t set_error(Ctx* c, int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->last_error = buf;
+  else g_create_error = buf;
+  return code;
+}
+int32_t check_cuda(Ctx* c, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return PTB_OK;
+  const int32_t code = e == cudaErrorMemoryAllocation ? PTB_ERR_OOM : PTB_ERR_CUDA;
+  return set_error(c, code, "CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+__global__ void k_scale_copy(const float* __restrict__ in, float* __restrict__ out, size_t n, float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * scale;
+}
+
+}  // namespace ptb
+
+using namespace ptb;
+
+#define CTX_OR_FAIL(ctx)                 \
+  if (!(ctx)) return PTB_ERR_INVALID;    \
+  Ctx* c = &(ctx)->c;                    \
+  if (cudaSetDevice(c->device) != cudaSuccess) return set_error(c, PTB_ERR_CUDA, "cudaSetDevice(%d) failed", c->device)
+
+extern "C" {
+
+uint32_t ptb_abi_version(void) { return PTB_ABI_VERSION; }
+
+int32_t ptb_device_count(int32_t* count) {
+  if (!count) return PTB_ERR_INVALID;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    *count = 0;
+    return set_error(nullptr, PTB_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  }
+  *count = n;
+  return PTB_OK;
+}
+
+int32_t ptb_create(int32_t device, ptb_ctx** out) {
+  if (!out) return PTB_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_error(nullptr, PTB_ERR_CUDA, "no CUDA device available (%s); ptb200 has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return set_error(nullptr, PTB_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+  ptb_ctx* ctx = new (std::nothrow) ptb_ctx();
+  if (!ctx) return PTB_ERR_OOM;
+  Ctx* c = &ctx->c;
+  c->device = device;
+  auto fail = [&](cudaError_t err, const char* what) {
+    int32_t rc = set_error(nullptr, PTB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+    delete ctx;
+    return rc;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(e, "cudaGetDeviceProperties");
+  if (prop.major < 10) {
+    int32_t rc = set_error(nullptr, PTB_ERR_CUDA, "device %d is sm_%d%d; ptb200 is built for sm_100a only", device, prop.major,
+                           prop.minor);
+    delete ctx;
+    return rc;
+  }
+  c->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
+  c->own_stream = true;
+  if ((e = cudaEventCreate(&c->ev_a)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&c->ev_b)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&c->ev_iter)) != cudaSuccess) return fail(e, "cudaEventCreate");
+  *out = ctx;
+  return PTB_OK;
+}
+
+int32_t ptb_destroy(ptb_ctx* ctx) {
+  if (!ctx) return PTB_OK;
+  Ctx* c = &ctx->c;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->ev_a) cudaEventDestroy(c->ev_a);
+  if (c->ev_b) cudaEventDestroy(c->ev_b);
+  if (c->ev_iter) cudaEventDestroy(c->ev_iter);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete ctx;  // DevBuf destructors release device memory
+  return PTB_OK;
+}
+
+const char* ptb_last_error(const ptb_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : g_create_error.c_str(); }
+
+int32_t ptb_set_stream(ptb_ctx* ctx, void* cuda_stream) {
+  CTX_OR_FAIL(ctx);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  c->own_stream = false;
+  return PTB_OK;
+}
+
+int32_t ptb_synchronize(ptb_ctx* ctx) {
+  CTX_OR_FAIL(ctx);
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return PTB_OK;
+}
+
+// ---------------------------------------------------------------- scene
+int32_t ptb_scene_set_spheres(ptb_ctx* ctx, const ptb_sphere* p, size_t n) {
+  CTX_OR_FAIL(ctx);
+  if (n && !p) return set_error(c, PTB_ERR_INVALID, "null spheres");
+  try { c->spheres.assign(p, p + n); } catch (const std::bad_alloc&) { return set_error(c, PTB_ERR_OOM, "host OOM"); }
+  c->committed = false;
+  return PTB_OK;
+}
+int32_t ptb_scene_set_triangles(ptb_ctx* ctx, const ptb_triangle* p, size_t n) {
+  CTX_OR_FAIL(ctx);
+  if (n && !p) return set_error(c, PTB_ERR_INVALID, "null triangles");
+  try { c->triangles.assign(p, p + n); } catch (const std::bad_alloc&) { return set_error(c, PTB_ERR_OOM, "host OOM"); }
+  c->committed = false;
+  return PTB_OK;
+}
+int32_t ptb_scene_set_materials(ptb_ctx* ctx, const ptb_material* p, size_t n) {
+  CTX_OR_FAIL(ctx);
+  if (n && !p) return set_error(c, PTB_ERR_INVALID, "null materials");
+  for (size_t i = 0; i < n; ++i)
+    if (p[i].kind > PTB_MAT_REFRACT) return set_error(c, PTB_ERR_INVALID, "material %zu: unknown kind %u", i, p[i].kind);
+  c->materials.assign(p, p + n);
+  c->committed = false;
+  return PTB_OK;
+}
+int32_t ptb_scene_set_textures(ptb_ctx* ctx, const ptb_texture* p, size_t n) {
+  CTX_OR_FAIL(ctx);
+  if (n && !p) return set_error(c, PTB_ERR_INVALID, "null textures");
+  for (size_t i = 0; i < n; ++i)
+    if (p[i].kind > PTB_TEX_PERLIN) return set_error(c, PTB_ERR_INVALID, "texture %zu: unknown kind %u", i, p[i].kind);
+  c->textures.assign(p, p + n);
+  c->committed = false;
+  return PTB_OK;
+}
+int32_t ptb_scene_set_camera(ptb_ctx* ctx, const ptb_camera* cam) {
+  CTX_OR_FAIL(ctx);
+  if (!cam) return set_error(c, PTB_ERR_INVALID, "null camera");
+  c->camera = *cam;
+  c->have_camera = true;
+  c->committed = false;
+  return PTB_OK;
+}
+int32_t ptb_scene_set_sky(ptb_ctx* ctx, const ptb_sky* sky) {
+  CTX_OR_FAIL(ctx);
+  if (!sky) return set_error(c, PTB_ERR_INVALID, "null sky");
+  c->sky = *sky;
+  c->have_sky = true;
+  c->committed = false;
+  return PTB_OK;
+}
+
+int32_t ptb_scene_upload(ptb_ctx* ctx, const ptb_host_scene* s) {
+  if (!ctx || !s) return PTB_ERR_INVALID;
+  const ptb_sphere* sp; const ptb_triangle* tr; const ptb_material* ma; const ptb_texture* te;
+  size_t ns = ptb_host_scene_spheres(s, &sp), nt = ptb_host_scene_triangles(s, &tr);
+  size_t nm = ptb_host_scene_materials(s, &ma), nx = ptb_host_scene_textures(s, &te);
+  ptb_camera cam; ptb_sky sky;
+  ptb_host_scene_camera(s, &cam);
+  ptb_host_scene_sky(s, &sky);
+  int32_t rc;
+  if ((rc = ptb_scene_set_textures(ctx, te, nx)) != PTB_OK) return rc;
+  if ((rc = ptb_scene_set_materials(ctx, ma, nm)) != PTB_OK) return rc;
+  if ((rc = ptb_scene_set_spheres(ctx, sp, ns)) != PTB_OK) return rc;
+  if ((rc = ptb_scene_set_triangles(ctx, tr, nt)) != PTB_OK) return rc;
+  if ((rc = ptb_scene_set_camera(ctx, &cam)) != PTB_OK) return rc;
+  return ptb_scene_set_sky(ctx, &sky);
+}
+
+int32_t ptb_scene_commit(ptb_ctx* ctx, uint32_t build_flags) {
+  CTX_OR_FAIL(ctx);
+  return build_scene(c, build_flags);
+}
+
+int32_t ptb_bvh_info(ptb_ctx* ctx, uint64_t* n_prims, uint64_t* n_nodes) {
+  CTX_OR_FAIL(ctx);
+  if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
+  if (n_prims) *n_prims = c->n_prims;
+  if (n_nodes) *n_nodes = c->n_nodes;
+  return PTB_OK;
+}
+
+int32_t ptb_bvh_export(ptb_ctx* ctx, uint32_t* morton_sorted, uint32_t* prim_sorted, ptb_bvh_node* nodes) {
+  CTX_OR_FAIL(ctx);
+  if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
+  if (c->n_prims == 0) return PTB_OK;
+  if (morton_sorted)
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(morton_sorted, c->d_morton.p, c->n_prims * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prim_sorted)
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(prim_sorted, c->d_slot_prim.p, c->n_prims * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (nodes)
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(nodes, c->d_nodes.p, c->n_nodes * sizeof(ptb_bvh_node), cudaMemcpyDeviceToHost, c->stream));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  if (nodes)  // the sphere flag of leaf references is device-internal
+    for (uint64_t i = 0; i < c->n_nodes; ++i) {
+      if (nodes[i].left & PTB_LEAF_BIT) nodes[i].left &= ~kSphereBit;
+      if (nodes[i].right & PTB_LEAF_BIT) nodes[i].right &= ~kSphereBit;
+    }
+  return PTB_OK;
+}
+
+// ---------------------------------------------------------------- closest hit
+int32_t ptb_closest_hit_device(ptb_ctx* ctx, const void* d_rays, size_t n, void* d_hits) {
+  CTX_OR_FAIL(ctx);
+  if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
+  if (n && (!d_rays || !d_hits)) return set_error(c, PTB_ERR_INVALID, "null device buffer");
+  return launch_closest_hit(c, d_rays, n, d_hits);
+}
+
+int32_t ptb_closest_hit(ptb_ctx* ctx, const ptb_ray* rays, size_t n, ptb_hit* hits) {
+  CTX_OR_FAIL(ctx);
+  if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
+  if (n == 0) return PTB_OK;
+  if (!rays || !hits) return set_error(c, PTB_ERR_INVALID, "null host buffer");
+  const size_t chunk = (size_t)1 << 26;  // 64 Mi rays per batch: 2 GiB of rays + 1 GiB of hits resident
+  const size_t cap = n < chunk ? n : chunk;
+  PTB_CUDA_TRY(c, c->d_rays.reserve(cap * sizeof(ptb_ray)));
+  PTB_CUDA_TRY(c, c->d_hits.reserve(cap * sizeof(ptb_hit)));
+  for (size_t off = 0; off < n; off += chunk) {
+    const size_t m = n - off < chunk ? n - off : chunk;
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_rays.p, rays + off, m * sizeof(ptb_ray), cudaMemcpyHostToDevice, c->stream));
+    int32_t rc = launch_closest_hit(c, c->d_rays.p, m, c->d_hits.p);
+    if (rc != PTB_OK) return rc;
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(hits + off, c->d_hits.p, m * sizeof(ptb_hit), cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  }
+  return PTB_OK;
+}
+
+// ---------------------------------------------------------------- render
+static int32_t ensure_accum(Ctx* c, uint32_t w, uint32_t h) {
+  if (c->accum_w == w && c->accum_h == h && c->d_accum.p) return PTB_OK;
+  const size_t bytes = (size_t)w * h * 3 * sizeof(float);
+  PTB_CUDA_TRY(c, c->d_accum.alloc(bytes));
+  PTB_CUDA_TRY(c, cudaMemsetAsync(c->d_accum.p, 0, bytes, c->stream));
+  c->accum_w = w;
+  c->accum_h = h;
+  c->accum_samples = 0;
+  return PTB_OK;
+}
+
+int32_t ptb_render(ptb_ctx* ctx, const ptb_render_opts* opts, ptb_progress_fn progress, void* user) {
+  CTX_OR_FAIL(ctx);
+  if (!opts) return set_error(c, PTB_ERR_INVALID, "null render opts");
+  if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
+  if (opts->width < 2 || opts->height < 2) return set_error(c, PTB_ERR_INVALID, "width and height must be >= 2");
+  if ((uint64_t)opts->width * opts->height > 0x7FFFFFFFull) return set_error(c, PTB_ERR_INVALID, "image too large");
+  if (opts->method != PTB_METHOD_NAIVE && opts->method != PTB_METHOD_MIS) return set_error(c, PTB_ERR_INVALID, "unknown method");
+  int32_t rc = ensure_accum(c, opts->width, opts->height);
+  if (rc != PTB_OK) return rc;
+  return render_wavefront(c, *opts, progress, user);
+}
+
+int32_t ptb_accum_clear(ptb_ctx* ctx) {
+  CTX_OR_FAIL(ctx);
+  if (c->d_accum.p) PTB_CUDA_TRY(c, cudaMemsetAsync(c->d_accum.p, 0, (size_t)c->accum_w * c->accum_h * 12, c->stream));
+  c->accum_samples = 0;
+  return PTB_OK;
+}
+
+int32_t ptb_accum_read(ptb_ctx* ctx, float* rgb, size_t n_floats, int32_t normalise) {
+  CTX_OR_FAIL(ctx);
+  if (!c->d_accum.p) return set_error(c, PTB_ERR_INVALID, "nothing rendered yet");
+  const size_t n = (size_t)c->accum_w * c->accum_h * 3;
+  if (!rgb || n_floats != n) return set_error(c, PTB_ERR_INVALID, "accum_read expects %zu floats", n);
+  if (normalise && c->accum_samples > 0) {
+    // running mean of src/main.rs:179-185 == sum / samples; scaled on the device into the staging buffer
+    PTB_CUDA_TRY(c, c->d_hits.reserve(n * sizeof(float)));
+    k_scale_copy<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_accum.as<float>(), c->d_hits.as<float>(), n,
+                                                                     1.0f / (float)c->accum_samples);
+    c->stats.kernel_launches += 1;
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(rgb, c->d_hits.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(rgb, c->d_accum.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  return PTB_OK;
+}
+
+int32_t ptb_accum_device_ptr(ptb_ctx* ctx, void** d_ptr, size_t* n_floats) {
+  CTX_OR_FAIL(ctx);
+  if (!c->d_accum.p) return set_error(c, PTB_ERR_INVALID, "nothing rendered yet");
+  if (d_ptr) *d_ptr = c->d_accum.p;
+  if (n_floats) *n_floats = (size_t)c->accum_w * c->accum_h * 3;
+  return PTB_OK;
+}
+
+int32_t ptb_accum_set_samples(ptb_ctx* ctx, uint64_t total_samples) {
+  CTX_OR_FAIL(ctx);
+  c->accum_samples = total_samples;
+  return PTB_OK;
+}
+
+int32_t ptb_stats_get(ptb_ctx* ctx, ptb_stats* out) {
+  CTX_OR_FAIL(ctx);
+  if (!out) return PTB_ERR_INVALID;
+  *out = c->stats;
+  return PTB_OK;
+}
+int32_t ptb_stats_reset(ptb_ctx* ctx) {
+  CTX_OR_FAIL(ctx);
+  const double b = c->stats.build_ms;
+  c->stats = ptb_stats{};
+  c->stats.build_ms = b;
+  return PTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,613 @@
+// ptb200 — device LBVH build (sm_100a). Replaces Bvh::new / build_bvh
+// (implementations/src/acceleration/mod.rs:58-160; split.rs) with a fully parallel construction:
+//   K2  primitive AABB + centroid + scene centroid bounds   (PrimitiveInfo::new, acceleration/mod.rs:29-41;
+//                                                            get_aabb sphere.rs:175-181, triangle.rs:285-307)
+//   K3  30-bit Morton codes
+//   K4  stable LSD radix sort, 4 passes x 8 bits, (key = Morton, value = primitive id)
+//   K5  Karras-2012 hierarchy, duplicate keys tie-broken by index
+//   K6  bottom-up AABB refit with atomic arrival flags (AABB::merge, aabb.rs:59-67); every 64-byte node stores
+//       both children's boxes
+//   then primitives are gathered into Morton (slot) order as 3 x float4 records.
+// The result is bit-exact against oracle/lbvh_ref.hpp (tests/test_gpu_lbvh.py): min/max and the Morton arithmetic are
+// order-independent and IEEE-exact, the sort is stable, the hierarchy is a pure function of the sorted keys.
+#include <cstdarg>
+
+#include "ptb_internal.h"
+
+namespace ptb {
+
+// ------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint32_t float_flip(float f) {  // order-preserving float -> uint
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_unflip(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+__device__ __forceinline__ uint32_t quantise10(float c, float cmin, float ext) {
+  float n = ext > 0.0f ? (c - cmin) / ext : 0.0f;
+  float s = fminf(fmaxf(n * 1024.0f, 0.0f), 1023.0f);
+  return (uint32_t)s;
+}
+
+// ------------------------------------------------------------------------------------------ K2
+// bounds[0..2] = flipped min of centroids, bounds[3..5] = flipped max
+__global__ void k_prim_bounds(const ptb_sphere* __restrict__ spheres, uint32_t n_spheres,
+                              const ptb_triangle* __restrict__ tris, uint32_t n_tris, float4* __restrict__ bmin,
+                              float4* __restrict__ bmax, uint32_t* __restrict__ bounds) {
+  const uint32_t n = n_spheres + n_tris;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float inf = __int_as_float(0x7f800000);
+  v3 cmin = mk(inf, inf, inf), cmax = mk(-inf, -inf, -inf);
+  if (i < n) {
+    v3 mn, mx;
+    if (i < n_spheres) {
+      const ptb_sphere s = spheres[i];
+      const v3 c = mk(s.center.x, s.center.y, s.center.z);
+      mn = c - s.radius * mk(1.0f, 1.0f, 1.0f);
+      mx = c + s.radius * mk(1.0f, 1.0f, 1.0f);
+    } else {
+      const ptb_triangle* t = tris + (i - n_spheres);
+      const v3 p0 = mk(t->p[0].x, t->p[0].y, t->p[0].z), p1 = mk(t->p[1].x, t->p[1].y, t->p[1].z),
+               p2 = mk(t->p[2].x, t->p[2].y, t->p[2].z);
+      mn = vmin(p0, vmin(p1, p2));
+      mx = vmax(p0, vmax(p1, p2));
+    }
+    bmin[i] = make_float4(mn.x, mn.y, mn.z, 0.0f);
+    bmax[i] = make_float4(mx.x, mx.y, mx.z, 0.0f);
+    const v3 c = 0.5f * (mn + mx);
+    cmin = c;
+    cmax = c;
+  }
+  // warp reduce then one atomic per warp per component
+  for (int off = 16; off > 0; off >>= 1) {
+    cmin.x = fminf(cmin.x, __shfl_xor_sync(0xffffffffu, cmin.x, off));
+    cmin.y = fminf(cmin.y, __shfl_xor_sync(0xffffffffu, cmin.y, off));
+    cmin.z = fminf(cmin.z, __shfl_xor_sync(0xffffffffu, cmin.z, off));
+    cmax.x = fmaxf(cmax.x, __shfl_xor_sync(0xffffffffu, cmax.x, off));
+    cmax.y = fmaxf(cmax.y, __shfl_xor_sync(0xffffffffu, cmax.y, off));
+    cmax.z = fmaxf(cmax.z, __shfl_xor_sync(0xffffffffu, cmax.z, off));
+  }
+  if ((threadIdx.x & 31) == 0 && cmin.x <= cmax.x) {
+    atomicMin(bounds + 0, float_flip(cmin.x));
+    atomicMin(bounds + 1, float_flip(cmin.y));
+    atomicMin(bounds + 2, float_flip(cmin.z));
+    atomicMax(bounds + 3, float_flip(cmax.x));
+    atomicMax(bounds + 4, float_flip(cmax.y));
+    atomicMax(bounds + 5, float_flip(cmax.z));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K3
+__global__ void k_morton(const float4* __restrict__ bmin, const float4* __restrict__ bmax, uint32_t n,
+                         const uint32_t* __restrict__ bounds, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const v3 cmin = mk(float_unflip(bounds[0]), float_unflip(bounds[1]), float_unflip(bounds[2]));
+  const v3 cmax = mk(float_unflip(bounds[3]), float_unflip(bounds[4]), float_unflip(bounds[5]));
+  const v3 ext = cmax - cmin;
+  const v3 c = 0.5f * (from4(bmin[i]) + from4(bmax[i]));
+  const uint32_t qx = quantise10(c.x, cmin.x, ext.x), qy = quantise10(c.y, cmin.y, ext.y),
+                 qz = quantise10(c.z, cmin.z, ext.z);
+  keys[i] = (expand_bits10(qx) << 2) | (expand_bits10(qy) << 1) | expand_bits10(qz);
+  vals[i] = i;
+}
+
+// ------------------------------------------------------------------------------------------ K4: radix sort
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;                       // keys per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;     // 4096 keys per block
+constexpr int RS_WARP_TILE = 32 * RS_ITEMS;        // contiguous keys per warp (keeps the sort stable)
+
+// Per-warp digit counts of this block's tile. Warp w owns tile elements [w*512, (w+1)*512), walked 32 at a time in
+// order; lanes holding the same digit are grouped with match.any so only the group leader touches shared memory.
+template <bool SCATTER>
+__global__ void __launch_bounds__(RS_THREADS)
+k_radix_pass(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
+             uint32_t* __restrict__ vals_out, uint32_t n, int shift, uint32_t* __restrict__ hist, uint32_t n_tiles) {
+  __shared__ uint32_t cnt[RS_WARPS][256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tile = blockIdx.x;
+  for (int d = threadIdx.x; d < RS_WARPS * 256; d += RS_THREADS) (&cnt[0][0])[d] = 0;
+  __syncthreads();
+
+  uint32_t key[RS_ITEMS];
+  const uint32_t base = tile * RS_TILE + warp * RS_WARP_TILE + lane;
+#pragma unroll
+  for (int c = 0; c < RS_ITEMS; ++c) {
+    const uint32_t idx = base + c * 32;
+    key[c] = idx < n ? keys_in[idx] : 0xFFFFFFFFu;
+  }
+#pragma unroll
+  for (int c = 0; c < RS_ITEMS; ++c) {
+    const uint32_t idx = base + c * 32;
+    const bool valid = idx < n;
+    const uint32_t digit = (key[c] >> shift) & 255u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : (256u + lane));
+    if (valid && (__ffs(peers) - 1) == lane) cnt[warp][digit] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (!SCATTER) {
+    const int d = threadIdx.x;  // RS_THREADS == 256 digits
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) total += cnt[w][d];
+    hist[(size_t)d * n_tiles + tile] = total;
+    return;
+  }
+  {  // turn counts into running output offsets: global digit offset + counts of the earlier warps of this tile
+    const int d = threadIdx.x;
+    uint32_t run = hist[(size_t)d * n_tiles + tile];
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const uint32_t c = cnt[w][d];
+      cnt[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < RS_ITEMS; ++c) {
+    const uint32_t idx = base + c * 32;
+    const bool valid = idx < n;
+    const uint32_t digit = (key[c] >> shift) & 255u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : (256u + lane));
+    if (valid) {
+      const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+      const uint32_t dst = cnt[warp][digit] + rank;
+      keys_out[dst] = key[c];
+      vals_out[dst] = vals_in[idx];
+    }
+    __syncwarp();
+    if (valid && (__ffs(peers) - 1) == lane) cnt[warp][digit] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+// exclusive scan of hist in digit-major order (256 rows x n_tiles), in place. One block, one warp per row at a time.
+__global__ void __launch_bounds__(256) k_radix_scan(uint32_t* __restrict__ hist, uint32_t n_tiles) {
+  __shared__ uint32_t row_total[256];
+  __shared__ uint32_t row_base[256];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = warp; row < 256; row += 8) {
+    uint32_t carry = 0;
+    uint32_t* r = hist + (size_t)row * n_tiles;
+    for (uint32_t b = 0; b < n_tiles; b += 32) {
+      const uint32_t i = b + lane;
+      const uint32_t v = i < n_tiles ? r[i] : 0;
+      uint32_t inc = v;
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+      }
+      if (i < n_tiles) r[i] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) row_total[row] = carry;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int d = 0; d < 256; ++d) {
+      row_base[d] = run;
+      run += row_total[d];
+    }
+  }
+  __syncthreads();
+  for (int row = warp; row < 256; row += 8) {
+    const uint32_t add = row_base[row];
+    uint32_t* r = hist + (size_t)row * n_tiles;
+    for (uint32_t i = lane; i < n_tiles; i += 32) r[i] += add;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K5
+__device__ __forceinline__ int lbvh_delta(const uint32_t* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const uint32_t a = keys[i], b = keys[j];
+  if (a == b) return 32 + __clz((uint32_t)i ^ (uint32_t)j);
+  return __clz(a ^ b);
+}
+__global__ void k_hierarchy(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ prim_sorted, uint32_t n_prims,
+                            uint32_t n_spheres, BvhNode* __restrict__ nodes, uint32_t* __restrict__ leaf_parent) {
+  const int n = (int)n_prims;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const int d = (lbvh_delta(keys, n, i, i + 1) - lbvh_delta(keys, n, i, i - 1)) < 0 ? -1 : 1;
+  const int dmin = lbvh_delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (lbvh_delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int t = lmax / 2; t >= 1; t /= 2)
+    if (lbvh_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = lbvh_delta(keys, n, i, j);
+  int s = 0;
+  for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+    if (lbvh_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    if (t == 1) break;
+  }
+  const int gam = i + s * d + (d < 0 ? -1 : 0);
+  const int lo = min(i, j), hi = max(i, j);
+  uint32_t left, right;
+  if (lo == gam) {
+    left = PTB_LEAF_BIT | (prim_sorted[gam] < n_spheres ? kSphereBit : 0u) | (uint32_t)gam;
+    leaf_parent[gam] = (uint32_t)i;
+  } else {
+    left = (uint32_t)gam;
+    nodes[gam].n3.z = (uint32_t)i;
+  }
+  if (hi == gam + 1) {
+    right = PTB_LEAF_BIT | (prim_sorted[gam + 1] < n_spheres ? kSphereBit : 0u) | (uint32_t)(gam + 1);
+    leaf_parent[gam + 1] = (uint32_t)i;
+  } else {
+    right = (uint32_t)(gam + 1);
+    nodes[gam + 1].n3.z = (uint32_t)i;
+  }
+  nodes[i].n3.x = left;
+  nodes[i].n3.y = right;
+  nodes[i].n3.w = 0u;
+  if (i == 0) nodes[0].n3.z = kNone;
+}
+
+// ------------------------------------------------------------------------------------------ K6
+__device__ __forceinline__ void child_box(uint32_t ref, const uint32_t* __restrict__ prim_sorted,
+                                          const float4* __restrict__ bmin, const float4* __restrict__ bmax,
+                                          const float4* nbmin, const float4* nbmax, v3& mn, v3& mx) {
+  if (ref & PTB_LEAF_BIT) {
+    const uint32_t p = prim_sorted[ref & kSlotMask];
+    mn = from4(bmin[p]);
+    mx = from4(bmax[p]);
+  } else {
+    mn = from4(__ldcg(nbmin + ref));  // written by another SM: read through L2
+    mx = from4(__ldcg(nbmax + ref));
+  }
+}
+__global__ void k_refit(uint32_t n_prims, const uint32_t* __restrict__ prim_sorted, const uint32_t* __restrict__ leaf_parent,
+                        const float4* __restrict__ bmin, const float4* __restrict__ bmax, BvhNode* nodes, float4* nbmin,
+                        float4* nbmax, uint32_t* flags) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_prims) return;
+  uint32_t cur = leaf_parent[s];
+  while (cur != kNone) {
+    __threadfence();
+    if (atomicAdd(flags + cur, 1u) == 0u) return;  // first arrival: the sibling subtree is not finished yet
+    __threadfence();
+    const uint4 links = nodes[cur].n3;  // written by k_hierarchy (previous launch)
+    v3 lmn, lmx, rmn, rmx;
+    child_box(links.x, prim_sorted, bmin, bmax, nbmin, nbmax, lmn, lmx);
+    child_box(links.y, prim_sorted, bmin, bmax, nbmin, nbmax, rmn, rmx);
+    nodes[cur].n0 = make_float4(lmn.x, lmn.y, lmn.z, lmx.x);
+    nodes[cur].n1 = make_float4(lmx.y, lmx.z, rmn.x, rmn.y);
+    nodes[cur].n2 = make_float4(rmn.z, rmx.x, rmx.y, rmx.z);
+    const v3 mn = vmin(lmn, rmn), mx = vmax(lmx, rmx);
+    __stcg(nbmin + cur, make_float4(mn.x, mn.y, mn.z, 0.0f));
+    __stcg(nbmax + cur, make_float4(mx.x, mx.y, mx.z, 0.0f));
+    cur = links.z;
+  }
+}
+
+// single primitive: one node, both child slots reference leaf 0 (see oracle/lbvh_ref.hpp)
+__global__ void k_single_node(const uint32_t* __restrict__ prim_sorted, uint32_t n_spheres, const float4* __restrict__ bmin,
+                              const float4* __restrict__ bmax, BvhNode* nodes) {
+  const uint32_t p = prim_sorted[0];
+  const v3 mn = from4(bmin[p]), mx = from4(bmax[p]);
+  const uint32_t ref = PTB_LEAF_BIT | (p < n_spheres ? kSphereBit : 0u);
+  nodes[0].n0 = make_float4(mn.x, mn.y, mn.z, mx.x);
+  nodes[0].n1 = make_float4(mx.y, mx.z, mn.x, mn.y);
+  nodes[0].n2 = make_float4(mn.z, mx.x, mx.y, mx.z);
+  nodes[0].n3 = make_uint4(ref, ref, kNone, 0u);
+}
+
+// ------------------------------------------------------------------------------------------ gather into slot order
+__global__ void k_gather(const ptb_sphere* __restrict__ spheres, uint32_t n_spheres, const ptb_triangle* __restrict__ tris,
+                         uint32_t n_prims, const uint32_t* __restrict__ prim_sorted, const DevMaterial* __restrict__ mats,
+                         float4* __restrict__ geom, float4* __restrict__ normals, uint32_t* __restrict__ slot_mat,
+                         uint32_t* __restrict__ prim_slot) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_prims) return;
+  const uint32_t p = prim_sorted[slot];
+  prim_slot[p] = slot;
+  uint32_t mat;
+  float4 g0, g1, g2, m0, m1, m2;
+  if (p < n_spheres) {
+    const ptb_sphere s = spheres[p];
+    g0 = make_float4(s.center.x, s.center.y, s.center.z, s.radius);
+    g1 = g2 = m0 = m1 = m2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    mat = s.material;
+  } else {
+    const ptb_triangle* t = tris + (p - n_spheres);
+    g0 = make_float4(t->p[0].x, t->p[0].y, t->p[0].z, 0.f);
+    g1 = make_float4(t->p[1].x, t->p[1].y, t->p[1].z, 0.f);
+    g2 = make_float4(t->p[2].x, t->p[2].y, t->p[2].z, 0.f);
+    m0 = make_float4(t->n[0].x, t->n[0].y, t->n[0].z, 0.f);
+    m1 = make_float4(t->n[1].x, t->n[1].y, t->n[1].z, 0.f);
+    m2 = make_float4(t->n[2].x, t->n[2].y, t->n[2].z, 0.f);
+    mat = t->material;
+  }
+  geom[3 * (size_t)slot + 0] = g0;
+  geom[3 * (size_t)slot + 1] = g1;
+  geom[3 * (size_t)slot + 2] = g2;
+  normals[3 * (size_t)slot + 0] = m0;
+  normals[3 * (size_t)slot + 1] = m1;
+  normals[3 * (size_t)slot + 2] = m2;
+  slot_mat[slot] = (mats[mat].kind << 24) | (mat & 0x00FFFFFFu);
+}
+__global__ void k_light_slots(const uint32_t* __restrict__ light_prims, uint32_t n_lights, uint32_t n_spheres,
+                              const uint32_t* __restrict__ prim_slot, uint32_t* __restrict__ lights) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lights) return;
+  const uint32_t p = light_prims[i];
+  lights[i] = (p < n_spheres ? kSphereBit : 0u) | prim_slot[p];
+}
+
+// ------------------------------------------------------------------------------------------ host: sky table
+// Sky::new (implementations/src/sky.rs:20-37) = generate_values (textures/mod.rs:32-50) + Distribution2D::new
+// (statistics/distributions.rs:11-44, 82-99), in the reference's f32 operation order.
+static void host_texture_colour(const ptb_texture& t, const float d[3], const float p[3], float out[3]) {
+  switch (t.kind) {
+    case PTB_TEX_CHECKERED: {
+      float sign = sinf(10.0f * p[0]) * sinf(10.0f * p[1]) * sinf(10.0f * p[2]);
+      const ptb_vec3& c = sign > 0.0f ? t.a : t.b;
+      out[0] = c.x; out[1] = c.y; out[2] = c.z;
+      break;
+    }
+    case PTB_TEX_SOLID:
+      out[0] = t.a.x; out[1] = t.a.y; out[2] = t.a.z;
+      break;
+    case PTB_TEX_LERP: {
+      float tt = d[2] * 0.5f + 0.5f;
+      out[0] = t.a.x * tt + t.b.x * (1.0f - tt);
+      out[1] = t.a.y * tt + t.b.y * (1.0f - tt);
+      out[2] = t.a.z * tt + t.b.z * (1.0f - tt);
+      break;
+    }
+    default:
+      out[0] = out[1] = out[2] = 1.0f;
+  }
+}
+static void dist1d(const float* values, size_t n, std::vector<float>& pdf, std::vector<float>& cdf) {
+  cdf.assign(1, 0.0f);
+  for (size_t i = 1; i <= n; ++i) cdf.push_back(cdf[i - 1] + values[i - 1]);
+  const float c = cdf[n];
+  for (auto& v : cdf)
+    if (c != 0.0f) v /= c;
+  pdf.clear();
+  float last = 0.0f;
+  for (size_t i = 1; i <= n; ++i) {
+    pdf.push_back(cdf[i] - last);
+    last = cdf[i];
+  }
+}
+static int32_t build_sky(Ctx* c) {
+  const uint32_t rx = c->sky.sampler_res_x, ry = c->sky.sampler_res_y;
+  c->dev.sky_tex = c->sky.texture;
+  c->dev.sky_rx = rx;
+  c->dev.sky_ry = ry;
+  c->dev.sky_ycdf = c->dev.sky_ypdf = c->dev.sky_xcdf = c->dev.sky_xpdf = nullptr;
+  if ((rx | ry) == 0) return PTB_OK;
+  if (rx == 0 || ry == 0) return set_error(c, PTB_ERR_INVALID, "sky sampler_res must be (0,0) or both non-zero");
+  const ptb_texture& tex = c->textures[c->sky.texture];
+  std::vector<float> values;
+  values.reserve((size_t)rx * ry);
+  const float step_x = 1.0f / (float)rx, step_y = 1.0f / (float)ry;
+  for (uint32_t y = 0; y < ry; ++y)
+    for (uint32_t x = 0; x < rx; ++x) {
+      float u = ((float)x + 0.5f) * step_x, v = ((float)y + 0.5f) * step_y;
+      float phi = u * 2.0f * kPi, theta = v * kPi;
+      float sin_theta = sinf(theta);
+      float dir[3] = {cosf(phi) * sin_theta, sinf(phi) * sin_theta, cosf(theta)};
+      float zero[3] = {0, 0, 0}, col[3];
+      host_texture_colour(tex, dir, zero, col);
+      values.push_back((0.2126f * col[0] + 0.7152f * col[1] + 0.0722f * col[2]) * sin_theta);
+    }
+  std::vector<float> ycdf, ypdf, xcdf, xpdf, yvals, p, q;
+  for (uint32_t y = 0; y < ry; ++y) {
+    dist1d(&values[(size_t)y * rx], rx, p, q);
+    xpdf.insert(xpdf.end(), p.begin(), p.end());
+    xcdf.insert(xcdf.end(), q.begin(), q.end());
+    float row_sum = 0.0f;
+    for (uint32_t x = 0; x < rx; ++x) row_sum += values[(size_t)y * rx + x];
+    yvals.push_back(row_sum);
+  }
+  dist1d(yvals.data(), ry, ypdf, ycdf);
+  PTB_CUDA_TRY(c, c->d_sky_ycdf.alloc(ycdf.size() * 4));
+  PTB_CUDA_TRY(c, c->d_sky_ypdf.alloc(ypdf.size() * 4));
+  PTB_CUDA_TRY(c, c->d_sky_xcdf.alloc(xcdf.size() * 4));
+  PTB_CUDA_TRY(c, c->d_sky_xpdf.alloc(xpdf.size() * 4));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_sky_ycdf.p, ycdf.data(), ycdf.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_sky_ypdf.p, ypdf.data(), ypdf.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_sky_xcdf.p, xcdf.data(), xcdf.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_sky_xpdf.p, xpdf.data(), xpdf.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));  // the host vectors die at scope exit
+  c->dev.sky_ycdf = c->d_sky_ycdf.as<float>();
+  c->dev.sky_ypdf = c->d_sky_ypdf.as<float>();
+  c->dev.sky_xcdf = c->d_sky_xcdf.as<float>();
+  c->dev.sky_xpdf = c->d_sky_xpdf.as<float>();
+  return PTB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ host: build
+int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
+  const size_t ns = c->spheres.size(), nt = c->triangles.size();
+  const size_t n = ns + nt;
+  if (n >= (size_t)kSlotMask) return set_error(c, PTB_ERR_INVALID, "too many primitives (%zu)", n);
+  if (!c->have_camera) return set_error(c, PTB_ERR_INVALID, "scene has no camera");
+  if (c->materials.empty() || c->textures.empty()) return set_error(c, PTB_ERR_INVALID, "scene has no materials/textures");
+  for (const auto& s : c->spheres)
+    if (s.material >= c->materials.size()) return set_error(c, PTB_ERR_INVALID, "sphere material index out of range");
+  for (const auto& t : c->triangles)
+    if (t.material >= c->materials.size()) return set_error(c, PTB_ERR_INVALID, "triangle material index out of range");
+  for (const auto& m : c->materials)
+    if (m.texture >= c->textures.size()) return set_error(c, PTB_ERR_INVALID, "material texture index out of range");
+  if (!c->have_sky) {  // loader default: __DEFAULT_TEX, 100x100 (loader/src/misc.rs:22-25) needs an explicit sky here
+    return set_error(c, PTB_ERR_INVALID, "scene has no sky (ptb_scene_set_sky)");
+  }
+  if (c->sky.texture >= c->textures.size()) return set_error(c, PTB_ERR_INVALID, "sky texture index out of range");
+  for (const auto& t : c->textures)
+    if (t.kind == PTB_TEX_IMAGE || t.kind == PTB_TEX_PERLIN)
+      return set_error(c, PTB_ERR_UNSUPPORTED, "image/perlin textures are not supported by the cuda backend yet");
+  for (const auto& m : c->materials)
+    if (m.kind == PTB_MAT_TROWBRIDGE_REITZ)
+      return set_error(c, PTB_ERR_UNSUPPORTED, "trowbridge_reitz is not supported by the cuda backend yet");
+
+  cudaStream_t st = c->stream;
+  c->committed = false;
+
+  // materials / textures / camera
+  std::vector<DevMaterial> dm(c->materials.size());
+  for (size_t i = 0; i < dm.size(); ++i) {
+    const ptb_material& m = c->materials[i];
+    dm[i].kind = m.kind; dm[i].tex = m.texture; dm[i].param = m.param; dm[i].metallic = m.metallic;
+    dm[i].ior[0] = m.ior.x; dm[i].ior[1] = m.ior.y; dm[i].ior[2] = m.ior.z; dm[i]._pad = 0;
+  }
+  std::vector<DevTexture> dt(c->textures.size());
+  for (size_t i = 0; i < dt.size(); ++i) {
+    const ptb_texture& t = c->textures[i];
+    dt[i].kind = t.kind;
+    dt[i].a[0] = t.a.x; dt[i].a[1] = t.a.y; dt[i].a[2] = t.a.z;
+    dt[i].b[0] = t.b.x; dt[i].b[1] = t.b.y; dt[i].b[2] = t.b.z;
+    dt[i]._pad = 0;
+  }
+  PTB_CUDA_TRY(c, c->d_materials.alloc(dm.size() * sizeof(DevMaterial)));
+  PTB_CUDA_TRY(c, c->d_textures.alloc(dt.size() * sizeof(DevTexture)));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_materials.p, dm.data(), dm.size() * sizeof(DevMaterial), cudaMemcpyHostToDevice, st));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_textures.p, dt.data(), dt.size() * sizeof(DevTexture), cudaMemcpyHostToDevice, st));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
+  c->dev.materials = c->d_materials.as<DevMaterial>();
+  c->dev.textures = c->d_textures.as<DevTexture>();
+  c->dev.cam_origin = mk(c->camera.origin.x, c->camera.origin.y, c->camera.origin.z);
+  c->dev.cam_lower_left = mk(c->camera.lower_left.x, c->camera.lower_left.y, c->camera.lower_left.z);
+  c->dev.cam_horizontal = mk(c->camera.horizontal.x, c->camera.horizontal.y, c->camera.horizontal.z);
+  c->dev.cam_vertical = mk(c->camera.vertical.x, c->camera.vertical.y, c->camera.vertical.z);
+  {
+    int32_t rc = build_sky(c);
+    if (rc != PTB_OK) return rc;
+  }
+
+  c->n_prims = n;
+  c->n_nodes = n == 0 ? 0 : (n == 1 ? 1 : n - 1);
+  c->dev.n_prims = (uint32_t)n;
+  c->dev.n_lights = 0;
+  c->dev.geom = nullptr; c->dev.normals = nullptr; c->dev.slot_prim = nullptr; c->dev.slot_mat = nullptr;
+  c->dev.nodes = nullptr; c->dev.lights = nullptr;
+  if (n == 0) {
+    c->committed = true;
+    c->stats.build_ms = 0.0;
+    return PTB_OK;
+  }
+
+  // lights in ORIGINAL primitive order (deterministic): material.is_light() (acceleration/mod.rs:84-88)
+  std::vector<uint32_t> light_prims;
+  for (size_t i = 0; i < ns; ++i)
+    if (c->materials[c->spheres[i].material].kind == PTB_MAT_EMIT) light_prims.push_back((uint32_t)i);
+  for (size_t i = 0; i < nt; ++i)
+    if (c->materials[c->triangles[i].material].kind == PTB_MAT_EMIT) light_prims.push_back((uint32_t)(ns + i));
+
+  DevBuf raw_spheres, raw_tris, bmin, bmax, bounds, keys_a, keys_b, vals_a, vals_b, hist, leaf_parent, nbmin, nbmax, flags,
+      prim_slot, d_light_prims;
+  PTB_CUDA_TRY(c, raw_spheres.alloc(ns * sizeof(ptb_sphere)));
+  PTB_CUDA_TRY(c, raw_tris.alloc(nt * sizeof(ptb_triangle)));
+  if (ns) PTB_CUDA_TRY(c, cudaMemcpyAsync(raw_spheres.p, c->spheres.data(), ns * sizeof(ptb_sphere), cudaMemcpyHostToDevice, st));
+  if (nt) PTB_CUDA_TRY(c, cudaMemcpyAsync(raw_tris.p, c->triangles.data(), nt * sizeof(ptb_triangle), cudaMemcpyHostToDevice, st));
+
+  const uint32_t n32 = (uint32_t)n, ns32 = (uint32_t)ns, nt32 = (uint32_t)nt;
+  const uint32_t n_tiles = (n32 + RS_TILE - 1) / RS_TILE;
+  PTB_CUDA_TRY(c, bmin.alloc(n * 16));
+  PTB_CUDA_TRY(c, bmax.alloc(n * 16));
+  PTB_CUDA_TRY(c, bounds.alloc(6 * 4));
+  PTB_CUDA_TRY(c, keys_a.alloc(n * 4));
+  PTB_CUDA_TRY(c, keys_b.alloc(n * 4));
+  PTB_CUDA_TRY(c, vals_a.alloc(n * 4));
+  PTB_CUDA_TRY(c, vals_b.alloc(n * 4));
+  PTB_CUDA_TRY(c, hist.alloc((size_t)256 * n_tiles * 4));
+  PTB_CUDA_TRY(c, leaf_parent.alloc(n * 4));
+  PTB_CUDA_TRY(c, nbmin.alloc(c->n_nodes * 16));
+  PTB_CUDA_TRY(c, nbmax.alloc(c->n_nodes * 16));
+  PTB_CUDA_TRY(c, flags.alloc(c->n_nodes * 4));
+  PTB_CUDA_TRY(c, prim_slot.alloc(n * 4));
+  PTB_CUDA_TRY(c, c->d_nodes.alloc(c->n_nodes * sizeof(BvhNode)));
+  PTB_CUDA_TRY(c, c->d_geom.alloc(n * 48));
+  PTB_CUDA_TRY(c, c->d_normals.alloc(n * 48));
+  PTB_CUDA_TRY(c, c->d_slot_mat.alloc(n * 4));
+  PTB_CUDA_TRY(c, c->d_lights.alloc(light_prims.size() * 4));
+  PTB_CUDA_TRY(c, d_light_prims.alloc(light_prims.size() * 4));
+
+  PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
+  {
+    const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(bounds.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+  }
+  const int T = 256;
+  const uint32_t gn = (n32 + T - 1) / T;
+  k_prim_bounds<<<gn, T, 0, st>>>(raw_spheres.as<ptb_sphere>(), ns32, raw_tris.as<ptb_triangle>(), nt32, bmin.as<float4>(),
+                                  bmax.as<float4>(), bounds.as<uint32_t>());
+  k_morton<<<gn, T, 0, st>>>(bmin.as<float4>(), bmax.as<float4>(), n32, bounds.as<uint32_t>(), keys_a.as<uint32_t>(),
+                             vals_a.as<uint32_t>());
+  c->stats.kernel_launches += 2;
+  uint32_t *ka = keys_a.as<uint32_t>(), *kb = keys_b.as<uint32_t>(), *va = vals_a.as<uint32_t>(), *vb = vals_b.as<uint32_t>();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = pass * 8;
+    k_radix_pass<false><<<n_tiles, RS_THREADS, 0, st>>>(ka, va, kb, vb, n32, shift, hist.as<uint32_t>(), n_tiles);
+    k_radix_scan<<<1, 256, 0, st>>>(hist.as<uint32_t>(), n_tiles);
+    k_radix_pass<true><<<n_tiles, RS_THREADS, 0, st>>>(ka, va, kb, vb, n32, shift, hist.as<uint32_t>(), n_tiles);
+    c->stats.kernel_launches += 3;
+    uint32_t* t;
+    t = ka; ka = kb; kb = t;
+    t = va; va = vb; vb = t;
+  }
+  // after 4 passes the sorted data is back in (keys_a, vals_a) == (ka, va)
+  if (n == 1) {
+    k_single_node<<<1, 1, 0, st>>>(va, ns32, bmin.as<float4>(), bmax.as<float4>(), c->d_nodes.as<BvhNode>());
+    c->stats.kernel_launches += 1;
+  } else {
+    PTB_CUDA_TRY(c, cudaMemsetAsync(flags.p, 0, c->n_nodes * 4, st));
+    k_hierarchy<<<(n32 - 1 + T - 1) / T, T, 0, st>>>(ka, va, n32, ns32, c->d_nodes.as<BvhNode>(), leaf_parent.as<uint32_t>());
+    k_refit<<<gn, T, 0, st>>>(n32, va, leaf_parent.as<uint32_t>(), bmin.as<float4>(), bmax.as<float4>(),
+                              c->d_nodes.as<BvhNode>(), nbmin.as<float4>(), nbmax.as<float4>(), flags.as<uint32_t>());
+    c->stats.kernel_launches += 2;
+  }
+  k_gather<<<gn, T, 0, st>>>(raw_spheres.as<ptb_sphere>(), ns32, raw_tris.as<ptb_triangle>(), n32, va,
+                             c->d_materials.as<DevMaterial>(), c->d_geom.as<float4>(), c->d_normals.as<float4>(),
+                             c->d_slot_mat.as<uint32_t>(), prim_slot.as<uint32_t>());
+  c->stats.kernel_launches += 1;
+  if (!light_prims.empty()) {
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(d_light_prims.p, light_prims.data(), light_prims.size() * 4, cudaMemcpyHostToDevice, st));
+    const uint32_t nl = (uint32_t)light_prims.size();
+    k_light_slots<<<(nl + T - 1) / T, T, 0, st>>>(d_light_prims.as<uint32_t>(), nl, ns32, prim_slot.as<uint32_t>(),
+                                                  c->d_lights.as<uint32_t>());
+    c->stats.kernel_launches += 1;
+  }
+  // keep the sorted keys / ids for ptb_bvh_export
+  PTB_CUDA_TRY(c, c->d_morton.alloc(n * 4));
+  PTB_CUDA_TRY(c, c->d_slot_prim.alloc(n * 4));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_morton.p, ka, n * 4, cudaMemcpyDeviceToDevice, st));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_slot_prim.p, va, n * 4, cudaMemcpyDeviceToDevice, st));
+  PTB_CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
+  PTB_CUDA_TRY(c, cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+  c->stats.build_ms = ms;
+
+  c->dev.geom = c->d_geom.as<float4>();
+  c->dev.normals = c->d_normals.as<float4>();
+  c->dev.slot_prim = c->d_slot_prim.as<uint32_t>();
+  c->dev.slot_mat = c->d_slot_mat.as<uint32_t>();
+  c->dev.nodes = c->d_nodes.as<BvhNode>();
+  c->dev.lights = c->d_lights.as<uint32_t>();
+  c->dev.n_lights = (uint32_t)light_prims.size();
+  c->committed = true;
+  return PTB_OK;
+}
+
+}  // namespace ptb

@@ -1,0 +1,128 @@
+// ptb200 internal host-side declarations shared by the .cu translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "ptb_common.cuh"
+
+namespace ptb {
+
+// RAII device allocation
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  cudaError_t alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    else p = nullptr;
+    return e;
+  }
+  // grow-only
+  cudaError_t reserve(size_t n) { return n <= bytes ? cudaSuccess : alloc(n); }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Wavefront state for one render call (device pointers). See wavefront.cu.
+struct PathPool {
+  uint32_t capacity = 0;
+  float4* ray_o = nullptr;  // origin.xyz | pixel (bits)
+  float4* ray_d = nullptr;  // normalised direction.xyz | depth + flags (bits)
+  float4* thr = nullptr;    // throughput.rgb | absolute sample index (bits)
+  float4* rad = nullptr;    // radiance gathered so far .rgb | m_pdf of the last BSDF sample (MIS)
+  float4* prev = nullptr;   // MIS: previous (un-offset) hit point.xyz | unused
+  uint2* hit = nullptr;     // t (bits), leaf ref (kNone = miss)
+};
+
+constexpr int kNumKinds = 6;  // shade queues: 0 = miss (sky), 1 + PTB_MAT_* otherwise
+
+struct WaveCounters {  // lives in device memory; mirrored to pinned host memory once per iteration
+  uint32_t n_free;          // entries in q_free
+  uint32_t n_active[2];     // entries in q_active[k]
+  uint32_t n_new;           // camera paths generated this iteration
+  uint32_t n_trace;         // rays to trace this iteration
+  uint32_t free_base;       // q_free[free_base .. free_base + n_new) feed the generator
+  uint32_t n_kind[kNumKinds];
+  uint32_t n_shadow;
+  uint32_t cur;             // which q_active is the trace queue
+  uint32_t trace_head, shade_head, shadow_head;  // persistent-kernel work cursors
+  uint32_t _pad;
+  unsigned long long next_sample;   // next global sample index (pixel-major within a pass)
+  unsigned long long total_samples;
+  // statistics (ptb_stats)
+  unsigned long long rays_camera, rays_bounce, rays_shadow_light, rays_shadow_sky, rays_reference, paths;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string last_error;
+  int sm_count = 148;
+
+  // host copy of the scene (ptb_scene_set_*)
+  std::vector<ptb_sphere> spheres;
+  std::vector<ptb_triangle> triangles;
+  std::vector<ptb_material> materials;
+  std::vector<ptb_texture> textures;
+  ptb_camera camera{};
+  ptb_sky sky{};
+  bool have_camera = false, have_sky = false;
+  bool committed = false;
+
+  // device scene
+  DevScene dev{};
+  DevBuf d_geom, d_normals, d_slot_prim, d_slot_mat, d_nodes, d_morton, d_materials, d_textures, d_lights;
+  DevBuf d_sky_ycdf, d_sky_ypdf, d_sky_xcdf, d_sky_xpdf;
+  uint64_t n_prims = 0, n_nodes = 0;
+
+  // render state
+  DevBuf d_accum;
+  uint32_t accum_w = 0, accum_h = 0;
+  uint64_t accum_samples = 0;
+  DevBuf d_pool_mem, d_queues, d_shadow, d_counters;
+  PathPool pool;
+  WaveCounters* h_counters = nullptr;  // pinned
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_iter = nullptr;
+
+  // closest-hit staging
+  DevBuf d_rays, d_hits;
+
+  ptb_stats stats{};
+};
+
+int32_t set_error(Ctx* c, int32_t code, const char* fmt, ...);
+int32_t check_cuda(Ctx* c, cudaError_t e, const char* what);
+
+// lbvh_build.cu — uploads the host scene and builds the device LBVH (K2..K6)
+int32_t build_scene(Ctx* c, uint32_t flags);
+// wavefront.cu
+int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progress, void* user);
+int32_t launch_closest_hit(Ctx* c, const void* d_rays, size_t n, void* d_hits);
+void free_render_state(Ctx* c);
+
+}  // namespace ptb
+
+struct ptb_ctx {
+  ptb::Ctx c;
+};
+
+#define PTB_CUDA_TRY(ctx, expr)                                   \
+  do {                                                            \
+    cudaError_t _e = (expr);                                      \
+    if (_e != cudaSuccess) return ptb::check_cuda(ctx, _e, #expr); \
+  } while (0)

@@ -1,0 +1,174 @@
+// Primitive and box intersection for ptb200 (device).
+//   sphere_t / sphere_hit     : implementations/src/primitives/sphere.rs:34-105
+//   triangle_t / triangle_hit : implementations/src/primitives/triangle.rs:105-216 (PBRT-v3 watertight test with the
+//                               reference's own axis permutation, f64 fallback and conservative t bound)
+//   box_entry                 : implementations/src/acceleration/aabb.rs:22-57 (slab test, far side widened by
+//                               1+2*gamma(3)), extended with the entry distance for ordered, t-culled traversal
+// Operation order matches the reference statement by statement (see ptb_common.cuh for the arithmetic contract).
+#pragma once
+#include "ptb_common.cuh"
+
+namespace ptb {
+
+struct HitRec {  // rt_core/src/primitive.rs:3-10 minus uv (never consumed by any texture)
+  float t;
+  v3 point, error, normal;
+  bool out;
+  float b1, b2;  // triangle.rs:149-151 barycentrics (closest-hit API output only)
+};
+
+// ---- sphere -------------------------------------------------------------------------------------------------------
+// returns t > 0 or -1 (no hit / behind)
+PTB_DEV float sphere_t(const Ray& ray, v3 center, float radius) {
+  v3 deltap = center - ray.o;
+  float ddp = dot(ray.d, deltap);
+  float deltapdot = dot(deltap, deltap);
+  v3 remedy = deltap - ddp * ray.d;
+  float discriminant = radius * radius - dot(remedy, remedy);
+  if (!(discriminant > 0.0f)) return -1.0f;
+  float sqrt_val = sqrtf(discriminant);
+  float q = ddp > 0.0f ? ddp + sqrt_val : ddp - sqrt_val;
+  float t0 = q;
+  float t1 = (deltapdot - radius * radius) / q;
+  if (t1 < t0) { float tmp = t0; t0 = t1; t1 = tmp; }
+  if (t0 > 0.0f) return t0;
+  if (t1 <= 0.0f) return -1.0f;
+  return t1;  // NaN propagates as in the reference (callers test `t > 0`)
+}
+PTB_DEV bool sphere_hit(const Ray& ray, v3 center, float radius, HitRec& h) {
+  float t = sphere_t(ray, center, radius);
+  if (t == -1.0f) return false;
+  v3 point = ray_at(ray, t);
+  v3 normal = (point - center) / radius;
+  bool out = true;
+  if (dot(normal, ray.d) > 0.0f) { out = false; normal = -normal; }
+  h.t = t;
+  h.point = point;
+  h.error = kEpsRt * mk(1.0f, 1.0f, 1.0f);
+  h.normal = normal;
+  h.out = out;
+  h.b1 = 0.0f;
+  h.b2 = 0.0f;
+  return true;
+}
+
+// ---- triangle -----------------------------------------------------------------------------------------------------
+struct TriCore {
+  float t, b0, b1, b2;
+};
+PTB_DEV bool triangle_core(const Ray& ray, v3 p0, v3 p1, v3 p2, TriCore& c) {
+  v3 p0t = p0 - ray.o, p1t = p1 - ray.o, p2t = p2 - ray.o;
+  if (ray.swap_xz) {
+    float tmp;
+    tmp = p0t.x; p0t.x = p0t.z; p0t.z = tmp;
+    tmp = p1t.x; p1t.x = p1t.z; p1t.z = tmp;
+    tmp = p2t.x; p2t.x = p2t.z; p2t.z = tmp;
+  }
+  p0t.x += ray.shear.x * p0t.z; p0t.y += ray.shear.y * p0t.z;
+  p1t.x += ray.shear.x * p1t.z; p1t.y += ray.shear.y * p1t.z;
+  p2t.x += ray.shear.x * p2t.z; p2t.y += ray.shear.y * p2t.z;
+
+  float e0 = p1t.x * p2t.y - p1t.y * p2t.x;
+  float e1 = p2t.x * p0t.y - p2t.y * p0t.x;
+  float e2 = p0t.x * p1t.y - p0t.y * p1t.x;
+  if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {
+    e0 = (float)__dsub_rn(__dmul_rn((double)p1t.x, (double)p2t.y), __dmul_rn((double)p1t.y, (double)p2t.x));
+    e1 = (float)__dsub_rn(__dmul_rn((double)p2t.x, (double)p0t.y), __dmul_rn((double)p2t.y, (double)p0t.x));
+    e2 = (float)__dsub_rn(__dmul_rn((double)p0t.x, (double)p1t.y), __dmul_rn((double)p0t.y, (double)p1t.x));
+  }
+  if ((e0 < 0.0f || e1 < 0.0f || e2 < 0.0f) && (e0 > 0.0f || e1 > 0.0f || e2 > 0.0f)) return false;
+  float det = e0 + e1 + e2;
+  if (det == 0.0f) return false;
+
+  p0t = p0t * ray.shear.z;
+  p1t = p1t * ray.shear.z;
+  p2t = p2t * ray.shear.z;
+
+  float t_scaled = e0 * p0t.z + e1 * p1t.z + e2 * p2t.z;
+  if ((det < 0.0f && t_scaled >= 0.0f) || (det > 0.0f && t_scaled <= 0.0f)) return false;
+
+  float inv_det = 1.0f / det;
+  float b0 = e0 * inv_det, b1 = e1 * inv_det, b2 = e2 * inv_det;
+  float t = inv_det * t_scaled;
+
+  float max_z_t = cmax3(fabsf(p0t.z), fabsf(p1t.z), fabsf(p2t.z));
+  float delta_z = gamma_n(3) * max_z_t;
+  float max_x_t = cmax3(fabsf(p0t.x), fabsf(p1t.x), fabsf(p2t.x));
+  float max_y_t = cmax3(fabsf(p0t.y), fabsf(p1t.y), fabsf(p2t.y));
+  float delta_x = gamma_n(5) * (max_x_t + max_z_t);
+  float delta_y = gamma_n(5) * (max_y_t + max_z_t);
+  float delta_e = 2.0f * (gamma_n(2) * max_x_t * max_y_t + delta_y * max_x_t + delta_x * max_y_t);
+  float max_e = cmax3(fabsf(e0), fabsf(e1), fabsf(e2));
+  float delta_t = 3.0f * (gamma_n(3) * max_e * max_z_t + delta_e * max_z_t + delta_z * max_e) * fabsf(inv_det);
+  if (t < delta_t) return false;
+  c.t = t; c.b0 = b0; c.b1 = b1; c.b2 = b2;
+  return true;
+}
+// returns t > 0 or -1
+PTB_DEV float triangle_t(const Ray& ray, v3 p0, v3 p1, v3 p2) {
+  TriCore c;
+  if (!triangle_core(ray, p0, p1, p2, c)) return -1.0f;
+  return c.t;
+}
+PTB_DEV bool triangle_hit(const Ray& ray, v3 p0, v3 p1, v3 p2, v3 n0, v3 n1, v3 n2, HitRec& h) {
+  TriCore c;
+  if (!triangle_core(ray, p0, p1, p2, c)) return false;
+  v3 normal = c.b0 * n0 + c.b1 * n1 + c.b2 * n2;
+  bool out = true;
+  if (dot(normal, ray.d) > 0.0f) { normal = -normal; out = false; }  // utility/mod.rs:6-13 check_side
+  float x_abs_sum = fabsf(c.b0 * p0.x) + fabsf(c.b1 * p1.x) + fabsf(c.b2 * p2.x);
+  float y_abs_sum = fabsf(c.b0 * p0.y) + fabsf(c.b1 * p1.y) + fabsf(c.b2 * p2.y);
+  float z_abs_sum = fabsf(c.b0 * p0.z) + fabsf(c.b1 * p1.z) + fabsf(c.b2 * p2.z);
+  h.error = gamma_n(7) * mk(x_abs_sum, y_abs_sum, z_abs_sum) + gamma_n(6) * mk(c.b2 * p2.x, c.b2 * p2.y, c.b2 * p2.z);
+  h.point = c.b0 * p0 + c.b1 * p1 + c.b2 * p2;
+  h.t = c.t;
+  h.normal = normal;
+  h.out = out;
+  h.b1 = c.b1;
+  h.b2 = c.b2;
+  return true;
+}
+
+// ---- slot-level dispatch ---------------------------------------------------------------------------------------------
+// `ref` = leaf reference (kSphereBit | slot)
+PTB_DEV float prim_t(const DevScene& sc, const Ray& ray, uint32_t ref) {
+  const uint32_t slot = ref & kSlotMask;
+  const float4* g = sc.geom + 3u * (size_t)slot;
+  const float4 g0 = __ldg(g);
+  if (ref & kSphereBit) return sphere_t(ray, from4(g0), g0.w);
+  const float4 g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+  return triangle_t(ray, from4(g0), from4(g1), from4(g2));
+}
+PTB_DEV bool prim_hit(const DevScene& sc, const Ray& ray, uint32_t ref, HitRec& h) {
+  const uint32_t slot = ref & kSlotMask;
+  const float4* g = sc.geom + 3u * (size_t)slot;
+  const float4 g0 = __ldg(g);
+  if (ref & kSphereBit) return sphere_hit(ray, from4(g0), g0.w, h);
+  const float4 g1 = __ldg(g + 1), g2 = __ldg(g + 2);
+  const float4* nn = sc.normals + 3u * (size_t)slot;
+  const float4 n0 = __ldg(nn), n1 = __ldg(nn + 1), n2 = __ldg(nn + 2);
+  return triangle_hit(ray, from4(g0), from4(g1), from4(g2), from4(n0), from4(n1), from4(n2), h);
+}
+
+// ---- box -----------------------------------------------------------------------------------------------------------------
+// hit when the reference's does_int would accept the box AND its entry distance does not exceed best_t.
+PTB_DEV bool box_entry(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Ray& ray, float best_t,
+                       float& tnear) {
+  const float k = 1.0f + 2.0f * gamma_n(3);
+  float t1 = (mnx - ray.o.x) * ray.dinv.x;
+  float t2 = (mxx - ray.o.x) * ray.dinv.x;
+  float tmin = fminf(t1, t2);
+  float tmax = fmaxf(t1, t2) * k;
+  t1 = (mny - ray.o.y) * ray.dinv.y;
+  t2 = (mxy - ray.o.y) * ray.dinv.y;
+  tmin = fmaxf(tmin, fminf(t1, t2));
+  tmax = fminf(tmax, fmaxf(t1, t2) * k);
+  t1 = (mnz - ray.o.z) * ray.dinv.z;
+  t2 = (mxz - ray.o.z) * ray.dinv.z;
+  tmin = fmaxf(tmin, fminf(t1, t2));
+  tmax = fminf(tmax, fmaxf(t1, t2) * k);
+  tnear = tmin;
+  return tmax > fmaxf(tmin, 0.0f) && tmin <= best_t;
+}
+
+}  // namespace ptb

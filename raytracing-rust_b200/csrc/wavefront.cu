@@ -1,0 +1,797 @@
+// ptb200 — wavefront path tracer (sm_100a). Replaces RandomSampler::sample_image + the integrators
+// (implementations/src/samplers/random_sampler.rs:23-99, integrators/mod.rs:22-78, integrators/mis.rs:6-157) and
+// everything they call per bounce (materials/*.rs, sky.rs, textures/mod.rs, primitives light sampling).
+//
+// One wavefront iteration =
+//   k_prepare   (1 thread)   pool bookkeeping: how many camera paths to regenerate into freed slots, queue resets
+//   k_generate  K1           camera rays for (pixel, sample) pairs          random_sampler.rs:50-61, camera.rs:57-63
+//   k_trace     K8 + K11     closest hit for every live path (persistent warps pulling 32-ray batches), result
+//                            pushed to one queue per material kind (warp-aggregated atomics)
+//   k_shade     K10 + K12    per material-kind queue: emission, MIS weights, NEE sample -> shadow queue, BSDF sample
+//                            -> next ray, Russian roulette, path termination -> accumulator
+//   k_shadow    K9           any-hit for the NEE queue; unoccluded contributions are added to the path's radiance
+// Paths live in pool slots (SoA float4 records); queues carry slot indices. A finished path frees its slot, which
+// the next k_generate refills, so the device stays full until the last sample has been issued.
+//
+// The RNG is counter-based (Philox4x32-10 keyed by seed; counter = pixel, absolute sample, depth|purpose, block):
+// the image is a pure function of (scene, seed, sample range) — independent of pool size, scheduling and GPU count.
+#include "ptb_internal.h"
+#include "ptb_traverse.cuh"
+
+namespace ptb {
+
+struct RenderParams {
+  uint32_t width, height, npix;
+  uint32_t sample_offset;
+  uint32_t method, max_depth, rr_threshold;
+  uint32_t k0, k1;  // Philox key
+};
+
+struct Queues {
+  uint32_t* active[2];
+  uint32_t* free_slots;
+  uint32_t* kind[kNumKinds];
+  float4* shadow;  // 3 x float4 per entry: o.xyz|tmax, d.xyz|exclude slot, contrib.rgb|path slot
+};
+
+constexpr uint32_t kFlagPrevDelta = 1u << 8;  // stored above the 8-bit depth in ray_d.w
+
+// ------------------------------------------------------------------------------------------ textures / sky
+// implementations/src/textures/mod.rs:61-73 (checkered), 193-200 (solid), 283-291 (lerp)
+PTB_DEV v3 texture_colour(const DevScene& sc, uint32_t tex, v3 direction, v3 point) {
+  const DevTexture* t = sc.textures + tex;
+  const uint32_t kind = __ldg(&t->kind);
+  const v3 a = mk(__ldg(&t->a[0]), __ldg(&t->a[1]), __ldg(&t->a[2]));
+  if (kind == PTB_TEX_SOLID) return a;
+  const v3 b = mk(__ldg(&t->b[0]), __ldg(&t->b[1]), __ldg(&t->b[2]));
+  if (kind == PTB_TEX_LERP) {
+    const float tt = direction.z * 0.5f + 0.5f;
+    return a * tt + b * (1.0f - tt);
+  }
+  if (kind == PTB_TEX_CHECKERED) {
+    const float sign = sinf(10.0f * point.x) * sinf(10.0f * point.y) * sinf(10.0f * point.z);
+    return sign > 0.0f ? a : b;
+  }
+  return mk(1.0f, 1.0f, 1.0f);
+}
+
+// statistics/distributions.rs:51-72
+PTB_DEV uint32_t dist1d_sample(const float* __restrict__ cdf, uint32_t cdf_len, float num) {
+  uint32_t first = 0, len = cdf_len;
+  while (len > 0) {
+    const uint32_t half = len >> 1;
+    const uint32_t middle = first + half;
+    if (__ldg(cdf + middle) <= num) {
+      first = middle + 1;
+      len -= half + 1;
+    } else {
+      len = half;
+    }
+  }
+  const uint32_t r = first - 1u, hi = cdf_len - 2u;
+  return r > hi ? hi : r;
+}
+PTB_DEV uint32_t sat_index(float f, uint32_t hi) {  // Rust `as usize` then clamp(0, hi)
+  if (!(f > 0.0f)) return 0u;
+  if (f >= 4294967040.0f) return hi;
+  const uint32_t i = (uint32_t)f;
+  return i > hi ? hi : i;
+}
+// sky.rs:43-60
+PTB_DEV float sky_pdf(const DevScene& sc, v3 wi) {
+  const float sin_theta = sqrtf(1.0f - wi.z * wi.z);
+  if (sin_theta <= 0.0f) return 0.0f;
+  const float theta = acosf(wi.z);
+  float phi = atan2f(wi.y, wi.x);
+  if (phi < 0.0f) phi += 2.0f * kPi;
+  const float u = phi / (2.0f * kPi);
+  const float v = theta / kPi;
+  const uint32_t ui = sat_index((float)sc.sky_rx * u, sc.sky_rx - 1u);
+  const uint32_t vi = sat_index((float)sc.sky_ry * v, sc.sky_ry - 1u);
+  const float pdf = __ldg(sc.sky_ypdf + vi) * __ldg(sc.sky_xpdf + (size_t)vi * sc.sky_rx + ui);
+  return (float)sc.sky_rx * (float)sc.sky_ry * pdf / (sin_theta * kTau * kPi);
+}
+// sky.rs:64-78 with draws (row, column, u jitter, v jitter)
+PTB_DEV v3 sky_sample(const DevScene& sc, float r_row, float r_col, float r_u, float r_v) {
+  const uint32_t vi = dist1d_sample(sc.sky_ycdf, sc.sky_ry + 1u, r_row);
+  const uint32_t ui = dist1d_sample(sc.sky_xcdf + (size_t)vi * (sc.sky_rx + 1u), sc.sky_rx + 1u, r_col);
+  const float u = next_float((float)ui + r_u) / (float)sc.sky_rx;
+  const float v = next_float((float)vi + r_v) / (float)sc.sky_ry;
+  const float phi = u * 2.0f * kPi;
+  const float theta = v * kPi;
+  const float st = sinf(theta), ct = cosf(theta), sp = sinf(phi), cp = cosf(phi);
+  return mk(st * cp, st * sp, ct);
+}
+
+// ------------------------------------------------------------------------------------------ lights
+// sphere.rs:112-154 / triangle.rs:258-277 (MeshTriangle variant, quirk Q8)
+PTB_DEV v3 light_sample_dir(const DevScene& sc, uint32_t ref, v3 in_point, float r1, float r2) {
+  const float4* g = sc.geom + 3u * (size_t)(ref & kSlotMask);
+  const float4 g0 = __ldg(g);
+  v3 point;
+  if (ref & kSphereBit) {
+    const v3 center = from4(g0);
+    const float radius = g0.w;
+    const float distance_sq = mag_sq(in_point - center);
+    if (distance_sq <= radius * radius) {
+      const float z = 1.0f - 2.0f * r1;
+      const float a = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+      const float b = 2.0f * kPi * r2;
+      point = center + radius * mk(a * cosf(b), a * sinf(b), z);
+    } else {
+      const float distance = sqrtf(distance_sq);
+      const float sin_theta_max_sq = radius * radius / distance_sq;
+      const float cos_theta_max = sqrtf(fmaxf(1.0f - sin_theta_max_sq, 0.0f));
+      const float cos_theta = (1.0f - r1) + r1 * cos_theta_max;
+      const float sin_theta = sqrtf(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
+      const float phi = 2.0f * r2 * kPi;
+      const float ds = distance * cos_theta - sqrtf(fmaxf(radius * radius - distance_sq * sin_theta * sin_theta, 0.0f));
+      const float cos_alpha = (distance_sq + radius * radius - ds * ds) / (2.0f * distance * radius);
+      const float sin_alpha = sqrtf(fmaxf(1.0f - cos_alpha * cos_alpha, 0.0f));
+      const v3 vec = onb_to_world(normalised(in_point - center), mk(sin_alpha * cosf(phi), sin_alpha * sinf(phi), cos_alpha));
+      point = center + radius * vec;
+    }
+  } else {
+    const v3 p0 = from4(g0), p1 = from4(__ldg(g + 1)), p2 = from4(__ldg(g + 2));
+    const float s = sqrtf(r1);
+    const float u0 = 1.0f - s;
+    const float u1 = s * sqrtf(r2);
+    point = u0 * p0 + u1 * p1 + (1.0f - u0 - u1) * p2;
+  }
+  return normalised(point - in_point);
+}
+// sphere.rs:155-170 / triangle.rs:249-257, 278-280
+PTB_DEV float light_pdf(const DevScene& sc, uint32_t ref, v3 hit_point, v3 wi, v3 s_point, v3 s_normal) {
+  const float4* g = sc.geom + 3u * (size_t)(ref & kSlotMask);
+  const float4 g0 = __ldg(g);
+  if (ref & kSphereBit) {
+    const v3 center = from4(g0);
+    const float radius = g0.w;
+    const float rsq = radius * radius;
+    const float dsq = mag_sq(hit_point - center);
+    if (dsq <= rsq) {
+      const float area = 4.0f * kPi * radius * radius;
+      return mag_sq(s_point - hit_point) / (fabsf(dot(wi, s_normal)) * area);
+    }
+    const float sin_theta_max_sq = rsq / dsq;
+    const float cos_theta_max = sqrtf(fmaxf(1.0f - sin_theta_max_sq, 0.0f));
+    return 1.0f / (2.0f * kPi * (1.0f - cos_theta_max));
+  }
+  const v3 p0 = from4(g0), p1 = from4(__ldg(g + 1)), p2 = from4(__ldg(g + 2));
+  const float area = 0.5f * mag(cross(p1 - p0, p2 - p0));
+  return mag_sq(s_point - hit_point) / (fabsf(dot(wi, s_normal)) * area);
+}
+
+// ------------------------------------------------------------------------------------------ bookkeeping kernels
+__global__ void k_init_pool(uint32_t* free_slots, uint32_t capacity, WaveCounters* wc, unsigned long long total_samples) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < capacity) free_slots[i] = capacity - 1u - i;  // popped from the end: slot 0 first
+  if (i == 0) {
+    wc->n_free = capacity;
+    wc->n_active[0] = wc->n_active[1] = 0;
+    wc->n_new = wc->n_trace = wc->free_base = 0;
+    for (int k = 0; k < kNumKinds; ++k) wc->n_kind[k] = 0;
+    wc->n_shadow = 0;
+    wc->cur = 0;
+    wc->trace_head = wc->shade_head = wc->shadow_head = 0;
+    wc->next_sample = 0;
+    wc->total_samples = total_samples;
+    wc->rays_camera = wc->rays_bounce = wc->rays_shadow_light = wc->rays_shadow_sky = wc->rays_reference = wc->paths = 0;
+  }
+}
+
+// Runs between iterations. Folds the finished iteration's counts into the statistics, flips the active queues and
+// decides how many camera paths the next k_generate starts.
+__global__ void k_prepare(WaveCounters* wc, uint32_t method, uint32_t first) {
+  if (!first) {
+    const uint32_t cur = wc->cur, nxt = cur ^ 1u;
+    const uint32_t traced = wc->n_trace, survivors = wc->n_active[nxt];
+    wc->rays_camera += wc->n_new;
+    wc->rays_bounce += traced - wc->n_new;
+    wc->rays_reference += method == PTB_METHOD_NAIVE ? traced : survivors;  // Q7: naive 1/check_hit, MIS 1/bounce iteration
+    wc->paths += traced - survivors;
+    wc->n_active[cur] = 0;
+    wc->cur = nxt;
+  }
+  const uint32_t cur = wc->cur;
+  const unsigned long long remaining = wc->total_samples - wc->next_sample;
+  const uint32_t n_free = wc->n_free;
+  const uint32_t n_new = remaining < (unsigned long long)n_free ? (uint32_t)remaining : n_free;
+  wc->n_new = n_new;
+  wc->free_base = n_free - n_new;
+  wc->n_free = n_free - n_new;
+  wc->n_trace = wc->n_active[cur] + n_new;
+  for (int k = 0; k < kNumKinds; ++k) wc->n_kind[k] = 0;
+  wc->n_shadow = 0;
+  wc->trace_head = wc->shade_head = wc->shadow_head = 0;
+}
+
+// ------------------------------------------------------------------------------------------ K1 camera rays
+__global__ void __launch_bounds__(256)
+k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_new = wc->n_new;
+  if (i >= n_new) return;
+  const uint32_t cur = wc->cur;
+  const uint32_t slot = q.free_slots[wc->free_base + (n_new - 1u - i)];
+  const unsigned long long g = wc->next_sample + i;
+  const uint32_t pixel = (uint32_t)(g % rp.npix);
+  const uint32_t sample = rp.sample_offset + (uint32_t)(g / rp.npix);
+  const uint32_t x = pixel % rp.width, y = pixel / rp.width;
+  const uint4 r = philox4x32_10(pixel, sample, (0u << 8) | RNG_JITTER, 0u, rp.k0, rp.k1);
+  // random_sampler.rs:55-59 (note W-1 / H-1)
+  const float u = (u32_to_unit(r.x) + (float)x) / (float)(rp.width - 1u);
+  const float v = 1.0f - (u32_to_unit(r.y) + (float)y) / (float)(rp.height - 1u);
+  // camera.rs:57-63 + Ray::new (ray.rs:13-46)
+  const v3 dir = sc.cam_lower_left + sc.cam_horizontal * u + sc.cam_vertical * v - sc.cam_origin;
+  const v3 d = dir / mag(dir);
+  pool.ray_o[slot] = make_float4(sc.cam_origin.x, sc.cam_origin.y, sc.cam_origin.z, __uint_as_float(pixel));
+  pool.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(0u));
+  pool.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(sample));
+  pool.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  q.active[cur][wc->n_active[cur] + i] = slot;
+  if (i == 0) {
+    // single writer; every other thread only reads n_new / free_base / n_active, which k_prepare fixed
+    // (next_sample is advanced by the following k_prepare via n_new) -> done in k_advance to avoid a read/write race
+  }
+}
+__global__ void k_advance(WaveCounters* wc) { wc->next_sample += wc->n_new; }
+
+// ------------------------------------------------------------------------------------------ K8 closest hit + K11 queueing
+__global__ void __launch_bounds__(256)
+k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n = wc->n_trace;
+  const uint32_t* __restrict__ queue = q.active[wc->cur];
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&wc->trace_head, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const uint32_t i = base + lane;
+    uint32_t kind = 0xFFu;  // inactive lane
+    uint32_t slot = 0;
+    if (i < n) {
+      slot = queue[i];
+      const float4 o = pool.ray_o[slot], d = pool.ray_d[slot];
+      const Ray ray = make_ray(from4(o), from4(d));
+      const TraceResult tr = closest_hit(sc, ray);
+      pool.hit[slot] = make_uint2(__float_as_uint(tr.t), tr.ref);
+      kind = tr.ref == kNone ? 0u : 1u + (__ldg(sc.slot_mat + (tr.ref & kSlotMask)) >> 24);
+    }
+    // warp-aggregated push into the per-kind shade queues
+    const uint32_t peers = __match_any_sync(0xffffffffu, kind);
+    if (kind != 0xFFu) {
+      const uint32_t leader = __ffs(peers) - 1u;
+      uint32_t pos = 0;
+      if (lane == leader) pos = atomicAdd(&wc->n_kind[kind], __popc(peers));
+      pos = __shfl_sync(peers, pos, leader);
+      q.kind[kind][pos + __popc(peers & ((1u << lane) - 1u))] = slot;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K10 shade
+struct Surface {  // what the integrators read from `hit` + `mat`
+  HitRec h;
+  uint32_t kind, tex;
+  float param;
+  bool miss;
+};
+
+// rt_core/src/material.rs:20-26 + materials/lambertian.rs:42-47 / reflect.rs:37-39 / refract.rs:51-53
+PTB_DEV float mat_scattering_pdf(const Surface& s, v3 wi) {
+  if (s.kind == PTB_MAT_LAMBERTIAN) return fmaxf(dot(wi, s.h.normal), 0.0f) / kPi;
+  return 0.0f;  // Reflect / Refract keep the trait default (quirk Q4)
+}
+PTB_DEV v3 mat_eval(const DevScene& sc, const Surface& s, v3 wo, v3 wi) {
+  const v3 col = texture_colour(sc, s.tex, wo, s.h.point);
+  if (s.kind == PTB_MAT_LAMBERTIAN) return col * s.param * fmaxf(dot(s.h.normal, wi), 0.0f) / kPi;
+  return col;
+}
+
+PTB_DEV void finish_path(float* __restrict__ accum, uint32_t pixel, v3 L, bool nan_check) {
+  if (nan_check && (contains_nan(L) || !any_finite(L))) return;  // integrators/mod.rs:74-76, mis.rs:88-90
+  atomicAdd(accum + 3u * (size_t)pixel + 0, L.x);
+  atomicAdd(accum + 3u * (size_t)pixel + 1, L.y);
+  atomicAdd(accum + 3u * (size_t)pixel + 2, L.z);
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(256)
+k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  // locate (kind queue, offset) for work item i in the concatenation of the kind queues
+  uint32_t total = 0, kq = kNumKinds, off = 0;
+#pragma unroll
+  for (int k = 0; k < kNumKinds; ++k) {
+    const uint32_t c = wc->n_kind[k];
+    if (kq == (uint32_t)kNumKinds && i < total + c) { kq = k; off = i - total; }
+    total += c;
+  }
+  const bool active = kq != (uint32_t)kNumKinds;
+  const uint32_t nxt = wc->cur ^ 1u;
+
+  bool alive = false;     // path continues: goes to the next active queue
+  bool finished = false;  // path ended: slot returns to the free list
+  bool shadow = false;    // an NEE ray was produced
+  uint32_t slot = 0;
+  float4 sh_o, sh_d, sh_c;
+  uint32_t shadow_is_sky = 0;
+
+  if (active) {
+    slot = q.kind[kq][off];
+    const float4 ro = pool.ray_o[slot], rd = pool.ray_d[slot], th = pool.thr[slot], ra = pool.rad[slot];
+    const uint2 ht = pool.hit[slot];
+    const uint32_t pixel = __float_as_uint(ro.w), sample = __float_as_uint(th.w);
+    const uint32_t df = __float_as_uint(rd.w);
+    uint32_t depth = df & 0xFFu;
+    const bool prev_delta = (df & kFlagPrevDelta) != 0u;
+    const Ray ray = make_ray(from4(ro), from4(rd));
+    const v3 wo = ray.d;
+    v3 T = from4(th), L = from4(ra);
+
+    Surface s;
+    s.miss = ht.y == kNone;
+    if (s.miss) {  // sky.rs:79-91: zero Hit + Emit(sky texture, 1.0)
+      s.h.t = 0.0f;
+      s.h.point = s.h.error = s.h.normal = mk(0.0f, 0.0f, 0.0f);
+      s.h.out = false;
+      s.kind = PTB_MAT_EMIT;
+      s.tex = sc.sky_tex;
+      s.param = 1.0f;
+    } else {
+      prim_hit(sc, ray, ht.y, s.h);  // same arithmetic as the traversal: reproduces t, adds point/normal/error/out
+      const uint32_t mi = __ldg(sc.slot_mat + (ht.y & kSlotMask)) & 0x00FFFFFFu;
+      const DevMaterial* m = sc.materials + mi;
+      s.kind = __ldg(&m->kind);
+      s.tex = __ldg(&m->tex);
+      s.param = __ldg(&m->param);
+    }
+    const bool is_emit = s.kind == PTB_MAT_EMIT;
+    bool depart = false;
+    bool nan_check = true;
+
+    if (METHOD == PTB_METHOD_NAIVE) {
+      // integrators/mod.rs:29-72
+      if (is_emit) {
+        const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);        // emissive.rs:23-26
+        const v3 emission = s.param * texture_colour(sc, s.tex, wo, point);
+        L = L + T * emission;  // depth 0: throughput is exactly (1,1,1)
+        finished = true;
+      } else {
+        depart = true;
+      }
+    } else {
+      // integrators/mis.rs:17-31 (first hit) and :52-80 (after each bounce)
+      if (depth == 0u) {
+        if (is_emit) {
+          const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+          L = L + s.param * texture_colour(sc, s.tex, wo, point);
+          finished = true;
+          nan_check = false;  // mis.rs:29-31 returns before the NaN test
+        } else {
+          depth = 1u;
+          depart = true;
+        }
+      } else {
+        if (is_emit) {
+          // mis.rs:55: emission of the NEW material evaluated with the PREVIOUS hit record (quirk Q6); the
+          // previous hit's offset point is this ray's origin (lambertian.rs:37, reflect.rs:29)
+          const v3 le = s.param * texture_colour(sc, s.tex, wo, ray.o);
+          if (!is_zero(le)) {
+            const bool sky_samplable = (sc.sky_rx | sc.sky_ry) != 0u;
+            const bool use_mis = s.miss ? sky_samplable : !prev_delta;  // mis.rs:57-60 (an emissive prim is in `lights`)
+            if (use_mis) {
+              const float divisor = (float)(sky_samplable ? sc.n_lights + 1u : sc.n_lights);  // acceleration/mod.rs:299-318
+              const v3 prev_point = from4(pool.prev[slot]);
+              const float l_pdf = s.miss ? sky_pdf(sc, wo) / divisor
+                                         : light_pdf(sc, ht.y, prev_point, wo, s.h.point, s.h.normal) / divisor;
+              const float w = power_heuristic(ra.w, l_pdf);
+              L = L + T * le * w;
+            } else {
+              L = L + T * le;
+            }
+          }
+          finished = true;  // mis.rs:69-71
+        } else {
+          bool survive = true;
+          if (depth > rp.rr_threshold) {  // mis.rs:73-80
+            const float p = cmax3(T.x, T.y, T.z);
+            const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_RR, 0u, rp.k0, rp.k1);
+            if (u32_to_unit(r.x) > p) survive = false;
+            else T = T / p;
+          }
+          depth += 1u;
+          if (survive && depth < rp.max_depth) depart = true;
+          else finished = true;
+        }
+      }
+    }
+
+    if (depart) {
+      float m_pdf = 0.0f;
+      // ---- next-event estimation (MIS only): integrators/mis.rs:36-43, 95-157
+      if (METHOD == PTB_METHOD_MIS) {
+        const uint32_t n_l = sc.n_lights;
+        const bool sky_s = (sc.sky_rx | sc.sky_ry) != 0u;
+        if (n_l != 0u || sky_s) {
+          const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_NEE, 0u, rp.k0, rp.k1);
+          bool do_sky;
+          float mult;
+          uint32_t li = 0;
+          if (n_l == 0u) { do_sky = true; mult = 1.0f; }
+          else if (!sky_s) { do_sky = false; mult = 1.0f / (float)n_l; li = rng_below(r.x, n_l); }
+          else { mult = 1.0f / (float)(n_l + 1u); li = rng_below(r.x, n_l + 1u); do_sky = li == n_l; }
+          const v3 so = s.h.point + 0.0001f * s.h.normal;  // mis.rs:106,124
+          v3 l_wi, le;
+          float l_pdf = 0.0f, tmax = __int_as_float(0x7f800000);
+          uint32_t exclude = kNone;
+          bool usable = false;
+          if (do_sky) {
+            const uint4 r2 = philox4x32_10(pixel, sample, (depth << 8) | RNG_NEE, 1u, rp.k0, rp.k1);
+            l_wi = sky_sample(sc, u32_to_unit(r.y), u32_to_unit(r.z), u32_to_unit(r.w), u32_to_unit(r2.x));
+            const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+            le = 1.0f * texture_colour(sc, sc.sky_tex, l_wi, point);
+            l_pdf = sky_pdf(sc, l_wi) * mult;
+            usable = true;
+            shadow_is_sky = 1u;
+          } else {
+            const uint32_t lref = __ldg(sc.lights + li);
+            l_wi = light_sample_dir(sc, lref, s.h.point, u32_to_unit(r.y), u32_to_unit(r.z));
+            const Ray sray = make_ray_from_raw(so, l_wi);
+            HitRec si;
+            if (prim_hit(sc, sray, lref, si) && si.t > 0.0f) {  // acceleration/mod.rs:231-243
+              const float pdf = light_pdf(sc, lref, s.h.point, l_wi, si.point, si.normal);
+              if (pdf > 0.0f) {
+                const uint32_t lmi = __ldg(sc.slot_mat + (lref & kSlotMask)) & 0x00FFFFFFu;
+                const DevMaterial* lm = sc.materials + lmi;
+                const v3 lpoint = offset_ray(si.point, si.normal, si.error, true);
+                le = __ldg(&lm->param) * texture_colour(sc, __ldg(&lm->tex), l_wi, lpoint);
+                l_pdf = pdf * mult;
+                tmax = si.t;
+                exclude = lref & kSlotMask;
+                usable = true;
+              }
+            }
+          }
+          if (usable) {
+            const float mp = mat_scattering_pdf(s, l_wi);
+            const float w = power_heuristic(l_pdf, mp);
+            const v3 contrib = T * mat_eval(sc, s, wo, l_wi) * w * le / l_pdf;  // mis.rs:42
+            const v3 sd = l_wi / mag(l_wi);  // Ray::new normalises (ray.rs:14)
+            sh_o = make_float4(so.x, so.y, so.z, tmax);
+            sh_d = make_float4(sd.x, sd.y, sd.z, __uint_as_float(exclude));
+            sh_c = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(slot));
+            shadow = true;
+          }
+        }
+      }
+      // ---- BSDF sample -> next ray
+      const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_SCATTER, 0u, rp.k0, rp.k1);
+      v3 new_o, new_dir;
+      bool delta = false;
+      if (s.kind == PTB_MAT_LAMBERTIAN) {
+        // lambertian.rs:30-41, statistics/bxdfs/lambertian.rs:5-18, utility/coord.rs:10-30
+        const float cos_theta = sqrtf(1.0f - u32_to_unit(r.x));
+        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        const float phi = 2.0f * kPi * u32_to_unit(r.y);
+        new_dir = onb_to_world(s.h.normal, mk(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cos_theta));
+        new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+      } else if (s.kind == PTB_MAT_REFLECT) {
+        // reflect.rs:26-36; random_unit_vector (utility/mod.rs:15-25) is a rejection loop whose result is uniform on
+        // the sphere — drawn directly here from two uniforms (fixed RNG budget), same distribution
+        const float z = 1.0f - 2.0f * u32_to_unit(r.x);
+        const float rr = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+        const float phi = 2.0f * kPi * u32_to_unit(r.y);
+        const v3 unit = mk(rr * cosf(phi), rr * sinf(phi), z);
+        new_dir = reflected(-wo, s.h.normal) + s.param * unit;
+        new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+        delta = true;
+      } else {  // PTB_MAT_REFRACT — refract.rs:27-50
+        float eta_fraction = 1.0f / s.param;
+        if (!s.h.out) eta_fraction = s.param;
+        const float cos_theta = fminf(dot(-wo, s.h.normal), 1.0f);
+        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        const bool cannot_refract = eta_fraction * sin_theta > 1.0f;
+        float f0 = (1.0f - eta_fraction) / (1.0f + eta_fraction);
+        f0 = f0 * f0 * 1.0f;
+        const float fres = f0 + (1.0f - f0) * powf(1.0f - cos_theta, 5.0f);  // refract.rs:59-61
+        if (cannot_refract || fres > u32_to_unit(r.x)) {
+          new_dir = reflected(-wo, s.h.normal);  // Reflect{fuzz: 0}: the unit vector is multiplied by 0
+          new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+        } else {
+          const v3 perp = eta_fraction * (wo + cos_theta * s.h.normal);
+          const v3 para = -1.0f * sqrtf(fabsf(1.0f - mag_sq(perp))) * s.h.normal;
+          new_dir = perp + para;
+          new_o = offset_ray(s.h.point, s.h.normal, s.h.error, false);
+        }
+        delta = true;
+      }
+      const v3 nd = new_dir / mag(new_dir);  // Ray::new
+      const v3 col = texture_colour(sc, s.tex, wo, s.h.point);
+      if (METHOD == PTB_METHOD_NAIVE) {
+        // integrators/mod.rs:57-70
+        if (s.kind == PTB_MAT_LAMBERTIAN) T = T * (col * s.param);
+        else T = T * col;
+        bool survive = true;
+        if (depth > rp.rr_threshold) {
+          const float p = cmax3(T.x, T.y, T.z);
+          const uint4 r3 = philox4x32_10(pixel, sample, (depth << 8) | RNG_RR, 0u, rp.k0, rp.k1);
+          if (u32_to_unit(r3.x) > p) survive = false;
+          else T = T / p;
+        }
+        depth += 1u;
+        if (survive && depth < rp.max_depth) alive = true;
+        else finished = true;
+      } else {
+        // mis.rs:54-56: m_pdf and throughput use the previous hit only, so they are folded in at departure
+        if (s.kind == PTB_MAT_LAMBERTIAN) {
+          m_pdf = fmaxf(dot(nd, s.h.normal), 0.0f) / kPi;
+          T = T * (col * s.param);
+        } else {
+          m_pdf = 0.0f;
+          T = T * (col / 0.0f);  // eval / scattering_pdf with the default pdf 0 (quirk Q4)
+        }
+        pool.prev[slot] = make_float4(s.h.point.x, s.h.point.y, s.h.point.z, 0.0f);
+        alive = true;
+      }
+      if (alive) {
+        pool.ray_o[slot] = make_float4(new_o.x, new_o.y, new_o.z, ro.w);
+        pool.ray_d[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(depth | (delta ? kFlagPrevDelta : 0u)));
+        pool.thr[slot] = make_float4(T.x, T.y, T.z, th.w);
+        pool.rad[slot] = make_float4(L.x, L.y, L.z, m_pdf);
+      }
+    }
+    if (finished) finish_path(accum, pixel, L, nan_check);
+  }
+
+  // ---- warp-aggregated queue pushes
+  {
+    const uint32_t m = __ballot_sync(0xffffffffu, alive);
+    if (m) {
+      uint32_t pos = 0;
+      const uint32_t leader = __ffs(m) - 1u;
+      if (lane == leader) pos = atomicAdd(&wc->n_active[nxt], __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, leader);
+      if (alive) q.active[nxt][pos + __popc(m & ((1u << lane) - 1u))] = slot;
+    }
+  }
+  {
+    const uint32_t m = __ballot_sync(0xffffffffu, finished);
+    if (m) {
+      uint32_t pos = 0;
+      const uint32_t leader = __ffs(m) - 1u;
+      if (lane == leader) pos = atomicAdd(&wc->n_free, __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, leader);
+      if (finished) q.free_slots[pos + __popc(m & ((1u << lane) - 1u))] = slot;
+    }
+  }
+  if (METHOD == PTB_METHOD_MIS) {
+    const uint32_t m = __ballot_sync(0xffffffffu, shadow);
+    if (m) {
+      uint32_t pos = 0;
+      const uint32_t leader = __ffs(m) - 1u;
+      const uint32_t n_sky = __popc(__ballot_sync(0xffffffffu, shadow && shadow_is_sky));
+      if (lane == leader) {
+        pos = atomicAdd(&wc->n_shadow, __popc(m));
+        if (n_sky) atomicAdd(&wc->rays_shadow_sky, (unsigned long long)n_sky);
+        if (__popc(m) - n_sky) atomicAdd(&wc->rays_shadow_light, (unsigned long long)(__popc(m) - n_sky));
+      }
+      pos = __shfl_sync(0xffffffffu, pos, leader);
+      if (shadow) {
+        float4* e = q.shadow + 3u * (size_t)(pos + __popc(m & ((1u << lane) - 1u)));
+        e[0] = sh_o;
+        e[1] = sh_d;
+        e[2] = sh_c;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K9 shadow rays
+__global__ void __launch_bounds__(256) k_shadow(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n = wc->n_shadow;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&wc->shadow_head, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const uint32_t i = base + lane;
+    if (i >= n) continue;
+    const float4* e = q.shadow + 3u * (size_t)i;
+    const float4 o = e[0], d = e[1], cc = e[2];
+    const Ray ray = make_ray(from4(o), from4(d));
+    if (!occluded(sc, ray, o.w, __float_as_uint(d.w))) {
+      const uint32_t slot = __float_as_uint(cc.w);
+      float4 ra = pool.rad[slot];
+      ra.x += cc.x; ra.y += cc.y; ra.z += cc.z;  // output += throughput * eval * mis_weight * le / l_pdf (mis.rs:42)
+      pool.rad[slot] = ra;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ closest-hit API kernel
+// check_hit for a batch of caller rays (acceleration/mod.rs:265-298): 2 x float4 in, 16 B out.
+__global__ void __launch_bounds__(256)
+k_closest_hit_api(DevScene sc, const float4* __restrict__ rays, uint32_t n, uint4* __restrict__ hits, uint32_t* head) {
+  const uint32_t lane = threadIdx.x & 31u;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(head, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const uint32_t i = base + lane;
+    if (i >= n) continue;
+    const float4 o = __ldg(rays + 2u * (size_t)i), d = __ldg(rays + 2u * (size_t)i + 1u);
+    const Ray ray = make_ray_from_raw(from4(o), from4(d));
+    const TraceResult tr = closest_hit(sc, ray);
+    uint4 out = make_uint4(__float_as_uint(0.0f), PTB_MISS, 0u, 0u);
+    if (tr.ref != kNone) {
+      HitRec h;
+      prim_hit(sc, ray, tr.ref, h);
+      out = make_uint4(__float_as_uint(tr.t), __ldg(sc.slot_prim + (tr.ref & kSlotMask)), __float_as_uint(h.b1),
+                       __float_as_uint(h.b2));
+    }
+    hits[i] = out;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static int persistent_grid(Ctx* c, const void* kernel, int threads) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return c->sm_count * per_sm;
+}
+
+int32_t launch_closest_hit(Ctx* c, const void* d_rays, size_t n, void* d_hits) {
+  if (n == 0) return PTB_OK;
+  if (n > 0xFFFFFFF0ull) return set_error(c, PTB_ERR_INVALID, "too many rays in one batch");
+  PTB_CUDA_TRY(c, c->d_counters.reserve(sizeof(WaveCounters) + 64));
+  uint32_t* head = reinterpret_cast<uint32_t*>(c->d_counters.as<char>() + sizeof(WaveCounters));
+  PTB_CUDA_TRY(c, cudaMemsetAsync(head, 0, 4, c->stream));
+  const int grid = persistent_grid(c, (const void*)k_closest_hit_api, 256);
+  k_closest_hit_api<<<grid, 256, 0, c->stream>>>(c->dev, reinterpret_cast<const float4*>(d_rays), (uint32_t)n,
+                                                 reinterpret_cast<uint4*>(d_hits), head);
+  c->stats.kernel_launches += 1;
+  PTB_CUDA_TRY(c, cudaGetLastError());
+  return PTB_OK;
+}
+
+void free_render_state(Ctx* c) {
+  c->d_pool_mem.release();
+  c->d_queues.release();
+  c->d_shadow.release();
+  c->pool = PathPool();
+}
+
+static uint32_t pool_capacity_for(unsigned long long total) {
+  unsigned long long cap = 1ull << 21;  // 2 Mi paths in flight (~190 MB of path state)
+  if (const char* e = getenv("PTB_POOL_PATHS")) {
+    unsigned long long v = strtoull(e, nullptr, 10);
+    if (v >= 1024 && v <= (1ull << 26)) cap = v;
+  }
+  if (total < cap) cap = total < 1024 ? 1024 : total;
+  return (uint32_t)((cap + 255ull) & ~255ull);
+}
+
+int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progress, void* user) {
+  cudaStream_t st = c->stream;
+  const uint32_t npix = o.width * o.height;
+  const unsigned long long total = (unsigned long long)npix * o.samples_per_pixel;
+  if (total == 0) return PTB_OK;
+  const uint32_t P = pool_capacity_for(total);
+
+  // ---- device state (grow-only across calls)
+  if (c->pool.capacity != P) {
+    const size_t pool_bytes = (size_t)P * (5 * 16 + 8);
+    PTB_CUDA_TRY(c, c->d_pool_mem.reserve(pool_bytes));
+    char* b = c->d_pool_mem.as<char>();
+    c->pool.capacity = P;
+    c->pool.ray_o = reinterpret_cast<float4*>(b); b += (size_t)P * 16;
+    c->pool.ray_d = reinterpret_cast<float4*>(b); b += (size_t)P * 16;
+    c->pool.thr = reinterpret_cast<float4*>(b); b += (size_t)P * 16;
+    c->pool.rad = reinterpret_cast<float4*>(b); b += (size_t)P * 16;
+    c->pool.prev = reinterpret_cast<float4*>(b); b += (size_t)P * 16;
+    c->pool.hit = reinterpret_cast<uint2*>(b);
+    PTB_CUDA_TRY(c, c->d_queues.reserve((size_t)P * 4 * (3 + kNumKinds)));
+    PTB_CUDA_TRY(c, c->d_shadow.reserve((size_t)P * 48));
+  }
+  PTB_CUDA_TRY(c, c->d_counters.reserve(sizeof(WaveCounters) + 64));
+  Queues q;
+  {
+    uint32_t* b = c->d_queues.as<uint32_t>();
+    q.active[0] = b; b += P;
+    q.active[1] = b; b += P;
+    q.free_slots = b; b += P;
+    for (int k = 0; k < kNumKinds; ++k) { q.kind[k] = b; b += P; }
+    q.shadow = c->d_shadow.as<float4>();
+  }
+  WaveCounters* wc = c->d_counters.as<WaveCounters>();
+  if (!c->h_counters) PTB_CUDA_TRY(c, cudaMallocHost(&c->h_counters, 2 * sizeof(WaveCounters)));
+
+  RenderParams rp;
+  rp.width = o.width; rp.height = o.height; rp.npix = npix;
+  rp.sample_offset = o.sample_offset;
+  rp.method = o.method;
+  rp.max_depth = o.max_depth ? o.max_depth : 50u;
+  if (rp.max_depth > 255u) return set_error(c, PTB_ERR_INVALID, "max_depth must be <= 255");
+  rp.rr_threshold = o.rr_threshold == PTB_RR_DEFAULT ? 3u : o.rr_threshold;
+  rp.k0 = (uint32_t)o.seed; rp.k1 = (uint32_t)(o.seed >> 32);
+
+  float* accum = c->d_accum.as<float>();
+  const int T = 256;
+  const uint32_t grid_p = (P + T - 1) / T;
+  const int grid_trace = persistent_grid(c, (const void*)k_trace, T);
+  const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
+  const bool mis = o.method == PTB_METHOD_MIS;
+
+  PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
+  k_init_pool<<<grid_p, T, 0, st>>>(q.free_slots, P, wc, total);
+  c->stats.kernel_launches += 1;
+
+  int32_t rc = PTB_OK;
+  uint64_t iter = 0;
+  uint64_t last_pass_reported = 0;
+  bool done = false;
+  // Two pinned mirrors + events so the host inspects iteration k-1 while iteration k runs.
+  cudaEvent_t ev[2] = {c->ev_iter, c->ev_b};
+  while (!done) {
+    k_prepare<<<1, 1, 0, st>>>(wc, o.method, iter == 0 ? 1u : 0u);
+    k_generate<<<grid_p, T, 0, st>>>(c->dev, c->pool, q, wc, rp);
+    k_advance<<<1, 1, 0, st>>>(wc);
+    k_trace<<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
+    if (mis) k_shade<PTB_METHOD_MIS><<<grid_p, T, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+    else k_shade<PTB_METHOD_NAIVE><<<grid_p, T, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+    c->stats.kernel_launches += 5;
+    if (mis) {
+      k_shadow<<<grid_shadow, T, 0, st>>>(c->dev, c->pool, q, wc);
+      c->stats.kernel_launches += 1;
+    }
+    const int slot = (int)(iter & 1u);
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + slot, wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+    PTB_CUDA_TRY(c, cudaEventRecord(ev[slot], st));
+    if (iter > 0) {  // inspect the previous iteration (already finished or about to)
+      const int ps = slot ^ 1;
+      PTB_CUDA_TRY(c, cudaEventSynchronize(ev[ps]));
+      const WaveCounters& h = c->h_counters[ps];
+      if (h.next_sample >= h.total_samples && h.n_active[h.cur ^ 1u] == 0) done = true;
+      if (progress && !done) {
+        const uint64_t passes = h.next_sample / npix;
+        if (passes != last_pass_reported) {
+          last_pass_reported = passes;
+          if (progress(user, passes, h.rays_reference)) { rc = PTB_ERR_ABORTED; done = true; }
+        }
+      }
+    }
+    ++iter;
+    if (iter > (1ull << 40)) return set_error(c, PTB_ERR_INVALID, "wavefront did not terminate");
+  }
+  // fold the last iteration's counts into the statistics
+  k_prepare<<<1, 1, 0, st>>>(wc, o.method, 0u);
+  c->stats.kernel_launches += 1;
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+  PTB_CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
+  PTB_CUDA_TRY(c, cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+  const WaveCounters& h = c->h_counters[0];
+  c->stats.rays_camera += h.rays_camera;
+  c->stats.rays_bounce += h.rays_bounce;
+  c->stats.rays_shadow_light += h.rays_shadow_light;
+  c->stats.rays_shadow_sky += h.rays_shadow_sky;
+  c->stats.rays_reference += h.rays_reference;
+  c->stats.paths += h.paths;
+  c->stats.wavefront_iterations += iter;
+  c->stats.render_ms = ms;
+  if (rc == PTB_OK) {
+    c->accum_samples += o.samples_per_pixel;
+    if (progress) progress(user, o.samples_per_pixel, h.rays_reference);
+  }
+  return rc;
+}
+
+}  // namespace ptb

@@ -165,8 +165,16 @@ typedef struct ptb_stats {
   uint64_t paths;              /* camera paths finished                                       */
   uint64_t wavefront_iterations;
   uint64_t kernel_launches;    /* kernels of this library launched since the last ptb_stats_reset */
+  uint64_t nodes_fetched;      /* PTB_OPT_COUNT_TRAVERSAL: 64-byte BVH nodes fetched by closest-hit traversals */
+  uint64_t prims_tested;       /* PTB_OPT_COUNT_TRAVERSAL: primitives tested by closest-hit traversals          */
+  uint64_t rays_counted;       /* PTB_OPT_COUNT_TRAVERSAL: closest-hit traversals the two counters cover        */
+  uint64_t trace_launches;     /* closest-hit kernel launches (k_trace / k_closest_hit_api)                     */
   double   build_ms;           /* last ptb_scene_commit: device LBVH build time               */
   double   render_ms;          /* last ptb_render: device time (CUDA events)                  */
+  double   ms_generate;        /* PTB_OPT_TIME_KERNELS: summed CUDA-event time per kernel class */
+  double   ms_trace;
+  double   ms_shade;
+  double   ms_shadow;
 } ptb_stats;
 
 typedef struct ptb_ctx ptb_ctx;
@@ -183,6 +191,9 @@ int32_t     ptb_destroy(ptb_ctx* ctx);
 const char* ptb_last_error(const ptb_ctx* ctx);           /* ctx may be NULL: last error of ptb_create */
 int32_t     ptb_set_stream(ptb_ctx* ctx, void* cuda_stream); /* optional: run on the caller's cudaStream_t */
 int32_t     ptb_synchronize(ptb_ctx* ctx);
+/* Measurement switches (off by default; they add event records / atomic counters to the hot path). */
+enum { PTB_OPT_TIME_KERNELS = 1, PTB_OPT_COUNT_TRAVERSAL = 2 };
+int32_t     ptb_set_option(ptb_ctx* ctx, uint32_t option, uint32_t value);
 
 /* ---------------------------------------------------------------- scene -- */
 /* Replaces what loader::load_file_full returns (loader/lib.rs:196-243) + Bvh::new's input

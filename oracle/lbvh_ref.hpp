@@ -142,23 +142,34 @@ struct Lbvh {
     }
   }
 
-  // Slab test of aabb.rs:22-57 with the device's additions: entry distance returned, culled against best t.
-  static inline bool box_hit(const float* mn, const float* mx, const Ray& ray, Float best_t, Float& tnear) {
+  // Slab test of aabb.rs:22-57 with the device's additions: the box is culled only when its entry distance, less an
+  // error slack of 32*eps*(largest finite slab distance), exceeds best t. The slack keeps a primitive whose COMPUTED t
+  // rounds to just before its own box's computed entry (the reference never culls by t). `tkey` is that cull key.
+  static inline bool box_hit(const float* mn, const float* mx, const Ray& ray, Float best_t, Float& tkey) {
     const Float k = 1.0f + 2.0f * gamma(3);
+    const Float slack = 32.0f * F32_EPS;
     Float t1 = (mn[0] - ray.origin.x) * ray.d_inverse.x;
     Float t2 = (mx[0] - ray.origin.x) * ray.d_inverse.x;
-    Float tmin = fmin_(t1, t2);
-    Float tmax = fmax_(t1, t2) * k;
+    Float lo = fmin_(t1, t2), hi = fmax_(t1, t2);
+    Float tmin = lo;
+    Float tmax = hi * k;
+    const Float m_x = fmax_(hi, -lo);
     t1 = (mn[1] - ray.origin.y) * ray.d_inverse.y;
     t2 = (mx[1] - ray.origin.y) * ray.d_inverse.y;
-    tmin = fmax_(tmin, fmin_(t1, t2));
-    tmax = fmin_(tmax, fmax_(t1, t2) * k);
+    lo = fmin_(t1, t2); hi = fmax_(t1, t2);
+    tmin = fmax_(tmin, lo);
+    tmax = fmin_(tmax, hi * k);
+    const Float m_y = fmax_(hi, -lo);
     t1 = (mn[2] - ray.origin.z) * ray.d_inverse.z;
     t2 = (mx[2] - ray.origin.z) * ray.d_inverse.z;
-    tmin = fmax_(tmin, fmin_(t1, t2));
-    tmax = fmin_(tmax, fmax_(t1, t2) * k);
-    tnear = tmin;
-    return tmax > fmax_(tmin, 0.0f) && tmin <= best_t;
+    lo = fmin_(t1, t2); hi = fmax_(t1, t2);
+    tmin = fmax_(tmin, lo);
+    tmax = fmin_(tmax, hi * k);
+    const Float m_z = fmax_(hi, -lo);
+    Float m = fmax_(m_x, fmax_(m_y, m_z));
+    if (!(m < 3.0e38f)) m = fmax_(m_x < 3.0e38f ? m_x : 0.0f, fmax_(m_y < 3.0e38f ? m_y : 0.0f, m_z < 3.0e38f ? m_z : 0.0f));
+    tkey = tmin - slack * m;
+    return tmax > fmax_(tmin, 0.0f) && tkey <= best_t;
   }
 
   // Ordered (near child first), t-culled closest hit. Ties on t go to the lower ORIGINAL primitive id.

@@ -25,6 +25,7 @@ PTB_RR_DEFAULT = 0xFFFFFFFF
 MAT_EMIT, MAT_LAMBERTIAN, MAT_TROWBRIDGE_REITZ, MAT_REFLECT, MAT_REFRACT = range(5)
 TEX_CHECKERED, TEX_SOLID, TEX_IMAGE, TEX_LERP, TEX_PERLIN = range(5)
 METHOD_NAIVE, METHOD_MIS = 0, 1
+OPT_TIME_KERNELS, OPT_COUNT_TRAVERSAL = 1, 2
 
 # numpy mirrors of the POD structs (sizes asserted against the header's layout in tests/test_abi.py)
 sphere_dtype = np.dtype([("center", "<f4", 3), ("radius", "<f4"), ("material", "<u4")])
@@ -48,8 +49,10 @@ class RenderOpts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays_camera", C.c_uint64), ("rays_bounce", C.c_uint64), ("rays_shadow_light", C.c_uint64),
                 ("rays_shadow_sky", C.c_uint64), ("rays_reference", C.c_uint64), ("paths", C.c_uint64),
-                ("wavefront_iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("build_ms", C.c_double),
-                ("render_ms", C.c_double)]
+                ("wavefront_iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("nodes_fetched", C.c_uint64),
+                ("prims_tested", C.c_uint64), ("rays_counted", C.c_uint64), ("trace_launches", C.c_uint64),
+                ("build_ms", C.c_double), ("render_ms", C.c_double), ("ms_generate", C.c_double),
+                ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("ms_shadow", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -76,6 +79,7 @@ SYMBOLS = [
     ("ptb_last_error", C.c_char_p, [_P]),
     ("ptb_set_stream", C.c_int32, [_P, _P]),
     ("ptb_synchronize", C.c_int32, [_P]),
+    ("ptb_set_option", C.c_int32, [_P, C.c_uint32, C.c_uint32]),
     ("ptb_scene_set_spheres", C.c_int32, [_P, _P, C.c_size_t]),
     ("ptb_scene_set_triangles", C.c_int32, [_P, _P, C.c_size_t]),
     ("ptb_scene_set_materials", C.c_int32, [_P, _P, C.c_size_t]),

@@ -75,6 +75,9 @@ class Context:
     def set_stream(self, cuda_stream_ptr: int):
         _check(self._h, L.lib.ptb_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_option(self, option: int, value: int):
+        _check(self._h, L.lib.ptb_set_option(self._h, option, value))
+
     def synchronize(self):
         _check(self._h, L.lib.ptb_synchronize(self._h))
 

@@ -102,6 +102,8 @@ int32_t ptb_destroy(ptb_ctx* ctx) {
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
   if (c->ev_iter) cudaEventDestroy(c->ev_iter);
+  for (cudaEvent_t e : c->ev_prof)
+    if (e) cudaEventDestroy(e);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete ctx;  // DevBuf destructors release device memory
   return PTB_OK;
@@ -115,6 +117,14 @@ int32_t ptb_set_stream(ptb_ctx* ctx, void* cuda_stream) {
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
   c->own_stream = false;
+  return PTB_OK;
+}
+
+int32_t ptb_set_option(ptb_ctx* ctx, uint32_t option, uint32_t value) {
+  CTX_OR_FAIL(ctx);
+  if (option == PTB_OPT_TIME_KERNELS) c->opt_time_kernels = value != 0;
+  else if (option == PTB_OPT_COUNT_TRAVERSAL) c->opt_count_traversal = value != 0;
+  else return set_error(c, PTB_ERR_INVALID, "unknown option %u", option);
   return PTB_OK;
 }
 

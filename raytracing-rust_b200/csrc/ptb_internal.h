@@ -65,6 +65,7 @@ struct WaveCounters {  // lives in device memory; mirrored to pinned host memory
   unsigned long long total_samples;
   // statistics (ptb_stats)
   unsigned long long rays_camera, rays_bounce, rays_shadow_light, rays_shadow_sky, rays_reference, paths;
+  unsigned long long nodes_fetched, prims_tested, rays_counted;  // PTB_OPT_COUNT_TRAVERSAL
 };
 
 struct Ctx {
@@ -98,6 +99,8 @@ struct Ctx {
   PathPool pool;
   WaveCounters* h_counters = nullptr;  // pinned
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_iter = nullptr;
+  cudaEvent_t ev_prof[16] = {};  // PTB_OPT_TIME_KERNELS: 2 iterations x 4 kernel classes x (start, stop)
+  bool opt_time_kernels = false, opt_count_traversal = false;
 
   // closest-hit staging
   DevBuf d_rays, d_hits;

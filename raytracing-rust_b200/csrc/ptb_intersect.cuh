@@ -151,24 +151,40 @@ PTB_DEV bool prim_hit(const DevScene& sc, const Ray& ray, uint32_t ref, HitRec& 
 }
 
 // ---- box -----------------------------------------------------------------------------------------------------------------
-// hit when the reference's does_int would accept the box AND its entry distance does not exceed best_t.
+// Accepts the box when the reference's does_int would (far side widened by 1+2*gamma(3), entry < exit, exit > 0) AND
+// its entry distance cannot exclude a hit closer than best_t. `tkey` = entry distance minus an error slack: a
+// primitive's COMPUTED t may fall slightly before its box's computed entry (e.g. the radius-1000 ground spheres of the
+// shipped scenes: |t error| ~ 1e-5), and the reference never culls by t, so culling must not either in that band.
+// The slack is kCullSlack * (largest finite slab distance of this box), which bounds the magnitude of the terms the
+// sphere quadratic / watertight triangle test (its own bound is delta_t, triangle.rs:160-177) round off.
+constexpr float kCullSlack = 32.0f * kF32Eps;
 PTB_DEV bool box_entry(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Ray& ray, float best_t,
-                       float& tnear) {
+                       float& tkey) {
   const float k = 1.0f + 2.0f * gamma_n(3);
   float t1 = (mnx - ray.o.x) * ray.dinv.x;
   float t2 = (mxx - ray.o.x) * ray.dinv.x;
-  float tmin = fminf(t1, t2);
-  float tmax = fmaxf(t1, t2) * k;
+  float lo = fminf(t1, t2), hi = fmaxf(t1, t2);
+  float tmin = lo;
+  float tmax = hi * k;
+  const float mx = fmaxf(hi, -lo);
   t1 = (mny - ray.o.y) * ray.dinv.y;
   t2 = (mxy - ray.o.y) * ray.dinv.y;
-  tmin = fmaxf(tmin, fminf(t1, t2));
-  tmax = fminf(tmax, fmaxf(t1, t2) * k);
+  lo = fminf(t1, t2); hi = fmaxf(t1, t2);
+  tmin = fmaxf(tmin, lo);
+  tmax = fminf(tmax, hi * k);
+  const float my = fmaxf(hi, -lo);
   t1 = (mnz - ray.o.z) * ray.dinv.z;
   t2 = (mxz - ray.o.z) * ray.dinv.z;
-  tmin = fmaxf(tmin, fminf(t1, t2));
-  tmax = fminf(tmax, fmaxf(t1, t2) * k);
-  tnear = tmin;
-  return tmax > fmaxf(tmin, 0.0f) && tmin <= best_t;
+  lo = fminf(t1, t2); hi = fmaxf(t1, t2);
+  tmin = fmaxf(tmin, lo);
+  tmax = fminf(tmax, hi * k);
+  const float mz = fmaxf(hi, -lo);
+  float m = fmaxf(mx, fmaxf(my, mz));
+  if (!(m < 3.0e38f)) {  // axis-parallel ray: ignore the slabs it never crosses
+    m = fmaxf(mx < 3.0e38f ? mx : 0.0f, fmaxf(my < 3.0e38f ? my : 0.0f, mz < 3.0e38f ? mz : 0.0f));
+  }
+  tkey = tmin - kCullSlack * m;
+  return tmax > fmaxf(tmin, 0.0f) && tkey <= best_t;
 }
 
 }  // namespace ptb

@@ -27,7 +27,10 @@ PTB_DEV void load_node(const BvhNode* __restrict__ nodes, uint32_t idx, float4& 
   n3 = __ldg(reinterpret_cast<const uint4*>(p + 3));
 }
 
-PTB_DEV TraceResult closest_hit(const DevScene& sc, const Ray& ray) {
+// COUNT: also report how many 64-byte nodes were fetched and how many primitives were tested (the V and T of the
+// algorithmic-bytes-per-ray figure); compiled out otherwise.
+template <bool COUNT>
+PTB_DEV TraceResult closest_hit_t(const DevScene& sc, const Ray& ray, uint32_t& n_nodes, uint32_t& n_prims) {
   TraceResult res;
   res.t = 0.0f;
   res.ref = kNone;
@@ -41,6 +44,7 @@ PTB_DEV TraceResult closest_hit(const DevScene& sc, const Ray& ray) {
   for (;;) {
     if (cur & PTB_LEAF_BIT) {
       const float t = prim_t(sc, ray, cur);
+      if (COUNT) ++n_prims;
       if (t > 0.0f) {
         if (t < best_t) {
           best_t = t;
@@ -62,6 +66,7 @@ PTB_DEV TraceResult closest_hit(const DevScene& sc, const Ray& ray) {
     float4 n0, n1, n2;
     uint4 n3;
     load_node(sc.nodes, cur, n0, n1, n2, n3);
+    if (COUNT) ++n_nodes;
     float tl, tr;
     const bool hl = box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ray, best_t, tl);
     const bool hr = box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ray, best_t, tr);
@@ -91,6 +96,11 @@ PTB_DEV TraceResult closest_hit(const DevScene& sc, const Ray& ray) {
     res.ref = best_ref & ~PTB_LEAF_BIT;
   }
   return res;
+}
+
+PTB_DEV TraceResult closest_hit(const DevScene& sc, const Ray& ray) {
+  uint32_t a = 0, b = 0;
+  return closest_hit_t<false>(sc, ray, a, b);
 }
 
 // true when some primitive other than `exclude_slot` is hit with 0 < t < tmax

@@ -177,6 +177,7 @@ __global__ void k_init_pool(uint32_t* free_slots, uint32_t capacity, WaveCounter
     wc->next_sample = 0;
     wc->total_samples = total_samples;
     wc->rays_camera = wc->rays_bounce = wc->rays_shadow_light = wc->rays_shadow_sky = wc->rays_reference = wc->paths = 0;
+    wc->nodes_fetched = wc->prims_tested = wc->rays_counted = 0;
   }
 }
 
@@ -238,9 +239,11 @@ k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams 
 __global__ void k_advance(WaveCounters* wc) { wc->next_sample += wc->n_new; }
 
 // ------------------------------------------------------------------------------------------ K8 closest hit + K11 queueing
+template <bool COUNT>
 __global__ void __launch_bounds__(256)
 k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
   const uint32_t lane = threadIdx.x & 31u;
+  uint32_t cnt_nodes = 0, cnt_prims = 0, cnt_rays = 0;
   const uint32_t n = wc->n_trace;
   const uint32_t* __restrict__ queue = q.active[wc->cur];
   for (;;) {
@@ -255,7 +258,8 @@ k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
       slot = queue[i];
       const float4 o = pool.ray_o[slot], d = pool.ray_d[slot];
       const Ray ray = make_ray(from4(o), from4(d));
-      const TraceResult tr = closest_hit(sc, ray);
+      const TraceResult tr = closest_hit_t<COUNT>(sc, ray, cnt_nodes, cnt_prims);
+      if (COUNT) ++cnt_rays;
       pool.hit[slot] = make_uint2(__float_as_uint(tr.t), tr.ref);
       kind = tr.ref == kNone ? 0u : 1u + (__ldg(sc.slot_mat + (tr.ref & kSlotMask)) >> 24);
     }
@@ -267,6 +271,18 @@ k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
       if (lane == leader) pos = atomicAdd(&wc->n_kind[kind], __popc(peers));
       pos = __shfl_sync(peers, pos, leader);
       q.kind[kind][pos + __popc(peers & ((1u << lane) - 1u))] = slot;
+    }
+  }
+  if (COUNT) {
+    for (int off = 16; off > 0; off >>= 1) {
+      cnt_nodes += __shfl_xor_sync(0xffffffffu, cnt_nodes, off);
+      cnt_prims += __shfl_xor_sync(0xffffffffu, cnt_prims, off);
+      cnt_rays += __shfl_xor_sync(0xffffffffu, cnt_rays, off);
+    }
+    if (lane == 0 && cnt_rays) {
+      atomicAdd(&wc->nodes_fetched, (unsigned long long)cnt_nodes);
+      atomicAdd(&wc->prims_tested, (unsigned long long)cnt_prims);
+      atomicAdd(&wc->rays_counted, (unsigned long long)cnt_rays);
     }
   }
 }
@@ -615,9 +631,12 @@ __global__ void __launch_bounds__(256) k_shadow(DevScene sc, PathPool pool, Queu
 
 // ------------------------------------------------------------------------------------------ closest-hit API kernel
 // check_hit for a batch of caller rays (acceleration/mod.rs:265-298): 2 x float4 in, 16 B out.
+template <bool COUNT>
 __global__ void __launch_bounds__(256)
-k_closest_hit_api(DevScene sc, const float4* __restrict__ rays, uint32_t n, uint4* __restrict__ hits, uint32_t* head) {
+k_closest_hit_api(DevScene sc, const float4* __restrict__ rays, uint32_t n, uint4* __restrict__ hits, uint32_t* head,
+                  unsigned long long* counts) {
   const uint32_t lane = threadIdx.x & 31u;
+  uint32_t cnt_nodes = 0, cnt_prims = 0;
   for (;;) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(head, 32u);
@@ -627,7 +646,7 @@ k_closest_hit_api(DevScene sc, const float4* __restrict__ rays, uint32_t n, uint
     if (i >= n) continue;
     const float4 o = __ldg(rays + 2u * (size_t)i), d = __ldg(rays + 2u * (size_t)i + 1u);
     const Ray ray = make_ray_from_raw(from4(o), from4(d));
-    const TraceResult tr = closest_hit(sc, ray);
+    const TraceResult tr = closest_hit_t<COUNT>(sc, ray, cnt_nodes, cnt_prims);
     uint4 out = make_uint4(__float_as_uint(0.0f), PTB_MISS, 0u, 0u);
     if (tr.ref != kNone) {
       HitRec h;
@@ -636,6 +655,16 @@ k_closest_hit_api(DevScene sc, const float4* __restrict__ rays, uint32_t n, uint
                        __float_as_uint(h.b2));
     }
     hits[i] = out;
+  }
+  if (COUNT) {
+    for (int off = 16; off > 0; off >>= 1) {
+      cnt_nodes += __shfl_xor_sync(0xffffffffu, cnt_nodes, off);
+      cnt_prims += __shfl_xor_sync(0xffffffffu, cnt_prims, off);
+    }
+    if (lane == 0) {
+      atomicAdd(counts + 0, (unsigned long long)cnt_nodes);
+      atomicAdd(counts + 1, (unsigned long long)cnt_prims);
+    }
   }
 }
 
@@ -650,12 +679,28 @@ int32_t launch_closest_hit(Ctx* c, const void* d_rays, size_t n, void* d_hits) {
   if (n == 0) return PTB_OK;
   if (n > 0xFFFFFFF0ull) return set_error(c, PTB_ERR_INVALID, "too many rays in one batch");
   PTB_CUDA_TRY(c, c->d_counters.reserve(sizeof(WaveCounters) + 64));
-  uint32_t* head = reinterpret_cast<uint32_t*>(c->d_counters.as<char>() + sizeof(WaveCounters));
-  PTB_CUDA_TRY(c, cudaMemsetAsync(head, 0, 4, c->stream));
-  const int grid = persistent_grid(c, (const void*)k_closest_hit_api, 256);
-  k_closest_hit_api<<<grid, 256, 0, c->stream>>>(c->dev, reinterpret_cast<const float4*>(d_rays), (uint32_t)n,
-                                                 reinterpret_cast<uint4*>(d_hits), head);
+  // scratch after the wavefront counters: [0] work cursor, [8..24) node / primitive counters
+  char* scratch = c->d_counters.as<char>() + sizeof(WaveCounters);
+  uint32_t* head = reinterpret_cast<uint32_t*>(scratch);
+  unsigned long long* counts = reinterpret_cast<unsigned long long*>(scratch + 8);
+  PTB_CUDA_TRY(c, cudaMemsetAsync(scratch, 0, 24, c->stream));
+  const float4* r4 = reinterpret_cast<const float4*>(d_rays);
+  uint4* h4 = reinterpret_cast<uint4*>(d_hits);
+  if (c->opt_count_traversal) {
+    const int grid = persistent_grid(c, (const void*)k_closest_hit_api<true>, 256);
+    k_closest_hit_api<true><<<grid, 256, 0, c->stream>>>(c->dev, r4, (uint32_t)n, h4, head, counts);
+    unsigned long long hc[2] = {0, 0};
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(hc, counts, 16, cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->stats.nodes_fetched += hc[0];
+    c->stats.prims_tested += hc[1];
+    c->stats.rays_counted += n;
+  } else {
+    const int grid = persistent_grid(c, (const void*)k_closest_hit_api<false>, 256);
+    k_closest_hit_api<false><<<grid, 256, 0, c->stream>>>(c->dev, r4, (uint32_t)n, h4, head, counts);
+  }
   c->stats.kernel_launches += 1;
+  c->stats.trace_launches += 1;
   PTB_CUDA_TRY(c, cudaGetLastError());
   return PTB_OK;
 }
@@ -724,9 +769,25 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   float* accum = c->d_accum.as<float>();
   const int T = 256;
   const uint32_t grid_p = (P + T - 1) / T;
-  const int grid_trace = persistent_grid(c, (const void*)k_trace, T);
+  const bool count = c->opt_count_traversal;
+  const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true> : (const void*)k_trace<false>, T);
   const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
   const bool mis = o.method == PTB_METHOD_MIS;
+  const bool prof = c->opt_time_kernels;
+  if (prof)
+    for (cudaEvent_t& e : c->ev_prof)
+      if (!e) PTB_CUDA_TRY(c, cudaEventCreate(&e));
+  // ev_prof[(iter & 1) * 8 + 2 * k + {0,1}] brackets kernel class k (0 generate, 1 trace, 2 shade, 3 shadow)
+  double* prof_ms[4] = {&c->stats.ms_generate, &c->stats.ms_trace, &c->stats.ms_shade, &c->stats.ms_shadow};
+  auto prof_collect = [&](int half) {
+    for (int k = 0; k < (mis ? 4 : 3); ++k) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->ev_prof[half * 8 + 2 * k], c->ev_prof[half * 8 + 2 * k + 1]) == cudaSuccess)
+        *prof_ms[k] += ms;
+    }
+  };
+#define PTB_PROF(k, which) \
+  if (prof) cudaEventRecord(c->ev_prof[(int)(iter & 1u) * 8 + 2 * (k) + (which)], st)
 
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
   k_init_pool<<<grid_p, T, 0, st>>>(q.free_slots, P, wc, total);
@@ -740,14 +801,24 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   cudaEvent_t ev[2] = {c->ev_iter, c->ev_b};
   while (!done) {
     k_prepare<<<1, 1, 0, st>>>(wc, o.method, iter == 0 ? 1u : 0u);
+    PTB_PROF(0, 0);
     k_generate<<<grid_p, T, 0, st>>>(c->dev, c->pool, q, wc, rp);
+    PTB_PROF(0, 1);
     k_advance<<<1, 1, 0, st>>>(wc);
-    k_trace<<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
+    PTB_PROF(1, 0);
+    if (count) k_trace<true><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
+    else k_trace<false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
+    PTB_PROF(1, 1);
+    PTB_PROF(2, 0);
     if (mis) k_shade<PTB_METHOD_MIS><<<grid_p, T, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
     else k_shade<PTB_METHOD_NAIVE><<<grid_p, T, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+    PTB_PROF(2, 1);
     c->stats.kernel_launches += 5;
+    c->stats.trace_launches += 1;
     if (mis) {
+      PTB_PROF(3, 0);
       k_shadow<<<grid_shadow, T, 0, st>>>(c->dev, c->pool, q, wc);
+      PTB_PROF(3, 1);
       c->stats.kernel_launches += 1;
     }
     const int slot = (int)(iter & 1u);
@@ -756,6 +827,7 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
     if (iter > 0) {  // inspect the previous iteration (already finished or about to)
       const int ps = slot ^ 1;
       PTB_CUDA_TRY(c, cudaEventSynchronize(ev[ps]));
+      if (prof) prof_collect(ps);
       const WaveCounters& h = c->h_counters[ps];
       if (h.next_sample >= h.total_samples && h.n_active[h.cur ^ 1u] == 0) done = true;
       if (progress && !done) {
@@ -776,9 +848,14 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
   PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
   PTB_CUDA_TRY(c, cudaGetLastError());
+  if (prof && iter > 0) prof_collect((int)((iter - 1) & 1u));
+#undef PTB_PROF
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
   const WaveCounters& h = c->h_counters[0];
+  c->stats.nodes_fetched += h.nodes_fetched;
+  c->stats.prims_tested += h.prims_tested;
+  c->stats.rays_counted += h.rays_counted;
   c->stats.rays_camera += h.rays_camera;
   c->stats.rays_bounce += h.rays_bounce;
   c->stats.rays_shadow_light += h.rays_shadow_light;

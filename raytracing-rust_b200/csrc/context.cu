@@ -84,6 +84,10 @@ int32_t ptb_create(int32_t device, ptb_ctx** out) {
     return rc;
   }
   c->sm_count = prop.multiProcessorCount;
+  c->dev.trace_burst = 4;
+  c->dev.trace_fetch_threshold = 8;
+  if (const char* e = getenv("PTB_TRACE_BURST")) { int v = atoi(e); if (v >= 1 && v <= 64) c->dev.trace_burst = v; }
+  if (const char* e = getenv("PTB_TRACE_FETCH")) { int v = atoi(e); if (v >= 1 && v <= 32) c->dev.trace_fetch_threshold = v; }
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");
   c->own_stream = true;
   if ((e = cudaEventCreate(&c->ev_a)) != cudaSuccess) return fail(e, "cudaEventCreate");

@@ -40,13 +40,13 @@ struct DevBuf {
 // Wavefront state for one render call (device pointers). See wavefront.cu.
 struct PathPool {
   uint32_t capacity = 0;
-  float4* ray_o = nullptr;  // origin.xyz | pixel (bits)
-  float4* ray_d = nullptr;  // normalised direction.xyz | depth + flags (bits)
-  float4* thr = nullptr;    // throughput.rgb | absolute sample index (bits)
-  float4* rad = nullptr;    // radiance gathered so far .rgb | m_pdf of the last BSDF sample (MIS)
-  float4* prev = nullptr;   // MIS: previous (un-offset) hit point.xyz | unused
-  uint2* hit = nullptr;     // t (bits), leaf ref (kNone = miss)
+  // Records are 32-byte sectors written whole by one thread (a 16-byte store to a scattered slot costs a
+  // read-modify-write at the DRAM side; two adjacent 16-byte stores do not).
+  float4* ray = nullptr;   // [2*slot]   origin.xyz | hit t        [2*slot+1] normalised direction.xyz | hit leaf ref (bits)
+  float4* col = nullptr;   // [2*slot]   throughput.rgb | pixel    [2*slot+1] radiance so far .rgb | sample<<9 | flags<<8 | depth
+  float4* prev = nullptr;  // MIS only: previous (un-offset) hit point.xyz | m_pdf of the last BSDF sample
 };
+constexpr uint32_t kMaxSampleIndex = 1u << 23;  // sample index shares a word with depth (8 bits) and one flag
 
 constexpr int kNumKinds = 6;  // shade queues: 0 = miss (sky), 1 + PTB_MAT_* otherwise
 

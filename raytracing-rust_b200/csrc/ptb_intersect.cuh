@@ -161,26 +161,19 @@ constexpr float kCullSlack = 32.0f * kF32Eps;
 PTB_DEV bool box_entry(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Ray& ray, float best_t,
                        float& tkey) {
   const float k = 1.0f + 2.0f * gamma_n(3);
-  float t1 = (mnx - ray.o.x) * ray.dinv.x;
-  float t2 = (mxx - ray.o.x) * ray.dinv.x;
-  float lo = fminf(t1, t2), hi = fmaxf(t1, t2);
-  float tmin = lo;
-  float tmax = hi * k;
-  const float mx = fmaxf(hi, -lo);
-  t1 = (mny - ray.o.y) * ray.dinv.y;
-  t2 = (mxy - ray.o.y) * ray.dinv.y;
-  lo = fminf(t1, t2); hi = fmaxf(t1, t2);
-  tmin = fmaxf(tmin, lo);
-  tmax = fminf(tmax, hi * k);
-  const float my = fmaxf(hi, -lo);
-  t1 = (mnz - ray.o.z) * ray.dinv.z;
-  t2 = (mxz - ray.o.z) * ray.dinv.z;
-  lo = fminf(t1, t2); hi = fmaxf(t1, t2);
-  tmin = fmaxf(tmin, lo);
-  tmax = fminf(tmax, hi * k);
-  const float mz = fmaxf(hi, -lo);
-  float m = fmaxf(mx, fmaxf(my, mz));
+  const float ax = (mnx - ray.o.x) * ray.dinv.x, bx = (mxx - ray.o.x) * ray.dinv.x;
+  const float ay = (mny - ray.o.y) * ray.dinv.y, by = (mxy - ray.o.y) * ray.dinv.y;
+  const float az = (mnz - ray.o.z) * ray.dinv.z, bz = (mxz - ray.o.z) * ray.dinv.z;
+  const float lox = fminf(ax, bx), hix = fmaxf(ax, bx);
+  const float loy = fminf(ay, by), hiy = fmaxf(ay, by);
+  const float loz = fminf(az, bz), hiz = fmaxf(az, bz);
+  // 3-input min/max (FMNMX3 on sm_100a). min(hi*k) == min(hi)*k: rounding is monotone, so k is applied once.
+  const float tmin = fmaxf(fmaxf(lox, loy), loz);
+  const float hmin = fminf(fminf(hix, hiy), hiz);
+  const float tmax = hmin * k;
+  float m = fmaxf(fmaxf(fmaxf(hix, hiy), hiz), -fminf(fminf(lox, loy), loz));
   if (!(m < 3.0e38f)) {  // axis-parallel ray: ignore the slabs it never crosses
+    const float mx = fmaxf(hix, -lox), my = fmaxf(hiy, -loy), mz = fmaxf(hiz, -loz);
     m = fmaxf(mx < 3.0e38f ? mx : 0.0f, fmaxf(my < 3.0e38f ? my : 0.0f, mz < 3.0e38f ? mz : 0.0f));
   }
   tkey = tmin - kCullSlack * m;

@@ -1,18 +1,29 @@
-// BVH2 traversal for ptb200 (device): ordered (near child first), t-culled, per-lane stack.
-//   closest_hit : replaces get_intersection_candidates + check_hit
+// BVH2 traversal for ptb200 (device): ordered (near child first), t-culled, per-lane stack, persistent warps.
+//   closest hit : replaces get_intersection_candidates + check_hit
 //                 (implementations/src/acceleration/mod.rs:199-224, 265-298). The reference keeps the minimum t > 0
 //                 over every primitive in every leaf whose box the ray line crosses; an ordered traversal that only
-//                 culls boxes entered beyond the current best t returns the same minimum. Exact-t ties go to the
-//                 lower ORIGINAL primitive id (the reference: first found in its BFS order — quirk Q2).
-//   occluded    : replaces the blocker scan of check_hit_index (acceleration/mod.rs:226-263) and the sky visibility
+//                 culls boxes entered beyond the current best t (less an error slack, see box_entry) returns the same
+//                 minimum. Exact-t ties go to the lower ORIGINAL primitive id (the reference: first found in its BFS
+//                 order — quirk Q2).
+//   any hit     : replaces the blocker scan of check_hit_index (acceleration/mod.rs:226-263) and the sky visibility
 //                 test of sample_lights (integrators/mis.rs:104-115): any primitive != exclude with 0 < t < tmax.
+//
+// Execution shape (the first ncu capture showed the naive one-ray-per-lane loop issue-bound at 11-15 active lanes of
+// 32): every warp is persistent and keeps its 32 lanes busy —
+//   * "while-while": a lane walks internal nodes until EVERY lane of the warp holds a postponed leaf, then all lanes
+//     run the primitive test together (Aila & Laine 2009, speculative traversal);
+//   * dynamic fetch: when fewer than kFetchThreshold lanes still have work, the warp leaves the traversal loop and
+//     refills its idle lanes from the global ray queue (one warp-aggregated atomicAdd) instead of dragging a few long
+//     rays along with 90 % of the lanes idle.
 // Node fetches are four 16-byte loads of one 64-byte node that carries BOTH children's boxes.
 #pragma once
 #include "ptb_intersect.cuh"
 
 namespace ptb {
 
-constexpr int kStackDepth = 64;  // LBVH depth <= 30 Morton bits + 32 index tie-break bits; one push per level
+constexpr int kStackDepth = 64;        // LBVH depth <= 30 Morton bits + 32 index tie-break bits; one push per level
+constexpr int kFetchThreshold = 20;    // lanes; below this the warp refills from the queue
+constexpr int kNodeBurst = 4;          // node steps per warp-level scheduling decision
 
 struct TraceResult {
   float t;       // 0 on miss (sky.rs:79-91)
@@ -27,116 +38,179 @@ PTB_DEV void load_node(const BvhNode* __restrict__ nodes, uint32_t idx, float4& 
   n3 = __ldg(reinterpret_cast<const uint4*>(p + 3));
 }
 
-// COUNT: also report how many 64-byte nodes were fetched and how many primitives were tested (the V and T of the
-// algorithmic-bytes-per-ray figure); compiled out otherwise.
+// Per-lane traversal state. `cur`: internal node index, or a leaf reference (bit 31), or kNone when the stack ran dry.
+// `leaf`: postponed leaf reference or kNone.
+struct TravState {
+  uint32_t cur, leaf;
+  int sp;
+  float best_t;       // closest hit so far (closest-hit) / tmax (any-hit)
+  uint32_t best_ref;  // closest-hit: winning leaf ref; any-hit: kNone = unoccluded, 0 = occluded
+  PTB_DEV bool done() const { return cur == kNone && leaf == kNone; }
+};
+
+PTB_DEV void trav_init(TravState& s, uint32_t n_prims, float tmax) {
+  s.cur = n_prims ? 0u : kNone;
+  s.leaf = kNone;
+  s.sp = 0;
+  s.best_t = tmax;
+  s.best_ref = kNone;
+}
+
+PTB_DEV uint32_t trav_pop(TravState& s, const uint32_t* stack, const float* stack_t) {
+  while (s.sp > 0) {
+    --s.sp;
+    if (stack_t[s.sp] <= s.best_t) return stack[s.sp];
+  }
+  return kNone;
+}
+
+// One internal-node step of the lane: fetch the 64-byte node, test both child boxes, descend into the nearer hit child
+// (deferring the other on the stack), and postpone the first leaf reached so the walk can continue.
 template <bool COUNT>
-PTB_DEV TraceResult closest_hit_t(const DevScene& sc, const Ray& ray, uint32_t& n_nodes, uint32_t& n_prims) {
-  TraceResult res;
-  res.t = 0.0f;
-  res.ref = kNone;
-  if (sc.n_prims == 0) return res;
-  float best_t = __int_as_float(0x7f800000);
-  uint32_t best_ref = kNone;
+PTB_DEV void trav_node_step(const DevScene& sc, const Ray& ray, TravState& s, uint32_t* stack, float* stack_t,
+                            uint32_t& n_nodes) {
+  float4 n0, n1, n2;
+  uint4 n3;
+  load_node(sc.nodes, s.cur, n0, n1, n2, n3);
+  if (COUNT) ++n_nodes;
+  float tl, tr;
+  const bool hl = box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ray, s.best_t, tl);
+  const bool hr = box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ray, s.best_t, tr);
+  if (hl && hr) {
+    uint32_t nearc = n3.x, farc = n3.y;
+    float tfar = tr;
+    if (tr < tl) { nearc = n3.y; farc = n3.x; tfar = tl; }
+    stack[s.sp] = farc;
+    stack_t[s.sp] = tfar;
+    ++s.sp;
+    s.cur = nearc;
+  } else if (hl) {
+    s.cur = n3.x;
+  } else if (hr) {
+    s.cur = n3.y;
+  } else {
+    s.cur = trav_pop(s, stack, stack_t);
+  }
+  if ((s.cur & PTB_LEAF_BIT) && s.cur != kNone && s.leaf == kNone) {  // first leaf: postpone, keep walking
+    s.leaf = s.cur;
+    s.cur = trav_pop(s, stack, stack_t);
+  }
+}
+
+// One primitive step of the lane: test the postponed leaf; if the walk itself is parked on a leaf, that one is next.
+template <bool ANYHIT, bool COUNT>
+PTB_DEV void trav_prim_step(const DevScene& sc, const Ray& ray, TravState& s, uint32_t* stack, float* stack_t,
+                            uint32_t exclude, uint32_t& n_prims) {
+  const uint32_t ref = s.leaf;
+  s.leaf = kNone;
+  if (ANYHIT) {
+    if ((ref & kSlotMask) != exclude) {
+      const float t = prim_t(sc, ray, ref);
+      if (COUNT) ++n_prims;
+      if (t > 0.0f && t < s.best_t) {  // blocker found: stop
+        s.best_ref = 0u;
+        s.cur = kNone;
+        s.sp = 0;
+        return;
+      }
+    }
+  } else {
+    const float t = prim_t(sc, ray, ref);
+    if (COUNT) ++n_prims;
+    if (t > 0.0f) {
+      if (t < s.best_t) {
+        s.best_t = t;
+        s.best_ref = ref;
+      } else if (t == s.best_t) {
+        const uint32_t a = __ldg(sc.slot_prim + (ref & kSlotMask));
+        const uint32_t b = __ldg(sc.slot_prim + (s.best_ref & kSlotMask));
+        if (a < b) s.best_ref = ref;
+      }
+    }
+  }
+  if ((s.cur & PTB_LEAF_BIT) && s.cur != kNone) {
+    s.leaf = s.cur;
+    s.cur = trav_pop(s, stack, stack_t);
+  }
+}
+
+PTB_DEV TraceResult trav_result(const TravState& s) {
+  TraceResult r;
+  r.t = 0.0f;
+  r.ref = kNone;
+  if (s.best_ref != kNone) {
+    r.t = s.best_t;
+    r.ref = s.best_ref & ~PTB_LEAF_BIT;
+  }
+  return r;
+}
+
+// Persistent-warp driver, warp-synchronous: all 32 lanes run this loop in lock step (full-mask ballots only), so the
+// SIMT efficiency is decided here and not by the compiler's reconvergence choices.
+//   service : when fewer than kFetchThreshold lanes still have work, finished lanes are retired and idle lanes are
+//             refilled from the global queue with one warp-aggregated atomicAdd;
+//   phase   : each iteration runs EITHER a node step for the lanes parked on an internal node OR a primitive step for
+//             the lanes holding a postponed leaf — whichever has more ready lanes.
+// `fetch(i, ray, tmax, exclude)` loads work item i into the lane; `retire(fin, state)` is called by ALL 32 lanes together
+// (fin = this lane just completed its item) so it may use warp-wide primitives.
+template <bool ANYHIT, bool COUNT, class Fetch, class Retire>
+PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fetch& fetch, Retire& retire,
+                              uint32_t& cnt_nodes, uint32_t& cnt_prims, uint32_t& cnt_rays) {
+  const uint32_t lane = threadIdx.x & 31u;
   uint32_t stack[kStackDepth];
   float stack_t[kStackDepth];
-  int sp = 0;
-  uint32_t cur = 0;
+  TravState st;
+  st.cur = st.leaf = kNone;
+  st.sp = 0;
+  st.best_t = 0.0f;
+  st.best_ref = kNone;
+  Ray ray;
+  ray.o = ray.d = ray.dinv = ray.shear = mk(0.0f, 0.0f, 0.0f);
+  ray.swap_xz = false;
+  uint32_t exclude = kNone;
+  bool has_ray = false, exhausted = false;
   for (;;) {
-    if (cur & PTB_LEAF_BIT) {
-      const float t = prim_t(sc, ray, cur);
-      if (COUNT) ++n_prims;
-      if (t > 0.0f) {
-        if (t < best_t) {
-          best_t = t;
-          best_ref = cur;
-        } else if (t == best_t) {
-          const uint32_t a = __ldg(sc.slot_prim + (cur & kSlotMask));
-          const uint32_t b = __ldg(sc.slot_prim + (best_ref & kSlotMask));
-          if (a < b) best_ref = cur;
+    // a lane with work is parked on an internal node, holds a postponed leaf, or both
+    bool node_ready = has_ray && !(st.cur & PTB_LEAF_BIT);
+    const bool leaf_ready = has_ray && st.leaf != kNone;
+    const uint32_t m_node = __ballot_sync(0xffffffffu, node_ready);
+    const uint32_t m_leaf = __ballot_sync(0xffffffffu, leaf_ready);
+    if ((uint32_t)__popc(m_node | m_leaf) < (exhausted ? 1u : (uint32_t)sc.trace_fetch_threshold)) {
+      // ---- service: retire finished items, refill idle lanes
+      const bool fin = has_ray && !node_ready && !leaf_ready;
+      retire(fin, st, ray);
+      if (fin) has_ray = false;
+      if (exhausted) {
+        if (!__any_sync(0xffffffffu, has_ray)) break;
+        continue;
+      }
+      const uint32_t idle = __ballot_sync(0xffffffffu, !has_ray);
+      if (idle) {
+        const uint32_t leader = __ffs(idle) - 1u, want = __popc(idle);
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(head, want);
+        base = __shfl_sync(0xffffffffu, base, leader);
+        const uint32_t mine = base + __popc(idle & ((1u << lane) - 1u));
+        if (!has_ray && mine < n) {
+          float tmax = __int_as_float(0x7f800000);
+          fetch(mine, ray, tmax, exclude);
+          trav_init(st, sc.n_prims, tmax);
+          has_ray = true;
+          if (COUNT) ++cnt_rays;
         }
+        if (base + want >= n) exhausted = true;
       }
-      bool popped = false;
-      while (sp > 0) {
-        --sp;
-        if (stack_t[sp] <= best_t) { cur = stack[sp]; popped = true; break; }
-      }
-      if (!popped) break;
       continue;
     }
-    float4 n0, n1, n2;
-    uint4 n3;
-    load_node(sc.nodes, cur, n0, n1, n2, n3);
-    if (COUNT) ++n_nodes;
-    float tl, tr;
-    const bool hl = box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ray, best_t, tl);
-    const bool hr = box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ray, best_t, tr);
-    if (hl && hr) {
-      uint32_t nearc = n3.x, farc = n3.y;
-      float tfar = tr;
-      if (tr < tl) { nearc = n3.y; farc = n3.x; tfar = tl; }
-      stack[sp] = farc;
-      stack_t[sp] = tfar;
-      ++sp;
-      cur = nearc;
-    } else if (hl) {
-      cur = n3.x;
-    } else if (hr) {
-      cur = n3.y;
-    } else {
-      bool popped = false;
-      while (sp > 0) {
-        --sp;
-        if (stack_t[sp] <= best_t) { cur = stack[sp]; popped = true; break; }
+    if (__popc(m_node) >= __popc(m_leaf)) {
+      // ---- node phase: a short burst of node steps amortises the warp-level bookkeeping above
+#pragma unroll 1
+      for (int burst = 0; burst < sc.trace_burst && node_ready; ++burst) {
+        trav_node_step<COUNT>(sc, ray, st, stack, stack_t, cnt_nodes);
+        node_ready = !(st.cur & PTB_LEAF_BIT);
       }
-      if (!popped) break;
-    }
-  }
-  if (best_ref != kNone) {
-    res.t = best_t;
-    res.ref = best_ref & ~PTB_LEAF_BIT;
-  }
-  return res;
-}
-
-PTB_DEV TraceResult closest_hit(const DevScene& sc, const Ray& ray) {
-  uint32_t a = 0, b = 0;
-  return closest_hit_t<false>(sc, ray, a, b);
-}
-
-// true when some primitive other than `exclude_slot` is hit with 0 < t < tmax
-PTB_DEV bool occluded(const DevScene& sc, const Ray& ray, float tmax, uint32_t exclude_slot) {
-  if (sc.n_prims == 0) return false;
-  uint32_t stack[kStackDepth];
-  int sp = 0;
-  uint32_t cur = 0;
-  for (;;) {
-    if (cur & PTB_LEAF_BIT) {
-      if ((cur & kSlotMask) != exclude_slot) {
-        const float t = prim_t(sc, ray, cur);
-        if (t > 0.0f && t < tmax) return true;
-      }
-      if (sp == 0) return false;
-      cur = stack[--sp];
-      continue;
-    }
-    float4 n0, n1, n2;
-    uint4 n3;
-    load_node(sc.nodes, cur, n0, n1, n2, n3);
-    float tl, tr;
-    const bool hl = box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ray, tmax, tl);
-    const bool hr = box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ray, tmax, tr);
-    if (hl && hr) {
-      uint32_t nearc = n3.x, farc = n3.y;
-      if (tr < tl) { nearc = n3.y; farc = n3.x; }
-      stack[sp++] = farc;
-      cur = nearc;
-    } else if (hl) {
-      cur = n3.x;
-    } else if (hr) {
-      cur = n3.y;
-    } else {
-      if (sp == 0) return false;
-      cur = stack[--sp];
+    } else if (leaf_ready) {
+      trav_prim_step<ANYHIT, COUNT>(sc, ray, st, stack, stack_t, exclude, cnt_prims);
     }
   }
 }

@@ -210,10 +210,9 @@ __global__ void k_prepare(WaveCounters* wc, uint32_t method, uint32_t first) {
 // ------------------------------------------------------------------------------------------ K1 camera rays
 __global__ void __launch_bounds__(256)
 k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t n_new = wc->n_new;
-  if (i >= n_new) return;
   const uint32_t cur = wc->cur;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
   const uint32_t slot = q.free_slots[wc->free_base + (n_new - 1u - i)];
   const unsigned long long g = wc->next_sample + i;
   const uint32_t pixel = (uint32_t)(g % rp.npix);
@@ -226,53 +225,64 @@ k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams 
   // camera.rs:57-63 + Ray::new (ray.rs:13-46)
   const v3 dir = sc.cam_lower_left + sc.cam_horizontal * u + sc.cam_vertical * v - sc.cam_origin;
   const v3 d = dir / mag(dir);
-  pool.ray_o[slot] = make_float4(sc.cam_origin.x, sc.cam_origin.y, sc.cam_origin.z, __uint_as_float(pixel));
-  pool.ray_d[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(0u));
-  pool.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(sample));
-  pool.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  pool.ray[2u * (size_t)slot] = make_float4(sc.cam_origin.x, sc.cam_origin.y, sc.cam_origin.z, 0.0f);
+  pool.ray[2u * (size_t)slot + 1u] = make_float4(d.x, d.y, d.z, __uint_as_float(kNone));
+  pool.col[2u * (size_t)slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pixel));
+  pool.col[2u * (size_t)slot + 1u] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(sample << 9));
   q.active[cur][wc->n_active[cur] + i] = slot;
-  if (i == 0) {
-    // single writer; every other thread only reads n_new / free_base / n_active, which k_prepare fixed
-    // (next_sample is advanced by the following k_prepare via n_new) -> done in k_advance to avoid a read/write race
   }
 }
+// next_sample is advanced by a separate 1-thread launch: every k_generate thread reads it
 __global__ void k_advance(WaveCounters* wc) { wc->next_sample += wc->n_new; }
 
 // ------------------------------------------------------------------------------------------ K8 closest hit + K11 queueing
+struct TraceFetch {
+  const PathPool& pool;
+  const uint32_t* __restrict__ queue;
+  uint32_t slot;
+  PTB_DEV void operator()(uint32_t i, Ray& ray, float& /*tmax*/, uint32_t& /*exclude*/) {
+    slot = queue[i];
+    const float4 o = pool.ray[2u * (size_t)slot], d = pool.ray[2u * (size_t)slot + 1u];
+    ray = make_ray(from4(o), from4(d));
+  }
+};
+struct TraceRetire {
+  const DevScene& sc;
+  const PathPool& pool;
+  const Queues& q;
+  WaveCounters* wc;
+  const TraceFetch& f;
+  // called by all 32 lanes: write the hit (the whole 32-byte ray record, so the store is a full sector), then a
+  // warp-aggregated push into the per-material-kind shade queue
+  PTB_DEV void operator()(bool fin, const TravState& st, const Ray& ray) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t kind = 0xFFu;
+    if (fin) {
+      const TraceResult tr = trav_result(st);
+      pool.ray[2u * (size_t)f.slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, tr.t);
+      pool.ray[2u * (size_t)f.slot + 1u] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(tr.ref));
+      kind = tr.ref == kNone ? 0u : 1u + (__ldg(sc.slot_mat + (tr.ref & kSlotMask)) >> 24);
+    }
+    if (!__any_sync(0xffffffffu, fin)) return;
+    const uint32_t peers = __match_any_sync(0xffffffffu, kind);
+    if (fin) {
+      const uint32_t leader = __ffs(peers) - 1u;
+      uint32_t pos = 0;
+      if (lane == leader) pos = atomicAdd(&wc->n_kind[kind], __popc(peers));
+      pos = __shfl_sync(peers, pos, leader);
+      q.kind[kind][pos + __popc(peers & ((1u << lane) - 1u))] = f.slot;
+    }
+  }
+};
+
 template <bool COUNT>
 __global__ void __launch_bounds__(256)
 k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t cnt_nodes = 0, cnt_prims = 0, cnt_rays = 0;
-  const uint32_t n = wc->n_trace;
-  const uint32_t* __restrict__ queue = q.active[wc->cur];
-  for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&wc->trace_head, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;
-    const uint32_t i = base + lane;
-    uint32_t kind = 0xFFu;  // inactive lane
-    uint32_t slot = 0;
-    if (i < n) {
-      slot = queue[i];
-      const float4 o = pool.ray_o[slot], d = pool.ray_d[slot];
-      const Ray ray = make_ray(from4(o), from4(d));
-      const TraceResult tr = closest_hit_t<COUNT>(sc, ray, cnt_nodes, cnt_prims);
-      if (COUNT) ++cnt_rays;
-      pool.hit[slot] = make_uint2(__float_as_uint(tr.t), tr.ref);
-      kind = tr.ref == kNone ? 0u : 1u + (__ldg(sc.slot_mat + (tr.ref & kSlotMask)) >> 24);
-    }
-    // warp-aggregated push into the per-kind shade queues
-    const uint32_t peers = __match_any_sync(0xffffffffu, kind);
-    if (kind != 0xFFu) {
-      const uint32_t leader = __ffs(peers) - 1u;
-      uint32_t pos = 0;
-      if (lane == leader) pos = atomicAdd(&wc->n_kind[kind], __popc(peers));
-      pos = __shfl_sync(peers, pos, leader);
-      q.kind[kind][pos + __popc(peers & ((1u << lane) - 1u))] = slot;
-    }
-  }
+  TraceFetch fetch{pool, q.active[wc->cur], 0u};
+  TraceRetire retire{sc, pool, q, wc, fetch};
+  persistent_trace<false, COUNT>(sc, wc->n_trace, &wc->trace_head, fetch, retire, cnt_nodes, cnt_prims, cnt_rays);
   if (COUNT) {
     for (int off = 16; off > 0; off >>= 1) {
       cnt_nodes += __shfl_xor_sync(0xffffffffu, cnt_nodes, off);
@@ -317,17 +327,21 @@ template <int METHOD>
 __global__ void __launch_bounds__(256)
 k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum) {
   const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  // locate (kind queue, offset) for work item i in the concatenation of the kind queues
+  const uint32_t nxt = wc->cur ^ 1u;
+  uint32_t n_kind[kNumKinds], n_total = 0;
+#pragma unroll
+  for (int k = 0; k < kNumKinds; ++k) { n_kind[k] = wc->n_kind[k]; n_total += n_kind[k]; }
+  // grid-stride over the concatenation of the kind queues; whole blocks iterate together (ballots below)
+  for (uint32_t base = blockIdx.x * blockDim.x; base < n_total; base += gridDim.x * blockDim.x) {
+  const uint32_t i = base + threadIdx.x;
   uint32_t total = 0, kq = kNumKinds, off = 0;
 #pragma unroll
   for (int k = 0; k < kNumKinds; ++k) {
-    const uint32_t c = wc->n_kind[k];
+    const uint32_t c = n_kind[k];
     if (kq == (uint32_t)kNumKinds && i < total + c) { kq = k; off = i - total; }
     total += c;
   }
   const bool active = kq != (uint32_t)kNumKinds;
-  const uint32_t nxt = wc->cur ^ 1u;
 
   bool alive = false;     // path continues: goes to the next active queue
   bool finished = false;  // path ended: slot returns to the free list
@@ -338,10 +352,12 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
 
   if (active) {
     slot = q.kind[kq][off];
-    const float4 ro = pool.ray_o[slot], rd = pool.ray_d[slot], th = pool.thr[slot], ra = pool.rad[slot];
-    const uint2 ht = pool.hit[slot];
-    const uint32_t pixel = __float_as_uint(ro.w), sample = __float_as_uint(th.w);
-    const uint32_t df = __float_as_uint(rd.w);
+    const float4 ro = pool.ray[2u * (size_t)slot], rd = pool.ray[2u * (size_t)slot + 1u];
+    const float4 th = pool.col[2u * (size_t)slot], ra = pool.col[2u * (size_t)slot + 1u];
+    const uint2 ht = make_uint2(__float_as_uint(ro.w), __float_as_uint(rd.w));
+    const uint32_t pixel = __float_as_uint(th.w);
+    const uint32_t df = __float_as_uint(ra.w);
+    const uint32_t sample = df >> 9;
     uint32_t depth = df & 0xFFu;
     const bool prev_delta = (df & kFlagPrevDelta) != 0u;
     const Ray ray = make_ray(from4(ro), from4(rd));
@@ -401,10 +417,10 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
             const bool use_mis = s.miss ? sky_samplable : !prev_delta;  // mis.rs:57-60 (an emissive prim is in `lights`)
             if (use_mis) {
               const float divisor = (float)(sky_samplable ? sc.n_lights + 1u : sc.n_lights);  // acceleration/mod.rs:299-318
-              const v3 prev_point = from4(pool.prev[slot]);
+              const float4 pv = pool.prev[slot];  // previous hit point | m_pdf of the BSDF sample that got us here
               const float l_pdf = s.miss ? sky_pdf(sc, wo) / divisor
-                                         : light_pdf(sc, ht.y, prev_point, wo, s.h.point, s.h.normal) / divisor;
-              const float w = power_heuristic(ra.w, l_pdf);
+                                         : light_pdf(sc, ht.y, from4(pv), wo, s.h.point, s.h.normal) / divisor;
+              const float w = power_heuristic(pv.w, l_pdf);
               L = L + T * le * w;
             } else {
               L = L + T * le;
@@ -550,14 +566,15 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
           m_pdf = 0.0f;
           T = T * (col / 0.0f);  // eval / scattering_pdf with the default pdf 0 (quirk Q4)
         }
-        pool.prev[slot] = make_float4(s.h.point.x, s.h.point.y, s.h.point.z, 0.0f);
+        pool.prev[slot] = make_float4(s.h.point.x, s.h.point.y, s.h.point.z, m_pdf);
         alive = true;
       }
       if (alive) {
-        pool.ray_o[slot] = make_float4(new_o.x, new_o.y, new_o.z, ro.w);
-        pool.ray_d[slot] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(depth | (delta ? kFlagPrevDelta : 0u)));
-        pool.thr[slot] = make_float4(T.x, T.y, T.z, th.w);
-        pool.rad[slot] = make_float4(L.x, L.y, L.z, m_pdf);
+        pool.ray[2u * (size_t)slot] = make_float4(new_o.x, new_o.y, new_o.z, 0.0f);
+        pool.ray[2u * (size_t)slot + 1u] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(kNone));
+        pool.col[2u * (size_t)slot] = make_float4(T.x, T.y, T.z, th.w);
+        pool.col[2u * (size_t)slot + 1u] =
+            make_float4(L.x, L.y, L.z, __uint_as_float((sample << 9) | (delta ? kFlagPrevDelta : 0u) | depth));
       }
     }
     if (finished) finish_path(accum, pixel, L, nan_check);
@@ -604,58 +621,80 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
       }
     }
   }
+  }  // grid-stride
 }
 
 // ------------------------------------------------------------------------------------------ K9 shadow rays
-__global__ void __launch_bounds__(256) k_shadow(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const uint32_t n = wc->n_shadow;
-  for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&wc->shadow_head, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;
-    const uint32_t i = base + lane;
-    if (i >= n) continue;
+struct ShadowFetch {
+  const Queues& q;
+  float4 contrib;  // rgb | path slot
+  PTB_DEV void operator()(uint32_t i, Ray& ray, float& tmax, uint32_t& exclude) {
     const float4* e = q.shadow + 3u * (size_t)i;
-    const float4 o = e[0], d = e[1], cc = e[2];
-    const Ray ray = make_ray(from4(o), from4(d));
-    if (!occluded(sc, ray, o.w, __float_as_uint(d.w))) {
-      const uint32_t slot = __float_as_uint(cc.w);
-      float4 ra = pool.rad[slot];
-      ra.x += cc.x; ra.y += cc.y; ra.z += cc.z;  // output += throughput * eval * mis_weight * le / l_pdf (mis.rs:42)
-      pool.rad[slot] = ra;
+    const float4 o = e[0], d = e[1];
+    contrib = e[2];
+    ray = make_ray(from4(o), from4(d));
+    tmax = o.w;
+    exclude = __float_as_uint(d.w);
+  }
+};
+struct ShadowRetire {
+  const PathPool& pool;
+  const ShadowFetch& f;
+  PTB_DEV void operator()(bool fin, const TravState& st, const Ray&) {
+    if (fin && st.best_ref == kNone) {  // unoccluded
+      const uint32_t slot = __float_as_uint(f.contrib.w);
+      float4 ra = pool.col[2u * (size_t)slot + 1u];
+      ra.x += f.contrib.x; ra.y += f.contrib.y; ra.z += f.contrib.z;  // output += throughput*eval*mis*le/l_pdf (mis.rs:42)
+      pool.col[2u * (size_t)slot + 1u] = ra;
     }
   }
+};
+__global__ void __launch_bounds__(256) k_shadow(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
+  uint32_t a = 0, b = 0, r = 0;
+  ShadowFetch fetch{q, make_float4(0.f, 0.f, 0.f, 0.f)};
+  ShadowRetire retire{pool, fetch};
+  persistent_trace<true, false>(sc, wc->n_shadow, &wc->shadow_head, fetch, retire, a, b, r);
 }
 
 // ------------------------------------------------------------------------------------------ closest-hit API kernel
 // check_hit for a batch of caller rays (acceleration/mod.rs:265-298): 2 x float4 in, 16 B out.
+struct ApiFetch {
+  const float4* __restrict__ rays;
+  uint32_t idx;
+  Ray ray;
+  PTB_DEV void operator()(uint32_t i, Ray& r, float& /*tmax*/, uint32_t& /*exclude*/) {
+    idx = i;
+    const float4 o = __ldg(rays + 2u * (size_t)i), d = __ldg(rays + 2u * (size_t)i + 1u);
+    r = make_ray_from_raw(from4(o), from4(d));
+    ray = r;
+  }
+};
+struct ApiRetire {
+  const DevScene& sc;
+  uint4* __restrict__ hits;
+  const ApiFetch& f;
+  PTB_DEV void operator()(bool fin, const TravState& st, const Ray&) {
+    if (!fin) return;
+    const TraceResult tr = trav_result(st);
+    uint4 out = make_uint4(__float_as_uint(0.0f), PTB_MISS, 0u, 0u);
+    if (tr.ref != kNone) {
+      HitRec h;
+      prim_hit(sc, f.ray, tr.ref, h);
+      out = make_uint4(__float_as_uint(tr.t), __ldg(sc.slot_prim + (tr.ref & kSlotMask)), __float_as_uint(h.b1),
+                       __float_as_uint(h.b2));
+    }
+    hits[f.idx] = out;
+  }
+};
 template <bool COUNT>
 __global__ void __launch_bounds__(256)
 k_closest_hit_api(DevScene sc, const float4* __restrict__ rays, uint32_t n, uint4* __restrict__ hits, uint32_t* head,
                   unsigned long long* counts) {
   const uint32_t lane = threadIdx.x & 31u;
-  uint32_t cnt_nodes = 0, cnt_prims = 0;
-  for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(head, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= n) break;
-    const uint32_t i = base + lane;
-    if (i >= n) continue;
-    const float4 o = __ldg(rays + 2u * (size_t)i), d = __ldg(rays + 2u * (size_t)i + 1u);
-    const Ray ray = make_ray_from_raw(from4(o), from4(d));
-    const TraceResult tr = closest_hit_t<COUNT>(sc, ray, cnt_nodes, cnt_prims);
-    uint4 out = make_uint4(__float_as_uint(0.0f), PTB_MISS, 0u, 0u);
-    if (tr.ref != kNone) {
-      HitRec h;
-      prim_hit(sc, ray, tr.ref, h);
-      out = make_uint4(__float_as_uint(tr.t), __ldg(sc.slot_prim + (tr.ref & kSlotMask)), __float_as_uint(h.b1),
-                       __float_as_uint(h.b2));
-    }
-    hits[i] = out;
-  }
+  uint32_t cnt_nodes = 0, cnt_prims = 0, cnt_rays = 0;
+  ApiFetch fetch{rays, 0u, Ray()};
+  ApiRetire retire{sc, hits, fetch};
+  persistent_trace<false, COUNT>(sc, n, head, fetch, retire, cnt_nodes, cnt_prims, cnt_rays);
   if (COUNT) {
     for (int off = 16; off > 0; off >>= 1) {
       cnt_nodes += __shfl_xor_sync(0xffffffffu, cnt_nodes, off);
@@ -713,7 +752,7 @@ void free_render_state(Ctx* c) {
 }
 
 static uint32_t pool_capacity_for(unsigned long long total) {
-  unsigned long long cap = 1ull << 21;  // 2 Mi paths in flight (~190 MB of path state)
+  unsigned long long cap = 1ull << 24;  // 16 Mi paths in flight (1.3 GB of path state): long launches hide each launch's tail
   if (const char* e = getenv("PTB_POOL_PATHS")) {
     unsigned long long v = strtoull(e, nullptr, 10);
     if (v >= 1024 && v <= (1ull << 26)) cap = v;
@@ -731,16 +770,13 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
 
   // ---- device state (grow-only across calls)
   if (c->pool.capacity != P) {
-    const size_t pool_bytes = (size_t)P * (5 * 16 + 8);
+    const size_t pool_bytes = (size_t)P * (32 + 32 + 16);
     PTB_CUDA_TRY(c, c->d_pool_mem.reserve(pool_bytes));
     char* b = c->d_pool_mem.as<char>();
     c->pool.capacity = P;
-    c->pool.ray_o = reinterpret_cast<float4*>(b); b += (size_t)P * 16;
-    c->pool.ray_d = reinterpret_cast<float4*>(b); b += (size_t)P * 16;
-    c->pool.thr = reinterpret_cast<float4*>(b); b += (size_t)P * 16;
-    c->pool.rad = reinterpret_cast<float4*>(b); b += (size_t)P * 16;
-    c->pool.prev = reinterpret_cast<float4*>(b); b += (size_t)P * 16;
-    c->pool.hit = reinterpret_cast<uint2*>(b);
+    c->pool.ray = reinterpret_cast<float4*>(b); b += (size_t)P * 32;
+    c->pool.col = reinterpret_cast<float4*>(b); b += (size_t)P * 32;
+    c->pool.prev = reinterpret_cast<float4*>(b);
     PTB_CUDA_TRY(c, c->d_queues.reserve((size_t)P * 4 * (3 + kNumKinds)));
     PTB_CUDA_TRY(c, c->d_shadow.reserve((size_t)P * 48));
   }
@@ -763,16 +799,21 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   rp.method = o.method;
   rp.max_depth = o.max_depth ? o.max_depth : 50u;
   if (rp.max_depth > 255u) return set_error(c, PTB_ERR_INVALID, "max_depth must be <= 255");
+  if ((uint64_t)o.sample_offset + o.samples_per_pixel > kMaxSampleIndex)
+    return set_error(c, PTB_ERR_INVALID, "sample_offset + samples_per_pixel must be <= %u", kMaxSampleIndex);
   rp.rr_threshold = o.rr_threshold == PTB_RR_DEFAULT ? 3u : o.rr_threshold;
   rp.k0 = (uint32_t)o.seed; rp.k1 = (uint32_t)(o.seed >> 32);
 
   float* accum = c->d_accum.as<float>();
   const int T = 256;
+  const bool mis = o.method == PTB_METHOD_MIS;
   const uint32_t grid_p = (P + T - 1) / T;
+  auto capped = [&](const void* k) { const int g = persistent_grid(c, k, T); return (uint32_t)g < grid_p ? (uint32_t)g : grid_p; };
+  const uint32_t grid_gen = capped((const void*)k_generate);
+  const uint32_t grid_shade = capped(mis ? (const void*)k_shade<PTB_METHOD_MIS> : (const void*)k_shade<PTB_METHOD_NAIVE>);
   const bool count = c->opt_count_traversal;
   const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true> : (const void*)k_trace<false>, T);
   const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
-  const bool mis = o.method == PTB_METHOD_MIS;
   const bool prof = c->opt_time_kernels;
   if (prof)
     for (cudaEvent_t& e : c->ev_prof)
@@ -802,7 +843,7 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   while (!done) {
     k_prepare<<<1, 1, 0, st>>>(wc, o.method, iter == 0 ? 1u : 0u);
     PTB_PROF(0, 0);
-    k_generate<<<grid_p, T, 0, st>>>(c->dev, c->pool, q, wc, rp);
+    k_generate<<<grid_gen, T, 0, st>>>(c->dev, c->pool, q, wc, rp);
     PTB_PROF(0, 1);
     k_advance<<<1, 1, 0, st>>>(wc);
     PTB_PROF(1, 0);
@@ -810,8 +851,8 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
     else k_trace<false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
     PTB_PROF(1, 1);
     PTB_PROF(2, 0);
-    if (mis) k_shade<PTB_METHOD_MIS><<<grid_p, T, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
-    else k_shade<PTB_METHOD_NAIVE><<<grid_p, T, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+    if (mis) k_shade<PTB_METHOD_MIS><<<grid_shade, T, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+    else k_shade<PTB_METHOD_NAIVE><<<grid_shade, T, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
     PTB_PROF(2, 1);
     c->stats.kernel_launches += 5;
     c->stats.trace_launches += 1;

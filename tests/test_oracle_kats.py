@@ -1,0 +1,289 @@
+"""Pins the oracle (oracle/*.hpp) against every known-answer / property / statistical test the reference holds for
+the hot path, plus the hand-derived answers of SURVEY.md appendix B. No GPU.
+
+reference test                                              -> here
+  utility/mod.rs:141-149   sort_by_indices KAT              -> test_sort_by_indices_kat
+  utility/coord.rs:39-49   ONB inverse property             -> test_coordinate_inverse_property
+  bxdfs/lambertian.rs:30-48 chi^2 lambertian sample vs pdf  -> test_lambertian_chi_squared[local/world]
+  spherical_sampling.rs:244-252 cosine hemisphere           -> (same sampler, covered above)
+  distributions.rs:186-300 chi^2 Distribution1D/2D          -> test_distribution1d_chi_squared / test_distribution2d_chi_squared
+  tests/sampling.rs:239-297 furnace = 0.25 +- 0.001         -> test_furnace (naive, MIS, MIS + sky sampling)
+  tests/sampling.rs:181-207 MIS == naive                    -> test_mis_equals_naive
+  sky.rs:104-115 sky sampling (todo!() in the reference)    -> test_sky_sample_matches_pdf
+Philox4x32-10 (not in the reference: shared RNG of oracle and device) is pinned by the Random123 KAT vectors.
+"""
+import numpy as np
+import pytest
+from scipy import stats
+
+from conftest import furnace_scene
+
+
+def test_philox_random123_kat(orc):
+    assert [hex(x) for x in orc.philox([0] * 4, [0] * 2)] == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    assert [hex(x) for x in orc.philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2)] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
+    assert [hex(x) for x in orc.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0])] == \
+        ['0xd16cfe09', '0x94fdcceb', '0x5001e420', '0x24126ea1']
+
+
+def test_numpy_philox_matches_oracle(ptb, orc):
+    c = np.array([[1, 2, 3, 4], [0xFFFFFFFF, 7, 0, 9]], np.uint64)
+    out = ptb.meshgen.philox4x32_10(c[:, 0], c[:, 1], c[:, 2], c[:, 3], 0x5EED, 0)
+    for i in range(2):
+        assert [int(o[i]) for o in out] == [int(x) for x in orc.philox(c[i], [0x5EED, 0])]
+
+
+def test_sort_by_indices_kat(orc):
+    # values a..e encoded 0..4, indices [0,4,2,1,3] -> ["a","e","c","b","d"]
+    assert list(orc.sort_by_indices([0, 1, 2, 3, 4], [0, 4, 2, 1, 3])) == [0, 4, 2, 1, 3]
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 17, 1000):
+        perm = rng.permutation(n)
+        vals = rng.integers(0, 1 << 30, n)
+        assert np.array_equal(orc.sort_by_indices(vals, perm), vals[perm])  # new[i] = old[indices[i]]
+
+
+def test_coordinate_inverse_property(orc):
+    z = orc.random_unit_vectors(200, seed=3)
+    v = orc.random_unit_vectors(200, seed=4)
+    for zi, vi in zip(z, v):
+        a, b = orc.coord_roundtrip(zi, vi)
+        assert np.sum((vi - a) ** 2) < 1e-6 and np.sum((vi - b) ** 2) < 1e-6
+
+
+def test_next_previous_float_and_gamma(orc):
+    for f in (0.0, 1.0, -1.0, 1e-30, 123.456, -7.5e10):
+        f32 = np.float32(f)
+        assert orc.next_float(f32) == np.nextafter(f32, np.float32(np.inf))
+        assert orc.previous_float(f32) == np.nextafter(f32, np.float32(-np.inf))
+    assert orc.next_float(np.inf) == np.inf and orc.previous_float(-np.inf) == -np.inf
+    eps = np.float32(np.finfo(np.float32).eps)
+    for n in (2, 3, 5, 6, 7):
+        nm = np.float32(n) * np.float32(0.5) * eps
+        assert orc.gamma(n) == np.float32(nm / (np.float32(1) - nm))
+
+
+def test_offset_ray_moves_away_from_surface(orc):
+    o = np.array([1.0, 2.0, 3.0], np.float32)
+    n = np.array([0.0, 0.0, 1.0], np.float32)
+    e = np.array([3e-4] * 3, np.float32)
+    up, down = orc.offset_ray(o, n, e, True), orc.offset_ray(o, n, e, False)
+    assert up[2] > o[2] + 2.9e-4 and down[2] < o[2] - 2.9e-4
+    # x, y: offset component is 0 -> previous_float (utility/mod.rs:99-109)
+    assert up[0] == np.nextafter(np.float32(1), np.float32(-np.inf))
+
+
+def test_ray_new_quirk_q1(orc):
+    """rt_core/src/ray.rs:16-37: x<->z swap for BOTH x- and y-dominant directions."""
+    r = orc.ray_new((0, 0, 0), (0.2, 3.0, 0.5))       # y-dominant: swapped z is dir.x
+    d = r["direction"]
+    assert np.allclose(np.linalg.norm(d), 1, atol=1e-6)
+    assert np.allclose(r["shear"], [-d[2] / d[0], -d[1] / d[0], 1 / d[0]], rtol=1e-6)
+    r = orc.ray_new((0, 0, 0), (0.2, 0.3, 5.0))       # z-dominant: no swap
+    d = r["direction"]
+    assert np.allclose(r["shear"], [-d[0] / d[2], -d[1] / d[2], 1 / d[2]], rtol=1e-6)
+    assert np.allclose(r["d_inverse"], 1 / d, rtol=1e-6)
+
+
+def test_rtweekend1_appendix_b(ptb, orc, rtweekend1):
+    """camera basis, BVH shape, central ray, miss pixel."""
+    cam = rtweekend1.camera[0]
+    assert np.allclose(cam["horizontal"], [-32 / 9, 0, 0], atol=1e-5)
+    assert np.allclose(cam["vertical"], [0, 0, 2], atol=1e-5)
+    assert np.allclose(cam["lower_left"], [16 / 9, 1, -1], atol=1e-5)
+    oc = orc.camera_make((0, 0, 0), (0, 1, 0), (0, 0, 1), 121.28449291441745, 16 / 9, 0.0, 1.0)
+    for k in ("origin", "lower_left", "horizontal", "vertical"):
+        assert np.array_equal(oc[k], cam[k]), k            # host loader == oracle camera, bit for bit
+    o = orc.OracleScene(rtweekend1)
+    assert o.num_nodes() == 3 and o.num_lights() == 0
+    h = o.hit_record((0, 0, 0), (0, 1, 0))
+    assert h["hit"] and h["t"] == np.float32(0.5) and h["prim"] == 1 and h["out"]
+    assert np.allclose(h["point"], [0, 0.5, 0]) and np.allclose(h["normal"], [0, -1, 0])
+    # a ray that misses returns exactly the Lerp sky colour, for both integrators
+    d = np.array([0.3, 0.4, 0.8660254], np.float32)
+    d /= np.linalg.norm(d)
+    t = np.float32(0.5) * d[2] + np.float32(0.5)
+    expect = np.array([0.5, 0.7, 1.0], np.float32) * t + np.float32(1) * (np.float32(1) - t)
+    for method in (0, 1):
+        got = o.radiance((0, 0, 0), d, method, 16)
+        assert np.allclose(got, expect, atol=1e-6)
+
+
+def test_analytic_ray_sphere(ptb, orc):
+    s = furnace_scene(ptb)
+    o = orc.OracleScene(s)
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        org = rng.normal(size=3) * 3
+        if np.linalg.norm(org) < 0.6:
+            continue
+        target = rng.normal(size=3) * 0.3
+        d = target - org
+        d /= np.linalg.norm(d)
+        h = o.hit_record(org, d)
+        # closed form against the r = 0.5 sphere at the origin (may be missed: then the r = 1000 shell or prim 2)
+        b = np.dot(org, d)
+        disc = b * b - (np.dot(org, org) - 0.25)
+        if disc > 1e-6 and h["prim"] == 0:
+            t = -b - np.sqrt(disc)
+            assert abs(h["t"] - t) <= 1e-4 * max(1, t)
+            assert np.allclose(h["point"], org + t * d, atol=1e-4)
+            assert np.allclose(h["normal"], (org + t * d) / 0.5, atol=1e-3)
+
+
+def _chi2_sphere(dirs, pdf_fn, n_theta=40, n_phi=80):
+    """The reference's spherical chi^2 harness (spherical_sampling.rs:64-226) in numpy: bin samples on a (theta, phi)
+    grid, expected counts by midpoint quadrature of the pdf over each bin."""
+    n = len(dirs)
+    theta = np.arccos(np.clip(dirs[:, 2], -1, 1))
+    phi = np.mod(np.arctan2(dirs[:, 1], dirs[:, 0]), 2 * np.pi)
+    ti = np.minimum((theta / np.pi * n_theta).astype(int), n_theta - 1)
+    pj = np.minimum((phi / (2 * np.pi) * n_phi).astype(int), n_phi - 1)
+    obs = np.zeros((n_theta, n_phi))
+    np.add.at(obs, (ti, pj), 1)
+    sub = 8
+    exp = np.zeros((n_theta, n_phi))
+    for a in range(sub):
+        for b in range(sub):
+            th = (np.arange(n_theta)[:, None] + (a + 0.5) / sub) * np.pi / n_theta
+            ph = (np.arange(n_phi)[None, :] + (b + 0.5) / sub) * 2 * np.pi / n_phi
+            d = np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th) * np.ones_like(ph)], -1)
+            p = pdf_fn(d.reshape(-1, 3).astype(np.float32)).reshape(n_theta, n_phi)
+            exp += p * np.sin(th)
+    exp *= (np.pi / n_theta) * (2 * np.pi / n_phi) / (sub * sub) * n
+    # pool low-expectation cells like chi_squared.rs:6-70
+    order = np.argsort(exp.ravel())
+    e, o = exp.ravel()[order], obs.ravel()[order]
+    chi2, dof, pe, po = 0.0, 0, 0.0, 0.0
+    for ev, ov in zip(e, o):
+        pe += ev
+        po += ov
+        if pe >= 5:
+            chi2 += (po - pe) ** 2 / pe
+            dof += 1
+            pe = po = 0.0
+    return stats.chi2.sf(chi2, max(dof - 1, 1)), abs(exp.sum() - n) / n
+
+
+@pytest.mark.parametrize("local", [True, False])
+def test_lambertian_chi_squared(orc, local):
+    normal = np.array([0.0, 0.0, 1.0], np.float32) if local else orc.random_unit_vectors(1, seed=11)[0]
+    dirs = orc.lambertian_sample(normal, 400_000, seed=21, local=local)
+    assert np.allclose(np.linalg.norm(dirs, axis=1), 1, atol=1e-5)
+    p, mass_err = _chi2_sphere(dirs, lambda d: orc.lambertian_pdf(normal, d, local=local))
+    assert mass_err < 2e-3          # the pdf integrates to 1
+    assert p > 0.01 / 10            # Sidak-style threshold of the reference harness
+
+
+def test_random_unit_vector_is_uniform(orc):
+    d = orc.random_unit_vectors(300_000, seed=5)
+    assert np.allclose(np.linalg.norm(d, axis=1), 1, atol=1e-5)
+    p, _ = _chi2_sphere(d, lambda x: np.full(len(x), 1 / (4 * np.pi), np.float32))
+    assert p > 1e-3
+
+
+def test_distribution1d_chi_squared(orc):
+    rng = np.random.default_rng(3)
+    values = rng.uniform(0, 100, 100).astype(np.float32)
+    pdf, cdf, counts = orc.dist1d(values, nsamples=1_000_000, seed=9)
+    assert np.isclose(pdf.sum(), 1, atol=1e-5) and cdf[0] == 0 and np.isclose(cdf[-1], 1, atol=1e-6)
+    assert np.allclose(pdf, values / values.sum(), rtol=2e-4, atol=2e-6)   # pdf = differences of an f32 cdf
+    p64 = pdf.astype(np.float64)
+    assert stats.chisquare(counts, p64 / p64.sum() * counts.sum()).pvalue > 1e-3
+
+
+def test_distribution1d_all_zero_quirk_q3(orc):
+    """distributions.rs:26-31,51-72: an all-zero table is not normalised; sampling returns the last cell, pdf 0."""
+    pdf, cdf, counts = orc.dist1d(np.zeros(10, np.float32), nsamples=1000, seed=1)
+    assert np.all(pdf == 0) and np.all(cdf == 0)
+    assert counts[-1] == 1000 and counts[:-1].sum() == 0
+
+
+def test_distribution2d_chi_squared(orc):
+    rng = np.random.default_rng(4)
+    values = rng.uniform(0, 100, (30, 50)).astype(np.float32)
+    pdf, counts = orc.dist2d(values, 50, nsamples=2_000_000, seed=2)
+    expect = values / values.sum()
+    assert np.allclose(pdf, expect, rtol=5e-4, atol=1e-8)
+    e64 = expect.ravel().astype(np.float64)
+    assert stats.chisquare(counts.ravel(), e64 / e64.sum() * counts.sum()).pvalue > 1e-3
+
+
+def test_sky_sample_matches_pdf(ptb, orc, rtweekend1):
+    o = orc.OracleScene(rtweekend1)
+    d = o.sky_sample(400_000, seed=7)
+    assert np.allclose(np.linalg.norm(d, axis=1), 1, atol=1e-5)
+    p, mass_err = _chi2_sphere(d, o.sky_pdf, n_theta=25, n_phi=50)  # bins aligned with the 100x100 table
+    assert mass_err < 5e-3
+    assert p > 1e-3
+
+
+@pytest.mark.parametrize("res,method", [((0, 0), 0), ((0, 0), 1), ((10, 10), 1)])
+def test_furnace(ptb, orc, res, method):
+    o = orc.OracleScene(furnace_scene(ptb, res))
+    val = o.radiance((0, 0, 3), (0, 0, -1), method, 2_000_000, seed=13)
+    assert np.linalg.norm(val - 0.25) < 1e-3, val
+
+
+def test_mis_equals_naive(ptb, orc, overshadowed):
+    """tests/sampling.rs:181-207 on the shipped emitter scene, sky sampling off (quirk Q3 otherwise)."""
+    import copy
+    s = copy.deepcopy(overshadowed)
+    s.set_sky(int(s.sky["texture"][0]), (0, 0))
+    o = orc.OracleScene(s)
+    org, d = o.camera_ray(0.45, 0.4)
+    a = o.radiance(org, d, 0, 1_500_000, seed=3)
+    b = o.radiance(org, d, 1, 1_500_000, seed=3)
+    assert np.linalg.norm(a - b) < 2e-3 + 0.02 * np.linalg.norm(a), (a, b)
+
+
+def test_black_sky_mis_nan_quirk_q3(ptb, orc):
+    """Quirk Q3: a black but samplable sky has an all-zero table; when its NEE ray escapes, the contribution is
+    throughput*eval*w*0/0 = NaN and the whole sample is zeroed (mis.rs:42,88-90). One Lambertian sphere lit by one emitter,
+    seen from -z so that the (fixed, last-cell) sky direction leaves the surface: half of the NEE draws pick the sky and zero the sample."""
+    s = ptb.HostScene()
+    black = s.add_texture(ptb.TEX_SOLID, (0, 0, 0))
+    grey = s.add_texture(ptb.TEX_SOLID, (0.5, 0.5, 0.5))
+    white = s.add_texture(ptb.TEX_SOLID, (1, 1, 1))
+    lam = s.add_material(ptb.MAT_LAMBERTIAN, grey, 0.5)
+    emit = s.add_material(ptb.MAT_EMIT, white, 5.0)
+    s.add_sphere((0, 0, 0), 0.5, lam)
+    s.add_sphere((0, 3, -3), 0.5, emit)
+    s.set_camera((0, 1.0, -3), (0, 0, 0), (0, 1, 0), 25)   # the all-zero table always samples its last cell: direction ~ -z
+    s.set_sky(black, (100, 100))
+    ray = ((0, 0, -3), (0, 0, 1))
+    o = orc.OracleScene(s)
+    strict = np.array([o.radiance(*ray, 1, 1, seed=k)[0] for k in range(200)])
+    s.set_sky(black, (0, 0))
+    o = orc.OracleScene(s)
+    nosky = np.array([o.radiance(*ray, 1, 1, seed=k)[0] for k in range(200)])
+    assert np.all(np.isfinite(strict)) and np.all(np.isfinite(nosky))
+    assert 0.35 < (strict == 0).mean() < 0.65        # the sky draw (probability 1/2) poisons the sample
+    assert (nosky == 0).mean() < 0.05
+    # ...yet the estimator stays unbiased here: the surviving light samples carry the 1/(1/2) selection weight
+    assert abs(strict.mean() - nosky.mean()) < 0.25 * nosky.mean()
+
+
+def test_reference_bvh_vs_brute_force_and_lbvh(ptb, orc):
+    """The three CPU answers (reference SAH+BFS, brute force, ordered LBVH traversal) agree on random rays."""
+    s = ptb.meshgen.c3_scene(0.03)
+    o = orc.OracleScene(s)
+    rays = ptb.meshgen.philox_rays(20_000, seed=8, centre=(0, 4, 1), radius=4.0)
+    r, br = o.closest_hit(rays), o.closest_hit_brute(rays)
+    lb, nodes, prims = o.lbvh_closest_hit(rays)
+    d = rays["d"] / np.linalg.norm(rays["d"], axis=1, keepdims=True)
+    ok = ~((np.abs(d[:, 1]) > np.abs(d[:, 2])) & (np.abs(d[:, 0]) < 1e-3 * np.abs(d[:, 1])))
+    for other in (br, lb):
+        assert np.array_equal(r["prim"][ok], other["prim"][ok])
+        assert np.array_equal(r["t"][ok].view(np.uint32), other["t"][ok].view(np.uint32))
+
+
+def test_sah_builder_shape(ptb, orc, overshadowed):
+    o = orc.OracleScene(overshadowed)
+    order = o.bvh_order()
+    assert sorted(order) == list(range(14))      # a permutation of the 2 spheres + 12 cuboid triangles
+    assert o.num_lights() == 1 and 3 <= o.depth() <= 14
+    for split in (orc.SPLIT_MIDDLE, orc.SPLIT_EQUAL_COUNTS):
+        o2 = orc.OracleScene(overshadowed, split)
+        rays = ptb.meshgen.philox_rays(5000, seed=2, centre=(-0.3, 0.3, -0.3), radius=1.5)
+        assert np.array_equal(o2.closest_hit(rays)["t"], o.closest_hit(rays)["t"])

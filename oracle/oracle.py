@@ -59,6 +59,7 @@ def _load():
     lib.orc_lbvh_build.argtypes = [P]
     lib.orc_lbvh_export.argtypes = [P, P, P, P]
     lib.orc_lbvh_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
+    lib.orc_sah_ordered_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_philox4x32_10.argtypes = [P, P, P]
     lib.orc_sort_by_indices_u32.argtypes = [P, P, C.c_size_t]
     for n in ("orc_next_float", "orc_previous_float"):
@@ -143,6 +144,14 @@ class OracleScene:
         out = np.zeros(len(rays), hit_dtype)
         lib.orc_closest_hit_brute(self._h, _p(rays), len(rays), _p(out), threads)
         return out
+
+    def sah_ordered_closest_hit(self, rays, threads=0):
+        """Ordered, t-culled traversal of the reference's SAH tree: (hits, internal nodes expanded, prims tested)."""
+        rays = np.ascontiguousarray(rays, dtype=ray_dtype)
+        out = np.zeros(len(rays), hit_dtype)
+        counts = np.zeros(2, np.uint64)
+        lib.orc_sah_ordered_closest_hit(self._h, _p(rays), len(rays), _p(out), threads, _p(counts))
+        return out, int(counts[0]), int(counts[1])
 
     def hit_record(self, origin, direction):
         r = np.zeros(1, ray_dtype)

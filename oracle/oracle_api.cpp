@@ -244,6 +244,63 @@ void orc_lbvh_closest_hit(const orc_scene* s, const ptb_ray* rays, size_t n, ptb
   }
 }
 
+// Ordered, t-culled traversal of the REFERENCE's SAH tree (not something the reference does — it is BFS un-culled):
+// measures how many 2-child node fetches a SAH-quality tree would need for the same rays, to judge LBVH quality.
+// counts2: internal nodes expanded, primitives tested.
+void orc_sah_ordered_closest_hit(const orc_scene* s, const ptb_ray* rays, size_t n, ptb_hit* out, int threads, uint64_t* counts2) {
+  unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
+  std::vector<uint64_t> nv(nt ? nt : 1, 0), pt(nt ? nt : 1, 0);
+  const Bvh& bvh = s->bvh;
+  parallel_for(n, threads, [&](unsigned tid, size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      Ray ray(Vec3(rays[i].ox, rays[i].oy, rays[i].oz), Vec3(rays[i].dx, rays[i].dy, rays[i].dz), 0.0f);
+      Hit best, h;
+      Float best_t = INF_F;
+      uint32_t bp = PTB_MISS;
+      size_t stack[256];
+      Float stack_t[256];
+      int sp = 0;
+      size_t cur = 0;
+      bool have_cur = !bvh.nodes.empty();
+      while (have_cur) {
+        const Node& nd = bvh.nodes[cur];
+        have_cur = false;
+        if (!nd.has_children) {
+          for (size_t k = nd.primitive_offset; k < nd.primitive_offset + nd.number_primitives; ++k) {
+            ++pt[tid];
+            if (bvh.primitives[k].get_int(ray, h) && h.t > 0.0f && h.t < best_t) { best_t = h.t; best = h; bp = bvh.primitives[k].orig_id; }
+          }
+        } else {
+          ++nv[tid];
+          const Node& l = bvh.nodes[nd.children[0]];
+          const Node& r = bvh.nodes[nd.children[1]];
+          float lmn[3] = {l.bounds.min.x, l.bounds.min.y, l.bounds.min.z}, lmx[3] = {l.bounds.max.x, l.bounds.max.y, l.bounds.max.z};
+          float rmn[3] = {r.bounds.min.x, r.bounds.min.y, r.bounds.min.z}, rmx[3] = {r.bounds.max.x, r.bounds.max.y, r.bounds.max.z};
+          Float tl, tr;
+          bool hl = Lbvh::box_hit(lmn, lmx, ray, best_t, tl), hr = Lbvh::box_hit(rmn, rmx, ray, best_t, tr);
+          if (hl && hr) {
+            size_t nearc = nd.children[0], farc = nd.children[1];
+            Float tf = tr;
+            if (tr < tl) { nearc = nd.children[1]; farc = nd.children[0]; tf = tl; }
+            stack[sp] = farc; stack_t[sp] = tf; ++sp;
+            cur = nearc; have_cur = true;
+          } else if (hl) { cur = nd.children[0]; have_cur = true; }
+          else if (hr) { cur = nd.children[1]; have_cur = true; }
+        }
+        while (!have_cur && sp > 0) {
+          --sp;
+          if (stack_t[sp] <= best_t) { cur = stack[sp]; have_cur = true; }
+        }
+      }
+      fill_hit(out[i], bp != PTB_MISS, best, bp);
+    }
+  });
+  if (counts2) {
+    counts2[0] = counts2[1] = 0;
+    for (size_t i = 0; i < nv.size(); ++i) { counts2[0] += nv[i]; counts2[1] += pt[i]; }
+  }
+}
+
 // ------------------------------------------------------------- KAT hooks
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { Philox::block(ctr, key, out); }
 void orc_sort_by_indices_u32(uint32_t* values, const uint64_t* indices, size_t n) {

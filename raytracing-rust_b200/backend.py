@@ -133,8 +133,11 @@ class Context:
     def accum_clear(self):
         _check(self._h, L.lib.ptb_accum_clear(self._h))
 
-    def accum_read(self, width: int, height: int, normalise: bool = True) -> np.ndarray:
-        out = np.zeros(width * height * 3, np.float32)
+    def accum_read(self, width: int, height: int, normalise: bool = True, out: np.ndarray | None = None) -> np.ndarray:
+        """`out`: optional caller-owned float32 buffer of W*H*3 elements (e.g. pinned memory) to read into."""
+        if out is None:
+            out = np.empty(width * height * 3, np.float32)
+        out = out.reshape(-1)
         _check(self._h, L.lib.ptb_accum_read(self._h, L.ptr(out), out.size, 1 if normalise else 0))
         return out.reshape(height, width, 3)
 

@@ -142,15 +142,25 @@ int32_t ptb_synchronize(ptb_ctx* ctx) {
 int32_t ptb_scene_set_spheres(ptb_ctx* ctx, const ptb_sphere* p, size_t n) {
   CTX_OR_FAIL(ctx);
   if (n && !p) return set_error(c, PTB_ERR_INVALID, "null spheres");
-  try { c->spheres.assign(p, p + n); } catch (const std::bad_alloc&) { return set_error(c, PTB_ERR_OOM, "host OOM"); }
+  // "the library copies on upload": straight into device memory (pinned caller buffers DMA at PCIe rate), no host
+  // staging copy; the stream is drained before returning so the caller may reuse its buffer immediately.
   c->committed = false;
+  c->n_spheres = 0;
+  PTB_CUDA_TRY(c, c->d_raw_spheres.reserve(n * sizeof(ptb_sphere)));
+  if (n) PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_raw_spheres.p, p, n * sizeof(ptb_sphere), cudaMemcpyHostToDevice, c->stream));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->n_spheres = n;
   return PTB_OK;
 }
 int32_t ptb_scene_set_triangles(ptb_ctx* ctx, const ptb_triangle* p, size_t n) {
   CTX_OR_FAIL(ctx);
   if (n && !p) return set_error(c, PTB_ERR_INVALID, "null triangles");
-  try { c->triangles.assign(p, p + n); } catch (const std::bad_alloc&) { return set_error(c, PTB_ERR_OOM, "host OOM"); }
   c->committed = false;
+  c->n_tris = 0;
+  PTB_CUDA_TRY(c, c->d_raw_tris.reserve(n * sizeof(ptb_triangle)));
+  if (n) PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_raw_tris.p, p, n * sizeof(ptb_triangle), cudaMemcpyHostToDevice, c->stream));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  c->n_tris = n;
   return PTB_OK;
 }
 int32_t ptb_scene_set_materials(ptb_ctx* ctx, const ptb_material* p, size_t n) {

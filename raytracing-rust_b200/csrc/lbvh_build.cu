@@ -420,10 +420,10 @@ static int32_t build_sky(Ctx* c) {
     yvals.push_back(row_sum);
   }
   dist1d(yvals.data(), ry, ypdf, ycdf);
-  PTB_CUDA_TRY(c, c->d_sky_ycdf.alloc(ycdf.size() * 4));
-  PTB_CUDA_TRY(c, c->d_sky_ypdf.alloc(ypdf.size() * 4));
-  PTB_CUDA_TRY(c, c->d_sky_xcdf.alloc(xcdf.size() * 4));
-  PTB_CUDA_TRY(c, c->d_sky_xpdf.alloc(xpdf.size() * 4));
+  PTB_CUDA_TRY(c, c->d_sky_ycdf.reserve(ycdf.size() * 4));
+  PTB_CUDA_TRY(c, c->d_sky_ypdf.reserve(ypdf.size() * 4));
+  PTB_CUDA_TRY(c, c->d_sky_xcdf.reserve(xcdf.size() * 4));
+  PTB_CUDA_TRY(c, c->d_sky_xpdf.reserve(xpdf.size() * 4));
   PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_sky_ycdf.p, ycdf.data(), ycdf.size() * 4, cudaMemcpyHostToDevice, c->stream));
   PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_sky_ypdf.p, ypdf.data(), ypdf.size() * 4, cudaMemcpyHostToDevice, c->stream));
   PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_sky_xcdf.p, xcdf.data(), xcdf.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -437,16 +437,24 @@ static int32_t build_sky(Ctx* c) {
 }
 
 // ------------------------------------------------------------------------------------------ host: build
+// Material-index validation + light list, on the device: the host never walks the primitive arrays.
+// out[0] = number of lights, out[1] = 1 if some material index is out of range; list = light primitive ids (unordered).
+__global__ void k_collect_lights(const ptb_sphere* __restrict__ spheres, uint32_t n_spheres, const ptb_triangle* __restrict__ tris,
+                                 uint32_t n_prims, const DevMaterial* __restrict__ mats, uint32_t n_mats, uint32_t* out,
+                                 uint32_t* __restrict__ list) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_prims) return;
+  const uint32_t mat = i < n_spheres ? spheres[i].material : tris[i - n_spheres].material;
+  if (mat >= n_mats) { atomicOr(out + 1, 1u); return; }
+  if (mats[mat].kind == PTB_MAT_EMIT) list[atomicAdd(out, 1u)] = i;  // material.is_light() (acceleration/mod.rs:84-88)
+}
+
 int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
-  const size_t ns = c->spheres.size(), nt = c->triangles.size();
+  const size_t ns = c->n_spheres, nt = c->n_tris;
   const size_t n = ns + nt;
   if (n >= (size_t)kSlotMask) return set_error(c, PTB_ERR_INVALID, "too many primitives (%zu)", n);
   if (!c->have_camera) return set_error(c, PTB_ERR_INVALID, "scene has no camera");
   if (c->materials.empty() || c->textures.empty()) return set_error(c, PTB_ERR_INVALID, "scene has no materials/textures");
-  for (const auto& s : c->spheres)
-    if (s.material >= c->materials.size()) return set_error(c, PTB_ERR_INVALID, "sphere material index out of range");
-  for (const auto& t : c->triangles)
-    if (t.material >= c->materials.size()) return set_error(c, PTB_ERR_INVALID, "triangle material index out of range");
   for (const auto& m : c->materials)
     if (m.texture >= c->textures.size()) return set_error(c, PTB_ERR_INVALID, "material texture index out of range");
   if (!c->have_sky) {  // loader default: __DEFAULT_TEX, 100x100 (loader/src/misc.rs:22-25) needs an explicit sky here
@@ -478,8 +486,8 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
     dt[i].b[0] = t.b.x; dt[i].b[1] = t.b.y; dt[i].b[2] = t.b.z;
     dt[i]._pad = 0;
   }
-  PTB_CUDA_TRY(c, c->d_materials.alloc(dm.size() * sizeof(DevMaterial)));
-  PTB_CUDA_TRY(c, c->d_textures.alloc(dt.size() * sizeof(DevTexture)));
+  PTB_CUDA_TRY(c, c->d_materials.reserve(dm.size() * sizeof(DevMaterial)));
+  PTB_CUDA_TRY(c, c->d_textures.reserve(dt.size() * sizeof(DevTexture)));
   PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_materials.p, dm.data(), dm.size() * sizeof(DevMaterial), cudaMemcpyHostToDevice, st));
   PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_textures.p, dt.data(), dt.size() * sizeof(DevTexture), cudaMemcpyHostToDevice, st));
   PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
@@ -506,49 +514,52 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
     return PTB_OK;
   }
 
-  // lights in ORIGINAL primitive order (deterministic): material.is_light() (acceleration/mod.rs:84-88)
-  std::vector<uint32_t> light_prims;
-  for (size_t i = 0; i < ns; ++i)
-    if (c->materials[c->spheres[i].material].kind == PTB_MAT_EMIT) light_prims.push_back((uint32_t)i);
-  for (size_t i = 0; i < nt; ++i)
-    if (c->materials[c->triangles[i].material].kind == PTB_MAT_EMIT) light_prims.push_back((uint32_t)(ns + i));
-
-  DevBuf raw_spheres, raw_tris, bmin, bmax, bounds, keys_a, keys_b, vals_a, vals_b, hist, leaf_parent, nbmin, nbmax, flags,
-      prim_slot, d_light_prims;
-  PTB_CUDA_TRY(c, raw_spheres.alloc(ns * sizeof(ptb_sphere)));
-  PTB_CUDA_TRY(c, raw_tris.alloc(nt * sizeof(ptb_triangle)));
-  if (ns) PTB_CUDA_TRY(c, cudaMemcpyAsync(raw_spheres.p, c->spheres.data(), ns * sizeof(ptb_sphere), cudaMemcpyHostToDevice, st));
-  if (nt) PTB_CUDA_TRY(c, cudaMemcpyAsync(raw_tris.p, c->triangles.data(), nt * sizeof(ptb_triangle), cudaMemcpyHostToDevice, st));
-
+  // Primitives were uploaded by ptb_scene_set_* (c->d_raw_spheres / d_raw_tris). Build temporaries live in the context
+  // and only ever grow: a re-commit of a same-sized scene performs no cudaMalloc / cudaFree at all.
+  DevBuf &raw_spheres = c->d_raw_spheres, &raw_tris = c->d_raw_tris;
+  DevBuf &bmin = c->scratch[0], &bmax = c->scratch[1], &bounds = c->scratch[2], &keys_a = c->scratch[3], &keys_b = c->scratch[4],
+         &vals_a = c->scratch[5], &vals_b = c->scratch[6], &hist = c->scratch[7], &leaf_parent = c->scratch[8],
+         &nbmin = c->scratch[9], &nbmax = c->scratch[10], &flags = c->scratch[11], &prim_slot = c->scratch[12],
+         &d_light_prims = c->scratch[13], &d_light_tmp = c->scratch[14], &d_light_out = c->scratch[15];
   const uint32_t n32 = (uint32_t)n, ns32 = (uint32_t)ns, nt32 = (uint32_t)nt;
   const uint32_t n_tiles = (n32 + RS_TILE - 1) / RS_TILE;
-  PTB_CUDA_TRY(c, bmin.alloc(n * 16));
-  PTB_CUDA_TRY(c, bmax.alloc(n * 16));
-  PTB_CUDA_TRY(c, bounds.alloc(6 * 4));
-  PTB_CUDA_TRY(c, keys_a.alloc(n * 4));
-  PTB_CUDA_TRY(c, keys_b.alloc(n * 4));
-  PTB_CUDA_TRY(c, vals_a.alloc(n * 4));
-  PTB_CUDA_TRY(c, vals_b.alloc(n * 4));
-  PTB_CUDA_TRY(c, hist.alloc((size_t)256 * n_tiles * 4));
-  PTB_CUDA_TRY(c, leaf_parent.alloc(n * 4));
-  PTB_CUDA_TRY(c, nbmin.alloc(c->n_nodes * 16));
-  PTB_CUDA_TRY(c, nbmax.alloc(c->n_nodes * 16));
-  PTB_CUDA_TRY(c, flags.alloc(c->n_nodes * 4));
-  PTB_CUDA_TRY(c, prim_slot.alloc(n * 4));
-  PTB_CUDA_TRY(c, c->d_nodes.alloc(c->n_nodes * sizeof(BvhNode)));
-  PTB_CUDA_TRY(c, c->d_geom.alloc(n * 48));
-  PTB_CUDA_TRY(c, c->d_normals.alloc(n * 48));
-  PTB_CUDA_TRY(c, c->d_slot_mat.alloc(n * 4));
-  PTB_CUDA_TRY(c, c->d_lights.alloc(light_prims.size() * 4));
-  PTB_CUDA_TRY(c, d_light_prims.alloc(light_prims.size() * 4));
+  PTB_CUDA_TRY(c, bmin.reserve(n * 16));
+  PTB_CUDA_TRY(c, bmax.reserve(n * 16));
+  PTB_CUDA_TRY(c, bounds.reserve(6 * 4));
+  PTB_CUDA_TRY(c, keys_a.reserve(n * 4));
+  PTB_CUDA_TRY(c, keys_b.reserve(n * 4));
+  PTB_CUDA_TRY(c, vals_a.reserve(n * 4));
+  PTB_CUDA_TRY(c, vals_b.reserve(n * 4));
+  PTB_CUDA_TRY(c, hist.reserve((size_t)256 * n_tiles * 4));
+  PTB_CUDA_TRY(c, leaf_parent.reserve(n * 4));
+  PTB_CUDA_TRY(c, nbmin.reserve(c->n_nodes * 16));
+  PTB_CUDA_TRY(c, nbmax.reserve(c->n_nodes * 16));
+  PTB_CUDA_TRY(c, flags.reserve(c->n_nodes * 4));
+  PTB_CUDA_TRY(c, prim_slot.reserve(n * 4));
+  PTB_CUDA_TRY(c, d_light_prims.reserve(n * 4));
+  PTB_CUDA_TRY(c, d_light_tmp.reserve(n * 4));
+  PTB_CUDA_TRY(c, d_light_out.reserve(8));
+  PTB_CUDA_TRY(c, c->d_nodes.reserve(c->n_nodes * sizeof(BvhNode)));
+  PTB_CUDA_TRY(c, c->d_geom.reserve(n * 48));
+  PTB_CUDA_TRY(c, c->d_normals.reserve(n * 48));
+  PTB_CUDA_TRY(c, c->d_slot_mat.reserve(n * 4));
+  PTB_CUDA_TRY(c, c->d_morton.reserve(n * 4));
+  PTB_CUDA_TRY(c, c->d_slot_prim.reserve(n * 4));
 
+  const int T = 256;
+  const uint32_t gn = (n32 + T - 1) / T;
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
+  // lights + material-index validation (device), then the light ids are put in ORIGINAL primitive order (deterministic)
+  uint32_t h_light_out[2] = {0u, 0u};
+  PTB_CUDA_TRY(c, cudaMemsetAsync(d_light_out.p, 0, 8, st));
+  k_collect_lights<<<gn, T, 0, st>>>(raw_spheres.as<ptb_sphere>(), ns32, raw_tris.as<ptb_triangle>(), n32,
+                                     c->d_materials.as<DevMaterial>(), (uint32_t)c->materials.size(), d_light_out.as<uint32_t>(),
+                                     d_light_prims.as<uint32_t>());
+  c->stats.kernel_launches += 1;
   {
     const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
     PTB_CUDA_TRY(c, cudaMemcpyAsync(bounds.p, init, sizeof init, cudaMemcpyHostToDevice, st));
   }
-  const int T = 256;
-  const uint32_t gn = (n32 + T - 1) / T;
   k_prim_bounds<<<gn, T, 0, st>>>(raw_spheres.as<ptb_sphere>(), ns32, raw_tris.as<ptb_triangle>(), nt32, bmin.as<float4>(),
                                   bmax.as<float4>(), bounds.as<uint32_t>());
   k_morton<<<gn, T, 0, st>>>(bmin.as<float4>(), bmax.as<float4>(), n32, bounds.as<uint32_t>(), keys_a.as<uint32_t>(),
@@ -580,18 +591,34 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
                              c->d_materials.as<DevMaterial>(), c->d_geom.as<float4>(), c->d_normals.as<float4>(),
                              c->d_slot_mat.as<uint32_t>(), prim_slot.as<uint32_t>());
   c->stats.kernel_launches += 1;
-  if (!light_prims.empty()) {
-    PTB_CUDA_TRY(c, cudaMemcpyAsync(d_light_prims.p, light_prims.data(), light_prims.size() * 4, cudaMemcpyHostToDevice, st));
-    const uint32_t nl = (uint32_t)light_prims.size();
-    k_light_slots<<<(nl + T - 1) / T, T, 0, st>>>(d_light_prims.as<uint32_t>(), nl, ns32, prim_slot.as<uint32_t>(),
-                                                  c->d_lights.as<uint32_t>());
-    c->stats.kernel_launches += 1;
-  }
-  // keep the sorted keys / ids for ptb_bvh_export
-  PTB_CUDA_TRY(c, c->d_morton.alloc(n * 4));
-  PTB_CUDA_TRY(c, c->d_slot_prim.alloc(n * 4));
+  // keep the sorted keys / ids for ptb_bvh_export and the traversal's tie-break
   PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_morton.p, ka, n * 4, cudaMemcpyDeviceToDevice, st));
   PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_slot_prim.p, va, n * 4, cudaMemcpyDeviceToDevice, st));
+  // light list: count + validation flag back to the host (8 bytes), ids sorted with the same radix passes
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(h_light_out, d_light_out.p, 8, cudaMemcpyDeviceToHost, st));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
+  if (h_light_out[1]) return set_error(c, PTB_ERR_INVALID, "primitive material index out of range");
+  const uint32_t nl = h_light_out[0];
+  if (nl) {
+    PTB_CUDA_TRY(c, c->d_lights.reserve((size_t)nl * 4));
+    uint32_t *la = d_light_prims.as<uint32_t>(), *lb = d_light_tmp.as<uint32_t>();
+    if (nl > 1) {
+      const uint32_t lt = (nl + RS_TILE - 1) / RS_TILE;  // <= n_tiles: hist is large enough
+      // values ride along unused: keys double as values (keys_b / vals_b are free again)
+      uint32_t *lva = keys_b.as<uint32_t>(), *lvb = vals_b.as<uint32_t>();
+      for (int pass = 0; pass < 4; ++pass) {
+        k_radix_pass<false><<<lt, RS_THREADS, 0, st>>>(la, lva, lb, lvb, nl, pass * 8, hist.as<uint32_t>(), lt);
+        k_radix_scan<<<1, 256, 0, st>>>(hist.as<uint32_t>(), lt);
+        k_radix_pass<true><<<lt, RS_THREADS, 0, st>>>(la, lva, lb, lvb, nl, pass * 8, hist.as<uint32_t>(), lt);
+        c->stats.kernel_launches += 3;
+        uint32_t* t;
+        t = la; la = lb; lb = t;
+        t = lva; lva = lvb; lvb = t;
+      }
+    }
+    k_light_slots<<<(nl + T - 1) / T, T, 0, st>>>(la, nl, ns32, prim_slot.as<uint32_t>(), c->d_lights.as<uint32_t>());
+    c->stats.kernel_launches += 1;
+  }
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
   PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
   PTB_CUDA_TRY(c, cudaGetLastError());
@@ -605,7 +632,7 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
   c->dev.slot_mat = c->d_slot_mat.as<uint32_t>();
   c->dev.nodes = c->d_nodes.as<BvhNode>();
   c->dev.lights = c->d_lights.as<uint32_t>();
-  c->dev.n_lights = (uint32_t)light_prims.size();
+  c->dev.n_lights = nl;
   c->committed = true;
   return PTB_OK;
 }

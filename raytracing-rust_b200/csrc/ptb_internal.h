@@ -75,9 +75,11 @@ struct Ctx {
   std::string last_error;
   int sm_count = 148;
 
-  // host copy of the scene (ptb_scene_set_*)
-  std::vector<ptb_sphere> spheres;
-  std::vector<ptb_triangle> triangles;
+  // scene as handed over by ptb_scene_set_*: primitives go straight to the device (no host copy), the small tables
+  // are kept on the host until commit
+  DevBuf d_raw_spheres, d_raw_tris;
+  size_t n_spheres = 0, n_tris = 0;
+  DevBuf scratch[16];  // LBVH build temporaries, grow-only (lbvh_build.cu)
   std::vector<ptb_material> materials;
   std::vector<ptb_texture> textures;
   ptb_camera camera{};

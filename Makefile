@@ -11,7 +11,7 @@ CPP_SRCS := $(PKG)/host/ssml_loader.cpp $(PKG)/host/image_out.cpp
 HDRS     := include/ptb200.h $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h)
 OBJS     := $(CU_SRCS:.cu=.o) $(CPP_SRCS:.cpp=.o)
 
-all: $(PKG)/libptb200.so oracle
+all: $(PKG)/libptb200.so cli oracle
 
 $(PKG)/csrc/%.o: $(PKG)/csrc/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)

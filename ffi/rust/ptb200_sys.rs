@@ -1,0 +1,53 @@
+//! `extern "C"` surface of libptb200.so — mirrors include/ptb200.h one to one (un-compiled here).
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_void};
+
+pub const PTB_OK: i32 = 0;
+pub const PTB_MISS: u32 = 0xFFFF_FFFF;
+pub const PTB_RR_DEFAULT: u32 = 0xFFFF_FFFF;
+pub const PTB_METHOD_NAIVE: u32 = 0;
+pub const PTB_METHOD_MIS: u32 = 1;
+
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct ptb_vec3 { pub x: f32, pub y: f32, pub z: f32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct ptb_sphere { pub center: ptb_vec3, pub radius: f32, pub material: u32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct ptb_triangle { pub p: [ptb_vec3; 3], pub n: [ptb_vec3; 3], pub material: u32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct ptb_material { pub kind: u32, pub texture: u32, pub param: f32, pub ior: ptb_vec3, pub metallic: f32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct ptb_texture { pub kind: u32, pub a: ptb_vec3, pub b: ptb_vec3 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct ptb_camera { pub origin: ptb_vec3, pub lower_left: ptb_vec3, pub horizontal: ptb_vec3, pub vertical: ptb_vec3 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct ptb_sky { pub texture: u32, pub sampler_res_x: u32, pub sampler_res_y: u32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct ptb_ray { pub o: [f32; 3], pub _pad0: f32, pub d: [f32; 3], pub _pad1: f32 }
+#[repr(C)] #[derive(Clone, Copy)] pub struct ptb_hit { pub t: f32, pub prim: u32, pub u: f32, pub v: f32 }
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct ptb_render_opts {
+    pub width: u32, pub height: u32, pub samples_per_pixel: u32, pub sample_offset: u32,
+    pub method: u32, pub max_depth: u32, pub rr_threshold: u32, pub flags: u32, pub seed: u64,
+}
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct ptb_stats {
+    pub rays_camera: u64, pub rays_bounce: u64, pub rays_shadow_light: u64, pub rays_shadow_sky: u64,
+    pub rays_reference: u64, pub paths: u64, pub wavefront_iterations: u64, pub kernel_launches: u64,
+    pub nodes_fetched: u64, pub prims_tested: u64, pub rays_counted: u64, pub trace_launches: u64,
+    pub build_ms: f64, pub render_ms: f64, pub ms_generate: f64, pub ms_trace: f64, pub ms_shade: f64, pub ms_shadow: f64,
+}
+#[repr(C)] pub struct ptb_ctx { _private: [u8; 0] }
+pub type ptb_progress_fn = Option<unsafe extern "C" fn(user: *mut c_void, samples_completed: u64, rays_shot: u64) -> i32>;
+
+extern "C" {
+    pub fn ptb_abi_version() -> u32;
+    pub fn ptb_create(device: i32, out: *mut *mut ptb_ctx) -> i32;
+    pub fn ptb_destroy(ctx: *mut ptb_ctx) -> i32;
+    pub fn ptb_last_error(ctx: *const ptb_ctx) -> *const c_char;
+    pub fn ptb_scene_set_spheres(ctx: *mut ptb_ctx, p: *const ptb_sphere, n: usize) -> i32;
+    pub fn ptb_scene_set_triangles(ctx: *mut ptb_ctx, p: *const ptb_triangle, n: usize) -> i32;
+    pub fn ptb_scene_set_materials(ctx: *mut ptb_ctx, p: *const ptb_material, n: usize) -> i32;
+    pub fn ptb_scene_set_textures(ctx: *mut ptb_ctx, p: *const ptb_texture, n: usize) -> i32;
+    pub fn ptb_scene_set_camera(ctx: *mut ptb_ctx, cam: *const ptb_camera) -> i32;
+    pub fn ptb_scene_set_sky(ctx: *mut ptb_ctx, sky: *const ptb_sky) -> i32;
+    pub fn ptb_scene_commit(ctx: *mut ptb_ctx, build_flags: u32) -> i32;
+    pub fn ptb_closest_hit(ctx: *mut ptb_ctx, rays: *const ptb_ray, n: usize, hits: *mut ptb_hit) -> i32;
+    pub fn ptb_render(ctx: *mut ptb_ctx, opts: *const ptb_render_opts, progress: ptb_progress_fn, user: *mut c_void) -> i32;
+    pub fn ptb_accum_clear(ctx: *mut ptb_ctx) -> i32;
+    pub fn ptb_accum_read(ctx: *mut ptb_ctx, rgb: *mut f32, n_floats: usize, normalise: i32) -> i32;
+    pub fn ptb_accum_device_ptr(ctx: *mut ptb_ctx, d_ptr: *mut *mut c_void, n_floats: *mut usize) -> i32;
+    pub fn ptb_stats_get(ctx: *mut ptb_ctx, out: *mut ptb_stats) -> i32;
+}

@@ -1,0 +1,67 @@
+"""(1) The V / T of the algorithmic-bytes-per-ray figure: the device's instrumented traversal vs the CPU LBVH oracle's
+ordered, t-culled traversal of the same (bit-exact) tree. The device walks speculatively (a lane holding a postponed leaf
+keeps descending before its best-t is updated), so it may fetch slightly MORE nodes than the sequential oracle — never
+fewer primitives' worth of work than needed, and the hits are identical.
+(2) The C++ frontend (ptb200-cli) end to end against the Python binding."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import random_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def test_traversal_counts_match_lbvh_oracle(ptb, orc, gpu_ctx):
+    s = ptb.meshgen.c3_scene(0.1)
+    rays = random_rays(ptb, 200_000, 21, centre=(0, 4, 1), radius=5.0)
+    gpu_ctx.upload(s)
+    gpu_ctx.commit()
+    gpu_ctx.set_option(ptb._lib.OPT_COUNT_TRAVERSAL, 1)
+    gpu_ctx.stats_reset()
+    g = gpu_ctx.closest_hit(rays)
+    st = gpu_ctx.stats()
+    gpu_ctx.set_option(ptb._lib.OPT_COUNT_TRAVERSAL, 0)
+    o = orc.OracleScene(s, split_type=-1)
+    h, nodes, prims = o.lbvh_closest_hit(rays)
+    assert np.array_equal(g["prim"], h["prim"]) and np.array_equal(g["t"].view(np.uint32), h["t"].view(np.uint32))
+    assert st.rays_counted == len(rays)
+    v_dev, v_cpu = st.nodes_fetched / len(rays), nodes / len(rays)
+    t_dev, t_cpu = st.prims_tested / len(rays), prims / len(rays)
+    assert v_cpu <= v_dev <= 1.10 * v_cpu, (v_dev, v_cpu)     # speculation costs a few percent of extra node fetches
+    assert t_cpu <= t_dev <= 1.25 * t_cpu, (t_dev, t_cpu)
+
+
+def test_stats_kernel_timers(ptb, gpu_ctx, rtweekend1):
+    sc = ptb.Scene(rtweekend1, ctx=gpu_ctx)
+    gpu_ctx.set_option(ptb._lib.OPT_TIME_KERNELS, 1)
+    gpu_ctx.stats_reset()
+    sc.render(ptb.RenderOptions(samples_per_pixel=8, render_method=1, width=320, height=180))
+    st = gpu_ctx.stats()
+    gpu_ctx.set_option(ptb._lib.OPT_TIME_KERNELS, 0)
+    assert st.ms_trace > 0 and st.ms_shade > 0 and st.ms_generate > 0 and st.ms_shadow > 0
+    assert st.ms_trace + st.ms_shade + st.ms_generate + st.ms_shadow <= st.render_ms * 1.05
+    assert st.trace_launches == st.wavefront_iterations and st.kernel_launches >= 6 * st.wavefront_iterations
+
+
+def test_cli_matches_binding(ptb, gpu_ctx, root, tmp_path):
+    cli = os.path.join(root, "raytracing-rust_b200", "ptb200-cli")
+    assert os.path.exists(cli), "build the frontend with `make cli`"
+    out = tmp_path / "img.pfm"
+    scene_path = os.path.join(root, "scenes", "overshadowed.ssml")
+    r = subprocess.run([cli, "-f", scene_path, "-s", "8", "-x", "96", "-y", "54", "-r", "naive", "-o", str(out), "--seed", "5"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Render started:" in r.stderr and "Rays shot:" in r.stderr and "Mray/s" in r.stderr
+    raw = out.read_bytes()
+    hdr_end = raw.index(b"-1.0\n") + 5
+    img = np.frombuffer(raw[hdr_end:], np.float32).reshape(54, 96, 3)[::-1]     # PFM stores rows bottom-up
+    sc = ptb.Scene(ptb.load_file(scene_path), ctx=gpu_ctx)
+    ref = sc.render(ptb.RenderOptions(samples_per_pixel=8, render_method=0, width=96, height=54, seed=5))
+    assert np.max(np.abs(img - ref)) < 1e-5
+    # argument errors mirror clap's behaviour: usage + non-zero exit, and the gui flag answers like the reference
+    assert subprocess.run([cli], capture_output=True).returncode != 0
+    g = subprocess.run([cli, "-g", "-f", scene_path], capture_output=True, text=True)
+    assert g.returncode == 0 and "feature: gui not enabled" in g.stdout

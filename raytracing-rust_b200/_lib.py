@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libptb200.so")
+LIB_PATH = os.environ.get("PTB200_LIB") or os.path.join(_HERE, "libptb200.so")  # PTB200_LIB: tuning builds only
 
 PTB_OK = 0
 ERR_NAMES = {

@@ -22,6 +22,7 @@ namespace ptb {
 
 struct RenderParams {
   uint32_t width, height, npix;
+  uint32_t tile_w, tile_h;  // pixel issue order (k_generate); tile_h == 1 -> row-major
   uint32_t sample_offset;
   uint32_t method, max_depth, rr_threshold;
   uint32_t k0, k1;  // Philox key
@@ -215,9 +216,21 @@ k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams 
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
   const uint32_t slot = q.free_slots[wc->free_base + (n_new - 1u - i)];
   const unsigned long long g = wc->next_sample + i;
-  const uint32_t pixel = (uint32_t)(g % rp.npix);
+  const uint32_t lin = (uint32_t)(g % rp.npix);
   const uint32_t sample = rp.sample_offset + (uint32_t)(g / rp.npix);
-  const uint32_t x = pixel % rp.width, y = pixel / rp.width;
+  // A warp's 32 consecutive work items cover a tile_w x tile_h block of pixels (8x4 when the image allows) instead of a
+  // 32x1 strip: camera rays of a warp stay coherent in both directions. Only the issue ORDER changes; RNG and
+  // accumulator are keyed by the true pixel index.
+  uint32_t x, y;
+  if (rp.tile_h > 1u) {
+    const uint32_t tile = lin >> 5, within = lin & 31u, tiles_x = rp.width / rp.tile_w;
+    x = (tile % tiles_x) * rp.tile_w + within % rp.tile_w;
+    y = (tile / tiles_x) * rp.tile_h + within / rp.tile_w;
+  } else {
+    x = lin % rp.width;
+    y = lin / rp.width;
+  }
+  const uint32_t pixel = y * rp.width + x;
   const uint4 r = philox4x32_10(pixel, sample, (0u << 8) | RNG_JITTER, 0u, rp.k0, rp.k1);
   // random_sampler.rs:55-59 (note W-1 / H-1)
   const float u = (u32_to_unit(r.x) + (float)x) / (float)(rp.width - 1u);
@@ -275,8 +288,14 @@ struct TraceRetire {
   }
 };
 
+#ifndef PTB_TRACE_MIN_BLOCKS
+#define PTB_TRACE_MIN_BLOCKS 5  // 48 registers: +4 % over the unconstrained 56-register build (sweep in profiles/)
+#endif
+#ifndef PTB_SHADE_MIN_BLOCKS
+#define PTB_SHADE_MIN_BLOCKS 1
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PTB_TRACE_MIN_BLOCKS)
 k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t cnt_nodes = 0, cnt_prims = 0, cnt_rays = 0;
@@ -324,7 +343,7 @@ PTB_DEV void finish_path(float* __restrict__ accum, uint32_t pixel, v3 L, bool n
 }
 
 template <int METHOD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PTB_SHADE_MIN_BLOCKS)
 k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t nxt = wc->cur ^ 1u;
@@ -795,6 +814,12 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
 
   RenderParams rp;
   rp.width = o.width; rp.height = o.height; rp.npix = npix;
+  rp.tile_w = 32u; rp.tile_h = 1u;
+  // Measured on B200 (C3 and rtweekend1 4K): 8x4 tiles gain nothing in k_trace (-2 %) and cost 5 % in k_shade (less
+  // coalesced accumulator atomics), so row-major order is the default; PTB_TILES=1 enables the tiled order.
+  if (getenv("PTB_TILES"))
+    for (uint32_t th = 4u; th > 1u; th >>= 1)
+      if (o.height % th == 0u && o.width % (32u / th) == 0u) { rp.tile_h = th; rp.tile_w = 32u / th; break; }
   rp.sample_offset = o.sample_offset;
   rp.method = o.method;
   rp.max_depth = o.max_depth ? o.max_depth : 50u;

@@ -42,8 +42,9 @@ struct PathPool {
   uint32_t capacity = 0;
   // Records are 32-byte sectors written whole by one thread (a 16-byte store to a scattered slot costs a
   // read-modify-write at the DRAM side; two adjacent 16-byte stores do not).
-  float4* ray = nullptr;   // [2*slot]   origin.xyz | hit t        [2*slot+1] normalised direction.xyz | hit leaf ref (bits)
-  float4* col = nullptr;   // [2*slot]   throughput.rgb | pixel    [2*slot+1] radiance so far .rgb | sample<<9 | flags<<8 | depth
+  // one 64-byte block per path (4 x float4); col == ray + 2
+  float4* ray = nullptr;   // [4*slot]   origin.xyz | hit t        [4*slot+1] normalised direction.xyz | hit leaf ref (bits)
+  float4* col = nullptr;   // [4*slot]   throughput.rgb | pixel    [4*slot+1] radiance so far .rgb | sample<<9 | flags<<8 | depth
   float4* prev = nullptr;  // MIS only: previous (un-offset) hit point.xyz | m_pdf of the last BSDF sample
 };
 constexpr uint32_t kMaxSampleIndex = 1u << 23;  // sample index shares a word with depth (8 bits) and one flag

@@ -56,19 +56,27 @@ PTB_DEV void trav_init(TravState& s, uint32_t n_prims, float tmax) {
   s.best_ref = kNone;
 }
 
-PTB_DEV uint32_t trav_pop(TravState& s, const uint32_t* stack, const float* stack_t) {
-  while (s.sp > 0) {
+// Stack entry = (node or leaf reference, cull key of its box) in one 8-byte local-memory word.
+// Pops the next entry whose box can still hold a closer hit; a popped leaf is postponed when the slot is free and the
+// pop continues, so on return `cur` is an internal node, a second leaf, or kNone (stack exhausted).
+PTB_DEV void trav_pop(TravState& s, const uint2* stack) {
+  for (;;) {
+    if (s.sp == 0) { s.cur = kNone; return; }
     --s.sp;
-    if (stack_t[s.sp] <= s.best_t) return stack[s.sp];
+    const uint2 e = stack[s.sp];
+    if (__uint_as_float(e.y) <= s.best_t) {
+      if ((e.x & PTB_LEAF_BIT) && s.leaf == kNone) { s.leaf = e.x; continue; }
+      s.cur = e.x;
+      return;
+    }
   }
-  return kNone;
 }
 
 // One internal-node step of the lane: fetch the 64-byte node, test both child boxes, descend into the nearer hit child
-// (deferring the other on the stack), and postpone the first leaf reached so the walk can continue.
+// (deferring the other on the stack), and postpone the first leaf reached so the walk can continue. All pops of the step
+// go through ONE loop (the profile showed two divergent pop sites running at 7 active lanes).
 template <bool COUNT>
-PTB_DEV void trav_node_step(const DevScene& sc, const Ray& ray, TravState& s, uint32_t* stack, float* stack_t,
-                            uint32_t& n_nodes) {
+PTB_DEV void trav_node_step(const DevScene& sc, const Ray& ray, TravState& s, uint2* stack, uint32_t& n_nodes) {
   float4 n0, n1, n2;
   uint4 n3;
   load_node(sc.nodes, s.cur, n0, n1, n2, n3);
@@ -76,31 +84,27 @@ PTB_DEV void trav_node_step(const DevScene& sc, const Ray& ray, TravState& s, ui
   float tl, tr;
   const bool hl = box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ray, s.best_t, tl);
   const bool hr = box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ray, s.best_t, tr);
-  if (hl && hr) {
-    uint32_t nearc = n3.x, farc = n3.y;
-    float tfar = tr;
-    if (tr < tl) { nearc = n3.y; farc = n3.x; tfar = tl; }
-    stack[s.sp] = farc;
-    stack_t[s.sp] = tfar;
-    ++s.sp;
-    s.cur = nearc;
-  } else if (hl) {
-    s.cur = n3.x;
-  } else if (hr) {
-    s.cur = n3.y;
-  } else {
-    s.cur = trav_pop(s, stack, stack_t);
+  bool want_pop = !(hl || hr);
+  if (!want_pop) {
+    const bool both = hl && hr;
+    const bool right_first = both ? (tr < tl) : hr;
+    if (both) {
+      stack[s.sp] = make_uint2(right_first ? n3.x : n3.y, __float_as_uint(right_first ? tl : tr));
+      ++s.sp;
+    }
+    s.cur = right_first ? n3.y : n3.x;
+    if ((s.cur & PTB_LEAF_BIT) && s.leaf == kNone) {  // first leaf: postpone, keep walking
+      s.leaf = s.cur;
+      want_pop = true;
+    }
   }
-  if ((s.cur & PTB_LEAF_BIT) && s.cur != kNone && s.leaf == kNone) {  // first leaf: postpone, keep walking
-    s.leaf = s.cur;
-    s.cur = trav_pop(s, stack, stack_t);
-  }
+  if (want_pop) trav_pop(s, stack);
 }
 
 // One primitive step of the lane: test the postponed leaf; if the walk itself is parked on a leaf, that one is next.
 template <bool ANYHIT, bool COUNT>
-PTB_DEV void trav_prim_step(const DevScene& sc, const Ray& ray, TravState& s, uint32_t* stack, float* stack_t,
-                            uint32_t exclude, uint32_t& n_prims) {
+PTB_DEV void trav_prim_step(const DevScene& sc, const Ray& ray, TravState& s, uint2* stack, uint32_t exclude,
+                            uint32_t& n_prims) {
   const uint32_t ref = s.leaf;
   s.leaf = kNone;
   if (ANYHIT) {
@@ -128,9 +132,9 @@ PTB_DEV void trav_prim_step(const DevScene& sc, const Ray& ray, TravState& s, ui
       }
     }
   }
-  if ((s.cur & PTB_LEAF_BIT) && s.cur != kNone) {
+  if ((s.cur & PTB_LEAF_BIT) && s.cur != kNone) {  // the walk itself is parked on a leaf: it is next
     s.leaf = s.cur;
-    s.cur = trav_pop(s, stack, stack_t);
+    trav_pop(s, stack);
   }
 }
 
@@ -157,8 +161,7 @@ template <bool ANYHIT, bool COUNT, class Fetch, class Retire>
 PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fetch& fetch, Retire& retire,
                               uint32_t& cnt_nodes, uint32_t& cnt_prims, uint32_t& cnt_rays) {
   const uint32_t lane = threadIdx.x & 31u;
-  uint32_t stack[kStackDepth];
-  float stack_t[kStackDepth];
+  uint2 stack[kStackDepth];
   TravState st;
   st.cur = st.leaf = kNone;
   st.sp = 0;
@@ -206,11 +209,11 @@ PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fe
       // ---- node phase: a short burst of node steps amortises the warp-level bookkeeping above
 #pragma unroll 1
       for (int burst = 0; burst < sc.trace_burst && node_ready; ++burst) {
-        trav_node_step<COUNT>(sc, ray, st, stack, stack_t, cnt_nodes);
+        trav_node_step<COUNT>(sc, ray, st, stack, cnt_nodes);
         node_ready = !(st.cur & PTB_LEAF_BIT);
       }
     } else if (leaf_ready) {
-      trav_prim_step<ANYHIT, COUNT>(sc, ray, st, stack, stack_t, exclude, cnt_prims);
+      trav_prim_step<ANYHIT, COUNT>(sc, ray, st, stack, exclude, cnt_prims);
     }
   }
 }

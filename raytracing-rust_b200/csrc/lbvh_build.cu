@@ -94,8 +94,8 @@ __global__ void k_morton(const float4* __restrict__ bmin, const float4* __restri
   const v3 cmax = mk(float_unflip(bounds[3]), float_unflip(bounds[4]), float_unflip(bounds[5]));
   const v3 ext = cmax - cmin;
   const v3 c = 0.5f * (from4(bmin[i]) + from4(bmax[i]));
-  const uint32_t qx = quantise10(c.x, cmin.x, ext.x), qy = quantise10(c.y, cmin.y, ext.y),
-                 qz = quantise10(c.z, cmin.z, ext.z);
+  const float e = fmaxf(ext.x, fmaxf(ext.y, ext.z));  // cubic grid (see oracle/lbvh_ref.hpp)
+  const uint32_t qx = quantise10(c.x, cmin.x, e), qy = quantise10(c.y, cmin.y, e), qz = quantise10(c.z, cmin.z, e);
   keys[i] = (expand_bits10(qx) << 2) | (expand_bits10(qy) << 1) | expand_bits10(qz);
   vals[i] = i;
 }

@@ -197,7 +197,7 @@ struct DevScene {
   // camera (implementations/src/camera.rs:57-63)
   v3 cam_origin, cam_lower_left, cam_horizontal, cam_vertical;
   // traversal scheduling knobs (ptb_traverse.cuh); defaults set in ptb_create, PTB_TRACE_BURST / PTB_TRACE_FETCH override
-  int trace_burst, trace_fetch_threshold;
+  int trace_burst, trace_fetch_threshold, trace_prim_bias;
 };
 
 }  // namespace ptb

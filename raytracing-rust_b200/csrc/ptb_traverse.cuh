@@ -8,22 +8,28 @@
 //   any hit     : replaces the blocker scan of check_hit_index (acceleration/mod.rs:226-263) and the sky visibility
 //                 test of sample_lights (integrators/mis.rs:104-115): any primitive != exclude with 0 < t < tmax.
 //
-// Execution shape (the first ncu capture showed the naive one-ray-per-lane loop issue-bound at 11-15 active lanes of
-// 32): every warp is persistent and keeps its 32 lanes busy —
-//   * "while-while": a lane walks internal nodes until EVERY lane of the warp holds a postponed leaf, then all lanes
-//     run the primitive test together (Aila & Laine 2009, speculative traversal);
-//   * dynamic fetch: when fewer than kFetchThreshold lanes still have work, the warp leaves the traversal loop and
-//     refills its idle lanes from the global ray queue (one warp-aggregated atomicAdd) instead of dragging a few long
-//     rays along with 90 % of the lanes idle.
+// Execution shape. The first ncu capture showed the naive one-ray-per-lane loop issue-bound at 11-15 active lanes of 32,
+// so every warp is persistent and all scheduling is warp-synchronous (full-mask ballots; Volta+ gives no lock-step
+// guarantee to rely on):
+//   * leaf queue: a lane does not test a primitive when it reaches a leaf; it queues the leaf (with the cull key of its
+//     box) and keeps walking internal nodes, until its small queue is full (speculative "while-while", Aila & Laine 2009);
+//   * phases: each iteration of the warp runs EITHER a burst of node steps for the lanes parked on an internal node OR one
+//     primitive step for the lanes with queued leaves — whichever has more ready lanes; queued leaves whose box entry has
+//     meanwhile fallen behind the best hit are dropped without a test;
+//   * dynamic fetch: when fewer than `trace_fetch_threshold` lanes still have work, finished rays are retired and idle
+//     lanes refilled from the global ray queue with one warp-aggregated atomicAdd.
 // Node fetches are four 16-byte loads of one 64-byte node that carries BOTH children's boxes.
 #pragma once
 #include "ptb_intersect.cuh"
 
 namespace ptb {
 
-constexpr int kStackDepth = 64;        // LBVH depth <= 30 Morton bits + 32 index tie-break bits; one push per level
-constexpr int kFetchThreshold = 20;    // lanes; below this the warp refills from the queue
-constexpr int kNodeBurst = 4;          // node steps per warp-level scheduling decision
+constexpr int kStackDepth = 64;  // LBVH depth <= 30 Morton bits + 32 index tie-break bits; one push per level
+#ifndef PTB_LEAF_QUEUE
+#define PTB_LEAF_QUEUE 1         // postponed leaves per lane (power of two). Measured on C3: 1 -> 1911-1927 Mrays/s,
+                                 // 2 -> 1872, 4 -> 1856, 8 -> 1825: deeper queues speculate more (V 32.9 -> 35.8 nodes/ray)
+#endif
+constexpr uint32_t kLeafQueue = PTB_LEAF_QUEUE;
 
 struct TraceResult {
   float t;       // 0 on miss (sky.rs:79-91)
@@ -38,34 +44,47 @@ PTB_DEV void load_node(const BvhNode* __restrict__ nodes, uint32_t idx, float4& 
   n3 = __ldg(reinterpret_cast<const uint4*>(p + 3));
 }
 
-// Per-lane traversal state. `cur`: internal node index, or a leaf reference (bit 31), or kNone when the stack ran dry.
-// `leaf`: postponed leaf reference or kNone.
+// Per-lane traversal state. `cur`: internal node index, or a PARKED leaf reference (bit 31: the leaf queue was full), or
+// kNone when the stack ran dry. The leaf queue is a ring of (reference, cull key) in local memory.
 struct TravState {
-  uint32_t cur, leaf;
+  uint32_t cur;
+  float cur_key;      // cull key of a parked leaf
   int sp;
+  uint32_t lq_head, lq_count;
   float best_t;       // closest hit so far (closest-hit) / tmax (any-hit)
   uint32_t best_ref;  // closest-hit: winning leaf ref; any-hit: kNone = unoccluded, 0 = occluded
-  PTB_DEV bool done() const { return cur == kNone && leaf == kNone; }
+  PTB_DEV bool done() const { return cur == kNone && lq_count == 0u; }
 };
 
 PTB_DEV void trav_init(TravState& s, uint32_t n_prims, float tmax) {
   s.cur = n_prims ? 0u : kNone;
-  s.leaf = kNone;
+  s.cur_key = 0.0f;
   s.sp = 0;
+  s.lq_head = 0u;
+  s.lq_count = 0u;
   s.best_t = tmax;
   s.best_ref = kNone;
 }
 
+PTB_DEV void lq_push(TravState& s, uint2* lq, uint32_t ref, float key) {
+  lq[(s.lq_head + s.lq_count) & (kLeafQueue - 1u)] = make_uint2(ref, __float_as_uint(key));
+  ++s.lq_count;
+}
+
 // Stack entry = (node or leaf reference, cull key of its box) in one 8-byte local-memory word.
-// Pops the next entry whose box can still hold a closer hit; a popped leaf is postponed when the slot is free and the
-// pop continues, so on return `cur` is an internal node, a second leaf, or kNone (stack exhausted).
-PTB_DEV void trav_pop(TravState& s, const uint2* stack) {
+// Pops until an internal node is found (-> cur), the stack is empty (-> kNone), or a leaf turns up while the leaf queue is
+// full (-> parked in cur). Entries whose box can no longer hold a closer hit are dropped; leaves go to the queue.
+PTB_DEV void trav_pop(TravState& s, const uint2* stack, uint2* lq) {
   for (;;) {
     if (s.sp == 0) { s.cur = kNone; return; }
     --s.sp;
     const uint2 e = stack[s.sp];
-    if (__uint_as_float(e.y) <= s.best_t) {
-      if ((e.x & PTB_LEAF_BIT) && s.leaf == kNone) { s.leaf = e.x; continue; }
+    const float key = __uint_as_float(e.y);
+    if (key <= s.best_t) {
+      if (e.x & PTB_LEAF_BIT) {
+        if (s.lq_count < kLeafQueue) { lq_push(s, lq, e.x, key); continue; }
+        s.cur_key = key;
+      }
       s.cur = e.x;
       return;
     }
@@ -73,10 +92,9 @@ PTB_DEV void trav_pop(TravState& s, const uint2* stack) {
 }
 
 // One internal-node step of the lane: fetch the 64-byte node, test both child boxes, descend into the nearer hit child
-// (deferring the other on the stack), and postpone the first leaf reached so the walk can continue. All pops of the step
-// go through ONE loop (the profile showed two divergent pop sites running at 7 active lanes).
+// (deferring the other on the stack); a leaf child is queued and the walk continues from the stack.
 template <bool COUNT>
-PTB_DEV void trav_node_step(const DevScene& sc, const Ray& ray, TravState& s, uint2* stack, uint32_t& n_nodes) {
+PTB_DEV void trav_node_step(const DevScene& sc, const Ray& ray, TravState& s, uint2* stack, uint2* lq, uint32_t& n_nodes) {
   float4 n0, n1, n2;
   uint4 n3;
   load_node(sc.nodes, s.cur, n0, n1, n2, n3);
@@ -93,48 +111,59 @@ PTB_DEV void trav_node_step(const DevScene& sc, const Ray& ray, TravState& s, ui
       ++s.sp;
     }
     s.cur = right_first ? n3.y : n3.x;
-    if ((s.cur & PTB_LEAF_BIT) && s.leaf == kNone) {  // first leaf: postpone, keep walking
-      s.leaf = s.cur;
-      want_pop = true;
+    if (s.cur & PTB_LEAF_BIT) {
+      const float key = right_first ? tr : tl;
+      if (s.lq_count < kLeafQueue) {
+        lq_push(s, lq, s.cur, key);
+        want_pop = true;
+      } else {
+        s.cur_key = key;  // queue full: park on the leaf until the next primitive phase
+      }
     }
   }
-  if (want_pop) trav_pop(s, stack);
+  if (want_pop) trav_pop(s, stack, lq);
 }
 
-// One primitive step of the lane: test the postponed leaf; if the walk itself is parked on a leaf, that one is next.
+// One primitive step of the lane: take the oldest queued leaf (the nearest, as the walk is near-first), drop it if its box
+// has fallen behind the best hit, else test it; then move a parked leaf into the freed queue slot and resume the walk.
 template <bool ANYHIT, bool COUNT>
-PTB_DEV void trav_prim_step(const DevScene& sc, const Ray& ray, TravState& s, uint2* stack, uint32_t exclude,
+PTB_DEV void trav_prim_step(const DevScene& sc, const Ray& ray, TravState& s, uint2* stack, uint2* lq, uint32_t exclude,
                             uint32_t& n_prims) {
-  const uint32_t ref = s.leaf;
-  s.leaf = kNone;
-  if (ANYHIT) {
-    if ((ref & kSlotMask) != exclude) {
+  const uint2 e = lq[s.lq_head];
+  s.lq_head = (s.lq_head + 1u) & (kLeafQueue - 1u);
+  --s.lq_count;
+  const uint32_t ref = e.x;
+  if (__uint_as_float(e.y) <= s.best_t) {
+    if (ANYHIT) {
+      if ((ref & kSlotMask) != exclude) {
+        const float t = prim_t(sc, ray, ref);
+        if (COUNT) ++n_prims;
+        if (t > 0.0f && t < s.best_t) {  // blocker found: stop
+          s.best_ref = 0u;
+          s.cur = kNone;
+          s.sp = 0;
+          s.lq_count = 0u;
+          return;
+        }
+      }
+    } else {
       const float t = prim_t(sc, ray, ref);
       if (COUNT) ++n_prims;
-      if (t > 0.0f && t < s.best_t) {  // blocker found: stop
-        s.best_ref = 0u;
-        s.cur = kNone;
-        s.sp = 0;
-        return;
-      }
-    }
-  } else {
-    const float t = prim_t(sc, ray, ref);
-    if (COUNT) ++n_prims;
-    if (t > 0.0f) {
-      if (t < s.best_t) {
-        s.best_t = t;
-        s.best_ref = ref;
-      } else if (t == s.best_t) {
-        const uint32_t a = __ldg(sc.slot_prim + (ref & kSlotMask));
-        const uint32_t b = __ldg(sc.slot_prim + (s.best_ref & kSlotMask));
-        if (a < b) s.best_ref = ref;
+      if (t > 0.0f) {
+        if (t < s.best_t) {
+          s.best_t = t;
+          s.best_ref = ref;
+        } else if (t == s.best_t) {
+          const uint32_t a = __ldg(sc.slot_prim + (ref & kSlotMask));
+          const uint32_t b = __ldg(sc.slot_prim + (s.best_ref & kSlotMask));
+          if (a < b) s.best_ref = ref;
+        }
       }
     }
   }
-  if ((s.cur & PTB_LEAF_BIT) && s.cur != kNone) {  // the walk itself is parked on a leaf: it is next
-    s.leaf = s.cur;
-    trav_pop(s, stack);
+  if ((s.cur & PTB_LEAF_BIT) && s.cur != kNone) {  // a leaf was parked: it fits now
+    lq_push(s, lq, s.cur, s.cur_key);
+    trav_pop(s, stack, lq);
   }
 }
 
@@ -149,33 +178,25 @@ PTB_DEV TraceResult trav_result(const TravState& s) {
   return r;
 }
 
-// Persistent-warp driver, warp-synchronous: all 32 lanes run this loop in lock step (full-mask ballots only), so the
-// SIMT efficiency is decided here and not by the compiler's reconvergence choices.
-//   service : when fewer than kFetchThreshold lanes still have work, finished lanes are retired and idle lanes are
-//             refilled from the global queue with one warp-aggregated atomicAdd;
-//   phase   : each iteration runs EITHER a node step for the lanes parked on an internal node OR a primitive step for
-//             the lanes holding a postponed leaf — whichever has more ready lanes.
-// `fetch(i, ray, tmax, exclude)` loads work item i into the lane; `retire(fin, state)` is called by ALL 32 lanes together
-// (fin = this lane just completed its item) so it may use warp-wide primitives.
+// Persistent-warp driver. `fetch(i, ray, tmax, exclude)` loads work item i into the lane; `retire(fin, state, ray)` is
+// called by ALL 32 lanes together (fin = this lane just completed its item) so it may use warp-wide primitives.
 template <bool ANYHIT, bool COUNT, class Fetch, class Retire>
 PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fetch& fetch, Retire& retire,
                               uint32_t& cnt_nodes, uint32_t& cnt_prims, uint32_t& cnt_rays) {
   const uint32_t lane = threadIdx.x & 31u;
   uint2 stack[kStackDepth];
+  uint2 lq[kLeafQueue];
   TravState st;
-  st.cur = st.leaf = kNone;
-  st.sp = 0;
-  st.best_t = 0.0f;
-  st.best_ref = kNone;
+  trav_init(st, 0u, 0.0f);
   Ray ray;
   ray.o = ray.d = ray.dinv = ray.shear = mk(0.0f, 0.0f, 0.0f);
   ray.swap_xz = false;
   uint32_t exclude = kNone;
   bool has_ray = false, exhausted = false;
   for (;;) {
-    // a lane with work is parked on an internal node, holds a postponed leaf, or both
+    // a lane with work is parked on an internal node, holds queued leaves, or both
     bool node_ready = has_ray && !(st.cur & PTB_LEAF_BIT);
-    const bool leaf_ready = has_ray && st.leaf != kNone;
+    const bool leaf_ready = has_ray && st.lq_count != 0u;
     const uint32_t m_node = __ballot_sync(0xffffffffu, node_ready);
     const uint32_t m_leaf = __ballot_sync(0xffffffffu, leaf_ready);
     if ((uint32_t)__popc(m_node | m_leaf) < (exhausted ? 1u : (uint32_t)sc.trace_fetch_threshold)) {
@@ -205,15 +226,18 @@ PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fe
       }
       continue;
     }
-    if (__popc(m_node) >= __popc(m_leaf)) {
-      // ---- node phase: a short burst of node steps amortises the warp-level bookkeeping above
+    // node phase while it keeps at least as many lanes busy as a primitive phase would (blocked lanes = queued leaves
+    // but nowhere to walk; `trace_prim_bias` shifts the balance towards batching more leaves per primitive phase)
+    const int n_node = __popc(m_node), n_blocked = __popc(m_leaf & ~m_node), n_leaf = __popc(m_leaf);
+    const bool do_node = sc.trace_prim_bias ? (n_node >= n_blocked * sc.trace_prim_bias) : (n_node >= n_leaf);
+    if (do_node) {
 #pragma unroll 1
       for (int burst = 0; burst < sc.trace_burst && node_ready; ++burst) {
-        trav_node_step<COUNT>(sc, ray, st, stack, cnt_nodes);
+        trav_node_step<COUNT>(sc, ray, st, stack, lq, cnt_nodes);
         node_ready = !(st.cur & PTB_LEAF_BIT);
       }
     } else if (leaf_ready) {
-      trav_prim_step<ANYHIT, COUNT>(sc, ray, st, stack, exclude, cnt_prims);
+      trav_prim_step<ANYHIT, COUNT>(sc, ray, st, stack, lq, exclude, cnt_prims);
     }
   }
 }

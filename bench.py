@@ -25,6 +25,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of k_trace per ray, from the committed ncu capture (profiles/)
+NCU_DRAM_BYTES_PER_RAY = {"c3": (1.244e9 + 0.6104e9) / 16.78e6}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -360,7 +363,15 @@ def run_ours(args):
             "gpu_launches": int(st.kernel_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "peak_source": peak_src,
+                         # DRAM bytes per k_trace launch: per-ray figure from the committed `ncu --set full` capture
+                         # (profiles/r1_final_c3.md: 1.244 GB read + 0.610 GB written for a 16.78 M-ray launch on this
+                         # workload) x this run's mean rays per launch. The 1 M-triangle scene is L2 resident, so real
+                         # traffic is ~20x below the algorithmic bytes: the kernel is ALU-issue bound, not HBM bound.
+                         "traffic": (NCU_DRAM_BYTES_PER_RAY.get(args.workload) * traced / max(int(st.trace_launches), 1)
+                                     if NCU_DRAM_BYTES_PER_RAY.get(args.workload) else None),
+                         "traffic_source": "ncu capture profiles/r1_final_c3.md (bytes/ray) x rays per launch of this run",
+                         "algorithmic_bytes_per_launch": b_ray * traced / max(int(st.trace_launches), 1),
                          "bytes_per_ray": b_ray, "nodes_per_ray": V, "prims_per_ray": T,
                          "k_trace_ms": st.ms_trace, "k_shade_ms": st.ms_shade, "k_generate_ms": st.ms_generate,
                          "k_shadow_ms": st.ms_shadow, "k_trace_share_of_step": st.ms_trace / dev_ms if dev_ms else None,

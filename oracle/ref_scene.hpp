@@ -166,6 +166,72 @@ static inline Float pdf(const Vec3& outgoing, const Vec3& normal) { return fmax_
 // materials/refract.rs:59-61
 static inline Vec3 fresnel(Float cos, const Vec3& f0) { return f0 + (1.0f - f0) * std::pow(1.0f - cos, 5.0f); }
 
+// statistics/bxdfs/trowbridge_reitz.rs:17-24,62-89 and trowbridge_reitz_vndf.rs (isotropic = anisotropic with a_x = a_y)
+// Parity status: pinned by the reference's GGX tests (trowbridge_reitz.rs:128-230: projected area = 1, G1 integral =
+// cos, weak white furnace = 1, G2 integral <= 1) and its chi-squared tests of the VNDF sampler against the pdf
+// (trowbridge_reitz_vndf.rs:156-184), restated in tests/test_oracle_kats.py.
+namespace tr {
+static inline Float d(Float alpha, Float cos_theta) {  // trowbridge_reitz.rs:17-24
+  if (cos_theta <= 0.0f) return 0.0f;
+  Float a_sq = alpha * alpha;
+  Float tmp = cos_theta * cos_theta * (a_sq - 1.0f) + 1.0f;
+  return a_sq / (PI_F * tmp * tmp);
+}
+static inline Float g2(Float alpha, const Vec3& normal, const Vec3& h, const Vec3& incoming, const Vec3& outgoing) {  // :62-78
+  if (incoming.dot(h) / incoming.dot(normal) <= 0.0f || outgoing.dot(h) / outgoing.dot(normal) <= 0.0f) return 0.0f;
+  Float alpha_sq = alpha * alpha;
+  Float one_minus_alpha_sq = 1.0f - alpha_sq;
+  Float cos_i = normal.dot(incoming);
+  Float cos_i_sq = cos_i * cos_i;
+  Float tmp_a = alpha_sq + one_minus_alpha_sq * cos_i_sq;
+  Float cos_o = normal.dot(outgoing);
+  Float cos_o_sq = cos_o * cos_o;
+  Float tmp_b = alpha_sq + one_minus_alpha_sq * cos_o_sq;
+  return 2.0f * cos_i * cos_o / (cos_o * std::sqrt(tmp_a) + cos_i * std::sqrt(tmp_b));
+}
+static inline Float g1(Float alpha, const Vec3& normal, const Vec3& h, const Vec3& v) {  // :80-89
+  if (v.dot(h) / v.dot(normal) <= 0.0f) return 0.0f;
+  Float cos = normal.dot(v);
+  Float cos_sq = cos * cos;
+  Float alpha_sq = alpha * alpha;
+  Float tmp = alpha_sq + (1.0f - alpha_sq) * cos_sq;
+  return 2.0f * cos / (std::sqrt(tmp) + cos);
+}
+static inline Float vndf(Float a, const Vec3& h, const Vec3& incoming) {  // vndf.rs:9-15
+  if (h.z < 0.0f) return 0.0f;
+  return g1(a, Vec3(0.0f, 0.0f, 1.0f), h, incoming) * fmax_(incoming.dot(h), 0.0f) * d(a, h.z) / incoming.z;
+}
+static inline Vec3 sample_vndf(Float a_x, Float a_y, const Vec3& incoming) {  // vndf.rs:84-113
+  Vec3 v_hemisphere = normalised(Vec3(a_x * incoming.x, a_y * incoming.y, incoming.z));
+  Float len_sq = v_hemisphere.x * v_hemisphere.x + v_hemisphere.y * v_hemisphere.y;
+  Vec3 basis_two = len_sq > 0.0f ? Vec3(-v_hemisphere.y, v_hemisphere.x, 0.0f) / std::sqrt(len_sq) : Vec3(1.0f, 0.0f, 0.0f);
+  Vec3 basis_three = v_hemisphere.cross(basis_two);
+  Float r = std::sqrt(g_rng.next_float01());
+  Float phi = TAU_F * g_rng.next_float01();
+  Float tx = r * std::cos(phi), ty = r * std::sin(phi);
+  Float s = 0.5f * (1.0f + v_hemisphere.z);
+  ty = (1.0f - s) * std::sqrt(1.0f - tx * tx) + s * ty;
+  Vec3 h_hemisphere = tx * basis_two + ty * basis_three + std::sqrt(fmax_(1.0f - tx * tx - ty * ty, 0.0f)) * v_hemisphere;
+  return normalised(Vec3(a_x * h_hemisphere.x, a_y * h_hemisphere.y, fmax_(h_hemisphere.z, 0.0f)));
+}
+static inline Vec3 sample_local(Float a, const Vec3& incoming) { return reflected(incoming, sample_vndf(a, a, incoming)); }
+static inline Float pdf_local(Float alpha, const Vec3& incoming, const Vec3& outgoing) {  // vndf.rs:26-33
+  Vec3 h = normalised(outgoing + incoming);
+  if (h.z < 0.0f) h = -h;
+  return vndf(alpha, h, incoming) / (4.0f * incoming.dot(h));
+}
+static inline Vec3 sample(Float a, const Vec3& incoming, const Vec3& normal) {  // vndf.rs:35-40
+  Coordinate coord = Coordinate::new_from_z(normal);
+  Coordinate inverse = coord.create_inverse();
+  Vec3 h = coord.to_coord(sample_vndf(a, a, inverse.to_coord(incoming)));
+  return reflected(incoming, h);
+}
+static inline Float pdf(Float alpha, const Vec3& incoming, const Vec3& outgoing, const Vec3& normal) {  // vndf.rs:42-52
+  Coordinate inverse = Coordinate::new_from_z(normal).create_inverse();
+  return pdf_local(alpha, inverse.to_coord(incoming), inverse.to_coord(outgoing));
+}
+}  // namespace tr
+
 struct Material {
   uint32_t kind;
   const Texture* texture;

@@ -292,7 +292,7 @@ struct TraceRetire {
 #define PTB_TRACE_MIN_BLOCKS 5  // 48 registers: +4 % over the unconstrained 56-register build (sweep in profiles/)
 #endif
 #ifndef PTB_SHADE_MIN_BLOCKS
-#define PTB_SHADE_MIN_BLOCKS 1
+#define PTB_SHADE_MIN_BLOCKS 2  // caps k_shade<MIS> at 128 registers (2 x 256 threads per SM): +6 % on rtweekend1 4K
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(256, PTB_TRACE_MIN_BLOCKS)
@@ -838,7 +838,12 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   const uint32_t grid_p = (P + T - 1) / T;
   auto capped = [&](const void* k) { const int g = persistent_grid(c, k, T); return (uint32_t)g < grid_p ? (uint32_t)g : grid_p; };
   const uint32_t grid_gen = capped((const void*)k_generate);
-  const uint32_t grid_shade = capped(mis ? (const void*)k_shade<PTB_METHOD_MIS> : (const void*)k_shade<PTB_METHOD_NAIVE>);
+  // k_shade is register-heavy (MIS: ~130): smaller blocks let more of them share an SM's register file
+  int TS = mis ? 128 : 256;
+  if (const char* e = getenv("PTB_SHADE_THREADS")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) TS = v; }
+  const void* shade_fn = mis ? (const void*)k_shade<PTB_METHOD_MIS> : (const void*)k_shade<PTB_METHOD_NAIVE>;
+  uint32_t grid_shade = (uint32_t)persistent_grid(c, shade_fn, TS);
+  if (grid_shade > (P + TS - 1) / TS) grid_shade = (P + TS - 1) / TS;
   const bool count = c->opt_count_traversal;
   const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true> : (const void*)k_trace<false>, T);
   const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
@@ -879,8 +884,8 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
     else k_trace<false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
     PTB_PROF(1, 1);
     PTB_PROF(2, 0);
-    if (mis) k_shade<PTB_METHOD_MIS><<<grid_shade, T, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
-    else k_shade<PTB_METHOD_NAIVE><<<grid_shade, T, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+    if (mis) k_shade<PTB_METHOD_MIS><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+    else k_shade<PTB_METHOD_NAIVE><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
     PTB_PROF(2, 1);
     c->stats.kernel_launches += 5;
     c->stats.trace_launches += 1;

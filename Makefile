@@ -7,7 +7,7 @@ NVCC     ?= nvcc
 NVFLAGS  ?= -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
             -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unused-parameter -Xptxas -v
 CU_SRCS  := $(PKG)/csrc/context.cu $(PKG)/csrc/lbvh_build.cu $(PKG)/csrc/wavefront.cu
-CPP_SRCS := $(PKG)/host/ssml_loader.cpp $(PKG)/host/image_out.cpp
+CPP_SRCS := $(PKG)/host/ssml_loader.cpp $(PKG)/host/image_out.cpp $(PKG)/host/image_in.cpp
 HDRS     := include/ptb200.h $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h)
 OBJS     := $(CU_SRCS:.cu=.o) $(CPP_SRCS:.cpp=.o)
 

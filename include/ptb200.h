@@ -82,10 +82,12 @@ typedef struct ptb_material {
 enum {
   PTB_TEX_CHECKERED = 0, /* textures/mod.rs:26-30,61-73   a = colour_one, b = colour_two */
   PTB_TEX_SOLID = 1,     /* textures/mod.rs:182-200       a = colour                     */
-  PTB_TEX_IMAGE = 2,     /* textures/mod.rs:202-266       (not supported by the device path yet) */
+  PTB_TEX_IMAGE = 2,     /* textures/mod.rs:202-266       pixels via ptb_scene_set_texture_data  */
   PTB_TEX_LERP = 3,      /* textures/mod.rs:268-291       a = colour_one, b = colour_two */
-  PTB_TEX_PERLIN = 4     /* textures/mod.rs:75-180        (not supported by the device path yet) */
+  PTB_TEX_PERLIN = 4     /* textures/mod.rs:75-180        tables via ptb_scene_set_texture_data  */
 };
+#define PTB_PERLIN_TABLE_WORDS 1024u /* 256 f32 ran_vecs[i].x (every ran_vec is r*(1,1,1), textures/mod.rs:96-99)
+                                        then perm_x, perm_y, perm_z as 3 x 256 uint32 bit patterns */
 typedef struct ptb_texture {
   uint32_t kind;
   ptb_vec3 a;
@@ -202,6 +204,11 @@ int32_t ptb_scene_set_spheres(ptb_ctx* ctx, const ptb_sphere* spheres, size_t n)
 int32_t ptb_scene_set_triangles(ptb_ctx* ctx, const ptb_triangle* triangles, size_t n);
 int32_t ptb_scene_set_materials(ptb_ctx* ctx, const ptb_material* materials, size_t n);
 int32_t ptb_scene_set_textures(ptb_ctx* ctx, const ptb_texture* textures, size_t n);
+/* Bulk data of one texture (copied). PTB_TEX_IMAGE: ImageTexture.data (textures/mod.rs:202-245) = width*height RGB f32,
+ * row-major, n_floats = 3*width*height. PTB_TEX_PERLIN: Perlin's tables (textures/mod.rs:75-112), width = height = 0,
+ * n_floats = PTB_PERLIN_TABLE_WORDS. Call after ptb_scene_set_textures; commit fails with PTB_ERR_MISSING without it. */
+int32_t ptb_scene_set_texture_data(ptb_ctx* ctx, uint32_t texture, uint32_t width, uint32_t height, const float* data,
+                                   size_t n_floats);
 int32_t ptb_scene_set_camera(ptb_ctx* ctx, const ptb_camera* camera);
 int32_t ptb_scene_set_sky(ptb_ctx* ctx, const ptb_sky* sky);
 
@@ -250,11 +257,23 @@ size_t  ptb_host_scene_spheres(const ptb_host_scene* s, const ptb_sphere** out);
 size_t  ptb_host_scene_triangles(const ptb_host_scene* s, const ptb_triangle** out);
 size_t  ptb_host_scene_materials(const ptb_host_scene* s, const ptb_material** out);
 size_t  ptb_host_scene_textures(const ptb_host_scene* s, const ptb_texture** out);
+/* bulk data of texture `texture` (see ptb_scene_set_texture_data); returns n_floats, 0 if the texture has none */
+size_t  ptb_host_scene_texture_data(const ptb_host_scene* s, uint32_t texture, uint32_t* width, uint32_t* height,
+                                    const float** data);
 int32_t ptb_host_scene_camera(const ptb_host_scene* s, ptb_camera* out);
 int32_t ptb_host_scene_sky(const ptb_host_scene* s, ptb_sky* out);
 /* SimpleCamera::new (camera.rs:20-53); aspect is 16/9 in the loader (loader/misc.rs:15). */
 int32_t ptb_camera_make(ptb_vec3 origin, ptb_vec3 lookat, ptb_vec3 vup, float hfov_deg, float aspect,
                         float aperture, float focus_dist, ptb_camera* out);
+/* Perlin::new (textures/mod.rs:90-112, 141-159): 256 gen_range(-1..1) scalars + three Fisher-Yates permutations
+ * (`target = gen_range(0..i)` for i = 255..1). The reference seeds them from OS entropy (unpinned); here they are a pure
+ * function of `seed` (Philox4x32-10). out = PTB_PERLIN_TABLE_WORDS words. */
+int32_t ptb_perlin_tables(uint64_t seed, float* out);
+/* ImageTexture::new's decode (textures/mod.rs:208-245, `image` crate to_rgb32f): ppm/pgm (P2,P3,P5,P6), pfm, bmp
+ * (24/32 bit) and png (8/16 bit, non-interlaced). *rgb = width*height*3 f32, released with ptb_image_free. */
+int32_t ptb_image_load(const char* filename, uint32_t* width, uint32_t* height, float** rgb);
+void    ptb_image_free(float* rgb);
+const char* ptb_image_last_error(void);
 /* ptb_scene_set_* for every array of a loaded scene. */
 int32_t ptb_scene_upload(ptb_ctx* ctx, const ptb_host_scene* s);
 

@@ -41,7 +41,7 @@ def _load():
     lib = C.CDLL(LIB_PATH)
     P = C.c_void_p
     lib.orc_scene_create.restype = P
-    lib.orc_scene_create.argtypes = [P, C.c_size_t, P, C.c_size_t, P, C.c_size_t, P, C.c_size_t, P, P, C.c_int]
+    lib.orc_scene_create.argtypes = [P, C.c_size_t, P, C.c_size_t, P, C.c_size_t, P, C.c_size_t, P, P, C.c_int, P, P]
     lib.orc_scene_destroy.argtypes = [P]
     for n in ("orc_bvh_num_nodes", "orc_bvh_depth", "orc_num_lights", "orc_lbvh_num_nodes"):
         getattr(lib, n).restype = C.c_size_t
@@ -75,6 +75,10 @@ def _load():
     lib.orc_lambertian_sample.argtypes = [P, C.c_uint64, C.c_size_t, C.c_int, P]
     lib.orc_lambertian_pdf.argtypes = [P, P, C.c_size_t, C.c_int, P]
     lib.orc_random_unit_vectors.argtypes = [C.c_uint64, C.c_size_t, P]
+    lib.orc_tr_sample.argtypes = [C.c_float, P, P, C.c_uint64, C.c_size_t, C.c_int, P]
+    lib.orc_tr_pdf.argtypes = [C.c_float, P, P, P, C.c_size_t, C.c_int, P]
+    lib.orc_tr_integrand.argtypes = [C.c_float, P, P, P, C.c_size_t, C.c_int, P]
+    lib.orc_material_terms.argtypes = [P, C.c_uint32, P, P, P, P, P]
     lib.orc_dist1d.argtypes = [P, C.c_size_t, P, P, C.c_uint64, C.c_size_t, P]
     lib.orc_dist2d.argtypes = [P, C.c_size_t, C.c_size_t, P, C.c_uint64, C.c_size_t, P]
     lib.orc_sky_sample.argtypes = [P, C.c_uint64, C.c_size_t, P]
@@ -104,8 +108,15 @@ class OracleScene:
         self._keep = [np.ascontiguousarray(a) for a in (s.spheres, s.triangles, s.materials, s.textures, s.camera, s.sky)]
         sp, tr, ma, te, cam, sky = self._keep
         self.n_prims = len(sp) + len(tr)
+        tex_ptrs = (C.c_void_p * max(len(te), 1))()
+        tex_dims = np.zeros(3 * max(len(te), 1), np.uint32)
+        for i, (w, h, words) in getattr(s, "texture_data", {}).items():
+            words = np.ascontiguousarray(words, dtype=np.float32)
+            self._keep.append(words)
+            tex_ptrs[i] = words.ctypes.data
+            tex_dims[3 * i:3 * i + 3] = (w, h, words.size)
         self._h = lib.orc_scene_create(_p(sp), len(sp), _p(tr), len(tr), _p(ma), len(ma), _p(te), len(te), _p(cam), _p(sky),
-                                       split_type)
+                                       split_type, C.cast(tex_ptrs, C.c_void_p), _p(tex_dims))
         self.sky_res = (int(sky["sampler_res_x"][0]), int(sky["sampler_res_y"][0]))
         self._lbvh = False
 
@@ -195,6 +206,20 @@ class OracleScene:
         out = np.zeros(len(dirs), np.float32)
         lib.orc_sky_pdf(self._h, _p(dirs), len(dirs), _p(out))
         return out
+
+    def sky_table(self):
+        """(ycdf, xcdf, ypdf, xpdf) of the sky's Distribution2D (sky.rs:20-37, distributions.rs:82-99)."""
+        rx, ry = self.sky_res
+        ycdf, xcdf = np.zeros(ry + 1, np.float32), np.zeros(ry * (rx + 1), np.float32)
+        ypdf, xpdf = np.zeros(ry, np.float32), np.zeros(ry * rx, np.float32)
+        lib.orc_sky_table(self._h, _p(ycdf), _p(xcdf), _p(ypdf), _p(xpdf))
+        return ycdf, xcdf, ypdf, xpdf
+
+    def material_terms(self, mat, normal, point, wo, wi):
+        """(scattering_pdf, eval, eval_over_scattering_pdf) of material `mat` at a synthetic hit."""
+        out = np.zeros(7, np.float32)
+        lib.orc_material_terms(self._h, mat, _p(f3(normal)), _p(f3(point)), _p(f3(wo)), _p(f3(wi)), _p(out))
+        return float(out[0]), out[1:4].copy(), out[4:7].copy()
 
     def texture_colour(self, tex, direction, point=(0, 0, 0)):
         out = np.zeros(3, np.float32)
@@ -287,6 +312,29 @@ def lambertian_pdf(normal, dirs, local=False):
     dirs = np.ascontiguousarray(dirs, np.float32)
     out = np.zeros(len(dirs), np.float32)
     lib.orc_lambertian_pdf(_p(f3(normal)), _p(dirs), len(dirs), int(local), _p(out))
+    return out
+
+
+TR_H, TR_LOCAL, TR_WORLD = 0, 1, 2
+
+
+def tr_sample(alpha, incoming, n, seed=0, which=TR_WORLD, normal=(0, 0, 1)):
+    d = np.zeros((n, 3), np.float32)
+    lib.orc_tr_sample(alpha, _p(f3(incoming)), _p(f3(normal)), seed, n, which, _p(d))
+    return d
+
+
+def tr_pdf(alpha, incoming, dirs, which=TR_WORLD, normal=(0, 0, 1)):
+    dirs = np.ascontiguousarray(dirs, np.float32)
+    out = np.zeros(len(dirs), np.float32)
+    lib.orc_tr_pdf(alpha, _p(f3(incoming)), _p(f3(normal)), _p(dirs), len(dirs), which, _p(out))
+    return out
+
+
+def tr_integrand(alpha, a, dirs, which, normal=(0, 0, 1)):
+    dirs = np.ascontiguousarray(dirs, np.float32)
+    out = np.zeros(len(dirs), np.float32)
+    lib.orc_tr_integrand(alpha, _p(f3(a)), _p(f3(normal)), _p(dirs), len(dirs), which, _p(out))
     return out
 
 

@@ -18,6 +18,7 @@ using namespace ref;
 struct orc_scene {
   std::vector<Texture> textures;
   std::vector<Material> materials;
+  std::vector<std::vector<Float>> texture_words;  // owned copies of image pixels / perlin tables
   std::vector<Prim> prims_original;  // loader order: spheres first, then triangles
   Bvh bvh;
   Camera camera;
@@ -55,19 +56,30 @@ extern "C" {
 
 orc_scene* orc_scene_create(const ptb_sphere* spheres, size_t ns, const ptb_triangle* tris, size_t nt,
                             const ptb_material* mats, size_t nm, const ptb_texture* texs, size_t ntex,
-                            const ptb_camera* cam, const ptb_sky* sky, int split_type) {
+                            const ptb_camera* cam, const ptb_sky* sky, int split_type, const float* const* tex_data,
+                            const uint32_t* tex_dims /* width, height, n_words per texture */) {
   orc_scene* s = new orc_scene();
   s->textures.resize(ntex);
+  s->texture_words.resize(ntex);
   for (size_t i = 0; i < ntex; ++i) {
     s->textures[i].kind = texs[i].kind;
     s->textures[i].a = v3(texs[i].a);
     s->textures[i].b = v3(texs[i].b);
+    if (tex_data && tex_data[i]) {
+      s->texture_words[i].assign(tex_data[i], tex_data[i] + tex_dims[3 * i + 2]);
+      s->textures[i].data = s->texture_words[i].data();
+      s->textures[i].perm = reinterpret_cast<const uint32_t*>(s->texture_words[i].data()) + 256;
+      s->textures[i].width = tex_dims[3 * i];
+      s->textures[i].height = tex_dims[3 * i + 1];
+    }
   }
   s->materials.resize(nm);
   for (size_t i = 0; i < nm; ++i) {
     s->materials[i].kind = mats[i].kind;
     s->materials[i].texture = &s->textures[mats[i].texture];
     s->materials[i].param = mats[i].param;
+    s->materials[i].ior = v3(mats[i].ior);
+    s->materials[i].metallic = mats[i].metallic;
   }
   s->prims_original.reserve(ns + nt);
   for (size_t i = 0; i < ns; ++i) {
@@ -364,6 +376,56 @@ void orc_lambertian_pdf(const float normal[3], const float* dirs, size_t n, int 
     Vec3 d(dirs[3 * k], dirs[3 * k + 1], dirs[3 * k + 2]);
     pdf[k] = local ? lambertian::pdf_local(d) : lambertian::pdf(d, nn);
   }
+}
+// Trowbridge-Reitz (statistics/bxdfs/trowbridge_reitz.rs, trowbridge_reitz_vndf.rs isotropic). which: 0 = sample_vndf /
+// vndf (half vectors, local frame), 1 = sample_local / pdf_local, 2 = sample / pdf about `normal`.
+void orc_tr_sample(float alpha, const float incoming[3], const float normal[3], uint64_t seed, size_t n, int which, float* dirs) {
+  g_rng.seed(seed);
+  Vec3 in(incoming[0], incoming[1], incoming[2]), nn(normal[0], normal[1], normal[2]);
+  for (size_t k = 0; k < n; ++k) {
+    g_rng.path((uint32_t)k, (uint32_t)(k >> 32));
+    g_rng.select(0, RNG_TEST);
+    Vec3 d = which == 0 ? tr::sample_vndf(alpha, alpha, in) : which == 1 ? tr::sample_local(alpha, in) : tr::sample(alpha, in, nn);
+    dirs[3 * k] = d.x; dirs[3 * k + 1] = d.y; dirs[3 * k + 2] = d.z;
+  }
+}
+void orc_tr_pdf(float alpha, const float incoming[3], const float normal[3], const float* dirs, size_t n, int which, float* pdf) {
+  Vec3 in(incoming[0], incoming[1], incoming[2]), nn(normal[0], normal[1], normal[2]);
+  for (size_t k = 0; k < n; ++k) {
+    Vec3 d(dirs[3 * k], dirs[3 * k + 1], dirs[3 * k + 2]);
+    pdf[k] = which == 0 ? tr::vndf(alpha, d, in) : which == 1 ? tr::pdf_local(alpha, in, d) : tr::pdf(alpha, in, d, nn);
+  }
+}
+// integrands of the reference's GGX integration tests (trowbridge_reitz.rs:128-230), evaluated at `dirs`:
+//   0 g1_cos_test  1 projected_area  2 weak_furnace  3 g2_test     (a = the fixed direction, normal = the frame's z)
+void orc_tr_integrand(float alpha, const float a_[3], const float normal[3], const float* dirs, size_t n, int which, float* out) {
+  Vec3 a(a_[0], a_[1], a_[2]), nn(normal[0], normal[1], normal[2]);
+  for (size_t k = 0; k < n; ++k) {
+    Vec3 b(dirs[3 * k], dirs[3 * k + 1], dirs[3 * k + 2]);
+    Float v = 0.0f;
+    if (which == 0) v = tr::g1(alpha, nn, b, a) * fmax_(a.dot(b), 0.0f) * tr::d(alpha, b.dot(nn));
+    else if (which == 1) v = tr::d(alpha, b.dot(nn)) * b.dot(nn);
+    else {
+      Vec3 h = normalised(b + a);
+      if (h.dot(nn) < 0.0f) h = -h;
+      Float denom = 4.0f * std::fabs(a.dot(nn));
+      if (denom >= 0.000000001f)
+        v = (which == 2 ? tr::g1(alpha, nn, h, a) : tr::g2(alpha, nn, h, a, b)) * tr::d(alpha, h.dot(nn)) / denom;
+    }
+    out[k] = v;
+  }
+}
+// Scatter methods of one material at a synthetic hit (normal, point): out = scattering_pdf, eval(3), eval_over_pdf(3)
+void orc_material_terms(const orc_scene* s, uint32_t mat, const float normal[3], const float point[3], const float wo[3],
+                        const float wi[3], float out[7]) {
+  Hit h;
+  h.normal = Vec3(normal[0], normal[1], normal[2]);
+  h.point = Vec3(point[0], point[1], point[2]);
+  Vec3 o(wo[0], wo[1], wo[2]), i(wi[0], wi[1], wi[2]);
+  const Material& m = s->materials[mat];
+  out[0] = m.scattering_pdf(h, o, i);
+  Vec3 e = m.eval(h, o, i), r = m.eval_over_scattering_pdf(h, o, i);
+  out[1] = e.x; out[2] = e.y; out[3] = e.z; out[4] = r.x; out[5] = r.y; out[6] = r.z;
 }
 void orc_random_unit_vectors(uint64_t seed, size_t n, float* dirs) {
   g_rng.seed(seed);

@@ -167,4 +167,12 @@ static inline size_t sat_usize(Float f) {
   return (size_t)f;
 }
 
+// Rust `as i32` on a float saturates (NaN -> 0).
+static inline int32_t sat_i32(Float f) {
+  if (f != f) return 0;
+  if (f >= 2147483648.0f) return INT32_MAX;
+  if (f <= -2147483648.0f) return INT32_MIN;
+  return (int32_t)f;
+}
+
 }  // namespace ref

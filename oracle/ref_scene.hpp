@@ -34,6 +34,36 @@ static inline Vec3 random_unit_vector() {
 struct Texture {
   uint32_t kind;
   Vec3 a, b;
+  // ImageTexture: `data` = width*height RGB f32 rows (textures/mod.rs:202-245; dim = (width-1, height-1)).
+  // Perlin: `data` = 256 ran_vecs scalars (every ran_vec is r*Vec3::one(), textures/mod.rs:96-99), `perm` = perm_x|perm_y|perm_z.
+  const Float* data = nullptr;
+  const uint32_t* perm = nullptr;
+  uint32_t width = 0, height = 0;
+
+  // textures/mod.rs:114-139, 161-179
+  Float perlin_noise(const Vec3& point) const {
+    Float fx = std::floor(point.x), fy = std::floor(point.y), fz = std::floor(point.z);
+    Float u = point.x - fx, v = point.y - fy, w = point.z - fz;
+    int32_t i = sat_i32(fx), j = sat_i32(fy), k = sat_i32(fz);
+    Float c[8];
+    for (int index = 0; index < 8; ++index) {
+      int32_t di = index / 4, dj = (index / 2) % 2, dk = index % 2;
+      uint32_t h = perm[((uint32_t)i + (uint32_t)di) & 255u] ^ perm[256u + (((uint32_t)j + (uint32_t)dj) & 255u)] ^
+                   perm[512u + (((uint32_t)k + (uint32_t)dk) & 255u)];
+      c[index] = data[h];
+    }
+    Float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+    Float value = 0.0f;
+    for (int index = 0; index < 8; ++index) {
+      int ii = index / 4, jj = (index / 2) % 2, kk = index % 2;
+      Vec3 weight(u - (Float)ii, v - (Float)jj, w - (Float)kk);
+      Vec3 cv = c[ii * 4 + jj * 2 + kk] * Vec3::one();
+      value += ((Float)ii * uu + (1.0f - (Float)ii) * (1.0f - uu)) * ((Float)jj * vv + (1.0f - (Float)jj) * (1.0f - vv)) *
+               ((Float)kk * ww + (1.0f - (Float)kk) * (1.0f - ww)) * cv.dot(weight);
+    }
+    return value;
+  }
+
   Vec3 colour_value(const Vec3& direction, const Vec3& point) const {
     switch (kind) {
       case PTB_TEX_CHECKERED: {  // textures/mod.rs:61-73
@@ -46,6 +76,19 @@ struct Texture {
         Float t = direction.z * 0.5f + 0.5f;
         return a * t + b * (1.0f - t);
       }
+      case PTB_TEX_IMAGE: {  // textures/mod.rs:248-262 (lat-long lookup by DIRECTION, nearest texel)
+        Float phi = std::atan2(direction.y, direction.x) + PI_F;
+        Float theta = std::acos(direction.z);
+        Float uvx = phi / (2.0f * PI_F), uvy = theta / PI_F;
+        size_t dim0 = width - 1, dim1 = height - 1;
+        size_t x_pixel = sat_usize((Float)dim0 * uvx), y_pixel = sat_usize((Float)dim1 * uvy);
+        if (x_pixel > dim0) x_pixel = dim0;  // the reference would panic on an out-of-range index; unreachable for unit directions
+        if (y_pixel > dim1) y_pixel = dim1;
+        size_t index = y_pixel * (dim0 + 1) + x_pixel;
+        return Vec3(data[3 * index], data[3 * index + 1], data[3 * index + 2]);
+      }
+      case PTB_TEX_PERLIN:  // textures/mod.rs:171-179
+        return 0.5f * Vec3::one() * (1.0f + perlin_noise(point));
       default:  // trait default (textures/mod.rs:10-12)
         return Vec3(1.0f, 1.0f, 1.0f);
     }
@@ -236,6 +279,16 @@ struct Material {
   uint32_t kind;
   const Texture* texture;
   Float param;
+  Vec3 ior = Vec3(1.0f, 1.0f, 1.0f);  // TrowbridgeReitz only (trowbridge_reitz.rs:6-11); param = alpha
+  Float metallic = 0.0f;
+
+  // trowbridge_reitz.rs:26-31
+  Vec3 tr_fresnel(const Hit& hit, const Vec3& wo, const Vec3& wi, const Vec3& h) const {
+    Vec3 f0 = ((1.0f - ior) / (ior + 1.0f)).abs();
+    f0 = f0 * f0;
+    f0 = (1.0f - metallic) * f0 + metallic * texture->colour_value(wi, hit.point);  // lerp, trowbridge_reitz.rs:86-88
+    return fresnel(wo.dot(h), f0);
+  }
 
   // rt_core/src/material.rs:4-30 defaults + the overrides of materials/{emissive,lambertian,reflect,refract}.rs
   bool is_light() const { return kind == PTB_MAT_EMIT; }
@@ -254,6 +307,12 @@ struct Material {
         return true;
       case PTB_MAT_LAMBERTIAN: {  // lambertian.rs:30-41
         Vec3 direction = lambertian::sample(hit.normal);
+        Vec3 point = offset_ray(hit.point, hit.normal, hit.error, true);
+        ray = Ray(point, direction, ray.time);
+        return false;
+      }
+      case PTB_MAT_TROWBRIDGE_REITZ: {  // trowbridge_reitz.rs:38-50
+        Vec3 direction = tr::sample(param, -ray.direction, hit.normal);
         Vec3 point = offset_ray(hit.point, hit.normal, hit.error, true);
         ray = Ray(point, direction, ray.time);
         return false;
@@ -280,17 +339,38 @@ struct Material {
         return true;
     }
   }
-  Float scattering_pdf(const Hit& hit, const Vec3& /*wo*/, const Vec3& wi) const {
+  Float scattering_pdf(const Hit& hit, const Vec3& wo, const Vec3& wi) const {
     if (kind == PTB_MAT_LAMBERTIAN) return lambertian::pdf(wi, hit.normal);  // lambertian.rs:42-44
+    if (kind == PTB_MAT_TROWBRIDGE_REITZ) {  // trowbridge_reitz.rs:51-59
+      Float a = tr::pdf(param, -wo, wi, hit.normal);
+      return a == 0.0f ? INF_F : a;
+    }
     return 0.0f;  // trait default (material.rs:20-22): Reflect/Refract do not override (quirk Q4)
   }
   Vec3 eval(const Hit& hit, const Vec3& wo, const Vec3& wi) const {
     if (kind == PTB_MAT_LAMBERTIAN)  // lambertian.rs:45-47
       return texture->colour_value(wo, hit.point) * param * fmax_(hit.normal.dot(wi), 0.0f) / PI_F;
+    if (kind == PTB_MAT_TROWBRIDGE_REITZ) {  // trowbridge_reitz.rs:60-73
+      Vec3 wo_ = -wo;
+      Vec3 h = normalised(wi + wo_);
+      if (wi.dot(hit.normal) < 0.0f || h.dot(wo_) < 0.0f) return Vec3::zero();
+      Vec3 f = tr_fresnel(hit, wo_, wi, h);
+      Float g = tr::g2(param, hit.normal, h, wo_, wi);
+      Float d = tr::d(param, hit.normal.dot(h));
+      return f * g * d / (4.0f * std::fabs(wo_.dot(hit.normal)) * wi.dot(hit.normal));
+    }
     return texture->colour_value(wo, hit.point);  // reflect.rs:37-39, refract.rs:51-53
   }
   Vec3 eval_over_scattering_pdf(const Hit& hit, const Vec3& wo, const Vec3& wi) const {
     if (kind == PTB_MAT_LAMBERTIAN) return texture->colour_value(wo, hit.point) * param;  // lambertian.rs:48-50
+    if (kind == PTB_MAT_TROWBRIDGE_REITZ) {  // trowbridge_reitz.rs:74-87
+      Vec3 wo_ = -wo;
+      Vec3 h = normalised(wi + wo_);
+      if (wo_.dot(h) < 0.0f || wi.dot(hit.normal) < 0.0f) return Vec3::zero();
+      Vec3 f = tr_fresnel(hit, wo_, wi, h);
+      Float g = tr::g2(param, hit.normal, h, wo_, wi);
+      return f * g / tr::g1(param, hit.normal, h, wo_);
+    }
     return eval(hit, wo, wi) / scattering_pdf(hit, wo, wi);  // material.rs:24-26  (colour / 0.0)
   }
   Vec3 get_emission(const Hit& hit, const Vec3& wo) const {

@@ -25,6 +25,7 @@ PTB_RR_DEFAULT = 0xFFFFFFFF
 MAT_EMIT, MAT_LAMBERTIAN, MAT_TROWBRIDGE_REITZ, MAT_REFLECT, MAT_REFRACT = range(5)
 TEX_CHECKERED, TEX_SOLID, TEX_IMAGE, TEX_LERP, TEX_PERLIN = range(5)
 METHOD_NAIVE, METHOD_MIS = 0, 1
+PERLIN_TABLE_WORDS = 1024
 OPT_TIME_KERNELS, OPT_COUNT_TRAVERSAL = 1, 2
 
 # numpy mirrors of the POD structs (sizes asserted against the header's layout in tests/test_abi.py)
@@ -84,6 +85,7 @@ SYMBOLS = [
     ("ptb_scene_set_triangles", C.c_int32, [_P, _P, C.c_size_t]),
     ("ptb_scene_set_materials", C.c_int32, [_P, _P, C.c_size_t]),
     ("ptb_scene_set_textures", C.c_int32, [_P, _P, C.c_size_t]),
+    ("ptb_scene_set_texture_data", C.c_int32, [_P, C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_size_t]),
     ("ptb_scene_set_camera", C.c_int32, [_P, _P]),
     ("ptb_scene_set_sky", C.c_int32, [_P, _P]),
     ("ptb_scene_commit", C.c_int32, [_P, C.c_uint32]),
@@ -106,9 +108,14 @@ SYMBOLS = [
     ("ptb_host_scene_triangles", C.c_size_t, [_P, C.POINTER(_P)]),
     ("ptb_host_scene_materials", C.c_size_t, [_P, C.POINTER(_P)]),
     ("ptb_host_scene_textures", C.c_size_t, [_P, C.POINTER(_P)]),
+    ("ptb_host_scene_texture_data", C.c_size_t, [_P, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(_P)]),
     ("ptb_host_scene_camera", C.c_int32, [_P, _P]),
     ("ptb_host_scene_sky", C.c_int32, [_P, _P]),
     ("ptb_camera_make", C.c_int32, [Vec3, Vec3, Vec3, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
+    ("ptb_perlin_tables", C.c_int32, [C.c_uint64, _P]),
+    ("ptb_image_load", C.c_int32, [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(_P)]),
+    ("ptb_image_free", None, [_P]),
+    ("ptb_image_last_error", C.c_char_p, []),
     ("ptb_scene_upload", C.c_int32, [_P, _P]),
     ("ptb_image_save", C.c_int32, [C.c_char_p, C.c_uint32, C.c_uint32, _P, C.c_float]),
 ]

@@ -85,6 +85,8 @@ class Context:
         """ptb_scene_set_* for every array (host -> library copy)."""
         h = self._h
         _check(h, L.lib.ptb_scene_set_textures(h, L.ptr(s.textures), len(s.textures)))
+        for i, (w, hh, words) in s.texture_data.items():
+            _check(h, L.lib.ptb_scene_set_texture_data(h, i, w, hh, L.ptr(words), words.size))
         _check(h, L.lib.ptb_scene_set_materials(h, L.ptr(s.materials), len(s.materials)))
         _check(h, L.lib.ptb_scene_set_spheres(h, L.ptr(s.spheres), len(s.spheres)))
         _check(h, L.lib.ptb_scene_set_triangles(h, L.ptr(s.triangles), len(s.triangles)))

@@ -180,6 +180,31 @@ int32_t ptb_scene_set_textures(ptb_ctx* ctx, const ptb_texture* p, size_t n) {
   for (size_t i = 0; i < n; ++i)
     if (p[i].kind > PTB_TEX_PERLIN) return set_error(c, PTB_ERR_INVALID, "texture %zu: unknown kind %u", i, p[i].kind);
   c->textures.assign(p, p + n);
+  c->texture_data.clear();
+  c->committed = false;
+  return PTB_OK;
+}
+int32_t ptb_scene_set_texture_data(ptb_ctx* ctx, uint32_t texture, uint32_t width, uint32_t height, const float* data,
+                                   size_t n_floats) {
+  CTX_OR_FAIL(ctx);
+  if (texture >= c->textures.size()) return set_error(c, PTB_ERR_INVALID, "texture index %u out of range", texture);
+  if (!data) return set_error(c, PTB_ERR_INVALID, "null texture data");
+  const uint32_t kind = c->textures[texture].kind;
+  if (kind == PTB_TEX_IMAGE) {
+    if (width == 0 || height == 0 || n_floats != (size_t)width * height * 3)  // textures/mod.rs:229 asserts non-zero
+      return set_error(c, PTB_ERR_INVALID, "image texture %u: need 3*width*height floats and non-zero dimensions", texture);
+  } else if (kind == PTB_TEX_PERLIN) {
+    if (n_floats != PTB_PERLIN_TABLE_WORDS) return set_error(c, PTB_ERR_INVALID, "perlin texture %u: need %u words", texture, PTB_PERLIN_TABLE_WORDS);
+    const uint32_t* perm = reinterpret_cast<const uint32_t*>(data) + 256;
+    for (uint32_t i = 0; i < 768; ++i)
+      if (perm[i] > 255u) return set_error(c, PTB_ERR_INVALID, "perlin texture %u: permutation entry out of range", texture);
+  } else {
+    return set_error(c, PTB_ERR_INVALID, "texture %u takes no bulk data", texture);
+  }
+  Ctx::TexData& td = c->texture_data[texture];
+  td.width = width;
+  td.height = height;
+  td.data.assign(data, data + n_floats);
   c->committed = false;
   return PTB_OK;
 }
@@ -210,6 +235,12 @@ int32_t ptb_scene_upload(ptb_ctx* ctx, const ptb_host_scene* s) {
   ptb_host_scene_sky(s, &sky);
   int32_t rc;
   if ((rc = ptb_scene_set_textures(ctx, te, nx)) != PTB_OK) return rc;
+  for (size_t i = 0; i < nx; ++i) {
+    uint32_t w = 0, h = 0;
+    const float* data = nullptr;
+    const size_t n = ptb_host_scene_texture_data(s, (uint32_t)i, &w, &h, &data);
+    if (n && (rc = ptb_scene_set_texture_data(ctx, (uint32_t)i, w, h, data, n)) != PTB_OK) return rc;
+  }
   if ((rc = ptb_scene_set_materials(ctx, ma, nm)) != PTB_OK) return rc;
   if ((rc = ptb_scene_set_spheres(ctx, sp, ns)) != PTB_OK) return rc;
   if ((rc = ptb_scene_set_triangles(ctx, tr, nt)) != PTB_OK) return rc;

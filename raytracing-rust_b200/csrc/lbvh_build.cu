@@ -353,27 +353,14 @@ __global__ void k_light_slots(const uint32_t* __restrict__ light_prims, uint32_t
 // ------------------------------------------------------------------------------------------ host: sky table
 // Sky::new (implementations/src/sky.rs:20-37) = generate_values (textures/mod.rs:32-50) + Distribution2D::new
 // (statistics/distributions.rs:11-44, 82-99), in the reference's f32 operation order.
-static void host_texture_colour(const ptb_texture& t, const float d[3], const float p[3], float out[3]) {
-  switch (t.kind) {
-    case PTB_TEX_CHECKERED: {
-      float sign = sinf(10.0f * p[0]) * sinf(10.0f * p[1]) * sinf(10.0f * p[2]);
-      const ptb_vec3& c = sign > 0.0f ? t.a : t.b;
-      out[0] = c.x; out[1] = c.y; out[2] = c.z;
-      break;
-    }
-    case PTB_TEX_SOLID:
-      out[0] = t.a.x; out[1] = t.a.y; out[2] = t.a.z;
-      break;
-    case PTB_TEX_LERP: {
-      float tt = d[2] * 0.5f + 0.5f;
-      out[0] = t.a.x * tt + t.b.x * (1.0f - tt);
-      out[1] = t.a.y * tt + t.b.y * (1.0f - tt);
-      out[2] = t.a.z * tt + t.b.z * (1.0f - tt);
-      break;
-    }
-    default:
-      out[0] = out[1] = out[2] = 1.0f;
-  }
+static void host_texture_colour(const Ctx* c, uint32_t tex, const float d[3], const float p[3], float out[3]) {
+  const ptb_texture& t = c->textures[tex];
+  auto it = c->texture_data.find(tex);
+  TexWords words{it == c->texture_data.end() ? nullptr : it->second.data.data()};
+  const uint32_t w = it == c->texture_data.end() ? 0u : it->second.width, h = it == c->texture_data.end() ? 0u : it->second.height;
+  const v3 col = texture_eval(t.kind, mk(t.a.x, t.a.y, t.a.z), mk(t.b.x, t.b.y, t.b.z), w, h, words, mk(d[0], d[1], d[2]),
+                              mk(p[0], p[1], p[2]));
+  out[0] = col.x; out[1] = col.y; out[2] = col.z;
 }
 static void dist1d(const float* values, size_t n, std::vector<float>& pdf, std::vector<float>& cdf) {
   cdf.assign(1, 0.0f);
@@ -396,7 +383,6 @@ static int32_t build_sky(Ctx* c) {
   c->dev.sky_ycdf = c->dev.sky_ypdf = c->dev.sky_xcdf = c->dev.sky_xpdf = nullptr;
   if ((rx | ry) == 0) return PTB_OK;
   if (rx == 0 || ry == 0) return set_error(c, PTB_ERR_INVALID, "sky sampler_res must be (0,0) or both non-zero");
-  const ptb_texture& tex = c->textures[c->sky.texture];
   std::vector<float> values;
   values.reserve((size_t)rx * ry);
   const float step_x = 1.0f / (float)rx, step_y = 1.0f / (float)ry;
@@ -407,7 +393,7 @@ static int32_t build_sky(Ctx* c) {
       float sin_theta = sinf(theta);
       float dir[3] = {cosf(phi) * sin_theta, sinf(phi) * sin_theta, cosf(theta)};
       float zero[3] = {0, 0, 0}, col[3];
-      host_texture_colour(tex, dir, zero, col);
+      host_texture_colour(c, c->sky.texture, dir, zero, col);
       values.push_back((0.2126f * col[0] + 0.7152f * col[1] + 0.0722f * col[2]) * sin_theta);
     }
   std::vector<float> ycdf, ypdf, xcdf, xpdf, yvals, p, q;
@@ -461,15 +447,15 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
     return set_error(c, PTB_ERR_INVALID, "scene has no sky (ptb_scene_set_sky)");
   }
   if (c->sky.texture >= c->textures.size()) return set_error(c, PTB_ERR_INVALID, "sky texture index out of range");
-  for (const auto& t : c->textures)
-    if (t.kind == PTB_TEX_IMAGE || t.kind == PTB_TEX_PERLIN)
-      return set_error(c, PTB_ERR_UNSUPPORTED, "image/perlin textures are not supported by the cuda backend yet");
-  for (const auto& m : c->materials)
-    if (m.kind == PTB_MAT_TROWBRIDGE_REITZ)
-      return set_error(c, PTB_ERR_UNSUPPORTED, "trowbridge_reitz is not supported by the cuda backend yet");
+  for (size_t i = 0; i < c->textures.size(); ++i)
+    if ((c->textures[i].kind == PTB_TEX_IMAGE || c->textures[i].kind == PTB_TEX_PERLIN) && !c->texture_data.count((uint32_t)i))
+      return set_error(c, PTB_ERR_MISSING, "texture %zu needs ptb_scene_set_texture_data before commit", i);
 
   cudaStream_t st = c->stream;
   c->committed = false;
+  c->scene_needs_full_shade = false;
+  for (const auto& t : c->textures) c->scene_needs_full_shade |= t.kind == PTB_TEX_IMAGE || t.kind == PTB_TEX_PERLIN;
+  for (const auto& m : c->materials) c->scene_needs_full_shade |= m.kind == PTB_MAT_TROWBRIDGE_REITZ;
 
   // materials / textures / camera
   std::vector<DevMaterial> dm(c->materials.size());
@@ -479,13 +465,26 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
     dm[i].ior[0] = m.ior.x; dm[i].ior[1] = m.ior.y; dm[i].ior[2] = m.ior.z; dm[i]._pad = 0;
   }
   std::vector<DevTexture> dt(c->textures.size());
+  std::vector<float> tex_words;
   for (size_t i = 0; i < dt.size(); ++i) {
     const ptb_texture& t = c->textures[i];
+    dt[i] = DevTexture{};
     dt[i].kind = t.kind;
     dt[i].a[0] = t.a.x; dt[i].a[1] = t.a.y; dt[i].a[2] = t.a.z;
     dt[i].b[0] = t.b.x; dt[i].b[1] = t.b.y; dt[i].b[2] = t.b.z;
-    dt[i]._pad = 0;
+    auto it = c->texture_data.find((uint32_t)i);
+    if (it != c->texture_data.end()) {
+      if (tex_words.size() + it->second.data.size() > 0xFFFFFFF0ull) return set_error(c, PTB_ERR_INVALID, "texture data exceeds 16 GiB");
+      dt[i].data_off = (uint32_t)tex_words.size();
+      dt[i].width = it->second.width;
+      dt[i].height = it->second.height;
+      tex_words.insert(tex_words.end(), it->second.data.begin(), it->second.data.end());
+    }
   }
+  PTB_CUDA_TRY(c, c->d_tex_data.reserve(tex_words.size() * sizeof(float)));
+  if (!tex_words.empty())
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_tex_data.p, tex_words.data(), tex_words.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+  c->dev.tex_data = c->d_tex_data.as<float>();
   PTB_CUDA_TRY(c, c->d_materials.reserve(dm.size() * sizeof(DevMaterial)));
   PTB_CUDA_TRY(c, c->d_textures.reserve(dt.size() * sizeof(DevTexture)));
   PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_materials.p, dm.data(), dm.size() * sizeof(DevMaterial), cudaMemcpyHostToDevice, st));

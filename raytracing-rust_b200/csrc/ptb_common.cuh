@@ -170,11 +170,80 @@ struct DevMaterial {
   float ior[3];
   uint32_t _pad;
 };
-struct DevTexture {
+struct DevTexture {  // 48 B
   uint32_t kind;
   float a[3], b[3];
-  uint32_t _pad;
+  uint32_t data_off;       // first word of this texture's bulk data in DevScene::tex_data (image pixels / perlin tables)
+  uint32_t width, height;  // ImageTexture only
+  uint32_t _pad[2];
 };
+
+// ---------------------------------------------------------------- textures (implementations/src/textures/mod.rs)
+// One definition for the device (k_shade) and the host (sky table at commit). `words` = the texture's bulk data.
+struct TexWords {
+  const float* p;
+  PTB_HD float f(uint32_t i) const {
+#ifdef __CUDA_ARCH__
+    return __ldg(p + i);
+#else
+    return p[i];
+#endif
+  }
+  PTB_HD uint32_t u(uint32_t i) const { return f2u(f(i)); }
+};
+PTB_HD int32_t sat_i32(float f) {  // Rust `as i32`: saturating, NaN -> 0
+  if (f != f) return 0;
+  if (f >= 2147483648.0f) return 2147483647;
+  if (f <= -2147483648.0f) return (-2147483647 - 1);
+  return (int32_t)f;
+}
+PTB_HD uint32_t sat_index(float f, uint32_t hi) {  // Rust `as usize` then clamp(0, hi)
+  if (!(f > 0.0f)) return 0u;
+  if (f >= 4294967040.0f) return hi;
+  const uint32_t i = (uint32_t)f;
+  return i > hi ? hi : i;
+}
+// Perlin::noise + trilinear_lerp (textures/mod.rs:114-139, 161-179); words = 256 ran scalars | perm_x | perm_y | perm_z
+PTB_HD float perlin_noise(TexWords words, v3 point) {
+  const float fx = floorf(point.x), fy = floorf(point.y), fz = floorf(point.z);
+  const float u = point.x - fx, v = point.y - fy, w = point.z - fz;
+  const uint32_t i = (uint32_t)sat_i32(fx), j = (uint32_t)sat_i32(fy), k = (uint32_t)sat_i32(fz);
+  const float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+  float value = 0.0f;
+#pragma unroll
+  for (uint32_t index = 0; index < 8u; ++index) {
+    const uint32_t di = index >> 2, dj = (index >> 1) & 1u, dk = index & 1u;
+    const uint32_t h = words.u(256u + ((i + di) & 255u)) ^ words.u(512u + ((j + dj) & 255u)) ^ words.u(768u + ((k + dk) & 255u));
+    const float r = words.f(h & 255u);
+    const float fi = (float)di, fj = (float)dj, fk = (float)dk;
+    const v3 c = r * mk(1.0f, 1.0f, 1.0f);
+    value += (fi * uu + (1.0f - fi) * (1.0f - uu)) * (fj * vv + (1.0f - fj) * (1.0f - vv)) * (fk * ww + (1.0f - fk) * (1.0f - ww)) *
+             dot(c, mk(u - fi, v - fj, w - fk));
+  }
+  return value;
+}
+PTB_HD v3 texture_eval(uint32_t kind, v3 a, v3 b, uint32_t width, uint32_t height, TexWords words, v3 direction, v3 point) {
+  if (kind == PTB_TEX_SOLID) return a;  // :193-200
+  if (kind == PTB_TEX_LERP) {           // :283-291
+    const float tt = direction.z * 0.5f + 0.5f;
+    return a * tt + b * (1.0f - tt);
+  }
+  if (kind == PTB_TEX_CHECKERED) {      // :61-73
+    const float sign = sinf(10.0f * point.x) * sinf(10.0f * point.y) * sinf(10.0f * point.z);
+    return sign > 0.0f ? a : b;
+  }
+  if (kind == PTB_TEX_IMAGE) {          // :248-262: lat-long lookup by direction, nearest texel, dim = (w-1, h-1)
+    const float phi = atan2f(direction.y, direction.x) + kPi;
+    const float theta = acosf(direction.z);
+    const float uvx = phi / (2.0f * kPi), uvy = theta / kPi;
+    const uint32_t dim0 = width - 1u, dim1 = height - 1u;
+    const uint32_t x_pixel = sat_index((float)dim0 * uvx, dim0), y_pixel = sat_index((float)dim1 * uvy, dim1);
+    const uint32_t index = 3u * (y_pixel * (dim0 + 1u) + x_pixel);
+    return mk(words.f(index), words.f(index + 1u), words.f(index + 2u));
+  }
+  if (kind == PTB_TEX_PERLIN) return 0.5f * mk(1.0f, 1.0f, 1.0f) * (1.0f + perlin_noise(words, point));  // :171-179
+  return mk(1.0f, 1.0f, 1.0f);          // trait default :10-12
+}
 
 struct DevScene {
   // geometry in Morton-sorted slot order, 3 x float4 per slot:
@@ -186,6 +255,7 @@ struct DevScene {
   const BvhNode* nodes;
   const DevMaterial* materials;
   const DevTexture* textures;
+  const float* tex_data;      // bulk texture data (image pixels, perlin tables), see DevTexture::data_off
   const uint32_t* lights;     // slots (with kSphereBit where applicable) whose material is_light()
   uint32_t n_prims, n_lights;
   // sky (implementations/src/sky.rs): Emit(texture, 1.0) + lat-long Distribution2D

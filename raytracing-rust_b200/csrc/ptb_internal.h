@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -83,14 +84,17 @@ struct Ctx {
   DevBuf scratch[16];  // LBVH build temporaries, grow-only (lbvh_build.cu)
   std::vector<ptb_material> materials;
   std::vector<ptb_texture> textures;
+  struct TexData { uint32_t width = 0, height = 0; std::vector<float> data; };
+  std::map<uint32_t, TexData> texture_data;  // ptb_scene_set_texture_data
   ptb_camera camera{};
   ptb_sky sky{};
   bool have_camera = false, have_sky = false;
   bool committed = false;
+  bool scene_needs_full_shade = false;  // any Trowbridge-Reitz material or image / perlin texture (k_shade<.., FULL>)
 
   // device scene
   DevScene dev{};
-  DevBuf d_geom, d_normals, d_slot_prim, d_slot_mat, d_nodes, d_morton, d_materials, d_textures, d_lights;
+  DevBuf d_geom, d_normals, d_slot_prim, d_slot_mat, d_nodes, d_morton, d_materials, d_textures, d_tex_data, d_lights;
   DevBuf d_sky_ycdf, d_sky_ypdf, d_sky_xcdf, d_sky_xpdf;
   uint64_t n_prims = 0, n_nodes = 0;
 

@@ -38,22 +38,31 @@ struct Queues {
 constexpr uint32_t kFlagPrevDelta = 1u << 8;  // stored above the 8-bit depth in ray_d.w
 
 // ------------------------------------------------------------------------------------------ textures / sky
-// implementations/src/textures/mod.rs:61-73 (checkered), 193-200 (solid), 283-291 (lerp)
-PTB_DEV v3 texture_colour(const DevScene& sc, uint32_t tex, v3 direction, v3 point) {
-  const DevTexture* t = sc.textures + tex;
+// implementations/src/textures/mod.rs (all five kinds; the arithmetic is texture_eval in ptb_common.cuh)
+// FULL = false: kernels for scenes that hold only solid / lerp / checkered textures and no Trowbridge-Reitz material
+// (the host picks the instantiation at launch), so the common case does not pay registers for the rest.
+template <bool FULL>
+PTB_DEV v3 texture_colour(const DevTexture* __restrict__ textures, const float* __restrict__ tex_data, uint32_t tex,
+                          v3 direction, v3 point) {
+  const DevTexture* t = textures + tex;
   const uint32_t kind = __ldg(&t->kind);
   const v3 a = mk(__ldg(&t->a[0]), __ldg(&t->a[1]), __ldg(&t->a[2]));
   if (kind == PTB_TEX_SOLID) return a;
   const v3 b = mk(__ldg(&t->b[0]), __ldg(&t->b[1]), __ldg(&t->b[2]));
-  if (kind == PTB_TEX_LERP) {
-    const float tt = direction.z * 0.5f + 0.5f;
-    return a * tt + b * (1.0f - tt);
-  }
-  if (kind == PTB_TEX_CHECKERED) {
+  if (!FULL) {
+    if (kind == PTB_TEX_LERP) {
+      const float tt = direction.z * 0.5f + 0.5f;
+      return a * tt + b * (1.0f - tt);
+    }
     const float sign = sinf(10.0f * point.x) * sinf(10.0f * point.y) * sinf(10.0f * point.z);
     return sign > 0.0f ? a : b;
   }
-  return mk(1.0f, 1.0f, 1.0f);
+  TexWords words{tex_data + __ldg(&t->data_off)};
+  return texture_eval(kind, a, b, __ldg(&t->width), __ldg(&t->height), words, direction, point);
+}
+template <bool FULL>
+PTB_DEV v3 texture_colour(const DevScene& sc, uint32_t tex, v3 direction, v3 point) {
+  return texture_colour<FULL>(sc.textures, sc.tex_data, tex, direction, point);
 }
 
 // statistics/distributions.rs:51-72
@@ -71,12 +80,6 @@ PTB_DEV uint32_t dist1d_sample(const float* __restrict__ cdf, uint32_t cdf_len, 
   }
   const uint32_t r = first - 1u, hi = cdf_len - 2u;
   return r > hi ? hi : r;
-}
-PTB_DEV uint32_t sat_index(float f, uint32_t hi) {  // Rust `as usize` then clamp(0, hi)
-  if (!(f > 0.0f)) return 0u;
-  if (f >= 4294967040.0f) return hi;
-  const uint32_t i = (uint32_t)f;
-  return i > hi ? hi : i;
 }
 // sky.rs:43-60
 PTB_DEV float sky_pdf(const DevScene& sc, v3 wi) {
@@ -319,18 +322,123 @@ k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
 // ------------------------------------------------------------------------------------------ K10 shade
 struct Surface {  // what the integrators read from `hit` + `mat`
   HitRec h;
-  uint32_t kind, tex;
+  uint32_t kind, tex, mat;
   float param;
   bool miss;
 };
 
+// ------------------------------------------------------------------------------------------ Trowbridge-Reitz (GGX)
+// statistics/bxdfs/trowbridge_reitz.rs:17-24 (d), 62-78 (g2), 80-89 (g1); trowbridge_reitz_vndf.rs:9-15 (vndf),
+// 84-113 (sample_vndf, a_x = a_y), 35-52 (sample, pdf); materials/trowbridge_reitz.rs:26-88. Kept out of line: the
+// code is only reached from the Trowbridge-Reitz shade queue and must not cost the other materials registers.
+PTB_DEV float tr_d(float alpha, float cos_theta) {
+  if (cos_theta <= 0.0f) return 0.0f;
+  const float a_sq = alpha * alpha;
+  const float tmp = cos_theta * cos_theta * (a_sq - 1.0f) + 1.0f;
+  return a_sq / (kPi * tmp * tmp);
+}
+PTB_DEV float tr_g1(float alpha, v3 normal, v3 h, v3 v) {
+  if (dot(v, h) / dot(v, normal) <= 0.0f) return 0.0f;
+  const float c = dot(normal, v);
+  const float cos_sq = c * c;
+  const float alpha_sq = alpha * alpha;
+  const float tmp = alpha_sq + (1.0f - alpha_sq) * cos_sq;
+  return 2.0f * c / (sqrtf(tmp) + c);
+}
+PTB_DEV float tr_g2(float alpha, v3 normal, v3 h, v3 incoming, v3 outgoing) {
+  if (dot(incoming, h) / dot(incoming, normal) <= 0.0f || dot(outgoing, h) / dot(outgoing, normal) <= 0.0f) return 0.0f;
+  const float alpha_sq = alpha * alpha;
+  const float one_minus_alpha_sq = 1.0f - alpha_sq;
+  const float cos_i = dot(normal, incoming);
+  const float tmp_a = alpha_sq + one_minus_alpha_sq * (cos_i * cos_i);
+  const float cos_o = dot(normal, outgoing);
+  const float tmp_b = alpha_sq + one_minus_alpha_sq * (cos_o * cos_o);
+  return 2.0f * cos_i * cos_o / (cos_o * sqrtf(tmp_a) + cos_i * sqrtf(tmp_b));
+}
+PTB_DEV void onb_basis(v3 z, v3& x, v3& y) {  // utility/coord.rs:10-22
+  if (fabsf(z.x) > fabsf(z.y)) x = mk(-z.z, 0.0f, z.x) / sqrtf(z.x * z.x + z.z * z.z);
+  else x = mk(0.0f, z.z, -z.y) / sqrtf(z.y * z.y + z.z * z.z);
+  y = cross(x, z);
+}
+PTB_DEV v3 onb_to_local(v3 x, v3 y, v3 z, v3 v) {  // create_inverse().to_coord(v), coord.rs:23-30
+  return v.x * mk(x.x, y.x, z.x) + v.y * mk(x.y, y.y, z.y) + v.z * mk(x.z, y.z, z.z);
+}
+__device__ __noinline__ float tr_pdf(float alpha, v3 incoming, v3 outgoing, v3 normal) {
+  v3 x, y;
+  onb_basis(normal, x, y);
+  const v3 in = onb_to_local(x, y, normal, incoming), out = onb_to_local(x, y, normal, outgoing);
+  v3 h = normalised(out + in);
+  if (h.z < 0.0f) h = -h;
+  // vndf (h.z >= 0 here)
+  const float vndf = tr_g1(alpha, mk(0.0f, 0.0f, 1.0f), h, in) * fmaxf(dot(in, h), 0.0f) * tr_d(alpha, h.z) / in.z;
+  return vndf / (4.0f * dot(in, h));
+}
+__device__ __noinline__ v3 tr_sample(float a, v3 incoming, v3 normal, float u1, float u2) {
+  v3 x, y;
+  onb_basis(normal, x, y);
+  const v3 in = onb_to_local(x, y, normal, incoming);
+  const v3 vh = normalised(mk(a * in.x, a * in.y, in.z));
+  const float len_sq = vh.x * vh.x + vh.y * vh.y;
+  const v3 b2 = len_sq > 0.0f ? mk(-vh.y, vh.x, 0.0f) / sqrtf(len_sq) : mk(1.0f, 0.0f, 0.0f);
+  const v3 b3 = cross(vh, b2);
+  const float r = sqrtf(u1);
+  const float phi = kTau * u2;
+  const float tx = r * cosf(phi);
+  float ty = r * sinf(phi);
+  const float sh = 0.5f * (1.0f + vh.z);
+  ty = (1.0f - sh) * sqrtf(1.0f - tx * tx) + sh * ty;
+  const v3 hh = tx * b2 + ty * b3 + sqrtf(fmaxf(1.0f - tx * tx - ty * ty, 0.0f)) * vh;
+  const v3 hl = normalised(mk(a * hh.x, a * hh.y, fmaxf(hh.z, 0.0f)));
+  const v3 h = hl.x * x + hl.y * y + hl.z * normal;
+  return reflected(incoming, h);
+}
+// eval (which == 0) or eval_over_scattering_pdf (which == 1); wo is the integrator's wo (ray direction, INTO the surface).
+// Everything is passed by value: a reference to the kernel's DevScene / Surface would force them into local memory.
+struct TrArgs {
+  const DevMaterial* m;
+  const DevTexture* textures;
+  const float* tex_data;
+  uint32_t tex;
+  float alpha;
+  v3 normal, point;
+};
+__device__ __noinline__ v3 tr_eval_impl(TrArgs s, v3 wo_in, v3 wi, int which) {
+  const v3 wo = -wo_in;
+  const v3 h = normalised(wi + wo);
+  if (dot(wi, s.normal) < 0.0f || dot(h, wo) < 0.0f) return mk(0.0f, 0.0f, 0.0f);
+  const DevMaterial* m = s.m;
+  const v3 ior = mk(__ldg(&m->ior[0]), __ldg(&m->ior[1]), __ldg(&m->ior[2]));
+  const float metallic = __ldg(&m->metallic);
+  v3 f0 = vabs((mk(1.0f, 1.0f, 1.0f) - ior) / (mk(1.0f, 1.0f, 1.0f) + ior));
+  f0 = f0 * f0;
+  f0 = (1.0f - metallic) * f0 + metallic * texture_colour<true>(s.textures, s.tex_data, s.tex, wi, s.point);
+  const v3 f = f0 + (mk(1.0f, 1.0f, 1.0f) - f0) * powf(1.0f - dot(wo, h), 5.0f);  // refract.rs:59-61
+  const float g = tr_g2(s.alpha, s.normal, h, wo, wi);
+  if (which == 0) {
+    const float d = tr_d(s.alpha, dot(s.normal, h));
+    return f * g * d / (4.0f * fabsf(dot(wo, s.normal)) * dot(wi, s.normal));
+  }
+  return f * g / tr_g1(s.alpha, s.normal, h, wo);
+}
+PTB_DEV v3 tr_eval(const DevScene& sc, const Surface& s, v3 wo_in, v3 wi, int which) {
+  TrArgs a{sc.materials + s.mat, sc.textures, sc.tex_data, s.tex, s.param, s.h.normal, s.h.point};
+  return tr_eval_impl(a, wo_in, wi, which);
+}
+
 // rt_core/src/material.rs:20-26 + materials/lambertian.rs:42-47 / reflect.rs:37-39 / refract.rs:51-53
-PTB_DEV float mat_scattering_pdf(const Surface& s, v3 wi) {
+template <bool FULL>
+PTB_DEV float mat_scattering_pdf(const Surface& s, v3 wo, v3 wi) {
   if (s.kind == PTB_MAT_LAMBERTIAN) return fmaxf(dot(wi, s.h.normal), 0.0f) / kPi;
+  if (FULL && s.kind == PTB_MAT_TROWBRIDGE_REITZ) {  // trowbridge_reitz.rs:51-59
+    const float a = tr_pdf(s.param, -wo, wi, s.h.normal);
+    return a == 0.0f ? __int_as_float(0x7f800000) : a;
+  }
   return 0.0f;  // Reflect / Refract keep the trait default (quirk Q4)
 }
+template <bool FULL>
 PTB_DEV v3 mat_eval(const DevScene& sc, const Surface& s, v3 wo, v3 wi) {
-  const v3 col = texture_colour(sc, s.tex, wo, s.h.point);
+  if (FULL && s.kind == PTB_MAT_TROWBRIDGE_REITZ) return tr_eval(sc, s, wo, wi, 0);
+  const v3 col = texture_colour<FULL>(sc, s.tex, wo, s.h.point);
   if (s.kind == PTB_MAT_LAMBERTIAN) return col * s.param * fmaxf(dot(s.h.normal, wi), 0.0f) / kPi;
   return col;
 }
@@ -342,7 +450,7 @@ PTB_DEV void finish_path(float* __restrict__ accum, uint32_t pixel, v3 L, bool n
   atomicAdd(accum + 3u * (size_t)pixel + 2, L.z);
 }
 
-template <int METHOD>
+template <int METHOD, bool FULL>
 __global__ void __launch_bounds__(256, PTB_SHADE_MIN_BLOCKS)
 k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -391,11 +499,13 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
       s.h.out = false;
       s.kind = PTB_MAT_EMIT;
       s.tex = sc.sky_tex;
+      s.mat = 0u;
       s.param = 1.0f;
     } else {
       prim_hit(sc, ray, ht.y, s.h);  // same arithmetic as the traversal: reproduces t, adds point/normal/error/out
       const uint32_t mi = __ldg(sc.slot_mat + (ht.y & kSlotMask)) & 0x00FFFFFFu;
       const DevMaterial* m = sc.materials + mi;
+      s.mat = mi;
       s.kind = __ldg(&m->kind);
       s.tex = __ldg(&m->tex);
       s.param = __ldg(&m->param);
@@ -408,7 +518,7 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
       // integrators/mod.rs:29-72
       if (is_emit) {
         const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);        // emissive.rs:23-26
-        const v3 emission = s.param * texture_colour(sc, s.tex, wo, point);
+        const v3 emission = s.param * texture_colour<FULL>(sc, s.tex, wo, point);
         L = L + T * emission;  // depth 0: throughput is exactly (1,1,1)
         finished = true;
       } else {
@@ -419,7 +529,7 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
       if (depth == 0u) {
         if (is_emit) {
           const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);
-          L = L + s.param * texture_colour(sc, s.tex, wo, point);
+          L = L + s.param * texture_colour<FULL>(sc, s.tex, wo, point);
           finished = true;
           nan_check = false;  // mis.rs:29-31 returns before the NaN test
         } else {
@@ -430,7 +540,7 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
         if (is_emit) {
           // mis.rs:55: emission of the NEW material evaluated with the PREVIOUS hit record (quirk Q6); the
           // previous hit's offset point is this ray's origin (lambertian.rs:37, reflect.rs:29)
-          const v3 le = s.param * texture_colour(sc, s.tex, wo, ray.o);
+          const v3 le = s.param * texture_colour<FULL>(sc, s.tex, wo, ray.o);
           if (!is_zero(le)) {
             const bool sky_samplable = (sc.sky_rx | sc.sky_ry) != 0u;
             const bool use_mis = s.miss ? sky_samplable : !prev_delta;  // mis.rs:57-60 (an emissive prim is in `lights`)
@@ -484,7 +594,7 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
             const uint4 r2 = philox4x32_10(pixel, sample, (depth << 8) | RNG_NEE, 1u, rp.k0, rp.k1);
             l_wi = sky_sample(sc, u32_to_unit(r.y), u32_to_unit(r.z), u32_to_unit(r.w), u32_to_unit(r2.x));
             const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);
-            le = 1.0f * texture_colour(sc, sc.sky_tex, l_wi, point);
+            le = 1.0f * texture_colour<FULL>(sc, sc.sky_tex, l_wi, point);
             l_pdf = sky_pdf(sc, l_wi) * mult;
             usable = true;
             shadow_is_sky = 1u;
@@ -499,7 +609,7 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
                 const uint32_t lmi = __ldg(sc.slot_mat + (lref & kSlotMask)) & 0x00FFFFFFu;
                 const DevMaterial* lm = sc.materials + lmi;
                 const v3 lpoint = offset_ray(si.point, si.normal, si.error, true);
-                le = __ldg(&lm->param) * texture_colour(sc, __ldg(&lm->tex), l_wi, lpoint);
+                le = __ldg(&lm->param) * texture_colour<FULL>(sc, __ldg(&lm->tex), l_wi, lpoint);
                 l_pdf = pdf * mult;
                 tmax = si.t;
                 exclude = lref & kSlotMask;
@@ -508,9 +618,9 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
             }
           }
           if (usable) {
-            const float mp = mat_scattering_pdf(s, l_wi);
+            const float mp = mat_scattering_pdf<FULL>(s, wo, l_wi);
             const float w = power_heuristic(l_pdf, mp);
-            const v3 contrib = T * mat_eval(sc, s, wo, l_wi) * w * le / l_pdf;  // mis.rs:42
+            const v3 contrib = T * mat_eval<FULL>(sc, s, wo, l_wi) * w * le / l_pdf;  // mis.rs:42
             const v3 sd = l_wi / mag(l_wi);  // Ray::new normalises (ray.rs:14)
             sh_o = make_float4(so.x, so.y, so.z, tmax);
             sh_d = make_float4(sd.x, sd.y, sd.z, __uint_as_float(exclude));
@@ -529,6 +639,10 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
         const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
         const float phi = 2.0f * kPi * u32_to_unit(r.y);
         new_dir = onb_to_world(s.h.normal, mk(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cos_theta));
+        new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+      } else if (FULL && s.kind == PTB_MAT_TROWBRIDGE_REITZ) {
+        // trowbridge_reitz.rs:38-50: VNDF sample about the normal, draws (r, phi) = (sqrt(u1), tau * u2)
+        new_dir = tr_sample(s.param, -wo, s.h.normal, u32_to_unit(r.x), u32_to_unit(r.y));
         new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
       } else if (s.kind == PTB_MAT_REFLECT) {
         // reflect.rs:26-36; random_unit_vector (utility/mod.rs:15-25) is a rejection loop whose result is uniform on
@@ -561,11 +675,12 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
         delta = true;
       }
       const v3 nd = new_dir / mag(new_dir);  // Ray::new
-      const v3 col = texture_colour(sc, s.tex, wo, s.h.point);
+      const bool is_tr = FULL && s.kind == PTB_MAT_TROWBRIDGE_REITZ;
+      const v3 col = is_tr ? tr_eval(sc, s, wo, nd, 1) : texture_colour<FULL>(sc, s.tex, wo, s.h.point);
       if (METHOD == PTB_METHOD_NAIVE) {
         // integrators/mod.rs:57-70
         if (s.kind == PTB_MAT_LAMBERTIAN) T = T * (col * s.param);
-        else T = T * col;
+        else T = T * col;  // Trowbridge-Reitz: col is already eval_over_scattering_pdf
         bool survive = true;
         if (depth > rp.rr_threshold) {
           const float p = cmax3(T.x, T.y, T.z);
@@ -581,6 +696,9 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
         if (s.kind == PTB_MAT_LAMBERTIAN) {
           m_pdf = fmaxf(dot(nd, s.h.normal), 0.0f) / kPi;
           T = T * (col * s.param);
+        } else if (is_tr) {
+          m_pdf = mat_scattering_pdf<FULL>(s, wo, nd);
+          T = T * col;
         } else {
           m_pdf = 0.0f;
           T = T * (col / 0.0f);  // eval / scattering_pdf with the default pdf 0 (quirk Q4)
@@ -841,7 +959,9 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   // k_shade is register-heavy (MIS: ~130): smaller blocks let more of them share an SM's register file
   int TS = mis ? 128 : 256;
   if (const char* e = getenv("PTB_SHADE_THREADS")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) TS = v; }
-  const void* shade_fn = mis ? (const void*)k_shade<PTB_METHOD_MIS> : (const void*)k_shade<PTB_METHOD_NAIVE>;
+  const bool full = c->scene_needs_full_shade;
+  const void* shade_fn = mis ? (full ? (const void*)k_shade<PTB_METHOD_MIS, true> : (const void*)k_shade<PTB_METHOD_MIS, false>)
+                             : (full ? (const void*)k_shade<PTB_METHOD_NAIVE, true> : (const void*)k_shade<PTB_METHOD_NAIVE, false>);
   uint32_t grid_shade = (uint32_t)persistent_grid(c, shade_fn, TS);
   if (grid_shade > (P + TS - 1) / TS) grid_shade = (P + TS - 1) / TS;
   const bool count = c->opt_count_traversal;
@@ -884,8 +1004,13 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
     else k_trace<false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
     PTB_PROF(1, 1);
     PTB_PROF(2, 0);
-    if (mis) k_shade<PTB_METHOD_MIS><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
-    else k_shade<PTB_METHOD_NAIVE><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+    if (mis) {
+      if (full) k_shade<PTB_METHOD_MIS, true><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+      else k_shade<PTB_METHOD_MIS, false><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+    } else {
+      if (full) k_shade<PTB_METHOD_NAIVE, true><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+      else k_shade<PTB_METHOD_NAIVE, false><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
+    }
     PTB_PROF(2, 1);
     c->stats.kernel_launches += 5;
     c->stats.trace_launches += 1;

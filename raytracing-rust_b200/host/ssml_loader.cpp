@@ -238,6 +238,8 @@ struct ptb_host_scene {
   std::vector<ptb_triangle> triangles;
   std::vector<ptb_material> materials;
   std::vector<ptb_texture> textures;
+  struct TexData { uint32_t width = 0, height = 0; std::vector<float> data; };
+  std::map<uint32_t, TexData> texture_data;  // ImageTexture pixels / Perlin tables, keyed by texture index
   ptb_camera camera{};
   ptb_sky sky{};
   std::vector<std::string> warnings;
@@ -258,7 +260,7 @@ struct Loader {
   }
 
   // textures.rs:5-84
-  int32_t load_texture(const Object& o, ptb_texture& t) {
+  int32_t load_texture(const Object& o, ptb_texture& t, ptb_host_scene::TexData& td) {
     Props p(o);
     const std::string* kind = p.text("type");
     if (!kind) return fail(PTB_ERR_MISSING, "missing required type for object (texture)");
@@ -271,10 +273,29 @@ struct Loader {
       t.kind = PTB_TEX_SOLID;
       if (!p.vec3("colour", t.a)) t.a = smul(0.5f, V(1, 1, 1));
     } else if (*kind == "image") {
-      if (!p.text("filename")) return fail(PTB_ERR_MISSING, "missing required value for object: filename");
-      return fail(PTB_ERR_UNSUPPORTED, "texture type 'image' is not supported by the cuda backend yet");
+      // textures.rs:50-60 + ImageTexture::new (implementations/src/textures/mod.rs:208-245)
+      const std::string* fn = p.text("filename");
+      if (!fn) return fail(PTB_ERR_MISSING, "missing required value for object: filename");
+      t.kind = PTB_TEX_IMAGE;
+      std::string path = *fn;
+      {
+        std::ifstream probe(path, std::ios::binary);
+        if (!probe.good() && !base_dir.empty() && !path.empty() && path[0] != '/')
+          path = base_dir + "/" + *fn;  // extension: also resolve relative to the scene file
+      }
+      float* px = nullptr;
+      int32_t rc = ptb_image_load(path.c_str(), &td.width, &td.height, &px);
+      if (rc != PTB_OK) return fail(rc, std::string("image texture: ") + ptb_image_last_error());
+      td.data.assign(px, px + (size_t)td.width * td.height * 3);
+      ptb_image_free(px);
     } else if (*kind == "perlin") {
-      return fail(PTB_ERR_UNSUPPORTED, "texture type 'perlin' is not supported by the cuda backend yet");
+      // textures.rs:62-67 + Perlin::new (textures/mod.rs:90-112); the reference seeds the tables from OS entropy, here
+      // they are a pure function of the (optional, extension) `seed` key and the texture's position in the file
+      t.kind = PTB_TEX_PERLIN;
+      float seed = 0.0f;
+      p.flt("seed", seed);
+      td.data.resize(PTB_PERLIN_TABLE_WORDS);
+      ptb_perlin_tables(0x9E3779B97F4A7C15ull ^ ((uint64_t)(int64_t)seed << 20) ^ (uint64_t)sc->textures.size(), td.data.data());
     } else {
       return fail(PTB_ERR_MISSING, "required a known value for texture type, found '" + *kind + "'");
     }
@@ -435,8 +456,10 @@ struct Loader {
     for (const Object& o : objects) {
       if (o.kind != K_TEXTURE) continue;
       ptb_texture t;
-      if (load_texture(o, t) != PTB_OK) return err;
+      ptb_host_scene::TexData td;
+      if (load_texture(o, t, td) != PTB_OK) return err;
       sc->textures.push_back(t);
+      if (!td.data.empty()) sc->texture_data[(uint32_t)sc->textures.size() - 1] = std::move(td);
       if (o.has_name) {
         if (tex_lookup.count(o.name)) sc->warnings.push_back("Overwrote previous object of name: '" + o.name + "'");
         tex_lookup[o.name] = (uint32_t)sc->textures.size() - 1;
@@ -620,6 +643,15 @@ size_t ptb_host_scene_materials(const ptb_host_scene* s, const ptb_material** ou
 size_t ptb_host_scene_textures(const ptb_host_scene* s, const ptb_texture** out) {
   if (out) *out = s->textures.data();
   return s->textures.size();
+}
+size_t ptb_host_scene_texture_data(const ptb_host_scene* s, uint32_t texture, uint32_t* width, uint32_t* height,
+                                   const float** data) {
+  auto it = s->texture_data.find(texture);
+  if (it == s->texture_data.end()) return 0;
+  if (width) *width = it->second.width;
+  if (height) *height = it->second.height;
+  if (data) *data = it->second.data.data();
+  return it->second.data.size();
 }
 int32_t ptb_host_scene_camera(const ptb_host_scene* s, ptb_camera* out) {
   if (!s || !out) return PTB_ERR_INVALID;

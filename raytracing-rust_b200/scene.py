@@ -22,6 +22,8 @@ class HostScene:
     textures: np.ndarray = field(default_factory=lambda: np.zeros(0, L.texture_dtype))
     camera: np.ndarray = field(default_factory=lambda: np.zeros(1, L.camera_dtype))
     sky: np.ndarray = field(default_factory=lambda: np.zeros(1, L.sky_dtype))
+    # bulk data of ImageTexture / Perlin textures: texture index -> (width, height, float32 words)
+    texture_data: dict = field(default_factory=dict)
 
     @property
     def n_primitives(self) -> int:
@@ -30,7 +32,7 @@ class HostScene:
     def nbytes(self) -> int:
         """Bytes a ptb_scene_upload + commit moves host -> device."""
         return int(self.spheres.nbytes + self.triangles.nbytes + self.materials.nbytes + self.textures.nbytes
-                   + self.camera.nbytes + self.sky.nbytes)
+                   + self.camera.nbytes + self.sky.nbytes + sum(d.nbytes for _, _, d in self.texture_data.values()))
 
     # -- builders used by tests / generators ------------------------------------------------------------
     def add_texture(self, kind: int, a=(0, 0, 0), b=(0, 0, 0)) -> int:
@@ -39,9 +41,27 @@ class HostScene:
         self.textures = np.concatenate([self.textures, t])
         return len(self.textures) - 1
 
-    def add_material(self, kind: int, texture: int, param: float) -> int:
+    def add_image_texture(self, rgb: np.ndarray) -> int:
+        """ImageTexture (textures/mod.rs:202-266) from an (H, W, 3) float array."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32)
+        h, w, _ = rgb.shape
+        i = self.add_texture(L.TEX_IMAGE)
+        self.texture_data[i] = (w, h, rgb.reshape(-1).copy())
+        return i
+
+    def add_perlin_texture(self, seed: int = 0) -> int:
+        """Perlin (textures/mod.rs:75-180); tables are a pure function of `seed` (the reference uses OS entropy)."""
+        i = self.add_texture(L.TEX_PERLIN)
+        words = np.zeros(L.PERLIN_TABLE_WORDS, np.float32)
+        rc = L.lib.ptb_perlin_tables(seed, L.ptr(words))
+        if rc != L.PTB_OK:
+            raise L.PtbError(rc, "ptb_perlin_tables")
+        self.texture_data[i] = (0, 0, words)
+        return i
+
+    def add_material(self, kind: int, texture: int, param: float, ior=(1, 1, 1), metallic: float = 0.0) -> int:
         m = np.zeros(1, L.material_dtype)
-        m["kind"], m["texture"], m["param"], m["ior"] = kind, texture, param, (1, 1, 1)
+        m["kind"], m["texture"], m["param"], m["ior"], m["metallic"] = kind, texture, param, ior, metallic
         self.materials = np.concatenate([self.materials, m])
         return len(self.materials) - 1
 
@@ -80,6 +100,12 @@ def _from_handle(handle) -> HostScene:
     s.triangles = _copy_array(handle, L.lib.ptb_host_scene_triangles, L.triangle_dtype)
     s.materials = _copy_array(handle, L.lib.ptb_host_scene_materials, L.material_dtype)
     s.textures = _copy_array(handle, L.lib.ptb_host_scene_textures, L.texture_dtype)
+    for i in range(len(s.textures)):
+        w, h, p = C.c_uint32(), C.c_uint32(), C.c_void_p()
+        n = L.lib.ptb_host_scene_texture_data(handle, i, C.byref(w), C.byref(h), C.byref(p))
+        if n:
+            buf = (C.c_float * n).from_address(p.value)
+            s.texture_data[i] = (w.value, h.value, np.frombuffer(buf, dtype=np.float32, count=n).copy())
     L.lib.ptb_host_scene_camera(handle, L.ptr(s.camera))
     L.lib.ptb_host_scene_sky(handle, L.ptr(s.sky))
     return s
@@ -107,6 +133,19 @@ def load_str(text: str, base_dir: str = ".") -> HostScene:
         return _from_handle(h)
     finally:
         L.lib.ptb_host_scene_free(h)
+
+
+def load_image(filename: str) -> np.ndarray:
+    """ImageTexture::new's decode (textures/mod.rs:208-245): (H, W, 3) float32."""
+    w, h, p = C.c_uint32(), C.c_uint32(), C.c_void_p()
+    rc = L.lib.ptb_image_load(filename.encode(), C.byref(w), C.byref(h), C.byref(p))
+    if rc != L.PTB_OK:
+        raise L.PtbError(rc, L.lib.ptb_image_last_error().decode())
+    try:
+        buf = (C.c_float * (w.value * h.value * 3)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float32).reshape(h.value, w.value, 3).copy()
+    finally:
+        L.lib.ptb_image_free(p)
 
 
 def save_image(filename: str, width: int, height: int, rgb: np.ndarray, gamma: float = 2.2):

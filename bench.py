@@ -6,9 +6,9 @@
 
 Workload (default, BASELINE.json configs[2]): procedurally tessellated 1 000 000-triangle mesh (800k Lambertian
 terrain + 200k dielectric UV sphere), 1920x1080, naive integrator (quirk Q4: dielectrics are black under the
-reference's MIS), max depth 50. One STEP renders `--spp-per-step` samples of every pixel on every rank
-(4 steps x 64 spp = the config's 256 spp); with N ranks each rank renders its own sample range (weak scaling) and
-the per-rank accumulators are combined by ONE reduce(SUM) to rank 0 per step (NCCL over NVLink).
+reference's MIS), max depth 50. One STEP is one render call of the configuration as BASELINE.json states it:
+`--spp-per-step` = 256 samples of every pixel on every rank; with N ranks each rank renders its own sample range (weak
+scaling) and the per-rank accumulators are combined by ONE reduce(SUM) to rank 0 per step (NCCL over NVLink).
 
 A ray = one BVH traversal launched (camera, bounce, light-shadow, sky-shadow each count 1) — SURVEY.md §8(d).
 """
@@ -36,7 +36,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "rtweekend1", "overshadowed", "closest_hit"])
-    ap.add_argument("--spp-per-step", type=int, default=64)
+    ap.add_argument("--spp-per-step", type=int, default=256,
+                    help="samples per pixel one step renders on each rank (default: the config's full 256 spp)")
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--method", default="", choices=["", "naive", "mis"])

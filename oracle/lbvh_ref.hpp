@@ -42,7 +42,6 @@ struct Lbvh {
   std::vector<uint32_t> prim_sorted;  // sorted position -> original primitive id
   std::vector<ptb_bvh_node> nodes;  // n-1 internal nodes (1 when n == 1), root = 0
   Vec3 cmin, cmax;
-
   int delta(int64_t i, int64_t j) const {
     int64_t n = (int64_t)morton.size();
     if (j < 0 || j >= n) return -1;
@@ -145,34 +144,33 @@ struct Lbvh {
     }
   }
 
-  // Slab test of aabb.rs:22-57 with the device's additions: the box is culled only when its entry distance, less an
-  // error slack of 32*eps*(largest finite slab distance), exceeds best t. The slack keeps a primitive whose COMPUTED t
-  // rounds to just before its own box's computed entry (the reference never culls by t). `tkey` is that cull key.
-  static inline bool box_hit(const float* mn, const float* mx, const Ray& ray, Float best_t, Float& tkey) {
-    const Float k = 1.0f + 2.0f * gamma(3);
-    const Float slack = 32.0f * F32_EPS;
-    Float t1 = (mn[0] - ray.origin.x) * ray.d_inverse.x;
-    Float t2 = (mx[0] - ray.origin.x) * ray.d_inverse.x;
-    Float lo = fmin_(t1, t2), hi = fmax_(t1, t2);
-    Float tmin = lo;
-    Float tmax = hi * k;
-    const Float m_x = fmax_(hi, -lo);
-    t1 = (mn[1] - ray.origin.y) * ray.d_inverse.y;
-    t2 = (mx[1] - ray.origin.y) * ray.d_inverse.y;
-    lo = fmin_(t1, t2); hi = fmax_(t1, t2);
-    tmin = fmax_(tmin, lo);
-    tmax = fmin_(tmax, hi * k);
-    const Float m_y = fmax_(hi, -lo);
-    t1 = (mn[2] - ray.origin.z) * ray.d_inverse.z;
-    t2 = (mx[2] - ray.origin.z) * ray.d_inverse.z;
-    lo = fmin_(t1, t2); hi = fmax_(t1, t2);
-    tmin = fmax_(tmin, lo);
-    tmax = fmin_(tmax, hi * k);
-    const Float m_z = fmax_(hi, -lo);
-    Float m = fmax_(m_x, fmax_(m_y, m_z));
-    if (!(m < 3.0e38f)) m = fmax_(m_x < 3.0e38f ? m_x : 0.0f, fmax_(m_y < 3.0e38f ? m_y : 0.0f, m_z < 3.0e38f ? m_z : 0.0f));
-    tkey = tmin - slack * m;
-    return tmax > fmax_(tmin, 0.0f) && tkey <= best_t;
+  // The device's slab test (ptb_intersect.cuh box_entry), restated operation for operation: aabb.rs:22-57 with one fma
+  // per plane (plane * dinv - o * dinv, the product hoisted per ray), near / far plane chosen by the direction's sign,
+  // near distances moved down / far distances moved up by e_i = 2 eps |o_i dinv_i|, far side widened by 1 + 4 gamma(3).
+  // The box is culled only when its entry distance less 32 eps max(|entry|, |exit|) exceeds best t; `tkey` is that key.
+  struct SlabRay {
+    Vec3 dinv, c_lo, c_hi;
+  };
+  static SlabRay make_slab_ray(const Ray& ray) {
+    SlabRay r;
+    const Float H = 1.0e30f;  // clamp: plane * inf - o * inf would be NaN (see ptb_intersect.cuh)
+    r.dinv = Vec3(fmax_(fmin_(ray.d_inverse.x, H), -H), fmax_(fmin_(ray.d_inverse.y, H), -H), fmax_(fmin_(ray.d_inverse.z, H), -H));
+    const Vec3 od = ray.origin * r.dinv;
+    const Vec3 e = (2.0f * F32_EPS) * od.abs();
+    r.c_lo = -od - e;
+    r.c_hi = e - od;
+    return r;
+  }
+  static inline bool box_hit(const float* mn, const float* mx, const SlabRay& r, Float best_t, Float& tkey) {
+    const Float k = 1.0f + 4.0f * gamma(3);
+    const bool sx = r.dinv.x < 0.0f, sy = r.dinv.y < 0.0f, sz = r.dinv.z < 0.0f;
+    const Float lox = std::fmaf(sx ? mx[0] : mn[0], r.dinv.x, r.c_lo.x), hix = std::fmaf(sx ? mn[0] : mx[0], r.dinv.x, r.c_hi.x);
+    const Float loy = std::fmaf(sy ? mx[1] : mn[1], r.dinv.y, r.c_lo.y), hiy = std::fmaf(sy ? mn[1] : mx[1], r.dinv.y, r.c_hi.y);
+    const Float loz = std::fmaf(sz ? mx[2] : mn[2], r.dinv.z, r.c_lo.z), hiz = std::fmaf(sz ? mn[2] : mx[2], r.dinv.z, r.c_hi.z);
+    const Float tmin = fmax_(fmax_(lox, loy), loz);
+    const Float hmin = fmin_(fmin_(hix, hiy), hiz);
+    tkey = std::fmaf(-(32.0f * F32_EPS), fmax_(std::fabs(tmin), std::fabs(hmin)), tmin);
+    return hmin * k > fmax_(tmin, 0.0f) && tkey <= best_t;
   }
 
   // Ordered (near child first), t-culled closest hit. Ties on t go to the lower ORIGINAL primitive id.
@@ -181,6 +179,7 @@ struct Lbvh {
     best_prim = PTB_MISS;
     if (nodes.empty()) return false;
     Float best_t = INF_F;
+    const SlabRay slab = make_slab_ray(ray);
     uint32_t stack[128];
     Float stack_t[128];  // entry distance of the deferred child: re-checked against best_t when popped
     int sp = 0;
@@ -207,8 +206,8 @@ struct Lbvh {
       const ptb_bvh_node& nd = nodes[cur];
       if (nodes_fetched) ++*nodes_fetched;
       Float tl, tr;
-      bool hl = box_hit(nd.lmin, nd.lmax, ray, best_t, tl);
-      bool hr = box_hit(nd.rmin, nd.rmax, ray, best_t, tr);
+      bool hl = box_hit(nd.lmin, nd.lmax, slab, best_t, tl);
+      bool hr = box_hit(nd.rmin, nd.rmax, slab, best_t, tr);
       if (hl && hr) {
         uint32_t nearc = nd.left, farc = nd.right;
         Float tfar = tr;

@@ -238,6 +238,19 @@ void orc_lbvh_export(const orc_scene* s, uint32_t* morton, uint32_t* prim_sorted
   if (nodes) for (size_t i = 0; i < l.nodes.size(); ++i) nodes[i] = l.nodes[i];
 }
 // counts2: nodes fetched, primitives tested (summed over the batch)
+// nodes fetched by the ordered LBVH traversal, per ray (finds rays whose traversal is pathologically long)
+void orc_lbvh_node_counts(const orc_scene* s, const ptb_ray* rays, size_t n, uint32_t* nodes_out, int threads) {
+  parallel_for(n, threads, [&](unsigned, size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      Ray ray(Vec3(rays[i].ox, rays[i].oy, rays[i].oz), Vec3(rays[i].dx, rays[i].dy, rays[i].dz), 0.0f);
+      Hit h;
+      uint32_t prim;
+      uint64_t nv = 0, pt = 0;
+      s->lbvh.closest_hit(ray, h, prim, &nv, &pt);
+      nodes_out[i] = (uint32_t)nv;
+    }
+  });
+}
 void orc_lbvh_closest_hit(const orc_scene* s, const ptb_ray* rays, size_t n, ptb_hit* out, int threads, uint64_t* counts2) {
   unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
   std::vector<uint64_t> nv(nt ? nt : 1, 0), pt(nt ? nt : 1, 0);
@@ -269,6 +282,7 @@ void orc_sah_ordered_closest_hit(const orc_scene* s, const ptb_ray* rays, size_t
       Hit best, h;
       Float best_t = INF_F;
       uint32_t bp = PTB_MISS;
+      const Lbvh::SlabRay slab = Lbvh::make_slab_ray(ray);
       size_t stack[256];
       Float stack_t[256];
       int sp = 0;
@@ -289,7 +303,7 @@ void orc_sah_ordered_closest_hit(const orc_scene* s, const ptb_ray* rays, size_t
           float lmn[3] = {l.bounds.min.x, l.bounds.min.y, l.bounds.min.z}, lmx[3] = {l.bounds.max.x, l.bounds.max.y, l.bounds.max.z};
           float rmn[3] = {r.bounds.min.x, r.bounds.min.y, r.bounds.min.z}, rmx[3] = {r.bounds.max.x, r.bounds.max.y, r.bounds.max.z};
           Float tl, tr;
-          bool hl = Lbvh::box_hit(lmn, lmx, ray, best_t, tl), hr = Lbvh::box_hit(rmn, rmx, ray, best_t, tr);
+          bool hl = Lbvh::box_hit(lmn, lmx, slab, best_t, tl), hr = Lbvh::box_hit(rmn, rmx, slab, best_t, tr);
           if (hl && hr) {
             size_t nearc = nd.children[0], farc = nd.children[1];
             Float tf = tr;

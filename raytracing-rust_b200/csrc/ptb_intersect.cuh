@@ -151,15 +151,64 @@ PTB_DEV bool prim_hit(const DevScene& sc, const Ray& ray, uint32_t ref, HitRec& 
 }
 
 // ---- box -----------------------------------------------------------------------------------------------------------------
-// Accepts the box when the reference's does_int would (far side widened by 1+2*gamma(3), entry < exit, exit > 0) AND
-// its entry distance cannot exclude a hit closer than best_t. `tkey` = entry distance minus an error slack: a
-// primitive's COMPUTED t may fall slightly before its box's computed entry (e.g. the radius-1000 ground spheres of the
-// shipped scenes: |t error| ~ 1e-5), and the reference never culls by t, so culling must not either in that band.
-// The slack is kCullSlack * (largest finite slab distance of this box), which bounds the magnitude of the terms the
-// sphere quadratic / watertight triangle test (its own bound is delta_t, triangle.rs:160-177) round off.
+// Slab test for ordered, t-culled traversal; replaces AABB::does_int (implementations/src/acceleration/aabb.rs:22-57).
+// The reference evaluates (plane - o) * d_inverse per plane, widens the far side by 1 + 2*gamma(3) and accepts when
+// tmax > max(tmin, 0); it never culls by t. Here each plane distance is ONE fma, plane * dinv - o * dinv, with the
+// product o * dinv hoisted per ray, and the near / far plane of each axis is picked by the sign of the direction. The
+// hoisted product is rounded once, so a distance can be off by eps/2 * |o_i * dinv_i| beyond the reference's own two
+// roundings; the test stays a superset of the reference's by (a) moving the near distances down / the far distances up
+// by e_i = 2 * eps * |o_i * dinv_i| (folded into the fma addends, free) and (b) widening the far side by
+// 1 + 4 * gamma(3). `tkey` = entry distance minus the cull slack: a primitive's COMPUTED t may fall slightly before its
+// box's computed entry (radius-1000 ground spheres of the shipped scenes: |t error| ~ 1e-5, i.e. relative to the
+// sphere's size, not to t), so a box is culled only when tkey > best_t. The slack is kCullSlack * max(|entry|, |exit|)
+// of this box: the exit distance of a box the ray hits a primitive in is at least of the primitive's own scale.
+// (A per-ray slack from the scene extent is cheaper but wrong-sized: grazing rays, |dinv| ~ 1e4, then walk unculled.)
+// |dinv| is clamped to 1e30: plane * inf - o * inf would be NaN, which fminf / fmaxf ignore, and a ray whose slab is
+// ignored walks a whole slice of the tree (camera rays with an exactly-zero x component are not rare: the f32 camera
+// arithmetic cancels to 0 within an ulp of the image centre column — measured: 6761 nodes for one such ray, 7 ms for the
+// lane). With the clamp an axis-parallel ray is inside the slab iff near <= o <= far up to e_i, like the reference.
 constexpr float kCullSlack = 32.0f * kF32Eps;
-PTB_DEV bool box_entry(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Ray& ray, float best_t,
-                       float& tkey) {
+constexpr float kSlabErr = 2.0f * kF32Eps;
+constexpr float kDinvMax = 1.0e30f;
+struct SlabRay {
+  v3 dinv;  // 1 / d
+  v3 c_lo;  // -(o * dinv) - e   addend of the near planes
+  v3 c_hi;  // -(o * dinv) + e   addend of the far planes
+};
+PTB_HD SlabRay make_slab_ray(const Ray& ray) {
+  SlabRay r;
+  r.dinv = mk(fmaxf(fminf(ray.dinv.x, kDinvMax), -kDinvMax), fmaxf(fminf(ray.dinv.y, kDinvMax), -kDinvMax),
+              fmaxf(fminf(ray.dinv.z, kDinvMax), -kDinvMax));
+  const v3 od = ray.o * r.dinv;
+  const v3 e = kSlabErr * vabs(od);
+  r.c_lo = -od - e;
+  r.c_hi = e - od;
+  return r;
+}
+PTB_HD float fma_rn(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
+PTB_HD bool box_entry(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const SlabRay& r, float best_t,
+                      float& tkey) {
+  const float k = 1.0f + 4.0f * gamma_n(3);
+  const bool sx = r.dinv.x < 0.0f, sy = r.dinv.y < 0.0f, sz = r.dinv.z < 0.0f;
+  const float lox = fma_rn(sx ? mxx : mnx, r.dinv.x, r.c_lo.x), hix = fma_rn(sx ? mnx : mxx, r.dinv.x, r.c_hi.x);
+  const float loy = fma_rn(sy ? mxy : mny, r.dinv.y, r.c_lo.y), hiy = fma_rn(sy ? mny : mxy, r.dinv.y, r.c_hi.y);
+  const float loz = fma_rn(sz ? mxz : mnz, r.dinv.z, r.c_lo.z), hiz = fma_rn(sz ? mnz : mxz, r.dinv.z, r.c_hi.z);
+  // 3-input min/max (FMNMX3 on sm_100a)
+  const float tmin = fmaxf(fmaxf(lox, loy), loz);
+  const float hmin = fminf(fminf(hix, hiy), hiz);
+  tkey = fma_rn(-kCullSlack, fmaxf(fabsf(tmin), fabsf(hmin)), tmin);
+  return hmin * k > fmaxf(tmin, 0.0f) && tkey <= best_t;
+}
+
+#ifdef PTB_BOX_V1  // experiment: the previous sub+mul slab test with the per-box slack
+PTB_DEV bool box_entry_v1(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Ray& ray, float best_t,
+                          float& tkey) {
   const float k = 1.0f + 2.0f * gamma_n(3);
   const float ax = (mnx - ray.o.x) * ray.dinv.x, bx = (mxx - ray.o.x) * ray.dinv.x;
   const float ay = (mny - ray.o.y) * ray.dinv.y, by = (mxy - ray.o.y) * ray.dinv.y;
@@ -167,17 +216,17 @@ PTB_DEV bool box_entry(float mnx, float mny, float mnz, float mxx, float mxy, fl
   const float lox = fminf(ax, bx), hix = fmaxf(ax, bx);
   const float loy = fminf(ay, by), hiy = fmaxf(ay, by);
   const float loz = fminf(az, bz), hiz = fmaxf(az, bz);
-  // 3-input min/max (FMNMX3 on sm_100a). min(hi*k) == min(hi)*k: rounding is monotone, so k is applied once.
   const float tmin = fmaxf(fmaxf(lox, loy), loz);
   const float hmin = fminf(fminf(hix, hiy), hiz);
   const float tmax = hmin * k;
   float m = fmaxf(fmaxf(fmaxf(hix, hiy), hiz), -fminf(fminf(lox, loy), loz));
-  if (!(m < 3.0e38f)) {  // axis-parallel ray: ignore the slabs it never crosses
+  if (!(m < 3.0e38f)) {
     const float mx = fmaxf(hix, -lox), my = fmaxf(hiy, -loy), mz = fmaxf(hiz, -loz);
     m = fmaxf(mx < 3.0e38f ? mx : 0.0f, fmaxf(my < 3.0e38f ? my : 0.0f, mz < 3.0e38f ? mz : 0.0f));
   }
   tkey = tmin - kCullSlack * m;
   return tmax > fmaxf(tmin, 0.0f) && tkey <= best_t;
 }
+#endif
 
 }  // namespace ptb

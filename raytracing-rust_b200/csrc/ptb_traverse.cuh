@@ -94,14 +94,19 @@ PTB_DEV void trav_pop(TravState& s, const uint2* stack, uint2* lq) {
 // One internal-node step of the lane: fetch the 64-byte node, test both child boxes, descend into the nearer hit child
 // (deferring the other on the stack); a leaf child is queued and the walk continues from the stack.
 template <bool COUNT>
-PTB_DEV void trav_node_step(const DevScene& sc, const Ray& ray, TravState& s, uint2* stack, uint2* lq, uint32_t& n_nodes) {
+PTB_DEV void trav_node_step(const DevScene& sc, const SlabRay& ray, const Ray& full, TravState& s, uint2* stack, uint2* lq, uint32_t& n_nodes) {
   float4 n0, n1, n2;
   uint4 n3;
   load_node(sc.nodes, s.cur, n0, n1, n2, n3);
   if (COUNT) ++n_nodes;
   float tl, tr;
+#ifdef PTB_BOX_V1
+  const bool hl = box_entry_v1(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, full, s.best_t, tl);
+  const bool hr = box_entry_v1(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, full, s.best_t, tr);
+#else
   const bool hl = box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ray, s.best_t, tl);
   const bool hr = box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ray, s.best_t, tr);
+#endif
   bool want_pop = !(hl || hr);
   if (!want_pop) {
     const bool both = hl && hr;
@@ -191,15 +196,24 @@ PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fe
   Ray ray;
   ray.o = ray.d = ray.dinv = ray.shear = mk(0.0f, 0.0f, 0.0f);
   ray.swap_xz = false;
+  SlabRay slab;
+  slab.dinv = slab.c_lo = slab.c_hi = mk(0.0f, 0.0f, 0.0f);
   uint32_t exclude = kNone;
   bool has_ray = false, exhausted = false;
+  // Small launches (the tail of a render: a few thousand long paths) are latency bound: 32 rays in one warp run their
+  // phases one after the other while most SMs idle. Cap the rays a warp holds so the launch spreads over every
+  // resident warp; large launches keep all 32 lanes.
+  const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+  uint32_t cap = (n + total_warps - 1u) / total_warps;
+  cap = cap < 1u ? 1u : (cap > 32u ? 32u : cap);
+  const uint32_t fetch_below = (uint32_t)sc.trace_fetch_threshold < cap ? (uint32_t)sc.trace_fetch_threshold : cap;
   for (;;) {
     // a lane with work is parked on an internal node, holds queued leaves, or both
     bool node_ready = has_ray && !(st.cur & PTB_LEAF_BIT);
     const bool leaf_ready = has_ray && st.lq_count != 0u;
     const uint32_t m_node = __ballot_sync(0xffffffffu, node_ready);
     const uint32_t m_leaf = __ballot_sync(0xffffffffu, leaf_ready);
-    if ((uint32_t)__popc(m_node | m_leaf) < (exhausted ? 1u : (uint32_t)sc.trace_fetch_threshold)) {
+    if ((uint32_t)__popc(m_node | m_leaf) < (exhausted ? 1u : fetch_below)) {
       // ---- service: retire finished items, refill idle lanes
       const bool fin = has_ray && !node_ready && !leaf_ready;
       retire(fin, st, ray);
@@ -208,16 +222,23 @@ PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fe
         if (!__any_sync(0xffffffffu, has_ray)) break;
         continue;
       }
-      const uint32_t idle = __ballot_sync(0xffffffffu, !has_ray);
+      uint32_t idle = __ballot_sync(0xffffffffu, !has_ray);
+      if (cap < 32u) {  // keep only as many idle lanes as the cap allows (lowest lanes first)
+        const uint32_t busy = 32u - (uint32_t)__popc(idle);
+        const uint32_t allow = busy < cap ? cap - busy : 0u;
+        const uint32_t cut = __fns(idle, 0u, (int)allow + 1);  // position of the (allow+1)-th idle lane, or ~0u
+        if (cut != 0xffffffffu) idle &= (1u << cut) - 1u;
+      }
       if (idle) {
         const uint32_t leader = __ffs(idle) - 1u, want = __popc(idle);
         uint32_t base = 0;
         if (lane == leader) base = atomicAdd(head, want);
         base = __shfl_sync(0xffffffffu, base, leader);
         const uint32_t mine = base + __popc(idle & ((1u << lane) - 1u));
-        if (!has_ray && mine < n) {
+        if (((idle >> lane) & 1u) && mine < n) {
           float tmax = __int_as_float(0x7f800000);
           fetch(mine, ray, tmax, exclude);
+          slab = make_slab_ray(ray);
           trav_init(st, sc.n_prims, tmax);
           has_ray = true;
           if (COUNT) ++cnt_rays;
@@ -233,7 +254,7 @@ PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fe
     if (do_node) {
 #pragma unroll 1
       for (int burst = 0; burst < sc.trace_burst && node_ready; ++burst) {
-        trav_node_step<COUNT>(sc, ray, st, stack, lq, cnt_nodes);
+        trav_node_step<COUNT>(sc, slab, ray, st, stack, lq, cnt_nodes);
         node_ready = !(st.cur & PTB_LEAF_BIT);
       }
     } else if (leaf_ready) {

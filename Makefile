@@ -6,7 +6,7 @@ NVCC     ?= nvcc
 # -fmad=false: the reference (rustc) never contracts a*b+c; hit/miss decisions must match the oracle bit for bit.
 NVFLAGS  ?= -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
             -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unused-parameter -Xptxas -v
-CU_SRCS  := $(PKG)/csrc/context.cu $(PKG)/csrc/lbvh_build.cu $(PKG)/csrc/wavefront.cu
+CU_SRCS  := $(PKG)/csrc/context.cu $(PKG)/csrc/lbvh_build.cu $(PKG)/csrc/wavefront.cu $(PKG)/csrc/multi.cu
 CPP_SRCS := $(PKG)/host/ssml_loader.cpp $(PKG)/host/image_out.cpp $(PKG)/host/image_in.cpp
 HDRS     := include/ptb200.h $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h)
 OBJS     := $(CU_SRCS:.cu=.o) $(CPP_SRCS:.cpp=.o)
@@ -19,7 +19,7 @@ $(PKG)/host/%.o: $(PKG)/host/%.cpp include/ptb200.h
 	$(CXX) -O2 -std=c++17 -fPIC -Wall -Wextra -fno-fast-math -ffp-contract=off -c $< -o $@
 
 $(PKG)/libptb200.so: $(OBJS)
-	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(OBJS) -cudart static
+	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(OBJS) -cudart static -ldl
 
 cli: $(PKG)/ptb200-cli
 $(PKG)/ptb200-cli: $(PKG)/host/cli_main.cpp $(PKG)/libptb200.so include/ptb200.h

@@ -232,6 +232,16 @@ int32_t ptb_closest_hit_device(ptb_ctx* ctx, const void* d_rays, size_t n, void*
 /* Replaces Sampler::sample_image (samplers/mod.rs:7-20, random_sampler.rs:10-99) + the running mean of
  * src/main.rs:175-191: adds opts->samples_per_pixel samples per pixel into the device accumulator (sums). */
 int32_t ptb_render(ptb_ctx* ctx, const ptb_render_opts* opts, ptb_progress_fn progress, void* user);
+/* The reference's per-pass presentation contract (random_sampler.rs:31-98, SamplerProgress samplers/mod.rs:49-63): one
+ * pass = one sample of every pixel. `update` receives the SINGLE-SAMPLE image of a finished pass (row-major, top row
+ * first, RGB f32, n_floats = width*height*3; valid only during the call), the 1-based number of that pass and the
+ * pass's rays_shot (the reference's own ray counter). As in the reference the image of pass k is handed over after pass
+ * k+1 has been rendered, and the last one after the loop; a non-zero return stops the render (PTB_ERR_ABORTED; the
+ * reference returns without the final call). Every pass is also added to the device accumulator, so ptb_accum_read
+ * afterwards yields the running mean the TUI closure of src/main.rs:175-191 computes. Pass k uses absolute sample index
+ * opts->sample_offset + k: the sum of the passes equals one ptb_render call of the same options. */
+typedef int32_t (*ptb_pass_fn)(void* user, const float* pass_image, size_t n_floats, uint64_t pass_number, uint64_t rays_shot);
+int32_t ptb_render_passes(ptb_ctx* ctx, const ptb_render_opts* opts, ptb_pass_fn update, void* user);
 int32_t ptb_accum_clear(ptb_ctx* ctx);
 /* Reads back width*height*3 floats, row-major, top row first, RGB (the layout of
  * SamplerProgress.current_image, samplers/mod.rs:49-63). normalise != 0 divides by the samples accumulated. */
@@ -240,6 +250,17 @@ int32_t ptb_accum_read(ptb_ctx* ctx, float* rgb, size_t n_floats, int32_t normal
 int32_t ptb_accum_device_ptr(ptb_ctx* ctx, void** d_ptr, size_t* n_floats);
 /* After an external reduce wrote sums of `total_samples` samples into the accumulator. */
 int32_t ptb_accum_set_samples(ptb_ctx* ctx, uint64_t total_samples);
+
+/* ------------------------------------------------------------ multi-GPU -- */
+/* The path shards by samples (independent), scene and BVH replicated per GPU: rank r of `world` renders the absolute
+ * samples [first, first + count) of every pixel. */
+void    ptb_shard_samples(uint32_t samples_per_pixel, uint32_t sample_offset, int32_t rank, int32_t world,
+                          uint32_t* first, uint32_t* count);
+/* Scene::render across n GPUs of one box: ctxs[r] (one per GPU, scene already committed on each) renders its share on its
+ * own host thread, then ONE ncclReduce(sum) of the accumulators (width*height*3 f32) to ctxs[0] — the path's only
+ * collective. Afterwards ptb_accum_read(ctxs[0], ..) returns the image of all opts->samples_per_pixel samples. NCCL is
+ * bound at run time (libnccl.so.2, or $PTB_NCCL_LIB); n == 1 never touches it. */
+int32_t ptb_render_multi(ptb_ctx* const* ctxs, int32_t n, const ptb_render_opts* opts);
 
 int32_t ptb_stats_get(ptb_ctx* ctx, ptb_stats* out);
 int32_t ptb_stats_reset(ptb_ctx* ctx);

@@ -69,6 +69,7 @@ class Vec3(C.Structure):
 
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64)
+PASS_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.c_size_t, C.c_uint64, C.c_uint64)
 
 # every symbol include/ptb200.h declares: (name, restype, argtypes)
 _P = C.c_void_p
@@ -94,10 +95,13 @@ SYMBOLS = [
     ("ptb_closest_hit", C.c_int32, [_P, _P, C.c_size_t, _P]),
     ("ptb_closest_hit_device", C.c_int32, [_P, _P, C.c_size_t, _P]),
     ("ptb_render", C.c_int32, [_P, C.POINTER(RenderOpts), _P, _P]),
+    ("ptb_render_passes", C.c_int32, [_P, C.POINTER(RenderOpts), _P, _P]),
     ("ptb_accum_clear", C.c_int32, [_P]),
     ("ptb_accum_read", C.c_int32, [_P, _P, C.c_size_t, C.c_int32]),
     ("ptb_accum_device_ptr", C.c_int32, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     ("ptb_accum_set_samples", C.c_int32, [_P, C.c_uint64]),
+    ("ptb_shard_samples", None, [C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("ptb_render_multi", C.c_int32, [_P, C.c_int32, C.POINTER(RenderOpts)]),
     ("ptb_stats_get", C.c_int32, [_P, C.POINTER(Stats)]),
     ("ptb_stats_reset", C.c_int32, [_P]),
     ("ptb_ssml_load_file", C.c_int32, [C.c_char_p, C.POINTER(_P)]),

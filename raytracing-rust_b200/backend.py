@@ -132,6 +132,19 @@ class Context:
         self._progress_ref = None
         _check(self._h, rc)
 
+    def render_passes(self, opts: RenderOptions, update):
+        """The reference's per-pass contract (random_sampler.rs:31-98): `update(pass_image (H, W, 3), pass_number,
+        rays_shot) -> bool` once per pass with that pass's single-sample image; True stops the render."""
+        h, w = opts.height, opts.width
+
+        def thunk(user, img, n, i, rays):
+            a = np.ctypeslib.as_array(img, shape=(n,)).reshape(h, w, 3)
+            return 1 if update(a, int(i), int(rays)) else 0
+
+        cb = L.PASS_FN(thunk)
+        o = opts.to_c()
+        _check(self._h, L.lib.ptb_render_passes(self._h, C.byref(o), C.cast(cb, C.c_void_p), None))
+
     def accum_clear(self):
         _check(self._h, L.lib.ptb_accum_clear(self._h))
 
@@ -179,8 +192,13 @@ class Bvh:
 class RandomSampler:
     """RandomSampler::sample_image on the device: `spp` samples of every pixel into the accumulator."""
 
-    def sample_image(self, opts: RenderOptions, bvh: Bvh, update=None):
-        bvh.ctx.render(opts, progress=update)
+    def sample_image(self, opts: RenderOptions, bvh: Bvh, update=None, presentation_update=None):
+        """`presentation_update(pass_image, i, rays_shot) -> bool`: the reference's per-pass closure; `update(samples,
+        rays) -> bool`: counters only (one device accumulator, no per-pass read-back)."""
+        if presentation_update is not None:
+            bvh.ctx.render_passes(opts, presentation_update)
+        else:
+            bvh.ctx.render(opts, progress=update)
 
 
 class Scene:
@@ -191,11 +209,21 @@ class Scene:
         self.host = host_scene
         self.acceleration = Bvh(self.ctx, host_scene)
 
-    def render(self, opts: RenderOptions, update=None) -> np.ndarray:
+    def render(self, opts: RenderOptions, update=None, presentation_update=None) -> np.ndarray:
         """Returns the running-mean image (H, W, 3) the TUI closure of src/main.rs:175-191 would hold."""
         self.ctx.accum_clear()
-        RandomSampler().sample_image(opts, self.acceleration, update)
+        RandomSampler().sample_image(opts, self.acceleration, update, presentation_update)
         return self.ctx.accum_read(opts.width, opts.height, normalise=True)
+
+
+def render_multi(contexts, opts: RenderOptions) -> np.ndarray:
+    """Scene::render across several GPUs of one box through ptb_render_multi: every context (one per GPU, same scene
+    committed on each) renders its share of the samples on its own host thread inside the library, then one
+    ncclReduce(sum) to contexts[0]. Returns the mean image."""
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    o = opts.to_c()
+    _check(contexts[0]._h, L.lib.ptb_render_multi(C.cast(arr, C.c_void_p), len(contexts), C.byref(o)))
+    return contexts[0].accum_read(opts.width, opts.height, normalise=True)
 
 
 def make_rays(origins: np.ndarray, directions: np.ndarray) -> np.ndarray:

@@ -105,6 +105,8 @@ int32_t ptb_destroy(ptb_ctx* ctx) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->h_counters) cudaFreeHost(c->h_counters);
+  for (float* h : c->h_pass)
+    if (h) cudaFreeHost(h);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
   if (c->ev_iter) cudaEventDestroy(c->ev_iter);
@@ -330,6 +332,60 @@ int32_t ptb_render(ptb_ctx* ctx, const ptb_render_opts* opts, ptb_progress_fn pr
   int32_t rc = ensure_accum(c, opts->width, opts->height);
   if (rc != PTB_OK) return rc;
   return render_wavefront(c, *opts, progress, user);
+}
+
+__global__ void k_add_into(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+int32_t ptb_render_passes(ptb_ctx* ctx, const ptb_render_opts* opts, ptb_pass_fn update, void* user) {
+  CTX_OR_FAIL(ctx);
+  if (!opts) return set_error(c, PTB_ERR_INVALID, "null render opts");
+  if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
+  if (opts->width < 2 || opts->height < 2) return set_error(c, PTB_ERR_INVALID, "width and height must be >= 2");
+  if ((uint64_t)opts->width * opts->height > 0x7FFFFFFFull) return set_error(c, PTB_ERR_INVALID, "image too large");
+  if (opts->method != PTB_METHOD_NAIVE && opts->method != PTB_METHOD_MIS) return set_error(c, PTB_ERR_INVALID, "unknown method");
+  int32_t rc = ensure_accum(c, opts->width, opts->height);
+  if (rc != PTB_OK) return rc;
+  const size_t n = (size_t)opts->width * opts->height * 3;
+  PTB_CUDA_TRY(c, c->d_pass.reserve(n * sizeof(float)));
+  if (c->h_pass_floats < n) {
+    for (float*& h : c->h_pass) {
+      if (h) cudaFreeHost(h);
+      h = nullptr;
+      PTB_CUDA_TRY(c, cudaMallocHost(&h, n * sizeof(float)));
+    }
+    c->h_pass_floats = n;
+  }
+  uint64_t rays[2] = {0, 0};
+  for (uint32_t k = 0; k < opts->samples_per_pixel; ++k) {
+    const int cur = (int)(k & 1u);
+    // random_sampler.rs:31-81: render pass k into the `current` buffer
+    PTB_CUDA_TRY(c, cudaMemsetAsync(c->d_pass.p, 0, n * sizeof(float), c->stream));
+    ptb_render_opts one = *opts;
+    one.samples_per_pixel = 1;
+    one.sample_offset = opts->sample_offset + k;
+    const uint64_t before = c->stats.rays_reference;
+    c->accum_target = c->d_pass.as<float>();
+    rc = render_wavefront(c, one, nullptr, nullptr);
+    c->accum_target = nullptr;
+    if (rc != PTB_OK) return rc;
+    rays[cur] = c->stats.rays_reference - before;
+    k_add_into<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_pass.as<float>(), c->d_accum.as<float>(), n);
+    c->stats.kernel_launches += 1;
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_pass[cur], c->d_pass.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    // random_sampler.rs:82-88: `previous` (pass k-1) goes to the callback with i = k
+    if (k != 0 && update && update(user, c->h_pass[cur ^ 1], n, k, rays[cur ^ 1]))
+      return set_error(c, PTB_ERR_ABORTED, "render stopped by the presentation callback after pass %u", k);
+  }
+  // random_sampler.rs:91-98: the last pass, with i = samples_per_pixel
+  if (opts->samples_per_pixel && update) {
+    const int last = (int)((opts->samples_per_pixel - 1u) & 1u);
+    update(user, c->h_pass[last], n, opts->samples_per_pixel, rays[last]);
+  }
+  return PTB_OK;
 }
 
 int32_t ptb_accum_clear(ptb_ctx* ctx) {

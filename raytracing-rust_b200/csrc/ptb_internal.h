@@ -100,6 +100,10 @@ struct Ctx {
 
   // render state
   DevBuf d_accum;
+  float* accum_target = nullptr;  // ptb_render_passes: render into the single-pass buffer instead of d_accum
+  DevBuf d_pass;
+  float* h_pass[2] = {nullptr, nullptr};  // pinned
+  size_t h_pass_floats = 0;
   uint32_t accum_w = 0, accum_h = 0;
   uint64_t accum_samples = 0;
   DevBuf d_pool_mem, d_queues, d_shadow, d_counters;

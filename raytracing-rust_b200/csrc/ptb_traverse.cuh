@@ -36,12 +36,33 @@ struct TraceResult {
   uint32_t ref;  // kNone on miss, else (kSphereBit?) | slot
 };
 
+// 32 bytes per lane in one instruction (LDG.E.256, new on sm_100): incoherent traversal is bound by L1 wavefronts — one
+// per distinct 128-byte line PER LOAD INSTRUCTION (ncu: l1tex throughput 80 % with four 16-byte loads per node) — so a
+// 64-byte node costs two wavefronts instead of four. `p` must be 32-byte aligned.
+PTB_DEV void ldg256(const void* p, float4& a, float4& b) {
+#ifdef PTB_NO_LDG256
+  a = __ldg(reinterpret_cast<const float4*>(p));
+  b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#else
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p));
+#endif
+}
+PTB_DEV void ldg256_rw(const void* p, float4& a, float4& b) {  // same, for data this launch sequence also writes (no .nc)
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p) : "memory");
+}
+PTB_DEV void stg256(void* p, float4 a, float4 b) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
 PTB_DEV void load_node(const BvhNode* __restrict__ nodes, uint32_t idx, float4& n0, float4& n1, float4& n2, uint4& n3) {
-  const float4* p = reinterpret_cast<const float4*>(nodes + idx);
-  n0 = __ldg(p);
-  n1 = __ldg(p + 1);
-  n2 = __ldg(p + 2);
-  n3 = __ldg(reinterpret_cast<const uint4*>(p + 3));
+  float4 t;
+  ldg256(nodes + idx, n0, n1);
+  ldg256(reinterpret_cast<const float4*>(nodes + idx) + 2, n2, t);
+  n3 = make_uint4(__float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z), __float_as_uint(t.w));
 }
 
 // Per-lane traversal state. `cur`: internal node index, or a PARKED leaf reference (bit 31: the leaf queue was full), or

@@ -241,10 +241,11 @@ k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams 
   // camera.rs:57-63 + Ray::new (ray.rs:13-46)
   const v3 dir = sc.cam_lower_left + sc.cam_horizontal * u + sc.cam_vertical * v - sc.cam_origin;
   const v3 d = dir / mag(dir);
-  pool.ray[4u * (size_t)slot] = make_float4(sc.cam_origin.x, sc.cam_origin.y, sc.cam_origin.z, 0.0f);
-  pool.ray[4u * (size_t)slot + 1u] = make_float4(d.x, d.y, d.z, __uint_as_float(kNone));
-  pool.col[4u * (size_t)slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pixel));
-  pool.col[4u * (size_t)slot + 1u] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(sample << 9));
+  // the 64-byte path block as two 32-byte stores (STG.256, sm_100): half the L1 data-pipe wavefronts of four STG.128
+  stg256(pool.ray + 4u * (size_t)slot, make_float4(sc.cam_origin.x, sc.cam_origin.y, sc.cam_origin.z, 0.0f),
+         make_float4(d.x, d.y, d.z, __uint_as_float(kNone)));
+  stg256(pool.col + 4u * (size_t)slot, make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pixel)),
+         make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(sample << 9)));
   q.active[cur][wc->n_active[cur] + i] = slot;
   }
 }
@@ -258,7 +259,8 @@ struct TraceFetch {
   uint32_t slot;
   PTB_DEV void operator()(uint32_t i, Ray& ray, float& /*tmax*/, uint32_t& /*exclude*/) {
     slot = queue[i];
-    const float4 o = pool.ray[4u * (size_t)slot], d = pool.ray[4u * (size_t)slot + 1u];
+    float4 o, d;
+    ldg256_rw(pool.ray + 4u * (size_t)slot, o, d);
     ray = make_ray(from4(o), from4(d));
   }
 };
@@ -275,8 +277,8 @@ struct TraceRetire {
     uint32_t kind = 0xFFu;
     if (fin) {
       const TraceResult tr = trav_result(st);
-      pool.ray[4u * (size_t)f.slot] = make_float4(ray.o.x, ray.o.y, ray.o.z, tr.t);
-      pool.ray[4u * (size_t)f.slot + 1u] = make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(tr.ref));
+      stg256(pool.ray + 4u * (size_t)f.slot, make_float4(ray.o.x, ray.o.y, ray.o.z, tr.t),
+             make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(tr.ref)));
       kind = tr.ref == kNone ? 0u : 1u + (__ldg(sc.slot_mat + (tr.ref & kSlotMask)) >> 24);
     }
     if (!__any_sync(0xffffffffu, fin)) return;
@@ -479,8 +481,9 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
 
   if (active) {
     slot = q.kind[kq][off];
-    const float4 ro = pool.ray[4u * (size_t)slot], rd = pool.ray[4u * (size_t)slot + 1u];
-    const float4 th = pool.col[4u * (size_t)slot], ra = pool.col[4u * (size_t)slot + 1u];
+    float4 ro, rd, th, ra;
+    ldg256_rw(pool.ray + 4u * (size_t)slot, ro, rd);
+    ldg256_rw(pool.col + 4u * (size_t)slot, th, ra);
     const uint2 ht = make_uint2(__float_as_uint(ro.w), __float_as_uint(rd.w));
     const uint32_t pixel = __float_as_uint(th.w);
     const uint32_t df = __float_as_uint(ra.w);
@@ -707,11 +710,10 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
         alive = true;
       }
       if (alive) {
-        pool.ray[4u * (size_t)slot] = make_float4(new_o.x, new_o.y, new_o.z, 0.0f);
-        pool.ray[4u * (size_t)slot + 1u] = make_float4(nd.x, nd.y, nd.z, __uint_as_float(kNone));
-        pool.col[4u * (size_t)slot] = make_float4(T.x, T.y, T.z, th.w);
-        pool.col[4u * (size_t)slot + 1u] =
-            make_float4(L.x, L.y, L.z, __uint_as_float((sample << 9) | (delta ? kFlagPrevDelta : 0u) | depth));
+        stg256(pool.ray + 4u * (size_t)slot, make_float4(new_o.x, new_o.y, new_o.z, 0.0f),
+               make_float4(nd.x, nd.y, nd.z, __uint_as_float(kNone)));
+        stg256(pool.col + 4u * (size_t)slot, make_float4(T.x, T.y, T.z, th.w),
+               make_float4(L.x, L.y, L.z, __uint_as_float((sample << 9) | (delta ? kFlagPrevDelta : 0u) | depth)));
       }
     }
     if (finished) finish_path(accum, pixel, L, nan_check);
@@ -950,7 +952,7 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   rp.rr_threshold = o.rr_threshold == PTB_RR_DEFAULT ? 3u : o.rr_threshold;
   rp.k0 = (uint32_t)o.seed; rp.k1 = (uint32_t)(o.seed >> 32);
 
-  float* accum = c->d_accum.as<float>();
+  float* accum = c->accum_target ? c->accum_target : c->d_accum.as<float>();
   const int T = 256;
   const bool mis = o.method == PTB_METHOD_MIS;
   const uint32_t grid_p = (P + T - 1) / T;

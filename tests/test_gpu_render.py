@@ -155,3 +155,49 @@ def test_errors(ptb, gpu_ctx, rtweekend1):
     with pytest.raises(ptb.PtbError):
         c.render(ptb.RenderOptions(width=1, height=16, samples_per_pixel=1))    # W-1 == 0 divides by zero in the reference
     c.close()
+
+
+def test_per_pass_presentation_callback(ptb, gpu_ctx, rtweekend1):
+    """SURVEY.md §8(f) N4 — random_sampler.rs:82-98: the closure sees the single-sample image of every pass exactly once,
+    numbered 1..spp, and the TUI's running mean of those images (src/main.rs:179-185) equals the accumulator."""
+    sc = ptb.Scene(rtweekend1, ctx=gpu_ctx)
+    o = ptb.RenderOptions(samples_per_pixel=6, render_method=1, width=96, height=54, seed=8)
+    one_call = sc.render(o)
+    seen, mean = [], np.zeros((54, 96, 3), np.float64)
+
+    def closure(img, i, rays):
+        nonlocal mean
+        seen.append((i, rays))
+        mean += (img.astype(np.float64) - mean) / i          # `*pres += (acc - *pres) / i`
+        return False
+
+    passes = sc.render(o, presentation_update=closure)
+    assert [i for i, _ in seen] == [1, 2, 3, 4, 5, 6] and all(r > 0 for _, r in seen)
+    assert np.max(np.abs(passes - one_call)) < 1e-5          # same absolute sample indices -> same image
+    assert np.max(np.abs(mean - passes)) < 1e-5
+    # returning true stops the render like the reference's `return` (random_sampler.rs:84-86)
+    calls = []
+    with pytest.raises(ptb.PtbError) as e:
+        sc.render(o, presentation_update=lambda img, i, r: calls.append(i) or i == 2)
+    assert e.value.code == 7 and calls == [1, 2]
+
+
+def test_render_multi_c_abi(ptb, gpu_ctx, rtweekend1):
+    """ptb_render_multi — one context per GPU, spp split inside the library, one ncclReduce to ctxs[0].
+    With a single GPU it must equal Scene.render; with two or more the union of the shards is the same sample set."""
+    import ctypes as C
+    o = ptb.RenderOptions(samples_per_pixel=10, render_method=1, width=128, height=72, seed=6)
+    sc = ptb.Scene(rtweekend1, ctx=gpu_ctx)
+    want = sc.render(o)
+    assert np.max(np.abs(ptb.render_multi([gpu_ctx], o) - want)) < 1e-6
+    n = C.c_int32()
+    ptb._lib.lib.ptb_device_count(C.byref(n))
+    if n.value >= 2:
+        ctxs = [ptb.Context(d) for d in range(min(n.value, 4))]
+        for c in ctxs:
+            c.upload(rtweekend1)
+            c.commit()
+        got = ptb.render_multi(ctxs, o)
+        assert np.max(np.abs(got - want)) < 1e-5
+        for c in ctxs:
+            c.close()

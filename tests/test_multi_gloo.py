@@ -49,3 +49,14 @@ def test_shard_samples_tiles_the_range(ptb):
             for (a, n), (b, _) in zip(parts, parts[1:]):
                 assert a + n == b
             assert max(n for _, n in parts) - min(n for _, n in parts) <= 1
+
+
+def test_c_abi_shard_helper_matches(ptb):
+    """ptb_shard_samples (what ptb_render_multi uses inside the library) == the Python helper the torchrun path uses."""
+    import ctypes as C
+    for total in (0, 1, 7, 256, 4096):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                a, b = C.c_uint32(), C.c_uint32()
+                ptb._lib.lib.ptb_shard_samples(total, 11, r, world, C.byref(a), C.byref(b))
+                assert (a.value - 11, b.value) == ptb.shard_samples(total, r, world)

@@ -444,14 +444,21 @@ def run_ours_closest_hit(args, rank, world, local):
     b_ray = 32.0 + 16.0 + V * 64.0 + T * 48.0
     achieved = batch * K * b_ray / (ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
-    # e2e: host rays in, host hits out
+    # e2e: ptb_closest_hit with PINNED host rays in, pinned host hits out (upload | traverse | read-back pipelined inside)
     h_rays = ptb200.meshgen.philox_rays(batch, first=0)
-    t0 = time.perf_counter()
+    pin_r = torch.empty(batch * 32, dtype=torch.uint8, pin_memory=True)
+    pin_h = torch.empty(batch * 16, dtype=torch.uint8, pin_memory=True)
+    p_rays = np.frombuffer(pin_r.numpy().data, dtype=h_rays.dtype, count=batch)
+    p_rays[...] = h_rays
+    p_hits = np.frombuffer(pin_h.numpy().data, dtype=ptb200.hit_dtype, count=batch)
+    ctx.closest_hit(p_rays, out=p_hits)  # warm: staging buffers, copy streams
     k2 = max(1, min(K, 4))
+    t0 = time.perf_counter()
     for _ in range(k2):
-        ctx.closest_hit(h_rays)
+        ctx.closest_hit(p_rays, out=p_hits)
     dt = time.perf_counter() - t0
-    e2e = {"value": batch * k2 * world / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": batch * 32, "d2h_bytes_per_step": batch * 16}
+    e2e = {"value": batch * k2 * world / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": batch * 32, "d2h_bytes_per_step": batch * 16,
+           "host_buffers": "pinned"}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -111,10 +111,12 @@ class Context:
         return morton, prims, nodes
 
     # ---- closest hit
-    def closest_hit(self, rays: np.ndarray) -> np.ndarray:
-        """AccelerationStructure::check_hit for a batch (host buffers in, host buffers out)."""
+    def closest_hit(self, rays: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """AccelerationStructure::check_hit for a batch (host buffers in, host buffers out). `out`: optional caller-owned
+        hit buffer (e.g. pinned memory: the library overlaps upload, traversal and read-back of 4 Mi-ray batches)."""
         rays = np.ascontiguousarray(rays, dtype=L.ray_dtype)
-        hits = np.zeros(len(rays), L.hit_dtype)
+        hits = np.zeros(len(rays), L.hit_dtype) if out is None else out
+        assert hits.dtype == L.hit_dtype and len(hits) == len(rays) and hits.flags.c_contiguous
         _check(self._h, L.lib.ptb_closest_hit(self._h, L.ptr(rays), len(rays), L.ptr(hits)))
         return hits
 

@@ -110,6 +110,13 @@ int32_t ptb_destroy(ptb_ctx* ctx) {
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
   if (c->ev_iter) cudaEventDestroy(c->ev_iter);
+  for (int b = 0; b < 2; ++b) {
+    if (c->ev_in[b]) cudaEventDestroy(c->ev_in[b]);
+    if (c->ev_kernel[b]) cudaEventDestroy(c->ev_kernel[b]);
+    if (c->ev_out[b]) cudaEventDestroy(c->ev_out[b]);
+  }
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
   for (cudaEvent_t e : c->ev_prof)
     if (e) cudaEventDestroy(e);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -295,18 +302,49 @@ int32_t ptb_closest_hit(ptb_ctx* ctx, const ptb_ray* rays, size_t n, ptb_hit* hi
   if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
   if (n == 0) return PTB_OK;
   if (!rays || !hits) return set_error(c, PTB_ERR_INVALID, "null host buffer");
-  const size_t chunk = (size_t)1 << 26;  // 64 Mi rays per batch: 2 GiB of rays + 1 GiB of hits resident
+  // Batches of 4 Mi rays (128 MiB in, 64 MiB out) through two staging pairs: upload k+1 | traverse k | read back k-1.
+  // With pinned host buffers the three overlap and the call runs at PCIe speed; pageable buffers still work (the copies
+  // then serialise inside the driver).
+  size_t chunk = (size_t)1 << 22;
+  if (const char* e = getenv("PTB_HIT_BATCH")) { size_t v = strtoull(e, nullptr, 10); if (v >= 1024) chunk = v; }
   const size_t cap = n < chunk ? n : chunk;
-  PTB_CUDA_TRY(c, c->d_rays.reserve(cap * sizeof(ptb_ray)));
-  PTB_CUDA_TRY(c, c->d_hits.reserve(cap * sizeof(ptb_hit)));
-  for (size_t off = 0; off < n; off += chunk) {
-    const size_t m = n - off < chunk ? n - off : chunk;
-    PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_rays.p, rays + off, m * sizeof(ptb_ray), cudaMemcpyHostToDevice, c->stream));
-    int32_t rc = launch_closest_hit(c, c->d_rays.p, m, c->d_hits.p);
-    if (rc != PTB_OK) return rc;
-    PTB_CUDA_TRY(c, cudaMemcpyAsync(hits + off, c->d_hits.p, m * sizeof(ptb_hit), cudaMemcpyDeviceToHost, c->stream));
-    PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  DevBuf* dr[2] = {&c->d_rays, &c->d_rays2};
+  DevBuf* dh[2] = {&c->d_hits, &c->d_hits2};
+  const int nbuf = n > chunk ? 2 : 1;
+  for (int b = 0; b < nbuf; ++b) {
+    PTB_CUDA_TRY(c, dr[b]->reserve(cap * sizeof(ptb_ray)));
+    PTB_CUDA_TRY(c, dh[b]->reserve(cap * sizeof(ptb_hit)));
   }
+  if (!c->s_in) {
+    PTB_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    PTB_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_in[b], cudaEventDisableTiming));
+      PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_kernel[b], cudaEventDisableTiming));
+      PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_out[b], cudaEventDisableTiming));
+    }
+  }
+  // the staging buffers may still be in use by earlier work on the main stream
+  PTB_CUDA_TRY(c, cudaEventRecord(c->ev_kernel[0], c->stream));
+  PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_kernel[0], 0));
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += chunk, ++k) {
+    const size_t m = n - off < chunk ? n - off : chunk;
+    const int b = (int)(k & 1u);
+    if (k >= 2) PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_kernel[b], 0));  // batch k-2 no longer reads d_rays[b]
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(dr[b]->p, rays + off, m * sizeof(ptb_ray), cudaMemcpyHostToDevice, c->s_in));
+    PTB_CUDA_TRY(c, cudaEventRecord(c->ev_in[b], c->s_in));
+    PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
+    if (k >= 2) PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_out[b], 0));     // batch k-2's hits left d_hits[b]
+    int32_t rc = launch_closest_hit(c, dr[b]->p, m, dh[b]->p);
+    if (rc != PTB_OK) return rc;
+    PTB_CUDA_TRY(c, cudaEventRecord(c->ev_kernel[b], c->stream));
+    PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_out, c->ev_kernel[b], 0));
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(hits + off, dh[b]->p, m * sizeof(ptb_hit), cudaMemcpyDeviceToHost, c->s_out));
+    PTB_CUDA_TRY(c, cudaEventRecord(c->ev_out[b], c->s_out));
+  }
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return PTB_OK;
 }
 

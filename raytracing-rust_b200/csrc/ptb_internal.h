@@ -113,8 +113,11 @@ struct Ctx {
   cudaEvent_t ev_prof[16] = {};  // PTB_OPT_TIME_KERNELS: 2 iterations x 4 kernel classes x (start, stop)
   bool opt_time_kernels = false, opt_count_traversal = false;
 
-  // closest-hit staging
-  DevBuf d_rays, d_hits;
+  // closest-hit staging: two buffer pairs + copy streams so that the upload of batch k+1, the traversal of batch k and the
+  // read-back of batch k-1 overlap (ptb_closest_hit with host buffers)
+  DevBuf d_rays, d_hits, d_rays2, d_hits2;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {}, ev_kernel[2] = {}, ev_out[2] = {};
 
   ptb_stats stats{};
 };

@@ -120,3 +120,18 @@ def test_empty_and_edge_inputs(ptb, gpu_ctx, rtweekend1):
     gpu_ctx.commit()
     for n in (1, 31, 32, 33, 255, 257, 1025):
         assert len(gpu_ctx.closest_hit(random_rays(ptb, n, n))) == n
+
+
+def test_host_batches_are_pipelined_without_changing_results(ptb, gpu_ctx, monkeypatch):
+    """ptb_closest_hit splits a host ray array into batches over two staging pairs (upload | traverse | read back);
+    results must not depend on the batch size, including a ragged last batch and a caller-owned output buffer."""
+    s = ptb.meshgen.c3_scene(0.05)
+    gpu_ctx.upload(s)
+    gpu_ctx.commit()
+    rays = random_rays(ptb, 50_001, 5, centre=(0, 4, 1), radius=5.0)
+    whole = gpu_ctx.closest_hit(rays)
+    monkeypatch.setenv("PTB_HIT_BATCH", "4096")
+    out = np.zeros(len(rays), ptb.hit_dtype)
+    parts = gpu_ctx.closest_hit(rays, out=out)
+    assert parts is out and np.array_equal(whole, parts)
+    assert len(gpu_ctx.closest_hit(rays[:0])) == 0

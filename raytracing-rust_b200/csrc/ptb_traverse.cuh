@@ -67,10 +67,30 @@ PTB_DEV void load_node(const BvhNode* __restrict__ nodes, uint32_t idx, float4& 
 
 // Per-lane traversal state. `cur`: internal node index, or a PARKED leaf reference (bit 31: the leaf queue was full), or
 // kNone when the stack ran dry. The leaf queue is a ring of (reference, cull key) in local memory.
+#ifndef PTB_SHARED_STACK
+#define PTB_SHARED_STACK 0       // top-of-stack entries per lane kept in shared memory (power of two; 0 = local memory only).
+                                 // Measured on B200, C3 (profiles/r1_sweeps.md): 0 -> 2228 Mrays/s, 4 -> 2011, 8 -> 2045,
+                                 // 16 -> 2036: the extra index arithmetic and the smaller L1 cost more than the
+                                 // conflict-free accesses save, so the local-memory stack stays the default.
+#endif
+constexpr int kSharedStack = PTB_SHARED_STACK;
+constexpr int kTraceThreads = 256;  // block size of every kernel that runs persistent_trace
+
+// Traversal stack: (L1-cached) local memory, optionally with the newest kSharedStack entries in shared memory.
+// Lanes sit at different depths, so a local-memory access of a warp touches one 128-byte line PER LANE (ncu: a third of
+// the L1 wavefronts of k_trace are stack traffic); the shared copy is indexed [depth][thread], its bank depends on the
+// thread only, and an 8-byte access of a full warp is always two conflict-free wavefronts. Entries [lo, sp) are in
+// shared memory at slot (index mod kSharedStack), entries [0, lo) in local memory.
+struct TravStack {
+  uint2* local;   // kStackDepth entries (per lane)
+  uint2* shared;  // &smem[0][threadIdx.x], stride kTraceThreads
+};
+
 struct TravState {
   uint32_t cur;
   float cur_key;      // cull key of a parked leaf
   int sp;
+  int lo;             // first stack index resident in shared memory
   uint32_t lq_head, lq_count;
   float best_t;       // closest hit so far (closest-hit) / tmax (any-hit)
   uint32_t best_ref;  // closest-hit: winning leaf ref; any-hit: kNone = unoccluded, 0 = occluded
@@ -81,6 +101,7 @@ PTB_DEV void trav_init(TravState& s, uint32_t n_prims, float tmax) {
   s.cur = n_prims ? 0u : kNone;
   s.cur_key = 0.0f;
   s.sp = 0;
+  s.lo = 0;
   s.lq_head = 0u;
   s.lq_count = 0u;
   s.best_t = tmax;
@@ -92,14 +113,32 @@ PTB_DEV void lq_push(TravState& s, uint2* lq, uint32_t ref, float key) {
   ++s.lq_count;
 }
 
-// Stack entry = (node or leaf reference, cull key of its box) in one 8-byte local-memory word.
+PTB_DEV void stack_push(TravState& s, const TravStack& k, uint2 e) {
+  if (kSharedStack == 0) { k.local[s.sp++] = e; return; }
+  if (s.sp - s.lo == kSharedStack) {  // shared part full: its oldest entry moves to local memory
+    k.local[s.lo] = k.shared[(s.lo & (kSharedStack - 1)) * kTraceThreads];
+    ++s.lo;
+  }
+  k.shared[(s.sp & (kSharedStack - 1)) * kTraceThreads] = e;
+  ++s.sp;
+}
+PTB_DEV uint2 stack_pop(TravState& s, const TravStack& k) {  // requires sp > 0
+  --s.sp;
+  if (kSharedStack == 0) return k.local[s.sp];
+  if (s.sp < s.lo) {  // shared part empty: read the spilled entry in place
+    s.lo = s.sp;
+    return k.local[s.sp];
+  }
+  return k.shared[(s.sp & (kSharedStack - 1)) * kTraceThreads];
+}
+
+// Stack entry = (node or leaf reference, cull key of its box) in one 8-byte word.
 // Pops until an internal node is found (-> cur), the stack is empty (-> kNone), or a leaf turns up while the leaf queue is
 // full (-> parked in cur). Entries whose box can no longer hold a closer hit are dropped; leaves go to the queue.
-PTB_DEV void trav_pop(TravState& s, const uint2* stack, uint2* lq) {
+PTB_DEV void trav_pop(TravState& s, const TravStack& stack, uint2* lq) {
   for (;;) {
     if (s.sp == 0) { s.cur = kNone; return; }
-    --s.sp;
-    const uint2 e = stack[s.sp];
+    const uint2 e = stack_pop(s, stack);
     const float key = __uint_as_float(e.y);
     if (key <= s.best_t) {
       if (e.x & PTB_LEAF_BIT) {
@@ -115,7 +154,8 @@ PTB_DEV void trav_pop(TravState& s, const uint2* stack, uint2* lq) {
 // One internal-node step of the lane: fetch the 64-byte node, test both child boxes, descend into the nearer hit child
 // (deferring the other on the stack); a leaf child is queued and the walk continues from the stack.
 template <bool COUNT>
-PTB_DEV void trav_node_step(const DevScene& sc, const SlabRay& ray, const Ray& full, TravState& s, uint2* stack, uint2* lq, uint32_t& n_nodes) {
+PTB_DEV void trav_node_step(const DevScene& sc, const SlabRay& ray, const Ray& full, TravState& s, const TravStack& stack, uint2* lq,
+                            uint32_t& n_nodes) {
   float4 n0, n1, n2;
   uint4 n3;
   load_node(sc.nodes, s.cur, n0, n1, n2, n3);
@@ -132,10 +172,7 @@ PTB_DEV void trav_node_step(const DevScene& sc, const SlabRay& ray, const Ray& f
   if (!want_pop) {
     const bool both = hl && hr;
     const bool right_first = both ? (tr < tl) : hr;
-    if (both) {
-      stack[s.sp] = make_uint2(right_first ? n3.x : n3.y, __float_as_uint(right_first ? tl : tr));
-      ++s.sp;
-    }
+    if (both) stack_push(s, stack, make_uint2(right_first ? n3.x : n3.y, __float_as_uint(right_first ? tl : tr)));
     s.cur = right_first ? n3.y : n3.x;
     if (s.cur & PTB_LEAF_BIT) {
       const float key = right_first ? tr : tl;
@@ -153,7 +190,7 @@ PTB_DEV void trav_node_step(const DevScene& sc, const SlabRay& ray, const Ray& f
 // One primitive step of the lane: take the oldest queued leaf (the nearest, as the walk is near-first), drop it if its box
 // has fallen behind the best hit, else test it; then move a parked leaf into the freed queue slot and resume the walk.
 template <bool ANYHIT, bool COUNT>
-PTB_DEV void trav_prim_step(const DevScene& sc, const Ray& ray, TravState& s, uint2* stack, uint2* lq, uint32_t exclude,
+PTB_DEV void trav_prim_step(const DevScene& sc, const Ray& ray, TravState& s, const TravStack& stack, uint2* lq, uint32_t exclude,
                             uint32_t& n_prims) {
   const uint2 e = lq[s.lq_head];
   s.lq_head = (s.lq_head + 1u) & (kLeafQueue - 1u);
@@ -168,6 +205,7 @@ PTB_DEV void trav_prim_step(const DevScene& sc, const Ray& ray, TravState& s, ui
           s.best_ref = 0u;
           s.cur = kNone;
           s.sp = 0;
+          s.lo = 0;
           s.lq_count = 0u;
           return;
         }
@@ -210,7 +248,9 @@ template <bool ANYHIT, bool COUNT, class Fetch, class Retire>
 PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fetch& fetch, Retire& retire,
                               uint32_t& cnt_nodes, uint32_t& cnt_prims, uint32_t& cnt_rays) {
   const uint32_t lane = threadIdx.x & 31u;
-  uint2 stack[kStackDepth];
+  uint2 stack_local[kStackDepth];
+  __shared__ uint2 stack_shared[(kSharedStack ? kSharedStack : 1) * kTraceThreads];
+  const TravStack stack{stack_local, stack_shared + threadIdx.x};
   uint2 lq[kLeafQueue];
   TravState st;
   trav_init(st, 0u, 0.0f);

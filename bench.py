@@ -26,7 +26,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of k_trace per ray, from the committed ncu capture (profiles/)
-NCU_DRAM_BYTES_PER_RAY = {"c3": (1.244e9 + 0.6104e9) / 16.78e6}
+NCU_DRAM_BYTES_PER_RAY = {"c3": (2.02e9 + 0.7096e9) / 16.78e6}
+# what ncu says actually limits k_trace on C3 (same capture): the scene is L2 resident, so the HBM roofline does not bind
+NCU_LIMITER = {"c3": {"unit": "SM issue slots / L1 data-pipe wavefronts", "issue_active_pct": 68.6, "l1_data_pipe_pct": 67.4,
+                      "active_lanes_per_instruction": 17.4, "l2_hit_pct": 72.6, "source": "profiles/r1_final_c3.md"}}
 
 
 def parse_args():
@@ -366,13 +369,15 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
                          # DRAM bytes per k_trace launch: per-ray figure from the committed `ncu --set full` capture
-                         # (profiles/r1_final_c3.md: 1.244 GB read + 0.610 GB written for a 16.78 M-ray launch on this
+                         # (profiles/r1_final_c3.md: 2.02 GB read + 0.71 GB written for a 16.78 M-ray launch on this
                          # workload) x this run's mean rays per launch. The 1 M-triangle scene is L2 resident, so real
-                         # traffic is ~20x below the algorithmic bytes: the kernel is ALU-issue bound, not HBM bound.
+                         # traffic is ~13x below the algorithmic bytes and `frac` can exceed 1: the kernel is bound by
+                         # issue slots and L1 wavefronts (`limiter`), not by HBM.
                          "traffic": (NCU_DRAM_BYTES_PER_RAY.get(args.workload) * traced / max(int(st.trace_launches), 1)
                                      if NCU_DRAM_BYTES_PER_RAY.get(args.workload) else None),
                          "traffic_source": "ncu capture profiles/r1_final_c3.md (bytes/ray) x rays per launch of this run",
                          "algorithmic_bytes_per_launch": b_ray * traced / max(int(st.trace_launches), 1),
+                         "limiter": NCU_LIMITER.get(args.workload),
                          "bytes_per_ray": b_ray, "nodes_per_ray": V, "prims_per_ray": T,
                          "k_trace_ms": st.ms_trace, "k_shade_ms": st.ms_shade, "k_generate_ms": st.ms_generate,
                          "k_shadow_ms": st.ms_shadow, "k_trace_share_of_step": st.ms_trace / dev_ms if dev_ms else None,

@@ -31,6 +31,9 @@ pub struct ptb_stats {
 }
 #[repr(C)] pub struct ptb_ctx { _private: [u8; 0] }
 pub type ptb_progress_fn = Option<unsafe extern "C" fn(user: *mut c_void, samples_completed: u64, rays_shot: u64) -> i32>;
+/// per-pass presentation closure (random_sampler.rs:82-98): single-sample image of a finished pass, 1-based pass number
+pub type ptb_pass_fn = Option<unsafe extern "C" fn(user: *mut c_void, pass_image: *const f32, n_floats: usize, pass_number: u64, rays_shot: u64) -> i32>;
+pub const PTB_PERLIN_TABLE_WORDS: usize = 1024;
 
 extern "C" {
     pub fn ptb_abi_version() -> u32;
@@ -41,11 +44,15 @@ extern "C" {
     pub fn ptb_scene_set_triangles(ctx: *mut ptb_ctx, p: *const ptb_triangle, n: usize) -> i32;
     pub fn ptb_scene_set_materials(ctx: *mut ptb_ctx, p: *const ptb_material, n: usize) -> i32;
     pub fn ptb_scene_set_textures(ctx: *mut ptb_ctx, p: *const ptb_texture, n: usize) -> i32;
+    pub fn ptb_scene_set_texture_data(ctx: *mut ptb_ctx, texture: u32, width: u32, height: u32, data: *const f32, n_floats: usize) -> i32;
     pub fn ptb_scene_set_camera(ctx: *mut ptb_ctx, cam: *const ptb_camera) -> i32;
     pub fn ptb_scene_set_sky(ctx: *mut ptb_ctx, sky: *const ptb_sky) -> i32;
     pub fn ptb_scene_commit(ctx: *mut ptb_ctx, build_flags: u32) -> i32;
     pub fn ptb_closest_hit(ctx: *mut ptb_ctx, rays: *const ptb_ray, n: usize, hits: *mut ptb_hit) -> i32;
     pub fn ptb_render(ctx: *mut ptb_ctx, opts: *const ptb_render_opts, progress: ptb_progress_fn, user: *mut c_void) -> i32;
+    pub fn ptb_render_passes(ctx: *mut ptb_ctx, opts: *const ptb_render_opts, update: ptb_pass_fn, user: *mut c_void) -> i32;
+    pub fn ptb_render_multi(ctxs: *const *mut ptb_ctx, n: i32, opts: *const ptb_render_opts) -> i32;
+    pub fn ptb_shard_samples(samples_per_pixel: u32, sample_offset: u32, rank: i32, world: i32, first: *mut u32, count: *mut u32);
     pub fn ptb_accum_clear(ctx: *mut ptb_ctx) -> i32;
     pub fn ptb_accum_read(ctx: *mut ptb_ctx, rgb: *mut f32, n_floats: usize, normalise: i32) -> i32;
     pub fn ptb_accum_device_ptr(ctx: *mut ptb_ctx, d_ptr: *mut *mut c_void, n_floats: *mut usize) -> i32;

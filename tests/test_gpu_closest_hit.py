@@ -135,3 +135,44 @@ def test_host_batches_are_pipelined_without_changing_results(ptb, gpu_ctx, monke
     parts = gpu_ctx.closest_hit(rays, out=out)
     assert parts is out and np.array_equal(whole, parts)
     assert len(gpu_ctx.closest_hit(rays[:0])) == 0
+
+
+def test_full_size_c3_matches_lbvh_oracle(ptb, orc, gpu_ctx):
+    """BASELINE config C3 at full size (1 000 000 triangles), 1 M incoherent rays: the device against the CPU traversal of the
+    same (bit-exact) LBVH — identical primitive ids and bit-identical t — and the device's node count within the
+    speculation margin of the sequential oracle."""
+    s = ptb.meshgen.c3_scene(1.0)
+    rays = random_rays(ptb, 1 << 20, 77, centre=(0, 4, 1), radius=6.0)
+    gpu_ctx.upload(s)
+    gpu_ctx.commit()
+    g = gpu_ctx.closest_hit(rays)
+    o = orc.OracleScene(s, split_type=-1)
+    h, nodes, prims = o.lbvh_closest_hit(rays)
+    assert np.array_equal(g["prim"], h["prim"])
+    assert np.array_equal(g["t"].view(np.uint32), h["t"].view(np.uint32))
+    assert 0.2 < float((g["prim"] != ptb.PTB_MISS).mean()) < 0.9
+
+
+def test_full_size_heightfield_properties(ptb, gpu_ctx):
+    """BASELINE config C5 geometry (10 000 000-triangle heightfield), 4 M rays of the C5 stream: size-independent properties —
+    every hit lies on the surface z = h(x, y) (within the facet sag), t > 0, misses only where the ray leaves the slab
+    [-1,1]^2 x [-0.2,0.2] untouched, and the answer does not depend on the order of the rays."""
+    s = ptb.meshgen.heightfield_scene(2500, 2000)
+    assert len(s.triangles) == 10_000_000
+    gpu_ctx.upload(s)
+    gpu_ctx.commit()
+    n = 1 << 22
+    rays = ptb.meshgen.philox_rays(n, first=0)
+    hits = gpu_ctx.closest_hit(rays)
+    hit = hits["prim"] != ptb.PTB_MISS
+    assert 0.05 < hit.mean() < 0.95 and np.all(hits["t"][hit] > 0) and np.all(hits["t"][~hit] == 0)
+    assert hits["prim"][hit].max() < 10_000_000
+    d = rays["d"] / np.linalg.norm(rays["d"], axis=1, keepdims=True)
+    p = rays["o"][hit].astype(np.float64) + d[hit].astype(np.float64) * hits["t"][hit, None]
+    assert np.all(np.abs(p[:, 0]) <= 1 + 1e-5) and np.all(np.abs(p[:, 1]) <= 1 + 1e-5)
+    X, Y = p[:, 0], p[:, 1]
+    z = 0.1 * np.sin(9 * X) * np.cos(7 * Y) + 0.1 * np.sin(23 * X + 17 * Y)
+    assert np.max(np.abs(p[:, 2] - z)) < 2e-4          # facets of 8e-4 x 1e-3 under curvature <= ~85: sag ~1e-5 .. 1e-4
+    perm = np.random.default_rng(3).permutation(n)
+    again = gpu_ctx.closest_hit(rays[perm])
+    assert np.array_equal(again, hits[perm])

@@ -172,6 +172,7 @@ __global__ void k_init_pool(uint32_t* free_slots, uint32_t capacity, WaveCounter
   if (i < capacity) free_slots[i] = capacity - 1u - i;  // popped from the end: slot 0 first
   if (i == 0) {
     wc->n_free = capacity;
+    wc->push_pair = wc->shadow_pair = 0;
     wc->n_active[0] = wc->n_active[1] = 0;
     wc->n_new = wc->n_trace = wc->free_base = 0;
     for (int k = 0; k < kNumKinds; ++k) wc->n_kind[k] = 0;
@@ -190,7 +191,12 @@ __global__ void k_init_pool(uint32_t* free_slots, uint32_t capacity, WaveCounter
 __global__ void k_prepare(WaveCounters* wc, uint32_t method, uint32_t first) {
   if (!first) {
     const uint32_t cur = wc->cur, nxt = cur ^ 1u;
-    const uint32_t traced = wc->n_trace, survivors = wc->n_active[nxt];
+    const unsigned long long pp = wc->push_pair, sp = wc->shadow_pair;
+    const uint32_t traced = wc->n_trace, survivors = (uint32_t)pp;
+    wc->n_active[nxt] = survivors;
+    wc->n_free = (uint32_t)(pp >> 32);
+    wc->rays_shadow_sky += sp >> 32;
+    wc->rays_shadow_light += (uint32_t)sp - (uint32_t)(sp >> 32);
     wc->rays_camera += wc->n_new;
     wc->rays_bounce += traced - wc->n_new;
     wc->rays_reference += method == PTB_METHOD_NAIVE ? traced : survivors;  // Q7: naive 1/check_hit, MIS 1/bounce iteration
@@ -208,6 +214,8 @@ __global__ void k_prepare(WaveCounters* wc, uint32_t method, uint32_t first) {
   wc->n_trace = wc->n_active[cur] + n_new;
   for (int k = 0; k < kNumKinds; ++k) wc->n_kind[k] = 0;
   wc->n_shadow = 0;
+  wc->push_pair = (unsigned long long)(n_free - n_new) << 32;  // finished slots append after the remaining free ones
+  wc->shadow_pair = 0;
   wc->trace_head = wc->shade_head = wc->shadow_head = 0;
 }
 
@@ -719,41 +727,26 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
     if (finished) finish_path(accum, pixel, L, nan_check);
   }
 
-  // ---- warp-aggregated queue pushes
+  // ---- warp-aggregated queue pushes: lane 0 issues both returning atomics back to back (their round trips overlap)
   {
-    const uint32_t m = __ballot_sync(0xffffffffu, alive);
-    if (m) {
-      uint32_t pos = 0;
-      const uint32_t leader = __ffs(m) - 1u;
-      if (lane == leader) pos = atomicAdd(&wc->n_active[nxt], __popc(m));
-      pos = __shfl_sync(0xffffffffu, pos, leader);
-      if (alive) q.active[nxt][pos + __popc(m & ((1u << lane) - 1u))] = slot;
+    const uint32_t m_alive = __ballot_sync(0xffffffffu, alive), m_fin = __ballot_sync(0xffffffffu, finished);
+    const uint32_t m_sh = METHOD == PTB_METHOD_MIS ? __ballot_sync(0xffffffffu, shadow) : 0u;
+    const uint32_t m_sky = METHOD == PTB_METHOD_MIS ? __ballot_sync(0xffffffffu, shadow && shadow_is_sky) : 0u;
+    unsigned long long p1 = 0ull, p2 = 0ull;
+    if (lane == 0u) {
+      if (m_alive | m_fin)
+        p1 = atomicAdd(&wc->push_pair, ((unsigned long long)__popc(m_fin) << 32) | (unsigned long long)__popc(m_alive));
+      if (METHOD == PTB_METHOD_MIS && m_sh)
+        p2 = atomicAdd(&wc->shadow_pair, ((unsigned long long)__popc(m_sky) << 32) | (unsigned long long)__popc(m_sh));
     }
-  }
-  {
-    const uint32_t m = __ballot_sync(0xffffffffu, finished);
-    if (m) {
-      uint32_t pos = 0;
-      const uint32_t leader = __ffs(m) - 1u;
-      if (lane == leader) pos = atomicAdd(&wc->n_free, __popc(m));
-      pos = __shfl_sync(0xffffffffu, pos, leader);
-      if (finished) q.free_slots[pos + __popc(m & ((1u << lane) - 1u))] = slot;
-    }
-  }
-  if (METHOD == PTB_METHOD_MIS) {
-    const uint32_t m = __ballot_sync(0xffffffffu, shadow);
-    if (m) {
-      uint32_t pos = 0;
-      const uint32_t leader = __ffs(m) - 1u;
-      const uint32_t n_sky = __popc(__ballot_sync(0xffffffffu, shadow && shadow_is_sky));
-      if (lane == leader) {
-        pos = atomicAdd(&wc->n_shadow, __popc(m));
-        if (n_sky) atomicAdd(&wc->rays_shadow_sky, (unsigned long long)n_sky);
-        if (__popc(m) - n_sky) atomicAdd(&wc->rays_shadow_light, (unsigned long long)(__popc(m) - n_sky));
-      }
-      pos = __shfl_sync(0xffffffffu, pos, leader);
+    p1 = __shfl_sync(0xffffffffu, p1, 0);
+    const uint32_t below = (1u << lane) - 1u;
+    if (alive) q.active[nxt][(uint32_t)p1 + __popc(m_alive & below)] = slot;
+    if (finished) q.free_slots[(uint32_t)(p1 >> 32) + __popc(m_fin & below)] = slot;
+    if (METHOD == PTB_METHOD_MIS) {
+      p2 = __shfl_sync(0xffffffffu, p2, 0);
       if (shadow) {
-        float4* e = q.shadow + 3u * (size_t)(pos + __popc(m & ((1u << lane) - 1u)));
+        float4* e = q.shadow + 3u * (size_t)((uint32_t)p2 + __popc(m_sh & below));
         e[0] = sh_o;
         e[1] = sh_d;
         e[2] = sh_c;
@@ -792,7 +785,7 @@ __global__ void __launch_bounds__(256) k_shadow(DevScene sc, PathPool pool, Queu
   uint32_t a = 0, b = 0, r = 0;
   ShadowFetch fetch{q, make_float4(0.f, 0.f, 0.f, 0.f)};
   ShadowRetire retire{pool, fetch};
-  persistent_trace<true, false>(sc, wc->n_shadow, &wc->shadow_head, fetch, retire, a, b, r);
+  persistent_trace<true, false>(sc, (uint32_t)wc->shadow_pair, &wc->shadow_head, fetch, retire, a, b, r);
 }
 
 // ------------------------------------------------------------------------------------------ closest-hit API kernel
@@ -1030,7 +1023,7 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
       PTB_CUDA_TRY(c, cudaEventSynchronize(ev[ps]));
       if (prof) prof_collect(ps);
       const WaveCounters& h = c->h_counters[ps];
-      if (h.next_sample >= h.total_samples && h.n_active[h.cur ^ 1u] == 0) done = true;
+      if (h.next_sample >= h.total_samples && (uint32_t)h.push_pair == 0u) done = true;
       if (progress && !done) {
         const uint64_t passes = h.next_sample / npix;
         if (passes != last_pass_reported) {

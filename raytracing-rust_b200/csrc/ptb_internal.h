@@ -110,8 +110,10 @@ struct Ctx {
   size_t h_pass_floats = 0;
   uint32_t accum_w = 0, accum_h = 0;
   uint64_t accum_samples = 0;
-  DevBuf d_pool_mem, d_queues, d_shadow, d_counters;
+  DevBuf d_pool_mem, d_prev, d_queues, d_shadow, d_counters;
   PathPool pool;
+  size_t pool_budget_bytes = 0;  // half of the device memory that was free at the first large render (0 = not asked yet)
+  bool pool_has_mis = false;  // d_prev / d_shadow hold pool.capacity entries
   WaveCounters* h_counters = nullptr;  // pinned
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_iter = nullptr;
   cudaEvent_t ev_prof[16] = {};  // PTB_OPT_TIME_KERNELS: 2 iterations x 4 kernel classes x (start, stop)

@@ -242,6 +242,15 @@ PTB_DEV TraceResult trav_result(const TravState& s) {
   return r;
 }
 
+#ifdef PTB_LANE_STATS  // tuning builds only: where do the lanes of a warp spend their iterations?
+// [0] loop iterations  [1] lanes with work (sum)  [2] node phases  [3] node-ready lanes in them  [4] primitive phases
+// [5] leaf-ready lanes in them  [6] service passes  [7] node steps executed (lane level)
+__device__ unsigned long long g_lane_stats[8];
+#define PTB_LS(i, v) do { if (lane == 0u) ls[i] += (v); } while (0)
+#else
+#define PTB_LS(i, v) do { } while (0)
+#endif
+
 // Persistent-warp driver. `fetch(i, ray, tmax, exclude)` loads work item i into the lane; `retire(fin, state, ray)` is
 // called by ALL 32 lanes together (fin = this lane just completed its item) so it may use warp-wide primitives.
 template <bool ANYHIT, bool COUNT, class Fetch, class Retire>
@@ -268,13 +277,19 @@ PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fe
   uint32_t cap = (n + total_warps - 1u) / total_warps;
   cap = cap < 1u ? 1u : (cap > 32u ? 32u : cap);
   const uint32_t fetch_below = (uint32_t)sc.trace_fetch_threshold < cap ? (uint32_t)sc.trace_fetch_threshold : cap;
+#ifdef PTB_LANE_STATS
+  unsigned long long ls[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
   for (;;) {
     // a lane with work is parked on an internal node, holds queued leaves, or both
     bool node_ready = has_ray && !(st.cur & PTB_LEAF_BIT);
     const bool leaf_ready = has_ray && st.lq_count != 0u;
     const uint32_t m_node = __ballot_sync(0xffffffffu, node_ready);
     const uint32_t m_leaf = __ballot_sync(0xffffffffu, leaf_ready);
+    PTB_LS(0, 1);
+    PTB_LS(1, __popc(m_node | m_leaf));
     if ((uint32_t)__popc(m_node | m_leaf) < (exhausted ? 1u : fetch_below)) {
+      PTB_LS(6, 1);
       // ---- service: retire finished items, refill idle lanes
       const bool fin = has_ray && !node_ready && !leaf_ready;
       retire(fin, st, ray);
@@ -313,15 +328,27 @@ PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fe
     const int n_node = __popc(m_node), n_blocked = __popc(m_leaf & ~m_node), n_leaf = __popc(m_leaf);
     const bool do_node = sc.trace_prim_bias ? (n_node >= n_blocked * sc.trace_prim_bias) : (n_node >= n_leaf);
     if (do_node) {
+      PTB_LS(2, 1);
+      PTB_LS(3, n_node);
 #pragma unroll 1
       for (int burst = 0; burst < sc.trace_burst && node_ready; ++burst) {
         trav_node_step<COUNT>(sc, slab, ray, st, stack, lq, cnt_nodes);
         node_ready = !(st.cur & PTB_LEAF_BIT);
+#ifdef PTB_LANE_STATS
+        atomicAdd(&g_lane_stats[7], 1ull);
+#endif
       }
     } else if (leaf_ready) {
       trav_prim_step<ANYHIT, COUNT>(sc, ray, st, stack, lq, exclude, cnt_prims);
     }
+#ifdef PTB_LANE_STATS
+    if (!do_node) { PTB_LS(4, 1); PTB_LS(5, n_leaf); }
+#endif
   }
+#ifdef PTB_LANE_STATS
+  if (lane == 0u)
+    for (int i = 0; i < 7; ++i) atomicAdd(&g_lane_stats[i], ls[i]);
+#endif
 }
 
 }  // namespace ptb

@@ -876,18 +876,42 @@ int32_t launch_closest_hit(Ctx* c, const void* d_rays, size_t n, void* d_hits) {
   return PTB_OK;
 }
 
+static unsigned long long bytes_per_path(bool mis) {
+  // 64-byte path block + queues (2 active, free, kNumKinds shade queues) + MIS: previous-hit record, 48-byte shadow entry
+  return 64ull + 4ull * (3 + kNumKinds) + (mis ? 16ull + 48ull : 0ull);
+}
+
 void free_render_state(Ctx* c) {
   c->d_pool_mem.release();
+  c->d_prev.release();
   c->d_queues.release();
   c->d_shadow.release();
+  c->pool_has_mis = false;
   c->pool = PathPool();
 }
 
-static uint32_t pool_capacity_for(unsigned long long total) {
-  unsigned long long cap = 1ull << 24;  // 16 Mi paths in flight (1.3 GB of path state): long launches hide each launch's tail
+// Paths in flight. The wavefront is fastest when EVERY camera path of the call is resident: the iterations then become
+// depth-synchronous (iteration k traces bounce k of all paths: camera rays, the coherent half of the work, run together at
+// 5 Grays/s), there are ~55 launches per render instead of ~110, and only one tail. Measured on B200, C3 at 256 spp per
+// call (profiles/r1_sweeps.md): 16 Mi paths 2264 Mrays/s, 64 Mi 2461, 128 Mi 2612, 256 Mi 2760, 512 Mi 2839. Path state is
+// 100 B per path (naive) / 164 B (MIS: + previous-hit record and shadow queue), so the default of 256 Mi paths takes
+// 27 / 44 GB of the B200's 180 GB; the pool never takes more than half of the free device memory. PTB_POOL_PATHS overrides.
+static uint32_t pool_capacity_for(Ctx* c, unsigned long long total, bool mis) {
+  unsigned long long cap = 1ull << 28;
+  bool forced = false;
   if (const char* e = getenv("PTB_POOL_PATHS")) {
     unsigned long long v = strtoull(e, nullptr, 10);
-    if (v >= 1024 && v <= (1ull << 26)) cap = v;
+    if (v >= 1024 && v <= (1ull << 29)) { cap = v; forced = true; }
+  }
+  if (!forced && total > (1ull << 24)) {
+    // asked once per context (cudaMemGetInfo costs milliseconds once tens of GB are allocated): the budget is half of
+    // what was free before this context's first large pool
+    if (c->pool_budget_bytes == 0) {
+      size_t free_b = 0, total_b = 0;
+      c->pool_budget_bytes = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? free_b / 2 + 1 : ~(size_t)0;
+    }
+    const unsigned long long per_path = bytes_per_path(mis);
+    while (cap > (1ull << 24) && cap * per_path > c->pool_budget_bytes) cap >>= 1;
   }
   if (total < cap) cap = total < 1024 ? 1024 : total;
   return (uint32_t)((cap + 255ull) & ~255ull);
@@ -898,22 +922,25 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   const uint32_t npix = o.width * o.height;
   const unsigned long long total = (unsigned long long)npix * o.samples_per_pixel;
   if (total == 0) return PTB_OK;
-  const uint32_t P = pool_capacity_for(total);
+  const bool mis = o.method == PTB_METHOD_MIS;
+  const uint32_t P = pool_capacity_for(c, total, mis);
 
-  // ---- device state (grow-only across calls)
-  if (c->pool.capacity != P) {
-    const size_t pool_bytes = (size_t)P * (32 + 32 + 16);
-    PTB_CUDA_TRY(c, c->d_pool_mem.reserve(pool_bytes));
-    char* b = c->d_pool_mem.as<char>();
-    c->pool.capacity = P;
+  // ---- device state (grow-only across calls; the MIS-only arrays are allocated by the first MIS call)
+  if (c->pool.capacity != P || (mis && !c->pool_has_mis)) {
+    c->pool.capacity = 0;
     // one 64-byte block per path: ray record then colour record (a DRAM access atom; two scattered 32-byte sectors
     // per path cost generate/shade ~1 TB/s of effective write bandwidth)
-    c->pool.ray = reinterpret_cast<float4*>(b);
+    PTB_CUDA_TRY(c, c->d_pool_mem.reserve((size_t)P * 64));
+    c->pool.ray = c->d_pool_mem.as<float4>();
     c->pool.col = c->pool.ray + 2;
-    b += (size_t)P * 64;
-    c->pool.prev = reinterpret_cast<float4*>(b);
     PTB_CUDA_TRY(c, c->d_queues.reserve((size_t)P * 4 * (3 + kNumKinds)));
-    PTB_CUDA_TRY(c, c->d_shadow.reserve((size_t)P * 48));
+    if (mis || c->pool_has_mis) {
+      PTB_CUDA_TRY(c, c->d_prev.reserve((size_t)P * 16));
+      PTB_CUDA_TRY(c, c->d_shadow.reserve((size_t)P * 48));
+      c->pool_has_mis = true;
+    }
+    c->pool.prev = c->d_prev.as<float4>();
+    c->pool.capacity = P;
   }
   PTB_CUDA_TRY(c, c->d_counters.reserve(sizeof(WaveCounters) + 64));
   Queues q;
@@ -947,7 +974,6 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
 
   float* accum = c->accum_target ? c->accum_target : c->d_accum.as<float>();
   const int T = 256;
-  const bool mis = o.method == PTB_METHOD_MIS;
   const uint32_t grid_p = (P + T - 1) / T;
   auto capped = [&](const void* k) { const int g = persistent_grid(c, k, T); return (uint32_t)g < grid_p ? (uint32_t)g : grid_p; };
   const uint32_t grid_gen = capped((const void*)k_generate);
@@ -1044,6 +1070,17 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   PTB_CUDA_TRY(c, cudaGetLastError());
   if (prof && iter > 0) prof_collect((int)((iter - 1) & 1u));
 #undef PTB_PROF
+#ifdef PTB_LANE_STATS
+  {
+    unsigned long long ls[8];
+    cudaMemcpyFromSymbol(ls, g_lane_stats, sizeof(ls));
+    fprintf(stderr, "lane_stats iters %llu work_lanes/iter %.2f node_phases %llu (%.2f ready lanes) prim_phases %llu (%.2f ready lanes) "
+            "services %llu node_steps %llu\n", ls[0], (double)ls[1] / ls[0], ls[2], (double)ls[3] / (ls[2] ? ls[2] : 1), ls[4],
+            (double)ls[5] / (ls[4] ? ls[4] : 1), ls[6], ls[7]);
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_lane_stats, z, sizeof(z));
+  }
+#endif
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
   const WaveCounters& h = c->h_counters[0];

@@ -1,7 +1,6 @@
 #!/bin/bash
-# wavefront pool-size sweep on the sphere scenes (MIS), B200
-for p in 262144 524288 1048576 2097152 4194304 16777216; do
- for wl in "rtweekend1 --spp-per-step 16" "overshadowed --spp-per-step 64"; do
-  echo -n "pool=$p $wl: "; PTB_POOL_PATHS=$p python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu --no-e2e 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print(round(d['value']), 'ms/step', round(d['ms_per_step'],1), 'trace', round(r['k_trace_ms']), 'shade', round(r['k_shade_ms']), 'shadow', round(r['k_shadow_ms']), 'gen', round(r['k_generate_ms']), 'launches', d['gpu_launches'])"
- done
+# wavefront pool-size sweep (paths in flight) on C3 (naive, 64 and 256 spp per step) and rtweekend1 4K (MIS), B200
+for p in ${POOLS:-16777216 33554432 67108864 134217728 268435456}; do
+ echo -n "pool=$p: "; PTB_POOL_PATHS=$p bash scripts/quick_bench.sh 2>&1 | head -2 | tr '\n' '|'; 
+ PTB_POOL_PATHS=$p python bench.py --steps 2 --warmup 2 --no-cpu --no-e2e 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); r=d['roofline']; print('c3@256spp', round(d['value']), 'ms/step', round(d['ms_per_step'],1))"
 done

@@ -23,6 +23,7 @@ namespace ptb {
 struct RenderParams {
   uint32_t width, height, npix;
   uint32_t tile_w, tile_h;  // pixel issue order (k_generate); tile_h == 1 -> row-major
+  uint32_t group;           // samples of one pixel issued back to back (a divisor of the call's spp)
   uint32_t sample_offset;
   uint32_t method, max_depth, rr_threshold;
   uint32_t k0, k1;  // Philox key
@@ -227,8 +228,14 @@ k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams 
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
   const uint32_t slot = q.free_slots[wc->free_base + (n_new - 1u - i)];
   const unsigned long long g = wc->next_sample + i;
-  const uint32_t lin = (uint32_t)(g % rp.npix);
-  const uint32_t sample = rp.sample_offset + (uint32_t)(g / rp.npix);
+  // issue order: for each chunk of `group` samples, for each pixel, the chunk's samples — the 32 camera rays of a warp
+  // share a pixel (group = 32) and walk the same nodes down to the last levels. Only the ORDER changes; RNG and
+  // accumulator are keyed by (pixel, absolute sample).
+  const unsigned long long per_chunk = (unsigned long long)rp.npix * rp.group;
+  const uint32_t chunk = (uint32_t)(g / per_chunk);
+  const unsigned long long within_chunk = g % per_chunk;
+  const uint32_t lin = (uint32_t)(within_chunk / rp.group);
+  const uint32_t sample = rp.sample_offset + chunk * rp.group + (uint32_t)(within_chunk % rp.group);
   // A warp's 32 consecutive work items cover a tile_w x tile_h block of pixels (8x4 when the image allows) instead of a
   // 32x1 strip: camera rays of a warp stay coherent in both directions. Only the issue ORDER changes; RNG and
   // accumulator are keyed by the true pixel index.
@@ -963,6 +970,13 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   if (getenv("PTB_TILES"))
     for (uint32_t th = 4u; th > 1u; th >>= 1)
       if (o.height % th == 0u && o.width % (32u / th) == 0u) { rp.tile_h = th; rp.tile_w = 32u / th; break; }
+  rp.group = 1u;
+  {
+    uint32_t want = 1024u;
+    if (const char* e = getenv("PTB_SAMPLE_GROUP")) { int v = atoi(e); if (v >= 1 && v <= 1024) want = (uint32_t)v; }
+    for (uint32_t g = want < o.samples_per_pixel ? want : o.samples_per_pixel; g > 1u; --g)
+      if (o.samples_per_pixel % g == 0u) { rp.group = g; break; }
+  }
   rp.sample_offset = o.sample_offset;
   rp.method = o.method;
   rp.max_depth = o.max_depth ? o.max_depth : 50u;

@@ -62,7 +62,7 @@ struct WaveCounters {  // lives in device memory; mirrored to pinned host memory
   uint32_t n_shadow;
   uint32_t cur;             // which q_active is the trace queue
   uint32_t trace_head, shade_head, shadow_head;  // persistent-kernel work cursors
-  uint32_t _pad;
+  uint32_t n_win_alive;     // window mode: entries of win_list (non-empty windows of this iteration)
   // k_shade's queue cursors, packed so that one warp needs ONE returning atomic per pair (the kernel used to spend 40 % of
   // its stall samples waiting for three serial same-address atomics): push_pair = finished-slot cursor << 32 | next-active
   // cursor, shadow_pair = sky NEE rays << 32 | shadow-queue cursor. k_prepare unpacks them between iterations.
@@ -110,10 +110,9 @@ struct Ctx {
   size_t h_pass_floats = 0;
   uint32_t accum_w = 0, accum_h = 0;
   uint64_t accum_samples = 0;
-  DevBuf d_pool_mem, d_prev, d_queues, d_shadow, d_counters;
+  DevBuf d_pool_mem, d_prev, d_queues, d_shadow, d_counters, d_windows;
   PathPool pool;
   size_t pool_budget_bytes = 0;  // half of the device memory that was free at the first large render (0 = not asked yet)
-  bool pool_has_mis = false;  // d_prev / d_shadow hold pool.capacity entries
   WaveCounters* h_counters = nullptr;  // pinned
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_iter = nullptr;
   cudaEvent_t ev_prof[16] = {};  // PTB_OPT_TIME_KERNELS: 2 iterations x 4 kernel classes x (start, stop)

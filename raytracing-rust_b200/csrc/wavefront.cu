@@ -34,7 +34,16 @@ struct Queues {
   uint32_t* free_slots;
   uint32_t* kind[kNumKinds];
   float4* shadow;  // 3 x float4 per entry: o.xyz|tmax, d.xyz|exclude slot, contrib.rgb|path slot
+  // window mode (see "window wavefront" below)
+  uint32_t* win_count;   // [n_windows] live paths of each 256-slot window
+  uint32_t* win_prefix;  // [n_windows] exclusive prefix of win_count inside the window's 4096-window segment
+  uint32_t* seg_total;   // [n_windows / 4096 + 1] live paths per segment
+  uint8_t* bin;          // [capacity] direction bin of the path's next ray, kBinDead once the path has finished
+  uint32_t n_windows;
 };
+constexpr uint32_t kBinDead = 0xFFu;
+constexpr uint32_t kWindow = 256u;        // slots per window == threads of a window-mode shade block
+constexpr uint32_t kSegWindows = 4096u;   // windows per scan segment (1024 threads x 4)
 
 constexpr uint32_t kFlagPrevDelta = 1u << 8;  // stored above the 8-bit depth in ray_d.w
 
@@ -221,15 +230,10 @@ __global__ void k_prepare(WaveCounters* wc, uint32_t method, uint32_t first) {
 }
 
 // ------------------------------------------------------------------------------------------ K1 camera rays
-__global__ void __launch_bounds__(256)
-k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp) {
-  const uint32_t n_new = wc->n_new;
-  const uint32_t cur = wc->cur;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
-  const uint32_t slot = q.free_slots[wc->free_base + (n_new - 1u - i)];
-  const unsigned long long g = wc->next_sample + i;
+// One camera path: global path index g -> (pixel, sample) -> ray, written to `slot`.
+PTB_DEV void emit_camera_path(const DevScene& sc, const PathPool& pool, const RenderParams& rp, unsigned long long g, uint32_t slot) {
   // issue order: for each chunk of `group` samples, for each pixel, the chunk's samples — the 32 camera rays of a warp
-  // share a pixel (group = 32) and walk the same nodes down to the last levels. Only the ORDER changes; RNG and
+  // share a pixel (group >= 32) and walk the same nodes down to the last levels. Only the ORDER changes; RNG and
   // accumulator are keyed by (pixel, absolute sample).
   const unsigned long long per_chunk = (unsigned long long)rp.npix * rp.group;
   const uint32_t chunk = (uint32_t)(g / per_chunk);
@@ -237,8 +241,7 @@ k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams 
   const uint32_t lin = (uint32_t)(within_chunk / rp.group);
   const uint32_t sample = rp.sample_offset + chunk * rp.group + (uint32_t)(within_chunk % rp.group);
   // A warp's 32 consecutive work items cover a tile_w x tile_h block of pixels (8x4 when the image allows) instead of a
-  // 32x1 strip: camera rays of a warp stay coherent in both directions. Only the issue ORDER changes; RNG and
-  // accumulator are keyed by the true pixel index.
+  // 32x1 strip (group == 1 only matters): only the issue ORDER changes.
   uint32_t x, y;
   if (rp.tile_h > 1u) {
     const uint32_t tile = lin >> 5, within = lin & 31u, tiles_x = rp.width / rp.tile_w;
@@ -261,7 +264,16 @@ k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams 
          make_float4(d.x, d.y, d.z, __uint_as_float(kNone)));
   stg256(pool.col + 4u * (size_t)slot, make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pixel)),
          make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(sample << 9)));
-  q.active[cur][wc->n_active[cur] + i] = slot;
+}
+
+__global__ void __launch_bounds__(256)
+k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp) {
+  const uint32_t n_new = wc->n_new;
+  const uint32_t cur = wc->cur;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_new; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = q.free_slots[wc->free_base + (n_new - 1u - i)];
+    emit_camera_path(sc, pool, rp, wc->next_sample + i, slot);
+    q.active[cur][wc->n_active[cur] + i] = slot;
   }
 }
 // next_sample is advanced by a separate 1-thread launch: every k_generate thread reads it
@@ -279,6 +291,7 @@ struct TraceFetch {
     ray = make_ray(from4(o), from4(d));
   }
 };
+template <bool DENSE>
 struct TraceRetire {
   const DevScene& sc;
   const PathPool& pool;
@@ -294,8 +307,9 @@ struct TraceRetire {
       const TraceResult tr = trav_result(st);
       stg256(pool.ray + 4u * (size_t)f.slot, make_float4(ray.o.x, ray.o.y, ray.o.z, tr.t),
              make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(tr.ref)));
-      kind = tr.ref == kNone ? 0u : 1u + (__ldg(sc.slot_mat + (tr.ref & kSlotMask)) >> 24);
+      if (!DENSE) kind = tr.ref == kNone ? 0u : 1u + (__ldg(sc.slot_mat + (tr.ref & kSlotMask)) >> 24);
     }
+    if (DENSE) return;  // window mode: k_shade walks the windows, there is no per-kind queue
     if (!__any_sync(0xffffffffu, fin)) return;
     const uint32_t peers = __match_any_sync(0xffffffffu, kind);
     if (fin) {
@@ -314,13 +328,13 @@ struct TraceRetire {
 #ifndef PTB_SHADE_MIN_BLOCKS
 #define PTB_SHADE_MIN_BLOCKS 2  // caps k_shade<MIS> at 128 registers (2 x 256 threads per SM): +6 % on rtweekend1 4K
 #endif
-template <bool COUNT>
+template <bool COUNT, bool DENSE>
 __global__ void __launch_bounds__(256, PTB_TRACE_MIN_BLOCKS)
 k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t cnt_nodes = 0, cnt_prims = 0, cnt_rays = 0;
-  TraceFetch fetch{pool, q.active[wc->cur], 0u};
-  TraceRetire retire{sc, pool, q, wc, fetch};
+  TraceFetch fetch{pool, q.active[DENSE ? 0u : wc->cur], 0u};
+  TraceRetire<DENSE> retire{sc, pool, q, wc, fetch};
   persistent_trace<false, COUNT>(sc, wc->n_trace, &wc->trace_head, fetch, retire, cnt_nodes, cnt_prims, cnt_rays);
   if (COUNT) {
     for (int off = 16; off > 0; off >>= 1) {
@@ -460,32 +474,74 @@ PTB_DEV v3 mat_eval(const DevScene& sc, const Surface& s, v3 wo, v3 wi) {
   return col;
 }
 
-PTB_DEV void finish_path(float* __restrict__ accum, uint32_t pixel, v3 L, bool nan_check) {
-  if (nan_check && (contains_nan(L) || !any_finite(L))) return;  // integrators/mod.rs:74-76, mis.rs:88-90
-  atomicAdd(accum + 3u * (size_t)pixel + 0, L.x);
-  atomicAdd(accum + 3u * (size_t)pixel + 1, L.y);
-  atomicAdd(accum + 3u * (size_t)pixel + 2, L.z);
+// Adds the radiance of the paths that finished in this warp iteration to the accumulator. Called by all 32 lanes.
+// The samples of a pixel are issued back to back, so the finishing lanes of a warp usually share ONE pixel: their sum
+// is formed with shuffles and added with three atomics instead of 3 x 32 same-address ones.
+PTB_DEV void finish_paths(float* __restrict__ accum, bool contributes, uint32_t pixel, v3 L) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t m = __ballot_sync(0xffffffffu, contributes);
+  if (!m) return;
+  const uint32_t peers = __match_any_sync(0xffffffffu, contributes ? pixel : 0xffffffffu);
+  if (__all_sync(0xffffffffu, !contributes || peers == m)) {
+    if (!contributes) L = mk(0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      L.x += __shfl_xor_sync(0xffffffffu, L.x, o);
+      L.y += __shfl_xor_sync(0xffffffffu, L.y, o);
+      L.z += __shfl_xor_sync(0xffffffffu, L.z, o);
+    }
+    if (lane == (uint32_t)__ffs(m) - 1u) {
+      atomicAdd(accum + 3u * (size_t)pixel + 0, L.x);
+      atomicAdd(accum + 3u * (size_t)pixel + 1, L.y);
+      atomicAdd(accum + 3u * (size_t)pixel + 2, L.z);
+    }
+  } else if (contributes) {
+    atomicAdd(accum + 3u * (size_t)pixel + 0, L.x);
+    atomicAdd(accum + 3u * (size_t)pixel + 1, L.y);
+    atomicAdd(accum + 3u * (size_t)pixel + 2, L.z);
+  }
 }
 
-template <int METHOD, bool FULL>
+// 5-bit direction bin of a unit vector: octant (signs) x dominant axis. Window-mode k_shade orders the surviving paths of
+// a window by it, so the 32 consecutive rays a k_trace warp fetches share a pixel AND roughly a direction.
+PTB_DEV uint32_t direction_bin(v3 d) {
+  const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  const uint32_t major = ax >= ay ? (ax >= az ? 0u : 2u) : (ay >= az ? 1u : 2u);
+  return ((d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u)) * 4u + major;
+}
+
+// DENSE = window mode (ordered live-slot queue in, per-slot direction bin and per-window live count out), else the
+// per-material-kind queues of the regenerating queue mode.
+template <int METHOD, bool FULL, bool DENSE>
 __global__ void __launch_bounds__(256, PTB_SHADE_MIN_BLOCKS)
 k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum) {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t nxt = wc->cur ^ 1u;
   uint32_t n_kind[kNumKinds], n_total = 0;
+  if (DENSE) {
+    n_total = wc->n_trace;
+  } else {
 #pragma unroll
-  for (int k = 0; k < kNumKinds; ++k) { n_kind[k] = wc->n_kind[k]; n_total += n_kind[k]; }
-  // grid-stride over the concatenation of the kind queues; whole blocks iterate together (ballots below)
+    for (int k = 0; k < kNumKinds; ++k) { n_kind[k] = wc->n_kind[k]; n_total += n_kind[k]; }
+  }
+  // queue mode: grid-stride over the concatenation of the kind queues; window mode: over the ordered live-slot queue.
+  // Whole blocks iterate together (ballots below).
   for (uint32_t base = blockIdx.x * blockDim.x; base < n_total; base += gridDim.x * blockDim.x) {
   const uint32_t i = base + threadIdx.x;
-  uint32_t total = 0, kq = kNumKinds, off = 0;
+  uint32_t kq = kNumKinds, off = 0;
+  bool active;
+  if (DENSE) {
+    active = i < n_total;
+  } else {
+    uint32_t total = 0;
 #pragma unroll
-  for (int k = 0; k < kNumKinds; ++k) {
-    const uint32_t c = n_kind[k];
-    if (kq == (uint32_t)kNumKinds && i < total + c) { kq = k; off = i - total; }
-    total += c;
+    for (int k = 0; k < kNumKinds; ++k) {
+      const uint32_t c = n_kind[k];
+      if (kq == (uint32_t)kNumKinds && i < total + c) { kq = k; off = i - total; }
+      total += c;
+    }
+    active = kq != (uint32_t)kNumKinds;
   }
-  const bool active = kq != (uint32_t)kNumKinds;
 
   bool alive = false;     // path continues: goes to the next active queue
   bool finished = false;  // path ended: slot returns to the free list
@@ -493,9 +549,12 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
   uint32_t slot = 0;
   float4 sh_o, sh_d, sh_c;
   uint32_t shadow_is_sky = 0;
+  bool contributes = false;  // finished with a radiance that passes the NaN test (integrators/mod.rs:74-76, mis.rs:88-90)
+  uint32_t fin_pixel = 0;
+  v3 fin_L = mk(0.0f, 0.0f, 0.0f);
 
   if (active) {
-    slot = q.kind[kq][off];
+    slot = DENSE ? q.active[0][i] : q.kind[kq][off];
     float4 ro, rd, th, ra;
     ldg256_rw(pool.ray + 4u * (size_t)slot, ro, rd);
     ldg256_rw(pool.col + 4u * (size_t)slot, th, ra);
@@ -729,11 +788,38 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
                make_float4(nd.x, nd.y, nd.z, __uint_as_float(kNone)));
         stg256(pool.col + 4u * (size_t)slot, make_float4(T.x, T.y, T.z, th.w),
                make_float4(L.x, L.y, L.z, __uint_as_float((sample << 9) | (delta ? kFlagPrevDelta : 0u) | depth)));
+        if (DENSE) q.bin[slot] = (uint8_t)direction_bin(nd);
       }
     }
-    if (finished) finish_path(accum, pixel, L, nan_check);
+    if (finished) {
+      contributes = !(nan_check && (contains_nan(L) || !any_finite(L)));
+      fin_pixel = pixel;
+      fin_L = L;
+    }
   }
+  finish_paths(accum, contributes, fin_pixel, fin_L);
 
+  if (DENSE) {
+    // ---- window mode: paths stay in their slot. A finished path is marked dead and leaves its window's live count
+    // (lanes of a warp nearly always share the window: one atomic per warp); NEE rays go to the shadow queue.
+    if (finished) q.bin[slot] = (uint8_t)kBinDead;
+    const uint32_t window = slot / kWindow;
+    const uint32_t peers = __match_any_sync(0xffffffffu, finished ? window : 0xffffffffu);
+    if (finished && lane == (uint32_t)__ffs(peers) - 1u) atomicSub(&q.win_count[window], (uint32_t)__popc(peers));
+    if (METHOD == PTB_METHOD_MIS) {
+      const uint32_t m_sh = __ballot_sync(0xffffffffu, shadow), m_sky = __ballot_sync(0xffffffffu, shadow && shadow_is_sky);
+      unsigned long long p2 = 0ull;
+      if (lane == 0u && m_sh)
+        p2 = atomicAdd(&wc->shadow_pair, ((unsigned long long)__popc(m_sky) << 32) | (unsigned long long)__popc(m_sh));
+      p2 = __shfl_sync(0xffffffffu, p2, 0);
+      if (shadow) {
+        float4* e = q.shadow + 3u * (size_t)((uint32_t)p2 + __popc(m_sh & ((1u << lane) - 1u)));
+        e[0] = sh_o;
+        e[1] = sh_d;
+        e[2] = sh_c;
+      }
+    }
+  } else {
   // ---- warp-aggregated queue pushes: lane 0 issues both returning atomics back to back (their round trips overlap)
   {
     const uint32_t m_alive = __ballot_sync(0xffffffffu, alive), m_fin = __ballot_sync(0xffffffffu, finished);
@@ -760,7 +846,153 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
       }
     }
   }
+  }
   }  // grid-stride
+}
+
+// ------------------------------------------------------------------------------------------ window wavefront
+// When every camera path of a chunk fits the pool, the wavefront needs no free list and no compaction of scattered slots:
+// path g of the chunk lives in slot g for its whole life (pixel-major, the samples of a pixel adjacent), and each
+// iteration's trace queue is rebuilt IN SLOT ORDER from per-slot state: k_shade leaves a direction bin (or "dead") per
+// slot and keeps a live count per 256-slot window; a prefix sum over the window counts places every window's live slots
+// in the queue, ordered by direction bin inside the window. Consequences, all measured (profiles/r1_sweeps.md): the rays a
+// k_trace warp fetches share a pixel (origin) and roughly a direction at every depth, path records are gathered from one
+// 16 KB window at a time instead of from the whole pool, and iteration k holds exactly the rays of bounce k.
+//   k_win_generate   camera paths of the chunk, slot = index; window counts, bins
+//   k_win_scan       per 4096-window segment: exclusive prefix of the counts + segment total
+//   k_win_prepare    1 warp: statistics of the finished iteration, total of live paths, cursor resets
+//   k_win_fill       ordered live-slot queue (one warp per window: counting sort of its live slots by direction bin)
+__global__ void __launch_bounds__(256)
+k_win_generate(DevScene sc, PathPool pool, Queues q, RenderParams rp, unsigned long long first_path, uint32_t n_paths) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += gridDim.x * blockDim.x) {
+    emit_camera_path(sc, pool, rp, first_path + i, i);
+    q.bin[i] = 0;  // camera rays of a window are coherent as they are
+    if ((i & (kWindow - 1u)) == 0u) q.win_count[i / kWindow] = n_paths - i < kWindow ? n_paths - i : kWindow;
+  }
+}
+
+__global__ void __launch_bounds__(1024) k_win_scan(Queues q) {
+  __shared__ uint32_t warp_sum[32];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t w0 = blockIdx.x * kSegWindows + threadIdx.x * 4u;
+  uint32_t c[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c[k] = w0 + k < q.n_windows ? q.win_count[w0 + k] : 0u;
+  const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+  uint32_t inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += t;
+  }
+  if (lane == 31u) warp_sum[warp] = inc;
+  __syncthreads();
+  if (warp == 0u) {
+    const uint32_t v = warp_sum[lane];
+    uint32_t winc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= (uint32_t)o) winc += t;
+    }
+    warp_sum[lane] = winc - v;
+    if (lane == 31u) q.seg_total[blockIdx.x] = winc;
+  }
+  __syncthreads();
+  uint32_t run = warp_sum[warp] + inc - mine;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (w0 + k < q.n_windows) q.win_prefix[w0 + k] = run;
+    run += c[k];
+  }
+}
+
+// `prev` = what the finished iteration traced: 0 nothing (first of a chunk), 1 camera rays, 2 bounce rays
+__global__ void k_win_prepare(WaveCounters* wc, Queues q, uint32_t n_segments, uint32_t method, uint32_t prev) {
+  const uint32_t lane = threadIdx.x;
+  uint32_t total = 0;
+  for (uint32_t s = lane; s < n_segments; s += 32u) total += q.seg_total[s];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  if (lane != 0u) return;
+  if (prev) {
+    const uint32_t traced = wc->n_trace, survivors = total;
+    const unsigned long long sp = wc->shadow_pair;
+    wc->rays_shadow_sky += sp >> 32;
+    wc->rays_shadow_light += (uint32_t)sp - (uint32_t)(sp >> 32);
+    if (prev == 1u) wc->rays_camera += traced;
+    else wc->rays_bounce += traced;
+    wc->rays_reference += method == PTB_METHOD_NAIVE ? traced : survivors;  // Q7, as k_prepare
+    wc->paths += traced - survivors;
+  }
+  wc->n_trace = total;
+  wc->cur = 0;
+  wc->shadow_pair = 0;
+  wc->trace_head = wc->shade_head = wc->shadow_head = 0;
+}
+
+__global__ void __launch_bounds__(256) k_win_fill(Queues q, WaveCounters* wc) {
+  __shared__ uint32_t s_hist[8][33];  // per warp: bin counts, then running output offsets
+  const uint32_t lane = threadIdx.x & 31u, warp_in_block = threadIdx.x >> 5;
+  uint32_t* hist = s_hist[warp_in_block];
+  const uint32_t n_groups = (q.n_windows + 31u) / 32u;
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  uint32_t seg_cached = 0xffffffffu, seg_base = 0;
+  for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + warp_in_block; g < n_groups; g += warps) {
+    const uint32_t w = g * 32u + lane;
+    const uint32_t cnt = w < q.n_windows ? q.win_count[w] : 0u;
+    const uint32_t m = __ballot_sync(0xffffffffu, cnt != 0u);
+    if (!m) continue;
+    const uint32_t seg = (g * 32u) / kSegWindows;  // 32 divides kSegWindows: one segment per group
+    if (seg != seg_cached) {
+      uint32_t b = 0;
+      for (uint32_t s = lane; s < seg; s += 32u) b += q.seg_total[s];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+      seg_base = b;
+      seg_cached = seg;
+    }
+    const uint32_t start = cnt ? seg_base + q.win_prefix[w] : 0u;
+    for (uint32_t rest = m; rest; rest &= rest - 1u) {
+      const int b = __ffs(rest) - 1;
+      const uint32_t out = __shfl_sync(0xffffffffu, start, b);
+      const uint32_t first_slot = (g * 32u + (uint32_t)b) * kWindow;
+      // the window's 256 bin bytes, 8 consecutive slots per lane
+      const uint2 raw = *reinterpret_cast<const uint2*>(q.bin + first_slot + lane * 8u);
+      uint32_t bins[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bins[k] = ((k < 4 ? raw.x : raw.y) >> (8 * (k & 3))) & 0xFFu;
+      hist[lane] = 0u;
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool live = bins[k] != kBinDead;
+        const uint32_t peers = __match_any_sync(0xffffffffu, live ? bins[k] : 0x100u + lane);
+        if (live && lane == (uint32_t)__ffs(peers) - 1u) hist[bins[k]] += __popc(peers);
+        __syncwarp();
+      }
+      {  // exclusive scan over the 32 bins -> running offsets
+        const uint32_t c = hist[lane];
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= (uint32_t)o) inc += t;
+        }
+        hist[lane] = out + inc - c;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool live = bins[k] != kBinDead;
+        const uint32_t peers = __match_any_sync(0xffffffffu, live ? bins[k] : 0x100u + lane);
+        if (live) q.active[0][hist[bins[k]] + __popc(peers & ((1u << lane) - 1u))] = first_slot + lane * 8u + (uint32_t)k;
+        __syncwarp();
+        if (live && lane == (uint32_t)__ffs(peers) - 1u) hist[bins[k]] += __popc(peers);
+        __syncwarp();
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ K9 shadow rays
@@ -883,9 +1115,11 @@ int32_t launch_closest_hit(Ctx* c, const void* d_rays, size_t n, void* d_hits) {
   return PTB_OK;
 }
 
-static unsigned long long bytes_per_path(bool mis) {
-  // 64-byte path block + queues (2 active, free, kNumKinds shade queues) + MIS: previous-hit record, 48-byte shadow entry
-  return 64ull + 4ull * (3 + kNumKinds) + (mis ? 16ull + 48ull : 0ull);
+// bytes of device state per path in flight
+static unsigned long long bytes_per_path(bool mis, bool windows) {
+  // 64-byte path block + queues (window mode: the live-slot queue; queue mode: 2 active, free, kNumKinds shade queues)
+  // + MIS: previous-hit record, 48-byte shadow entry
+  return 64ull + (windows ? 4ull + 1ull : 4ull * (3 + kNumKinds)) + (mis ? 16ull + 48ull : 0ull);
 }
 
 void free_render_state(Ctx* c) {
@@ -893,76 +1127,106 @@ void free_render_state(Ctx* c) {
   c->d_prev.release();
   c->d_queues.release();
   c->d_shadow.release();
-  c->pool_has_mis = false;
+  c->d_windows.release();
   c->pool = PathPool();
 }
 
-// Paths in flight. The wavefront is fastest when EVERY camera path of the call is resident: the iterations then become
-// depth-synchronous (iteration k traces bounce k of all paths: camera rays, the coherent half of the work, run together at
-// 5 Grays/s), there are ~55 launches per render instead of ~110, and only one tail. Measured on B200, C3 at 256 spp per
-// call (profiles/r1_sweeps.md): 16 Mi paths 2264 Mrays/s, 64 Mi 2461, 128 Mi 2612, 256 Mi 2760, 512 Mi 2839. Path state is
-// 100 B per path (naive) / 164 B (MIS: + previous-hit record and shadow queue), so the default of 256 Mi paths takes
-// 27 / 44 GB of the B200's 180 GB; the pool never takes more than half of the free device memory. PTB_POOL_PATHS overrides.
-static uint32_t pool_capacity_for(Ctx* c, unsigned long long total, bool mis) {
-  unsigned long long cap = 1ull << 28;
+// Paths in flight. The wavefront is fastest when EVERY camera path of the call is resident: iteration k then traces bounce
+// k of all paths (camera rays, the coherent half of the work, run together), there are ~55 launches per render instead of
+// ~110 and only one tail. Measured on B200, C3 at 256 spp per call, queue mode (profiles/r1_sweeps.md): 16 Mi paths 2264
+// Mrays/s, 64 Mi 2461, 128 Mi 2612, 256 Mi 2760, 512 Mi 2839. Default: up to 512 Mi paths, never more than half of the
+// device memory that was free at the context's first large render (68 B per path in window mode, 132 B with MIS).
+// PTB_POOL_PATHS overrides.
+static uint32_t pool_capacity_for(Ctx* c, unsigned long long total, bool mis, bool windows) {
+  unsigned long long cap = 1ull << 29;
   bool forced = false;
   if (const char* e = getenv("PTB_POOL_PATHS")) {
     unsigned long long v = strtoull(e, nullptr, 10);
     if (v >= 1024 && v <= (1ull << 29)) { cap = v; forced = true; }
   }
   if (!forced && total > (1ull << 24)) {
-    // asked once per context (cudaMemGetInfo costs milliseconds once tens of GB are allocated): the budget is half of
-    // what was free before this context's first large pool
+    // asked once per context (cudaMemGetInfo costs milliseconds once tens of GB are allocated)
     if (c->pool_budget_bytes == 0) {
       size_t free_b = 0, total_b = 0;
       c->pool_budget_bytes = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? free_b / 2 + 1 : ~(size_t)0;
     }
-    const unsigned long long per_path = bytes_per_path(mis);
+    const unsigned long long per_path = bytes_per_path(mis, windows);
     while (cap > (1ull << 24) && cap * per_path > c->pool_budget_bytes) cap >>= 1;
   }
   if (total < cap) cap = total < 1024 ? 1024 : total;
   return (uint32_t)((cap + 255ull) & ~255ull);
 }
 
+struct RenderSetup {
+  RenderParams rp;
+  Queues q;
+  WaveCounters* wc;
+  float* accum;
+  uint32_t P;
+  bool mis, full, count, prof;
+};
+
+static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderSetup& rs, ptb_progress_fn progress, void* user);
+static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const RenderSetup& rs, ptb_progress_fn progress, void* user);
+
 int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progress, void* user) {
-  cudaStream_t st = c->stream;
   const uint32_t npix = o.width * o.height;
   const unsigned long long total = (unsigned long long)npix * o.samples_per_pixel;
   if (total == 0) return PTB_OK;
-  const bool mis = o.method == PTB_METHOD_MIS;
-  const uint32_t P = pool_capacity_for(c, total, mis);
+  RenderSetup rs;
+  rs.mis = o.method == PTB_METHOD_MIS;
+  // Window mode (default) needs chunks long enough to amortise their ~50-launch tail: the whole call in one chunk, or
+  // chunks of at least 32 Mi paths. PTB_WAVEFRONT=queue forces the regenerating queue mode.
+  bool windows = true;
+  if (const char* e = getenv("PTB_WAVEFRONT")) windows = strcmp(e, "queue") != 0;
+  uint32_t P = pool_capacity_for(c, total, rs.mis, windows);
+  if (windows && total > P && P < (1u << 25)) {
+    windows = false;
+    P = pool_capacity_for(c, total, rs.mis, false);
+  }
+  rs.P = P;
 
   // ---- device state (grow-only across calls; the MIS-only arrays are allocated by the first MIS call)
-  if (c->pool.capacity != P || (mis && !c->pool_has_mis)) {
-    c->pool.capacity = 0;
-    // one 64-byte block per path: ray record then colour record (a DRAM access atom; two scattered 32-byte sectors
-    // per path cost generate/shade ~1 TB/s of effective write bandwidth)
-    PTB_CUDA_TRY(c, c->d_pool_mem.reserve((size_t)P * 64));
-    c->pool.ray = c->d_pool_mem.as<float4>();
-    c->pool.col = c->pool.ray + 2;
-    PTB_CUDA_TRY(c, c->d_queues.reserve((size_t)P * 4 * (3 + kNumKinds)));
-    if (mis || c->pool_has_mis) {
-      PTB_CUDA_TRY(c, c->d_prev.reserve((size_t)P * 16));
-      PTB_CUDA_TRY(c, c->d_shadow.reserve((size_t)P * 48));
-      c->pool_has_mis = true;
-    }
-    c->pool.prev = c->d_prev.as<float4>();
-    c->pool.capacity = P;
+  // one 64-byte block per path: ray record then colour record (a DRAM access atom; two scattered 32-byte sectors per
+  // path cost generate/shade ~1 TB/s of effective write bandwidth)
+  PTB_CUDA_TRY(c, c->d_pool_mem.reserve((size_t)P * 64));
+  c->pool.capacity = P;
+  c->pool.ray = c->d_pool_mem.as<float4>();
+  c->pool.col = c->pool.ray + 2;
+  PTB_CUDA_TRY(c, c->d_queues.reserve((size_t)P * 4 * (windows ? 1 : 3 + kNumKinds)));
+  if (rs.mis) {
+    PTB_CUDA_TRY(c, c->d_prev.reserve((size_t)P * 16));
+    PTB_CUDA_TRY(c, c->d_shadow.reserve((size_t)P * 48));
   }
+  c->pool.prev = c->d_prev.as<float4>();
   PTB_CUDA_TRY(c, c->d_counters.reserve(sizeof(WaveCounters) + 64));
-  Queues q;
+  Queues& q = rs.q;
   {
     uint32_t* b = c->d_queues.as<uint32_t>();
     q.active[0] = b; b += P;
-    q.active[1] = b; b += P;
-    q.free_slots = b; b += P;
-    for (int k = 0; k < kNumKinds; ++k) { q.kind[k] = b; b += P; }
+    if (windows) b = c->d_queues.as<uint32_t>();  // window mode uses active[0] only
+    q.active[1] = b; b += windows ? 0 : P;
+    q.free_slots = b; b += windows ? 0 : P;
+    for (int k = 0; k < kNumKinds; ++k) { q.kind[k] = b; b += windows ? 0 : P; }
     q.shadow = c->d_shadow.as<float4>();
+    q.n_windows = P / kWindow;  // P is a multiple of 256
+    const size_t n_seg = (q.n_windows + kSegWindows - 1) / kSegWindows;
+    q.win_count = q.win_prefix = q.seg_total = nullptr;
+    q.bin = nullptr;
+    if (windows) {
+      const size_t words = ((size_t)q.n_windows * 2 + n_seg + 3) & ~(size_t)3;  // keeps the byte array 16-byte aligned
+      PTB_CUDA_TRY(c, c->d_windows.reserve(words * 4 + (size_t)P));
+      uint32_t* w = c->d_windows.as<uint32_t>();
+      q.win_count = w;
+      q.win_prefix = w + q.n_windows;
+      q.seg_total = w + 2 * (size_t)q.n_windows;
+      q.bin = reinterpret_cast<uint8_t*>(w + words);  // k_win_fill reads a window's 256 bytes as 32 x uint2
+    }
   }
-  WaveCounters* wc = c->d_counters.as<WaveCounters>();
+  rs.wc = c->d_counters.as<WaveCounters>();
   if (!c->h_counters) PTB_CUDA_TRY(c, cudaMallocHost(&c->h_counters, 2 * sizeof(WaveCounters)));
 
-  RenderParams rp;
+  RenderParams& rp = rs.rp;
   rp.width = o.width; rp.height = o.height; rp.npix = npix;
   rp.tile_w = 32u; rp.tile_h = 1u;
   // Measured on B200 (C3 and rtweekend1 4K): 8x4 tiles gain nothing in k_trace (-2 %) and cost 5 % in k_shade (less
@@ -970,6 +1234,8 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   if (getenv("PTB_TILES"))
     for (uint32_t th = 4u; th > 1u; th >>= 1)
       if (o.height % th == 0u && o.width % (32u / th) == 0u) { rp.tile_h = th; rp.tile_w = 32u / th; break; }
+  // samples of one pixel issued back to back: the largest divisor of spp <= 1024 (PTB_SAMPLE_GROUP). Measured on C3 at
+  // 256 spp: group 1 -> 2760 Mrays/s, 32 -> 3066, 256 -> 3197 (camera rays of a warp walk the same nodes).
   rp.group = 1u;
   {
     uint32_t want = 1024u;
@@ -986,7 +1252,160 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   rp.rr_threshold = o.rr_threshold == PTB_RR_DEFAULT ? 3u : o.rr_threshold;
   rp.k0 = (uint32_t)o.seed; rp.k1 = (uint32_t)(o.seed >> 32);
 
-  float* accum = c->accum_target ? c->accum_target : c->d_accum.as<float>();
+  rs.accum = c->accum_target ? c->accum_target : c->d_accum.as<float>();
+  rs.full = c->scene_needs_full_shade;
+  rs.count = c->opt_count_traversal;
+  rs.prof = c->opt_time_kernels;
+  if (rs.prof)
+    for (cudaEvent_t& e : c->ev_prof)
+      if (!e) PTB_CUDA_TRY(c, cudaEventCreate(&e));
+  return windows ? render_window_mode(c, o, rs, progress, user) : render_queue_mode(c, o, rs, progress, user);
+}
+
+// ev_prof[(iter & 1) * 8 + 2 * k + {0,1}] brackets kernel class k (0 generate + bookkeeping, 1 trace, 2 shade, 3 shadow)
+#define PTB_PROF(k, which) \
+  if (prof) cudaEventRecord(c->ev_prof[(int)(iter & 1u) * 8 + 2 * (k) + (which)], st)
+static void prof_collect(Ctx* c, int half, bool mis) {
+  double* prof_ms[4] = {&c->stats.ms_generate, &c->stats.ms_trace, &c->stats.ms_shade, &c->stats.ms_shadow};
+  for (int k = 0; k < (mis ? 4 : 3); ++k) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_prof[half * 8 + 2 * k], c->ev_prof[half * 8 + 2 * k + 1]) == cudaSuccess)
+      *prof_ms[k] += ms;
+  }
+}
+static void fold_counters(Ctx* c, const WaveCounters& h, uint64_t iterations) {
+  c->stats.nodes_fetched += h.nodes_fetched;
+  c->stats.prims_tested += h.prims_tested;
+  c->stats.rays_counted += h.rays_counted;
+  c->stats.rays_camera += h.rays_camera;
+  c->stats.rays_bounce += h.rays_bounce;
+  c->stats.rays_shadow_light += h.rays_shadow_light;
+  c->stats.rays_shadow_sky += h.rays_shadow_sky;
+  c->stats.rays_reference += h.rays_reference;
+  c->stats.paths += h.paths;
+  c->stats.wavefront_iterations += iterations;
+}
+template <bool DENSE>
+static void launch_shade(const RenderSetup& rs, Ctx* c, uint32_t grid, int threads, cudaStream_t st) {
+  const Queues& q = rs.q;
+  if (rs.mis) {
+    if (rs.full) k_shade<PTB_METHOD_MIS, true, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum);
+    else k_shade<PTB_METHOD_MIS, false, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum);
+  } else {
+    if (rs.full) k_shade<PTB_METHOD_NAIVE, true, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum);
+    else k_shade<PTB_METHOD_NAIVE, false, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum);
+  }
+}
+template <bool DENSE>
+static const void* shade_fn(const RenderSetup& rs) {
+  return rs.mis ? (rs.full ? (const void*)k_shade<PTB_METHOD_MIS, true, DENSE> : (const void*)k_shade<PTB_METHOD_MIS, false, DENSE>)
+                : (rs.full ? (const void*)k_shade<PTB_METHOD_NAIVE, true, DENSE> : (const void*)k_shade<PTB_METHOD_NAIVE, false, DENSE>);
+}
+
+// ---- window mode: chunk by chunk, every path of a chunk resident, one bounce of all of them per iteration
+static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const RenderSetup& rs, ptb_progress_fn progress, void* user) {
+  cudaStream_t st = c->stream;
+  const Queues& q = rs.q;
+  WaveCounters* wc = rs.wc;
+  const uint32_t npix = rs.rp.npix, P = rs.P;
+  const unsigned long long total = (unsigned long long)npix * o.samples_per_pixel;
+  const bool mis = rs.mis, prof = rs.prof, count = rs.count;
+  const int T = 256;
+  const uint32_t n_seg = (q.n_windows + kSegWindows - 1) / kSegWindows;
+  auto capped = [&](const void* k, uint32_t items_per_block, uint32_t items) {
+    const uint32_t g = (uint32_t)persistent_grid(c, k, T), need = (items + items_per_block - 1) / items_per_block;
+    return g < need ? g : (need ? need : 1u);
+  };
+  const uint32_t grid_fill = capped((const void*)k_win_fill, 32u * (T / 32), q.n_windows);
+  // k_shade is register-heavy (MIS: ~130): smaller blocks let more of them share an SM's register file
+  int TS = mis ? 128 : 256;
+  if (const char* e = getenv("PTB_SHADE_THREADS")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) TS = v; }
+  uint32_t grid_shade = (uint32_t)persistent_grid(c, shade_fn<true>(rs), TS);
+  if (grid_shade > (P + TS - 1) / TS) grid_shade = (P + TS - 1) / TS;
+  const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true, true> : (const void*)k_trace<false, true>, T);
+  const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
+
+  PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
+  k_init_pool<<<1, 32, 0, st>>>(q.active[0], 0u, wc, total);  // counters only
+  c->stats.kernel_launches += 1;
+  int32_t rc = PTB_OK;
+  uint64_t iter = 0;
+  cudaEvent_t ev[2] = {c->ev_iter, c->ev_b};
+  for (unsigned long long first = 0; first < total && rc == PTB_OK; first += P) {
+    const uint32_t n_paths = (uint32_t)(total - first < P ? total - first : P);
+    PTB_CUDA_TRY(c, cudaMemsetAsync(q.win_count, 0, (size_t)q.n_windows * 4, st));
+    if (n_paths % kWindow)  // slots of the last window that hold no path
+      PTB_CUDA_TRY(c, cudaMemsetAsync(q.bin + n_paths, (int)kBinDead, kWindow - n_paths % kWindow, st));
+    PTB_PROF(0, 0);
+    k_win_generate<<<capped((const void*)k_win_generate, T, n_paths), T, 0, st>>>(c->dev, c->pool, q, rs.rp, first, n_paths);
+    c->stats.kernel_launches += 1;
+    bool done = false;
+    for (uint64_t depth = 0; !done; ++depth, ++iter) {
+      if (depth) PTB_PROF(0, 0);
+      k_win_scan<<<n_seg, 1024, 0, st>>>(q);
+      k_win_prepare<<<1, 32, 0, st>>>(wc, q, n_seg, o.method, depth == 0 ? 0u : (depth == 1 ? 1u : 2u));
+      k_win_fill<<<grid_fill, T, 0, st>>>(q, wc);
+      PTB_PROF(0, 1);
+      PTB_PROF(1, 0);
+      if (count) k_trace<true, true><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
+      else k_trace<false, true><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
+      PTB_PROF(1, 1);
+      PTB_PROF(2, 0);
+      launch_shade<true>(rs, c, grid_shade, TS, st);
+      PTB_PROF(2, 1);
+      c->stats.kernel_launches += 5;
+      c->stats.trace_launches += 1;
+      if (mis) {
+        PTB_PROF(3, 0);
+        k_shadow<<<grid_shadow, T, 0, st>>>(c->dev, c->pool, q, wc);
+        PTB_PROF(3, 1);
+        c->stats.kernel_launches += 1;
+      }
+      // two pinned mirrors + events: the host inspects iteration k-1 while iteration k runs
+      const int slot = (int)(iter & 1u);
+      PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + slot, wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+      PTB_CUDA_TRY(c, cudaEventRecord(ev[slot], st));
+      if (depth > 0) {
+        const int ps = slot ^ 1;
+        PTB_CUDA_TRY(c, cudaEventSynchronize(ev[ps]));
+        if (prof) prof_collect(c, ps, mis);
+        if (c->h_counters[ps].n_trace == 0u) done = true;  // iteration depth-1 had nothing left to trace
+      }
+      if (depth > 4096) return set_error(c, PTB_ERR_INVALID, "wavefront did not terminate");
+    }
+    // the iteration launched last is empty as well (its k_win_prepare folded the statistics of the last real one)
+    PTB_CUDA_TRY(c, cudaEventSynchronize(ev[(int)((iter - 1) & 1u)]));
+    if (prof) prof_collect(c, (int)((iter - 1) & 1u), mis);
+    if (progress && first + n_paths < total) {
+      const WaveCounters& h = c->h_counters[(int)((iter - 1) & 1u)];
+      if (progress(user, (first + n_paths) / npix, h.rays_reference)) rc = PTB_ERR_ABORTED;
+    }
+  }
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+  PTB_CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
+  PTB_CUDA_TRY(c, cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+  const WaveCounters& h = c->h_counters[0];
+  fold_counters(c, h, iter);
+  c->stats.render_ms = ms;
+  if (rc == PTB_OK) {
+    c->accum_samples += o.samples_per_pixel;
+    if (progress) progress(user, o.samples_per_pixel, h.rays_reference);
+  }
+  return rc;
+}
+
+// ---- queue mode: a pool smaller than the call; freed slots are refilled with new camera paths every iteration
+static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderSetup& rs, ptb_progress_fn progress, void* user) {
+  cudaStream_t st = c->stream;
+  const Queues& q = rs.q;
+  WaveCounters* wc = rs.wc;
+  const RenderParams& rp = rs.rp;
+  const uint32_t npix = rp.npix, P = rs.P;
+  const unsigned long long total = (unsigned long long)npix * o.samples_per_pixel;
+  const bool mis = rs.mis, prof = rs.prof, count = rs.count;
   const int T = 256;
   const uint32_t grid_p = (P + T - 1) / T;
   auto capped = [&](const void* k) { const int g = persistent_grid(c, k, T); return (uint32_t)g < grid_p ? (uint32_t)g : grid_p; };
@@ -994,29 +1413,10 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   // k_shade is register-heavy (MIS: ~130): smaller blocks let more of them share an SM's register file
   int TS = mis ? 128 : 256;
   if (const char* e = getenv("PTB_SHADE_THREADS")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) TS = v; }
-  const bool full = c->scene_needs_full_shade;
-  const void* shade_fn = mis ? (full ? (const void*)k_shade<PTB_METHOD_MIS, true> : (const void*)k_shade<PTB_METHOD_MIS, false>)
-                             : (full ? (const void*)k_shade<PTB_METHOD_NAIVE, true> : (const void*)k_shade<PTB_METHOD_NAIVE, false>);
-  uint32_t grid_shade = (uint32_t)persistent_grid(c, shade_fn, TS);
+  uint32_t grid_shade = (uint32_t)persistent_grid(c, shade_fn<false>(rs), TS);
   if (grid_shade > (P + TS - 1) / TS) grid_shade = (P + TS - 1) / TS;
-  const bool count = c->opt_count_traversal;
-  const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true> : (const void*)k_trace<false>, T);
+  const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true, false> : (const void*)k_trace<false, false>, T);
   const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
-  const bool prof = c->opt_time_kernels;
-  if (prof)
-    for (cudaEvent_t& e : c->ev_prof)
-      if (!e) PTB_CUDA_TRY(c, cudaEventCreate(&e));
-  // ev_prof[(iter & 1) * 8 + 2 * k + {0,1}] brackets kernel class k (0 generate, 1 trace, 2 shade, 3 shadow)
-  double* prof_ms[4] = {&c->stats.ms_generate, &c->stats.ms_trace, &c->stats.ms_shade, &c->stats.ms_shadow};
-  auto prof_collect = [&](int half) {
-    for (int k = 0; k < (mis ? 4 : 3); ++k) {
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, c->ev_prof[half * 8 + 2 * k], c->ev_prof[half * 8 + 2 * k + 1]) == cudaSuccess)
-        *prof_ms[k] += ms;
-    }
-  };
-#define PTB_PROF(k, which) \
-  if (prof) cudaEventRecord(c->ev_prof[(int)(iter & 1u) * 8 + 2 * (k) + (which)], st)
 
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
   k_init_pool<<<grid_p, T, 0, st>>>(q.free_slots, P, wc, total);
@@ -1035,17 +1435,11 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
     PTB_PROF(0, 1);
     k_advance<<<1, 1, 0, st>>>(wc);
     PTB_PROF(1, 0);
-    if (count) k_trace<true><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
-    else k_trace<false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
+    if (count) k_trace<true, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
+    else k_trace<false, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
     PTB_PROF(1, 1);
     PTB_PROF(2, 0);
-    if (mis) {
-      if (full) k_shade<PTB_METHOD_MIS, true><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
-      else k_shade<PTB_METHOD_MIS, false><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
-    } else {
-      if (full) k_shade<PTB_METHOD_NAIVE, true><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
-      else k_shade<PTB_METHOD_NAIVE, false><<<grid_shade, TS, 0, st>>>(c->dev, c->pool, q, wc, rp, accum);
-    }
+    launch_shade<false>(rs, c, grid_shade, TS, st);
     PTB_PROF(2, 1);
     c->stats.kernel_launches += 5;
     c->stats.trace_launches += 1;
@@ -1061,7 +1455,7 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
     if (iter > 0) {  // inspect the previous iteration (already finished or about to)
       const int ps = slot ^ 1;
       PTB_CUDA_TRY(c, cudaEventSynchronize(ev[ps]));
-      if (prof) prof_collect(ps);
+      if (prof) prof_collect(c, ps, mis);
       const WaveCounters& h = c->h_counters[ps];
       if (h.next_sample >= h.total_samples && (uint32_t)h.push_pair == 0u) done = true;
       if (progress && !done) {
@@ -1082,32 +1476,11 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
   PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
   PTB_CUDA_TRY(c, cudaGetLastError());
-  if (prof && iter > 0) prof_collect((int)((iter - 1) & 1u));
-#undef PTB_PROF
-#ifdef PTB_LANE_STATS
-  {
-    unsigned long long ls[8];
-    cudaMemcpyFromSymbol(ls, g_lane_stats, sizeof(ls));
-    fprintf(stderr, "lane_stats iters %llu work_lanes/iter %.2f node_phases %llu (%.2f ready lanes) prim_phases %llu (%.2f ready lanes) "
-            "services %llu node_steps %llu\n", ls[0], (double)ls[1] / ls[0], ls[2], (double)ls[3] / (ls[2] ? ls[2] : 1), ls[4],
-            (double)ls[5] / (ls[4] ? ls[4] : 1), ls[6], ls[7]);
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    cudaMemcpyToSymbol(g_lane_stats, z, sizeof(z));
-  }
-#endif
+  if (prof && iter > 0) prof_collect(c, (int)((iter - 1) & 1u), mis);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
   const WaveCounters& h = c->h_counters[0];
-  c->stats.nodes_fetched += h.nodes_fetched;
-  c->stats.prims_tested += h.prims_tested;
-  c->stats.rays_counted += h.rays_counted;
-  c->stats.rays_camera += h.rays_camera;
-  c->stats.rays_bounce += h.rays_bounce;
-  c->stats.rays_shadow_light += h.rays_shadow_light;
-  c->stats.rays_shadow_sky += h.rays_shadow_sky;
-  c->stats.rays_reference += h.rays_reference;
-  c->stats.paths += h.paths;
-  c->stats.wavefront_iterations += iter;
+  fold_counters(c, h, iter);
   c->stats.render_ms = ms;
   if (rc == PTB_OK) {
     c->accum_samples += o.samples_per_pixel;
@@ -1115,5 +1488,6 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   }
   return rc;
 }
+#undef PTB_PROF
 
 }  // namespace ptb

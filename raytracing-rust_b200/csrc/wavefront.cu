@@ -931,7 +931,8 @@ __global__ void k_win_prepare(WaveCounters* wc, Queues q, uint32_t n_segments, u
   wc->trace_head = wc->shade_head = wc->shadow_head = 0;
 }
 
-__global__ void __launch_bounds__(256) k_win_fill(Queues q, WaveCounters* wc) {
+// `identity`: first iteration of a chunk — every slot is live and in camera order, no sort needed
+__global__ void __launch_bounds__(256) k_win_fill(Queues q, WaveCounters* wc, uint32_t identity) {
   __shared__ uint32_t s_hist[8][33];  // per warp: bin counts, then running output offsets
   const uint32_t lane = threadIdx.x & 31u, warp_in_block = threadIdx.x >> 5;
   uint32_t* hist = s_hist[warp_in_block];
@@ -957,6 +958,11 @@ __global__ void __launch_bounds__(256) k_win_fill(Queues q, WaveCounters* wc) {
       const int b = __ffs(rest) - 1;
       const uint32_t out = __shfl_sync(0xffffffffu, start, b);
       const uint32_t first_slot = (g * 32u + (uint32_t)b) * kWindow;
+      if (identity) {
+        const uint32_t wn = __shfl_sync(0xffffffffu, cnt, b);
+        for (uint32_t j = lane; j < wn; j += 32u) q.active[0][out + j] = first_slot + j;
+        continue;
+      }
       // the window's 256 bin bytes, 8 consecutive slots per lane
       const uint2 raw = *reinterpret_cast<const uint2*>(q.bin + first_slot + lane * 8u);
       uint32_t bins[8];
@@ -967,7 +973,8 @@ __global__ void __launch_bounds__(256) k_win_fill(Queues q, WaveCounters* wc) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const bool live = bins[k] != kBinDead;
-        const uint32_t peers = __match_any_sync(0xffffffffu, live ? bins[k] : 0x100u + lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, live ? bins[k] : 0x100u);  // one key for all dead lanes: MATCH
+        // iterates over the distinct values
         if (live && lane == (uint32_t)__ffs(peers) - 1u) hist[bins[k]] += __popc(peers);
         __syncwarp();
       }
@@ -985,7 +992,8 @@ __global__ void __launch_bounds__(256) k_win_fill(Queues q, WaveCounters* wc) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const bool live = bins[k] != kBinDead;
-        const uint32_t peers = __match_any_sync(0xffffffffu, live ? bins[k] : 0x100u + lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, live ? bins[k] : 0x100u);  // one key for all dead lanes: MATCH
+        // iterates over the distinct values
         if (live) q.active[0][hist[bins[k]] + __popc(peers & ((1u << lane) - 1u))] = first_slot + lane * 8u + (uint32_t)k;
         __syncwarp();
         if (live && lane == (uint32_t)__ffs(peers) - 1u) hist[bins[k]] += __popc(peers);
@@ -1344,7 +1352,7 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
       if (depth) PTB_PROF(0, 0);
       k_win_scan<<<n_seg, 1024, 0, st>>>(q);
       k_win_prepare<<<1, 32, 0, st>>>(wc, q, n_seg, o.method, depth == 0 ? 0u : (depth == 1 ? 1u : 2u));
-      k_win_fill<<<grid_fill, T, 0, st>>>(q, wc);
+      k_win_fill<<<grid_fill, T, 0, st>>>(q, wc, depth == 0 ? 1u : 0u);
       PTB_PROF(0, 1);
       PTB_PROF(1, 0);
       if (count) k_trace<true, true><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);

@@ -24,6 +24,7 @@ struct RenderParams {
   uint32_t width, height, npix;
   uint32_t tile_w, tile_h;  // pixel issue order (k_generate); tile_h == 1 -> row-major
   uint32_t group;           // samples of one pixel issued back to back (a divisor of the call's spp)
+  uint32_t dir_bins;        // window mode: order a window's live rays by direction bin (PTB_DIRBINS=0 disables)
   uint32_t sample_offset;
   uint32_t method, max_depth, rr_threshold;
   uint32_t k0, k1;  // Philox key
@@ -788,7 +789,7 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
                make_float4(nd.x, nd.y, nd.z, __uint_as_float(kNone)));
         stg256(pool.col + 4u * (size_t)slot, make_float4(T.x, T.y, T.z, th.w),
                make_float4(L.x, L.y, L.z, __uint_as_float((sample << 9) | (delta ? kFlagPrevDelta : 0u) | depth)));
-        if (DENSE) q.bin[slot] = (uint8_t)direction_bin(nd);
+        if (DENSE) q.bin[slot] = rp.dir_bins ? (uint8_t)direction_bin(nd) : (uint8_t)0;
       }
     }
     if (finished) {
@@ -1251,6 +1252,8 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
     for (uint32_t g = want < o.samples_per_pixel ? want : o.samples_per_pixel; g > 1u; --g)
       if (o.samples_per_pixel % g == 0u) { rp.group = g; break; }
   }
+  rp.dir_bins = 1u;
+  if (const char* e = getenv("PTB_DIRBINS")) rp.dir_bins = atoi(e) != 0;
   rp.sample_offset = o.sample_offset;
   rp.method = o.method;
   rp.max_depth = o.max_depth ? o.max_depth : 50u;

@@ -84,7 +84,7 @@ int32_t ptb_create(int32_t device, ptb_ctx** out) {
     return rc;
   }
   c->sm_count = prop.multiProcessorCount;
-  c->dev.trace_burst = 4;
+  c->dev.trace_burst = 8;  // window mode, C3: 2 -> 3285, 4 -> 3425, 8 -> 3472 Mrays/s (profiles/r1_sweeps.md)
   c->dev.trace_fetch_threshold = 8;
   c->dev.trace_prim_bias = 0;
   if (const char* e = getenv("PTB_TRACE_PRIM_BIAS")) { int v = atoi(e); if (v >= 0 && v <= 32) c->dev.trace_prim_bias = v; }

@@ -1185,11 +1185,14 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   RenderSetup rs;
   rs.mis = o.method == PTB_METHOD_MIS;
   // Window mode (default) needs chunks long enough to amortise their ~50-launch tail: the whole call in one chunk, or
-  // chunks of at least 32 Mi paths. PTB_WAVEFRONT=queue forces the regenerating queue mode.
-  bool windows = true;
-  if (const char* e = getenv("PTB_WAVEFRONT")) windows = strcmp(e, "queue") != 0;
+  // chunks of at least 32 Mi paths. PTB_WAVEFRONT=queue forces the regenerating queue mode, =window the window mode.
+  bool windows = true, forced_windows = false;
+  if (const char* e = getenv("PTB_WAVEFRONT")) {
+    windows = strcmp(e, "queue") != 0;
+    forced_windows = strcmp(e, "window") == 0;
+  }
   uint32_t P = pool_capacity_for(c, total, rs.mis, windows);
-  if (windows && total > P && P < (1u << 25)) {
+  if (windows && !forced_windows && total > P && P < (1u << 25)) {
     windows = false;
     P = pool_capacity_for(c, total, rs.mis, false);
   }
@@ -1328,8 +1331,9 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
     return g < need ? g : (need ? need : 1u);
   };
   const uint32_t grid_fill = capped((const void*)k_win_fill, 32u * (T / 32), q.n_windows);
-  // k_shade is register-heavy (MIS: ~130): smaller blocks let more of them share an SM's register file
-  int TS = mis ? 128 : 256;
+  // k_shade is register-heavy (84 naive / 116 MIS): 128-thread blocks let more of them share an SM's register file
+  // (window mode, C3: 256 threads 3438 Mrays/s, 128 -> 3500, 64 -> 3499)
+  int TS = 128;
   if (const char* e = getenv("PTB_SHADE_THREADS")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) TS = v; }
   uint32_t grid_shade = (uint32_t)persistent_grid(c, shade_fn<true>(rs), TS);
   if (grid_shade > (P + TS - 1) / TS) grid_shade = (P + TS - 1) / TS;

@@ -212,3 +212,29 @@ def test_converged_images_agree_with_independent_samples(ptb, orc, gpu_ctx, rtwe
         g = sc.render(ptb.RenderOptions(samples_per_pixel=spp, render_method=method, width=w, height=h, seed=101))
         acc, _, _ = orc.OracleScene(rtweekend1).render(w, h, spp, method, seed=202)
         assert rmse(g, acc / spp) < 1e-2, (method, rmse(g, acc / spp))
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_window_and_queue_wavefronts_agree(ptb, gpu_ctx, overshadowed, method, monkeypatch):
+    """The window wavefront (default: every path resident, slot = generation index), its chunked form and the
+    regenerating queue mode trace the same paths: same image (f32 summation order aside), same ray counters."""
+    sc = ptb.Scene(overshadowed, ctx=gpu_ctx)
+    o = ptb.RenderOptions(samples_per_pixel=12, render_method=method, width=96, height=54, seed=9)
+
+    def run():
+        gpu_ctx.stats_reset()
+        img = sc.render(o)
+        st = gpu_ctx.stats()
+        return img, (st.rays_camera, st.rays_bounce, st.rays_shadow_light, st.rays_shadow_sky, st.rays_reference, st.paths)
+
+    a, ca = run()
+    monkeypatch.setenv("PTB_WAVEFRONT", "window")
+    monkeypatch.setenv("PTB_POOL_PATHS", "8192")  # 62 208 paths -> 8 chunks
+    b, cb = run()
+    monkeypatch.setenv("PTB_WAVEFRONT", "queue")
+    c, cc = run()
+    monkeypatch.delenv("PTB_WAVEFRONT")
+    monkeypatch.delenv("PTB_POOL_PATHS")
+    assert ca[0] == 96 * 54 * 12 and ca[5] == 96 * 54 * 12
+    assert ca == cb == cc
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-5) and np.allclose(a, c, rtol=1e-5, atol=1e-5)

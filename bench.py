@@ -25,11 +25,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of k_trace per ray, from the committed ncu capture (profiles/)
-NCU_DRAM_BYTES_PER_RAY = {"c3": (2.02e9 + 0.7096e9) / 16.78e6}
-# what ncu says actually limits k_trace on C3 (same capture): the scene is L2 resident, so the HBM roofline does not bind
-NCU_LIMITER = {"c3": {"unit": "SM issue slots / L1 data-pipe wavefronts", "issue_active_pct": 68.6, "l1_data_pipe_pct": 67.4,
-                      "active_lanes_per_instruction": 17.4, "l2_hit_pct": 72.6, "source": "profiles/r1_final_c3.md"}}
+# dram__bytes_read.sum + dram__bytes_write.sum of k_trace per ray, from the committed ncu capture (profiles/r1_final_c3.md:
+# the camera, first-bounce and second-bounce launches of a 16-spp render, 95 % of its rays)
+NCU_DRAM_BYTES_PER_RAY = {"c3": (2.325e9 + 1.126e9 + 1.766e9 + 0.6921e9 + 0.6635e9 + 0.1815e9) / (33.18e6 + 19.3e6 + 4.6e6)}
+# what ncu says actually limits k_trace on C3 (same capture, weighted over the three launches): the scene is L2 resident,
+# so the HBM roofline does not bind
+NCU_LIMITER = {"c3": {"unit": "SM issue slots / L1 data-pipe wavefronts", "issue_active_pct": 73.3, "l1_data_pipe_pct": 72.3,
+                      "active_lanes_per_instruction": 20.4, "l2_hit_pct": 70.2,
+                      "per_launch": {"camera": {"issue_active_pct": 78.9, "lanes": 24.5, "l1_data_pipe_pct": 68.8},
+                                     "first_bounce": {"issue_active_pct": 71.5, "lanes": 18.0, "l1_data_pipe_pct": 74.1}},
+                      "source": "profiles/r1_final_c3.md"}}
 
 
 def parse_args():
@@ -348,7 +353,7 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        spp_cpu = args.cpu_spp or max(1, int(round(8.0e6 / (w * h))))
+        spp_cpu = args.cpu_spp or max(1, int(round(32.0e6 / (w * h))))  # ~10 s of host work on C3
         rays_c, secs_c, cores, build_s, _ = cpu_render_leg(scene, w, h, method, spp_cpu)
         cpu = {"value": rays_c / secs_c / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
                "sample": f"{w}x{h} x {spp_cpu} spp, reference SAH BVH (built in {build_s:.2f} s, not timed), {secs_c:.1f} s"}
@@ -360,7 +365,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": label, "spp_per_step_per_gpu": S, "width": w, "height": h, "primitives": n_prims,
                        "bvh_nodes": n_nodes, "bvh_build_ms": build_ms, "parallelism": f"spp-split x{world}, scene replicated",
-                       "l2": "scene+BVH (168 MB at 1M triangles) plus path state (190 MB) exceed the 126 MB L2; no explicit flush",
+                       "l2": "scene+BVH (168 MB at 1M triangles) plus path state (69 B per path in flight: 36 GB at 256 spp) exceed the 126 MB L2; no explicit flush",
                        "ray_definition": "one BVH traversal launched (camera + bounce + shadow)",
                        "rays_reference_style": st.rays_reference, "wall_s": t_wall},
             "e2e": e2e,
@@ -369,9 +374,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
                          # DRAM bytes per k_trace launch: per-ray figure from the committed `ncu --set full` capture
-                         # (profiles/r1_final_c3.md: 2.02 GB read + 0.71 GB written for a 16.78 M-ray launch on this
-                         # workload) x this run's mean rays per launch. The 1 M-triangle scene is L2 resident, so real
-                         # traffic is ~13x below the algorithmic bytes and `frac` can exceed 1: the kernel is bound by
+                         # (profiles/r1_final_c3.md: 6.75 GB read + written over the 57.1 M rays of the first three
+                         # launches) x this run's mean rays per launch. The 1 M-triangle scene is L2 resident, so real
+                         # traffic is ~18x below the algorithmic bytes and `frac` can exceed 1: the kernel is bound by
                          # issue slots and L1 wavefronts (`limiter`), not by HBM.
                          "traffic": (NCU_DRAM_BYTES_PER_RAY.get(args.workload) * traced / max(int(st.trace_launches), 1)
                                      if NCU_DRAM_BYTES_PER_RAY.get(args.workload) else None),

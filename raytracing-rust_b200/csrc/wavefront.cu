@@ -43,6 +43,7 @@ struct Queues {
   uint32_t n_windows;
 };
 constexpr uint32_t kBinDead = 0xFFu;
+constexpr unsigned long long kNoCamera = ~0ull;
 constexpr uint32_t kWindow = 256u;        // slots per window == threads of a window-mode shade block
 constexpr uint32_t kSegWindows = 4096u;   // windows per scan segment (1024 threads x 4)
 
@@ -231,8 +232,8 @@ __global__ void k_prepare(WaveCounters* wc, uint32_t method, uint32_t first) {
 }
 
 // ------------------------------------------------------------------------------------------ K1 camera rays
-// One camera path: global path index g -> (pixel, sample) -> ray, written to `slot`.
-PTB_DEV void emit_camera_path(const DevScene& sc, const PathPool& pool, const RenderParams& rp, unsigned long long g, uint32_t slot) {
+// Global path index g -> pixel (x, y) and absolute sample index.
+PTB_DEV void camera_pixel_sample(const RenderParams& rp, unsigned long long g, uint32_t& x, uint32_t& y, uint32_t& sample) {
   // issue order: for each chunk of `group` samples, for each pixel, the chunk's samples — the 32 camera rays of a warp
   // share a pixel (group >= 32) and walk the same nodes down to the last levels. Only the ORDER changes; RNG and
   // accumulator are keyed by (pixel, absolute sample).
@@ -240,10 +241,9 @@ PTB_DEV void emit_camera_path(const DevScene& sc, const PathPool& pool, const Re
   const uint32_t chunk = (uint32_t)(g / per_chunk);
   const unsigned long long within_chunk = g % per_chunk;
   const uint32_t lin = (uint32_t)(within_chunk / rp.group);
-  const uint32_t sample = rp.sample_offset + chunk * rp.group + (uint32_t)(within_chunk % rp.group);
+  sample = rp.sample_offset + chunk * rp.group + (uint32_t)(within_chunk % rp.group);
   // A warp's 32 consecutive work items cover a tile_w x tile_h block of pixels (8x4 when the image allows) instead of a
   // 32x1 strip (group == 1 only matters): only the issue ORDER changes.
-  uint32_t x, y;
   if (rp.tile_h > 1u) {
     const uint32_t tile = lin >> 5, within = lin & 31u, tiles_x = rp.width / rp.tile_w;
     x = (tile % tiles_x) * rp.tile_w + within % rp.tile_w;
@@ -252,18 +252,25 @@ PTB_DEV void emit_camera_path(const DevScene& sc, const PathPool& pool, const Re
     x = lin % rp.width;
     y = lin / rp.width;
   }
+}
+// random_sampler.rs:55-59 (note W-1 / H-1), camera.rs:57-63; the caller's make_ray is Ray::new (ray.rs:13-46)
+PTB_DEV v3 camera_direction(const DevScene& sc, const RenderParams& rp, uint32_t x, uint32_t y, uint32_t sample) {
   const uint32_t pixel = y * rp.width + x;
   const uint4 r = philox4x32_10(pixel, sample, (0u << 8) | RNG_JITTER, 0u, rp.k0, rp.k1);
-  // random_sampler.rs:55-59 (note W-1 / H-1)
   const float u = (u32_to_unit(r.x) + (float)x) / (float)(rp.width - 1u);
   const float v = 1.0f - (u32_to_unit(r.y) + (float)y) / (float)(rp.height - 1u);
-  // camera.rs:57-63 + Ray::new (ray.rs:13-46)
   const v3 dir = sc.cam_lower_left + sc.cam_horizontal * u + sc.cam_vertical * v - sc.cam_origin;
-  const v3 d = dir / mag(dir);
-  // the 64-byte path block as two 32-byte stores (STG.256, sm_100): half the L1 data-pipe wavefronts of four STG.128
+  return dir / mag(dir);
+}
+// One camera path (queue mode): written to `slot` as the 64-byte path block.
+PTB_DEV void emit_camera_path(const DevScene& sc, const PathPool& pool, const RenderParams& rp, unsigned long long g, uint32_t slot) {
+  uint32_t x, y, sample;
+  camera_pixel_sample(rp, g, x, y, sample);
+  const v3 d = camera_direction(sc, rp, x, y, sample);
+  // two 32-byte stores (STG.256, sm_100): half the L1 data-pipe wavefronts of four STG.128
   stg256(pool.ray + 4u * (size_t)slot, make_float4(sc.cam_origin.x, sc.cam_origin.y, sc.cam_origin.z, 0.0f),
          make_float4(d.x, d.y, d.z, __uint_as_float(kNone)));
-  stg256(pool.col + 4u * (size_t)slot, make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(pixel)),
+  stg256(pool.col + 4u * (size_t)slot, make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(y * rp.width + x)),
          make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(sample << 9)));
 }
 
@@ -281,24 +288,37 @@ k_generate(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams 
 __global__ void k_advance(WaveCounters* wc) { wc->next_sample += wc->n_new; }
 
 // ------------------------------------------------------------------------------------------ K8 closest hit + K11 queueing
+// CAMERA (window mode, first iteration of a chunk): work item i IS slot i and its ray is the camera ray of path
+// first + i, computed here — the chunk's camera rays are never written to and read back from memory.
+template <bool CAMERA>
 struct TraceFetch {
   const PathPool& pool;
   const uint32_t* __restrict__ queue;
   uint32_t slot;
+  const DevScene& sc;
+  const RenderParams& rp;
+  unsigned long long first;
   PTB_DEV void operator()(uint32_t i, Ray& ray, float& /*tmax*/, uint32_t& /*exclude*/) {
+    if (CAMERA) {
+      slot = i;
+      uint32_t x, y, sample;
+      camera_pixel_sample(rp, first + i, x, y, sample);
+      ray = make_ray(sc.cam_origin, camera_direction(sc, rp, x, y, sample));
+      return;
+    }
     slot = queue[i];
     float4 o, d;
     ldg256_rw(pool.ray + 4u * (size_t)slot, o, d);
     ray = make_ray(from4(o), from4(d));
   }
 };
-template <bool DENSE>
+template <bool DENSE, bool CAMERA>
 struct TraceRetire {
   const DevScene& sc;
   const PathPool& pool;
   const Queues& q;
   WaveCounters* wc;
-  const TraceFetch& f;
+  const TraceFetch<CAMERA>& f;
   // called by all 32 lanes: write the hit (the whole 32-byte ray record, so the store is a full sector), then a
   // warp-aggregated push into the per-material-kind shade queue
   PTB_DEV void operator()(bool fin, const TravState& st, const Ray& ray) {
@@ -329,13 +349,13 @@ struct TraceRetire {
 #ifndef PTB_SHADE_MIN_BLOCKS
 #define PTB_SHADE_MIN_BLOCKS 2  // caps k_shade<MIS> at 128 registers (2 x 256 threads per SM): +6 % on rtweekend1 4K
 #endif
-template <bool COUNT, bool DENSE>
+template <bool COUNT, bool DENSE, bool CAMERA>
 __global__ void __launch_bounds__(256, PTB_TRACE_MIN_BLOCKS)
-k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
+k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, unsigned long long first) {
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t cnt_nodes = 0, cnt_prims = 0, cnt_rays = 0;
-  TraceFetch fetch{pool, q.active[DENSE ? 0u : wc->cur], 0u};
-  TraceRetire<DENSE> retire{sc, pool, q, wc, fetch};
+  TraceFetch<CAMERA> fetch{pool, q.active[DENSE ? 0u : wc->cur], 0u, sc, rp, first};
+  TraceRetire<DENSE, CAMERA> retire{sc, pool, q, wc, fetch};
   persistent_trace<false, COUNT>(sc, wc->n_trace, &wc->trace_head, fetch, retire, cnt_nodes, cnt_prims, cnt_rays);
   if (COUNT) {
     for (int off = 16; off > 0; off >>= 1) {
@@ -515,7 +535,11 @@ PTB_DEV uint32_t direction_bin(v3 d) {
 // per-material-kind queues of the regenerating queue mode.
 template <int METHOD, bool FULL, bool DENSE>
 __global__ void __launch_bounds__(256, PTB_SHADE_MIN_BLOCKS)
-k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum) {
+k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum,
+        unsigned long long camera_first) {
+  // window mode, first iteration of a chunk (camera_first != kNoCamera): work item i is slot i, every slot is live and its
+  // colour record is the camera path's initial state, derived from the path index instead of read from memory
+  const bool depth0 = DENSE && camera_first != kNoCamera;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t nxt = wc->cur ^ 1u;
   uint32_t n_kind[kNumKinds], n_total = 0;
@@ -555,10 +579,17 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
   v3 fin_L = mk(0.0f, 0.0f, 0.0f);
 
   if (active) {
-    slot = DENSE ? q.active[0][i] : q.kind[kq][off];
+    slot = DENSE ? (depth0 ? i : q.active[0][i]) : q.kind[kq][off];
     float4 ro, rd, th, ra;
     ldg256_rw(pool.ray + 4u * (size_t)slot, ro, rd);
-    ldg256_rw(pool.col + 4u * (size_t)slot, th, ra);
+    if (depth0) {
+      uint32_t x, y, smp;
+      camera_pixel_sample(rp, camera_first + slot, x, y, smp);
+      th = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(y * rp.width + x));
+      ra = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(smp << 9));
+    } else {
+      ldg256_rw(pool.col + 4u * (size_t)slot, th, ra);
+    }
     const uint2 ht = make_uint2(__float_as_uint(ro.w), __float_as_uint(rd.w));
     const uint32_t pixel = __float_as_uint(th.w);
     const uint32_t df = __float_as_uint(ra.w);
@@ -859,16 +890,15 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
 // in the queue, ordered by direction bin inside the window. Consequences, all measured (profiles/r1_sweeps.md): the rays a
 // k_trace warp fetches share a pixel (origin) and roughly a direction at every depth, path records are gathered from one
 // 16 KB window at a time instead of from the whole pool, and iteration k holds exactly the rays of bounce k.
-//   k_win_generate   camera paths of the chunk, slot = index; window counts, bins
+//   k_win_init       window counts of a fresh chunk (its camera rays are computed by the first k_trace itself)
 //   k_win_scan       per 4096-window segment: exclusive prefix of the counts + segment total
 //   k_win_prepare    1 warp: statistics of the finished iteration, total of live paths, cursor resets
 //   k_win_fill       ordered live-slot queue (one warp per window: counting sort of its live slots by direction bin)
-__global__ void __launch_bounds__(256)
-k_win_generate(DevScene sc, PathPool pool, Queues q, RenderParams rp, unsigned long long first_path, uint32_t n_paths) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_paths; i += gridDim.x * blockDim.x) {
-    emit_camera_path(sc, pool, rp, first_path + i, i);
-    q.bin[i] = 0;  // camera rays of a window are coherent as they are
-    if ((i & (kWindow - 1u)) == 0u) q.win_count[i / kWindow] = n_paths - i < kWindow ? n_paths - i : kWindow;
+__global__ void __launch_bounds__(256) k_win_init(Queues q, uint32_t n_paths) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < q.n_windows) {
+    const unsigned long long first = (unsigned long long)w * kWindow;
+    q.win_count[w] = first >= n_paths ? 0u : (n_paths - first < kWindow ? (uint32_t)(n_paths - first) : kWindow);
   }
 }
 
@@ -932,8 +962,7 @@ __global__ void k_win_prepare(WaveCounters* wc, Queues q, uint32_t n_segments, u
   wc->trace_head = wc->shade_head = wc->shadow_head = 0;
 }
 
-// `identity`: first iteration of a chunk — every slot is live and in camera order, no sort needed
-__global__ void __launch_bounds__(256) k_win_fill(Queues q, WaveCounters* wc, uint32_t identity) {
+__global__ void __launch_bounds__(256) k_win_fill(Queues q, WaveCounters* wc) {
   __shared__ uint32_t s_hist[8][33];  // per warp: bin counts, then running output offsets
   const uint32_t lane = threadIdx.x & 31u, warp_in_block = threadIdx.x >> 5;
   uint32_t* hist = s_hist[warp_in_block];
@@ -959,11 +988,6 @@ __global__ void __launch_bounds__(256) k_win_fill(Queues q, WaveCounters* wc, ui
       const int b = __ffs(rest) - 1;
       const uint32_t out = __shfl_sync(0xffffffffu, start, b);
       const uint32_t first_slot = (g * 32u + (uint32_t)b) * kWindow;
-      if (identity) {
-        const uint32_t wn = __shfl_sync(0xffffffffu, cnt, b);
-        for (uint32_t j = lane; j < wn; j += 32u) q.active[0][out + j] = first_slot + j;
-        continue;
-      }
       // the window's 256 bin bytes, 8 consecutive slots per lane
       const uint2 raw = *reinterpret_cast<const uint2*>(q.bin + first_slot + lane * 8u);
       uint32_t bins[8];
@@ -1300,14 +1324,15 @@ static void fold_counters(Ctx* c, const WaveCounters& h, uint64_t iterations) {
   c->stats.wavefront_iterations += iterations;
 }
 template <bool DENSE>
-static void launch_shade(const RenderSetup& rs, Ctx* c, uint32_t grid, int threads, cudaStream_t st) {
+static void launch_shade(const RenderSetup& rs, Ctx* c, uint32_t grid, int threads, cudaStream_t st,
+                         unsigned long long camera_first = kNoCamera) {
   const Queues& q = rs.q;
   if (rs.mis) {
-    if (rs.full) k_shade<PTB_METHOD_MIS, true, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum);
-    else k_shade<PTB_METHOD_MIS, false, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum);
+    if (rs.full) k_shade<PTB_METHOD_MIS, true, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum, camera_first);
+    else k_shade<PTB_METHOD_MIS, false, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum, camera_first);
   } else {
-    if (rs.full) k_shade<PTB_METHOD_NAIVE, true, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum);
-    else k_shade<PTB_METHOD_NAIVE, false, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum);
+    if (rs.full) k_shade<PTB_METHOD_NAIVE, true, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum, camera_first);
+    else k_shade<PTB_METHOD_NAIVE, false, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum, camera_first);
   }
 }
 template <bool DENSE>
@@ -1337,7 +1362,8 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   if (const char* e = getenv("PTB_SHADE_THREADS")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) TS = v; }
   uint32_t grid_shade = (uint32_t)persistent_grid(c, shade_fn<true>(rs), TS);
   if (grid_shade > (P + TS - 1) / TS) grid_shade = (P + TS - 1) / TS;
-  const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true, true> : (const void*)k_trace<false, true>, T);
+  const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true, true, false> : (const void*)k_trace<false, true, false>, T);
+  const int grid_trace_cam = persistent_grid(c, count ? (const void*)k_trace<true, true, true> : (const void*)k_trace<false, true, true>, T);
   const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
 
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
@@ -1352,23 +1378,28 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
     if (n_paths % kWindow)  // slots of the last window that hold no path
       PTB_CUDA_TRY(c, cudaMemsetAsync(q.bin + n_paths, (int)kBinDead, kWindow - n_paths % kWindow, st));
     PTB_PROF(0, 0);
-    k_win_generate<<<capped((const void*)k_win_generate, T, n_paths), T, 0, st>>>(c->dev, c->pool, q, rs.rp, first, n_paths);
+    k_win_init<<<(q.n_windows + T - 1) / T, T, 0, st>>>(q, n_paths);
     c->stats.kernel_launches += 1;
     bool done = false;
     for (uint64_t depth = 0; !done; ++depth, ++iter) {
       if (depth) PTB_PROF(0, 0);
       k_win_scan<<<n_seg, 1024, 0, st>>>(q);
       k_win_prepare<<<1, 32, 0, st>>>(wc, q, n_seg, o.method, depth == 0 ? 0u : (depth == 1 ? 1u : 2u));
-      k_win_fill<<<grid_fill, T, 0, st>>>(q, wc, depth == 0 ? 1u : 0u);
+      if (depth) k_win_fill<<<grid_fill, T, 0, st>>>(q, wc);  // depth 0: work item i is slot i, no queue
       PTB_PROF(0, 1);
       PTB_PROF(1, 0);
-      if (count) k_trace<true, true><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
-      else k_trace<false, true><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
+      if (depth == 0) {
+        if (count) k_trace<true, true, true><<<grid_trace_cam, T, 0, st>>>(c->dev, c->pool, q, wc, rs.rp, first);
+        else k_trace<false, true, true><<<grid_trace_cam, T, 0, st>>>(c->dev, c->pool, q, wc, rs.rp, first);
+      } else {
+        if (count) k_trace<true, true, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc, rs.rp, 0ull);
+        else k_trace<false, true, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc, rs.rp, 0ull);
+      }
       PTB_PROF(1, 1);
       PTB_PROF(2, 0);
-      launch_shade<true>(rs, c, grid_shade, TS, st);
+      launch_shade<true>(rs, c, grid_shade, TS, st, depth == 0 ? first : kNoCamera);
       PTB_PROF(2, 1);
-      c->stats.kernel_launches += 5;
+      c->stats.kernel_launches += depth ? 5 : 4;
       c->stats.trace_launches += 1;
       if (mis) {
         PTB_PROF(3, 0);
@@ -1430,7 +1461,7 @@ static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderS
   if (const char* e = getenv("PTB_SHADE_THREADS")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) TS = v; }
   uint32_t grid_shade = (uint32_t)persistent_grid(c, shade_fn<false>(rs), TS);
   if (grid_shade > (P + TS - 1) / TS) grid_shade = (P + TS - 1) / TS;
-  const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true, false> : (const void*)k_trace<false, false>, T);
+  const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true, false, false> : (const void*)k_trace<false, false, false>, T);
   const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
 
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
@@ -1450,8 +1481,8 @@ static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderS
     PTB_PROF(0, 1);
     k_advance<<<1, 1, 0, st>>>(wc);
     PTB_PROF(1, 0);
-    if (count) k_trace<true, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
-    else k_trace<false, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc);
+    if (count) k_trace<true, false, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc, rp, 0ull);
+    else k_trace<false, false, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc, rp, 0ull);
     PTB_PROF(1, 1);
     PTB_PROF(2, 0);
     launch_shade<false>(rs, c, grid_shade, TS, st);

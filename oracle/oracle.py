@@ -60,6 +60,7 @@ def _load():
     lib.orc_lbvh_export.argtypes = [P, P, P, P]
     lib.orc_lbvh_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_lbvh_node_counts.argtypes = [P, P, C.c_size_t, P, C.c_int]
+    lib.orc_lbvh_wide_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_sah_ordered_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_philox4x32_10.argtypes = [P, P, P]
     lib.orc_sort_by_indices_u32.argtypes = [P, P, C.c_size_t]
@@ -252,6 +253,16 @@ class OracleScene:
         lib.orc_lbvh_closest_hit(self._h, _p(rays), len(rays), _p(out), threads, _p(counts))
         return out, int(counts[0]), int(counts[1])
 
+
+    def lbvh_wide_closest_hit(self, rays, threads=0):
+        """Same over the 4-wide collapse of the LBVH: (hits, wide nodes fetched, prims tested)."""
+        if not self._lbvh:
+            self.lbvh_build()
+        rays = np.ascontiguousarray(rays, dtype=ray_dtype)
+        out = np.zeros(len(rays), hit_dtype)
+        counts = np.zeros(2, np.uint64)
+        lib.orc_lbvh_wide_closest_hit(self._h, _p(rays), len(rays), _p(out), threads, _p(counts))
+        return out, int(counts[0]), int(counts[1])
 
     def lbvh_node_counts(self, rays, threads=0):
         """Nodes fetched per ray by the ordered LBVH traversal."""

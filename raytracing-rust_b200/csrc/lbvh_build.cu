@@ -297,6 +297,38 @@ __global__ void k_refit(uint32_t n_prims, const uint32_t* __restrict__ prim_sort
 }
 
 // single primitive: one node, both child slots reference leaf 0 (see oracle/lbvh_ref.hpp)
+// ------------------------------------------------------------------------------------------ 4-wide collapse
+// One thread per LBVH node: nodes at even depth (parent chain walked to the root) gather their grandchildren into a
+// 128-byte wide node at the same index. No reference counterpart (the reference's tree is binary); the CPU definition is
+// Lbvh::build_wide in oracle/lbvh_ref.hpp.
+__global__ void k_collapse4(const BvhNode* __restrict__ nodes, uint32_t n_nodes, BvhNode4* __restrict__ wide) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  uint32_t depth = 0;
+  for (uint32_t p = nodes[i].n3.z; p != kNone; p = nodes[p].n3.z) ++depth;
+  if (depth & 1u) return;
+  const BvhNode nd = nodes[i];
+  BvhNode4 w;
+  int k = 0;
+  auto put = [&](uint32_t ref, float mnx, float mny, float mnz, float mxx, float mxy, float mxz) {
+    float* b = w.box + 6 * k;
+    b[0] = mnx; b[1] = mny; b[2] = mnz; b[3] = mxx; b[4] = mxy; b[5] = mxz;
+    w.child[k++] = ref;
+  };
+  auto expand = [&](uint32_t ref, float mnx, float mny, float mnz, float mxx, float mxy, float mxz) {
+    if (ref & PTB_LEAF_BIT) { put(ref, mnx, mny, mnz, mxx, mxy, mxz); return; }
+    const BvhNode c = nodes[ref];
+    put(c.n3.x, c.n0.x, c.n0.y, c.n0.z, c.n0.w, c.n1.x, c.n1.y);
+    put(c.n3.y, c.n1.z, c.n1.w, c.n2.x, c.n2.y, c.n2.z, c.n2.w);
+  };
+  expand(nd.n3.x, nd.n0.x, nd.n0.y, nd.n0.z, nd.n0.w, nd.n1.x, nd.n1.y);
+  expand(nd.n3.y, nd.n1.z, nd.n1.w, nd.n2.x, nd.n2.y, nd.n2.z, nd.n2.w);
+  const float inf = __int_as_float(0x7f800000);
+  for (; k < 4;) put(kNone, inf, inf, inf, -inf, -inf, -inf);
+  for (int j = 0; j < 4; ++j) w.pad[j] = 0u;
+  wide[i] = w;
+}
+
 __global__ void k_single_node(const uint32_t* __restrict__ prim_sorted, uint32_t n_spheres, const float4* __restrict__ bmin,
                               const float4* __restrict__ bmax, BvhNode* nodes) {
   const uint32_t p = prim_sorted[0];
@@ -586,6 +618,11 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
                               c->d_nodes.as<BvhNode>(), nbmin.as<float4>(), nbmax.as<float4>(), flags.as<uint32_t>());
     c->stats.kernel_launches += 2;
   }
+  if (PTB_WIDE_BVH) {
+    PTB_CUDA_TRY(c, c->d_nodes4.reserve(c->n_nodes * sizeof(BvhNode4)));
+    k_collapse4<<<((uint32_t)c->n_nodes + T - 1) / T, T, 0, st>>>(c->d_nodes.as<BvhNode>(), (uint32_t)c->n_nodes, c->d_nodes4.as<BvhNode4>());
+    c->stats.kernel_launches += 1;
+  }
   k_gather<<<gn, T, 0, st>>>(raw_spheres.as<ptb_sphere>(), ns32, raw_tris.as<ptb_triangle>(), n32, va,
                              c->d_materials.as<DevMaterial>(), c->d_geom.as<float4>(), c->d_normals.as<float4>(),
                              c->d_slot_mat.as<uint32_t>(), prim_slot.as<uint32_t>());
@@ -630,6 +667,7 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
   c->dev.slot_prim = c->d_slot_prim.as<uint32_t>();
   c->dev.slot_mat = c->d_slot_mat.as<uint32_t>();
   c->dev.nodes = c->d_nodes.as<BvhNode>();
+  c->dev.nodes4 = c->d_nodes4.as<BvhNode4>();
   c->dev.lights = c->d_lights.as<uint32_t>();
   c->dev.n_lights = nl;
   c->committed = true;

@@ -163,6 +163,21 @@ struct __align__(16) BvhNode {  // 64 B, same memory layout as ptb_bvh_node
   uint4 n3;   // left, right, parent, pad   (refs: bit31 leaf, bit30 sphere, low bits slot)
 };
 static_assert(sizeof(BvhNode) == 64 && sizeof(ptb_bvh_node) == 64, "node layout");
+// 4-wide node the traversal kernels walk (PTB_WIDE_BVH): the LBVH node of the same index at EVEN depth with its
+// grandchildren (or a child itself where that child is a leaf) as children; odd-depth entries are unused. 128 B =
+// four 32-byte loads: 24 box floats (child k: min.xyz max.xyz at floats [6k, 6k+6)), then the four references
+// (kNone = empty slot, its box is inverted so that it can never be hit).
+struct __align__(32) BvhNode4 {
+  float box[24];
+  uint32_t child[4];
+  uint32_t pad[4];
+};
+static_assert(sizeof(BvhNode4) == 128, "wide node layout");
+#ifndef PTB_WIDE_BVH
+#define PTB_WIDE_BVH 0  // measured on B200 (profiles/r1_sweeps.md): half the node visits, but k_trace on C3 183 ms vs 160 ms
+                        // for the binary step (same number of slab tests per ray, dearer child ordering, 68 - 74 registers
+                        // wanted); only the 2-sphere scene gains (rtweekend1 4K: 9341 vs 8697 Mrays/s). Off by default.
+#endif
 
 struct DevMaterial {
   uint32_t kind, tex;
@@ -253,6 +268,7 @@ struct DevScene {
   const uint32_t* slot_prim;  // slot -> original primitive id (loader order)
   const uint32_t* slot_mat;   // slot -> (material kind << 24) | material index
   const BvhNode* nodes;
+  const BvhNode4* nodes4;     // 4-wide collapse of `nodes` (same indices, even-depth entries only)
   const DevMaterial* materials;
   const DevTexture* textures;
   const float* tex_data;      // bulk texture data (image pixels, perlin tables), see DevTexture::data_off

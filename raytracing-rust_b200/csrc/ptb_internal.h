@@ -98,7 +98,7 @@ struct Ctx {
 
   // device scene
   DevScene dev{};
-  DevBuf d_geom, d_normals, d_slot_prim, d_slot_mat, d_nodes, d_morton, d_materials, d_textures, d_tex_data, d_lights;
+  DevBuf d_geom, d_normals, d_slot_prim, d_slot_mat, d_nodes, d_nodes4, d_morton, d_materials, d_textures, d_tex_data, d_lights;
   DevBuf d_sky_ycdf, d_sky_ypdf, d_sky_xcdf, d_sky_xpdf;
   uint64_t n_prims = 0, n_nodes = 0;
 

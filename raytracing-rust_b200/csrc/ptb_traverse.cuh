@@ -24,7 +24,8 @@
 
 namespace ptb {
 
-constexpr int kStackDepth = 64;  // LBVH depth <= 30 Morton bits + 32 index tie-break bits; one push per level
+constexpr int kStackDepth = PTB_WIDE_BVH ? 96 : 64;  // LBVH depth <= 30 Morton bits + 32 index tie-break bits: one push per
+                                                   // binary level, up to three per 4-wide level (two binary levels each)
 #ifndef PTB_LEAF_QUEUE
 #define PTB_LEAF_QUEUE 1         // postponed leaves per lane (power of two). Measured on C3: 1 -> 1911-1927 Mrays/s,
                                  // 2 -> 1872, 4 -> 1856, 8 -> 1825: deeper queues speculate more (V 32.9 -> 35.8 nodes/ray)
@@ -208,6 +209,55 @@ PTB_DEV void trav_node_step(const DevScene& sc, const SlabRay& ray, const Ray& f
   if (want_pop) trav_pop(s, stack, lq);
 }
 
+// The same step over a 4-wide node (PTB_WIDE_BVH): four 32-byte loads, four slab tests, the hit children ranked by cull key
+// (ties: lower slot first); the nearest becomes `cur`, the others go to the stack with the nearest on top — each hit child
+// stores itself at the position its rank gives it, no sorting network. Identical decisions to Lbvh::closest_hit_wide.
+template <bool COUNT>
+PTB_DEV void trav_node_step4(const DevScene& sc, const SlabRay& ray, TravState& s, const TravStack& stack, uint2* lq,
+                             uint32_t& n_nodes) {
+  static_assert(!PTB_WIDE_BVH || kSharedStack == 0, "the wide step writes the local-memory stack directly");
+  const float4* p = reinterpret_cast<const float4*>(sc.nodes4 + s.cur);
+  float4 a0, a1, b0, b1, c0, c1, d0, d1;
+  ldg256(p, a0, a1);
+  ldg256(p + 2, b0, b1);
+  ldg256(p + 4, c0, c1);
+  ldg256(p + 6, d0, d1);
+  if (COUNT) ++n_nodes;
+  const uint32_t r0 = __float_as_uint(d0.x), r1 = __float_as_uint(d0.y), r2 = __float_as_uint(d0.z), r3 = __float_as_uint(d0.w);
+  float t0, t1, t2, t3;
+  const bool h0 = box_entry(a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, ray, s.best_t, t0);  // slot 0 is never empty
+  const bool h1 = box_entry(a1.z, a1.w, b0.x, b0.y, b0.z, b0.w, ray, s.best_t, t1);  // nor slot 1
+  const bool h2 = r2 != kNone && box_entry(b1.x, b1.y, b1.z, b1.w, c0.x, c0.y, ray, s.best_t, t2);
+  const bool h3 = r3 != kNone && box_entry(c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, ray, s.best_t, t3);
+  const int n_hit = (int)h0 + (int)h1 + (int)h2 + (int)h3;
+  bool want_pop = n_hit == 0;
+  if (!want_pop) {
+    // rank of a hit child = number of hit children that come before it
+    const int k0 = (int)(h1 && t1 < t0) + (int)(h2 && t2 < t0) + (int)(h3 && t3 < t0);
+    const int k1 = (int)(h0 && t0 <= t1) + (int)(h2 && t2 < t1) + (int)(h3 && t3 < t1);
+    const int k2 = (int)(h0 && t0 <= t2) + (int)(h1 && t1 <= t2) + (int)(h3 && t3 < t2);
+    const int k3 = (int)(h0 && t0 <= t3) + (int)(h1 && t1 <= t3) + (int)(h2 && t2 <= t3);
+    uint2* top = stack.local + s.sp + n_hit - 1;  // rank r (>= 1) lives at top[-r]
+    uint32_t cur = r0;
+    float key = t0;
+    if (h0 && k0) top[-k0] = make_uint2(r0, __float_as_uint(t0));
+    if (h1) { if (k1) top[-k1] = make_uint2(r1, __float_as_uint(t1)); else { cur = r1; key = t1; } }
+    if (h2) { if (k2) top[-k2] = make_uint2(r2, __float_as_uint(t2)); else { cur = r2; key = t2; } }
+    if (h3) { if (k3) top[-k3] = make_uint2(r3, __float_as_uint(t3)); else { cur = r3; key = t3; } }
+    s.sp += n_hit - 1;
+    s.cur = cur;
+    if (cur & PTB_LEAF_BIT) {
+      if (s.lq_count < kLeafQueue) {
+        lq_push(s, lq, cur, key);
+        want_pop = true;
+      } else {
+        s.cur_key = key;  // queue full: park on the leaf until the next primitive phase
+      }
+    }
+  }
+  if (want_pop) trav_pop(s, stack, lq);
+}
+
 // One primitive step of the lane: take the oldest queued leaf (the nearest, as the walk is near-first), drop it if its box
 // has fallen behind the best hit, else test it; then move a parked leaf into the freed queue slot and resume the walk.
 template <bool ANYHIT, bool COUNT>
@@ -354,7 +404,11 @@ PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fe
       PTB_LS(3, n_node);
 #pragma unroll 1
       for (int burst = 0; burst < sc.trace_burst && node_ready; ++burst) {
+#if PTB_WIDE_BVH
+        trav_node_step4<COUNT>(sc, slab, st, stack, lq, cnt_nodes);
+#else
         trav_node_step<COUNT>(sc, slab, ray, st, stack, lq, cnt_nodes);
+#endif
         node_ready = !(st.cur & PTB_LEAF_BIT);
 #ifdef PTB_LANE_STATS
         atomicAdd(&g_lane_stats[7], 1ull);

@@ -287,3 +287,19 @@ def test_sah_builder_shape(ptb, orc, overshadowed):
         o2 = orc.OracleScene(overshadowed, split)
         rays = ptb.meshgen.philox_rays(5000, seed=2, centre=(-0.3, 0.3, -0.3), radius=1.5)
         assert np.array_equal(o2.closest_hit(rays)["t"], o.closest_hit(rays)["t"])
+
+
+def test_wide_collapse_traversal_returns_the_same_hits(orc):
+    """oracle/lbvh_ref.hpp build_wide / closest_hit_wide (the CPU definition of the optional 4-wide device traversal,
+    -DPTB_WIDE_BVH=1): same closest hits as the binary ordered traversal, about half the node visits."""
+    import importlib
+    import numpy as np
+    mg = importlib.import_module("raytracing-rust_b200.meshgen")
+    s = mg.c3_scene(0.05)
+    o = orc.OracleScene(s, split_type=-1)
+    rays = mg.philox_rays(20000, seed=7, centre=(0.0, 4.0, 1.0), radius=5.0)
+    h2, v2, t2 = o.lbvh_closest_hit(rays)
+    h4, v4, t4 = o.lbvh_wide_closest_hit(rays)
+    assert np.array_equal(h2["prim"], h4["prim"]) and np.array_equal(h2["t"].view(np.uint32), h4["t"].view(np.uint32))
+    assert 0.4 * v2 < v4 < 0.65 * v2
+    assert abs(t4 - t2) <= 0.02 * t2

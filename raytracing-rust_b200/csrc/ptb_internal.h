@@ -62,7 +62,7 @@ struct WaveCounters {  // lives in device memory; mirrored to pinned host memory
   uint32_t n_shadow;
   uint32_t cur;             // which q_active is the trace queue
   uint32_t trace_head, shade_head, shadow_head;  // persistent-kernel work cursors
-  uint32_t n_win_alive;     // window mode: entries of win_list (non-empty windows of this iteration)
+  uint32_t _pad;
   // k_shade's queue cursors, packed so that one warp needs ONE returning atomic per pair (the kernel used to spend 40 % of
   // its stall samples waiting for three serial same-address atomics): push_pair = finished-slot cursor << 32 | next-active
   // cursor, shadow_pair = sky NEE rays << 32 | shadow-queue cursor. k_prepare unpacks them between iterations.

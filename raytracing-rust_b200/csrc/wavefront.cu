@@ -1311,7 +1311,19 @@ static void prof_collect(Ctx* c, int half, bool mis) {
       *prof_ms[k] += ms;
   }
 }
+static void dump_lane_stats() {
+#ifdef PTB_LANE_STATS  // tuning builds (scripts/lane_stats.sh): where the lanes of persistent_trace spent their iterations
+  unsigned long long ls[8];
+  cudaMemcpyFromSymbol(ls, g_lane_stats, sizeof(ls));
+  fprintf(stderr, "lane_stats iters %llu work_lanes/iter %.2f node_phases %llu (%.2f ready lanes) prim_phases %llu (%.2f ready lanes) "
+          "services %llu node_steps %llu\n", ls[0], (double)ls[1] / (ls[0] ? ls[0] : 1), ls[2], (double)ls[3] / (ls[2] ? ls[2] : 1), ls[4],
+          (double)ls[5] / (ls[4] ? ls[4] : 1), ls[6], ls[7]);
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_lane_stats, z, sizeof(z));
+#endif
+}
 static void fold_counters(Ctx* c, const WaveCounters& h, uint64_t iterations) {
+  dump_lane_stats();
   c->stats.nodes_fetched += h.nodes_fetched;
   c->stats.prims_tested += h.prims_tested;
   c->stats.rays_counted += h.rays_counted;

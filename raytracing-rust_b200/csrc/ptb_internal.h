@@ -121,6 +121,7 @@ struct Ctx {
   // closest-hit staging: two buffer pairs + copy streams so that the upload of batch k+1, the traversal of batch k and the
   // read-back of batch k-1 overlap (ptb_closest_hit with host buffers)
   DevBuf d_rays, d_hits, d_rays2, d_hits2;
+  DevBuf d_hit_sort;  // ray ordering scratch of the closest-hit API: 4 x n words (keys / indices, ping-pong) + histogram
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {}, ev_kernel[2] = {}, ev_out[2] = {};
 
@@ -132,6 +133,8 @@ int32_t check_cuda(Ctx* c, cudaError_t e, const char* what);
 
 // lbvh_build.cu — uploads the host scene and builds the device LBVH (K2..K6)
 int32_t build_scene(Ctx* c, uint32_t flags);
+void radix_sort_pairs(Ctx* c, uint32_t*& ka, uint32_t*& va, uint32_t*& kb, uint32_t*& vb, uint32_t n, int passes, uint32_t* hist);
+size_t radix_sort_hist_words(uint32_t n);
 // wavefront.cu
 int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progress, void* user);
 int32_t launch_closest_hit(Ctx* c, const void* d_rays, size_t n, void* d_hits);

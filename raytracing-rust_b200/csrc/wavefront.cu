@@ -44,7 +44,15 @@ struct Queues {
 };
 constexpr uint32_t kBinDead = 0xFFu;
 constexpr unsigned long long kNoCamera = ~0ull;
-constexpr uint32_t kWindow = 256u;        // slots per window == threads of a window-mode shade block
+#ifndef PTB_WINDOW
+#define PTB_WINDOW 4096  // slots per window (256 * 1, 2, 4, 8 or 16): the span inside which k_win_fill orders the live rays by direction
+#endif
+#ifndef PTB_DIR_BITS
+#define PTB_DIR_BITS 8   // direction bins per window: 5 = octant x dominant axis, 8 = 16 x 16 octahedral map in Morton order
+#endif
+constexpr uint32_t kWindow = PTB_WINDOW;
+constexpr uint32_t kWinItems = kWindow / 256u;  // slots per k_win_fill thread
+static_assert(kWindow % 256u == 0 && kWinItems >= 1 && kWinItems <= 16 && (kWinItems & (kWinItems - 1)) == 0, "window size");
 constexpr uint32_t kSegWindows = 4096u;   // windows per scan segment (1024 threads x 4)
 
 constexpr uint32_t kFlagPrevDelta = 1u << 8;  // stored above the 8-bit depth in ray_d.w
@@ -523,12 +531,31 @@ PTB_DEV void finish_paths(float* __restrict__ accum, bool contributes, uint32_t 
   }
 }
 
-// 5-bit direction bin of a unit vector: octant (signs) x dominant axis. Window-mode k_shade orders the surviving paths of
-// a window by it, so the 32 consecutive rays a k_trace warp fetches share a pixel AND roughly a direction.
+// Direction bin of a unit vector. Window-mode k_shade leaves it per slot and k_win_fill orders the live rays of a window
+// by it, so the 32 consecutive rays a k_trace warp fetches start in the same few pixels AND point the same way.
+//   5 bits: octant (signs) x dominant axis;
+//   8 bits: 16 x 16 cells of the octahedral map (|x|+|y|+|z| = 1 unfolded onto the square), cell index in Morton
+//           order so that neighbouring bins are neighbouring directions; bin 255 is reserved for finished paths.
 PTB_DEV uint32_t direction_bin(v3 d) {
+#if PTB_DIR_BITS == 5
   const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
   const uint32_t major = ax >= ay ? (ax >= az ? 0u : 2u) : (ay >= az ? 1u : 2u);
   return ((d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u)) * 4u + major;
+#else
+  const float inv = 1.0f / (fabsf(d.x) + fabsf(d.y) + fabsf(d.z));
+  float u = d.x * inv, v = d.y * inv;
+  if (d.z < 0.0f) {
+    const float fu = (1.0f - fabsf(v)) * (u < 0.0f ? -1.0f : 1.0f), fv = (1.0f - fabsf(u)) * (v < 0.0f ? -1.0f : 1.0f);
+    u = fu;
+    v = fv;
+  }
+  const uint32_t iu = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * 16.0f, 0.0f), 15.0f);
+  const uint32_t iv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * 16.0f, 0.0f), 15.0f);
+  uint32_t m = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) m |= (((iu >> b) & 1u) << (2 * b + 1)) | (((iv >> b) & 1u) << (2 * b));
+  return m < 255u ? m : 254u;
+#endif
 }
 
 // DENSE = window mode (ordered live-slot queue in, per-slot direction bin and per-window live count out), else the
@@ -893,7 +920,7 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
 //   k_win_init       window counts of a fresh chunk (its camera rays are computed by the first k_trace itself)
 //   k_win_scan       per 4096-window segment: exclusive prefix of the counts + segment total
 //   k_win_prepare    1 warp: statistics of the finished iteration, total of live paths, cursor resets
-//   k_win_fill       ordered live-slot queue (one warp per window: counting sort of its live slots by direction bin)
+//   k_win_fill       ordered live-slot queue (one block per window: counting sort of its live slots by direction bin)
 __global__ void __launch_bounds__(256) k_win_init(Queues q, uint32_t n_paths) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w < q.n_windows) {
@@ -962,68 +989,84 @@ __global__ void k_win_prepare(WaveCounters* wc, Queues q, uint32_t n_segments, u
   wc->trace_head = wc->shade_head = wc->shadow_head = 0;
 }
 
+constexpr uint32_t kFillGroup = 8u;  // windows whose live counts a k_win_fill block fetches (and skips) together
 __global__ void __launch_bounds__(256) k_win_fill(Queues q, WaveCounters* wc) {
-  __shared__ uint32_t s_hist[8][33];  // per warp: bin counts, then running output offsets
-  const uint32_t lane = threadIdx.x & 31u, warp_in_block = threadIdx.x >> 5;
-  uint32_t* hist = s_hist[warp_in_block];
-  const uint32_t n_groups = (q.n_windows + 31u) / 32u;
-  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-  uint32_t seg_cached = 0xffffffffu, seg_base = 0;
-  for (uint32_t g = blockIdx.x * (blockDim.x >> 5) + warp_in_block; g < n_groups; g += warps) {
-    const uint32_t w = g * 32u + lane;
-    const uint32_t cnt = w < q.n_windows ? q.win_count[w] : 0u;
-    const uint32_t m = __ballot_sync(0xffffffffu, cnt != 0u);
-    if (!m) continue;
-    const uint32_t seg = (g * 32u) / kSegWindows;  // 32 divides kSegWindows: one segment per group
-    if (seg != seg_cached) {
-      uint32_t b = 0;
-      for (uint32_t s = lane; s < seg; s += 32u) b += q.seg_total[s];
+  __shared__ uint32_t s_cnt[kFillGroup];
+  __shared__ uint32_t s_hist[2][256];  // per direction bin: count, then running output offset (double-buffered)
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_seg_base;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t n_groups = (q.n_windows + kFillGroup - 1u) / kFillGroup;
+  uint32_t seg_cached = 0xffffffffu, buf = 0;
+  s_hist[0][tid] = 0u;
+  for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const uint32_t wmine = g * kFillGroup + tid;
+    const uint32_t cmine = tid < kFillGroup && wmine < q.n_windows ? q.win_count[wmine] : 0u;
+    __syncthreads();  // the previous group's readers of s_cnt are done; s_hist[buf] is zero and visible
+    if (tid < kFillGroup) s_cnt[tid] = cmine;
+    if (!__syncthreads_or(cmine != 0u)) continue;
+    for (uint32_t j = 0; j < kFillGroup; ++j) {
+      const uint32_t cnt = s_cnt[j];
+      if (cnt == 0u) continue;  // uniform
+      const uint32_t w = g * kFillGroup + j;
+      const uint32_t seg = w / kSegWindows;
+      if (seg != seg_cached) {  // uniform, rare: base of the segment = live paths of all earlier segments
+        uint32_t b = 0;
+        for (uint32_t sgi = tid; sgi < seg; sgi += 256u) b += q.seg_total[sgi];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
-      seg_base = b;
-      seg_cached = seg;
-    }
-    const uint32_t start = cnt ? seg_base + q.win_prefix[w] : 0u;
-    for (uint32_t rest = m; rest; rest &= rest - 1u) {
-      const int b = __ffs(rest) - 1;
-      const uint32_t out = __shfl_sync(0xffffffffu, start, b);
-      const uint32_t first_slot = (g * 32u + (uint32_t)b) * kWindow;
-      // the window's 256 bin bytes, 8 consecutive slots per lane
-      const uint2 raw = *reinterpret_cast<const uint2*>(q.bin + first_slot + lane * 8u);
-      uint32_t bins[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) bins[k] = ((k < 4 ? raw.x : raw.y) >> (8 * (k & 3))) & 0xFFu;
-      hist[lane] = 0u;
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const bool live = bins[k] != kBinDead;
-        const uint32_t peers = __match_any_sync(0xffffffffu, live ? bins[k] : 0x100u);  // one key for all dead lanes: MATCH
-        // iterates over the distinct values
-        if (live && lane == (uint32_t)__ffs(peers) - 1u) hist[bins[k]] += __popc(peers);
-        __syncwarp();
+        for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        __syncthreads();
+        if (lane == 0u) s_warp[warp] = b;
+        __syncthreads();
+        if (tid == 0u) {
+          uint32_t t = 0;
+          for (int k = 0; k < 8; ++k) t += s_warp[k];
+          s_seg_base = t;
+        }
+        __syncthreads();
+        seg_cached = seg;
       }
-      {  // exclusive scan over the 32 bins -> running offsets
-        const uint32_t c = hist[lane];
+      const uint32_t out = s_seg_base + q.win_prefix[w];
+      const uint32_t first_slot = w * kWindow;
+      uint32_t* hist = s_hist[buf];
+      // this thread's kWinItems consecutive slots: their bins, and (from the returning atomic) their place inside the bin
+      uint32_t bins[kWinItems], offs[kWinItems];
+      {
+        const uint8_t* src = q.bin + first_slot + tid * kWinItems;
+        if (kWinItems == 16) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(src);
+          const uint32_t r4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (uint32_t k = 0; k < kWinItems; ++k) bins[k] = (r4[(k >> 2) & 3u] >> (8u * (k & 3u))) & 0xFFu;
+        } else {
+#pragma unroll
+          for (uint32_t k = 0; k < kWinItems; ++k) bins[k] = src[k];
+        }
+      }
+#pragma unroll
+      for (uint32_t k = 0; k < kWinItems; ++k) offs[k] = bins[k] != kBinDead ? atomicAdd(&hist[bins[k]], 1u) : 0u;
+      __syncthreads();
+      {  // exclusive scan over the 256 bins; the other buffer is cleared for the next window meanwhile
+        const uint32_t c = hist[tid];
         uint32_t inc = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
           if (lane >= (uint32_t)o) inc += t;
         }
-        hist[lane] = out + inc - c;
-      }
-      __syncwarp();
+        if (lane == 31u) s_warp[warp] = inc;
+        s_hist[buf ^ 1u][tid] = 0u;
+        __syncthreads();
+        uint32_t before = 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const bool live = bins[k] != kBinDead;
-        const uint32_t peers = __match_any_sync(0xffffffffu, live ? bins[k] : 0x100u);  // one key for all dead lanes: MATCH
-        // iterates over the distinct values
-        if (live) q.active[0][hist[bins[k]] + __popc(peers & ((1u << lane) - 1u))] = first_slot + lane * 8u + (uint32_t)k;
-        __syncwarp();
-        if (live && lane == (uint32_t)__ffs(peers) - 1u) hist[bins[k]] += __popc(peers);
-        __syncwarp();
+        for (uint32_t k = 0; k < 8u; ++k) before += k < warp ? s_warp[k] : 0u;
+        hist[tid] = out + before + inc - c;
       }
+      __syncthreads();
+#pragma unroll
+      for (uint32_t k = 0; k < kWinItems; ++k)
+        if (bins[k] != kBinDead) q.active[0][hist[bins[k]] + offs[k]] = first_slot + tid * kWinItems + k;
+      buf ^= 1u;
     }
   }
 }
@@ -1241,7 +1284,8 @@ static uint32_t pool_capacity_for(Ctx* c, unsigned long long total, bool mis, bo
     while (cap > (1ull << 24) && cap * per_path > c->pool_budget_bytes) cap >>= 1;
   }
   if (total < cap) cap = total < 1024 ? 1024 : total;
-  return (uint32_t)((cap + 255ull) & ~255ull);
+  const unsigned long long gran = kWindow;  // whole windows
+  return (uint32_t)((cap + gran - 1ull) / gran * gran);
 }
 
 struct RenderSetup {
@@ -1299,7 +1343,7 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
     q.free_slots = b; b += windows ? 0 : P;
     for (int k = 0; k < kNumKinds; ++k) { q.kind[k] = b; b += windows ? 0 : P; }
     q.shadow = c->d_shadow.as<float4>();
-    q.n_windows = P / kWindow;  // P is a multiple of 256
+    q.n_windows = P / kWindow;  // P is a multiple of kWindow
     const size_t n_seg = (q.n_windows + kSegWindows - 1) / kSegWindows;
     q.win_count = q.win_prefix = q.seg_total = nullptr;
     q.bin = nullptr;
@@ -1421,7 +1465,7 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
     const uint32_t g = (uint32_t)persistent_grid(c, k, T), need = (items + items_per_block - 1) / items_per_block;
     return g < need ? g : (need ? need : 1u);
   };
-  const uint32_t grid_fill = capped((const void*)k_win_fill, 32u * (T / 32), q.n_windows);
+  const uint32_t grid_fill = capped((const void*)k_win_fill, kFillGroup, q.n_windows);
   // k_shade is register-heavy (84 naive / 116 MIS): 128-thread blocks let more of them share an SM's register file
   // (window mode, C3: 256 threads 3438 Mrays/s, 128 -> 3500, 64 -> 3499)
   int TS = 128;

@@ -36,7 +36,7 @@ struct Queues {
   uint32_t* kind[kNumKinds];
   float4* shadow;  // 3 x float4 per entry: o.xyz|tmax, d.xyz|exclude slot, contrib.rgb|path slot
   // window mode (see "window wavefront" below)
-  uint32_t* win_count;   // [n_windows] live paths of each 256-slot window
+  uint32_t* win_count;   // [n_windows] live paths of each kWindow-slot window
   uint32_t* win_prefix;  // [n_windows] exclusive prefix of win_count inside the window's 4096-window segment
   uint32_t* seg_total;   // [n_windows / 4096 + 1] live paths per segment
   uint8_t* bin;          // [capacity] direction bin of the path's next ray, kBinDead once the path has finished
@@ -913,10 +913,10 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
 // When every camera path of a chunk fits the pool, the wavefront needs no free list and no compaction of scattered slots:
 // path g of the chunk lives in slot g for its whole life (pixel-major, the samples of a pixel adjacent), and each
 // iteration's trace queue is rebuilt IN SLOT ORDER from per-slot state: k_shade leaves a direction bin (or "dead") per
-// slot and keeps a live count per 256-slot window; a prefix sum over the window counts places every window's live slots
+// slot and keeps a live count per 4096-slot window; a prefix sum over the window counts places every window's live slots
 // in the queue, ordered by direction bin inside the window. Consequences, all measured (profiles/r1_sweeps.md): the rays a
 // k_trace warp fetches share a pixel (origin) and roughly a direction at every depth, path records are gathered from one
-// 16 KB window at a time instead of from the whole pool, and iteration k holds exactly the rays of bounce k.
+// 256 KB window at a time instead of from the whole pool, and iteration k holds exactly the rays of bounce k.
 //   k_win_init       window counts of a fresh chunk (its camera rays are computed by the first k_trace itself)
 //   k_win_scan       per 4096-window segment: exclusive prefix of the counts + segment total
 //   k_win_prepare    1 warp: statistics of the finished iteration, total of live paths, cursor resets

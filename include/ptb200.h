@@ -223,14 +223,19 @@ int32_t ptb_bvh_export(ptb_ctx* ctx, uint32_t* morton_sorted, uint32_t* prim_sor
 
 /* ---------------------------------------------------------- closest hit -- */
 /* Replaces AccelerationStructure::check_hit (acceleration/mod.rs:265-298) for a batch of rays.
- * Host buffers; H2D + kernel + D2H. */
+ * Host buffers; H2D + kernel + D2H. hits[i] answers rays[i]; internally batches of >= 65 536 rays are traced in a
+ * spatially sorted order (PTB_HIT_SORT=0 disables), which needs 16 B of device scratch per ray. */
 int32_t ptb_closest_hit(ptb_ctx* ctx, const ptb_ray* rays, size_t n, ptb_hit* hits);
 /* Same, buffers already resident in device memory (kernel only; used for roofline timing). */
 int32_t ptb_closest_hit_device(ptb_ctx* ctx, const void* d_rays, size_t n, void* d_hits);
 
 /* --------------------------------------------------------------- render -- */
 /* Replaces Sampler::sample_image (samplers/mod.rs:7-20, random_sampler.rs:10-99) + the running mean of
- * src/main.rs:175-191: adds opts->samples_per_pixel samples per pixel into the device accumulator (sums). */
+ * src/main.rs:175-191: adds opts->samples_per_pixel samples per pixel into the device accumulator (sums).
+ * Device memory: the call keeps up to 2^29 camera paths resident at once (69 B per path, 133 B with MIS; e.g. 36 GB for
+ * 1920x1080x256), never more than half of the memory that was free at the context's first large render; larger calls run
+ * chunk by chunk. PTB_POOL_PATHS=<paths> caps it, PTB_WAVEFRONT=queue selects the small-pool regenerating mode. The
+ * image is a pure function of (scene, opts): pool size, chunking and GPU count only change the f32 summation order. */
 int32_t ptb_render(ptb_ctx* ctx, const ptb_render_opts* opts, ptb_progress_fn progress, void* user);
 /* The reference's per-pass presentation contract (random_sampler.rs:31-98, SamplerProgress samplers/mod.rs:49-63): one
  * pass = one sample of every pixel. `update` receives the SINGLE-SAMPLE image of a finished pass (row-major, top row

@@ -1318,20 +1318,29 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
     windows = false;
     P = pool_capacity_for(c, total, rs.mis, false);
   }
-  rs.P = P;
-
   // ---- device state (grow-only across calls; the MIS-only arrays are allocated by the first MIS call)
   // one 64-byte block per path: ray record then colour record (a DRAM access atom; two scattered 32-byte sectors per
-  // path cost generate/shade ~1 TB/s of effective write bandwidth)
-  PTB_CUDA_TRY(c, c->d_pool_mem.reserve((size_t)P * 64));
+  // path cost generate/shade ~1 TB/s of effective write bandwidth). If the device cannot provide the pool (another
+  // process holds the memory), the pool is halved and the call runs in more chunks.
+  for (;;) {
+    const size_t n_seg = ((size_t)P / kWindow + kSegWindows - 1) / kSegWindows;
+    const size_t win_bytes = windows ? ((((size_t)P / kWindow * 2 + n_seg + 3) & ~(size_t)3) * 4 + (size_t)P) : 0;
+    cudaError_t e = c->d_pool_mem.reserve((size_t)P * 64);
+    if (e == cudaSuccess) e = c->d_queues.reserve((size_t)P * 4 * (windows ? 1 : 3 + kNumKinds));
+    if (e == cudaSuccess && rs.mis) e = c->d_prev.reserve((size_t)P * 16);
+    if (e == cudaSuccess && rs.mis) e = c->d_shadow.reserve((size_t)P * 48);
+    if (e == cudaSuccess && windows) e = c->d_windows.reserve(win_bytes);
+    if (e == cudaSuccess) break;
+    if (e != cudaErrorMemoryAllocation || P <= (1u << 20)) return check_cuda(c, e, "path pool allocation");
+    cudaGetLastError();  // clear the sticky allocation error
+    free_render_state(c);
+    P = (P / 2 + kWindow - 1) / kWindow * kWindow;
+    if (windows && P < (1u << 25) && !forced_windows) windows = false;  // too many chunks for window mode
+  }
+  rs.P = P;
   c->pool.capacity = P;
   c->pool.ray = c->d_pool_mem.as<float4>();
   c->pool.col = c->pool.ray + 2;
-  PTB_CUDA_TRY(c, c->d_queues.reserve((size_t)P * 4 * (windows ? 1 : 3 + kNumKinds)));
-  if (rs.mis) {
-    PTB_CUDA_TRY(c, c->d_prev.reserve((size_t)P * 16));
-    PTB_CUDA_TRY(c, c->d_shadow.reserve((size_t)P * 48));
-  }
   c->pool.prev = c->d_prev.as<float4>();
   PTB_CUDA_TRY(c, c->d_counters.reserve(sizeof(WaveCounters) + 64));
   Queues& q = rs.q;
@@ -1349,7 +1358,6 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
     q.bin = nullptr;
     if (windows) {
       const size_t words = ((size_t)q.n_windows * 2 + n_seg + 3) & ~(size_t)3;  // keeps the byte array 16-byte aligned
-      PTB_CUDA_TRY(c, c->d_windows.reserve(words * 4 + (size_t)P));
       uint32_t* w = c->d_windows.as<uint32_t>();
       q.win_count = w;
       q.win_prefix = w + q.n_windows;

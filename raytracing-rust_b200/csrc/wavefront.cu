@@ -2,16 +2,17 @@
 // (implementations/src/samplers/random_sampler.rs:23-99, integrators/mod.rs:22-78, integrators/mis.rs:6-157) and
 // everything they call per bounce (materials/*.rs, sky.rs, textures/mod.rs, primitives light sampling).
 //
-// One wavefront iteration =
-//   k_prepare   (1 thread)   pool bookkeeping: how many camera paths to regenerate into freed slots, queue resets
-//   k_generate  K1           camera rays for (pixel, sample) pairs          random_sampler.rs:50-61, camera.rs:57-63
-//   k_trace     K8 + K11     closest hit for every live path (persistent warps pulling 32-ray batches), result
-//                            pushed to one queue per material kind (warp-aggregated atomics)
-//   k_shade     K10 + K12    per material-kind queue: emission, MIS weights, NEE sample -> shadow queue, BSDF sample
-//                            -> next ray, Russian roulette, path termination -> accumulator
+// Window mode (default; see "window wavefront" below): every camera path of a chunk is resident, path g owns slot g, and
+// one iteration traces and shades bounce k of ALL of them:
+//   k_win_scan / k_win_prepare / k_win_fill   live counts -> ordered trace queue (slot order, direction-ordered per window)
+//   k_trace     K1 + K8      closest hit for every live path (persistent warps pulling 32-ray batches); the first
+//                            iteration of a chunk computes its camera rays in the fetch (random_sampler.rs:50-61,
+//                            camera.rs:57-63)
+//   k_shade     K10 + K12    emission, MIS weights, NEE sample -> shadow queue, BSDF sample -> next ray (written in place),
+//                            Russian roulette, path termination -> accumulator
 //   k_shadow    K9           any-hit for the NEE queue; unoccluded contributions are added to the path's radiance
-// Paths live in pool slots (SoA float4 records); queues carry slot indices. A finished path frees its slot, which
-// the next k_generate refills, so the device stays full until the last sample has been issued.
+// Queue mode (pools smaller than the call): k_prepare / k_generate refill freed slots with camera paths every iteration,
+// k_trace pushes its results to one queue per material kind, k_shade walks those queues.
 //
 // The RNG is counter-based (Philox4x32-10 keyed by seed; counter = pixel, absolute sample, depth|purpose, block):
 // the image is a pure function of (scene, seed, sample range) — independent of pool size, scheduling and GPU count.

@@ -356,7 +356,9 @@ struct TraceRetire {
 #define PTB_TRACE_MIN_BLOCKS 5  // 48 registers: +4 % over the unconstrained 56-register build (sweep in profiles/)
 #endif
 #ifndef PTB_SHADE_MIN_BLOCKS
-#define PTB_SHADE_MIN_BLOCKS 2  // caps k_shade<MIS> at 128 registers (2 x 256 threads per SM): +6 % on rtweekend1 4K
+#define PTB_SHADE_MIN_BLOCKS 4  // caps k_shade at 64 registers (32 B of spills). Window mode streams its records, so occupancy
+                                // pays now: 2 -> 4 blocks: C3 3664 -> 3746 Mrays/s, rtweekend1 4K MIS 8439 -> 8967 (queue mode
+                                // preferred 2: 128 registers, profiles/r1_sweeps.md)
 #endif
 template <bool COUNT, bool DENSE, bool CAMERA>
 __global__ void __launch_bounds__(256, PTB_TRACE_MIN_BLOCKS)

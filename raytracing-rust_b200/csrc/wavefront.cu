@@ -353,7 +353,7 @@ struct TraceRetire {
 };
 
 #ifndef PTB_TRACE_MIN_BLOCKS
-#define PTB_TRACE_MIN_BLOCKS 5  // 48 registers: +4 % over the unconstrained 56-register build (sweep in profiles/)
+#define PTB_TRACE_MIN_BLOCKS 6  // 40 registers. Window mode, C3: 4 blocks (64 registers) 3611 Mrays/s, 5 (48) 3664, 6 (40) 3730
 #endif
 #ifndef PTB_SHADE_MIN_BLOCKS
 #define PTB_SHADE_MIN_BLOCKS 4  // caps k_shade at 64 registers (32 B of spills). Window mode streams its records, so occupancy
@@ -1373,10 +1373,13 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
 
   RenderParams& rp = rs.rp;
   rp.width = o.width; rp.height = o.height; rp.npix = npix;
+  // Pixel issue order: 32 consecutive pixel indices cover an 8 x 4 tile when the image allows (else 16 x 2, else a row), so
+  // the 16 pixels of a 4096-slot window are an 8 x 2 block instead of a 16 x 1 strip: the origins of a window's rays lie
+  // closer together. Window mode, C3: 3793 -> 3834 Mrays/s (queue mode preferred rows). PTB_TILES=0 keeps rows.
   rp.tile_w = 32u; rp.tile_h = 1u;
-  // Measured on B200 (C3 and rtweekend1 4K): 8x4 tiles gain nothing in k_trace (-2 %) and cost 5 % in k_shade (less
-  // coalesced accumulator atomics), so row-major order is the default; PTB_TILES=1 enables the tiled order.
-  if (getenv("PTB_TILES"))
+  bool tiles = true;
+  if (const char* e = getenv("PTB_TILES")) tiles = atoi(e) != 0;
+  if (tiles)
     for (uint32_t th = 4u; th > 1u; th >>= 1)
       if (o.height % th == 0u && o.width % (32u / th) == 0u) { rp.tile_h = th; rp.tile_w = 32u / th; break; }
   // samples of one pixel issued back to back: the largest divisor of spp <= 1024 (PTB_SAMPLE_GROUP). Measured on C3 at

@@ -27,14 +27,14 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of k_trace per ray, from the committed ncu capture (profiles/r1_final_c3.md:
 # the camera, first-bounce and second-bounce launches of a 16-spp render, 95 % of its rays)
-NCU_DRAM_BYTES_PER_RAY = {"c3": (0.0626e9 + 1.127e9 + 1.768e9 + 0.6912e9 + 0.6637e9 + 0.1826e9) / (33.18e6 + 19.3e6 + 4.6e6)}
+NCU_DRAM_BYTES_PER_RAY = {"c3": (0.0822e9 + 1.218e9 + 1.916e9 + 0.8525e9 + 0.7222e9 + 0.2345e9) / (33.18e6 + 19.3e6 + 4.6e6)}
 # what ncu says actually limits k_trace on C3 (same capture, weighted over the three launches): the scene is L2 resident,
 # so the HBM roofline does not bind
-NCU_LIMITER = {"c3": {"unit": "SM issue slots / L1 data-pipe wavefronts", "issue_active_pct": 74.2, "l1_data_pipe_pct": 71.4,
-                      "active_lanes_per_instruction": 19.5, "l2_hit_pct": 71.6,
-                      "per_launch": {"camera": {"issue_active_pct": 81.5, "lanes": 24.3, "l1_data_pipe_pct": 65.7},
-                                     "first_bounce": {"issue_active_pct": 71.6, "lanes": 16.7, "l1_data_pipe_pct": 73.8},
-                                     "second_bounce": {"issue_active_pct": 67.7, "lanes": 16.2, "l1_data_pipe_pct": 75.5}},
+NCU_LIMITER = {"c3": {"unit": "SM issue slots / L1 data-pipe wavefronts", "issue_active_pct": 75.5, "l1_data_pipe_pct": 78.6,
+                      "active_lanes_per_instruction": 19.9, "l2_hit_pct": 74.1,
+                      "per_launch": {"camera": {"issue_active_pct": 82.8, "lanes": 24.0, "l1_data_pipe_pct": 67.0},
+                                     "first_bounce": {"issue_active_pct": 72.5, "lanes": 17.4, "l1_data_pipe_pct": 86.8},
+                                     "second_bounce": {"issue_active_pct": 68.6, "lanes": 16.6, "l1_data_pipe_pct": 81.0}},
                       "source": "profiles/r1_final_c3.md"}}
 
 
@@ -375,9 +375,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
                          # DRAM bytes per k_trace launch: per-ray figure from the committed `ncu --set full` capture
-                         # (profiles/r1_final_c3.md: 4.50 GB read + written over the 57.1 M rays of the first three
+                         # (profiles/r1_final_c3.md: 5.03 GB read + written over the 57.1 M rays of the first three
                          # launches) x this run's mean rays per launch. The 1 M-triangle scene is L2 resident, so real
-                         # traffic is ~27x below the algorithmic bytes and `frac` can exceed 1: the kernel is bound by
+                         # traffic is ~24x below the algorithmic bytes and `frac` can exceed 1: the kernel is bound by
                          # issue slots and L1 wavefronts (`limiter`), not by HBM.
                          "traffic": (NCU_DRAM_BYTES_PER_RAY.get(args.workload) * traced / max(int(st.trace_launches), 1)
                                      if NCU_DRAM_BYTES_PER_RAY.get(args.workload) else None),

@@ -50,13 +50,22 @@ PTB_DEV void ldg256(const void* p, float4& a, float4& b) {
       : "l"(p));
 #endif
 }
+#ifndef PTB_STREAM_HINTS
+#define PTB_STREAM_HINTS 0  // 1 = path records are loaded / stored with the evict-first (.cs) policy so that they do not displace
+                            // BVH nodes and triangles from L2
+#endif
+#if PTB_STREAM_HINTS
+#define PTB_CS ".cs"
+#else
+#define PTB_CS ""
+#endif
 PTB_DEV void ldg256_rw(const void* p, float4& a, float4& b) {  // same, for data this launch sequence also writes (no .nc)
-  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global" PTB_CS ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                : "l"(p) : "memory");
 }
 PTB_DEV void stg256(void* p, float4 a, float4 b) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+  asm volatile("st.global" PTB_CS ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
 }
 PTB_DEV void load_node(const BvhNode* __restrict__ nodes, uint32_t idx, float4& n0, float4& n1, float4& n2, uint4& n3) {

@@ -586,7 +586,6 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
          &nbmin = c->scratch[9], &nbmax = c->scratch[10], &flags = c->scratch[11], &prim_slot = c->scratch[12],
          &d_light_prims = c->scratch[13], &d_light_tmp = c->scratch[14], &d_light_out = c->scratch[15];
   const uint32_t n32 = (uint32_t)n, ns32 = (uint32_t)ns, nt32 = (uint32_t)nt;
-  const uint32_t n_tiles = (n32 + RS_TILE - 1) / RS_TILE;
   PTB_CUDA_TRY(c, bmin.reserve(n * 16));
   PTB_CUDA_TRY(c, bmax.reserve(n * 16));
   PTB_CUDA_TRY(c, bounds.reserve(6 * 4));
@@ -663,7 +662,7 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
     PTB_CUDA_TRY(c, c->d_lights.reserve((size_t)nl * 4));
     uint32_t *la = d_light_prims.as<uint32_t>(), *lb = d_light_tmp.as<uint32_t>();
     if (nl > 1) {
-      const uint32_t lt = (nl + RS_TILE - 1) / RS_TILE;  // <= n_tiles: hist is large enough
+      // nl <= n: the histogram scratch is large enough
       // values ride along unused: keys double as values (keys_b / vals_b are free again)
       uint32_t *lva = keys_b.as<uint32_t>(), *lvb = vals_b.as<uint32_t>();
       radix_sort_pairs(c, la, lva, lb, lvb, nl, 4, hist.as<uint32_t>());

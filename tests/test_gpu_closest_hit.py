@@ -176,3 +176,19 @@ def test_full_size_heightfield_properties(ptb, gpu_ctx):
     perm = np.random.default_rng(3).permutation(n)
     again = gpu_ctx.closest_hit(rays[perm])
     assert np.array_equal(again, hits[perm])
+
+
+def test_batch_ordering_does_not_change_results(ptb, gpu_ctx, monkeypatch):
+    """ptb_closest_hit orders batches of >= 65 536 rays (k_ray_sort_keys: reaches the scene box, Morton code of the entry
+    point, octant) and traces them through an index array: hits[i] must still answer rays[i], bit for bit."""
+    s = ptb.meshgen.c3_scene(0.1)
+    gpu_ctx.upload(s)
+    gpu_ctx.commit()
+    rays = random_rays(ptb, 150_000, 31, centre=(0, 4, 1), radius=6.0)
+    a = gpu_ctx.closest_hit(rays)
+    monkeypatch.setenv("PTB_HIT_SORT", "0")
+    b = gpu_ctx.closest_hit(rays)
+    monkeypatch.delenv("PTB_HIT_SORT")
+    assert 0.05 < np.mean(a["prim"] != ptb.PTB_MISS) < 0.95
+    for f in ("t", "prim", "u", "v"):
+        assert np.array_equal(a[f].view(np.uint32), b[f].view(np.uint32)), f

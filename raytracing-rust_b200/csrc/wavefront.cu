@@ -1490,6 +1490,8 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true, true, false> : (const void*)k_trace<false, true, false>, T);
   const int grid_trace_cam = persistent_grid(c, count ? (const void*)k_trace<true, true, true> : (const void*)k_trace<false, true, true>, T);
   const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
+  int cam_fetch = c->dev.trace_fetch_threshold < 4 ? c->dev.trace_fetch_threshold : 4;
+  if (const char* e = getenv("PTB_TRACE_FETCH_CAMERA")) { int v = atoi(e); if (v >= 1 && v <= 32) cam_fetch = v; }
 
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
   k_init_pool<<<1, 32, 0, st>>>(q.active[0], 0u, wc, total);  // counters only
@@ -1514,8 +1516,12 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
       PTB_PROF(0, 1);
       PTB_PROF(1, 0);
       if (depth == 0) {
-        if (count) k_trace<true, true, true><<<grid_trace_cam, T, 0, st>>>(c->dev, c->pool, q, wc, rs.rp, first);
-        else k_trace<false, true, true><<<grid_trace_cam, T, 0, st>>>(c->dev, c->pool, q, wc, rs.rp, first);
+        // camera rays of a warp finish together: refilling later (fewer, fuller service passes) suits them
+        // (C3, camera rays only: threshold 8 -> 8105 Mrays/s, 4 -> 8311; bounce rays prefer 8, profiles/r1_sweeps.md)
+        DevScene cam = c->dev;
+        cam.trace_fetch_threshold = cam_fetch;
+        if (count) k_trace<true, true, true><<<grid_trace_cam, T, 0, st>>>(cam, c->pool, q, wc, rs.rp, first);
+        else k_trace<false, true, true><<<grid_trace_cam, T, 0, st>>>(cam, c->pool, q, wc, rs.rp, first);
       } else {
         if (count) k_trace<true, true, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc, rs.rp, 0ull);
         else k_trace<false, true, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc, rs.rp, 0ull);

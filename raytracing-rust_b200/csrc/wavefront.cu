@@ -1100,7 +1100,15 @@ struct ShadowRetire {
     }
   }
 };
-__global__ void __launch_bounds__(256) k_shadow(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
+// same-run A/B (profiles/r1_sweeps.md): k_closest_hit_api at 6 blocks / SM (40 registers) C5 4116 -> 4816 Mrays/s; k_shadow
+// prefers its unconstrained 63 registers (rtweekend1 4K: 10 ms vs 13 - 14 ms of shadow per 3 steps)
+#ifndef PTB_SHADOW_MIN_BLOCKS
+#define PTB_SHADOW_MIN_BLOCKS 1
+#endif
+#ifndef PTB_API_MIN_BLOCKS
+#define PTB_API_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(256, PTB_SHADOW_MIN_BLOCKS) k_shadow(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
   uint32_t a = 0, b = 0, r = 0;
   ShadowFetch fetch{q, make_float4(0.f, 0.f, 0.f, 0.f)};
   ShadowRetire retire{pool, fetch};
@@ -1178,7 +1186,7 @@ struct ApiRetire {
   }
 };
 template <bool COUNT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PTB_API_MIN_BLOCKS)
 k_closest_hit_api(DevScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ order, uint32_t n,
                   uint4* __restrict__ hits, uint32_t* head, unsigned long long* counts) {
   const uint32_t lane = threadIdx.x & 31u;

@@ -238,3 +238,21 @@ def test_window_and_queue_wavefronts_agree(ptb, gpu_ctx, overshadowed, method, m
     assert ca[0] == 96 * 54 * 12 and ca[5] == 96 * 54 * 12
     assert ca == cb == cc
     assert np.allclose(a, b, rtol=1e-5, atol=1e-5) and np.allclose(a, c, rtol=1e-5, atol=1e-5)
+
+
+def test_abort_between_chunks_in_window_mode(ptb, gpu_ctx, rtweekend1, monkeypatch):
+    """Window mode calls the progress callback after each chunk; a non-zero return aborts the render (PTB_ERR_ABORTED),
+    as `true` from the reference's per-pass closure does (random_sampler.rs:82-88)."""
+    sc = ptb.Scene(rtweekend1, ctx=gpu_ctx)
+    monkeypatch.setenv("PTB_WAVEFRONT", "window")
+    monkeypatch.setenv("PTB_POOL_PATHS", "8192")
+    seen = []
+    with pytest.raises(ptb.PtbError) as e:
+        sc.render(ptb.RenderOptions(samples_per_pixel=16, render_method=0, width=64, height=36),
+                  update=lambda s, r: seen.append(s) or len(seen) >= 2)
+    monkeypatch.delenv("PTB_WAVEFRONT")
+    monkeypatch.delenv("PTB_POOL_PATHS")
+    assert e.value.code == 7 and len(seen) == 2 and seen[0] < seen[1] < 16
+    # the context stays usable
+    img = sc.render(ptb.RenderOptions(samples_per_pixel=2, render_method=0, width=64, height=36))
+    assert np.all(np.isfinite(img))

@@ -235,7 +235,10 @@ int32_t ptb_closest_hit_device(ptb_ctx* ctx, const void* d_rays, size_t n, void*
  * Device memory: the call keeps up to 2^29 camera paths resident at once (69 B per path, 133 B with MIS; e.g. 36 GB for
  * 1920x1080x256), never more than half of the memory that was free at the context's first large render; larger calls run
  * chunk by chunk. PTB_POOL_PATHS=<paths> caps it, PTB_WAVEFRONT=queue selects the small-pool regenerating mode. The
- * image is a pure function of (scene, opts): pool size, chunking and GPU count only change the f32 summation order. */
+ * image is a pure function of (scene, opts): pool size, chunking and GPU count only change the f32 summation order
+ * (finished paths are added with float atomics, so two runs of the same call agree to ~1e-6 relative, not bit for bit).
+ * A non-zero return of `progress` stops the call with PTB_ERR_ABORTED and CLEARS the accumulator (samples of earlier
+ * calls included): a partially rendered call has no sample count to normalise by. */
 int32_t ptb_render(ptb_ctx* ctx, const ptb_render_opts* opts, ptb_progress_fn progress, void* user);
 /* The reference's per-pass presentation contract (random_sampler.rs:31-98, SamplerProgress samplers/mod.rs:49-63): one
  * pass = one sample of every pixel. `update` receives the SINGLE-SAMPLE image of a finished pass (row-major, top row

@@ -51,6 +51,7 @@ def _load():
     lib.orc_bvh_order.argtypes = [P, P]
     lib.orc_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_closest_hit_brute.argtypes = [P, P, C.c_size_t, P, C.c_int]
+    lib.orc_closest_hit_f64.argtypes = [P, P, C.c_size_t, P, P, C.c_int]
     lib.orc_hit_record.argtypes = [P, P, P]
     lib.orc_hit_record.restype = C.c_int
     lib.orc_render.restype = C.c_double
@@ -157,6 +158,15 @@ class OracleScene:
         out = np.zeros(len(rays), hit_dtype)
         lib.orc_closest_hit_brute(self._h, _p(rays), len(rays), _p(out), threads)
         return out
+
+    def closest_hit_f64(self, rays, threads=0):
+        """Independent f64 Moller-Trumbore / quadratic intersector over every primitive (no BVH): (hits, margin).
+        `margin` is small where the f32 watertight path may legitimately decide differently (edge grazing, near ties)."""
+        rays = np.ascontiguousarray(rays, dtype=ray_dtype)
+        out = np.zeros(len(rays), hit_dtype)
+        margin = np.zeros(len(rays), np.float32)
+        lib.orc_closest_hit_f64(self._h, _p(rays), len(rays), _p(out), _p(margin), threads)
+        return out, margin
 
     def sah_ordered_closest_hit(self, rays, threads=0):
         """Ordered, t-culled traversal of the reference's SAH tree: (hits, internal nodes expanded, prims tested)."""

@@ -1,7 +1,9 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see ref_math.hpp header).
 // C entry points (ctypes-friendly) over the CPU restatement. Used by tests/, smoke() and bench.py's CPU legs.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <thread>
 #include <vector>
@@ -159,6 +161,82 @@ void orc_closest_hit_brute(const orc_scene* s, const ptb_ray* rays, size_t n, pt
         if (p.get_int(ray, h) && h.t > 0.0f && (bp == PTB_MISS || h.t < best.t)) { best = h; bp = p.orig_id; }
       }
       fill_hit(out[i], bp != PTB_MISS, best, bp);
+    }
+  });
+}
+
+// INDEPENDENT intersector: double precision, a different formulation from the reference's — Möller &
+// Trumbore 1997 ("Fast, minimum storage ray/triangle intersection": edge vectors, scalar triple products, no shear, no
+// axis permutation, no error bounds) for triangles and the textbook quadratic for spheres — over EVERY primitive, no
+// acceleration structure. It shares no arithmetic with triangle.rs:105-216 / sphere.rs:34-105 or with the slab test, so
+// agreement on non-degenerate rays pins the f32 watertight path against something other than a copy of itself.
+//   out[i]     = closest hit (t, original primitive id, barycentrics b1 b2 as the reference reports them), f64 rounded to f32
+//   margin[i]  = how far the ray is from a decision the two formulations may legitimately take differently:
+//                min( smallest barycentric coordinate of the winning triangle            (edge / vertex grazing),
+//                     sqrt(discriminant) / radius of the winning sphere                  (silhouette grazing),
+//                     relative t gap to the runner-up hit                                (near ties),
+//                     -(largest "smallest barycentric" over the triangles just missed)   (a grazing near-miss) )
+//                Tests compare ids only where margin > a stated threshold.
+void orc_closest_hit_f64(const orc_scene* s, const ptb_ray* rays, size_t n, ptb_hit* out, float* margin, int threads) {
+  struct D3 { double x, y, z; };
+  auto sub = [](D3 a, D3 b) { return D3{a.x - b.x, a.y - b.y, a.z - b.z}; };
+  auto dot = [](D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; };
+  auto cross = [](D3 a, D3 b) { return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; };
+  auto d3 = [](const Vec3& v) { return D3{(double)v.x, (double)v.y, (double)v.z}; };
+  parallel_for(n, threads, [&](unsigned, size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      const D3 o{rays[i].ox, rays[i].oy, rays[i].oz};
+      D3 d{rays[i].dx, rays[i].dy, rays[i].dz};
+      // the reference normalises in f32 (ray.rs:14) and reports t along that unit vector: do the same, then widen
+      {
+        Vec3 df = normalised(Vec3(rays[i].dx, rays[i].dy, rays[i].dz));
+        d = d3(df);
+      }
+      double best_t = 1e300, second_t = 1e300, best_m = 1e300, near_miss = -1e300, bb1 = 0.0, bb2 = 0.0;
+      uint32_t bp = PTB_MISS;
+      for (const Prim& p : s->prims_original) {
+        double t, m, b1 = 0.0, b2 = 0.0;
+        if (p.is_sphere) {
+          const D3 oc = sub(o, d3(p.center));
+          const double r = (double)p.radius;
+          const double hb = dot(oc, d), cc = dot(oc, oc) - r * r, dd = dot(d, d);
+          const double disc = hb * hb - dd * cc;
+          if (disc <= 0.0) { near_miss = std::max(near_miss, -std::sqrt(-disc) / (std::fabs(r) * std::sqrt(dd))); continue; }
+          const double sq = std::sqrt(disc);
+          double t0 = (-hb - sq) / dd, t1 = (-hb + sq) / dd;
+          t = t0 > 0.0 ? t0 : t1;
+          if (!(t > 0.0)) continue;
+          m = sq / (std::fabs(r) * std::sqrt(dd));
+        } else {
+          const D3 v0 = d3(p.p[0]), e1 = sub(d3(p.p[1]), v0), e2 = sub(d3(p.p[2]), v0);
+          const D3 pv = cross(d, e2);
+          const double det = dot(e1, pv);
+          if (det == 0.0) continue;
+          const double inv = 1.0 / det;
+          const D3 tv = sub(o, v0);
+          const double u = dot(tv, pv) * inv;
+          const D3 qv = cross(tv, e1);
+          const double v = dot(d, qv) * inv;
+          t = dot(e2, qv) * inv;
+          const double w = 1.0 - u - v;
+          const double mb = std::min(u, std::min(v, w));
+          if (!(t > 0.0)) continue;
+          if (mb < 0.0) { near_miss = std::max(near_miss, mb); continue; }
+          m = mb;
+          b1 = u; b2 = v;  // triangle.rs:149-151: b1, b2 weight p1, p2
+        }
+        if (t < best_t) { second_t = best_t; best_t = t; best_m = m; bp = p.orig_id; bb1 = b1; bb2 = b2; }
+        else if (t < second_t) second_t = t;
+      }
+      double mg = -near_miss;
+      if (bp != PTB_MISS) {
+        mg = std::min(mg, best_m);
+        if (second_t < 1e299) mg = std::min(mg, (second_t - best_t) / std::max(best_t, 1e-30));
+        out[i].t = (float)best_t; out[i].prim = bp; out[i].u = (float)bb1; out[i].v = (float)bb2;
+      } else {
+        out[i].t = 0.0f; out[i].prim = PTB_MISS; out[i].u = out[i].v = 0.0f;
+      }
+      if (margin) margin[i] = (float)std::min(mg, 1e30);
     }
   });
 }

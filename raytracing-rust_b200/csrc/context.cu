@@ -324,27 +324,41 @@ int32_t ptb_closest_hit(ptb_ctx* ctx, const ptb_ray* rays, size_t n, ptb_hit* hi
       PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_out[b], cudaEventDisableTiming));
     }
   }
+  // On any failure the copies of earlier batches may still be in flight against the caller's `rays` / `hits`: drain all
+  // three streams before returning, the caller is free to release its buffers as soon as the call is back.
+  auto drain = [&](int32_t rc) {
+    cudaStreamSynchronize(c->s_out);
+    cudaStreamSynchronize(c->s_in);
+    cudaStreamSynchronize(c->stream);
+    return rc;
+  };
+#define PTB_TRY_DRAIN(expr)                                                  \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) return drain(ptb::check_cuda(c, _e, #expr));      \
+  } while (0)
   // the staging buffers may still be in use by earlier work on the main stream
-  PTB_CUDA_TRY(c, cudaEventRecord(c->ev_kernel[0], c->stream));
-  PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_kernel[0], 0));
+  PTB_TRY_DRAIN(cudaEventRecord(c->ev_kernel[0], c->stream));
+  PTB_TRY_DRAIN(cudaStreamWaitEvent(c->s_in, c->ev_kernel[0], 0));
   size_t k = 0;
   for (size_t off = 0; off < n; off += chunk, ++k) {
     const size_t m = n - off < chunk ? n - off : chunk;
     const int b = (int)(k & 1u);
-    if (k >= 2) PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_in, c->ev_kernel[b], 0));  // batch k-2 no longer reads d_rays[b]
-    PTB_CUDA_TRY(c, cudaMemcpyAsync(dr[b]->p, rays + off, m * sizeof(ptb_ray), cudaMemcpyHostToDevice, c->s_in));
-    PTB_CUDA_TRY(c, cudaEventRecord(c->ev_in[b], c->s_in));
-    PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
-    if (k >= 2) PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_out[b], 0));     // batch k-2's hits left d_hits[b]
+    if (k >= 2) PTB_TRY_DRAIN(cudaStreamWaitEvent(c->s_in, c->ev_kernel[b], 0));  // batch k-2 no longer reads d_rays[b]
+    PTB_TRY_DRAIN(cudaMemcpyAsync(dr[b]->p, rays + off, m * sizeof(ptb_ray), cudaMemcpyHostToDevice, c->s_in));
+    PTB_TRY_DRAIN(cudaEventRecord(c->ev_in[b], c->s_in));
+    PTB_TRY_DRAIN(cudaStreamWaitEvent(c->stream, c->ev_in[b], 0));
+    if (k >= 2) PTB_TRY_DRAIN(cudaStreamWaitEvent(c->stream, c->ev_out[b], 0));     // batch k-2's hits left d_hits[b]
     int32_t rc = launch_closest_hit(c, dr[b]->p, m, dh[b]->p);
-    if (rc != PTB_OK) return rc;
-    PTB_CUDA_TRY(c, cudaEventRecord(c->ev_kernel[b], c->stream));
-    PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_out, c->ev_kernel[b], 0));
-    PTB_CUDA_TRY(c, cudaMemcpyAsync(hits + off, dh[b]->p, m * sizeof(ptb_hit), cudaMemcpyDeviceToHost, c->s_out));
-    PTB_CUDA_TRY(c, cudaEventRecord(c->ev_out[b], c->s_out));
+    if (rc != PTB_OK) return drain(rc);
+    PTB_TRY_DRAIN(cudaEventRecord(c->ev_kernel[b], c->stream));
+    PTB_TRY_DRAIN(cudaStreamWaitEvent(c->s_out, c->ev_kernel[b], 0));
+    PTB_TRY_DRAIN(cudaMemcpyAsync(hits + off, dh[b]->p, m * sizeof(ptb_hit), cudaMemcpyDeviceToHost, c->s_out));
+    PTB_TRY_DRAIN(cudaEventRecord(c->ev_out[b], c->s_out));
   }
-  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->s_out));
-  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  PTB_TRY_DRAIN(cudaStreamSynchronize(c->s_out));
+  PTB_TRY_DRAIN(cudaStreamSynchronize(c->stream));
+#undef PTB_TRY_DRAIN
   return PTB_OK;
 }
 
@@ -369,7 +383,16 @@ int32_t ptb_render(ptb_ctx* ctx, const ptb_render_opts* opts, ptb_progress_fn pr
   if (opts->method != PTB_METHOD_NAIVE && opts->method != PTB_METHOD_MIS) return set_error(c, PTB_ERR_INVALID, "unknown method");
   int32_t rc = ensure_accum(c, opts->width, opts->height);
   if (rc != PTB_OK) return rc;
-  return render_wavefront(c, *opts, progress, user);
+  rc = render_wavefront(c, *opts, progress, user);
+  if (rc == PTB_ERR_ABORTED) {
+    // An aborted call leaves the radiance of the paths that had finished in the accumulator (whole pixels in window
+    // mode) without a sample count to divide by: the accumulator is cleared, earlier samples included, exactly as the
+    // reference drops its buffers when the closure returns true (random_sampler.rs:84-86).
+    cudaMemsetAsync(c->d_accum.p, 0, (size_t)c->accum_w * c->accum_h * 12, c->stream);
+    cudaStreamSynchronize(c->stream);
+    c->accum_samples = 0;
+  }
+  return rc;
 }
 
 __global__ void k_add_into(const float* __restrict__ src, float* __restrict__ dst, size_t n) {

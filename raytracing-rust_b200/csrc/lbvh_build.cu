@@ -376,7 +376,7 @@ __global__ void k_single_node(const uint32_t* __restrict__ prim_sorted, uint32_t
 // ------------------------------------------------------------------------------------------ gather into slot order
 __global__ void k_gather(const ptb_sphere* __restrict__ spheres, uint32_t n_spheres, const ptb_triangle* __restrict__ tris,
                          uint32_t n_prims, const uint32_t* __restrict__ prim_sorted, const DevMaterial* __restrict__ mats,
-                         float4* __restrict__ geom, float4* __restrict__ normals, uint32_t* __restrict__ slot_mat,
+                         uint32_t n_mats, float4* __restrict__ geom, float4* __restrict__ normals, uint32_t* __restrict__ slot_mat,
                          uint32_t* __restrict__ prim_slot) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_prims) return;
@@ -405,7 +405,10 @@ __global__ void k_gather(const ptb_sphere* __restrict__ spheres, uint32_t n_sphe
   normals[3 * (size_t)slot + 0] = m0;
   normals[3 * (size_t)slot + 1] = m1;
   normals[3 * (size_t)slot + 2] = m2;
-  slot_mat[slot] = (mats[mat].kind << 24) | (mat & 0x00FFFFFFu);
+  // an out-of-range index is reported by k_collect_lights (commit then fails with PTB_ERR_INVALID); it must not be
+  // dereferenced here, the primitives never passed through the host
+  const uint32_t kind = mat < n_mats ? mats[mat].kind : 0u;
+  slot_mat[slot] = (kind << 24) | (mat & 0x00FFFFFFu);
 }
 __global__ void k_light_slots(const uint32_t* __restrict__ light_prims, uint32_t n_lights, uint32_t n_spheres,
                               const uint32_t* __restrict__ prim_slot, uint32_t* __restrict__ lights) {
@@ -647,7 +650,8 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
     c->stats.kernel_launches += 1;
   }
   k_gather<<<gn, T, 0, st>>>(raw_spheres.as<ptb_sphere>(), ns32, raw_tris.as<ptb_triangle>(), n32, va,
-                             c->d_materials.as<DevMaterial>(), c->d_geom.as<float4>(), c->d_normals.as<float4>(),
+                             c->d_materials.as<DevMaterial>(), (uint32_t)c->materials.size(), c->d_geom.as<float4>(),
+                             c->d_normals.as<float4>(),
                              c->d_slot_mat.as<uint32_t>(), prim_slot.as<uint32_t>());
   c->stats.kernel_launches += 1;
   // keep the sorted keys / ids for ptb_bvh_export and the traversal's tie-break

@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -157,6 +159,10 @@ bool inflate_raw(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
   return !br.bad;
 }
 
+// Header dimensions are untrusted: 65535 per side keeps every size product below 2^32 * 8 (no size_t wrap on 64-bit hosts)
+// and bounds the allocation a hostile header can request.
+bool dims_ok(uint32_t w, uint32_t h) { return w <= 65535u && h <= 65535u; }
+
 uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
 // ---------------------------------------------------------------------------------------------- png
@@ -179,9 +185,14 @@ bool decode_png(const std::vector<uint8_t>& f, uint32_t& w, uint32_t& h, std::ve
     pos += 12 + (size_t)len;
   }
   if (!have_ihdr || w == 0 || h == 0) { err = "png: missing IHDR"; return false; }
+  if (!dims_ok(w, h)) { err = "png: image dimensions above the supported 65535 x 65535"; return false; }
   if (interlace) { err = "png: interlaced files are not supported"; return false; }
   int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
-  if (!channels || !(depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) { err = "png: bad colour type"; return false; }
+  // PNG specification table 11.1: greyscale 1/2/4/8/16, palette 1/2/4/8, every other colour type 8/16
+  const bool depth_ok = ctype == 0 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)
+                        : ctype == 3 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8)
+                                     : (depth == 8 || depth == 16);
+  if (!channels || !depth_ok) { err = "png: bad colour type / bit depth combination"; return false; }
   if (idat.size() < 6) { err = "png: no image data"; return false; }
   std::vector<uint8_t> raw;
   if (!inflate_raw(idat.data() + 2, idat.size() - 2, raw)) { err = "png: corrupt deflate stream"; return false; }
@@ -262,6 +273,7 @@ bool decode_pnm(const std::vector<uint8_t>& f, uint32_t& w, uint32_t& h, std::ve
   h = (uint32_t)std::strtoul(t.c_str(), nullptr, 10);
   if (!tk.next(t)) { err = "pnm: truncated header"; return false; }
   if (w == 0 || h == 0) { err = "pnm: zero dimension"; return false; }
+  if (!dims_ok(w, h)) { err = "pnm: image dimensions above the supported 65535 x 65535"; return false; }
   rgb.resize((size_t)w * h * 3);
   if (pfm) {
     const double scale = std::strtod(t.c_str(), nullptr);
@@ -319,7 +331,8 @@ bool decode_bmp(const std::vector<uint8_t>& f, uint32_t& w, uint32_t& h, std::ve
   const uint32_t bpp = f[28] | (f[29] << 8), comp = le32(30);
   if (wi <= 0 || hi == 0 || (bpp != 24 && bpp != 32) || (comp != 0 && comp != 3)) { err = "bmp: only uncompressed 24/32-bit files are supported"; return false; }
   w = (uint32_t)wi;
-  h = (uint32_t)(hi < 0 ? -hi : hi);
+  h = hi < 0 ? (uint32_t)(-(int64_t)hi) : (uint32_t)hi;
+  if (!dims_ok(w, h)) { err = "bmp: image dimensions above the supported 65535 x 65535"; return false; }
   const size_t stride = (((size_t)w * bpp + 31) / 32) * 4;
   if ((size_t)off + stride * h > f.size()) { err = "bmp: truncated data"; return false; }
   rgb.resize((size_t)w * h * 3);
@@ -355,6 +368,7 @@ const char* ptb_image_last_error(void) { return g_image_error.c_str(); }
 
 int32_t ptb_image_load(const char* filename, uint32_t* width, uint32_t* height, float** rgb) {
   if (!filename || !width || !height || !rgb) return PTB_ERR_INVALID;
+  try {  // no C++ exception may cross the C boundary (std::bad_alloc from the decoders' buffers)
   std::vector<uint8_t> f;
   if (!read_file(filename, f)) { g_image_error = std::string("cannot read ") + filename; return PTB_ERR_IO; }
   std::vector<float> px;
@@ -371,6 +385,13 @@ int32_t ptb_image_load(const char* filename, uint32_t* width, uint32_t* height, 
   std::memcpy(out, px.data(), px.size() * sizeof(float));
   *width = w; *height = h; *rgb = out;
   return PTB_OK;
+  } catch (const std::bad_alloc&) {
+    g_image_error = std::string("out of memory decoding ") + filename;
+    return PTB_ERR_OOM;
+  } catch (const std::exception& e) {
+    g_image_error = std::string("decoder failure: ") + e.what();
+    return PTB_ERR_PARSE;
+  }
 }
 void ptb_image_free(float* rgb) { std::free(rgb); }
 

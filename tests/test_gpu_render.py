@@ -256,3 +256,46 @@ def test_abort_between_chunks_in_window_mode(ptb, gpu_ctx, rtweekend1, monkeypat
     # the context stays usable
     img = sc.render(ptb.RenderOptions(samples_per_pixel=2, render_method=0, width=64, height=36))
     assert np.all(np.isfinite(img))
+
+
+def test_abort_clears_the_accumulator(ptb, gpu_ctx, rtweekend1, monkeypatch):
+    """ptb200.h: an aborted ptb_render clears the accumulator, so a later read / render on the same context is not
+    normalised by a stale sample count (pixels finished before the abort used to come out over-bright)."""
+    ctx = gpu_ctx
+    ctx.upload(rtweekend1)
+    ctx.commit()
+    o = ptb.RenderOptions(samples_per_pixel=16, render_method=0, width=64, height=36, seed=2)
+    ctx.accum_clear()
+    ctx.render(o)
+    want = ctx.accum_read(64, 36, normalise=True).copy()
+    monkeypatch.setenv("PTB_WAVEFRONT", "window")
+    monkeypatch.setenv("PTB_POOL_PATHS", "8192")
+    ctx.accum_clear()
+    with pytest.raises(ptb.PtbError) as e:
+        ctx.render(o, progress=lambda s, r: True)
+    assert e.value.code == 7
+    monkeypatch.delenv("PTB_WAVEFRONT")
+    monkeypatch.delenv("PTB_POOL_PATHS")
+    assert not np.any(ctx.accum_read(64, 36, normalise=False))      # nothing left behind
+    ctx.render(o)                                                     # no accum_clear in between: starts from zero
+    got = ctx.accum_read(64, 36, normalise=True)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_out_of_range_material_index_is_an_error_not_a_fault(ptb, rtweekend1):
+    """a primitive whose material index is out of range must fail the commit with PTB_ERR_INVALID (the
+    primitives go straight to device memory, so the device validates) and leave the process and the context usable."""
+    import copy
+    bad = copy.deepcopy(rtweekend1)
+    bad.spheres = bad.spheres.copy()
+    bad.spheres["material"][0] = 0xFFFFFFFF
+    c = ptb.Context(0)
+    c.upload(bad)
+    with pytest.raises(ptb.PtbError) as e:
+        c.commit()
+    assert e.value.code == 1 and "material index" in str(e.value)
+    c.upload(rtweekend1)      # same context, valid scene: no sticky CUDA error
+    c.commit()
+    c.render(ptb.RenderOptions(samples_per_pixel=1, render_method=0, width=32, height=18))
+    assert np.all(np.isfinite(c.accum_read(32, 18)))
+    c.close()

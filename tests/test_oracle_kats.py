@@ -303,3 +303,36 @@ def test_wide_collapse_traversal_returns_the_same_hits(orc):
     assert np.array_equal(h2["prim"], h4["prim"]) and np.array_equal(h2["t"].view(np.uint32), h4["t"].view(np.uint32))
     assert 0.4 * v2 < v4 < 0.65 * v2
     assert abs(t4 - t2) <= 0.02 * t2
+
+
+# ---- independent f64 intersector ("an f64 brute-force intersector" as cross-check of the restatement)
+def _q1_region(rays, ratio):
+    d = rays["d"] / np.linalg.norm(rays["d"], axis=1, keepdims=True)
+    ax, ay, az = np.abs(d[:, 0]), np.abs(d[:, 1]), np.abs(d[:, 2])
+    return ~((ax > ay) & (ax > az)) & (ay > az) & (ax < ratio * ay)
+
+
+@pytest.mark.parametrize("which", ["rtweekend1", "overshadowed", "c3"])
+def test_oracle_agrees_with_f64_moller_trumbore(ptb, orc, rtweekend1, overshadowed, which):
+    """The f32 restatement (watertight triangle test with the reference's Q1 permutation, robust sphere quadratic) against
+    a double-precision Moller-Trumbore / textbook quadratic over every primitive: same primitive on every ray that is not
+    a grazing / near-tie decision and not in the Q1 region, t within 1e-5 of the magnitudes involved. In the Q1 region
+    (Y-dominant rays with |dir.x| < 0.25 |dir.y|) the reference may only LOSE hits (its t error bound rejects them)."""
+    scene, centre, radius, scale = {"rtweekend1": (rtweekend1, (0, 1, 0), 3.0, 105.0),
+                                    "overshadowed": (overshadowed, (-0.3, 0.3, -0.3), 1.5, 1004.0),
+                                    "c3": (ptb.meshgen.c3_scene(0.1), (0, 4, 1), 5.0, 12.0)}[which]
+    rays = ptb.meshgen.philox_rays(30_000, seed=43, centre=centre, radius=radius)
+    o = orc.OracleScene(scene)
+    r = o.closest_hit(rays)
+    f, margin = o.closest_hit_f64(rays)
+    q1 = _q1_region(rays, 0.25)
+    sure = ~q1 & (margin > 1e-4)
+    assert sure.mean() > 0.8
+    assert np.array_equal(r["prim"][sure], f["prim"][sure])
+    hit = sure & (f["prim"] != 0xFFFFFFFF)
+    assert hit.sum() > 3000
+    assert np.all(np.abs(r["t"][hit] - f["t"][hit]) <= 1e-5 * np.maximum(np.abs(f["t"][hit]), scale))
+    inq = q1 & (r["prim"] != f["prim"]) & (margin > 1e-4)
+    assert np.all((r["prim"][inq] == 0xFFFFFFFF) | (r["t"][inq] >= f["t"][inq] * (1 - 1e-5)))
+    if which == "c3":
+        assert inq.sum() > 0   # the quirk is real: the reference drops genuine triangle hits there

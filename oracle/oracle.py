@@ -185,9 +185,10 @@ class OracleScene:
                     out=bool(out[10]), prim=int(out[11]))
 
     def render(self, width, height, spp, method, seed=0, sample_offset=0, threads=0, max_depth=50, rr_threshold=3,
-               accum=None):
-        """Returns (sum image (H,W,3) float32, counts dict, seconds)."""
-        o = RenderOpts(width, height, spp, sample_offset, method, max_depth, rr_threshold, 0, seed)
+               accum=None, count_traversal=False):
+        """Returns (sum image (H,W,3) float32, counts dict, seconds). `count_traversal` fills nodes_visited /
+        prims_tested (off by default: the reference keeps no such counters and timed legs must not pay for them)."""
+        o = RenderOpts(width, height, spp, sample_offset, method, max_depth, rr_threshold, 1 if count_traversal else 0, seed)
         if accum is None:
             accum = np.zeros(width * height * 3, np.float32)
         counts = np.zeros(7, np.uint64)

@@ -269,6 +269,7 @@ double orc_render(const orc_scene* s, const ptb_render_opts* o, float* accum, in
   ro.integ.max_depth = o->max_depth ? o->max_depth : MAX_DEPTH;
   ro.integ.rr_threshold = o->rr_threshold == PTB_RR_DEFAULT ? RUSSIAN_ROULETTE_THRESHOLD : o->rr_threshold;
   ro.threads = threads > 0 ? (unsigned)threads : 0;
+  ro.count_traversal = (o->flags & 1u) != 0;  // ptb_render_opts::flags is reserved in the product ABI; the oracle uses bit 0
   auto t0 = std::chrono::steady_clock::now();
   RayCounts rc = sample_image(s->camera, s->bvh, ro, accum);
   double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -25,7 +25,12 @@ struct IntegratorOpts {
 struct RayCounts {
   uint64_t reference = 0;  // the reference's own ray_count (integrators/mod.rs:34, mis.rs:38)
   uint64_t camera = 0, bounce = 0, shadow_light = 0, shadow_sky = 0;  // every traversal launched, by class
+  // traversal statistics are OFF unless asked for (RenderOpts::count_traversal): the timed CPU baseline of bench.py
+  // must not pay for counters the reference does not keep
   uint64_t nodes_visited = 0, prims_tested = 0;
+  bool count_traversal = false;
+  uint64_t* nv() { return count_traversal ? &nodes_visited : nullptr; }
+  uint64_t* pt() { return count_traversal ? &prims_tested : nullptr; }
 };
 
 // integrators/mod.rs:22-78
@@ -35,7 +40,7 @@ static inline Vec3 naive_get_colour(Ray& ray, const Bvh& bvh, const IntegratorOp
   while (depth < o.max_depth) {
     Hit hit;
     const Material* mat;
-    bvh.check_hit(ray, hit, mat, &rc.nodes_visited, &rc.prims_tested);
+    bvh.check_hit(ray, hit, mat, rc.nv(), rc.pt());
     rc.reference += 1;
     if (depth == 0) rc.camera += 1; else rc.bounce += 1;
 
@@ -81,7 +86,7 @@ static inline bool sample_lights(const Bvh& bvh, const Hit& hit, uint32_t depth,
     Hit sa;
     const Material* m;
     rc.shadow_sky += 1;
-    size_t index = bvh.check_hit(ray, sa, m, &rc.nodes_visited, &rc.prims_tested);
+    size_t index = bvh.check_hit(ray, sa, m, rc.nv(), rc.pt());
     if (index == Bvh::MISS) {
       le = m->get_emission(hit, l_wi);
       l_pdf = sky.pdf(l_wi) * pdf_multiplier;
@@ -130,7 +135,7 @@ static inline Vec3 mis_get_colour(Ray& ray, const Bvh& bvh, const IntegratorOpts
   Hit hit;
   const Material* mat;
   rc.camera += 1;
-  bvh.check_hit(ray, hit, mat, &rc.nodes_visited, &rc.prims_tested);
+  bvh.check_hit(ray, hit, mat, rc.nv(), rc.pt());
   Vec3 wo = ray.direction;
   Vec3 emission = mat->get_emission(hit, wo);
   {
@@ -159,7 +164,7 @@ static inline Vec3 mis_get_colour(Ray& ray, const Bvh& bvh, const IntegratorOpts
     Hit next_hit;
     const Material* next_mat;
     rc.bounce += 1;
-    size_t index = bvh.check_hit(ray, next_hit, next_mat, &rc.nodes_visited, &rc.prims_tested);
+    size_t index = bvh.check_hit(ray, next_hit, next_mat, rc.nv(), rc.pt());
 
     Float m_pdf = mat->scattering_pdf(hit, wo, m_wi);
     Vec3 le2 = next_mat->get_emission(hit /* previous hit: quirk Q6 */, m_wi);
@@ -222,6 +227,7 @@ struct RenderOpts {
   uint64_t seed = 0;
   IntegratorOpts integ;
   unsigned threads = 0;  // 0 -> hardware_concurrency
+  bool count_traversal = false;  // fill RayCounts::nodes_visited / prims_tested (costs time; off for timed baselines)
 };
 
 // One sample of one pixel: samplers/random_sampler.rs:50-74
@@ -247,6 +253,7 @@ static inline RayCounts sample_image(const Camera& cam, const Bvh& bvh, const Re
   unsigned nthreads = o.threads ? o.threads : std::thread::hardware_concurrency();
   if (nthreads == 0) nthreads = 1;
   std::vector<RayCounts> per_thread(nthreads);
+  for (auto& rc : per_thread) rc.count_traversal = o.count_traversal;
   for (uint32_t s = 0; s < o.spp; ++s) {
     std::atomic<uint64_t> next_chunk(0);
     auto worker = [&](unsigned tid) {

@@ -1,8 +1,9 @@
 """ctypes binding of include/ptb200.h (libptb200.so).
 
-The library is the product: there is no Python or CPU fallback. If the shared object is missing the
-import fails loudly with the build command; if no CUDA device is present `ptb_create` fails with
-PTB_ERR_CUDA and `Context()` raises.
+The library is the product: there is no Python or CPU fallback. The shared object is mapped on the FIRST use of any
+entry point (`lib.<symbol>`), not at import: `bench.py --impl reference` imports this package only for the numpy scene
+generators and must provably not map the CUDA library. If the shared object is missing that first use fails loudly
+with the build command; if no CUDA device is present `ptb_create` fails with PTB_ERR_CUDA and `Context()` raises.
 """
 from __future__ import annotations
 
@@ -144,7 +145,25 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     return lib
 
 
-lib = load_library()
+class _LazyLib:
+    """`lib.ptb_xxx` maps libptb200.so on first use and checks every symbol the header declares."""
+
+    _cdll = None
+
+    def _load(self) -> C.CDLL:
+        if _LazyLib._cdll is None:
+            _LazyLib._cdll = load_library()
+        return _LazyLib._cdll
+
+    def __getattr__(self, name):
+        return getattr(self._load(), name)
+
+
+lib = _LazyLib()
+
+
+def is_loaded() -> bool:
+    return _LazyLib._cdll is not None
 
 
 def ptr(a: np.ndarray):

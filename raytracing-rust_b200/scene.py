@@ -14,6 +14,20 @@ import numpy as np
 from . import _lib as L
 
 
+def _camera_make_native(origin, lookat, vup, hfov_deg, aspect, aperture, focus_dist) -> np.ndarray:
+    cam = np.zeros(1, L.camera_dtype)
+    rc = L.lib.ptb_camera_make(L.Vec3(*map(float, origin)), L.Vec3(*map(float, lookat)), L.Vec3(*map(float, vup)),
+                               float(hfov_deg), float(aspect), float(aperture), float(focus_dist), L.ptr(cam))
+    if rc != L.PTB_OK:
+        raise L.PtbError(rc, "ptb_camera_make")
+    return cam
+
+
+# SimpleCamera::new. bench.py's `--impl reference` arm swaps in the CPU checker's restatement (bit-equal,
+# tests/ pin that) so that its process never maps libptb200.so; nothing in this package does.
+CAMERA_MAKE = _camera_make_native
+
+
 @dataclass
 class HostScene:
     spheres: np.ndarray = field(default_factory=lambda: np.zeros(0, L.sphere_dtype))
@@ -73,12 +87,7 @@ class HostScene:
 
     def set_camera(self, origin, lookat, vup, hfov_deg, aspect=16.0 / 9.0, aperture=0.0, focus_dist=10.0):
         """SimpleCamera::new (implementations/src/camera.rs:20-53)."""
-        cam = np.zeros(1, L.camera_dtype)
-        rc = L.lib.ptb_camera_make(L.Vec3(*map(float, origin)), L.Vec3(*map(float, lookat)), L.Vec3(*map(float, vup)),
-                                   float(hfov_deg), float(aspect), float(aperture), float(focus_dist), L.ptr(cam))
-        if rc != L.PTB_OK:
-            raise L.PtbError(rc, "ptb_camera_make")
-        self.camera = cam
+        self.camera = CAMERA_MAKE(origin, lookat, vup, hfov_deg, aspect, aperture, focus_dist)
 
     def set_sky(self, texture: int, sampler_res=(100, 100)):
         self.sky = np.zeros(1, L.sky_dtype)

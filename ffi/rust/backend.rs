@@ -97,7 +97,7 @@ impl CudaScene {
         ptb_render_opts {
             width: opts.width as u32, height: opts.height as u32, samples_per_pixel: opts.samples_per_pixel as u32, sample_offset: 0,
             method: match opts.render_method { RenderMethod::Naive => PTB_METHOD_NAIVE, RenderMethod::MIS => PTB_METHOD_MIS },
-            max_depth: 50, rr_threshold: PTB_RR_DEFAULT, flags: 0, seed,
+            max_depth: 50, rr_threshold: PTB_RR_DEFAULT, flags: 0, seed, row_begin: 0, row_count: 0,
         }
     }
 }

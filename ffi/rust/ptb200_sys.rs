@@ -21,6 +21,8 @@ pub const PTB_METHOD_MIS: u32 = 1;
 pub struct ptb_render_opts {
     pub width: u32, pub height: u32, pub samples_per_pixel: u32, pub sample_offset: u32,
     pub method: u32, pub max_depth: u32, pub rr_threshold: u32, pub flags: u32, pub seed: u64,
+    /// image tile (ABI 2): rows [row_begin, row_begin + row_count) only; row_count 0 = to the last row
+    pub row_begin: u32, pub row_count: u32,
 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct ptb_stats {
@@ -53,6 +55,7 @@ extern "C" {
     pub fn ptb_render_passes(ctx: *mut ptb_ctx, opts: *const ptb_render_opts, update: ptb_pass_fn, user: *mut c_void) -> i32;
     pub fn ptb_render_multi(ctxs: *const *mut ptb_ctx, n: i32, opts: *const ptb_render_opts) -> i32;
     pub fn ptb_shard_samples(samples_per_pixel: u32, sample_offset: u32, rank: i32, world: i32, first: *mut u32, count: *mut u32);
+    pub fn ptb_shard_rows(rows: u32, row_begin: u32, rank: i32, world: i32, first: *mut u32, count: *mut u32);
     pub fn ptb_accum_clear(ctx: *mut ptb_ctx) -> i32;
     pub fn ptb_accum_read(ctx: *mut ptb_ctx, rgb: *mut f32, n_floats: usize, normalise: i32) -> i32;
     pub fn ptb_accum_device_ptr(ctx: *mut ptb_ctx, d_ptr: *mut *mut c_void, n_floats: *mut usize) -> i32;

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 1u
+#define PTB_ABI_VERSION 2u  /* 2: ptb_render_opts gained row_begin / row_count (image-tile axis of the multi-GPU split) */
 
 /* ---------------------------------------------------------------- status -- */
 enum {
@@ -143,6 +143,9 @@ typedef struct ptb_render_opts {
   uint32_t rr_threshold;      /* 0xFFFFFFFF -> 3 (integrators/mod.rs:8); RR applies when depth > threshold */
   uint32_t flags;             /* reserved, 0                                                    */
   uint64_t seed;              /* counter-based RNG key; same seed + same sample range == same image */
+  uint32_t row_begin;         /* image tile: only the pixel rows [row_begin, row_begin + row_count) are rendered;   */
+  uint32_t row_count;         /* 0 -> every row from row_begin down. Pixels keep their full-image coordinates (camera,
+                                 RNG key, accumulator position), so the tiles of one image add up to the whole image. */
 } ptb_render_opts;
 #define PTB_RR_DEFAULT 0xFFFFFFFFu
 
@@ -264,9 +267,13 @@ int32_t ptb_accum_set_samples(ptb_ctx* ctx, uint64_t total_samples);
  * samples [first, first + count) of every pixel. */
 void    ptb_shard_samples(uint32_t samples_per_pixel, uint32_t sample_offset, int32_t rank, int32_t world,
                           uint32_t* first, uint32_t* count);
+/* Second axis, for requests with fewer samples than GPUs: rank r renders every sample of the pixel rows
+ * [first, first + count) of the `rows` rows starting at row_begin (bands of whole rows; sizes differ by at most 1). */
+void    ptb_shard_rows(uint32_t rows, uint32_t row_begin, int32_t rank, int32_t world, uint32_t* first, uint32_t* count);
 /* Scene::render across n GPUs of one box: ctxs[r] (one per GPU, scene already committed on each) renders its share on its
- * own host thread, then ONE ncclReduce(sum) of the accumulators (width*height*3 f32) to ctxs[0] — the path's only
- * collective. Afterwards ptb_accum_read(ctxs[0], ..) returns the image of all opts->samples_per_pixel samples. NCCL is
+ * own host thread — a sample range of every pixel when samples_per_pixel >= n, else a band of pixel rows at every sample —
+ * then ONE ncclReduce(sum) of the accumulators (width*height*3 f32) to ctxs[0] — the path's only collective; the
+ * communicators are checked with ncclCommGetAsyncError after the reduce has completed. Afterwards ptb_accum_read(ctxs[0], ..) returns the image of all opts->samples_per_pixel samples. NCCL is
  * bound at run time (libnccl.so.2, or $PTB_NCCL_LIB); n == 1 never touches it. */
 int32_t ptb_render_multi(ptb_ctx* const* ctxs, int32_t n, const ptb_render_opts* opts);
 

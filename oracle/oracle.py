@@ -28,7 +28,8 @@ bvh_node_dtype = np.dtype([("lmin", "<f4", 3), ("lmax", "<f4", 3), ("rmin", "<f4
 class RenderOpts(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("samples_per_pixel", C.c_uint32),
                 ("sample_offset", C.c_uint32), ("method", C.c_uint32), ("max_depth", C.c_uint32),
-                ("rr_threshold", C.c_uint32), ("flags", C.c_uint32), ("seed", C.c_uint64)]
+                ("rr_threshold", C.c_uint32), ("flags", C.c_uint32), ("seed", C.c_uint64),
+                ("row_begin", C.c_uint32), ("row_count", C.c_uint32)]
 
 
 def build():

@@ -45,7 +45,8 @@ bvh_node_dtype = np.dtype([("lmin", "<f4", 3), ("lmax", "<f4", 3), ("rmin", "<f4
 class RenderOpts(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("samples_per_pixel", C.c_uint32),
                 ("sample_offset", C.c_uint32), ("method", C.c_uint32), ("max_depth", C.c_uint32),
-                ("rr_threshold", C.c_uint32), ("flags", C.c_uint32), ("seed", C.c_uint64)]
+                ("rr_threshold", C.c_uint32), ("flags", C.c_uint32), ("seed", C.c_uint64),
+                ("row_begin", C.c_uint32), ("row_count", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -102,6 +103,7 @@ SYMBOLS = [
     ("ptb_accum_device_ptr", C.c_int32, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     ("ptb_accum_set_samples", C.c_int32, [_P, C.c_uint64]),
     ("ptb_shard_samples", None, [C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    ("ptb_shard_rows", None, [C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("ptb_render_multi", C.c_int32, [_P, C.c_int32, C.POINTER(RenderOpts)]),
     ("ptb_stats_get", C.c_int32, [_P, C.POINTER(Stats)]),
     ("ptb_stats_reset", C.c_int32, [_P]),

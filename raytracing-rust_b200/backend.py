@@ -36,10 +36,12 @@ class RenderOptions:
     max_depth: int = 50          # integrators/mod.rs:7
     rr_threshold: int = 3        # integrators/mod.rs:8
     seed: int = 0
+    row_begin: int = 0           # image tile (multi-GPU second axis): rows [row_begin, row_begin + row_count); 0 = to the end
+    row_count: int = 0
 
     def to_c(self) -> L.RenderOpts:
         return L.RenderOpts(self.width, self.height, self.samples_per_pixel, self.sample_offset, self.render_method,
-                            self.max_depth, self.rr_threshold, 0, self.seed)
+                            self.max_depth, self.rr_threshold, 0, self.seed, self.row_begin, self.row_count)
 
 
 class Context:

@@ -381,6 +381,9 @@ int32_t ptb_render(ptb_ctx* ctx, const ptb_render_opts* opts, ptb_progress_fn pr
   if (opts->width < 2 || opts->height < 2) return set_error(c, PTB_ERR_INVALID, "width and height must be >= 2");
   if ((uint64_t)opts->width * opts->height > 0x7FFFFFFFull) return set_error(c, PTB_ERR_INVALID, "image too large");
   if (opts->method != PTB_METHOD_NAIVE && opts->method != PTB_METHOD_MIS) return set_error(c, PTB_ERR_INVALID, "unknown method");
+  if (opts->row_begin >= opts->height || (uint64_t)opts->row_begin + opts->row_count > opts->height)
+    return set_error(c, PTB_ERR_INVALID, "image tile rows [%u, %u) outside the %u rows of the image", opts->row_begin,
+                     opts->row_begin + opts->row_count, opts->height);
   int32_t rc = ensure_accum(c, opts->width, opts->height);
   if (rc != PTB_OK) return rc;
   rc = render_wavefront(c, *opts, progress, user);
@@ -407,6 +410,9 @@ int32_t ptb_render_passes(ptb_ctx* ctx, const ptb_render_opts* opts, ptb_pass_fn
   if (opts->width < 2 || opts->height < 2) return set_error(c, PTB_ERR_INVALID, "width and height must be >= 2");
   if ((uint64_t)opts->width * opts->height > 0x7FFFFFFFull) return set_error(c, PTB_ERR_INVALID, "image too large");
   if (opts->method != PTB_METHOD_NAIVE && opts->method != PTB_METHOD_MIS) return set_error(c, PTB_ERR_INVALID, "unknown method");
+  if (opts->row_begin >= opts->height || (uint64_t)opts->row_begin + opts->row_count > opts->height)
+    return set_error(c, PTB_ERR_INVALID, "image tile rows [%u, %u) outside the %u rows of the image", opts->row_begin,
+                     opts->row_begin + opts->row_count, opts->height);
   int32_t rc = ensure_accum(c, opts->width, opts->height);
   if (rc != PTB_OK) return rc;
   const size_t n = (size_t)opts->width * opts->height * 3;

@@ -2,6 +2,8 @@
 // The path shards by samples: context r of n renders its share of the sample range of every pixel (scene and BVH are
 // replicated: each context committed its own copy; the build is deterministic), then the per-GPU accumulators — sums, not
 // means — are combined by ONE ncclReduce(sum) to context 0 over NVLink. That reduce is the only collective of the path.
+// A request with fewer samples than GPUs is split along the image instead (bands of pixel rows, every sample): pixels keep
+// their full-image coordinates, a band only ever adds to its own rows, so the same reduce combines the tiles.
 // One host thread per GPU drives its context; NCCL is bound at run time (dlopen) so libptb200.so carries no link-time
 // dependency on it and single-GPU users never load it.
 #include <dlfcn.h>
@@ -27,6 +29,7 @@ struct Nccl {
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t*) = nullptr;  // optional (NCCL >= 2.4)
   std::vector<int> devices;        // communicators are cached for the last device list
   std::vector<ncclComm_t> comms;
   std::mutex mu;
@@ -52,6 +55,7 @@ bool load_nccl(std::string& why) {
   PTB_SYM(GroupEnd, "ncclGroupEnd")
   PTB_SYM(GetErrorString, "ncclGetErrorString")
 #undef PTB_SYM
+  g_nccl.CommGetAsyncError = reinterpret_cast<decltype(g_nccl.CommGetAsyncError)>(dlsym(g_nccl.lib, "ncclCommGetAsyncError"));
   return true;
 }
 
@@ -71,6 +75,13 @@ void ptb_shard_samples(uint32_t samples_per_pixel, uint32_t sample_offset, int32
   if (count) *count = (uint32_t)(hi - lo);
 }
 
+void ptb_shard_rows(uint32_t rows, uint32_t row_begin, int32_t rank, int32_t world, uint32_t* first, uint32_t* count) {
+  const uint64_t lo = (uint64_t)rank * rows / (uint64_t)world;
+  const uint64_t hi = ((uint64_t)rank + 1u) * rows / (uint64_t)world;
+  if (first) *first = row_begin + (uint32_t)lo;
+  if (count) *count = (uint32_t)(hi - lo);
+}
+
 int32_t ptb_render_multi(ptb_ctx* const* ctxs, int32_t n, const ptb_render_opts* opts) {
   if (!ctxs || n < 1 || !opts) return PTB_ERR_INVALID;
   for (int32_t i = 0; i < n; ++i)
@@ -86,15 +97,23 @@ int32_t ptb_render_multi(ptb_ctx* const* ctxs, int32_t n, const ptb_render_opts*
   for (int32_t r = 0; r < n; ++r)
     threads.emplace_back([&, r]() {
       ptb_render_opts o = *opts;
-      ptb_shard_samples(opts->samples_per_pixel, opts->sample_offset, r, n, &o.sample_offset, &o.samples_per_pixel);
+      bool work = true;
+      if (opts->samples_per_pixel >= (uint32_t)n) {  // sample axis
+        ptb_shard_samples(opts->samples_per_pixel, opts->sample_offset, r, n, &o.sample_offset, &o.samples_per_pixel);
+      } else {  // image-tile axis: every sample of a band of rows
+        const uint32_t rows = opts->row_count ? opts->row_count : (opts->row_begin < opts->height ? opts->height - opts->row_begin : 0u);
+        ptb_shard_rows(rows, opts->row_begin, r, n, &o.row_begin, &o.row_count);
+        work = o.row_count != 0u;  // more GPUs than rows
+        if (!work) o.row_begin = 0u;
+      }
       int32_t rc;
       {  // zero passes: only sizes this context's accumulator
-        ptb_render_opts none = o;
+        ptb_render_opts none = *opts;
         none.samples_per_pixel = 0;
         rc = ptb_render(ctxs[r], &none, nullptr, nullptr);
       }
       if (rc == PTB_OK) rc = ptb_accum_clear(ctxs[r]);
-      if (rc == PTB_OK && o.samples_per_pixel) rc = ptb_render(ctxs[r], &o, nullptr, nullptr);
+      if (rc == PTB_OK && work && o.samples_per_pixel) rc = ptb_render(ctxs[r], &o, nullptr, nullptr);
       if (rc == PTB_OK) rc = ptb_synchronize(ctxs[r]);
       rcs[(size_t)r] = rc;
     });
@@ -133,6 +152,19 @@ int32_t ptb_render_multi(ptb_ctx* const* ctxs, int32_t n, const ptb_render_opts*
     const int32_t rc = ptb_synchronize(ctxs[r]);
     if (rc != PTB_OK) return rc;
   }
+  // a failed collective (peer fault, NVLink error) surfaces asynchronously on the communicator, not on the stream
+  if (g_nccl.CommGetAsyncError)
+    for (int32_t r = 0; r < n; ++r) {
+      ncclResult_t async = 0;
+      const ncclResult_t q = g_nccl.CommGetAsyncError(g_nccl.comms[(size_t)r], &async);
+      if (q != 0 || async != 0) {
+        const ncclResult_t bad = q != 0 ? q : async;
+        for (ncclComm_t cm : g_nccl.comms) g_nccl.CommDestroy(cm);  // the communicators are unusable after an async error
+        g_nccl.comms.clear();
+        g_nccl.devices.clear();
+        return set_error(root, PTB_ERR_CUDA, "ncclReduce failed asynchronously on GPU %d: %s", ctxs[r]->c.device, g_nccl.GetErrorString(bad));
+      }
+    }
   root->accum_samples = opts->samples_per_pixel;
   root->stats.kernel_launches += 1;
   return PTB_OK;

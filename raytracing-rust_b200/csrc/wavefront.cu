@@ -22,7 +22,8 @@
 namespace ptb {
 
 struct RenderParams {
-  uint32_t width, height, npix;
+  uint32_t width, height, npix;  // npix = width * (rows of this call's image tile)
+  uint32_t row_begin;            // first pixel row of the tile (ptb_render_opts::row_begin)
   uint32_t tile_w, tile_h;  // pixel issue order (k_generate); tile_h == 1 -> row-major
   uint32_t group;           // samples of one pixel issued back to back (a divisor of the call's spp)
   uint32_t dir_bins;        // window mode: order a window's live rays by direction bin (PTB_DIRBINS=0 disables)
@@ -261,6 +262,7 @@ PTB_DEV void camera_pixel_sample(const RenderParams& rp, unsigned long long g, u
     x = lin % rp.width;
     y = lin / rp.width;
   }
+  y += rp.row_begin;  // image tile: pixels keep their full-image coordinates
 }
 // random_sampler.rs:55-59 (note W-1 / H-1), camera.rs:57-63; the caller's make_ray is Ray::new (ray.rs:13-46)
 PTB_DEV v3 camera_direction(const DevScene& sc, const RenderParams& rp, uint32_t x, uint32_t y, uint32_t sample) {
@@ -1313,7 +1315,8 @@ static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderS
 static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const RenderSetup& rs, ptb_progress_fn progress, void* user);
 
 int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progress, void* user) {
-  const uint32_t npix = o.width * o.height;
+  const uint32_t rows = o.row_count ? o.row_count : o.height - o.row_begin;  // validated by ptb_render
+  const uint32_t npix = o.width * rows;
   const unsigned long long total = (unsigned long long)npix * o.samples_per_pixel;
   if (total == 0) return PTB_OK;
   RenderSetup rs;
@@ -1382,6 +1385,7 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
 
   RenderParams& rp = rs.rp;
   rp.width = o.width; rp.height = o.height; rp.npix = npix;
+  rp.row_begin = o.row_begin;
   // Pixel issue order: 32 consecutive pixel indices cover an 8 x 4 tile when the image allows (else 16 x 2, else a row), so
   // the 16 pixels of a 4096-slot window are an 8 x 2 block instead of a 16 x 1 strip: the origins of a window's rays lie
   // closer together. Window mode, C3: 3793 -> 3834 Mrays/s (queue mode preferred rows). PTB_TILES=0 keeps rows.
@@ -1390,7 +1394,7 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   if (const char* e = getenv("PTB_TILES")) tiles = atoi(e) != 0;
   if (tiles)
     for (uint32_t th = 4u; th > 1u; th >>= 1)
-      if (o.height % th == 0u && o.width % (32u / th) == 0u) { rp.tile_h = th; rp.tile_w = 32u / th; break; }
+      if (rows % th == 0u && o.width % (32u / th) == 0u) { rp.tile_h = th; rp.tile_w = 32u / th; break; }
   // samples of one pixel issued back to back: the largest divisor of spp <= 1024 (PTB_SAMPLE_GROUP). Measured on C3 at
   // 256 spp: group 1 -> 2760 Mrays/s, 32 -> 3066, 256 -> 3197 (camera rays of a warp walk the same nodes).
   rp.group = 1u;

@@ -2,13 +2,16 @@
 // Same flags, same defaults, same log lines; `--backend cuda` is the only backend this binary contains.
 //
 //   ptb200-cli -f scenes/rtweekend1.ssml -s 64 -x 800 -y 450 -r mis -o out.png [--backend cuda] [--device 0]
-//              [--seed 0] [--max-depth 50] [-b sah|middle|equal-counts (accepted, ignored: the device builds an LBVH)]
+//              [--gpus 1] [--seed 0] [--max-depth 50] [-b sah|middle|equal-counts (accepted, ignored: the device builds its own tree)]
+// --gpus N renders on GPUs device .. device+N-1 through ptb_render_multi (samples split N ways, or bands of image rows
+// when there are fewer samples than GPUs; one ncclReduce of the accumulators) — the rayon fan-out of random_sampler.rs:40-80.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ptb200.h"
@@ -27,6 +30,7 @@ struct Cli {
   float gamma = 2.2f;                 // :39-40
   std::string backend = "cuda";
   int device = 0;
+  int gpus = 1;
   unsigned long long seed = 0;
   unsigned max_depth = 50;
 };
@@ -74,6 +78,7 @@ int usage(const char* argv0, const char* err) {
                "      --gamma <GAMMA>                  [default: 2.2]\n"
                "      --backend <BACKEND>              [default: cuda] [possible values: cuda]\n"
                "      --device <INDEX>                 [default: 0]\n"
+               "      --gpus <N>                       [default: 1] GPUs device .. device+N-1 of this box\n"
                "      --seed <SEED>                    [default: 0]\n"
                "      --max-depth <DEPTH>              [default: 50]\n",
                argv0);
@@ -115,6 +120,7 @@ int main(int argc, char** argv) {
     else if (a == "--gamma") cli.gamma = std::strtof(value("--gamma"), nullptr);
     else if (a == "--backend") cli.backend = value("--backend");
     else if (a == "--device") cli.device = std::atoi(value("--device"));
+    else if (a == "--gpus") cli.gpus = std::atoi(value("--gpus"));
     else if (a == "--seed") cli.seed = std::strtoull(value("--seed"), nullptr, 10);
     else if (a == "--max-depth") cli.max_depth = (unsigned)std::atoi(value("--max-depth"));
     else if (a == "-h" || a == "--help") return usage(argv[0], nullptr), 0;
@@ -125,6 +131,7 @@ int main(int argc, char** argv) {
     return usage(argv[0], "invalid value for --bvh-type");
   if (cli.render_method != "naive" && cli.render_method != "mis") return usage(argv[0], "invalid value for --render-method");
   if (cli.backend != "cuda") return usage(argv[0], "this binary only contains the cuda backend (no CPU fallback)");
+  if (cli.gpus < 1 || cli.gpus > 64) return usage(argv[0], "invalid value for --gpus");
   if (cli.gui) {  // src/main.rs:226-229
     std::printf("feature: gui not enabled\n");
     return 0;
@@ -138,20 +145,38 @@ int main(int argc, char** argv) {
     log_line("ERROR", "frontend", std::string("failed to load scene: ") + ptb_host_last_error());
     return 101;  // the reference panics here
   }
-  ptb_ctx* ctx = nullptr;
-  if ((rc = ptb_create(cli.device, &ctx)) != PTB_OK) {
-    log_line("ERROR", "frontend", std::string("cuda backend unavailable: ") + ptb_last_error(nullptr));
-    return 1;
-  }
-  auto fail = [&](const char* what) {
-    log_line("ERROR", "frontend", std::string(what) + ": " + ptb_last_error(ctx));
-    ptb_destroy(ctx);
+  // one context per GPU, the scene replicated on each (uploads and builds run concurrently, one host thread per GPU)
+  std::vector<ptb_ctx*> ctxs((size_t)cli.gpus, nullptr);
+  auto destroy_all = [&]() {
+    for (ptb_ctx* c : ctxs) ptb_destroy(c);
     ptb_host_scene_free(scene);
+  };
+  for (int g = 0; g < cli.gpus; ++g)
+    if ((rc = ptb_create(cli.device + g, &ctxs[(size_t)g])) != PTB_OK) {
+      log_line("ERROR", "frontend", std::string("cuda backend unavailable: ") + ptb_last_error(nullptr));
+      destroy_all();
+      return 1;
+    }
+  ptb_ctx* ctx = ctxs[0];
+  auto fail = [&](const char* what, ptb_ctx* which = nullptr) {
+    log_line("ERROR", "frontend", std::string(what) + ": " + ptb_last_error(which ? which : ctx));
+    destroy_all();
     return 1;
   };
-  if (ptb_scene_upload(ctx, scene) != PTB_OK) return fail("scene upload");
-  if (ptb_scene_commit(ctx, PTB_BUILD_DEFAULT) != PTB_OK) return fail("bvh build");  // Bvh::new (parameters.rs:60)
-  if (cli.bvh_type != "sah") log_line("WARN", "frontend", "--bvh-type is ignored by the cuda backend (device LBVH)");
+  {
+    std::vector<int32_t> rcs((size_t)cli.gpus, PTB_OK);
+    std::vector<std::thread> th;
+    for (int g = 0; g < cli.gpus; ++g)
+      th.emplace_back([&, g]() {
+        int32_t r = ptb_scene_upload(ctxs[(size_t)g], scene);
+        if (r == PTB_OK) r = ptb_scene_commit(ctxs[(size_t)g], PTB_BUILD_DEFAULT);  // Bvh::new (parameters.rs:60)
+        rcs[(size_t)g] = r;
+      });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < cli.gpus; ++g)
+      if (rcs[(size_t)g] != PTB_OK) return fail("scene upload / bvh build", ctxs[(size_t)g]);
+  }
+  if (cli.bvh_type != "sah") log_line("WARN", "frontend", "--bvh-type is ignored by the cuda backend (it builds its own tree)");
 
   // output/src/lib.rs:126-136
   {
@@ -171,12 +196,24 @@ int main(int argc, char** argv) {
   o.rr_threshold = PTB_RR_DEFAULT;
   o.seed = cli.seed;
   Progress prog{cli.samples};
-  if (ptb_render(ctx, &o, on_progress, &prog) != PTB_OK) return fail("render");
+  if (cli.gpus == 1) {
+    if (ptb_render(ctx, &o, on_progress, &prog) != PTB_OK) return fail("render");
+  } else {
+    if (ptb_render_multi(ctxs.data(), cli.gpus, &o) != PTB_OK) return fail("multi-GPU render");
+  }
   std::vector<float> image((size_t)cli.width * cli.height * 3);
   if (ptb_accum_read(ctx, image.data(), image.size(), 1) != PTB_OK) return fail("accumulator read-back");
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
   ptb_stats st{};
   ptb_stats_get(ctx, &st);
+  for (int g = 1; g < cli.gpus; ++g) {  // counters add up over the GPUs; times are the slowest GPU's
+    ptb_stats s2{};
+    ptb_stats_get(ctxs[(size_t)g], &s2);
+    st.rays_camera += s2.rays_camera; st.rays_bounce += s2.rays_bounce; st.rays_shadow_light += s2.rays_shadow_light;
+    st.rays_shadow_sky += s2.rays_shadow_sky; st.rays_reference += s2.rays_reference; st.kernel_launches += s2.kernel_launches;
+    if (s2.render_ms > st.render_ms) st.render_ms = s2.render_ms;
+    if (s2.build_ms > st.build_ms) st.build_ms = s2.build_ms;
+  }
 
   // output/src/lib.rs:115-124 — the reference's own counter (Q7), then this backend's per-class counts
   {
@@ -188,10 +225,10 @@ int main(int argc, char** argv) {
     const unsigned long long all = st.rays_camera + st.rays_bounce + st.rays_shadow_light + st.rays_shadow_sky;
     std::snprintf(buf, sizeof buf,
                   "cuda backend: %llu traversals (camera %llu, bounce %llu, light-shadow %llu, sky-shadow %llu) @ %.2f Mray/s; "
-                  "device render %.1f ms, bvh build %.2f ms, %llu kernel launches",
+                  "device render %.1f ms, bvh build %.2f ms, %llu kernel launches, %d GPU(s)",
                   all, (unsigned long long)st.rays_camera, (unsigned long long)st.rays_bounce,
                   (unsigned long long)st.rays_shadow_light, (unsigned long long)st.rays_shadow_sky, (double)all / secs / 1e6,
-                  st.render_ms, st.build_ms, (unsigned long long)st.kernel_launches);
+                  st.render_ms, st.build_ms, (unsigned long long)st.kernel_launches, cli.gpus);
     log_line("INFO", "output", buf);
   }
   int exit_code = 0;
@@ -201,7 +238,6 @@ int main(int argc, char** argv) {
     else if (rc == PTB_ERR_INVALID) { std::printf("Invalid filename: %s\n", cli.output.c_str()); }
     else { log_line("ERROR", "output", "Unable to save file: " + cli.output); exit_code = 1; }
   }
-  ptb_destroy(ctx);
-  ptb_host_scene_free(scene);
+  destroy_all();
   return exit_code;
 }

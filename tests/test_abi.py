@@ -13,7 +13,7 @@ def test_every_declared_symbol_is_exported(ptb, root):
     lib = ctypes.CDLL(ptb._lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert ptb._lib.lib.ptb_abi_version() == 1
+    assert ptb._lib.lib.ptb_abi_version() == 2
 
 
 def test_pod_layouts(ptb):
@@ -22,7 +22,7 @@ def test_pod_layouts(ptb):
     assert L.material_dtype.itemsize == 28 and L.texture_dtype.itemsize == 28
     assert L.camera_dtype.itemsize == 48 and L.sky_dtype.itemsize == 12
     assert L.ray_dtype.itemsize == 32 and L.hit_dtype.itemsize == 16 and L.bvh_node_dtype.itemsize == 64
-    assert ctypes.sizeof(L.RenderOpts) == 40 and L.RenderOpts.seed.offset == 32
+    assert ctypes.sizeof(L.RenderOpts) == 48 and L.RenderOpts.seed.offset == 32 and L.RenderOpts.row_begin.offset == 40
     assert ctypes.sizeof(L.Stats) == 12 * 8 + 6 * 8
 
 

@@ -65,3 +65,32 @@ def test_cli_matches_binding(ptb, gpu_ctx, root, tmp_path):
     assert subprocess.run([cli], capture_output=True).returncode != 0
     g = subprocess.run([cli, "-g", "-f", scene_path], capture_output=True, text=True)
     assert g.returncode == 0 and "feature: gui not enabled" in g.stdout
+
+
+def test_cli_gpus_flag_and_exr_output(ptb, gpu_ctx, root, tmp_path):
+    """`--gpus N -o x.exr` — the multi-GPU render from the product boundary, written as linear f32 EXR
+    (output/src/lib.rs:98-104), equals the single-GPU image. With one GPU in the box N = 1 still goes through the flag."""
+    import ctypes as C
+    import struct
+    n = C.c_int32()
+    ptb._lib.lib.ptb_device_count(C.byref(n))
+    gpus = 2 if n.value >= 2 else 1
+    cli = os.path.join(root, "raytracing-rust_b200", "ptb200-cli")
+    out = tmp_path / "img.exr"
+    scene_path = os.path.join(root, "scenes", "rtweekend1.ssml")
+    r = subprocess.run([cli, "-f", scene_path, "-s", "6", "-x", "96", "-y", "54", "-r", "mis", "-o", str(out), "--seed", "9",
+                        "--gpus", str(gpus)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert f"{gpus} GPU(s)" in r.stderr and f"Image {out} saved" in r.stderr
+    raw = out.read_bytes()
+    assert struct.unpack_from("<I", raw, 0)[0] == 20000630
+    w, h = 96, 54
+    data = raw[len(raw) - h * (8 + 12 * w):]                    # uncompressed scanline chunks at the end of the file
+    img = np.zeros((h, w, 3), np.float32)
+    for y in range(h):
+        row = np.frombuffer(data, np.float32, 3 * w, y * (8 + 12 * w) + 8).reshape(3, w)
+        img[y] = row[::-1].T
+    sc = ptb.Scene(ptb.load_file(scene_path), ctx=gpu_ctx)
+    ref = sc.render(ptb.RenderOptions(samples_per_pixel=6, render_method=1, width=96, height=54, seed=9))
+    assert np.max(np.abs(img - ref)) < 1e-5
+    assert subprocess.run([cli, "-f", scene_path, "--gpus", "0"], capture_output=True).returncode != 0

@@ -170,3 +170,68 @@ def test_image_save(ptb, tmp_path):
         ptb.save_image(str(tmp_path / "a.b.png"), 8, 4, img)                # filename must split into exactly two parts
     with pytest.raises(ptb.PtbError):
         ptb.save_image(str(tmp_path / "out.webp"), 8, 4, img)
+
+
+def _read_exr(path):
+    """Minimal reader of the OpenEXR 2 scanline layout ("OpenEXR File Layout": magic, version, attributes, offset table,
+    per-scanline chunks with the channels in alphabetical order) — enough to check the writer against the specification."""
+    import struct
+    raw = open(path, "rb").read()
+    assert struct.unpack_from("<II", raw, 0) == (20000630, 2)
+    pos, attrs = 8, {}
+    while raw[pos] != 0:
+        e = raw.index(b"\0", pos); name = raw[pos:e].decode(); pos = e + 1
+        e = raw.index(b"\0", pos); typ = raw[pos:e].decode(); pos = e + 1
+        (size,) = struct.unpack_from("<i", raw, pos); pos += 4
+        attrs[name] = (typ, raw[pos:pos + size]); pos += size
+    pos += 1
+    assert attrs["compression"] == ("compression", b"\0") and attrs["lineOrder"] == ("lineOrder", b"\0")
+    x0, y0, x1, y1 = struct.unpack("<4i", attrs["dataWindow"][1])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    chans, c = [], attrs["channels"][1]
+    q = 0
+    while c[q] != 0:
+        e = c.index(b"\0", q); chans.append(c[q:e].decode())
+        assert struct.unpack_from("<i", c, e + 1)[0] == 2        # FLOAT
+        q = e + 1 + 16
+    assert chans == sorted(chans) == ["B", "G", "R"]
+    offsets = struct.unpack_from(f"<{h}Q", raw, pos)
+    img = np.zeros((h, w, 3), np.float32)
+    for y, off in enumerate(offsets):
+        yy, size = struct.unpack_from("<ii", raw, off)
+        assert yy == y and size == 12 * w
+        row = np.frombuffer(raw, np.float32, 3 * w, off + 8).reshape(3, w)
+        img[y] = row[::-1].T                                        # B, G, R planes -> RGB pixels
+    assert offsets[-1] + 8 + 12 * w == len(raw)
+    return img
+
+
+def test_image_save_every_reference_extension(ptb, tmp_path):
+    """SURVEY.md §8(f) N2 — output/src/lib.rs:89-107: png | jpg | jpeg | tiff | ppm | bmp through the 8-bit gamma mapping,
+    exr as linear f32. The files are read back with independent decoders (Pillow; the EXR layout parser above)."""
+    from PIL import Image
+    w, h = 67, 45                                                    # not multiples of the 8 x 8 JPEG block
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([xx / w, yy / h, 0.5 + 0.5 * np.sin(xx / 5.0) * np.cos(yy / 7.0)], -1).astype(np.float32)
+    img[5:9, 5:9] = [2.0, 0.0, 1.5]                                  # saturates: Rust `as u8` clamps
+    img[0, 0] = [np.nan, -1.0, 0.25]                                 # NaN and negatives -> 0
+    want8 = np.clip(np.nan_to_num(np.power(img, np.float32(1 / 2.2)) * np.float32(255.999), nan=0.0), 0, 255).astype(np.uint8)
+    for ext in ("png", "tiff", "bmp", "ppm"):
+        f = tmp_path / f"o.{ext}"
+        ptb.save_image(str(f), w, h, img, 2.2)
+        assert np.array_equal(np.asarray(Image.open(f).convert("RGB")), want8), ext
+    for ext in ("jpg", "jpeg"):
+        f = tmp_path / f"o.{ext}"
+        ptb.save_image(str(f), w, h, img, 2.2)
+        im = Image.open(f)
+        assert im.format == "JPEG" and im.size == (w, h)
+        got = np.asarray(im.convert("RGB")).astype(np.float64)
+        ours = np.sqrt(np.mean((got - want8) ** 2))
+        g = tmp_path / "pil.jpg"                                     # Pillow's own quality-75 4:4:4 encode of the same pixels
+        Image.fromarray(want8).save(g, quality=75, subsampling=0)
+        theirs = np.sqrt(np.mean((np.asarray(Image.open(g)).astype(np.float64) - want8) ** 2))
+        assert ours < 1.25 * theirs + 0.5, (ours, theirs)
+    f = tmp_path / "o.exr"
+    ptb.save_image(str(f), w, h, img, 2.2)                           # gamma is ignored for exr (lib.rs:98-99)
+    back = _read_exr(f)
+    assert np.array_equal(back.view(np.uint32), img.view(np.uint32))    # linear f32, bit for bit (NaN included)

@@ -331,7 +331,8 @@ def test_oracle_agrees_with_f64_moller_trumbore(ptb, orc, rtweekend1, overshadow
     assert np.array_equal(r["prim"][sure], f["prim"][sure])
     hit = sure & (f["prim"] != 0xFFFFFFFF)
     assert hit.sum() > 3000
-    assert np.all(np.abs(r["t"][hit] - f["t"][hit]) <= 1e-5 * np.maximum(np.abs(f["t"][hit]), scale))
+    # a sphere hit at grazing margin m = sqrt(discriminant) / radius is conditioned like 1 / m
+    assert np.all(np.abs(r["t"][hit] - f["t"][hit]) <= 1e-5 * np.abs(f["t"][hit]) + 2e-6 * scale / np.minimum(margin[hit], 1.0))
     inq = q1 & (r["prim"] != f["prim"]) & (margin > 1e-4)
     assert np.all((r["prim"][inq] == 0xFFFFFFFF) | (r["t"][inq] >= f["t"][inq] * (1 - 1e-5)))
     if which == "c3":

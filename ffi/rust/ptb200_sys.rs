@@ -31,6 +31,9 @@ pub struct ptb_stats {
     pub nodes_fetched: u64, pub prims_tested: u64, pub rays_counted: u64, pub trace_launches: u64,
     pub build_ms: f64, pub render_ms: f64, pub ms_generate: f64, pub ms_trace: f64, pub ms_shade: f64, pub ms_shadow: f64,
 }
+/// sampler test hook (chi-squared harness on the device samplers); kind = PTB_SAMPLER_* (0 lambertian, 1 TR VNDF, 2 sky, 3 light, 4 uniform sphere)
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct ptb_sampler_query { pub kind: u32, pub alpha: f32, pub normal: ptb_vec3, pub aux: ptb_vec3, pub light_index: u32, pub seed: u64 }
 #[repr(C)] pub struct ptb_ctx { _private: [u8; 0] }
 pub type ptb_progress_fn = Option<unsafe extern "C" fn(user: *mut c_void, samples_completed: u64, rays_shot: u64) -> i32>;
 /// per-pass presentation closure (random_sampler.rs:82-98): single-sample image of a finished pass, 1-based pass number
@@ -59,5 +62,7 @@ extern "C" {
     pub fn ptb_accum_clear(ctx: *mut ptb_ctx) -> i32;
     pub fn ptb_accum_read(ctx: *mut ptb_ctx, rgb: *mut f32, n_floats: usize, normalise: i32) -> i32;
     pub fn ptb_accum_device_ptr(ctx: *mut ptb_ctx, d_ptr: *mut *mut c_void, n_floats: *mut usize) -> i32;
+    pub fn ptb_sample_only(ctx: *mut ptb_ctx, query: *const ptb_sampler_query, n: usize, dirs: *mut f32, pdf: *mut f32) -> i32;
+    pub fn ptb_sampler_pdf(ctx: *mut ptb_ctx, query: *const ptb_sampler_query, dirs: *const f32, n: usize, pdf: *mut f32) -> i32;
     pub fn ptb_stats_get(ctx: *mut ptb_ctx, out: *mut ptb_stats) -> i32;
 }

@@ -277,6 +277,32 @@ void    ptb_shard_rows(uint32_t rows, uint32_t row_begin, int32_t rank, int32_t 
  * bound at run time (libnccl.so.2, or $PTB_NCCL_LIB); n == 1 never touches it. */
 int32_t ptb_render_multi(ptb_ctx* const* ctxs, int32_t n, const ptb_render_opts* opts);
 
+/* ----------------------------------------------------- sampler test hook -- */
+/* The reference's best-pinned tests are chi-squared tests of its direction samplers against their pdfs
+ * (implementations/statistics/spherical_sampling.rs:64-226, bxdfs/lambertian.rs:30-48, bxdfs/trowbridge_reitz_vndf.rs:156-218,
+ * sky.rs:43-78). These two entry points run the DEVICE samplers — the same functions the shade kernel calls — outside a
+ * render so the same harness can be pointed at them. Host buffers. */
+enum {
+  PTB_SAMPLER_LAMBERTIAN = 0,     /* lambertian::sample about `normal`                         (bxdfs/lambertian.rs:5-22)   */
+  PTB_SAMPLER_TR_VNDF = 1,        /* trowbridge_reitz_vndf::sample(alpha, incoming = aux, normal) (..._vndf.rs:35-52, 84-113) */
+  PTB_SAMPLER_SKY = 2,            /* Sky::sample / Sky::pdf of the committed scene             (sky.rs:43-78)               */
+  PTB_SAMPLER_LIGHT = 3,          /* sample_visible_from_point / scattering_pdf of light `light_index` seen from the shading
+                                     point aux with surface normal `normal`                   (sphere.rs:112-170, triangle.rs:249-280) */
+  PTB_SAMPLER_UNIFORM_SPHERE = 4  /* the fixed-budget stand-in for random_unit_vector          (utility/mod.rs:15-25)       */
+};
+typedef struct ptb_sampler_query {
+  uint32_t kind;         /* PTB_SAMPLER_*                                                                           */
+  float    alpha;        /* TR_VNDF                                                                                  */
+  ptb_vec3 normal;       /* LAMBERTIAN, TR_VNDF: surface normal; LIGHT: normal at the shading point                  */
+  ptb_vec3 aux;          /* TR_VNDF: unit direction from the surface towards the viewer; LIGHT: the shading point     */
+  uint32_t light_index;  /* LIGHT: index into the scene's light list (original primitive order)                       */
+  uint64_t seed;         /* sample k draws from Philox counter (k, 0, test stream), key = seed                        */
+} ptb_sampler_query;
+/* n sampled directions (3 floats each) and, when pdf != NULL, the sampler's own pdf of each. */
+int32_t ptb_sample_only(ptb_ctx* ctx, const ptb_sampler_query* query, size_t n, float* dirs, float* pdf);
+/* pdf of n given unit directions under the same sampler. */
+int32_t ptb_sampler_pdf(ptb_ctx* ctx, const ptb_sampler_query* query, const float* dirs, size_t n, float* pdf);
+
 int32_t ptb_stats_get(ptb_ctx* ctx, ptb_stats* out);
 int32_t ptb_stats_reset(ptb_ctx* ctx);
 

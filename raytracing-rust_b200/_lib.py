@@ -70,6 +70,14 @@ class Vec3(C.Structure):
     _fields_ = [("x", C.c_float), ("y", C.c_float), ("z", C.c_float)]
 
 
+SAMPLER_LAMBERTIAN, SAMPLER_TR_VNDF, SAMPLER_SKY, SAMPLER_LIGHT, SAMPLER_UNIFORM_SPHERE = range(5)
+
+
+class SamplerQuery(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("alpha", C.c_float), ("normal", Vec3), ("aux", Vec3), ("light_index", C.c_uint32),
+                ("seed", C.c_uint64)]
+
+
 PROGRESS_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64)
 PASS_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(C.c_float), C.c_size_t, C.c_uint64, C.c_uint64)
 
@@ -105,6 +113,8 @@ SYMBOLS = [
     ("ptb_shard_samples", None, [C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("ptb_shard_rows", None, [C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     ("ptb_render_multi", C.c_int32, [_P, C.c_int32, C.POINTER(RenderOpts)]),
+    ("ptb_sample_only", C.c_int32, [_P, C.POINTER(SamplerQuery), C.c_size_t, _P, _P]),
+    ("ptb_sampler_pdf", C.c_int32, [_P, C.POINTER(SamplerQuery), _P, C.c_size_t, _P]),
     ("ptb_stats_get", C.c_int32, [_P, C.POINTER(Stats)]),
     ("ptb_stats_reset", C.c_int32, [_P]),
     ("ptb_ssml_load_file", C.c_int32, [C.c_char_p, C.POINTER(_P)]),

@@ -168,6 +168,25 @@ class Context:
     def accum_set_samples(self, n: int):
         _check(self._h, L.lib.ptb_accum_set_samples(self._h, n))
 
+    # ---- sampler test hook (the reference's chi-squared harness pointed at the device samplers)
+    @staticmethod
+    def _query(kind, alpha, normal, aux, light_index, seed) -> L.SamplerQuery:
+        return L.SamplerQuery(kind, float(alpha), L.Vec3(*map(float, normal)), L.Vec3(*map(float, aux)), int(light_index), int(seed))
+
+    def sample_only(self, kind: int, n: int, alpha=0.0, normal=(0, 0, 1), aux=(0, 0, 1), light_index=0, seed=0):
+        """n directions from device sampler `kind` (L.SAMPLER_*) and the sampler's pdf of each: (dirs (n, 3), pdf (n,))."""
+        q = self._query(kind, alpha, normal, aux, light_index, seed)
+        dirs, pdf = np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
+        _check(self._h, L.lib.ptb_sample_only(self._h, C.byref(q), n, L.ptr(dirs), L.ptr(pdf)))
+        return dirs, pdf
+
+    def sampler_pdf(self, kind: int, dirs: np.ndarray, alpha=0.0, normal=(0, 0, 1), aux=(0, 0, 1), light_index=0):
+        q = self._query(kind, alpha, normal, aux, light_index, 0)
+        dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        pdf = np.zeros(len(dirs), np.float32)
+        _check(self._h, L.lib.ptb_sampler_pdf(self._h, C.byref(q), L.ptr(dirs), len(dirs), L.ptr(pdf)))
+        return pdf
+
     def stats(self) -> L.Stats:
         s = L.Stats()
         _check(self._h, L.lib.ptb_stats_get(self._h, C.byref(s)))

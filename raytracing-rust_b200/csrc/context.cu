@@ -495,6 +495,18 @@ int32_t ptb_accum_set_samples(ptb_ctx* ctx, uint64_t total_samples) {
   return PTB_OK;
 }
 
+// ---------------------------------------------------------------- sampler test hook
+int32_t ptb_sample_only(ptb_ctx* ctx, const ptb_sampler_query* query, size_t n, float* dirs, float* pdf) {
+  CTX_OR_FAIL(ctx);
+  if (!query || (n && !dirs)) return set_error(c, PTB_ERR_INVALID, "null argument");
+  return sampler_hook(c, *query, n, nullptr, dirs, pdf);
+}
+int32_t ptb_sampler_pdf(ptb_ctx* ctx, const ptb_sampler_query* query, const float* dirs, size_t n, float* pdf) {
+  CTX_OR_FAIL(ctx);
+  if (!query || (n && (!dirs || !pdf))) return set_error(c, PTB_ERR_INVALID, "null argument");
+  return sampler_hook(c, *query, n, dirs, nullptr, pdf);
+}
+
 int32_t ptb_stats_get(ptb_ctx* ctx, ptb_stats* out) {
   CTX_OR_FAIL(ctx);
   if (!out) return PTB_ERR_INVALID;

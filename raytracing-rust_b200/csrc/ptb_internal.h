@@ -139,6 +139,7 @@ size_t radix_sort_hist_words(uint32_t n);
 int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progress, void* user);
 int32_t launch_closest_hit(Ctx* c, const void* d_rays, size_t n, void* d_hits);
 void free_render_state(Ctx* c);
+int32_t sampler_hook(Ctx* c, const ptb_sampler_query& q, size_t n, const float* dirs_in, float* dirs_out, float* pdf_out);
 
 }  // namespace ptb
 

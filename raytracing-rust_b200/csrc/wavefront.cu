@@ -188,6 +188,25 @@ PTB_DEV float light_pdf(const DevScene& sc, uint32_t ref, v3 hit_point, v3 wi, v
   return mag_sq(s_point - hit_point) / (fabsf(dot(wi, s_normal)) * area);
 }
 
+// ------------------------------------------------------------------------------------------ BSDF direction samplers
+// The sampling arithmetic of k_shade as functions, so that the chi-squared test hook (k_sample_only below) draws from the
+// very code the integrator runs.
+// lambertian.rs:30-41, statistics/bxdfs/lambertian.rs:5-18, utility/coord.rs:10-30
+PTB_DEV v3 lambertian_sample_dir(v3 normal, float r1, float r2) {
+  const float cos_theta = sqrtf(1.0f - r1);
+  const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+  const float phi = 2.0f * kPi * r2;
+  return onb_to_world(normal, mk(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cos_theta));
+}
+// random_unit_vector (utility/mod.rs:15-25) is a rejection loop whose result is uniform on the sphere — drawn directly here
+// from two uniforms (fixed RNG budget), same distribution
+PTB_DEV v3 uniform_sphere_dir(float r1, float r2) {
+  const float z = 1.0f - 2.0f * r1;
+  const float rr = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+  const float phi = 2.0f * kPi * r2;
+  return mk(rr * cosf(phi), rr * sinf(phi), z);
+}
+
 // ------------------------------------------------------------------------------------------ bookkeeping kernels
 __global__ void k_init_pool(uint32_t* free_slots, uint32_t capacity, WaveCounters* wc, unsigned long long total_samples) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -776,23 +795,15 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
       v3 new_o, new_dir;
       bool delta = false;
       if (s.kind == PTB_MAT_LAMBERTIAN) {
-        // lambertian.rs:30-41, statistics/bxdfs/lambertian.rs:5-18, utility/coord.rs:10-30
-        const float cos_theta = sqrtf(1.0f - u32_to_unit(r.x));
-        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
-        const float phi = 2.0f * kPi * u32_to_unit(r.y);
-        new_dir = onb_to_world(s.h.normal, mk(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cos_theta));
+        new_dir = lambertian_sample_dir(s.h.normal, u32_to_unit(r.x), u32_to_unit(r.y));
         new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
       } else if (FULL && s.kind == PTB_MAT_TROWBRIDGE_REITZ) {
         // trowbridge_reitz.rs:38-50: VNDF sample about the normal, draws (r, phi) = (sqrt(u1), tau * u2)
         new_dir = tr_sample(s.param, -wo, s.h.normal, u32_to_unit(r.x), u32_to_unit(r.y));
         new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
       } else if (s.kind == PTB_MAT_REFLECT) {
-        // reflect.rs:26-36; random_unit_vector (utility/mod.rs:15-25) is a rejection loop whose result is uniform on
-        // the sphere — drawn directly here from two uniforms (fixed RNG budget), same distribution
-        const float z = 1.0f - 2.0f * u32_to_unit(r.x);
-        const float rr = sqrtf(fmaxf(1.0f - z * z, 0.0f));
-        const float phi = 2.0f * kPi * u32_to_unit(r.y);
-        const v3 unit = mk(rr * cosf(phi), rr * sinf(phi), z);
+        // reflect.rs:26-36
+        const v3 unit = uniform_sphere_dir(u32_to_unit(r.x), u32_to_unit(r.y));
         new_dir = reflected(-wo, s.h.normal) + s.param * unit;
         new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
         delta = true;
@@ -1206,6 +1217,99 @@ k_closest_hit_api(DevScene sc, const float4* __restrict__ rays, const uint32_t* 
       atomicAdd(counts + 1, (unsigned long long)cnt_prims);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------ sampler test hook
+// ptb_sample_only / ptb_sampler_pdf (include/ptb200.h): the reference's best-pinned tests are chi-squared tests of its
+// samplers against their pdfs (statistics/spherical_sampling.rs:64-226, bxdfs/lambertian.rs:30-48,
+// bxdfs/trowbridge_reitz_vndf.rs:156-218, distributions.rs:186-300). These two kernels expose the DEVICE samplers — the
+// functions k_shade calls — to the same harness: sample k draws its uniforms from Philox counter (k, 0, RNG_TEST, block).
+constexpr uint32_t RNG_TEST = 7;
+// light sampling as k_shade runs it (integrators/mis.rs:117-133, acceleration/mod.rs:231-243): pdf of direction `wi` from
+// the shading point (point, normal) towards light `lref`, 0 when the light is not hit
+PTB_DEV float light_dir_pdf(const DevScene& sc, uint32_t lref, v3 point, v3 normal, v3 wi) {
+  const v3 so = point + 0.0001f * normal;
+  const Ray sray = make_ray_from_raw(so, wi);
+  HitRec si;
+  if (prim_hit(sc, sray, lref, si) && si.t > 0.0f) return light_pdf(sc, lref, point, wi, si.point, si.normal);
+  return 0.0f;
+}
+__global__ void k_sample_only(DevScene sc, ptb_sampler_query q, uint32_t n, float* __restrict__ dirs, float* __restrict__ pdf) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t k0 = (uint32_t)q.seed, k1 = (uint32_t)(q.seed >> 32);
+  const uint4 r = philox4x32_10(k, 0u, RNG_TEST, 0u, k0, k1);
+  const v3 normal = mk(q.normal.x, q.normal.y, q.normal.z), aux = mk(q.aux.x, q.aux.y, q.aux.z);
+  v3 d = mk(0.0f, 0.0f, 0.0f);
+  float p = 0.0f;
+  switch (q.kind) {
+    case PTB_SAMPLER_LAMBERTIAN:
+      d = lambertian_sample_dir(normal, u32_to_unit(r.x), u32_to_unit(r.y));
+      p = fmaxf(dot(d, normal), 0.0f) / kPi;
+      break;
+    case PTB_SAMPLER_TR_VNDF:
+      d = tr_sample(q.alpha, aux, normal, u32_to_unit(r.x), u32_to_unit(r.y));
+      p = tr_pdf(q.alpha, aux, d, normal);
+      break;
+    case PTB_SAMPLER_SKY: {
+      const uint4 r2 = philox4x32_10(k, 0u, RNG_TEST, 1u, k0, k1);
+      d = sky_sample(sc, u32_to_unit(r.y), u32_to_unit(r.z), u32_to_unit(r.w), u32_to_unit(r2.x));  // draws as in k_shade
+      p = sky_pdf(sc, d);
+      break;
+    }
+    case PTB_SAMPLER_LIGHT: {
+      const uint32_t lref = __ldg(sc.lights + q.light_index);
+      d = light_sample_dir(sc, lref, aux, u32_to_unit(r.y), u32_to_unit(r.z));
+      p = light_dir_pdf(sc, lref, aux, normal, d);
+      break;
+    }
+    default:
+      d = uniform_sphere_dir(u32_to_unit(r.x), u32_to_unit(r.y));
+      p = 1.0f / (4.0f * kPi);
+  }
+  dirs[3u * (size_t)k + 0] = d.x; dirs[3u * (size_t)k + 1] = d.y; dirs[3u * (size_t)k + 2] = d.z;
+  if (pdf) pdf[k] = p;
+}
+__global__ void k_sampler_pdf(DevScene sc, ptb_sampler_query q, uint32_t n, const float* __restrict__ dirs, float* __restrict__ pdf) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const v3 normal = mk(q.normal.x, q.normal.y, q.normal.z), aux = mk(q.aux.x, q.aux.y, q.aux.z);
+  const v3 d = mk(dirs[3u * (size_t)k], dirs[3u * (size_t)k + 1], dirs[3u * (size_t)k + 2]);
+  float p;
+  switch (q.kind) {
+    case PTB_SAMPLER_LAMBERTIAN: p = fmaxf(dot(d, normal), 0.0f) / kPi; break;
+    case PTB_SAMPLER_TR_VNDF: p = tr_pdf(q.alpha, aux, d, normal); break;
+    case PTB_SAMPLER_SKY: p = sky_pdf(sc, d); break;
+    case PTB_SAMPLER_LIGHT: p = light_dir_pdf(sc, __ldg(sc.lights + q.light_index), aux, normal, d); break;
+    default: p = 1.0f / (4.0f * kPi);
+  }
+  pdf[k] = p;
+}
+int32_t sampler_hook(Ctx* c, const ptb_sampler_query& q, size_t n, const float* dirs_in, float* dirs_out, float* pdf_out) {
+  if (q.kind > PTB_SAMPLER_UNIFORM_SPHERE) return set_error(c, PTB_ERR_INVALID, "unknown sampler kind %u", q.kind);
+  if ((q.kind == PTB_SAMPLER_SKY || q.kind == PTB_SAMPLER_LIGHT) && !c->committed)
+    return set_error(c, PTB_ERR_INVALID, "sky / light samplers need a committed scene");
+  if (q.kind == PTB_SAMPLER_SKY && (c->dev.sky_rx | c->dev.sky_ry) == 0u) return set_error(c, PTB_ERR_INVALID, "the scene's sky is not samplable");
+  if (q.kind == PTB_SAMPLER_LIGHT && q.light_index >= c->dev.n_lights) return set_error(c, PTB_ERR_INVALID, "light index out of range");
+  if (n == 0) return PTB_OK;
+  if (n > 0x7FFFFFFFull) return set_error(c, PTB_ERR_INVALID, "too many samples");
+  PTB_CUDA_TRY(c, c->d_rays.reserve(n * 12));
+  PTB_CUDA_TRY(c, c->d_hits.reserve(n * 4));
+  float* d_dirs = c->d_rays.as<float>();
+  float* d_pdf = c->d_hits.as<float>();
+  const uint32_t n32 = (uint32_t)n, grid = (n32 + 255u) / 256u;
+  if (dirs_in) {
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(d_dirs, dirs_in, n * 12, cudaMemcpyHostToDevice, c->stream));
+    k_sampler_pdf<<<grid, 256, 0, c->stream>>>(c->dev, q, n32, d_dirs, d_pdf);
+  } else {
+    k_sample_only<<<grid, 256, 0, c->stream>>>(c->dev, q, n32, d_dirs, d_pdf);
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(dirs_out, d_dirs, n * 12, cudaMemcpyDeviceToHost, c->stream));
+  }
+  c->stats.kernel_launches += 1;
+  if (pdf_out) PTB_CUDA_TRY(c, cudaMemcpyAsync(pdf_out, d_pdf, n * 4, cudaMemcpyDeviceToHost, c->stream));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  PTB_CUDA_TRY(c, cudaGetLastError());
+  return PTB_OK;
 }
 
 // ------------------------------------------------------------------------------------------ host side

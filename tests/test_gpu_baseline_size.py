@@ -176,7 +176,7 @@ def test_converged_c3_mesh_1024spp(ptb, orc, gpu_ctx):
 
 
 # ------------------------------------------------------------------------------------------------ (vi) independent intersector
-def check_against_f64(ptb, g, f, margin, rays, scale):
+def check_against_f64(ptb, g, f, margin, rays, scale, bary_tol=1e-4):
     """Device (f32 watertight, reference arithmetic) vs f64 Moller-Trumbore over every primitive.
     Outside the Q1 region and away from grazing / near-tie decisions (margin > 1e-4): ids equal and
     |dt| <= 1e-5 t + 2e-6 scale / min(margin, 1): a sphere hit at grazing margin m = sqrt(discriminant) / radius is
@@ -190,8 +190,9 @@ def check_against_f64(ptb, g, f, margin, rays, scale):
     hit = sure & (f["prim"] != MISS)
     tol = 1e-5 * np.abs(f["t"][hit]) + 2e-6 * scale[hit] / np.minimum(margin[hit], 1.0)
     assert np.all(np.abs(g["t"][hit] - f["t"][hit]) <= tol)
+    # barycentrics: an f32 position error of ~t * 1e-6 relative to the triangle's size (2e-2 at 1 M triangles, t ~ 5)
     tri = hit & (f["u"] + f["v"] > 0)
-    assert np.all(np.abs(g["u"][tri] - f["u"][tri]) < 1e-4) and np.all(np.abs(g["v"][tri] - f["v"][tri]) < 1e-4)
+    assert np.all(np.abs(g["u"][tri] - f["u"][tri]) < bary_tol) and np.all(np.abs(g["v"][tri] - f["v"][tri]) < bary_tol)
     inq = q1 & (g["prim"] != f["prim"]) & (margin > 1e-4)
     lost = (g["prim"][inq] == MISS) | (g["t"][inq] >= f["t"][inq] * (1 - 1e-5))
     assert np.all(lost)
@@ -217,5 +218,5 @@ def test_f64_intersector_c3_full_size(ptb, gpu_ctx, c3_full, c3_full_oracle):
     gpu_ctx.commit()
     g = gpu_ctx.closest_hit(rays)
     f, margin = c3_full_oracle.closest_hit_f64(rays)
-    frac_q1_lost = check_against_f64(ptb, g, f, margin, rays, np.full(len(rays), 12.0, np.float32))
+    frac_q1_lost = check_against_f64(ptb, g, f, margin, rays, np.full(len(rays), 12.0, np.float32), bary_tol=2e-3)
     assert frac_q1_lost < 0.02

@@ -29,7 +29,7 @@ pub struct ptb_stats {
     pub rays_camera: u64, pub rays_bounce: u64, pub rays_shadow_light: u64, pub rays_shadow_sky: u64,
     pub rays_reference: u64, pub paths: u64, pub wavefront_iterations: u64, pub kernel_launches: u64,
     pub nodes_fetched: u64, pub prims_tested: u64, pub rays_counted: u64, pub trace_launches: u64,
-    pub build_ms: f64, pub render_ms: f64, pub ms_generate: f64, pub ms_trace: f64, pub ms_shade: f64, pub ms_shadow: f64,
+    pub build_ms: f64, pub render_ms: f64, pub ms_generate: f64, pub ms_trace: f64, pub ms_shade: f64, pub ms_shadow: f64, pub ms_tail: f64,
 }
 /// sampler test hook (chi-squared harness on the device samplers); kind = PTB_SAMPLER_* (0 lambertian, 1 TR VNDF, 2 sky, 3 light, 4 uniform sphere)
 #[repr(C)] #[derive(Clone, Copy)]

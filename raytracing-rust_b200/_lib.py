@@ -55,7 +55,7 @@ class Stats(C.Structure):
                 ("wavefront_iterations", C.c_uint64), ("kernel_launches", C.c_uint64), ("nodes_fetched", C.c_uint64),
                 ("prims_tested", C.c_uint64), ("rays_counted", C.c_uint64), ("trace_launches", C.c_uint64),
                 ("build_ms", C.c_double), ("render_ms", C.c_double), ("ms_generate", C.c_double),
-                ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("ms_shadow", C.c_double)]
+                ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("ms_shadow", C.c_double), ("ms_tail", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

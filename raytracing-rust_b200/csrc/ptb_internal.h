@@ -111,9 +111,14 @@ struct Ctx {
   uint32_t accum_w = 0, accum_h = 0;
   uint64_t accum_samples = 0;
   DevBuf d_pool_mem, d_prev, d_queues, d_shadow, d_counters, d_windows;
+  // second chunk slot of the window wavefront: chunk k+1's wide iterations run on the main stream while chunk k's fused
+  // tail (k_tail) finishes on `s_tail` in the other slot
+  DevBuf d_pool_mem2, d_prev2, d_queues2, d_shadow2, d_counters2, d_windows2;
+  cudaStream_t s_tail = nullptr;
+  cudaEvent_t ev_head_done[2] = {}, ev_tail_done[2] = {}, ev_tail_prof[4] = {};
   PathPool pool;
   size_t pool_budget_bytes = 0;  // half of the device memory that was free at the first large render (0 = not asked yet)
-  WaveCounters* h_counters = nullptr;  // pinned
+  WaveCounters* h_counters = nullptr;  // pinned: [0..1] per-iteration mirrors, [2..3] end-of-render copy of each slot
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_iter = nullptr;
   cudaEvent_t ev_prof[16] = {};  // PTB_OPT_TIME_KERNELS: 2 iterations x 4 kernel classes x (start, stop)
   bool opt_time_kernels = false, opt_count_traversal = false;

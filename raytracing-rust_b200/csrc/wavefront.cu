@@ -582,6 +582,269 @@ PTB_DEV uint32_t direction_bin(v3 d) {
 #endif
 }
 
+// One path, one bounce: everything the integrators do between two check_hit calls (emission, MIS weights, NEE sample, BSDF
+// sample, Russian roulette, termination). Reads the path's records (ray + hit, colour) from the pool and writes the
+// continuing path's records back; what the caller has to route (queues, accumulator, shadow ray) comes back in `o`.
+// Shared by the wavefront kernel k_shade and the fused tail kernel k_tail.
+struct ShadeOut {
+  bool alive = false;       // path continues: goes to the next active queue
+  bool finished = false;    // path ended: slot returns to the free list
+  bool shadow = false;      // an NEE ray was produced
+  bool contributes = false; // finished with a radiance that passes the NaN test (integrators/mod.rs:74-76, mis.rs:88-90)
+  uint32_t shadow_is_sky = 0, fin_pixel = 0;
+  uint32_t bin = 0;         // direction bin of the continuing ray
+  float4 sh_o, sh_d, sh_c;  // NEE ray: o.xyz|tmax, d.xyz|exclude slot, contribution.rgb|path slot
+  v3 fin_L;
+};
+template <int METHOD, bool FULL>
+PTB_DEV void shade_path(const DevScene& sc, const PathPool& pool, const RenderParams& rp, uint32_t slot, bool depth0,
+                        unsigned long long camera_first, ShadeOut& o) {
+  bool &alive = o.alive, &finished = o.finished, &shadow = o.shadow, &contributes = o.contributes;
+  uint32_t &shadow_is_sky = o.shadow_is_sky, &fin_pixel = o.fin_pixel;
+  float4 &sh_o = o.sh_o, &sh_d = o.sh_d, &sh_c = o.sh_c;
+  v3& fin_L = o.fin_L;
+  float4 ro, rd, th, ra;
+  ldg256_rw(pool.ray + 4u * (size_t)slot, ro, rd);
+  if (depth0) {
+    uint32_t x, y, smp;
+    camera_pixel_sample(rp, camera_first + slot, x, y, smp);
+    th = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(y * rp.width + x));
+    ra = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(smp << 9));
+  } else {
+    ldg256_rw(pool.col + 4u * (size_t)slot, th, ra);
+  }
+  const uint2 ht = make_uint2(__float_as_uint(ro.w), __float_as_uint(rd.w));
+  const uint32_t pixel = __float_as_uint(th.w);
+  const uint32_t df = __float_as_uint(ra.w);
+  const uint32_t sample = df >> 9;
+  uint32_t depth = df & 0xFFu;
+  const bool prev_delta = (df & kFlagPrevDelta) != 0u;
+  const Ray ray = make_ray(from4(ro), from4(rd));
+  const v3 wo = ray.d;
+  v3 T = from4(th), L = from4(ra);
+
+  Surface s;
+  s.miss = ht.y == kNone;
+  if (s.miss) {  // sky.rs:79-91: zero Hit + Emit(sky texture, 1.0)
+    s.h.t = 0.0f;
+    s.h.point = s.h.error = s.h.normal = mk(0.0f, 0.0f, 0.0f);
+    s.h.out = false;
+    s.kind = PTB_MAT_EMIT;
+    s.tex = sc.sky_tex;
+    s.mat = 0u;
+    s.param = 1.0f;
+  } else {
+    prim_hit(sc, ray, ht.y, s.h);  // same arithmetic as the traversal: reproduces t, adds point/normal/error/out
+    const uint32_t mi = __ldg(sc.slot_mat + (ht.y & kSlotMask)) & 0x00FFFFFFu;
+    const DevMaterial* m = sc.materials + mi;
+    s.mat = mi;
+    s.kind = __ldg(&m->kind);
+    s.tex = __ldg(&m->tex);
+    s.param = __ldg(&m->param);
+  }
+  const bool is_emit = s.kind == PTB_MAT_EMIT;
+  bool depart = false;
+  bool nan_check = true;
+
+  if (METHOD == PTB_METHOD_NAIVE) {
+    // integrators/mod.rs:29-72
+    if (is_emit) {
+      const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);        // emissive.rs:23-26
+      const v3 emission = s.param * texture_colour<FULL>(sc, s.tex, wo, point);
+      L = L + T * emission;  // depth 0: throughput is exactly (1,1,1)
+      finished = true;
+    } else {
+      depart = true;
+    }
+  } else {
+    // integrators/mis.rs:17-31 (first hit) and :52-80 (after each bounce)
+    if (depth == 0u) {
+      if (is_emit) {
+        const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+        L = L + s.param * texture_colour<FULL>(sc, s.tex, wo, point);
+        finished = true;
+        nan_check = false;  // mis.rs:29-31 returns before the NaN test
+      } else {
+        depth = 1u;
+        depart = true;
+      }
+    } else {
+      if (is_emit) {
+        // mis.rs:55: emission of the NEW material evaluated with the PREVIOUS hit record (quirk Q6); the
+        // previous hit's offset point is this ray's origin (lambertian.rs:37, reflect.rs:29)
+        const v3 le = s.param * texture_colour<FULL>(sc, s.tex, wo, ray.o);
+        if (!is_zero(le)) {
+          const bool sky_samplable = (sc.sky_rx | sc.sky_ry) != 0u;
+          const bool use_mis = s.miss ? sky_samplable : !prev_delta;  // mis.rs:57-60 (an emissive prim is in `lights`)
+          if (use_mis) {
+            const float divisor = (float)(sky_samplable ? sc.n_lights + 1u : sc.n_lights);  // acceleration/mod.rs:299-318
+            const float4 pv = pool.prev[slot];  // previous hit point | m_pdf of the BSDF sample that got us here
+            const float l_pdf = s.miss ? sky_pdf(sc, wo) / divisor
+                                       : light_pdf(sc, ht.y, from4(pv), wo, s.h.point, s.h.normal) / divisor;
+            const float w = power_heuristic(pv.w, l_pdf);
+            L = L + T * le * w;
+          } else {
+            L = L + T * le;
+          }
+        }
+        finished = true;  // mis.rs:69-71
+      } else {
+        bool survive = true;
+        if (depth > rp.rr_threshold) {  // mis.rs:73-80
+          const float p = cmax3(T.x, T.y, T.z);
+          const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_RR, 0u, rp.k0, rp.k1);
+          if (u32_to_unit(r.x) > p) survive = false;
+          else T = T / p;
+        }
+        depth += 1u;
+        if (survive && depth < rp.max_depth) depart = true;
+        else finished = true;
+      }
+    }
+  }
+
+  if (depart) {
+    float m_pdf = 0.0f;
+    // ---- next-event estimation (MIS only): integrators/mis.rs:36-43, 95-157
+    if (METHOD == PTB_METHOD_MIS) {
+      const uint32_t n_l = sc.n_lights;
+      const bool sky_s = (sc.sky_rx | sc.sky_ry) != 0u;
+      if (n_l != 0u || sky_s) {
+        const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_NEE, 0u, rp.k0, rp.k1);
+        bool do_sky;
+        float mult;
+        uint32_t li = 0;
+        if (n_l == 0u) { do_sky = true; mult = 1.0f; }
+        else if (!sky_s) { do_sky = false; mult = 1.0f / (float)n_l; li = rng_below(r.x, n_l); }
+        else { mult = 1.0f / (float)(n_l + 1u); li = rng_below(r.x, n_l + 1u); do_sky = li == n_l; }
+        const v3 so = s.h.point + 0.0001f * s.h.normal;  // mis.rs:106,124
+        v3 l_wi, le;
+        float l_pdf = 0.0f, tmax = __int_as_float(0x7f800000);
+        uint32_t exclude = kNone;
+        bool usable = false;
+        if (do_sky) {
+          const uint4 r2 = philox4x32_10(pixel, sample, (depth << 8) | RNG_NEE, 1u, rp.k0, rp.k1);
+          l_wi = sky_sample(sc, u32_to_unit(r.y), u32_to_unit(r.z), u32_to_unit(r.w), u32_to_unit(r2.x));
+          const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+          le = 1.0f * texture_colour<FULL>(sc, sc.sky_tex, l_wi, point);
+          l_pdf = sky_pdf(sc, l_wi) * mult;
+          usable = true;
+          shadow_is_sky = 1u;
+        } else {
+          const uint32_t lref = __ldg(sc.lights + li);
+          l_wi = light_sample_dir(sc, lref, s.h.point, u32_to_unit(r.y), u32_to_unit(r.z));
+          const Ray sray = make_ray_from_raw(so, l_wi);
+          HitRec si;
+          if (prim_hit(sc, sray, lref, si) && si.t > 0.0f) {  // acceleration/mod.rs:231-243
+            const float pdf = light_pdf(sc, lref, s.h.point, l_wi, si.point, si.normal);
+            if (pdf > 0.0f) {
+              const uint32_t lmi = __ldg(sc.slot_mat + (lref & kSlotMask)) & 0x00FFFFFFu;
+              const DevMaterial* lm = sc.materials + lmi;
+              const v3 lpoint = offset_ray(si.point, si.normal, si.error, true);
+              le = __ldg(&lm->param) * texture_colour<FULL>(sc, __ldg(&lm->tex), l_wi, lpoint);
+              l_pdf = pdf * mult;
+              tmax = si.t;
+              exclude = lref & kSlotMask;
+              usable = true;
+            }
+          }
+        }
+        if (usable) {
+          const float mp = mat_scattering_pdf<FULL>(s, wo, l_wi);
+          const float w = power_heuristic(l_pdf, mp);
+          const v3 contrib = T * mat_eval<FULL>(sc, s, wo, l_wi) * w * le / l_pdf;  // mis.rs:42
+          const v3 sd = l_wi / mag(l_wi);  // Ray::new normalises (ray.rs:14)
+          sh_o = make_float4(so.x, so.y, so.z, tmax);
+          sh_d = make_float4(sd.x, sd.y, sd.z, __uint_as_float(exclude));
+          sh_c = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(slot));
+          shadow = true;
+        }
+      }
+    }
+    // ---- BSDF sample -> next ray
+    const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_SCATTER, 0u, rp.k0, rp.k1);
+    v3 new_o, new_dir;
+    bool delta = false;
+    if (s.kind == PTB_MAT_LAMBERTIAN) {
+      new_dir = lambertian_sample_dir(s.h.normal, u32_to_unit(r.x), u32_to_unit(r.y));
+      new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+    } else if (FULL && s.kind == PTB_MAT_TROWBRIDGE_REITZ) {
+      // trowbridge_reitz.rs:38-50: VNDF sample about the normal, draws (r, phi) = (sqrt(u1), tau * u2)
+      new_dir = tr_sample(s.param, -wo, s.h.normal, u32_to_unit(r.x), u32_to_unit(r.y));
+      new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+    } else if (s.kind == PTB_MAT_REFLECT) {
+      // reflect.rs:26-36
+      const v3 unit = uniform_sphere_dir(u32_to_unit(r.x), u32_to_unit(r.y));
+      new_dir = reflected(-wo, s.h.normal) + s.param * unit;
+      new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+      delta = true;
+    } else {  // PTB_MAT_REFRACT — refract.rs:27-50
+      float eta_fraction = 1.0f / s.param;
+      if (!s.h.out) eta_fraction = s.param;
+      const float cos_theta = fminf(dot(-wo, s.h.normal), 1.0f);
+      const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+      const bool cannot_refract = eta_fraction * sin_theta > 1.0f;
+      float f0 = (1.0f - eta_fraction) / (1.0f + eta_fraction);
+      f0 = f0 * f0 * 1.0f;
+      const float fres = f0 + (1.0f - f0) * powf(1.0f - cos_theta, 5.0f);  // refract.rs:59-61
+      if (cannot_refract || fres > u32_to_unit(r.x)) {
+        new_dir = reflected(-wo, s.h.normal);  // Reflect{fuzz: 0}: the unit vector is multiplied by 0
+        new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+      } else {
+        const v3 perp = eta_fraction * (wo + cos_theta * s.h.normal);
+        const v3 para = -1.0f * sqrtf(fabsf(1.0f - mag_sq(perp))) * s.h.normal;
+        new_dir = perp + para;
+        new_o = offset_ray(s.h.point, s.h.normal, s.h.error, false);
+      }
+      delta = true;
+    }
+    const v3 nd = new_dir / mag(new_dir);  // Ray::new
+    const bool is_tr = FULL && s.kind == PTB_MAT_TROWBRIDGE_REITZ;
+    const v3 col = is_tr ? tr_eval(sc, s, wo, nd, 1) : texture_colour<FULL>(sc, s.tex, wo, s.h.point);
+    if (METHOD == PTB_METHOD_NAIVE) {
+      // integrators/mod.rs:57-70
+      if (s.kind == PTB_MAT_LAMBERTIAN) T = T * (col * s.param);
+      else T = T * col;  // Trowbridge-Reitz: col is already eval_over_scattering_pdf
+      bool survive = true;
+      if (depth > rp.rr_threshold) {
+        const float p = cmax3(T.x, T.y, T.z);
+        const uint4 r3 = philox4x32_10(pixel, sample, (depth << 8) | RNG_RR, 0u, rp.k0, rp.k1);
+        if (u32_to_unit(r3.x) > p) survive = false;
+        else T = T / p;
+      }
+      depth += 1u;
+      if (survive && depth < rp.max_depth) alive = true;
+      else finished = true;
+    } else {
+      // mis.rs:54-56: m_pdf and throughput use the previous hit only, so they are folded in at departure
+      if (s.kind == PTB_MAT_LAMBERTIAN) {
+        m_pdf = fmaxf(dot(nd, s.h.normal), 0.0f) / kPi;
+        T = T * (col * s.param);
+      } else if (is_tr) {
+        m_pdf = mat_scattering_pdf<FULL>(s, wo, nd);
+        T = T * col;
+      } else {
+        m_pdf = 0.0f;
+        T = T * (col / 0.0f);  // eval / scattering_pdf with the default pdf 0 (quirk Q4)
+      }
+      pool.prev[slot] = make_float4(s.h.point.x, s.h.point.y, s.h.point.z, m_pdf);
+      alive = true;
+    }
+    if (alive) {
+      stg256(pool.ray + 4u * (size_t)slot, make_float4(new_o.x, new_o.y, new_o.z, 0.0f),
+             make_float4(nd.x, nd.y, nd.z, __uint_as_float(kNone)));
+      stg256(pool.col + 4u * (size_t)slot, make_float4(T.x, T.y, T.z, th.w),
+             make_float4(L.x, L.y, L.z, __uint_as_float((sample << 9) | (delta ? kFlagPrevDelta : 0u) | depth)));
+      o.bin = rp.dir_bins ? direction_bin(nd) : 0u;
+    }
+  }
+  if (finished) {
+    contributes = !(nan_check && (contains_nan(L) || !any_finite(L)));
+    fin_pixel = pixel;
+    fin_L = L;
+  }
+}
+
 // DENSE = window mode (ordered live-slot queue in, per-slot direction bin and per-window live count out), else the
 // per-material-kind queues of the regenerating queue mode.
 // MIS shades at one block more per SM than naive (48 registers): rtweekend1 4K 9133 -> 9179 Mrays/s, C3 (naive) would lose 2 %
@@ -620,287 +883,43 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
     active = kq != (uint32_t)kNumKinds;
   }
 
-  bool alive = false;     // path continues: goes to the next active queue
-  bool finished = false;  // path ended: slot returns to the free list
-  bool shadow = false;    // an NEE ray was produced
   uint32_t slot = 0;
-  float4 sh_o, sh_d, sh_c;
-  uint32_t shadow_is_sky = 0;
-  bool contributes = false;  // finished with a radiance that passes the NaN test (integrators/mod.rs:74-76, mis.rs:88-90)
-  uint32_t fin_pixel = 0;
-  v3 fin_L = mk(0.0f, 0.0f, 0.0f);
+  ShadeOut so;
+  so.fin_L = mk(0.0f, 0.0f, 0.0f);
 
   if (active) {
     slot = DENSE ? (depth0 ? i : q.active[0][i]) : q.kind[kq][off];
-    float4 ro, rd, th, ra;
-    ldg256_rw(pool.ray + 4u * (size_t)slot, ro, rd);
-    if (depth0) {
-      uint32_t x, y, smp;
-      camera_pixel_sample(rp, camera_first + slot, x, y, smp);
-      th = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(y * rp.width + x));
-      ra = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(smp << 9));
-    } else {
-      ldg256_rw(pool.col + 4u * (size_t)slot, th, ra);
-    }
-    const uint2 ht = make_uint2(__float_as_uint(ro.w), __float_as_uint(rd.w));
-    const uint32_t pixel = __float_as_uint(th.w);
-    const uint32_t df = __float_as_uint(ra.w);
-    const uint32_t sample = df >> 9;
-    uint32_t depth = df & 0xFFu;
-    const bool prev_delta = (df & kFlagPrevDelta) != 0u;
-    const Ray ray = make_ray(from4(ro), from4(rd));
-    const v3 wo = ray.d;
-    v3 T = from4(th), L = from4(ra);
-
-    Surface s;
-    s.miss = ht.y == kNone;
-    if (s.miss) {  // sky.rs:79-91: zero Hit + Emit(sky texture, 1.0)
-      s.h.t = 0.0f;
-      s.h.point = s.h.error = s.h.normal = mk(0.0f, 0.0f, 0.0f);
-      s.h.out = false;
-      s.kind = PTB_MAT_EMIT;
-      s.tex = sc.sky_tex;
-      s.mat = 0u;
-      s.param = 1.0f;
-    } else {
-      prim_hit(sc, ray, ht.y, s.h);  // same arithmetic as the traversal: reproduces t, adds point/normal/error/out
-      const uint32_t mi = __ldg(sc.slot_mat + (ht.y & kSlotMask)) & 0x00FFFFFFu;
-      const DevMaterial* m = sc.materials + mi;
-      s.mat = mi;
-      s.kind = __ldg(&m->kind);
-      s.tex = __ldg(&m->tex);
-      s.param = __ldg(&m->param);
-    }
-    const bool is_emit = s.kind == PTB_MAT_EMIT;
-    bool depart = false;
-    bool nan_check = true;
-
-    if (METHOD == PTB_METHOD_NAIVE) {
-      // integrators/mod.rs:29-72
-      if (is_emit) {
-        const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);        // emissive.rs:23-26
-        const v3 emission = s.param * texture_colour<FULL>(sc, s.tex, wo, point);
-        L = L + T * emission;  // depth 0: throughput is exactly (1,1,1)
-        finished = true;
-      } else {
-        depart = true;
-      }
-    } else {
-      // integrators/mis.rs:17-31 (first hit) and :52-80 (after each bounce)
-      if (depth == 0u) {
-        if (is_emit) {
-          const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);
-          L = L + s.param * texture_colour<FULL>(sc, s.tex, wo, point);
-          finished = true;
-          nan_check = false;  // mis.rs:29-31 returns before the NaN test
-        } else {
-          depth = 1u;
-          depart = true;
-        }
-      } else {
-        if (is_emit) {
-          // mis.rs:55: emission of the NEW material evaluated with the PREVIOUS hit record (quirk Q6); the
-          // previous hit's offset point is this ray's origin (lambertian.rs:37, reflect.rs:29)
-          const v3 le = s.param * texture_colour<FULL>(sc, s.tex, wo, ray.o);
-          if (!is_zero(le)) {
-            const bool sky_samplable = (sc.sky_rx | sc.sky_ry) != 0u;
-            const bool use_mis = s.miss ? sky_samplable : !prev_delta;  // mis.rs:57-60 (an emissive prim is in `lights`)
-            if (use_mis) {
-              const float divisor = (float)(sky_samplable ? sc.n_lights + 1u : sc.n_lights);  // acceleration/mod.rs:299-318
-              const float4 pv = pool.prev[slot];  // previous hit point | m_pdf of the BSDF sample that got us here
-              const float l_pdf = s.miss ? sky_pdf(sc, wo) / divisor
-                                         : light_pdf(sc, ht.y, from4(pv), wo, s.h.point, s.h.normal) / divisor;
-              const float w = power_heuristic(pv.w, l_pdf);
-              L = L + T * le * w;
-            } else {
-              L = L + T * le;
-            }
-          }
-          finished = true;  // mis.rs:69-71
-        } else {
-          bool survive = true;
-          if (depth > rp.rr_threshold) {  // mis.rs:73-80
-            const float p = cmax3(T.x, T.y, T.z);
-            const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_RR, 0u, rp.k0, rp.k1);
-            if (u32_to_unit(r.x) > p) survive = false;
-            else T = T / p;
-          }
-          depth += 1u;
-          if (survive && depth < rp.max_depth) depart = true;
-          else finished = true;
-        }
-      }
-    }
-
-    if (depart) {
-      float m_pdf = 0.0f;
-      // ---- next-event estimation (MIS only): integrators/mis.rs:36-43, 95-157
-      if (METHOD == PTB_METHOD_MIS) {
-        const uint32_t n_l = sc.n_lights;
-        const bool sky_s = (sc.sky_rx | sc.sky_ry) != 0u;
-        if (n_l != 0u || sky_s) {
-          const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_NEE, 0u, rp.k0, rp.k1);
-          bool do_sky;
-          float mult;
-          uint32_t li = 0;
-          if (n_l == 0u) { do_sky = true; mult = 1.0f; }
-          else if (!sky_s) { do_sky = false; mult = 1.0f / (float)n_l; li = rng_below(r.x, n_l); }
-          else { mult = 1.0f / (float)(n_l + 1u); li = rng_below(r.x, n_l + 1u); do_sky = li == n_l; }
-          const v3 so = s.h.point + 0.0001f * s.h.normal;  // mis.rs:106,124
-          v3 l_wi, le;
-          float l_pdf = 0.0f, tmax = __int_as_float(0x7f800000);
-          uint32_t exclude = kNone;
-          bool usable = false;
-          if (do_sky) {
-            const uint4 r2 = philox4x32_10(pixel, sample, (depth << 8) | RNG_NEE, 1u, rp.k0, rp.k1);
-            l_wi = sky_sample(sc, u32_to_unit(r.y), u32_to_unit(r.z), u32_to_unit(r.w), u32_to_unit(r2.x));
-            const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);
-            le = 1.0f * texture_colour<FULL>(sc, sc.sky_tex, l_wi, point);
-            l_pdf = sky_pdf(sc, l_wi) * mult;
-            usable = true;
-            shadow_is_sky = 1u;
-          } else {
-            const uint32_t lref = __ldg(sc.lights + li);
-            l_wi = light_sample_dir(sc, lref, s.h.point, u32_to_unit(r.y), u32_to_unit(r.z));
-            const Ray sray = make_ray_from_raw(so, l_wi);
-            HitRec si;
-            if (prim_hit(sc, sray, lref, si) && si.t > 0.0f) {  // acceleration/mod.rs:231-243
-              const float pdf = light_pdf(sc, lref, s.h.point, l_wi, si.point, si.normal);
-              if (pdf > 0.0f) {
-                const uint32_t lmi = __ldg(sc.slot_mat + (lref & kSlotMask)) & 0x00FFFFFFu;
-                const DevMaterial* lm = sc.materials + lmi;
-                const v3 lpoint = offset_ray(si.point, si.normal, si.error, true);
-                le = __ldg(&lm->param) * texture_colour<FULL>(sc, __ldg(&lm->tex), l_wi, lpoint);
-                l_pdf = pdf * mult;
-                tmax = si.t;
-                exclude = lref & kSlotMask;
-                usable = true;
-              }
-            }
-          }
-          if (usable) {
-            const float mp = mat_scattering_pdf<FULL>(s, wo, l_wi);
-            const float w = power_heuristic(l_pdf, mp);
-            const v3 contrib = T * mat_eval<FULL>(sc, s, wo, l_wi) * w * le / l_pdf;  // mis.rs:42
-            const v3 sd = l_wi / mag(l_wi);  // Ray::new normalises (ray.rs:14)
-            sh_o = make_float4(so.x, so.y, so.z, tmax);
-            sh_d = make_float4(sd.x, sd.y, sd.z, __uint_as_float(exclude));
-            sh_c = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(slot));
-            shadow = true;
-          }
-        }
-      }
-      // ---- BSDF sample -> next ray
-      const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_SCATTER, 0u, rp.k0, rp.k1);
-      v3 new_o, new_dir;
-      bool delta = false;
-      if (s.kind == PTB_MAT_LAMBERTIAN) {
-        new_dir = lambertian_sample_dir(s.h.normal, u32_to_unit(r.x), u32_to_unit(r.y));
-        new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
-      } else if (FULL && s.kind == PTB_MAT_TROWBRIDGE_REITZ) {
-        // trowbridge_reitz.rs:38-50: VNDF sample about the normal, draws (r, phi) = (sqrt(u1), tau * u2)
-        new_dir = tr_sample(s.param, -wo, s.h.normal, u32_to_unit(r.x), u32_to_unit(r.y));
-        new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
-      } else if (s.kind == PTB_MAT_REFLECT) {
-        // reflect.rs:26-36
-        const v3 unit = uniform_sphere_dir(u32_to_unit(r.x), u32_to_unit(r.y));
-        new_dir = reflected(-wo, s.h.normal) + s.param * unit;
-        new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
-        delta = true;
-      } else {  // PTB_MAT_REFRACT — refract.rs:27-50
-        float eta_fraction = 1.0f / s.param;
-        if (!s.h.out) eta_fraction = s.param;
-        const float cos_theta = fminf(dot(-wo, s.h.normal), 1.0f);
-        const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
-        const bool cannot_refract = eta_fraction * sin_theta > 1.0f;
-        float f0 = (1.0f - eta_fraction) / (1.0f + eta_fraction);
-        f0 = f0 * f0 * 1.0f;
-        const float fres = f0 + (1.0f - f0) * powf(1.0f - cos_theta, 5.0f);  // refract.rs:59-61
-        if (cannot_refract || fres > u32_to_unit(r.x)) {
-          new_dir = reflected(-wo, s.h.normal);  // Reflect{fuzz: 0}: the unit vector is multiplied by 0
-          new_o = offset_ray(s.h.point, s.h.normal, s.h.error, true);
-        } else {
-          const v3 perp = eta_fraction * (wo + cos_theta * s.h.normal);
-          const v3 para = -1.0f * sqrtf(fabsf(1.0f - mag_sq(perp))) * s.h.normal;
-          new_dir = perp + para;
-          new_o = offset_ray(s.h.point, s.h.normal, s.h.error, false);
-        }
-        delta = true;
-      }
-      const v3 nd = new_dir / mag(new_dir);  // Ray::new
-      const bool is_tr = FULL && s.kind == PTB_MAT_TROWBRIDGE_REITZ;
-      const v3 col = is_tr ? tr_eval(sc, s, wo, nd, 1) : texture_colour<FULL>(sc, s.tex, wo, s.h.point);
-      if (METHOD == PTB_METHOD_NAIVE) {
-        // integrators/mod.rs:57-70
-        if (s.kind == PTB_MAT_LAMBERTIAN) T = T * (col * s.param);
-        else T = T * col;  // Trowbridge-Reitz: col is already eval_over_scattering_pdf
-        bool survive = true;
-        if (depth > rp.rr_threshold) {
-          const float p = cmax3(T.x, T.y, T.z);
-          const uint4 r3 = philox4x32_10(pixel, sample, (depth << 8) | RNG_RR, 0u, rp.k0, rp.k1);
-          if (u32_to_unit(r3.x) > p) survive = false;
-          else T = T / p;
-        }
-        depth += 1u;
-        if (survive && depth < rp.max_depth) alive = true;
-        else finished = true;
-      } else {
-        // mis.rs:54-56: m_pdf and throughput use the previous hit only, so they are folded in at departure
-        if (s.kind == PTB_MAT_LAMBERTIAN) {
-          m_pdf = fmaxf(dot(nd, s.h.normal), 0.0f) / kPi;
-          T = T * (col * s.param);
-        } else if (is_tr) {
-          m_pdf = mat_scattering_pdf<FULL>(s, wo, nd);
-          T = T * col;
-        } else {
-          m_pdf = 0.0f;
-          T = T * (col / 0.0f);  // eval / scattering_pdf with the default pdf 0 (quirk Q4)
-        }
-        pool.prev[slot] = make_float4(s.h.point.x, s.h.point.y, s.h.point.z, m_pdf);
-        alive = true;
-      }
-      if (alive) {
-        stg256(pool.ray + 4u * (size_t)slot, make_float4(new_o.x, new_o.y, new_o.z, 0.0f),
-               make_float4(nd.x, nd.y, nd.z, __uint_as_float(kNone)));
-        stg256(pool.col + 4u * (size_t)slot, make_float4(T.x, T.y, T.z, th.w),
-               make_float4(L.x, L.y, L.z, __uint_as_float((sample << 9) | (delta ? kFlagPrevDelta : 0u) | depth)));
-        if (DENSE) q.bin[slot] = rp.dir_bins ? (uint8_t)direction_bin(nd) : (uint8_t)0;
-      }
-    }
-    if (finished) {
-      contributes = !(nan_check && (contains_nan(L) || !any_finite(L)));
-      fin_pixel = pixel;
-      fin_L = L;
-    }
+    shade_path<METHOD, FULL>(sc, pool, rp, slot, depth0, camera_first, so);
   }
-  finish_paths(accum, contributes, fin_pixel, fin_L);
+  finish_paths(accum, so.contributes, so.fin_pixel, so.fin_L);
 
   if (DENSE) {
     // ---- window mode: paths stay in their slot. A finished path is marked dead and leaves its window's live count
     // (lanes of a warp nearly always share the window: one atomic per warp); NEE rays go to the shadow queue.
-    if (finished) q.bin[slot] = (uint8_t)kBinDead;
+    if (so.alive) q.bin[slot] = (uint8_t)so.bin;
+    if (so.finished) q.bin[slot] = (uint8_t)kBinDead;
     const uint32_t window = slot / kWindow;
-    const uint32_t peers = __match_any_sync(0xffffffffu, finished ? window : 0xffffffffu);
-    if (finished && lane == (uint32_t)__ffs(peers) - 1u) atomicSub(&q.win_count[window], (uint32_t)__popc(peers));
+    const uint32_t peers = __match_any_sync(0xffffffffu, so.finished ? window : 0xffffffffu);
+    if (so.finished && lane == (uint32_t)__ffs(peers) - 1u) atomicSub(&q.win_count[window], (uint32_t)__popc(peers));
     if (METHOD == PTB_METHOD_MIS) {
-      const uint32_t m_sh = __ballot_sync(0xffffffffu, shadow), m_sky = __ballot_sync(0xffffffffu, shadow && shadow_is_sky);
+      const uint32_t m_sh = __ballot_sync(0xffffffffu, so.shadow), m_sky = __ballot_sync(0xffffffffu, so.shadow && so.shadow_is_sky);
       unsigned long long p2 = 0ull;
       if (lane == 0u && m_sh)
         p2 = atomicAdd(&wc->shadow_pair, ((unsigned long long)__popc(m_sky) << 32) | (unsigned long long)__popc(m_sh));
       p2 = __shfl_sync(0xffffffffu, p2, 0);
-      if (shadow) {
+      if (so.shadow) {
         float4* e = q.shadow + 3u * (size_t)((uint32_t)p2 + __popc(m_sh & ((1u << lane) - 1u)));
-        e[0] = sh_o;
-        e[1] = sh_d;
-        e[2] = sh_c;
+        e[0] = so.sh_o;
+        e[1] = so.sh_d;
+        e[2] = so.sh_c;
       }
     }
   } else {
   // ---- warp-aggregated queue pushes: lane 0 issues both returning atomics back to back (their round trips overlap)
   {
-    const uint32_t m_alive = __ballot_sync(0xffffffffu, alive), m_fin = __ballot_sync(0xffffffffu, finished);
-    const uint32_t m_sh = METHOD == PTB_METHOD_MIS ? __ballot_sync(0xffffffffu, shadow) : 0u;
-    const uint32_t m_sky = METHOD == PTB_METHOD_MIS ? __ballot_sync(0xffffffffu, shadow && shadow_is_sky) : 0u;
+    const uint32_t m_alive = __ballot_sync(0xffffffffu, so.alive), m_fin = __ballot_sync(0xffffffffu, so.finished);
+    const uint32_t m_sh = METHOD == PTB_METHOD_MIS ? __ballot_sync(0xffffffffu, so.shadow) : 0u;
+    const uint32_t m_sky = METHOD == PTB_METHOD_MIS ? __ballot_sync(0xffffffffu, so.shadow && so.shadow_is_sky) : 0u;
     unsigned long long p1 = 0ull, p2 = 0ull;
     if (lane == 0u) {
       if (m_alive | m_fin)
@@ -910,15 +929,15 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
     }
     p1 = __shfl_sync(0xffffffffu, p1, 0);
     const uint32_t below = (1u << lane) - 1u;
-    if (alive) q.active[nxt][(uint32_t)p1 + __popc(m_alive & below)] = slot;
-    if (finished) q.free_slots[(uint32_t)(p1 >> 32) + __popc(m_fin & below)] = slot;
+    if (so.alive) q.active[nxt][(uint32_t)p1 + __popc(m_alive & below)] = slot;
+    if (so.finished) q.free_slots[(uint32_t)(p1 >> 32) + __popc(m_fin & below)] = slot;
     if (METHOD == PTB_METHOD_MIS) {
       p2 = __shfl_sync(0xffffffffu, p2, 0);
-      if (shadow) {
+      if (so.shadow) {
         float4* e = q.shadow + 3u * (size_t)((uint32_t)p2 + __popc(m_sh & below));
-        e[0] = sh_o;
-        e[1] = sh_d;
-        e[2] = sh_c;
+        e[0] = so.sh_o;
+        e[1] = so.sh_d;
+        e[2] = so.sh_c;
       }
     }
   }
@@ -1126,6 +1145,99 @@ __global__ void __launch_bounds__(256, PTB_SHADOW_MIN_BLOCKS) k_shadow(DevScene 
   ShadowFetch fetch{q, make_float4(0.f, 0.f, 0.f, 0.f)};
   ShadowRetire retire{pool, fetch};
   persistent_trace<true, false>(sc, (uint32_t)wc->shadow_pair, &wc->shadow_head, fetch, retire, a, b, r);
+}
+
+// ------------------------------------------------------------------------------------------ fused tail
+// The last few thousand paths of a chunk (glass paths bouncing up to max_depth times) used to cost ~45 wavefront iterations
+// of five dependent, nearly empty launches each: 5 - 8 ms per chunk whatever its size. k_tail finishes them in ONE launch:
+// a lane owns a path and alternates closest hit -> shade (-> NEE any-hit) until the path ends — the paths are independent,
+// so nothing synchronises; the launch is latency bound (one traversal after the other per lane) and runs on a side stream
+// underneath the next chunk's wide iterations. Same functions, same records, same RNG counters as the wavefront: the image
+// does not depend on where the hand-over happens (tests: PTB_TAIL_PATHS=0 disables it).
+template <bool ANYHIT>
+PTB_DEV TravState trace_lane(const DevScene& sc, const Ray& ray, float tmax, uint32_t exclude, uint2* stack_local) {
+  const TravStack stack{stack_local, nullptr};
+  static_assert(kSharedStack == 0, "trace_lane walks the local-memory stack");
+  uint2 lq[kLeafQueue];
+  TravState st;
+  trav_init(st, sc.n_prims, tmax);
+  const SlabRay slab = make_slab_ray(ray);
+  uint32_t unused = 0;
+  while (!st.done()) {
+    if (!(st.cur & PTB_LEAF_BIT)) {
+#if PTB_WIDE_BVH
+      trav_node_step4<false>(sc, slab, st, stack, lq, unused);
+#else
+      trav_node_step<false>(sc, slab, ray, st, stack, lq, unused);
+#endif
+    } else {
+      trav_prim_step<ANYHIT, false>(sc, ray, st, stack, lq, exclude, unused);
+    }
+  }
+  return st;
+}
+template <int METHOD, bool FULL>
+__global__ void __launch_bounds__(128)
+k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum) {
+  const uint32_t n = wc->n_trace;  // live paths, listed in q.active[0] by k_win_fill
+  uint2 stack_local[kStackDepth];
+  unsigned long long c_bounce = 0, c_sky = 0, c_light = 0, c_ref = 0, c_paths = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = q.active[0][i];
+    for (;;) {
+      // ---- closest hit (k_trace): the hit goes into the ray record, where shade_path reads it
+      float4 o4, d4;
+      ldg256_rw(pool.ray + 4u * (size_t)slot, o4, d4);
+      const Ray ray = make_ray(from4(o4), from4(d4));
+      const TraceResult tr = trav_result(trace_lane<false>(sc, ray, __int_as_float(0x7f800000), kNone, stack_local));
+      stg256(pool.ray + 4u * (size_t)slot, make_float4(ray.o.x, ray.o.y, ray.o.z, tr.t),
+             make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(tr.ref)));
+      ++c_bounce;
+      // ---- shade (k_shade)
+      ShadeOut so;
+      so.fin_L = mk(0.0f, 0.0f, 0.0f);
+      shade_path<METHOD, FULL>(sc, pool, rp, slot, false, kNoCamera, so);
+      if (METHOD == PTB_METHOD_NAIVE) ++c_ref;            // Q7: naive counts every check_hit ...
+      else if (so.alive) ++c_ref;                         // ... MIS every bounce iteration that continues
+      // ---- NEE visibility (k_shadow): unoccluded contributions join the path's radiance
+      if (METHOD == PTB_METHOD_MIS && so.shadow) {
+        if (so.shadow_is_sky) ++c_sky; else ++c_light;
+        const Ray sray = make_ray(from4(so.sh_o), from4(so.sh_d));
+        const TravState ss = trace_lane<true>(sc, sray, so.sh_o.w, __float_as_uint(so.sh_d.w), stack_local);
+        if (ss.best_ref == kNone) {
+          float4 ra = pool.col[4u * (size_t)slot + 1u];
+          ra.x += so.sh_c.x; ra.y += so.sh_c.y; ra.z += so.sh_c.z;
+          pool.col[4u * (size_t)slot + 1u] = ra;
+        }
+      }
+      if (so.finished) {
+        ++c_paths;
+        if (so.contributes) {
+          atomicAdd(accum + 3u * (size_t)so.fin_pixel + 0, so.fin_L.x);
+          atomicAdd(accum + 3u * (size_t)so.fin_pixel + 1, so.fin_L.y);
+          atomicAdd(accum + 3u * (size_t)so.fin_pixel + 2, so.fin_L.z);
+        }
+        q.bin[slot] = (uint8_t)kBinDead;
+        break;
+      }
+    }
+  }
+  // statistics: one set of atomics per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c_bounce += __shfl_xor_sync(0xffffffffu, c_bounce, o);
+    c_sky += __shfl_xor_sync(0xffffffffu, c_sky, o);
+    c_light += __shfl_xor_sync(0xffffffffu, c_light, o);
+    c_ref += __shfl_xor_sync(0xffffffffu, c_ref, o);
+    c_paths += __shfl_xor_sync(0xffffffffu, c_paths, o);
+  }
+  if ((threadIdx.x & 31u) == 0u && c_bounce) {
+    atomicAdd(&wc->rays_bounce, c_bounce);
+    if (c_sky) atomicAdd(&wc->rays_shadow_sky, c_sky);
+    if (c_light) atomicAdd(&wc->rays_shadow_light, c_light);
+    atomicAdd(&wc->rays_reference, c_ref);
+    atomicAdd(&wc->paths, c_paths);
+  }
 }
 
 // ------------------------------------------------------------------------------------------ closest-hit API kernel
@@ -1365,58 +1477,109 @@ int32_t launch_closest_hit(Ctx* c, const void* d_rays, size_t n, void* d_hits) {
 
 // bytes of device state per path in flight
 static unsigned long long bytes_per_path(bool mis, bool windows) {
-  // 64-byte path block + queues (window mode: the live-slot queue; queue mode: 2 active, free, kNumKinds shade queues)
-  // + MIS: previous-hit record, 48-byte shadow entry
+  // 64-byte path block + queues (window mode: the live-slot queue + one bin byte; queue mode: 2 active, free, kNumKinds
+  // shade queues) + MIS: previous-hit record, 48-byte shadow entry
   return 64ull + (windows ? 4ull + 1ull : 4ull * (3 + kNumKinds)) + (mis ? 16ull + 48ull : 0ull);
 }
 
 void free_render_state(Ctx* c) {
-  c->d_pool_mem.release();
-  c->d_prev.release();
-  c->d_queues.release();
-  c->d_shadow.release();
-  c->d_windows.release();
+  for (DevBuf* b : {&c->d_pool_mem, &c->d_prev, &c->d_queues, &c->d_shadow, &c->d_windows, &c->d_pool_mem2, &c->d_prev2,
+                    &c->d_queues2, &c->d_shadow2, &c->d_windows2})
+    b->release();
   c->pool = PathPool();
 }
 
-// Paths in flight. The wavefront is fastest when EVERY camera path of the call is resident: iteration k then traces bounce
-// k of all paths (camera rays, the coherent half of the work, run together), there are ~55 launches per render instead of
-// ~110 and only one tail. Measured on B200, C3 at 256 spp per call, queue mode (profiles/r1_sweeps.md): 16 Mi paths 2264
-// Mrays/s, 64 Mi 2461, 128 Mi 2612, 256 Mi 2760, 512 Mi 2839. Default: up to 512 Mi paths, never more than half of the
-// device memory that was free at the context's first large render (68 B per path in window mode, 132 B with MIS).
-// PTB_POOL_PATHS overrides.
-static uint32_t pool_capacity_for(Ctx* c, unsigned long long total, bool mis, bool windows) {
-  unsigned long long cap = 1ull << 29;
-  bool forced = false;
+// Paths in flight. Round 1 kept EVERY camera path of a call resident (36 GB for 1080p x 256 spp) to amortise the ~45
+// nearly empty iterations at the end of a wavefront; the fused tail kernel on a side stream removes that cost instead, so
+// the path state is bounded: two chunk slots of together PTB_POOL_BYTES (default 8 GiB), never more than half of the
+// device memory that was free at the context's first large render. A call is cut into equal chunks of at most one slot —
+// and into at least four once it has more than 8 Mi paths, so that only the LAST chunk's tail is exposed.
+// PTB_POOL_PATHS sets the slot size directly (tests; the queue mode's pool).
+struct PoolPlan {
+  uint32_t slot_paths;  // capacity of one slot (multiple of kWindow)
+  uint32_t n_chunks;
+  uint32_t chunk_paths; // paths per chunk (the last one may be shorter)
+};
+static PoolPlan plan_pool(Ctx* c, unsigned long long total, bool mis, bool windows) {
+  unsigned long long budget = 8ull << 30;
+  if (const char* e = getenv("PTB_POOL_BYTES")) { unsigned long long v = strtoull(e, nullptr, 10); if (v >= (64ull << 20)) budget = v; }
+  const unsigned long long per_path = bytes_per_path(mis, windows);
+  unsigned long long cap = 0;
   if (const char* e = getenv("PTB_POOL_PATHS")) {
     unsigned long long v = strtoull(e, nullptr, 10);
-    if (v >= 1024 && v <= (1ull << 29)) { cap = v; forced = true; }
+    if (v >= 1024 && v <= (1ull << 29)) cap = v;
   }
-  if (!forced && total > (1ull << 24)) {
-    // asked once per context (cudaMemGetInfo costs milliseconds once tens of GB are allocated)
-    if (c->pool_budget_bytes == 0) {
-      size_t free_b = 0, total_b = 0;
-      c->pool_budget_bytes = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? free_b / 2 + 1 : ~(size_t)0;
+  if (!cap) {
+    if (total * per_path > (1ull << 30)) {
+      // asked once per context (cudaMemGetInfo costs milliseconds once tens of GB are allocated)
+      if (c->pool_budget_bytes == 0) {
+        size_t free_b = 0, total_b = 0;
+        c->pool_budget_bytes = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? free_b / 2 + 1 : ~(size_t)0;
+      }
+      if (budget > c->pool_budget_bytes) budget = c->pool_budget_bytes;
     }
-    const unsigned long long per_path = bytes_per_path(mis, windows);
-    while (cap > (1ull << 24) && cap * per_path > c->pool_budget_bytes) cap >>= 1;
+    cap = budget / (windows ? 2ull : 1ull) / per_path;
+    if (cap > (1ull << 29)) cap = 1ull << 29;
+    if (cap < (1ull << 20)) cap = 1ull << 20;
   }
-  if (total < cap) cap = total < 1024 ? 1024 : total;
-  const unsigned long long gran = kWindow;  // whole windows
-  return (uint32_t)((cap + gran - 1ull) / gran * gran);
+  const unsigned long long gran = kWindow;
+  cap = cap / gran * gran;
+  if (cap < gran) cap = gran;
+  unsigned long long n_chunks = (total + cap - 1ull) / cap;
+  if (windows && n_chunks < 4ull && total > (1ull << 23)) n_chunks = 4ull;  // overlap the tails of all chunks but the last
+  unsigned long long chunk = (total + n_chunks - 1ull) / n_chunks;
+  chunk = (chunk + gran - 1ull) / gran * gran;
+  if (chunk > cap) chunk = cap;
+  PoolPlan p;
+  p.chunk_paths = (uint32_t)chunk;
+  p.n_chunks = (uint32_t)((total + chunk - 1ull) / chunk);
+  p.slot_paths = (uint32_t)(chunk < 1024ull ? ((1024ull + gran - 1ull) / gran * gran) : chunk);
+  return p;
 }
 
 struct RenderSetup {
   RenderParams rp;
-  Queues q;
+  Queues q;            // slot 0 (queue mode: the only one)
+  Queues q2;           // slot 1 (window mode, calls of more than one chunk)
+  PathPool pool2;
   WaveCounters* wc;
+  WaveCounters* wc2;
   float* accum;
-  uint32_t P;
+  uint32_t P;          // slot capacity in paths
+  uint32_t chunk_paths, n_chunks;
   bool mis, full, count, prof;
 };
 
 static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderSetup& rs, ptb_progress_fn progress, void* user);
 static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const RenderSetup& rs, ptb_progress_fn progress, void* user);
+
+// carve one slot's queue / window arrays out of its buffers
+static void bind_slot(Queues& q, PathPool& pool, uint32_t P, bool windows, DevBuf& pool_mem, DevBuf& prev, DevBuf& queues,
+                      DevBuf& shadow, DevBuf& win) {
+  pool.capacity = P;
+  pool.ray = pool_mem.as<float4>();
+  pool.col = pool.ray + 2;
+  pool.prev = prev.as<float4>();
+  uint32_t* b = queues.as<uint32_t>();
+  q.active[0] = b; b += P;
+  if (windows) b = queues.as<uint32_t>();  // window mode uses active[0] only
+  q.active[1] = b; b += windows ? 0 : P;
+  q.free_slots = b; b += windows ? 0 : P;
+  for (int k = 0; k < kNumKinds; ++k) { q.kind[k] = b; b += windows ? 0 : P; }
+  q.shadow = shadow.as<float4>();
+  q.n_windows = P / kWindow;  // P is a multiple of kWindow
+  const size_t n_seg = (q.n_windows + kSegWindows - 1) / kSegWindows;
+  q.win_count = q.win_prefix = q.seg_total = nullptr;
+  q.bin = nullptr;
+  if (windows) {
+    const size_t words = ((size_t)q.n_windows * 2 + n_seg + 3) & ~(size_t)3;  // keeps the byte array 16-byte aligned
+    uint32_t* w = win.as<uint32_t>();
+    q.win_count = w;
+    q.win_prefix = w + q.n_windows;
+    q.seg_total = w + 2 * (size_t)q.n_windows;
+    q.bin = reinterpret_cast<uint8_t*>(w + words);  // k_win_fill reads a window's 256 bytes as 32 x uint2
+  }
+}
 
 int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progress, void* user) {
   const uint32_t rows = o.row_count ? o.row_count : o.height - o.row_begin;  // validated by ptb_render
@@ -1425,67 +1588,58 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   if (total == 0) return PTB_OK;
   RenderSetup rs;
   rs.mis = o.method == PTB_METHOD_MIS;
-  // Window mode (default) needs chunks long enough to amortise their ~50-launch tail: the whole call in one chunk, or
-  // chunks of at least 32 Mi paths. PTB_WAVEFRONT=queue forces the regenerating queue mode, =window the window mode.
+  // Window mode (default) needs chunks long enough to keep its wide iterations wide: at least 32 Mi paths per slot, or the
+  // whole call in one chunk. PTB_WAVEFRONT=queue forces the regenerating queue mode, =window the window mode.
   bool windows = true, forced_windows = false;
   if (const char* e = getenv("PTB_WAVEFRONT")) {
     windows = strcmp(e, "queue") != 0;
     forced_windows = strcmp(e, "window") == 0;
   }
-  uint32_t P = pool_capacity_for(c, total, rs.mis, windows);
-  if (windows && !forced_windows && total > P && P < (1u << 25)) {
+  PoolPlan plan = plan_pool(c, total, rs.mis, windows);
+  if (windows && !forced_windows && plan.n_chunks > 1 && plan.slot_paths < (1u << 22)) {
     windows = false;
-    P = pool_capacity_for(c, total, rs.mis, false);
+    plan = plan_pool(c, total, rs.mis, false);
   }
   // ---- device state (grow-only across calls; the MIS-only arrays are allocated by the first MIS call)
   // one 64-byte block per path: ray record then colour record (a DRAM access atom; two scattered 32-byte sectors per
-  // path cost generate/shade ~1 TB/s of effective write bandwidth). If the device cannot provide the pool (another
-  // process holds the memory), the pool is halved and the call runs in more chunks.
+  // path cost generate/shade ~1 TB/s of effective write bandwidth). If the device cannot provide the slots (another
+  // process holds the memory), they are halved and the call runs in more chunks.
+  uint32_t P = plan.slot_paths;
   for (;;) {
+    const bool two = windows && plan.n_chunks > 1;
     const size_t n_seg = ((size_t)P / kWindow + kSegWindows - 1) / kSegWindows;
     const size_t win_bytes = windows ? ((((size_t)P / kWindow * 2 + n_seg + 3) & ~(size_t)3) * 4 + (size_t)P) : 0;
-    cudaError_t e = c->d_pool_mem.reserve((size_t)P * 64);
-    if (e == cudaSuccess) e = c->d_queues.reserve((size_t)P * 4 * (windows ? 1 : 3 + kNumKinds));
-    if (e == cudaSuccess && rs.mis) e = c->d_prev.reserve((size_t)P * 16);
-    if (e == cudaSuccess && rs.mis) e = c->d_shadow.reserve((size_t)P * 48);
-    if (e == cudaSuccess && windows) e = c->d_windows.reserve(win_bytes);
+    cudaError_t e = cudaSuccess;
+    DevBuf* sets[2][5] = {{&c->d_pool_mem, &c->d_queues, &c->d_prev, &c->d_shadow, &c->d_windows},
+                          {&c->d_pool_mem2, &c->d_queues2, &c->d_prev2, &c->d_shadow2, &c->d_windows2}};
+    for (int sl = 0; sl < (two ? 2 : 1) && e == cudaSuccess; ++sl) {
+      e = sets[sl][0]->reserve((size_t)P * 64);
+      if (e == cudaSuccess) e = sets[sl][1]->reserve((size_t)P * 4 * (windows ? 1 : 3 + kNumKinds));
+      if (e == cudaSuccess && rs.mis) e = sets[sl][2]->reserve((size_t)P * 16);
+      if (e == cudaSuccess && rs.mis) e = sets[sl][3]->reserve((size_t)P * 48);
+      if (e == cudaSuccess && windows) e = sets[sl][4]->reserve(win_bytes);
+    }
     if (e == cudaSuccess) break;
     if (e != cudaErrorMemoryAllocation || P <= (1u << 20)) return check_cuda(c, e, "path pool allocation");
     cudaGetLastError();  // clear the sticky allocation error
     free_render_state(c);
     P = (P / 2 + kWindow - 1) / kWindow * kWindow;
-    if (windows && P < (1u << 25) && !forced_windows) windows = false;  // too many chunks for window mode
+    plan.slot_paths = plan.chunk_paths = P;
+    plan.n_chunks = (uint32_t)((total + P - 1ull) / P);
+    if (windows && P < (1u << 22) && !forced_windows) windows = false;  // too many chunks for window mode
   }
   rs.P = P;
-  c->pool.capacity = P;
-  c->pool.ray = c->d_pool_mem.as<float4>();
-  c->pool.col = c->pool.ray + 2;
-  c->pool.prev = c->d_prev.as<float4>();
+  rs.chunk_paths = plan.chunk_paths;
+  rs.n_chunks = plan.n_chunks;
   PTB_CUDA_TRY(c, c->d_counters.reserve(sizeof(WaveCounters) + 64));
-  Queues& q = rs.q;
-  {
-    uint32_t* b = c->d_queues.as<uint32_t>();
-    q.active[0] = b; b += P;
-    if (windows) b = c->d_queues.as<uint32_t>();  // window mode uses active[0] only
-    q.active[1] = b; b += windows ? 0 : P;
-    q.free_slots = b; b += windows ? 0 : P;
-    for (int k = 0; k < kNumKinds; ++k) { q.kind[k] = b; b += windows ? 0 : P; }
-    q.shadow = c->d_shadow.as<float4>();
-    q.n_windows = P / kWindow;  // P is a multiple of kWindow
-    const size_t n_seg = (q.n_windows + kSegWindows - 1) / kSegWindows;
-    q.win_count = q.win_prefix = q.seg_total = nullptr;
-    q.bin = nullptr;
-    if (windows) {
-      const size_t words = ((size_t)q.n_windows * 2 + n_seg + 3) & ~(size_t)3;  // keeps the byte array 16-byte aligned
-      uint32_t* w = c->d_windows.as<uint32_t>();
-      q.win_count = w;
-      q.win_prefix = w + q.n_windows;
-      q.seg_total = w + 2 * (size_t)q.n_windows;
-      q.bin = reinterpret_cast<uint8_t*>(w + words);  // k_win_fill reads a window's 256 bytes as 32 x uint2
-    }
-  }
+  PTB_CUDA_TRY(c, c->d_counters2.reserve(sizeof(WaveCounters) + 64));
+  bind_slot(rs.q, c->pool, P, windows, c->d_pool_mem, c->d_prev, c->d_queues, c->d_shadow, c->d_windows);
+  rs.q2 = rs.q;
+  rs.pool2 = c->pool;
+  if (windows && plan.n_chunks > 1) bind_slot(rs.q2, rs.pool2, P, windows, c->d_pool_mem2, c->d_prev2, c->d_queues2, c->d_shadow2, c->d_windows2);
   rs.wc = c->d_counters.as<WaveCounters>();
-  if (!c->h_counters) PTB_CUDA_TRY(c, cudaMallocHost(&c->h_counters, 2 * sizeof(WaveCounters)));
+  rs.wc2 = c->d_counters2.as<WaveCounters>();
+  if (!c->h_counters) PTB_CUDA_TRY(c, cudaMallocHost(&c->h_counters, 4 * sizeof(WaveCounters)));
 
   RenderParams& rp = rs.rp;
   rp.width = o.width; rp.height = o.height; rp.npix = npix;
@@ -1523,9 +1677,12 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   rs.full = c->scene_needs_full_shade;
   rs.count = c->opt_count_traversal;
   rs.prof = c->opt_time_kernels;
-  if (rs.prof)
+  if (rs.prof) {
     for (cudaEvent_t& e : c->ev_prof)
       if (!e) PTB_CUDA_TRY(c, cudaEventCreate(&e));
+    for (cudaEvent_t& e : c->ev_tail_prof)
+      if (!e) PTB_CUDA_TRY(c, cudaEventCreate(&e));
+  }
   return windows ? render_window_mode(c, o, rs, progress, user) : render_queue_mode(c, o, rs, progress, user);
 }
 
@@ -1564,16 +1721,29 @@ static void fold_counters(Ctx* c, const WaveCounters& h, uint64_t iterations) {
   c->stats.paths += h.paths;
   c->stats.wavefront_iterations += iterations;
 }
+struct SlotRefs {  // the device state one chunk runs in
+  const PathPool& pool;
+  const Queues& q;
+  WaveCounters* wc;
+};
 template <bool DENSE>
-static void launch_shade(const RenderSetup& rs, Ctx* c, uint32_t grid, int threads, cudaStream_t st,
+static void launch_shade(const RenderSetup& rs, Ctx* c, const SlotRefs& sl, uint32_t grid, int threads, cudaStream_t st,
                          unsigned long long camera_first = kNoCamera) {
-  const Queues& q = rs.q;
   if (rs.mis) {
-    if (rs.full) k_shade<PTB_METHOD_MIS, true, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum, camera_first);
-    else k_shade<PTB_METHOD_MIS, false, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum, camera_first);
+    if (rs.full) k_shade<PTB_METHOD_MIS, true, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first);
+    else k_shade<PTB_METHOD_MIS, false, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first);
   } else {
-    if (rs.full) k_shade<PTB_METHOD_NAIVE, true, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum, camera_first);
-    else k_shade<PTB_METHOD_NAIVE, false, DENSE><<<grid, threads, 0, st>>>(c->dev, c->pool, q, rs.wc, rs.rp, rs.accum, camera_first);
+    if (rs.full) k_shade<PTB_METHOD_NAIVE, true, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first);
+    else k_shade<PTB_METHOD_NAIVE, false, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first);
+  }
+}
+static void launch_tail(const RenderSetup& rs, Ctx* c, const SlotRefs& sl, uint32_t grid, cudaStream_t st) {
+  if (rs.mis) {
+    if (rs.full) k_tail<PTB_METHOD_MIS, true><<<grid, 128, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum);
+    else k_tail<PTB_METHOD_MIS, false><<<grid, 128, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum);
+  } else {
+    if (rs.full) k_tail<PTB_METHOD_NAIVE, true><<<grid, 128, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum);
+    else k_tail<PTB_METHOD_NAIVE, false><<<grid, 128, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum);
   }
 }
 template <bool DENSE>
@@ -1582,21 +1752,23 @@ static const void* shade_fn(const RenderSetup& rs) {
                 : (rs.full ? (const void*)k_shade<PTB_METHOD_NAIVE, true, DENSE> : (const void*)k_shade<PTB_METHOD_NAIVE, false, DENSE>);
 }
 
-// ---- window mode: chunk by chunk, every path of a chunk resident, one bounce of all of them per iteration
+// ---- window mode: chunk by chunk, every path of a chunk resident, one bounce of all of them per iteration.
+// Chunk k runs its wide iterations on the main stream in slot k & 1; once fewer than `tail_paths` of its paths are alive
+// they are handed to ONE k_tail launch on the side stream, and chunk k+1 starts in the other slot right away.
 static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const RenderSetup& rs, ptb_progress_fn progress, void* user) {
   cudaStream_t st = c->stream;
-  const Queues& q = rs.q;
-  WaveCounters* wc = rs.wc;
-  const uint32_t npix = rs.rp.npix, P = rs.P;
+  const uint32_t npix = rs.rp.npix, P = rs.chunk_paths;
   const unsigned long long total = (unsigned long long)npix * o.samples_per_pixel;
   const bool mis = rs.mis, prof = rs.prof, count = rs.count;
   const int T = 256;
-  const uint32_t n_seg = (q.n_windows + kSegWindows - 1) / kSegWindows;
+  const SlotRefs slots[2] = {{c->pool, rs.q, rs.wc}, {rs.pool2, rs.q2, rs.wc2}};
+  const uint32_t n_windows = rs.q.n_windows;
+  const uint32_t n_seg = (n_windows + kSegWindows - 1) / kSegWindows;
   auto capped = [&](const void* k, uint32_t items_per_block, uint32_t items) {
     const uint32_t g = (uint32_t)persistent_grid(c, k, T), need = (items + items_per_block - 1) / items_per_block;
     return g < need ? g : (need ? need : 1u);
   };
-  const uint32_t grid_fill = capped((const void*)k_win_fill, kFillGroup, q.n_windows);
+  const uint32_t grid_fill = capped((const void*)k_win_fill, kFillGroup, n_windows);
   // k_shade is register-heavy (84 naive / 116 MIS): 128-thread blocks let more of them share an SM's register file
   // (window mode, C3: 256 threads 3438 Mrays/s, 128 -> 3500, 64 -> 3499)
   int TS = 128;
@@ -1608,49 +1780,95 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
   int cam_fetch = c->dev.trace_fetch_threshold < 4 ? c->dev.trace_fetch_threshold : 4;
   if (const char* e = getenv("PTB_TRACE_FETCH_CAMERA")) { int v = atoi(e); if (v >= 1 && v <= 32) cam_fetch = v; }
+  // hand-over point: live paths of a chunk at or below which the fused tail takes it (0: never; the traversal statistics
+  // build counts in k_trace only, so it keeps the wavefront to the end)
+  uint32_t tail_paths = 65536u;
+  if (const char* e = getenv("PTB_TAIL_PATHS")) { long v = atol(e); if (v >= 0 && v <= (1l << 24)) tail_paths = (uint32_t)v; }
+  if (count) tail_paths = 0u;
+  if (tail_paths) {
+    if (!c->s_tail) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = greatest priority: the tail's few blocks go first when slots free up
+      PTB_CUDA_TRY(c, cudaStreamCreateWithPriority(&c->s_tail, cudaStreamNonBlocking, hi));
+    }
+    for (int k = 0; k < 2; ++k) {
+      if (!c->ev_head_done[k]) PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_head_done[k], cudaEventDisableTiming));
+      if (!c->ev_tail_done[k]) PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_tail_done[k], cudaEventDisableTiming));
+    }
+  }
+  const uint32_t grid_tail = (tail_paths + 127u) / 128u;
+  bool tail_pending[2] = {false, false};  // a k_tail is (or may still be) running in that slot
+  auto collect_tail_prof = [&](int sl) {
+    float ms = 0.f;
+    if (prof && cudaEventElapsedTime(&ms, c->ev_tail_prof[2 * sl], c->ev_tail_prof[2 * sl + 1]) == cudaSuccess) c->stats.ms_tail += ms;
+  };
 
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
-  k_init_pool<<<1, 32, 0, st>>>(q.active[0], 0u, wc, total);  // counters only
-  c->stats.kernel_launches += 1;
+  k_init_pool<<<1, 32, 0, st>>>(rs.q.active[0], 0u, rs.wc, total);   // counters only
+  k_init_pool<<<1, 32, 0, st>>>(rs.q2.active[0], 0u, rs.wc2, total);
+  c->stats.kernel_launches += 2;
   int32_t rc = PTB_OK;
   uint64_t iter = 0;
   cudaEvent_t ev[2] = {c->ev_iter, c->ev_b};
-  for (unsigned long long first = 0; first < total && rc == PTB_OK; first += P) {
+  uint32_t chunk_index = 0;
+  for (unsigned long long first = 0; first < total && rc == PTB_OK; first += P, ++chunk_index) {
+    const int sl = rs.n_chunks > 1 ? (int)(chunk_index & 1u) : 0;
+    const SlotRefs& S = slots[sl];
+    const Queues& q = S.q;
+    WaveCounters* wc = S.wc;
     const uint32_t n_paths = (uint32_t)(total - first < P ? total - first : P);
+    if (tail_pending[sl]) {  // the slot's previous chunk (two chunks ago) must have left it
+      PTB_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_tail_done[sl], 0));
+      if (prof) { PTB_CUDA_TRY(c, cudaEventSynchronize(c->ev_tail_prof[2 * sl + 1])); collect_tail_prof(sl); }
+      tail_pending[sl] = false;
+    }
     PTB_CUDA_TRY(c, cudaMemsetAsync(q.win_count, 0, (size_t)q.n_windows * 4, st));
     if (n_paths % kWindow)  // slots of the last window that hold no path
       PTB_CUDA_TRY(c, cudaMemsetAsync(q.bin + n_paths, (int)kBinDead, kWindow - n_paths % kWindow, st));
     PTB_PROF(0, 0);
     k_win_init<<<(q.n_windows + T - 1) / T, T, 0, st>>>(q, n_paths);
     c->stats.kernel_launches += 1;
-    bool done = false;
+    bool done = false, tail_next = false;
     for (uint64_t depth = 0; !done; ++depth, ++iter) {
       if (depth) PTB_PROF(0, 0);
       k_win_scan<<<n_seg, 1024, 0, st>>>(q);
       k_win_prepare<<<1, 32, 0, st>>>(wc, q, n_seg, o.method, depth == 0 ? 0u : (depth == 1 ? 1u : 2u));
       if (depth) k_win_fill<<<grid_fill, T, 0, st>>>(q, wc);  // depth 0: work item i is slot i, no queue
       PTB_PROF(0, 1);
+      if (tail_next) {
+        // the live list is built; everything left of this chunk is ONE launch on the side stream
+        c->stats.kernel_launches += 4;
+        PTB_CUDA_TRY(c, cudaEventRecord(c->ev_head_done[sl], st));
+        PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_tail, c->ev_head_done[sl], 0));
+        if (prof) PTB_CUDA_TRY(c, cudaEventRecord(c->ev_tail_prof[2 * sl], c->s_tail));
+        launch_tail(rs, c, S, grid_tail, c->s_tail);
+        if (prof) PTB_CUDA_TRY(c, cudaEventRecord(c->ev_tail_prof[2 * sl + 1], c->s_tail));
+        PTB_CUDA_TRY(c, cudaEventRecord(c->ev_tail_done[sl], c->s_tail));
+        tail_pending[sl] = true;
+        ++iter;
+        break;
+      }
       PTB_PROF(1, 0);
       if (depth == 0) {
         // camera rays of a warp finish together: refilling later (fewer, fuller service passes) suits them
         // (C3, camera rays only: threshold 8 -> 8105 Mrays/s, 4 -> 8311; bounce rays prefer 8, profiles/r1_sweeps.md)
         DevScene cam = c->dev;
         cam.trace_fetch_threshold = cam_fetch;
-        if (count) k_trace<true, true, true><<<grid_trace_cam, T, 0, st>>>(cam, c->pool, q, wc, rs.rp, first);
-        else k_trace<false, true, true><<<grid_trace_cam, T, 0, st>>>(cam, c->pool, q, wc, rs.rp, first);
+        if (count) k_trace<true, true, true><<<grid_trace_cam, T, 0, st>>>(cam, S.pool, q, wc, rs.rp, first);
+        else k_trace<false, true, true><<<grid_trace_cam, T, 0, st>>>(cam, S.pool, q, wc, rs.rp, first);
       } else {
-        if (count) k_trace<true, true, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc, rs.rp, 0ull);
-        else k_trace<false, true, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc, rs.rp, 0ull);
+        if (count) k_trace<true, true, false><<<grid_trace, T, 0, st>>>(c->dev, S.pool, q, wc, rs.rp, 0ull);
+        else k_trace<false, true, false><<<grid_trace, T, 0, st>>>(c->dev, S.pool, q, wc, rs.rp, 0ull);
       }
       PTB_PROF(1, 1);
       PTB_PROF(2, 0);
-      launch_shade<true>(rs, c, grid_shade, TS, st, depth == 0 ? first : kNoCamera);
+      launch_shade<true>(rs, c, S, grid_shade, TS, st, depth == 0 ? first : kNoCamera);
       PTB_PROF(2, 1);
       c->stats.kernel_launches += depth ? 5 : 4;
       c->stats.trace_launches += 1;
       if (mis) {
         PTB_PROF(3, 0);
-        k_shadow<<<grid_shadow, T, 0, st>>>(c->dev, c->pool, q, wc);
+        k_shadow<<<grid_shadow, T, 0, st>>>(c->dev, S.pool, q, wc);
         PTB_PROF(3, 1);
         c->stats.kernel_launches += 1;
       }
@@ -1662,30 +1880,40 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
         const int ps = slot ^ 1;
         PTB_CUDA_TRY(c, cudaEventSynchronize(ev[ps]));
         if (prof) prof_collect(c, ps, mis);
-        if (c->h_counters[ps].n_trace == 0u) done = true;  // iteration depth-1 had nothing left to trace
+        const uint32_t traced_before = c->h_counters[ps].n_trace;  // rays of iteration depth-1: an upper bound of what is alive now
+        if (traced_before == 0u) done = true;
+        else if (tail_paths && traced_before <= tail_paths) tail_next = true;
       }
       if (depth > 4096) return set_error(c, PTB_ERR_INVALID, "wavefront did not terminate");
     }
-    // the iteration launched last is empty as well (its k_win_prepare folded the statistics of the last real one)
-    PTB_CUDA_TRY(c, cudaEventSynchronize(ev[(int)((iter - 1) & 1u)]));
-    if (prof) prof_collect(c, (int)((iter - 1) & 1u), mis);
-    if (progress && first + n_paths < total) {
-      const WaveCounters& h = c->h_counters[(int)((iter - 1) & 1u)];
-      if (progress(user, (first + n_paths) / npix, h.rays_reference)) rc = PTB_ERR_ABORTED;
+    {
+      // the last iteration with a mirror: without a hand-over the empty one launched last (its k_win_prepare folded the
+      // statistics of the last real one), else the one before the tail iteration
+      const int last = (int)((iter - (tail_next ? 2u : 1u)) & 1u);
+      PTB_CUDA_TRY(c, cudaEventSynchronize(ev[last]));
+      if (prof) prof_collect(c, last, mis);
+      if (progress && first + n_paths < total && progress(user, (first + n_paths) / npix, c->h_counters[last].rays_reference))
+        rc = PTB_ERR_ABORTED;
     }
   }
-  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters, wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+  for (int sl = 0; sl < 2; ++sl)
+    if (tail_pending[sl]) PTB_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_tail_done[sl], 0));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + 2, rs.wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + 3, rs.wc2, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
   PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
   PTB_CUDA_TRY(c, cudaGetLastError());
+  for (int sl = 0; sl < 2; ++sl)
+    if (tail_pending[sl]) collect_tail_prof(sl);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
-  const WaveCounters& h = c->h_counters[0];
-  fold_counters(c, h, iter);
+  const uint64_t ref_before = c->stats.rays_reference;
+  fold_counters(c, c->h_counters[2], iter);
+  fold_counters(c, c->h_counters[3], 0);
   c->stats.render_ms = ms;
   if (rc == PTB_OK) {
     c->accum_samples += o.samples_per_pixel;
-    if (progress) progress(user, o.samples_per_pixel, h.rays_reference);
+    if (progress) progress(user, o.samples_per_pixel, c->stats.rays_reference - ref_before);
   }
   return rc;
 }
@@ -1732,7 +1960,7 @@ static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderS
     else k_trace<false, false, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc, rp, 0ull);
     PTB_PROF(1, 1);
     PTB_PROF(2, 0);
-    launch_shade<false>(rs, c, grid_shade, TS, st);
+    launch_shade<false>(rs, c, SlotRefs{c->pool, q, wc}, grid_shade, TS, st);
     PTB_PROF(2, 1);
     c->stats.kernel_launches += 5;
     c->stats.trace_launches += 1;

@@ -23,7 +23,7 @@ def test_pod_layouts(ptb):
     assert L.camera_dtype.itemsize == 48 and L.sky_dtype.itemsize == 12
     assert L.ray_dtype.itemsize == 32 and L.hit_dtype.itemsize == 16 and L.bvh_node_dtype.itemsize == 64
     assert ctypes.sizeof(L.RenderOpts) == 48 and L.RenderOpts.seed.offset == 32 and L.RenderOpts.row_begin.offset == 40
-    assert ctypes.sizeof(L.Stats) == 12 * 8 + 6 * 8
+    assert ctypes.sizeof(L.Stats) == 12 * 8 + 7 * 8
 
 
 def test_no_cpu_fallback(ptb):

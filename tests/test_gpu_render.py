@@ -345,3 +345,38 @@ def test_render_multi_fewer_samples_than_gpus(ptb, gpu_ctx, rtweekend1):
     assert np.max(np.abs(got - want)) < 1e-6
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_fused_tail_hand_over_does_not_change_the_result(ptb, gpu_ctx, overshadowed, method, monkeypatch):
+    """The last live paths of a chunk are finished by ONE k_tail launch on a side stream (closest hit -> shade -> NEE per
+    lane) instead of ~45 nearly empty wavefront iterations. Same functions, same records, same RNG counters: the image and
+    every ray counter are independent of where the hand-over happens (PTB_TAIL_PATHS: 0 = never, default 65 536, and a
+    hand-over forced right after the first bounce)."""
+    scenes = [overshadowed, ptb.meshgen.c3_scene(0.05)] if method == 0 else [overshadowed]
+    for scene in scenes:
+        sc = ptb.Scene(scene, ctx=gpu_ctx)
+        o = ptb.RenderOptions(samples_per_pixel=16, render_method=method, width=160, height=90, seed=4)
+
+        def run():
+            gpu_ctx.stats_reset()
+            img = sc.render(o)
+            st = gpu_ctx.stats()
+            return img, (st.rays_camera, st.rays_bounce, st.rays_shadow_light, st.rays_shadow_sky, st.rays_reference, st.paths)
+
+        monkeypatch.setenv("PTB_TAIL_PATHS", "0")
+        a, ca = run()
+        monkeypatch.delenv("PTB_TAIL_PATHS")
+        b, cb = run()                                      # 230 400 paths: handed over once <= 65 536 are alive
+        monkeypatch.setenv("PTB_TAIL_PATHS", str(1 << 24))
+        c, cc = run()                                      # handed over after the first bounce
+        monkeypatch.setenv("PTB_WAVEFRONT", "window")
+        monkeypatch.setenv("PTB_POOL_PATHS", "32768")      # 8 chunks alternating between the two slots, tails overlapping
+        monkeypatch.setenv("PTB_TAIL_PATHS", "8192")
+        d, cd = run()
+        for k in ("PTB_TAIL_PATHS", "PTB_WAVEFRONT", "PTB_POOL_PATHS"):
+            monkeypatch.delenv(k)
+        assert ca == cb == cc == cd, (ca, cb, cc, cd)
+        assert ca[5] == 160 * 90 * 16
+        for other in (b, c, d):
+            assert np.allclose(a, other, rtol=1e-5, atol=1e-5)

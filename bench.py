@@ -498,7 +498,8 @@ def run_ours(args):
         node_bytes = 64.0
         b_ray = 48.0 + V * node_bytes + T * 48.0
         traced = st.rays_camera + st.rays_bounce
-        ms_by_kernel = {"k_trace": st.ms_trace, "k_shade": st.ms_shade, "k_shadow": st.ms_shadow, "bookkeeping": st.ms_generate}
+        ms_by_kernel = {"k_trace": st.ms_trace, "k_shade": st.ms_shade, "k_shadow": st.ms_shadow, "bookkeeping": st.ms_generate,
+                        "k_tail": st.ms_tail}
         dominant = max(("k_trace", "k_shade"), key=lambda k: ms_by_kernel[k])
         ev = ncu_evidence(f"{args.workload}:{dominant}") or {}
         alg_gbs = traced * b_ray / (st.ms_trace * 1e-3) / 1e9 if st.ms_trace > 0 else 0.0

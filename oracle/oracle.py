@@ -63,6 +63,10 @@ def _load():
     lib.orc_lbvh_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_lbvh_node_counts.argtypes = [P, P, C.c_size_t, P, C.c_int]
     lib.orc_lbvh_wide_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
+    lib.orc_cw_build.restype = C.c_size_t
+    lib.orc_cw_build.argtypes = [P, C.c_int]
+    lib.orc_cw_export.argtypes = [P, P, P]
+    lib.orc_cw_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_sah_ordered_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_philox4x32_10.argtypes = [P, P, P]
     lib.orc_sort_by_indices_u32.argtypes = [P, P, C.c_size_t]
@@ -274,6 +278,28 @@ class OracleScene:
         out = np.zeros(len(rays), hit_dtype)
         counts = np.zeros(2, np.uint64)
         lib.orc_lbvh_wide_closest_hit(self._h, _p(rays), len(rays), _p(out), threads, _p(counts))
+        return out, int(counts[0]), int(counts[1])
+
+    # -- compressed 8-wide BVH oracle (cwbvh_ref.hpp)
+    def cw_build(self, max_leaf=3):
+        """Builds the compressed wide BVH from the LBVH; returns the number of 96-byte nodes."""
+        self._lbvh = True
+        self._cw_nodes = lib.orc_cw_build(self._h, max_leaf)
+        return self._cw_nodes
+
+    def cw_export(self):
+        """(nodes as (n, 96) uint8 in the device layout, slot_prim: final primitive order -> original id)."""
+        nodes = np.zeros((self._cw_nodes, 96), np.uint8)
+        slot_prim = np.zeros(self.n_prims, np.uint32)
+        lib.orc_cw_export(self._h, _p(nodes), _p(slot_prim))
+        return nodes, slot_prim
+
+    def cw_closest_hit(self, rays, threads=0):
+        """(hits, wide nodes fetched, primitives tested) of the octant-ordered traversal of the compressed wide BVH."""
+        rays = np.ascontiguousarray(rays, dtype=ray_dtype)
+        out = np.zeros(len(rays), hit_dtype)
+        counts = np.zeros(2, np.uint64)
+        lib.orc_cw_closest_hit(self._h, _p(rays), len(rays), _p(out), threads, _p(counts))
         return out, int(counts[0]), int(counts[1])
 
     def lbvh_node_counts(self, rays, threads=0):

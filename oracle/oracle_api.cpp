@@ -8,6 +8,7 @@
 #include <thread>
 #include <vector>
 
+#include "cwbvh_ref.hpp"
 #include "lbvh_ref.hpp"
 #include "ref_integrators.hpp"
 
@@ -26,6 +27,7 @@ struct orc_scene {
   Camera camera;
   Lbvh lbvh;
   bool lbvh_built = false;
+  Cwbvh cw;
   double build_seconds = 0.0;
 };
 
@@ -339,6 +341,35 @@ void orc_lbvh_closest_hit(const orc_scene* s, const ptb_ray* rays, size_t n, ptb
       Hit h;
       uint32_t prim;
       bool have = s->lbvh.closest_hit(ray, h, prim, &nv[tid], &pt[tid]);
+      fill_hit(out[i], have, h, prim);
+    }
+  });
+  if (counts2) {
+    counts2[0] = counts2[1] = 0;
+    for (size_t i = 0; i < nv.size(); ++i) { counts2[0] += nv[i]; counts2[1] += pt[i]; }
+  }
+}
+
+// ------------------------------------------------------------------ compressed 8-wide BVH (cwbvh_ref.hpp)
+size_t orc_cw_build(orc_scene* s, int max_leaf) {
+  if (!s->lbvh_built) { s->lbvh.build(s->prims_original); s->lbvh_built = true; }
+  s->cw.build(s->lbvh, max_leaf);
+  return s->cw.nodes.size();
+}
+// nodes: n x 96 bytes in the device layout; slot_prim: final primitive order -> original id
+void orc_cw_export(const orc_scene* s, void* nodes, uint32_t* slot_prim) {
+  if (nodes) std::memcpy(nodes, s->cw.nodes.data(), s->cw.nodes.size() * sizeof(CwNode));
+  if (slot_prim) for (size_t i = 0; i < s->cw.slot_prim.size(); ++i) slot_prim[i] = s->cw.slot_prim[i];
+}
+void orc_cw_closest_hit(const orc_scene* s, const ptb_ray* rays, size_t n, ptb_hit* out, int threads, uint64_t* counts2) {
+  unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
+  std::vector<uint64_t> nv(nt ? nt : 1, 0), pt(nt ? nt : 1, 0);
+  parallel_for(n, threads, [&](unsigned tid, size_t b, size_t e) {
+    for (size_t i = b; i < e; ++i) {
+      Ray ray(Vec3(rays[i].ox, rays[i].oy, rays[i].oz), Vec3(rays[i].dx, rays[i].dy, rays[i].dz), 0.0f);
+      Hit h;
+      uint32_t prim;
+      bool have = s->cw.closest_hit(s->lbvh, ray, h, prim, &nv[tid], &pt[tid]);
       fill_hit(out[i], have, h, prim);
     }
   });

@@ -62,7 +62,11 @@ struct WaveCounters {  // lives in device memory; mirrored to pinned host memory
   uint32_t n_shadow;
   uint32_t cur;             // which q_active is the trace queue
   uint32_t trace_head, shade_head, shadow_head;  // persistent-kernel work cursors
-  uint32_t _pad;
+  // window mode, decided ON THE DEVICE by k_win_prepare so that the host never has to wait for an iteration before it
+  // enqueues the next: 0 wavefront iterations running, 1 this iteration hands the chunk's last n_tail paths to k_tail,
+  // 2 chunk finished, 3 handed over earlier — in every state but 0 the wavefront kernels find n_trace == 0 and return
+  uint32_t mode;
+  uint32_t n_tail, _pad;
   // k_shade's queue cursors, packed so that one warp needs ONE returning atomic per pair (the kernel used to spend 40 % of
   // its stall samples waiting for three serial same-address atomics): push_pair = finished-slot cursor << 32 | next-active
   // cursor, shadow_pair = sky NEE rays << 32 | shadow-queue cursor. k_prepare unpacks them between iterations.
@@ -72,6 +76,9 @@ struct WaveCounters {  // lives in device memory; mirrored to pinned host memory
   // statistics (ptb_stats)
   unsigned long long rays_camera, rays_bounce, rays_shadow_light, rays_shadow_sky, rays_reference, paths;
   unsigned long long nodes_fetched, prims_tested, rays_counted;  // PTB_OPT_COUNT_TRAVERSAL
+  // k_tail times itself (%globaltimer: first block in, last block out) — it runs on a side stream, detached from the
+  // host's view of the iterations; tail_ns sums the finished hand-overs of this slot
+  unsigned long long tail_t0, tail_t1, tail_ns;
 };
 
 struct Ctx {
@@ -115,12 +122,13 @@ struct Ctx {
   // tail (k_tail) finishes on `s_tail` in the other slot
   DevBuf d_pool_mem2, d_prev2, d_queues2, d_shadow2, d_counters2, d_windows2;
   cudaStream_t s_tail = nullptr;
-  cudaEvent_t ev_head_done[2] = {}, ev_tail_done[2] = {}, ev_tail_prof[4] = {};
+  cudaEvent_t ev_head_done[2] = {}, ev_tail_done[2] = {};
+  cudaEvent_t ev_ring[4] = {};  // per-iteration completion (the host runs at most 3 iterations ahead of the device)
   PathPool pool;
   size_t pool_budget_bytes = 0;  // half of the device memory that was free at the first large render (0 = not asked yet)
-  WaveCounters* h_counters = nullptr;  // pinned: [0..1] per-iteration mirrors, [2..3] end-of-render copy of each slot
+  WaveCounters* h_counters = nullptr;  // pinned: [0..3] per-iteration mirrors (ring), [4..5] end-of-render copy of each slot
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_iter = nullptr;
-  cudaEvent_t ev_prof[16] = {};  // PTB_OPT_TIME_KERNELS: 2 iterations x 4 kernel classes x (start, stop)
+  cudaEvent_t ev_prof[32] = {};  // PTB_OPT_TIME_KERNELS: 4 iterations (ring) x 4 kernel classes x (start, stop)
   bool opt_time_kernels = false, opt_count_traversal = false;
 
   // closest-hit staging: two buffer pairs + copy streams so that the upload of batch k+1, the traversal of batch k and the

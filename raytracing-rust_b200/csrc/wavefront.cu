@@ -224,6 +224,8 @@ __global__ void k_init_pool(uint32_t* free_slots, uint32_t capacity, WaveCounter
     wc->total_samples = total_samples;
     wc->rays_camera = wc->rays_bounce = wc->rays_shadow_light = wc->rays_shadow_sky = wc->rays_reference = wc->paths = 0;
     wc->nodes_fetched = wc->prims_tested = wc->rays_counted = 0;
+    wc->tail_t0 = ~0ull;
+    wc->tail_t1 = wc->tail_ns = 0ull;
   }
 }
 
@@ -957,8 +959,14 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
 //   k_win_scan       per 4096-window segment: exclusive prefix of the counts + segment total
 //   k_win_prepare    1 warp: statistics of the finished iteration, total of live paths, cursor resets
 //   k_win_fill       ordered live-slot queue (one block per window: counting sort of its live slots by direction bin)
-__global__ void __launch_bounds__(256) k_win_init(Queues q, uint32_t n_paths) {
+__global__ void __launch_bounds__(256) k_win_init(Queues q, WaveCounters* wc, uint32_t n_paths) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w == 0u) {
+    wc->mode = 0u; wc->n_tail = 0u; wc->n_trace = 0u;
+    if (wc->tail_t0 != ~0ull && wc->tail_t1 > wc->tail_t0) wc->tail_ns += wc->tail_t1 - wc->tail_t0;  // the slot's previous hand-over
+    wc->tail_t0 = ~0ull;
+    wc->tail_t1 = 0ull;
+  }
   if (w < q.n_windows) {
     const unsigned long long first = (unsigned long long)w * kWindow;
     q.win_count[w] = first >= n_paths ? 0u : (n_paths - first < kWindow ? (uint32_t)(n_paths - first) : kWindow);
@@ -1001,15 +1009,20 @@ __global__ void __launch_bounds__(1024) k_win_scan(Queues q) {
   }
 }
 
-// `prev` = what the finished iteration traced: 0 nothing (first of a chunk), 1 camera rays, 2 bounce rays
-__global__ void k_win_prepare(WaveCounters* wc, Queues q, uint32_t n_segments, uint32_t method, uint32_t prev) {
+// `prev` = what the finished iteration traced: 0 nothing (first of a chunk), 1 camera rays, 2 bounce rays.
+// Also the chunk's state machine (WaveCounters::mode): from iteration 2 on, a chunk with at most `tail_paths` live paths is
+// handed to k_tail (mode 1 for this iteration, 3 afterwards); with no live path left it is finished (2). The wavefront
+// kernels of an iteration in any state but 0 find n_trace == 0, so the host may enqueue iterations without waiting.
+__global__ void k_win_prepare(WaveCounters* wc, Queues q, uint32_t n_segments, uint32_t method, uint32_t prev, uint32_t depth,
+                              uint32_t tail_paths) {
   const uint32_t lane = threadIdx.x;
   uint32_t total = 0;
   for (uint32_t s = lane; s < n_segments; s += 32u) total += q.seg_total[s];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
   if (lane != 0u) return;
-  if (prev) {
+  uint32_t mode = wc->mode;
+  if (prev && mode == 0u) {
     const uint32_t traced = wc->n_trace, survivors = total;
     const unsigned long long sp = wc->shadow_pair;
     wc->rays_shadow_sky += sp >> 32;
@@ -1019,7 +1032,15 @@ __global__ void k_win_prepare(WaveCounters* wc, Queues q, uint32_t n_segments, u
     wc->rays_reference += method == PTB_METHOD_NAIVE ? traced : survivors;  // Q7, as k_prepare
     wc->paths += traced - survivors;
   }
-  wc->n_trace = total;
+  if (mode == 0u) {
+    if (total == 0u) mode = 2u;
+    else if (depth >= 2u && total <= tail_paths) { mode = 1u; wc->n_tail = total; }
+  } else if (mode == 1u) {
+    mode = 3u;
+    wc->n_tail = 0u;
+  }
+  wc->mode = mode;
+  wc->n_trace = mode == 0u ? total : 0u;
   wc->cur = 0;
   wc->shadow_pair = 0;
   wc->trace_head = wc->shade_head = wc->shadow_head = 0;
@@ -1033,6 +1054,7 @@ __global__ void __launch_bounds__(256) k_win_fill(Queues q, WaveCounters* wc) {
   __shared__ uint32_t s_seg_base;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t n_groups = (q.n_windows + kFillGroup - 1u) / kFillGroup;
+  if (wc->mode > 1u) return;  // chunk finished or handed over earlier: the live list must stay as the tail reads it
   uint32_t seg_cached = 0xffffffffu, buf = 0;
   s_hist[0][tid] = 0u;
   for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
@@ -1176,10 +1198,17 @@ PTB_DEV TravState trace_lane(const DevScene& sc, const Ray& ray, float tmax, uin
   }
   return st;
 }
+PTB_DEV unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 template <int METHOD, bool FULL>
 __global__ void __launch_bounds__(128)
 k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum) {
-  const uint32_t n = wc->n_trace;  // live paths, listed in q.active[0] by k_win_fill
+  if (wc->mode != 1u) return;      // launched after every iteration >= 2; only the hand-over iteration has work
+  const uint32_t n = wc->n_tail;   // live paths, listed in q.active[0] by k_win_fill
+  if (threadIdx.x == 0u) atomicMin(&wc->tail_t0, global_timer_ns());
   uint2 stack_local[kStackDepth];
   unsigned long long c_bounce = 0, c_sky = 0, c_light = 0, c_ref = 0, c_paths = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1231,6 +1260,7 @@ k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, 
     c_ref += __shfl_xor_sync(0xffffffffu, c_ref, o);
     c_paths += __shfl_xor_sync(0xffffffffu, c_paths, o);
   }
+  if (threadIdx.x == 0u) atomicMax(&wc->tail_t1, global_timer_ns());
   if ((threadIdx.x & 31u) == 0u && c_bounce) {
     atomicAdd(&wc->rays_bounce, c_bounce);
     if (c_sky) atomicAdd(&wc->rays_shadow_sky, c_sky);
@@ -1639,7 +1669,7 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   if (windows && plan.n_chunks > 1) bind_slot(rs.q2, rs.pool2, P, windows, c->d_pool_mem2, c->d_prev2, c->d_queues2, c->d_shadow2, c->d_windows2);
   rs.wc = c->d_counters.as<WaveCounters>();
   rs.wc2 = c->d_counters2.as<WaveCounters>();
-  if (!c->h_counters) PTB_CUDA_TRY(c, cudaMallocHost(&c->h_counters, 4 * sizeof(WaveCounters)));
+  if (!c->h_counters) PTB_CUDA_TRY(c, cudaMallocHost(&c->h_counters, 6 * sizeof(WaveCounters)));
 
   RenderParams& rp = rs.rp;
   rp.width = o.width; rp.height = o.height; rp.npix = npix;
@@ -1680,15 +1710,13 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   if (rs.prof) {
     for (cudaEvent_t& e : c->ev_prof)
       if (!e) PTB_CUDA_TRY(c, cudaEventCreate(&e));
-    for (cudaEvent_t& e : c->ev_tail_prof)
-      if (!e) PTB_CUDA_TRY(c, cudaEventCreate(&e));
   }
   return windows ? render_window_mode(c, o, rs, progress, user) : render_queue_mode(c, o, rs, progress, user);
 }
 
-// ev_prof[(iter & 1) * 8 + 2 * k + {0,1}] brackets kernel class k (0 generate + bookkeeping, 1 trace, 2 shade, 3 shadow)
+// ev_prof[(iter & 3) * 8 + 2 * k + {0,1}] brackets kernel class k (0 generate + bookkeeping, 1 trace, 2 shade, 3 shadow)
 #define PTB_PROF(k, which) \
-  if (prof) cudaEventRecord(c->ev_prof[(int)(iter & 1u) * 8 + 2 * (k) + (which)], st)
+  if (prof) cudaEventRecord(c->ev_prof[(int)(iter & 3u) * 8 + 2 * (k) + (which)], st)
 static void prof_collect(Ctx* c, int half, bool mis) {
   double* prof_ms[4] = {&c->stats.ms_generate, &c->stats.ms_trace, &c->stats.ms_shade, &c->stats.ms_shadow};
   for (int k = 0; k < (mis ? 4 : 3); ++k) {
@@ -1796,12 +1824,15 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
       if (!c->ev_tail_done[k]) PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_tail_done[k], cudaEventDisableTiming));
     }
   }
+  for (cudaEvent_t& e : c->ev_ring)
+    if (!e) PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   const uint32_t grid_tail = (tail_paths + 127u) / 128u;
   bool tail_pending[2] = {false, false};  // a k_tail is (or may still be) running in that slot
-  auto collect_tail_prof = [&](int sl) {
-    float ms = 0.f;
-    if (prof && cudaEventElapsedTime(&ms, c->ev_tail_prof[2 * sl], c->ev_tail_prof[2 * sl + 1]) == cudaSuccess) c->stats.ms_tail += ms;
-  };
+  // The host never waits for the iteration it has just enqueued: the chunk's state machine runs on the device
+  // (k_win_prepare) and every kernel of an iteration that has nothing to do returns at once. The host stays at most
+  // kAhead iterations in front and reads the mirror of iteration d - kAhead to learn that a chunk is over, so a chunk
+  // costs at most kAhead empty iterations (~20 us each) instead of one host round trip per iteration.
+  constexpr uint64_t kAhead = 3;
 
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
   k_init_pool<<<1, 32, 0, st>>>(rs.q.active[0], 0u, rs.wc, total);   // counters only
@@ -1809,8 +1840,8 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   c->stats.kernel_launches += 2;
   int32_t rc = PTB_OK;
   uint64_t iter = 0;
-  cudaEvent_t ev[2] = {c->ev_iter, c->ev_b};
   uint32_t chunk_index = 0;
+  uint64_t rays_ref_seen = 0;
   for (unsigned long long first = 0; first < total && rc == PTB_OK; first += P, ++chunk_index) {
     const int sl = rs.n_chunks > 1 ? (int)(chunk_index & 1u) : 0;
     const SlotRefs& S = slots[sl];
@@ -1819,34 +1850,45 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
     const uint32_t n_paths = (uint32_t)(total - first < P ? total - first : P);
     if (tail_pending[sl]) {  // the slot's previous chunk (two chunks ago) must have left it
       PTB_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_tail_done[sl], 0));
-      if (prof) { PTB_CUDA_TRY(c, cudaEventSynchronize(c->ev_tail_prof[2 * sl + 1])); collect_tail_prof(sl); }
       tail_pending[sl] = false;
     }
     PTB_CUDA_TRY(c, cudaMemsetAsync(q.win_count, 0, (size_t)q.n_windows * 4, st));
     if (n_paths % kWindow)  // slots of the last window that hold no path
       PTB_CUDA_TRY(c, cudaMemsetAsync(q.bin + n_paths, (int)kBinDead, kWindow - n_paths % kWindow, st));
     PTB_PROF(0, 0);
-    k_win_init<<<(q.n_windows + T - 1) / T, T, 0, st>>>(q, n_paths);
+    k_win_init<<<(q.n_windows + T - 1) / T, T, 0, st>>>(q, wc, n_paths);
     c->stats.kernel_launches += 1;
-    bool done = false, tail_next = false;
-    for (uint64_t depth = 0; !done; ++depth, ++iter) {
+    const uint64_t iter0 = iter;
+    bool over = false;
+    // drains iteration `it` of this chunk: its events are complete, its mirror says whether the chunk is over
+    auto drain = [&](uint64_t it) -> int32_t {
+      const int r = (int)(it & 3u);
+      PTB_CUDA_TRY(c, cudaEventSynchronize(c->ev_ring[r]));
+      if (prof) prof_collect(c, r, mis);
+      if (c->h_counters[r].mode != 0u) over = true;
+      rays_ref_seen = c->h_counters[r].rays_reference;
+      return PTB_OK;
+    };
+    for (uint64_t depth = 0; !over; ++depth, ++iter) {
+      if (depth >= kAhead) {
+        const int32_t d = drain(iter - kAhead);
+        if (d != PTB_OK) return d;
+        if (over) break;
+      }
       if (depth) PTB_PROF(0, 0);
       k_win_scan<<<n_seg, 1024, 0, st>>>(q);
-      k_win_prepare<<<1, 32, 0, st>>>(wc, q, n_seg, o.method, depth == 0 ? 0u : (depth == 1 ? 1u : 2u));
+      k_win_prepare<<<1, 32, 0, st>>>(wc, q, n_seg, o.method, depth == 0 ? 0u : (depth == 1 ? 1u : 2u), (uint32_t)depth, tail_paths);
       if (depth) k_win_fill<<<grid_fill, T, 0, st>>>(q, wc);  // depth 0: work item i is slot i, no queue
       PTB_PROF(0, 1);
-      if (tail_next) {
-        // the live list is built; everything left of this chunk is ONE launch on the side stream
-        c->stats.kernel_launches += 4;
+      if (tail_paths && depth >= 2) {
+        // k_tail runs in the iteration whose k_win_prepare hands the chunk over (and returns at once in all the others):
+        // everything left of the chunk is then ONE launch on the side stream
         PTB_CUDA_TRY(c, cudaEventRecord(c->ev_head_done[sl], st));
         PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_tail, c->ev_head_done[sl], 0));
-        if (prof) PTB_CUDA_TRY(c, cudaEventRecord(c->ev_tail_prof[2 * sl], c->s_tail));
         launch_tail(rs, c, S, grid_tail, c->s_tail);
-        if (prof) PTB_CUDA_TRY(c, cudaEventRecord(c->ev_tail_prof[2 * sl + 1], c->s_tail));
         PTB_CUDA_TRY(c, cudaEventRecord(c->ev_tail_done[sl], c->s_tail));
         tail_pending[sl] = true;
-        ++iter;
-        break;
+        c->stats.kernel_launches += 1;
       }
       PTB_PROF(1, 0);
       if (depth == 0) {
@@ -1872,44 +1914,38 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
         PTB_PROF(3, 1);
         c->stats.kernel_launches += 1;
       }
-      // two pinned mirrors + events: the host inspects iteration k-1 while iteration k runs
-      const int slot = (int)(iter & 1u);
-      PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + slot, wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
-      PTB_CUDA_TRY(c, cudaEventRecord(ev[slot], st));
-      if (depth > 0) {
-        const int ps = slot ^ 1;
-        PTB_CUDA_TRY(c, cudaEventSynchronize(ev[ps]));
-        if (prof) prof_collect(c, ps, mis);
-        const uint32_t traced_before = c->h_counters[ps].n_trace;  // rays of iteration depth-1: an upper bound of what is alive now
-        if (traced_before == 0u) done = true;
-        else if (tail_paths && traced_before <= tail_paths) tail_next = true;
-      }
+      // pinned mirrors + events, a ring of four
+      const int r = (int)(iter & 3u);
+      PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + r, wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+      PTB_CUDA_TRY(c, cudaEventRecord(c->ev_ring[r], st));
       if (depth > 4096) return set_error(c, PTB_ERR_INVALID, "wavefront did not terminate");
     }
-    {
-      // the last iteration with a mirror: without a hand-over the empty one launched last (its k_win_prepare folded the
-      // statistics of the last real one), else the one before the tail iteration
-      const int last = (int)((iter - (tail_next ? 2u : 1u)) & 1u);
-      PTB_CUDA_TRY(c, cudaEventSynchronize(ev[last]));
-      if (prof) prof_collect(c, last, mis);
-      if (progress && first + n_paths < total && progress(user, (first + n_paths) / npix, c->h_counters[last].rays_reference))
-        rc = PTB_ERR_ABORTED;
-    }
+    // the iterations still in flight are empty or the hand-over itself; the timing build collects their events
+    if (prof)
+      for (uint64_t it = iter > iter0 + kAhead ? iter - kAhead : iter0; it < iter; ++it) {
+        bool keep = over;
+        const int32_t d = drain(it);
+        over = keep || over;
+        if (d != PTB_OK) return d;
+      }
+    if (progress && first + n_paths < total && progress(user, (first + n_paths) / npix, rays_ref_seen)) rc = PTB_ERR_ABORTED;
   }
   for (int sl = 0; sl < 2; ++sl)
     if (tail_pending[sl]) PTB_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_tail_done[sl], 0));
-  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + 2, rs.wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
-  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + 3, rs.wc2, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + 4, rs.wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + 5, rs.wc2, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
   PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
   PTB_CUDA_TRY(c, cudaGetLastError());
-  for (int sl = 0; sl < 2; ++sl)
-    if (tail_pending[sl]) collect_tail_prof(sl);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
   const uint64_t ref_before = c->stats.rays_reference;
-  fold_counters(c, c->h_counters[2], iter);
-  fold_counters(c, c->h_counters[3], 0);
+  fold_counters(c, c->h_counters[4], iter);
+  fold_counters(c, c->h_counters[5], 0);
+  for (int k = 4; k < 6; ++k) {
+    const WaveCounters& h = c->h_counters[k];
+    c->stats.ms_tail += 1e-6 * (double)(h.tail_ns + (h.tail_t0 != ~0ull && h.tail_t1 > h.tail_t0 ? h.tail_t1 - h.tail_t0 : 0ull));
+  }
   c->stats.render_ms = ms;
   if (rc == PTB_OK) {
     c->accum_samples += o.samples_per_pixel;
@@ -1976,7 +2012,7 @@ static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderS
     if (iter > 0) {  // inspect the previous iteration (already finished or about to)
       const int ps = slot ^ 1;
       PTB_CUDA_TRY(c, cudaEventSynchronize(ev[ps]));
-      if (prof) prof_collect(c, ps, mis);
+      if (prof) prof_collect(c, (int)((iter - 1) & 3u), mis);
       const WaveCounters& h = c->h_counters[ps];
       if (h.next_sample >= h.total_samples && (uint32_t)h.push_pair == 0u) done = true;
       if (progress && !done) {
@@ -1997,7 +2033,7 @@ static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderS
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
   PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
   PTB_CUDA_TRY(c, cudaGetLastError());
-  if (prof && iter > 0) prof_collect(c, (int)((iter - 1) & 1u), mis);
+  if (prof && iter > 0) prof_collect(c, (int)((iter - 1) & 3u), mis);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
   const WaveCounters& h = c->h_counters[0];

@@ -8,5 +8,5 @@ for spec in "$@"; do
   echo "$line" | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']; m=r['ms_by_kernel']
-print('$label', 'Mrays/s', round(d['value']), 'ms/step', round(d['ms_per_step'],2), 'trace', round(m['k_trace']), 'shade', round(m['k_shade']), 'shadow', round(m['k_shadow']), 'book', round(m['bookkeeping']), 'launches', d['gpu_launches'], 'iters', d['run']['wavefront_iterations'])"
+print('$label', 'Mrays/s', round(d['value']), 'ms/step', round(d['ms_per_step'],2), 'trace', round(m['k_trace']), 'shade', round(m['k_shade']), 'shadow', round(m['k_shadow']), 'book', round(m['bookkeeping']), 'tail', round(m.get('k_tail',0),1), 'launches', d['gpu_launches'], 'iters', d['run']['wavefront_iterations'])"
 done

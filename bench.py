@@ -343,6 +343,7 @@ def run_ours(args):
     ctx.commit()
     build_ms = ctx.stats().build_ms
     n_prims, n_nodes = ctx.bvh_info()
+    n_wide, wide_leaf = ctx.bvh_wide_info()
     if strong:
         my_off, my_spp = ptb200.shard_samples(S, rank, world)
         step_span = S
@@ -495,7 +496,7 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         # Algorithmic bytes of a closest-hit traversal: 32 B ray in + 16 B hit out + V nodes + T primitives
-        node_bytes = 64.0
+        node_bytes = 96.0 if n_wide else 64.0   # compressed 8-wide node / binary node holding both children's boxes
         b_ray = 48.0 + V * node_bytes + T * 48.0
         traced = st.rays_camera + st.rays_bounce
         ms_by_kernel = {"k_trace": st.ms_trace, "k_shade": st.ms_shade, "k_shadow": st.ms_shadow, "bookkeeping": st.ms_generate,
@@ -522,7 +523,9 @@ def run_ours(args):
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": e2e, "gpu_launches": int(st.kernel_launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "run": {"spp_this_rank": my_spp, "bvh_nodes": n_nodes, "bvh_build_ms": build_ms, "rays_reference_style": st.rays_reference,
+            "run": {"spp_this_rank": my_spp, "bvh": (f"compressed 8-wide, {n_wide} nodes x 96 B, leaf groups <= {wide_leaf}" if n_wide
+                                                     else f"binary LBVH, {n_nodes} nodes x 64 B"),
+                    "bvh_nodes": n_wide or n_nodes, "node_bytes": node_bytes, "bvh_build_ms": build_ms, "rays_reference_style": st.rays_reference,
                     "wall_s": t_wall, "wavefront_iterations": int(st.wavefront_iterations)},
         }
         if multi_diff is not None:
@@ -552,6 +555,9 @@ def run_closest_hit(args, rank, world, local, n_tris, n_rays, cpu=True, steps=No
     ctx.upload(scene)
     ctx.commit()
     n_prims, n_nodes = ctx.bvh_info()
+    n_wide, wide_leaf = ctx.bvh_wide_info()
+    node_bytes = 96.0 if n_wide else 64.0
+    ctx_build_ms = ctx.stats().build_ms
     K = steps if steps is not None else args.steps
     W = warmup if warmup is not None else args.warmup
     batch = min(max(1, n_rays // max(K, 1)), 1 << 24)   # rays per step per rank
@@ -597,7 +603,7 @@ def run_closest_hit(args, rank, world, local, n_tris, n_rays, cpu=True, steps=No
     sc = ctx.stats()
     ctx.set_option(ptb200._lib.OPT_COUNT_TRAVERSAL, 0)
     V, T = sc.nodes_fetched / batch, sc.prims_tested / batch
-    b_ray = 32.0 + 16.0 + V * 64.0 + T * 48.0
+    b_ray = 32.0 + 16.0 + V * node_bytes + T * 48.0
     achieved = batch * K * b_ray / (ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
     ev = ncu_evidence("c5:k_closest_hit_api") or {}
@@ -645,7 +651,8 @@ def run_closest_hit(args, rank, world, local, n_tris, n_rays, cpu=True, steps=No
                      "algorithmic_bytes_per_launch": b_ray * batch, "bytes_per_ray": b_ray, "nodes_per_ray": V, "prims_per_ray": T,
                      "limiter": ev.get("limiter")},
         "cpu_baseline": cpu_b,
-        "run": {"rays_per_step_per_gpu": batch, "rays_timed": batch * K * world, "bvh_nodes": n_nodes, "hit_fraction": hit_frac,
+        "run": {"rays_per_step_per_gpu": batch, "rays_timed": batch * K * world, "bvh_nodes": n_wide or n_nodes, "node_bytes": node_bytes,
+                "bvh": "compressed 8-wide" if n_wide else "binary LBVH", "build_ms": ctx_build_ms, "hit_fraction": hit_frac,
                 "ray_stream_max_abs_dev_vs_numpy": stream_err},
     }
 

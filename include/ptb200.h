@@ -217,14 +217,23 @@ int32_t ptb_scene_set_texture_data(ptb_ctx* ctx, uint32_t texture, uint32_t widt
 int32_t ptb_scene_set_camera(ptb_ctx* ctx, const ptb_camera* camera);
 int32_t ptb_scene_set_sky(ptb_ctx* ctx, const ptb_sky* sky);
 
-/* Replaces Bvh::new (acceleration/mod.rs:58-93): uploads the scene and builds the LBVH on the device. */
-enum { PTB_BUILD_DEFAULT = 0 };
+/* Replaces Bvh::new (acceleration/mod.rs:58-93): builds the acceleration structure on the device — always the LBVH
+ * (Morton sort, Karras hierarchy, refit), and on top of it, when the wide tree is selected, its SAH-driven collapse into
+ * a compressed 8-wide BVH (quantised 96-byte nodes, leaf groups of up to 3 primitives) which the traversal kernels then
+ * walk instead. PTB_BUILD_DEFAULT follows the environment (PTB_BVH=binary|wide) and otherwise the library's default. */
+enum { PTB_BUILD_DEFAULT = 0, PTB_BUILD_BINARY = 1, PTB_BUILD_WIDE = 2 };
 int32_t ptb_scene_commit(ptb_ctx* ctx, uint32_t build_flags);
 
 /* Bit-exact test hooks: n_prims Morton codes and primitive ids in sorted order, n_prims-1 nodes
  * (1 node when n_prims == 1). Any pointer may be NULL. */
 int32_t ptb_bvh_info(ptb_ctx* ctx, uint64_t* n_prims, uint64_t* n_nodes);
 int32_t ptb_bvh_export(ptb_ctx* ctx, uint32_t* morton_sorted, uint32_t* prim_sorted, ptb_bvh_node* nodes);
+
+/* The compressed 8-wide tree, for bit-exact tests: *n_nodes = 0 when the committed scene uses the binary tree. Nodes are
+ * 96 bytes each (layout: raytracing-rust_b200/csrc/ptb_common.cuh CwNode == oracle/cwbvh_ref.hpp CwNode), slot_prim maps
+ * the tree's primitive order to original primitive ids (n_prims entries). Any pointer may be NULL. */
+int32_t ptb_bvh_wide_info(ptb_ctx* ctx, uint64_t* n_nodes, uint32_t* max_leaf);
+int32_t ptb_bvh_wide_export(ptb_ctx* ctx, void* nodes96, uint32_t* slot_prim);
 
 /* ---------------------------------------------------------- closest hit -- */
 /* Replaces AccelerationStructure::check_hit (acceleration/mod.rs:265-298) for a batch of rays.

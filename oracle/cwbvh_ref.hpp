@@ -342,37 +342,47 @@ struct Cwbvh {
     return r;
   }
   // One node against one ray: returns the hit mask (bits 24..31 inner children in octant order, bits 0..23 primitives).
+  // A quantised plane enters as the float F(q) = 1 + q 2^-15 (one byte permute on the device instead of a quarter-rate
+  // integer conversion), so the per-node constants carry the factor 2^15: ad = cell 2^15 dinv (near planes), adk = ad k (far
+  // planes, k = 1 + 8 gamma(3): the far side widened like aabb.rs:45-47 does), offsets c_lo = (base - err) - ad and
+  // c_hi = (base + err) k - adk, with base = p dinv - o dinv and err the rounding bound of that fold (make_ray) plus
+  // 2^-23 |ad| for the folded 2^15-cell constant. ONE cull bound serves all eight children: best t plus 32 eps times the
+  // largest plane distance the node can produce (the binary test's per-box slack, taken per node).
+  // A child is hit iff  max(near_x, near_y, near_z, 0) <= min(far_x, far_y, far_z, bound).
+  static Float plane(uint32_t q) { return bits_to_float(0x3F800000u | (q << 8)); }
   static uint32_t intersect_node(const CwNode& nd, const CwRay& r, Float best_t) {
     const Float k = 1.0f + 8.0f * gamma(3);
-    const Float cell[3] = {bits_to_float((uint32_t)nd.e[0] << 23), bits_to_float((uint32_t)nd.e[1] << 23), bits_to_float((uint32_t)nd.e[2] << 23)};
+    const Float q8 = 1.0f / 8388608.0f, c255 = 255.0f / 32768.0f;
     const Float dinv[3] = {r.dinv.x, r.dinv.y, r.dinv.z};
     const Float nod[3] = {r.neg_od.x, r.neg_od.y, r.neg_od.z}, ed[3] = {r.ed.x, r.ed.y, r.ed.z}, eo[3] = {r.eo.x, r.eo.y, r.eo.z};
-    Float ad[3], alo[3], ahi[3];
+    Float ad[3], adk[3], clo[3], chik[3], reach[3];
     for (int a = 0; a < 3; ++a) {
-      ad[a] = cell[a] * dinv[a];
+      const Float cell = bits_to_float(((uint32_t)nd.e[a] + 15u) << 23);
+      ad[a] = cell * dinv[a];
+      adk[a] = ad[a] * k;
       const Float base = std::fmaf(nd.p[a], dinv[a], nod[a]);
-      const Float err = std::fmaf(std::fabs(nd.p[a]), ed[a], eo[a]);
-      alo[a] = base - err;
-      ahi[a] = base + err;
+      const Float err = std::fmaf(std::fabs(nd.p[a]), ed[a], std::fmaf(std::fabs(ad[a]), q8, eo[a]));
+      clo[a] = (base - err) - ad[a];
+      chik[a] = (base + err) * k - adk[a];
+      reach[a] = std::fabs(base) + std::fmaf(c255, std::fabs(adk[a]), err);
     }
+    const Float bound = std::fmaf(32.0f * F32_EPS, fmax_(fmax_(reach[0], reach[1]), reach[2]), best_t);
     uint32_t mask = 0;
     for (int s = 0; s < 8; ++s) {
       const uint32_t meta = nd.meta[s];
-      if (meta == 0u) continue;
       Float tn[3], tf[3];
       for (int a = 0; a < 3; ++a) {
         const bool neg = dinv[a] < 0.0f;
-        const Float qn = (Float)(neg ? nd.qhi[a][s] : nd.qlo[a][s]), qf = (Float)(neg ? nd.qlo[a][s] : nd.qhi[a][s]);
-        tn[a] = std::fmaf(qn, ad[a], alo[a]);
-        tf[a] = std::fmaf(qf, ad[a], ahi[a]);
+        const Float qn = plane(neg ? nd.qhi[a][s] : nd.qlo[a][s]), qf = plane(neg ? nd.qlo[a][s] : nd.qhi[a][s]);
+        tn[a] = std::fmaf(qn, ad[a], clo[a]);
+        tf[a] = std::fmaf(qf, adk[a], chik[a]);
       }
-      const Float tmin = fmax_(fmax_(tn[0], tn[1]), tn[2]);
-      const Float hmin = fmin_(fmin_(tf[0], tf[1]), tf[2]);
-      const Float tkey = std::fmaf(-(32.0f * F32_EPS), fmax_(std::fabs(tmin), std::fabs(hmin)), tmin);
-      if (!(hmin * k > fmax_(tmin, 0.0f) && tkey <= best_t)) continue;
+      const Float lo = fmax_(fmax_(fmax_(tn[0], tn[1]), tn[2]), 0.0f);
+      const Float hi = fmin_(fmin_(tf[0], tf[1]), fmin_(tf[2], bound));
+      if (!(lo <= hi)) continue;
       const bool inner = (meta & 0x18u) == 0x18u;
       const uint32_t pos = inner ? ((meta & 31u) ^ r.oinv) : (meta & 31u);
-      mask |= (meta >> 5) << pos;
+      mask |= (meta >> 5) << pos;  // an empty slot (meta 0) contributes nothing
     }
     return mask;
   }

@@ -96,7 +96,8 @@ class Context:
         _check(h, L.lib.ptb_scene_set_sky(h, L.ptr(s.sky)))
 
     def commit(self, flags: int = 0):
-        """Bvh::new: upload + device LBVH build."""
+        """Bvh::new: device LBVH build (+ its collapse into the compressed 8-wide tree when selected: L.BUILD_WIDE, or
+        L.BUILD_DEFAULT with PTB_BVH=wide / the library default)."""
         _check(self._h, L.lib.ptb_scene_commit(self._h, flags))
 
     def bvh_info(self):
@@ -111,6 +112,21 @@ class Context:
         nodes = np.zeros(m, L.bvh_node_dtype)
         _check(self._h, L.lib.ptb_bvh_export(self._h, L.ptr(morton), L.ptr(prims), L.ptr(nodes)))
         return morton, prims, nodes
+
+    def bvh_wide_info(self):
+        """(number of 96-byte nodes of the compressed 8-wide tree — 0 when the scene uses the binary tree, max leaf size)."""
+        n, m = C.c_uint64(), C.c_uint32()
+        _check(self._h, L.lib.ptb_bvh_wide_info(self._h, C.byref(n), C.byref(m)))
+        return n.value, m.value
+
+    def bvh_wide_export(self):
+        """(nodes (n, 96) uint8, slot_prim: the wide tree's primitive order -> original primitive id)."""
+        n, _ = self.bvh_wide_info()
+        n_prims, _ = self.bvh_info()
+        nodes = np.zeros((n, 96), np.uint8)
+        slot_prim = np.zeros(n_prims, np.uint32)
+        _check(self._h, L.lib.ptb_bvh_wide_export(self._h, L.ptr(nodes), L.ptr(slot_prim)))
+        return nodes, slot_prim
 
     # ---- closest hit
     def closest_hit(self, rays: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:

@@ -280,8 +280,8 @@ int32_t ptb_bvh_export(ptb_ctx* ctx, uint32_t* morton_sorted, uint32_t* prim_sor
   if (c->n_prims == 0) return PTB_OK;
   if (morton_sorted)
     PTB_CUDA_TRY(c, cudaMemcpyAsync(morton_sorted, c->d_morton.p, c->n_prims * 4, cudaMemcpyDeviceToHost, c->stream));
-  if (prim_sorted)
-    PTB_CUDA_TRY(c, cudaMemcpyAsync(prim_sorted, c->d_slot_prim.p, c->n_prims * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (prim_sorted)  // Morton order (the wide tree keeps its own primitive order in d_slot_prim)
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(prim_sorted, c->wide ? c->d_prim_sorted.p : c->d_slot_prim.p, c->n_prims * 4, cudaMemcpyDeviceToHost, c->stream));
   if (nodes)
     PTB_CUDA_TRY(c, cudaMemcpyAsync(nodes, c->d_nodes.p, c->n_nodes * sizeof(ptb_bvh_node), cudaMemcpyDeviceToHost, c->stream));
   PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -290,6 +290,24 @@ int32_t ptb_bvh_export(ptb_ctx* ctx, uint32_t* morton_sorted, uint32_t* prim_sor
       if (nodes[i].left & PTB_LEAF_BIT) nodes[i].left &= ~kSphereBit;
       if (nodes[i].right & PTB_LEAF_BIT) nodes[i].right &= ~kSphereBit;
     }
+  return PTB_OK;
+}
+
+int32_t ptb_bvh_wide_info(ptb_ctx* ctx, uint64_t* n_nodes, uint32_t* max_leaf) {
+  CTX_OR_FAIL(ctx);
+  if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
+  if (n_nodes) *n_nodes = c->wide ? c->n_cw_nodes : 0;
+  if (max_leaf) *max_leaf = c->cw_max_leaf;
+  return PTB_OK;
+}
+int32_t ptb_bvh_wide_export(ptb_ctx* ctx, void* nodes96, uint32_t* slot_prim) {
+  CTX_OR_FAIL(ctx);
+  if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
+  if (!c->wide) return set_error(c, PTB_ERR_INVALID, "the committed scene uses the binary tree");
+  if (c->n_prims == 0) return PTB_OK;
+  if (nodes96) PTB_CUDA_TRY(c, cudaMemcpyAsync(nodes96, c->d_cw_nodes.p, c->n_cw_nodes * sizeof(CwNode), cudaMemcpyDeviceToHost, c->stream));
+  if (slot_prim) PTB_CUDA_TRY(c, cudaMemcpyAsync(slot_prim, c->d_slot_prim.p, c->n_prims * 4, cudaMemcpyDeviceToHost, c->stream));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
   return PTB_OK;
 }
 

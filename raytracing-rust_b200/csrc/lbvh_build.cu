@@ -11,6 +11,7 @@
 // The result is bit-exact against oracle/lbvh_ref.hpp (tests/test_gpu_lbvh.py): min/max and the Morton arithmetic are
 // order-independent and IEEE-exact, the sort is stable, the hierarchy is a pure function of the sorted keys.
 #include <cstdarg>
+#include <cstring>
 
 #include "ptb_internal.h"
 
@@ -251,7 +252,8 @@ __device__ __forceinline__ int lbvh_delta(const uint32_t* __restrict__ keys, int
   return __clz(a ^ b);
 }
 __global__ void k_hierarchy(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ prim_sorted, uint32_t n_prims,
-                            uint32_t n_spheres, BvhNode* __restrict__ nodes, uint32_t* __restrict__ leaf_parent) {
+                            uint32_t n_spheres, BvhNode* __restrict__ nodes, uint32_t* __restrict__ leaf_parent,
+                            uint2* __restrict__ range) {
   const int n = (int)n_prims;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
@@ -271,6 +273,7 @@ __global__ void k_hierarchy(const uint32_t* __restrict__ keys, const uint32_t* _
   }
   const int gam = i + s * d + (d < 0 ? -1 : 0);
   const int lo = min(i, j), hi = max(i, j);
+  if (range) range[i] = make_uint2((uint32_t)lo, (uint32_t)hi);  // Morton positions the node covers (wide collapse)
   uint32_t left, right;
   if (lo == gam) {
     left = PTB_LEAF_BIT | (prim_sorted[gam] < n_spheres ? kSphereBit : 0u) | (uint32_t)gam;
@@ -330,38 +333,6 @@ __global__ void k_refit(uint32_t n_prims, const uint32_t* __restrict__ prim_sort
 }
 
 // single primitive: one node, both child slots reference leaf 0 (see oracle/lbvh_ref.hpp)
-// ------------------------------------------------------------------------------------------ 4-wide collapse
-// One thread per LBVH node: nodes at even depth (parent chain walked to the root) gather their grandchildren into a
-// 128-byte wide node at the same index. No reference counterpart (the reference's tree is binary); the CPU definition is
-// Lbvh::build_wide in oracle/lbvh_ref.hpp.
-__global__ void k_collapse4(const BvhNode* __restrict__ nodes, uint32_t n_nodes, BvhNode4* __restrict__ wide) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_nodes) return;
-  uint32_t depth = 0;
-  for (uint32_t p = nodes[i].n3.z; p != kNone; p = nodes[p].n3.z) ++depth;
-  if (depth & 1u) return;
-  const BvhNode nd = nodes[i];
-  BvhNode4 w;
-  int k = 0;
-  auto put = [&](uint32_t ref, float mnx, float mny, float mnz, float mxx, float mxy, float mxz) {
-    float* b = w.box + 6 * k;
-    b[0] = mnx; b[1] = mny; b[2] = mnz; b[3] = mxx; b[4] = mxy; b[5] = mxz;
-    w.child[k++] = ref;
-  };
-  auto expand = [&](uint32_t ref, float mnx, float mny, float mnz, float mxx, float mxy, float mxz) {
-    if (ref & PTB_LEAF_BIT) { put(ref, mnx, mny, mnz, mxx, mxy, mxz); return; }
-    const BvhNode c = nodes[ref];
-    put(c.n3.x, c.n0.x, c.n0.y, c.n0.z, c.n0.w, c.n1.x, c.n1.y);
-    put(c.n3.y, c.n1.z, c.n1.w, c.n2.x, c.n2.y, c.n2.z, c.n2.w);
-  };
-  expand(nd.n3.x, nd.n0.x, nd.n0.y, nd.n0.z, nd.n0.w, nd.n1.x, nd.n1.y);
-  expand(nd.n3.y, nd.n1.z, nd.n1.w, nd.n2.x, nd.n2.y, nd.n2.z, nd.n2.w);
-  const float inf = __int_as_float(0x7f800000);
-  for (; k < 4;) put(kNone, inf, inf, inf, -inf, -inf, -inf);
-  for (int j = 0; j < 4; ++j) w.pad[j] = 0u;
-  wide[i] = w;
-}
-
 __global__ void k_single_node(const uint32_t* __restrict__ prim_sorted, uint32_t n_spheres, const float4* __restrict__ bmin,
                               const float4* __restrict__ bmax, BvhNode* nodes) {
   const uint32_t p = prim_sorted[0];
@@ -503,7 +474,10 @@ __global__ void k_collect_lights(const ptb_sphere* __restrict__ spheres, uint32_
   if (mats[mat].kind == PTB_MAT_EMIT) list[atomicAdd(out, 1u)] = i;  // material.is_light() (acceleration/mod.rs:84-88)
 }
 
-int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
+#ifndef PTB_DEFAULT_WIDE
+#define PTB_DEFAULT_WIDE 0  // tree behind PTB_BUILD_DEFAULT (see the comment at its use); decided by measurement, DESIGN.md
+#endif
+int32_t build_scene(Ctx* c, uint32_t build_flags) {
   const size_t ns = c->n_spheres, nt = c->n_tris;
   const size_t n = ns + nt;
   if (n >= (size_t)kSlotMask) return set_error(c, PTB_ERR_INVALID, "too many primitives (%zu)", n);
@@ -574,7 +548,8 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
   c->dev.n_prims = (uint32_t)n;
   c->dev.n_lights = 0;
   c->dev.geom = nullptr; c->dev.normals = nullptr; c->dev.slot_prim = nullptr; c->dev.slot_mat = nullptr;
-  c->dev.nodes = nullptr; c->dev.lights = nullptr;
+  c->dev.nodes = nullptr; c->dev.lights = nullptr; c->dev.cw_nodes = nullptr;
+  c->wide = false;
   if (n == 0) {
     c->committed = true;
     c->stats.build_ms = 0.0;
@@ -612,6 +587,20 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
   PTB_CUDA_TRY(c, c->d_morton.reserve(n * 4));
   PTB_CUDA_TRY(c, c->d_slot_prim.reserve(n * 4));
 
+  // Which tree the traversal kernels walk: the binary LBVH or its collapse into the compressed 8-wide tree
+  // (cwbvh_build.cu). build_flags picks; PTB_BUILD_DEFAULT follows PTB_BVH=binary|wide, else the measured default.
+  bool wide = PTB_DEFAULT_WIDE != 0;
+  if (const char* e = getenv("PTB_BVH")) wide = strcmp(e, "wide") == 0 ? true : (strcmp(e, "binary") == 0 ? false : wide);
+  if (build_flags & PTB_BUILD_BINARY) wide = false;
+  if (build_flags & PTB_BUILD_WIDE) wide = true;
+  c->cw_max_leaf = 3u;
+  if (const char* e = getenv("PTB_WIDE_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 3) c->cw_max_leaf = (uint32_t)v; }
+  DevBuf &range = c->cw_scratch[8], &final_prim = c->cw_scratch[9];
+  if (wide) {
+    PTB_CUDA_TRY(c, range.reserve(c->n_nodes * 8));
+    PTB_CUDA_TRY(c, final_prim.reserve(n * 4));
+    PTB_CUDA_TRY(c, c->d_prim_sorted.reserve(n * 4));
+  }
   const int T = 256;
   const uint32_t gn = (n32 + T - 1) / T;
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
@@ -639,24 +628,30 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
     c->stats.kernel_launches += 1;
   } else {
     PTB_CUDA_TRY(c, cudaMemsetAsync(flags.p, 0, c->n_nodes * 4, st));
-    k_hierarchy<<<(n32 - 1 + T - 1) / T, T, 0, st>>>(ka, va, n32, ns32, c->d_nodes.as<BvhNode>(), leaf_parent.as<uint32_t>());
+    k_hierarchy<<<(n32 - 1 + T - 1) / T, T, 0, st>>>(ka, va, n32, ns32, c->d_nodes.as<BvhNode>(), leaf_parent.as<uint32_t>(),
+                                                     wide ? range.as<uint2>() : nullptr);
     k_refit<<<gn, T, 0, st>>>(n32, va, leaf_parent.as<uint32_t>(), bmin.as<float4>(), bmax.as<float4>(),
                               c->d_nodes.as<BvhNode>(), nbmin.as<float4>(), nbmax.as<float4>(), flags.as<uint32_t>());
     c->stats.kernel_launches += 2;
   }
-  if (PTB_WIDE_BVH) {
-    PTB_CUDA_TRY(c, c->d_nodes4.reserve(c->n_nodes * sizeof(BvhNode4)));
-    k_collapse4<<<((uint32_t)c->n_nodes + T - 1) / T, T, 0, st>>>(c->d_nodes.as<BvhNode>(), (uint32_t)c->n_nodes, c->d_nodes4.as<BvhNode4>());
-    c->stats.kernel_launches += 1;
+  // slot order of the geometry: Morton order for the binary tree, the wide tree's own primitive order otherwise
+  const uint32_t* slot_order = va;
+  if (wide) {
+    CwBuildInputs bi{c->d_nodes.as<BvhNode>(), range.as<uint2>(), nbmin.as<float4>(), nbmax.as<float4>(), bmin.as<float4>(),
+                     bmax.as<float4>(), va, n32};
+    const int32_t rcw = build_wide(c, bi, final_prim.as<uint32_t>());
+    if (rcw != PTB_OK) return rcw;
+    slot_order = final_prim.as<uint32_t>();
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_prim_sorted.p, va, n * 4, cudaMemcpyDeviceToDevice, st));
   }
-  k_gather<<<gn, T, 0, st>>>(raw_spheres.as<ptb_sphere>(), ns32, raw_tris.as<ptb_triangle>(), n32, va,
+  k_gather<<<gn, T, 0, st>>>(raw_spheres.as<ptb_sphere>(), ns32, raw_tris.as<ptb_triangle>(), n32, slot_order,
                              c->d_materials.as<DevMaterial>(), (uint32_t)c->materials.size(), c->d_geom.as<float4>(),
                              c->d_normals.as<float4>(),
                              c->d_slot_mat.as<uint32_t>(), prim_slot.as<uint32_t>());
   c->stats.kernel_launches += 1;
   // keep the sorted keys / ids for ptb_bvh_export and the traversal's tie-break
   PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_morton.p, ka, n * 4, cudaMemcpyDeviceToDevice, st));
-  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_slot_prim.p, va, n * 4, cudaMemcpyDeviceToDevice, st));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->d_slot_prim.p, slot_order, n * 4, cudaMemcpyDeviceToDevice, st));
   // light list: count + validation flag back to the host (8 bytes), ids sorted with the same radix passes
   PTB_CUDA_TRY(c, cudaMemcpyAsync(h_light_out, d_light_out.p, 8, cudaMemcpyDeviceToHost, st));
   PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
@@ -686,7 +681,9 @@ int32_t build_scene(Ctx* c, uint32_t /*flags*/) {
   c->dev.slot_prim = c->d_slot_prim.as<uint32_t>();
   c->dev.slot_mat = c->d_slot_mat.as<uint32_t>();
   c->dev.nodes = c->d_nodes.as<BvhNode>();
-  c->dev.nodes4 = c->d_nodes4.as<BvhNode4>();
+  c->dev.cw_nodes = wide ? c->d_cw_nodes.as<CwNode>() : nullptr;
+  c->wide = wide;
+  if (!wide) c->n_cw_nodes = 0;
   c->dev.lights = c->d_lights.as<uint32_t>();
   c->dev.n_lights = nl;
   c->committed = true;

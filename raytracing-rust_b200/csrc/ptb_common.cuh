@@ -155,6 +155,38 @@ PTB_HD uint32_t rng_below(uint32_t u, uint32_t n) {
 #endif
 }
 
+// ---------------------------------------------------------------- wide loads / stores
+// 32 bytes per lane in one instruction (LDG.E.256, new on sm_100): incoherent traversal is bound by L1 wavefronts — one
+// per distinct 128-byte line PER LOAD INSTRUCTION (ncu: l1tex throughput 80 % with four 16-byte loads per node) — so a
+// 64-byte node costs two wavefronts instead of four. `p` must be 32-byte aligned.
+PTB_DEV void ldg256(const void* p, float4& a, float4& b) {
+#ifdef PTB_NO_LDG256
+  a = __ldg(reinterpret_cast<const float4*>(p));
+  b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#else
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p));
+#endif
+}
+#ifndef PTB_STREAM_HINTS
+#define PTB_STREAM_HINTS 0  // 1 = path records are loaded / stored with the evict-first (.cs) policy so that they do not displace
+                            // BVH nodes and triangles from L2
+#endif
+#if PTB_STREAM_HINTS
+#define PTB_CS ".cs"
+#else
+#define PTB_CS ""
+#endif
+PTB_DEV void ldg256_rw(const void* p, float4& a, float4& b) {  // same, for data this launch sequence also writes (no .nc)
+  asm volatile("ld.global" PTB_CS ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p) : "memory");
+}
+PTB_DEV void stg256(void* p, float4 a, float4 b) {
+  asm volatile("st.global" PTB_CS ".v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
 // ---------------------------------------------------------------- device scene
 struct __align__(16) BvhNode {  // 64 B, same memory layout as ptb_bvh_node
   float4 n0;  // lmin.x lmin.y lmin.z lmax.x
@@ -163,21 +195,17 @@ struct __align__(16) BvhNode {  // 64 B, same memory layout as ptb_bvh_node
   uint4 n3;   // left, right, parent, pad   (refs: bit31 leaf, bit30 sphere, low bits slot)
 };
 static_assert(sizeof(BvhNode) == 64 && sizeof(ptb_bvh_node) == 64, "node layout");
-// 4-wide node the traversal kernels walk (PTB_WIDE_BVH): the LBVH node of the same index at EVEN depth with its
-// grandchildren (or a child itself where that child is a leaf) as children; odd-depth entries are unused. 128 B =
-// four 32-byte loads: 24 box floats (child k: min.xyz max.xyz at floats [6k, 6k+6)), then the four references
-// (kNone = empty slot, its box is inverted so that it can never be hit).
-struct __align__(32) BvhNode4 {
-  float box[24];
-  uint32_t child[4];
+// Compressed 8-wide node (ptb_cwbvh.cuh has the layout's story; oracle/cwbvh_ref.hpp the CPU definition): 96 bytes.
+struct __align__(32) CwNode {
+  float p[3];            // grid origin = node box min
+  uint32_t e_imask;      // biased cell exponents x | y << 8 | z << 16, imask << 24 (bit s: slot s holds an inner child)
+  uint32_t child_base;   // index of the first inner child
+  uint32_t prim_base;    // first slot of the node's primitives
+  uint32_t meta[2];      // per slot one byte: 0 empty | inner 0x20 | (24 + s) | leaf group (2^count - 1) << 5 | offset
+  uint32_t q[12];        // qlo x, y, z then qhi x, y, z: 8 bytes (slots 0..7) each
   uint32_t pad[4];
 };
-static_assert(sizeof(BvhNode4) == 128, "wide node layout");
-#ifndef PTB_WIDE_BVH
-#define PTB_WIDE_BVH 0  // measured on B200 (profiles/r1_sweeps.md): half the node visits, but k_trace on C3 183 ms vs 160 ms
-                        // for the binary step (same number of slab tests per ray, dearer child ordering, 68 - 74 registers
-                        // wanted); only the 2-sphere scene gains (rtweekend1 4K: 9341 vs 8697 Mrays/s). Off by default.
-#endif
+static_assert(sizeof(CwNode) == 96, "wide node layout");
 
 struct DevMaterial {
   uint32_t kind, tex;
@@ -267,8 +295,8 @@ struct DevScene {
   const float4* normals;      // 3 x float4 per slot (triangles only): n0, n1, n2
   const uint32_t* slot_prim;  // slot -> original primitive id (loader order)
   const uint32_t* slot_mat;   // slot -> (material kind << 24) | material index
-  const BvhNode* nodes;
-  const BvhNode4* nodes4;     // 4-wide collapse of `nodes` (same indices, even-depth entries only)
+  const BvhNode* nodes;       // binary LBVH (leaf references: Morton position; traversed when `cw_nodes` is null)
+  const CwNode* cw_nodes;     // compressed 8-wide tree over the same primitives; geometry is then in ITS primitive order
   const DevMaterial* materials;
   const DevTexture* textures;
   const float* tex_data;      // bulk texture data (image pixels, perlin tables), see DevTexture::data_off

@@ -105,9 +105,12 @@ struct Ctx {
 
   // device scene
   DevScene dev{};
-  DevBuf d_geom, d_normals, d_slot_prim, d_slot_mat, d_nodes, d_nodes4, d_morton, d_materials, d_textures, d_tex_data, d_lights;
+  DevBuf d_geom, d_normals, d_slot_prim, d_slot_mat, d_nodes, d_cw_nodes, d_prim_sorted, d_morton, d_materials, d_textures, d_tex_data, d_lights;
   DevBuf d_sky_ycdf, d_sky_ypdf, d_sky_xcdf, d_sky_xpdf;
-  uint64_t n_prims = 0, n_nodes = 0;
+  uint64_t n_prims = 0, n_nodes = 0, n_cw_nodes = 0;
+  bool wide = false;          // the committed scene is traversed through the compressed 8-wide tree (d_cw_nodes)
+  uint32_t cw_max_leaf = 3;   // primitives per leaf group of the wide tree (1..3)
+  DevBuf cw_scratch[10];      // wide-tree build temporaries, grow-only (cwbvh_build.cu; [8] LBVH ranges, [9] final order)
 
   // render state
   DevBuf d_accum;
@@ -146,6 +149,17 @@ int32_t check_cuda(Ctx* c, cudaError_t e, const char* what);
 
 // lbvh_build.cu — uploads the host scene and builds the device LBVH (K2..K6)
 int32_t build_scene(Ctx* c, uint32_t flags);
+// cwbvh_build.cu — collapses the LBVH into the compressed 8-wide tree; leaves the final primitive order in
+// `final_prim` (final slot -> original primitive id, n words, device)
+struct CwBuildInputs {
+  const BvhNode* nodes;          // LBVH (n - 1 nodes)
+  const uint2* range;            // Morton range [lo, hi] of every LBVH node
+  const float4 *nbmin, *nbmax;   // box of every LBVH node
+  const float4 *bmin, *bmax;     // box of every primitive (original order)
+  const uint32_t* prim_sorted;   // Morton position -> original primitive id
+  uint32_t n_prims;
+};
+int32_t build_wide(Ctx* c, const CwBuildInputs& in, uint32_t* final_prim);
 void radix_sort_pairs(Ctx* c, uint32_t*& ka, uint32_t*& va, uint32_t*& kb, uint32_t*& vb, uint32_t n, int passes, uint32_t* hist);
 size_t radix_sort_hist_words(uint32_t n);
 // wavefront.cu

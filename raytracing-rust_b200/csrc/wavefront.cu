@@ -353,11 +353,10 @@ struct TraceRetire {
   const TraceFetch<CAMERA>& f;
   // called by all 32 lanes: write the hit (the whole 32-byte ray record, so the store is a full sector), then a
   // warp-aggregated push into the per-material-kind shade queue
-  PTB_DEV void operator()(bool fin, const TravState& st, const Ray& ray) {
+  PTB_DEV void operator()(bool fin, const TraceResult& tr, const Ray& ray) {
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t kind = 0xFFu;
     if (fin) {
-      const TraceResult tr = trav_result(st);
       stg256(pool.ray + 4u * (size_t)f.slot, make_float4(ray.o.x, ray.o.y, ray.o.z, tr.t),
              make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(tr.ref)));
       if (!DENSE) kind = tr.ref == kNone ? 0u : 1u + (__ldg(sc.slot_mat + (tr.ref & kSlotMask)) >> 24);
@@ -375,22 +374,19 @@ struct TraceRetire {
   }
 };
 
-#ifndef PTB_TRACE_MIN_BLOCKS
-#define PTB_TRACE_MIN_BLOCKS 6  // 40 registers. Window mode, C3: 4 blocks (64 registers) 3611 Mrays/s, 5 (48) 3664, 6 (40) 3730
-#endif
 #ifndef PTB_SHADE_MIN_BLOCKS
 #define PTB_SHADE_MIN_BLOCKS 4  // caps k_shade at 64 registers (32 B of spills). Window mode streams its records, so occupancy
                                 // pays now: 2 -> 4 blocks: C3 3664 -> 3746 Mrays/s, rtweekend1 4K MIS 8439 -> 8967 (queue mode
                                 // preferred 2: 128 registers, profiles/r1_sweeps.md)
 #endif
-template <bool COUNT, bool DENSE, bool CAMERA>
-__global__ void __launch_bounds__(256, PTB_TRACE_MIN_BLOCKS)
+template <class TR, bool COUNT, bool DENSE, bool CAMERA>
+__global__ void __launch_bounds__(256, TR::kTraceMinBlocks)
 k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, unsigned long long first) {
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t cnt_nodes = 0, cnt_prims = 0, cnt_rays = 0;
   TraceFetch<CAMERA> fetch{pool, q.active[DENSE ? 0u : wc->cur], 0u, sc, rp, first};
   TraceRetire<DENSE, CAMERA> retire{sc, pool, q, wc, fetch};
-  persistent_trace<false, COUNT>(sc, wc->n_trace, &wc->trace_head, fetch, retire, cnt_nodes, cnt_prims, cnt_rays);
+  persistent_trace<TR, false, COUNT>(sc, wc->n_trace, &wc->trace_head, fetch, retire, cnt_nodes, cnt_prims, cnt_rays);
   if (COUNT) {
     for (int off = 16; off > 0; off >>= 1) {
       cnt_nodes += __shfl_xor_sync(0xffffffffu, cnt_nodes, off);
@@ -1145,8 +1141,8 @@ struct ShadowFetch {
 struct ShadowRetire {
   const PathPool& pool;
   const ShadowFetch& f;
-  PTB_DEV void operator()(bool fin, const TravState& st, const Ray&) {
-    if (fin && st.best_ref == kNone) {  // unoccluded
+  PTB_DEV void operator()(bool fin, const TraceResult& tr, const Ray&) {
+    if (fin && tr.ref == kNone) {  // unoccluded
       const uint32_t slot = __float_as_uint(f.contrib.w);
       float4 ra = pool.col[4u * (size_t)slot + 1u];
       ra.x += f.contrib.x; ra.y += f.contrib.y; ra.z += f.contrib.z;  // output += throughput*eval*mis*le/l_pdf (mis.rs:42)
@@ -1159,14 +1155,12 @@ struct ShadowRetire {
 #ifndef PTB_SHADOW_MIN_BLOCKS
 #define PTB_SHADOW_MIN_BLOCKS 1
 #endif
-#ifndef PTB_API_MIN_BLOCKS
-#define PTB_API_MIN_BLOCKS 6
-#endif
+template <class TR>
 __global__ void __launch_bounds__(256, PTB_SHADOW_MIN_BLOCKS) k_shadow(DevScene sc, PathPool pool, Queues q, WaveCounters* wc) {
   uint32_t a = 0, b = 0, r = 0;
   ShadowFetch fetch{q, make_float4(0.f, 0.f, 0.f, 0.f)};
   ShadowRetire retire{pool, fetch};
-  persistent_trace<true, false>(sc, (uint32_t)wc->shadow_pair, &wc->shadow_head, fetch, retire, a, b, r);
+  persistent_trace<TR, true, false>(sc, (uint32_t)wc->shadow_pair, &wc->shadow_head, fetch, retire, a, b, r);
 }
 
 // ------------------------------------------------------------------------------------------ fused tail
@@ -1176,40 +1170,18 @@ __global__ void __launch_bounds__(256, PTB_SHADOW_MIN_BLOCKS) k_shadow(DevScene 
 // so nothing synchronises; the launch is latency bound (one traversal after the other per lane) and runs on a side stream
 // underneath the next chunk's wide iterations. Same functions, same records, same RNG counters as the wavefront: the image
 // does not depend on where the hand-over happens (tests: PTB_TAIL_PATHS=0 disables it).
-template <bool ANYHIT>
-PTB_DEV TravState trace_lane(const DevScene& sc, const Ray& ray, float tmax, uint32_t exclude, uint2* stack_local) {
-  const TravStack stack{stack_local, nullptr};
-  static_assert(kSharedStack == 0, "trace_lane walks the local-memory stack");
-  uint2 lq[kLeafQueue];
-  TravState st;
-  trav_init(st, sc.n_prims, tmax);
-  const SlabRay slab = make_slab_ray(ray);
-  uint32_t unused = 0;
-  while (!st.done()) {
-    if (!(st.cur & PTB_LEAF_BIT)) {
-#if PTB_WIDE_BVH
-      trav_node_step4<false>(sc, slab, st, stack, lq, unused);
-#else
-      trav_node_step<false>(sc, slab, ray, st, stack, lq, unused);
-#endif
-    } else {
-      trav_prim_step<ANYHIT, false>(sc, ray, st, stack, lq, exclude, unused);
-    }
-  }
-  return st;
-}
 PTB_DEV unsigned long long global_timer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-template <int METHOD, bool FULL>
+template <class TR, int METHOD, bool FULL>
 __global__ void __launch_bounds__(128)
 k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum) {
   if (wc->mode != 1u) return;      // launched after every iteration >= 2; only the hand-over iteration has work
   const uint32_t n = wc->n_tail;   // live paths, listed in q.active[0] by k_win_fill
   if (threadIdx.x == 0u) atomicMin(&wc->tail_t0, global_timer_ns());
-  uint2 stack_local[kStackDepth];
+  typename TR::Scratch scratch;
   unsigned long long c_bounce = 0, c_sky = 0, c_light = 0, c_ref = 0, c_paths = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t slot = q.active[0][i];
@@ -1218,7 +1190,7 @@ k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, 
       float4 o4, d4;
       ldg256_rw(pool.ray + 4u * (size_t)slot, o4, d4);
       const Ray ray = make_ray(from4(o4), from4(d4));
-      const TraceResult tr = trav_result(trace_lane<false>(sc, ray, __int_as_float(0x7f800000), kNone, stack_local));
+      const TraceResult tr = trace_lane<TR, false>(sc, ray, __int_as_float(0x7f800000), kNone, scratch);
       stg256(pool.ray + 4u * (size_t)slot, make_float4(ray.o.x, ray.o.y, ray.o.z, tr.t),
              make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(tr.ref)));
       ++c_bounce;
@@ -1232,8 +1204,8 @@ k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, 
       if (METHOD == PTB_METHOD_MIS && so.shadow) {
         if (so.shadow_is_sky) ++c_sky; else ++c_light;
         const Ray sray = make_ray(from4(so.sh_o), from4(so.sh_d));
-        const TravState ss = trace_lane<true>(sc, sray, so.sh_o.w, __float_as_uint(so.sh_d.w), stack_local);
-        if (ss.best_ref == kNone) {
+        const TraceResult ss = trace_lane<TR, true>(sc, sray, so.sh_o.w, __float_as_uint(so.sh_d.w), scratch);
+        if (ss.ref == kNone) {
           float4 ra = pool.col[4u * (size_t)slot + 1u];
           ra.x += so.sh_c.x; ra.y += so.sh_c.y; ra.z += so.sh_c.z;
           pool.col[4u * (size_t)slot + 1u] = ra;
@@ -1327,9 +1299,8 @@ struct ApiRetire {
   const DevScene& sc;
   uint4* __restrict__ hits;
   const ApiFetch& f;
-  PTB_DEV void operator()(bool fin, const TravState& st, const Ray&) {
+  PTB_DEV void operator()(bool fin, const TraceResult& tr, const Ray&) {
     if (!fin) return;
-    const TraceResult tr = trav_result(st);
     uint4 out = make_uint4(__float_as_uint(0.0f), PTB_MISS, 0u, 0u);
     if (tr.ref != kNone) {
       HitRec h;
@@ -1340,15 +1311,15 @@ struct ApiRetire {
     hits[f.idx] = out;
   }
 };
-template <bool COUNT>
-__global__ void __launch_bounds__(256, PTB_API_MIN_BLOCKS)
+template <class TR, bool COUNT>
+__global__ void __launch_bounds__(256, TR::kApiMinBlocks)
 k_closest_hit_api(DevScene sc, const float4* __restrict__ rays, const uint32_t* __restrict__ order, uint32_t n,
                   uint4* __restrict__ hits, uint32_t* head, unsigned long long* counts) {
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t cnt_nodes = 0, cnt_prims = 0, cnt_rays = 0;
   ApiFetch fetch{rays, order, 0u, Ray()};
   ApiRetire retire{sc, hits, fetch};
-  persistent_trace<false, COUNT>(sc, n, head, fetch, retire, cnt_nodes, cnt_prims, cnt_rays);
+  persistent_trace<TR, false, COUNT>(sc, n, head, fetch, retire, cnt_nodes, cnt_prims, cnt_rays);
   if (COUNT) {
     for (int off = 16; off > 0; off >>= 1) {
       cnt_nodes += __shfl_xor_sync(0xffffffffu, cnt_nodes, off);
@@ -1454,6 +1425,37 @@ int32_t sampler_hook(Ctx* c, const ptb_sampler_query& q, size_t n, const float* 
   return PTB_OK;
 }
 
+// ---- kernel tables: every persistent traversal kernel exists once per tree (BinTrav / CwTrav)
+template <class TR>
+static const void* trace_kernel_of(bool count, bool dense, bool camera) {
+  if (!dense) return count ? (const void*)k_trace<TR, true, false, false> : (const void*)k_trace<TR, false, false, false>;
+  if (camera) return count ? (const void*)k_trace<TR, true, true, true> : (const void*)k_trace<TR, false, true, true>;
+  return count ? (const void*)k_trace<TR, true, true, false> : (const void*)k_trace<TR, false, true, false>;
+}
+static const void* trace_kernel(const Ctx* c, bool count, bool dense, bool camera) {
+  return c->wide ? trace_kernel_of<CwTrav>(count, dense, camera) : trace_kernel_of<BinTrav>(count, dense, camera);
+}
+static const void* shadow_kernel(const Ctx* c) { return c->wide ? (const void*)k_shadow<CwTrav> : (const void*)k_shadow<BinTrav>; }
+static const void* api_kernel(const Ctx* c, bool count) {
+  if (c->wide) return count ? (const void*)k_closest_hit_api<CwTrav, true> : (const void*)k_closest_hit_api<CwTrav, false>;
+  return count ? (const void*)k_closest_hit_api<BinTrav, true> : (const void*)k_closest_hit_api<BinTrav, false>;
+}
+template <class TR>
+static const void* tail_kernel_of(bool mis, bool full) {
+  if (mis) return full ? (const void*)k_tail<TR, PTB_METHOD_MIS, true> : (const void*)k_tail<TR, PTB_METHOD_MIS, false>;
+  return full ? (const void*)k_tail<TR, PTB_METHOD_NAIVE, true> : (const void*)k_tail<TR, PTB_METHOD_NAIVE, false>;
+}
+static cudaError_t launch_trace(const void* fn, int grid, cudaStream_t st, const DevScene& sc, const PathPool& pool, const Queues& q,
+                                WaveCounters* wc, const RenderParams& rp, unsigned long long first) {
+  void* args[] = {(void*)&sc, (void*)&pool, (void*)&q, (void*)&wc, (void*)&rp, (void*)&first};
+  return cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, 0, st);
+}
+static cudaError_t launch_shadow(const void* fn, int grid, cudaStream_t st, const DevScene& sc, const PathPool& pool, const Queues& q,
+                                 WaveCounters* wc) {
+  void* args[] = {(void*)&sc, (void*)&pool, (void*)&q, (void*)&wc};
+  return cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, 0, st);
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static int persistent_grid(Ctx* c, const void* kernel, int threads) {
   int per_sm = 0;
@@ -1486,18 +1488,20 @@ int32_t launch_closest_hit(Ctx* c, const void* d_rays, size_t n, void* d_hits) {
     radix_sort_pairs(c, ka, va, kb, vb, n32, 3, hist);
     order = va;
   }
+  {
+    const void* fn = api_kernel(c, c->opt_count_traversal);
+    const int grid = persistent_grid(c, fn, 256);
+    uint32_t n32 = (uint32_t)n;
+    void* args[] = {(void*)&c->dev, (void*)&r4, (void*)&order, (void*)&n32, (void*)&h4, (void*)&head, (void*)&counts};
+    PTB_CUDA_TRY(c, cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(256), args, 0, c->stream));
+  }
   if (c->opt_count_traversal) {
-    const int grid = persistent_grid(c, (const void*)k_closest_hit_api<true>, 256);
-    k_closest_hit_api<true><<<grid, 256, 0, c->stream>>>(c->dev, r4, order, (uint32_t)n, h4, head, counts);
     unsigned long long hc[2] = {0, 0};
     PTB_CUDA_TRY(c, cudaMemcpyAsync(hc, counts, 16, cudaMemcpyDeviceToHost, c->stream));
     PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->stats.nodes_fetched += hc[0];
     c->stats.prims_tested += hc[1];
     c->stats.rays_counted += n;
-  } else {
-    const int grid = persistent_grid(c, (const void*)k_closest_hit_api<false>, 256);
-    k_closest_hit_api<false><<<grid, 256, 0, c->stream>>>(c->dev, r4, order, (uint32_t)n, h4, head, counts);
   }
   c->stats.kernel_launches += 1;
   c->stats.trace_launches += 1;
@@ -1766,13 +1770,11 @@ static void launch_shade(const RenderSetup& rs, Ctx* c, const SlotRefs& sl, uint
   }
 }
 static void launch_tail(const RenderSetup& rs, Ctx* c, const SlotRefs& sl, uint32_t grid, cudaStream_t st) {
-  if (rs.mis) {
-    if (rs.full) k_tail<PTB_METHOD_MIS, true><<<grid, 128, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum);
-    else k_tail<PTB_METHOD_MIS, false><<<grid, 128, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum);
-  } else {
-    if (rs.full) k_tail<PTB_METHOD_NAIVE, true><<<grid, 128, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum);
-    else k_tail<PTB_METHOD_NAIVE, false><<<grid, 128, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum);
-  }
+  const void* fn = c->wide ? tail_kernel_of<CwTrav>(rs.mis, rs.full) : tail_kernel_of<BinTrav>(rs.mis, rs.full);
+  WaveCounters* wc = sl.wc;
+  float* accum = rs.accum;
+  void* args[] = {(void*)&c->dev, (void*)&sl.pool, (void*)&sl.q, (void*)&wc, (void*)&rs.rp, (void*)&accum};
+  cudaLaunchKernel(fn, dim3(grid), dim3(128), args, 0, st);
 }
 template <bool DENSE>
 static const void* shade_fn(const RenderSetup& rs) {
@@ -1803,9 +1805,12 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   if (const char* e = getenv("PTB_SHADE_THREADS")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) TS = v; }
   uint32_t grid_shade = (uint32_t)persistent_grid(c, shade_fn<true>(rs), TS);
   if (grid_shade > (P + TS - 1) / TS) grid_shade = (P + TS - 1) / TS;
-  const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true, true, false> : (const void*)k_trace<false, true, false>, T);
-  const int grid_trace_cam = persistent_grid(c, count ? (const void*)k_trace<true, true, true> : (const void*)k_trace<false, true, true>, T);
-  const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
+  const void* fn_trace = trace_kernel(c, count, true, false);
+  const void* fn_trace_cam = trace_kernel(c, count, true, true);
+  const void* fn_shadow = shadow_kernel(c);
+  const int grid_trace = persistent_grid(c, fn_trace, T);
+  const int grid_trace_cam = persistent_grid(c, fn_trace_cam, T);
+  const int grid_shadow = persistent_grid(c, fn_shadow, T);
   int cam_fetch = c->dev.trace_fetch_threshold < 4 ? c->dev.trace_fetch_threshold : 4;
   if (const char* e = getenv("PTB_TRACE_FETCH_CAMERA")) { int v = atoi(e); if (v >= 1 && v <= 32) cam_fetch = v; }
   // hand-over point: live paths of a chunk at or below which the fused tail takes it (0: never; the traversal statistics
@@ -1896,11 +1901,9 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
         // (C3, camera rays only: threshold 8 -> 8105 Mrays/s, 4 -> 8311; bounce rays prefer 8, profiles/r1_sweeps.md)
         DevScene cam = c->dev;
         cam.trace_fetch_threshold = cam_fetch;
-        if (count) k_trace<true, true, true><<<grid_trace_cam, T, 0, st>>>(cam, S.pool, q, wc, rs.rp, first);
-        else k_trace<false, true, true><<<grid_trace_cam, T, 0, st>>>(cam, S.pool, q, wc, rs.rp, first);
+        PTB_CUDA_TRY(c, launch_trace(fn_trace_cam, grid_trace_cam, st, cam, S.pool, q, wc, rs.rp, first));
       } else {
-        if (count) k_trace<true, true, false><<<grid_trace, T, 0, st>>>(c->dev, S.pool, q, wc, rs.rp, 0ull);
-        else k_trace<false, true, false><<<grid_trace, T, 0, st>>>(c->dev, S.pool, q, wc, rs.rp, 0ull);
+        PTB_CUDA_TRY(c, launch_trace(fn_trace, grid_trace, st, c->dev, S.pool, q, wc, rs.rp, 0ull));
       }
       PTB_PROF(1, 1);
       PTB_PROF(2, 0);
@@ -1910,7 +1913,7 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
       c->stats.trace_launches += 1;
       if (mis) {
         PTB_PROF(3, 0);
-        k_shadow<<<grid_shadow, T, 0, st>>>(c->dev, S.pool, q, wc);
+        PTB_CUDA_TRY(c, launch_shadow(fn_shadow, grid_shadow, st, c->dev, S.pool, q, wc));
         PTB_PROF(3, 1);
         c->stats.kernel_launches += 1;
       }
@@ -1972,8 +1975,10 @@ static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderS
   if (const char* e = getenv("PTB_SHADE_THREADS")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) TS = v; }
   uint32_t grid_shade = (uint32_t)persistent_grid(c, shade_fn<false>(rs), TS);
   if (grid_shade > (P + TS - 1) / TS) grid_shade = (P + TS - 1) / TS;
-  const int grid_trace = persistent_grid(c, count ? (const void*)k_trace<true, false, false> : (const void*)k_trace<false, false, false>, T);
-  const int grid_shadow = persistent_grid(c, (const void*)k_shadow, T);
+  const void* fn_trace = trace_kernel(c, count, false, false);
+  const void* fn_shadow = shadow_kernel(c);
+  const int grid_trace = persistent_grid(c, fn_trace, T);
+  const int grid_shadow = persistent_grid(c, fn_shadow, T);
 
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
   k_init_pool<<<grid_p, T, 0, st>>>(q.free_slots, P, wc, total);
@@ -1992,8 +1997,7 @@ static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderS
     PTB_PROF(0, 1);
     k_advance<<<1, 1, 0, st>>>(wc);
     PTB_PROF(1, 0);
-    if (count) k_trace<true, false, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc, rp, 0ull);
-    else k_trace<false, false, false><<<grid_trace, T, 0, st>>>(c->dev, c->pool, q, wc, rp, 0ull);
+    PTB_CUDA_TRY(c, launch_trace(fn_trace, grid_trace, st, c->dev, c->pool, q, wc, rp, 0ull));
     PTB_PROF(1, 1);
     PTB_PROF(2, 0);
     launch_shade<false>(rs, c, SlotRefs{c->pool, q, wc}, grid_shade, TS, st);
@@ -2002,7 +2006,7 @@ static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderS
     c->stats.trace_launches += 1;
     if (mis) {
       PTB_PROF(3, 0);
-      k_shadow<<<grid_shadow, T, 0, st>>>(c->dev, c->pool, q, wc);
+      PTB_CUDA_TRY(c, launch_shadow(fn_shadow, grid_shadow, st, c->dev, c->pool, q, wc));
       PTB_PROF(3, 1);
       c->stats.kernel_launches += 1;
     }

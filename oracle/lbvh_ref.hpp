@@ -222,105 +222,6 @@ struct Lbvh {
     }
     return best_prim != PTB_MISS;
   }
-
-  // ---- 4-wide collapse (the tree the device traverses when built with the wide nodes): every LBVH node at EVEN depth
-  // becomes a wide node whose children are its grandchildren (or a child itself where that child is a leaf); the node's
-  // index is kept, odd-depth nodes drop out. A child slot is (reference, box); empty slots hold kWideEmpty.
-  static constexpr uint32_t kWideEmpty = 0xFFFFFFFFu;
-  struct WideNode {
-    float mn[4][3], mx[4][3];
-    uint32_t child[4];
-  };
-  std::vector<WideNode> wide;  // indexed like `nodes`; entries of odd-depth nodes are unused
-  void build_wide() {
-    wide.assign(nodes.size(), WideNode{});
-    if (nodes.empty()) return;
-    std::vector<uint32_t> todo{0};
-    while (!todo.empty()) {
-      const uint32_t i = todo.back();
-      todo.pop_back();
-      WideNode& w = wide[i];
-      int k = 0;
-      auto put = [&](uint32_t ref, const float* mn, const float* mx) {
-        for (int a = 0; a < 3; ++a) { w.mn[k][a] = mn[a]; w.mx[k][a] = mx[a]; }
-        w.child[k++] = ref;
-        if (!(ref & PTB_LEAF_BIT)) todo.push_back(ref);
-      };
-      const ptb_bvh_node& nd = nodes[i];
-      const uint32_t side[2] = {nd.left, nd.right};
-      const float* smn[2] = {nd.lmin, nd.rmin};
-      const float* smx[2] = {nd.lmax, nd.rmax};
-      for (int c = 0; c < 2; ++c) {
-        if (side[c] & PTB_LEAF_BIT) { put(side[c], smn[c], smx[c]); continue; }
-        const ptb_bvh_node& ch = nodes[side[c]];
-        put(ch.left, ch.lmin, ch.lmax);
-        put(ch.right, ch.rmin, ch.rmax);
-      }
-      for (; k < 4; ++k) {
-        for (int a = 0; a < 3; ++a) { w.mn[k][a] = INF_F; w.mx[k][a] = -INF_F; }
-        w.child[k] = kWideEmpty;
-      }
-    }
-  }
-  // Ordered, t-culled closest hit over the wide nodes: the hit children of a node are visited by ascending cull key
-  // (ties: lower slot first), the others wait on the stack, nearest on top, and are re-culled when popped.
-  bool closest_hit_wide(const Ray& ray, Hit& best, uint32_t& best_prim, uint64_t* nodes_fetched, uint64_t* prims_tested) const {
-    best_prim = PTB_MISS;
-    if (nodes.empty()) return false;
-    Float best_t = INF_F;
-    const SlabRay slab = make_slab_ray(ray);
-    uint32_t stack[192];
-    Float stack_t[192];
-    int sp = 0;
-    uint32_t cur = 0;
-    Hit h;
-    auto pop = [&](uint32_t& out) -> bool {
-      while (sp > 0) {
-        --sp;
-        if (stack_t[sp] <= best_t) { out = stack[sp]; return true; }
-      }
-      return false;
-    };
-    for (;;) {
-      if (cur & PTB_LEAF_BIT) {
-        uint32_t slot = cur & ~PTB_LEAF_BIT;
-        uint32_t pid = prim_sorted[slot];
-        if (prims_tested) ++*prims_tested;
-        if (prims[pid].get_int(ray, h) && h.t > 0.0f) {
-          if (h.t < best_t || (h.t == best_t && pid < best_prim)) { best_t = h.t; best = h; best_prim = pid; }
-        }
-        if (!pop(cur)) break;
-        continue;
-      }
-      const WideNode& w = wide[cur];
-      if (nodes_fetched) ++*nodes_fetched;
-      Float key[4];
-      bool hit[4];
-      int n_hit = 0;
-      for (int k = 0; k < 4; ++k) {
-        hit[k] = w.child[k] != kWideEmpty && box_hit(w.mn[k], w.mx[k], slab, best_t, key[k]);
-        n_hit += hit[k];
-      }
-      if (n_hit == 0) {
-        if (!pop(cur)) break;
-        continue;
-      }
-      int rank[4];
-      for (int k = 0; k < 4; ++k) {
-        rank[k] = 0;
-        if (!hit[k]) continue;
-        for (int j = 0; j < 4; ++j)
-          if (hit[j] && (key[j] < key[k] || (key[j] == key[k] && j < k))) ++rank[k];
-      }
-      for (int k = 0; k < 4; ++k) {
-        if (!hit[k]) continue;
-        if (rank[k] == 0) cur = w.child[k];
-        else { stack[sp + n_hit - 1 - rank[k]] = w.child[k]; stack_t[sp + n_hit - 1 - rank[k]] = key[k]; }
-      }
-      sp += n_hit - 1;
-    }
-    return best_prim != PTB_MISS;
-  }
 };
 
 }  // namespace ref

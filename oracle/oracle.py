@@ -62,7 +62,6 @@ def _load():
     lib.orc_lbvh_export.argtypes = [P, P, P, P]
     lib.orc_lbvh_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_lbvh_node_counts.argtypes = [P, P, C.c_size_t, P, C.c_int]
-    lib.orc_lbvh_wide_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_cw_build.restype = C.c_size_t
     lib.orc_cw_build.argtypes = [P, C.c_int]
     lib.orc_cw_export.argtypes = [P, P, P]
@@ -269,16 +268,6 @@ class OracleScene:
         lib.orc_lbvh_closest_hit(self._h, _p(rays), len(rays), _p(out), threads, _p(counts))
         return out, int(counts[0]), int(counts[1])
 
-
-    def lbvh_wide_closest_hit(self, rays, threads=0):
-        """Same over the 4-wide collapse of the LBVH: (hits, wide nodes fetched, prims tested)."""
-        if not self._lbvh:
-            self.lbvh_build()
-        rays = np.ascontiguousarray(rays, dtype=ray_dtype)
-        out = np.zeros(len(rays), hit_dtype)
-        counts = np.zeros(2, np.uint64)
-        lib.orc_lbvh_wide_closest_hit(self._h, _p(rays), len(rays), _p(out), threads, _p(counts))
-        return out, int(counts[0]), int(counts[1])
 
     # -- compressed 8-wide BVH oracle (cwbvh_ref.hpp)
     def cw_build(self, max_leaf=3):

@@ -379,26 +379,6 @@ void orc_cw_closest_hit(const orc_scene* s, const ptb_ray* rays, size_t n, ptb_h
   }
 }
 
-// same over the 4-wide collapse of the LBVH (counts2: wide nodes fetched, primitives tested)
-void orc_lbvh_wide_closest_hit(orc_scene* s, const ptb_ray* rays, size_t n, ptb_hit* out, int threads, uint64_t* counts2) {
-  if (s->lbvh.wide.size() != s->lbvh.nodes.size()) s->lbvh.build_wide();
-  unsigned nt = threads > 0 ? (unsigned)threads : std::thread::hardware_concurrency();
-  std::vector<uint64_t> nv(nt ? nt : 1, 0), pt(nt ? nt : 1, 0);
-  parallel_for(n, threads, [&](unsigned tid, size_t b, size_t e) {
-    for (size_t i = b; i < e; ++i) {
-      Ray ray(Vec3(rays[i].ox, rays[i].oy, rays[i].oz), Vec3(rays[i].dx, rays[i].dy, rays[i].dz), 0.0f);
-      Hit h;
-      uint32_t prim;
-      bool have = s->lbvh.closest_hit_wide(ray, h, prim, &nv[tid], &pt[tid]);
-      fill_hit(out[i], have, h, prim);
-    }
-  });
-  if (counts2) {
-    counts2[0] = counts2[1] = 0;
-    for (size_t i = 0; i < nv.size(); ++i) { counts2[0] += nv[i]; counts2[1] += pt[i]; }
-  }
-}
-
 // Ordered, t-culled traversal of the REFERENCE's SAH tree (not something the reference does — it is BFS un-culled):
 // measures how many 2-child node fetches a SAH-quality tree would need for the same rays, to judge LBVH quality.
 // counts2: internal nodes expanded, primitives tested.

@@ -289,20 +289,33 @@ def test_sah_builder_shape(ptb, orc, overshadowed):
         assert np.array_equal(o2.closest_hit(rays)["t"], o.closest_hit(rays)["t"])
 
 
-def test_wide_collapse_traversal_returns_the_same_hits(orc):
-    """oracle/lbvh_ref.hpp build_wide / closest_hit_wide (the CPU definition of the optional 4-wide device traversal,
-    -DPTB_WIDE_BVH=1): same closest hits as the binary ordered traversal, about half the node visits."""
-    import importlib
-    import numpy as np
-    mg = importlib.import_module("raytracing-rust_b200.meshgen")
-    s = mg.c3_scene(0.05)
-    o = orc.OracleScene(s, split_type=-1)
-    rays = mg.philox_rays(20000, seed=7, centre=(0.0, 4.0, 1.0), radius=5.0)
-    h2, v2, t2 = o.lbvh_closest_hit(rays)
-    h4, v4, t4 = o.lbvh_wide_closest_hit(rays)
-    assert np.array_equal(h2["prim"], h4["prim"]) and np.array_equal(h2["t"].view(np.uint32), h4["t"].view(np.uint32))
-    assert 0.4 * v2 < v4 < 0.65 * v2
-    assert abs(t4 - t2) <= 0.02 * t2
+@pytest.mark.parametrize("max_leaf", [1, 2, 3])
+def test_compressed_wide_bvh_definition(ptb, orc, rtweekend1, overshadowed, max_leaf):
+    """oracle/cwbvh_ref.hpp — the CPU definition of the compressed 8-wide tree the device builds and walks: whatever the
+    leaf size, its octant-ordered traversal returns exactly the hits of the LBVH traversal, of the reference-semantics SAH
+    oracle and of the brute-force loop over all primitives; node layout invariants hold."""
+    for scene, centre, radius in ((rtweekend1, (0, 1, 0), 3.0), (overshadowed, (-0.3, 0.3, -0.3), 1.5),
+                                  (ptb.meshgen.c3_scene(0.1), (0, 4, 1), 5.0)):
+        rays = ptb.meshgen.philox_rays(40_000, seed=61, centre=centre, radius=radius)
+        o = orc.OracleScene(scene)
+        n = o.cw_build(max_leaf)
+        cw, nv, pt = o.cw_closest_hit(rays)
+        lb, lnv, _ = o.lbvh_closest_hit(rays)
+        assert np.array_equal(cw, lb)
+        br = o.closest_hit_brute(rays)
+        tie = (cw["prim"] != br["prim"]) & (cw["t"] == br["t"])
+        assert np.array_equal(cw["prim"][~tie], br["prim"][~tie]) and np.array_equal(cw["t"].view(np.uint32), br["t"].view(np.uint32))
+        if scene.n_primitives > 1000:
+            assert nv < 0.6 * lnv                                   # a mesh: well under the binary walk's node fetches
+        nodes, slot_prim = o.cw_export()
+        assert nodes.shape == (n, 96) and sorted(slot_prim.tolist()) == list(range(scene.n_primitives))
+        meta = nodes[:, 24:32]
+        imask = nodes[:, 15]
+        inner = (meta & 0x18) == 0x18
+        assert np.array_equal(np.packbits(inner, axis=1, bitorder="little")[:, 0], imask)
+        assert inner.sum() == n - 1                                  # every node but the root is some node's inner child
+        leaf_counts = np.where(inner, 0, np.array([0, 1, 0, 2, 0, 0, 0, 3])[meta >> 5])
+        assert leaf_counts.max() <= max_leaf and leaf_counts.sum() == scene.n_primitives
 
 
 # ---- independent f64 intersector (SURVEY.md §8c: "an f64 brute-force intersector" as cross-check of the restatement)

@@ -66,7 +66,7 @@ struct WaveCounters {  // lives in device memory; mirrored to pinned host memory
   // enqueues the next: 0 wavefront iterations running, 1 this iteration hands the chunk's last n_tail paths to k_tail,
   // 2 chunk finished, 3 handed over earlier — in every state but 0 the wavefront kernels find n_trace == 0 and return
   uint32_t mode;
-  uint32_t n_tail, _pad;
+  uint32_t n_tail, tail_iter;  // set ONCE per chunk: live paths handed over, and the iteration whose k_tail launch takes them
   // k_shade's queue cursors, packed so that one warp needs ONE returning atomic per pair (the kernel used to spend 40 % of
   // its stall samples waiting for three serial same-address atomics): push_pair = finished-slot cursor << 32 | next-active
   // cursor, shadow_pair = sky NEE rays << 32 | shadow-queue cursor. k_prepare unpacks them between iterations.

@@ -125,7 +125,9 @@ PTB_DEV v3 sky_sample(const DevScene& sc, float r_row, float r_col, float r_u, f
   const float v = next_float((float)vi + r_v) / (float)sc.sky_ry;
   const float phi = u * 2.0f * kPi;
   const float theta = v * kPi;
-  const float st = sinf(theta), ct = cosf(theta), sp = sinf(phi), cp = cosf(phi);
+  float st, ct, sp, cp;  // sincosf: one range reduction for both; same values as sinf / cosf
+  sincosf(theta, &st, &ct);
+  sincosf(phi, &sp, &cp);
   return mk(st * cp, st * sp, ct);
 }
 
@@ -143,7 +145,9 @@ PTB_DEV v3 light_sample_dir(const DevScene& sc, uint32_t ref, v3 in_point, float
       const float z = 1.0f - 2.0f * r1;
       const float a = sqrtf(fmaxf(1.0f - z * z, 0.0f));
       const float b = 2.0f * kPi * r2;
-      point = center + radius * mk(a * cosf(b), a * sinf(b), z);
+      float sb, cb;
+      sincosf(b, &sb, &cb);
+      point = center + radius * mk(a * cb, a * sb, z);
     } else {
       const float distance = sqrtf(distance_sq);
       const float sin_theta_max_sq = radius * radius / distance_sq;
@@ -154,7 +158,9 @@ PTB_DEV v3 light_sample_dir(const DevScene& sc, uint32_t ref, v3 in_point, float
       const float ds = distance * cos_theta - sqrtf(fmaxf(radius * radius - distance_sq * sin_theta * sin_theta, 0.0f));
       const float cos_alpha = (distance_sq + radius * radius - ds * ds) / (2.0f * distance * radius);
       const float sin_alpha = sqrtf(fmaxf(1.0f - cos_alpha * cos_alpha, 0.0f));
-      const v3 vec = onb_to_world(normalised(in_point - center), mk(sin_alpha * cosf(phi), sin_alpha * sinf(phi), cos_alpha));
+      float sphi, cphi;
+      sincosf(phi, &sphi, &cphi);
+      const v3 vec = onb_to_world(normalised(in_point - center), mk(sin_alpha * cphi, sin_alpha * sphi, cos_alpha));
       point = center + radius * vec;
     }
   } else {
@@ -196,7 +202,9 @@ PTB_DEV v3 lambertian_sample_dir(v3 normal, float r1, float r2) {
   const float cos_theta = sqrtf(1.0f - r1);
   const float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
   const float phi = 2.0f * kPi * r2;
-  return onb_to_world(normal, mk(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cos_theta));
+  float sphi, cphi;
+  sincosf(phi, &sphi, &cphi);
+  return onb_to_world(normal, mk(cphi * sin_theta, sphi * sin_theta, cos_theta));
 }
 // random_unit_vector (utility/mod.rs:15-25) is a rejection loop whose result is uniform on the sphere — drawn directly here
 // from two uniforms (fixed RNG budget), same distribution
@@ -204,7 +212,9 @@ PTB_DEV v3 uniform_sphere_dir(float r1, float r2) {
   const float z = 1.0f - 2.0f * r1;
   const float rr = sqrtf(fmaxf(1.0f - z * z, 0.0f));
   const float phi = 2.0f * kPi * r2;
-  return mk(rr * cosf(phi), rr * sinf(phi), z);
+  float sphi, cphi;
+  sincosf(phi, &sphi, &cphi);
+  return mk(rr * cphi, rr * sphi, z);
 }
 
 // ------------------------------------------------------------------------------------------ bookkeeping kernels
@@ -465,8 +475,10 @@ __device__ __noinline__ v3 tr_sample(float a, v3 incoming, v3 normal, float u1, 
   const v3 b3 = cross(vh, b2);
   const float r = sqrtf(u1);
   const float phi = kTau * u2;
-  const float tx = r * cosf(phi);
-  float ty = r * sinf(phi);
+  float sphi, cphi;
+  sincosf(phi, &sphi, &cphi);
+  const float tx = r * cphi;
+  float ty = r * sphi;
   const float sh = 0.5f * (1.0f + vh.z);
   ty = (1.0f - sh) * sqrtf(1.0f - tx * tx) + sh * ty;
   const v3 hh = tx * b2 + ty * b3 + sqrtf(fmaxf(1.0f - tx * tx - ty * ty, 0.0f)) * vh;
@@ -958,7 +970,7 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
 __global__ void __launch_bounds__(256) k_win_init(Queues q, WaveCounters* wc, uint32_t n_paths) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w == 0u) {
-    wc->mode = 0u; wc->n_tail = 0u; wc->n_trace = 0u;
+    wc->mode = 0u; wc->n_tail = 0u; wc->tail_iter = 0xFFFFFFFFu; wc->n_trace = 0u;
     if (wc->tail_t0 != ~0ull && wc->tail_t1 > wc->tail_t0) wc->tail_ns += wc->tail_t1 - wc->tail_t0;  // the slot's previous hand-over
     wc->tail_t0 = ~0ull;
     wc->tail_t1 = 0ull;
@@ -1030,10 +1042,9 @@ __global__ void k_win_prepare(WaveCounters* wc, Queues q, uint32_t n_segments, u
   }
   if (mode == 0u) {
     if (total == 0u) mode = 2u;
-    else if (depth >= 2u && total <= tail_paths) { mode = 1u; wc->n_tail = total; }
+    else if (depth >= 2u && total <= tail_paths) { mode = 1u; wc->n_tail = total; wc->tail_iter = depth; }
   } else if (mode == 1u) {
-    mode = 3u;
-    wc->n_tail = 0u;
+    mode = 3u;  // n_tail / tail_iter stay: the k_tail launch of the hand-over iteration may not have started yet
   }
   wc->mode = mode;
   wc->n_trace = mode == 0u ? total : 0u;
@@ -1177,8 +1188,8 @@ PTB_DEV unsigned long long global_timer_ns() {
 }
 template <class TR, int METHOD, bool FULL>
 __global__ void __launch_bounds__(128)
-k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum) {
-  if (wc->mode != 1u) return;      // launched after every iteration >= 2; only the hand-over iteration has work
+k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum, uint32_t depth) {
+  if (wc->tail_iter != depth) return;  // launched after every iteration >= 2; only the hand-over iteration's launch has work
   const uint32_t n = wc->n_tail;   // live paths, listed in q.active[0] by k_win_fill
   if (threadIdx.x == 0u) atomicMin(&wc->tail_t0, global_timer_ns());
   typename TR::Scratch scratch;
@@ -1769,11 +1780,11 @@ static void launch_shade(const RenderSetup& rs, Ctx* c, const SlotRefs& sl, uint
     else k_shade<PTB_METHOD_NAIVE, false, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first);
   }
 }
-static void launch_tail(const RenderSetup& rs, Ctx* c, const SlotRefs& sl, uint32_t grid, cudaStream_t st) {
+static void launch_tail(const RenderSetup& rs, Ctx* c, const SlotRefs& sl, uint32_t grid, cudaStream_t st, uint32_t depth) {
   const void* fn = c->wide ? tail_kernel_of<CwTrav>(rs.mis, rs.full) : tail_kernel_of<BinTrav>(rs.mis, rs.full);
   WaveCounters* wc = sl.wc;
   float* accum = rs.accum;
-  void* args[] = {(void*)&c->dev, (void*)&sl.pool, (void*)&sl.q, (void*)&wc, (void*)&rs.rp, (void*)&accum};
+  void* args[] = {(void*)&c->dev, (void*)&sl.pool, (void*)&sl.q, (void*)&wc, (void*)&rs.rp, (void*)&accum, (void*)&depth};
   cudaLaunchKernel(fn, dim3(grid), dim3(128), args, 0, st);
 }
 template <bool DENSE>
@@ -1890,7 +1901,7 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
         // everything left of the chunk is then ONE launch on the side stream
         PTB_CUDA_TRY(c, cudaEventRecord(c->ev_head_done[sl], st));
         PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_tail, c->ev_head_done[sl], 0));
-        launch_tail(rs, c, S, grid_tail, c->s_tail);
+        launch_tail(rs, c, S, grid_tail, c->s_tail, (uint32_t)depth);
         PTB_CUDA_TRY(c, cudaEventRecord(c->ev_tail_done[sl], c->s_tail));
         tail_pending[sl] = true;
         c->stats.kernel_launches += 1;

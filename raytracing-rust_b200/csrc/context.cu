@@ -119,6 +119,9 @@ int32_t ptb_destroy(ptb_ctx* ctx) {
   for (cudaEvent_t e : c->ev_tail_done) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_ring) if (e) cudaEventDestroy(e);
   if (c->s_tail) { cudaStreamSynchronize(c->s_tail); cudaStreamDestroy(c->s_tail); }
+  if (c->s_work2) { cudaStreamSynchronize(c->s_work2); cudaStreamDestroy(c->s_work2); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->s_in) cudaStreamDestroy(c->s_in);
   if (c->s_out) cudaStreamDestroy(c->s_out);
   for (cudaEvent_t e : c->ev_prof)

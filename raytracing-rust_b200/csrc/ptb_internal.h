@@ -125,13 +125,15 @@ struct Ctx {
   // tail (k_tail) finishes on `s_tail` in the other slot
   DevBuf d_pool_mem2, d_prev2, d_queues2, d_shadow2, d_counters2, d_windows2;
   cudaStream_t s_tail = nullptr;
+  cudaStream_t s_work2 = nullptr;  // the odd chunks' wide iterations run here, concurrently with the even chunks' on `stream`
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_head_done[2] = {}, ev_tail_done[2] = {};
-  cudaEvent_t ev_ring[4] = {};  // per-iteration completion (the host runs at most 3 iterations ahead of the device)
+  cudaEvent_t ev_ring[8] = {};  // per-slot ring of 4: iteration completion (the host runs at most 3 iterations ahead)
   PathPool pool;
   size_t pool_budget_bytes = 0;  // half of the device memory that was free at the first large render (0 = not asked yet)
-  WaveCounters* h_counters = nullptr;  // pinned: [0..3] per-iteration mirrors (ring), [4..5] end-of-render copy of each slot
+  WaveCounters* h_counters = nullptr;  // pinned: [0..7] per-iteration mirrors (a ring of 4 per slot), [8..9] end-of-render copy of each slot
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_iter = nullptr;
-  cudaEvent_t ev_prof[32] = {};  // PTB_OPT_TIME_KERNELS: 4 iterations (ring) x 4 kernel classes x (start, stop)
+  cudaEvent_t ev_prof[64] = {};  // PTB_OPT_TIME_KERNELS: 2 slots x 4 iterations (ring) x 4 kernel classes x (start, stop)
   bool opt_time_kernels = false, opt_count_traversal = false;
 
   // closest-hit staging: two buffer pairs + copy streams so that the upload of batch k+1, the traversal of batch k and the

@@ -1684,7 +1684,7 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   if (windows && plan.n_chunks > 1) bind_slot(rs.q2, rs.pool2, P, windows, c->d_pool_mem2, c->d_prev2, c->d_queues2, c->d_shadow2, c->d_windows2);
   rs.wc = c->d_counters.as<WaveCounters>();
   rs.wc2 = c->d_counters2.as<WaveCounters>();
-  if (!c->h_counters) PTB_CUDA_TRY(c, cudaMallocHost(&c->h_counters, 6 * sizeof(WaveCounters)));
+  if (!c->h_counters) PTB_CUDA_TRY(c, cudaMallocHost(&c->h_counters, 10 * sizeof(WaveCounters)));
 
   RenderParams& rp = rs.rp;
   rp.width = o.width; rp.height = o.height; rp.npix = npix;
@@ -1732,7 +1732,7 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
 // ev_prof[(iter & 3) * 8 + 2 * k + {0,1}] brackets kernel class k (0 generate + bookkeeping, 1 trace, 2 shade, 3 shadow)
 #define PTB_PROF(k, which) \
   if (prof) cudaEventRecord(c->ev_prof[(int)(iter & 3u) * 8 + 2 * (k) + (which)], st)
-static void prof_collect(Ctx* c, int half, bool mis) {
+static void prof_collect(Ctx* c, int half, bool mis) {  // half = ring position (+ 4 for the second slot's ring)
   double* prof_ms[4] = {&c->stats.ms_generate, &c->stats.ms_trace, &c->stats.ms_shade, &c->stats.ms_shadow};
   for (int k = 0; k < (mis ? 4 : 3); ++k) {
     float ms = 0.f;
@@ -1842,121 +1842,197 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   }
   for (cudaEvent_t& e : c->ev_ring)
     if (!e) PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (!c->ev_fork) PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  if (!c->ev_join) PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  const bool two = rs.n_chunks > 1;
+  if (two && !c->s_work2) PTB_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_work2, cudaStreamNonBlocking));
   const uint32_t grid_tail = (tail_paths + 127u) / 128u;
-  bool tail_pending[2] = {false, false};  // a k_tail is (or may still be) running in that slot
+  // Two chunks are in flight at any time, one per slot, each on its own stream: the block scheduler fills the drain of
+  // one chunk's persistent kernel (its last long rays) and its small late iterations with the other chunk's blocks. The
+  // FIRST chunk is half as long as the others, so the two streams stay half a chunk out of phase — while one is in its
+  // narrow iterations the other is in its wide ones.
   // The host never waits for the iteration it has just enqueued: the chunk's state machine runs on the device
   // (k_win_prepare) and every kernel of an iteration that has nothing to do returns at once. The host stays at most
-  // kAhead iterations in front and reads the mirror of iteration d - kAhead to learn that a chunk is over, so a chunk
-  // costs at most kAhead empty iterations (~20 us each) instead of one host round trip per iteration.
+  // kAhead iterations in front of each chunk and reads the mirror of iteration d - kAhead to learn that the chunk is over.
   constexpr uint64_t kAhead = 3;
+  struct ChunkRun {
+    bool active = false;
+    unsigned long long first = 0;
+    uint32_t n_paths = 0;
+    uint64_t depth = 0;    // iterations enqueued
+    uint64_t drained = 0;  // iterations whose mirror has been read
+    bool over = false;
+    bool tail_pending = false;  // a k_tail launch of this slot may still be running
+    uint64_t rays_ref_seen = 0;
+  };
+  ChunkRun run[2];
+  cudaStream_t wst[2] = {st, two ? c->s_work2 : st};
 
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
   k_init_pool<<<1, 32, 0, st>>>(rs.q.active[0], 0u, rs.wc, total);   // counters only
   k_init_pool<<<1, 32, 0, st>>>(rs.q2.active[0], 0u, rs.wc2, total);
   c->stats.kernel_launches += 2;
+  if (two) {  // the second stream starts after whatever the caller queued before this render
+    PTB_CUDA_TRY(c, cudaEventRecord(c->ev_fork, st));
+    PTB_CUDA_TRY(c, cudaStreamWaitEvent(wst[1], c->ev_fork, 0));
+  }
   int32_t rc = PTB_OK;
-  uint64_t iter = 0;
-  uint32_t chunk_index = 0;
-  uint64_t rays_ref_seen = 0;
-  for (unsigned long long first = 0; first < total && rc == PTB_OK; first += P, ++chunk_index) {
-    const int sl = rs.n_chunks > 1 ? (int)(chunk_index & 1u) : 0;
+  uint64_t iterations = 0;
+  unsigned long long next_first = 0, paths_done = 0;
+  uint32_t chunks_started = 0;
+
+  auto prof_rec = [&](int sl, uint64_t it, int k, int which) {
+    if (prof) cudaEventRecord(c->ev_prof[(sl * 4 + (int)(it & 3u)) * 8 + 2 * k + which], wst[sl]);
+  };
+  // start the next chunk in slot sl
+  auto start_chunk = [&](int sl) -> int32_t {
+    ChunkRun& R = run[sl];
+    const SlotRefs& S = slots[sl];
+    // chunk 0 is half a chunk long (see above); the others P, the last one what is left
+    unsigned long long len = P;
+    if (two && chunks_started == 0 && total > (unsigned long long)P) len = (P / 2 + kWindow - 1) / kWindow * kWindow;
+    if (len > total - next_first) len = total - next_first;
+    R = ChunkRun();
+    R.active = true;
+    R.first = next_first;
+    R.n_paths = (uint32_t)len;
+    next_first += len;
+    ++chunks_started;
+    cudaStream_t s = wst[sl];
+    if (tail_paths)  // the slot's previous chunk has left it (a no-op while the event has never been recorded)
+      PTB_CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_tail_done[sl], 0));
+    PTB_CUDA_TRY(c, cudaMemsetAsync(S.q.win_count, 0, (size_t)S.q.n_windows * 4, s));
+    if (R.n_paths % kWindow)  // slots of the last window that hold no path
+      PTB_CUDA_TRY(c, cudaMemsetAsync(S.q.bin + R.n_paths, (int)kBinDead, kWindow - R.n_paths % kWindow, s));
+    prof_rec(sl, 0, 0, 0);
+    k_win_init<<<(S.q.n_windows + T - 1) / T, T, 0, s>>>(S.q, S.wc, R.n_paths);
+    c->stats.kernel_launches += 1;
+    return PTB_OK;
+  };
+  // enqueue iteration R.depth of the chunk in slot sl
+  auto enqueue_iteration = [&](int sl) -> int32_t {
+    ChunkRun& R = run[sl];
     const SlotRefs& S = slots[sl];
     const Queues& q = S.q;
     WaveCounters* wc = S.wc;
-    const uint32_t n_paths = (uint32_t)(total - first < P ? total - first : P);
-    if (tail_pending[sl]) {  // the slot's previous chunk (two chunks ago) must have left it
-      PTB_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_tail_done[sl], 0));
-      tail_pending[sl] = false;
+    cudaStream_t s = wst[sl];
+    const uint64_t depth = R.depth;
+    if (depth) prof_rec(sl, depth, 0, 0);
+    k_win_scan<<<n_seg, 1024, 0, s>>>(q);
+    k_win_prepare<<<1, 32, 0, s>>>(wc, q, n_seg, o.method, depth == 0 ? 0u : (depth == 1 ? 1u : 2u), (uint32_t)depth, tail_paths);
+    if (depth) k_win_fill<<<grid_fill, T, 0, s>>>(q, wc);  // depth 0: work item i is slot i, no queue
+    prof_rec(sl, depth, 0, 1);
+    if (tail_paths && depth >= 2) {
+      // k_tail runs in the iteration whose k_win_prepare hands the chunk over (and returns at once in all the others):
+      // everything left of the chunk is then ONE launch on the side stream
+      PTB_CUDA_TRY(c, cudaEventRecord(c->ev_head_done[sl], s));
+      PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_tail, c->ev_head_done[sl], 0));
+      launch_tail(rs, c, S, grid_tail, c->s_tail, (uint32_t)depth);
+      PTB_CUDA_TRY(c, cudaEventRecord(c->ev_tail_done[sl], c->s_tail));
+      R.tail_pending = true;
+      c->stats.kernel_launches += 1;
     }
-    PTB_CUDA_TRY(c, cudaMemsetAsync(q.win_count, 0, (size_t)q.n_windows * 4, st));
-    if (n_paths % kWindow)  // slots of the last window that hold no path
-      PTB_CUDA_TRY(c, cudaMemsetAsync(q.bin + n_paths, (int)kBinDead, kWindow - n_paths % kWindow, st));
-    PTB_PROF(0, 0);
-    k_win_init<<<(q.n_windows + T - 1) / T, T, 0, st>>>(q, wc, n_paths);
-    c->stats.kernel_launches += 1;
-    const uint64_t iter0 = iter;
-    bool over = false;
-    // drains iteration `it` of this chunk: its events are complete, its mirror says whether the chunk is over
-    auto drain = [&](uint64_t it) -> int32_t {
-      const int r = (int)(it & 3u);
-      PTB_CUDA_TRY(c, cudaEventSynchronize(c->ev_ring[r]));
-      if (prof) prof_collect(c, r, mis);
-      if (c->h_counters[r].mode != 0u) over = true;
-      rays_ref_seen = c->h_counters[r].rays_reference;
-      return PTB_OK;
-    };
-    for (uint64_t depth = 0; !over; ++depth, ++iter) {
-      if (depth >= kAhead) {
-        const int32_t d = drain(iter - kAhead);
-        if (d != PTB_OK) return d;
-        if (over) break;
-      }
-      if (depth) PTB_PROF(0, 0);
-      k_win_scan<<<n_seg, 1024, 0, st>>>(q);
-      k_win_prepare<<<1, 32, 0, st>>>(wc, q, n_seg, o.method, depth == 0 ? 0u : (depth == 1 ? 1u : 2u), (uint32_t)depth, tail_paths);
-      if (depth) k_win_fill<<<grid_fill, T, 0, st>>>(q, wc);  // depth 0: work item i is slot i, no queue
-      PTB_PROF(0, 1);
-      if (tail_paths && depth >= 2) {
-        // k_tail runs in the iteration whose k_win_prepare hands the chunk over (and returns at once in all the others):
-        // everything left of the chunk is then ONE launch on the side stream
-        PTB_CUDA_TRY(c, cudaEventRecord(c->ev_head_done[sl], st));
-        PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_tail, c->ev_head_done[sl], 0));
-        launch_tail(rs, c, S, grid_tail, c->s_tail, (uint32_t)depth);
-        PTB_CUDA_TRY(c, cudaEventRecord(c->ev_tail_done[sl], c->s_tail));
-        tail_pending[sl] = true;
-        c->stats.kernel_launches += 1;
-      }
-      PTB_PROF(1, 0);
-      if (depth == 0) {
-        // camera rays of a warp finish together: refilling later (fewer, fuller service passes) suits them
-        // (C3, camera rays only: threshold 8 -> 8105 Mrays/s, 4 -> 8311; bounce rays prefer 8, profiles/r1_sweeps.md)
-        DevScene cam = c->dev;
-        cam.trace_fetch_threshold = cam_fetch;
-        PTB_CUDA_TRY(c, launch_trace(fn_trace_cam, grid_trace_cam, st, cam, S.pool, q, wc, rs.rp, first));
-      } else {
-        PTB_CUDA_TRY(c, launch_trace(fn_trace, grid_trace, st, c->dev, S.pool, q, wc, rs.rp, 0ull));
-      }
-      PTB_PROF(1, 1);
-      PTB_PROF(2, 0);
-      launch_shade<true>(rs, c, S, grid_shade, TS, st, depth == 0 ? first : kNoCamera);
-      PTB_PROF(2, 1);
-      c->stats.kernel_launches += depth ? 5 : 4;
-      c->stats.trace_launches += 1;
-      if (mis) {
-        PTB_PROF(3, 0);
-        PTB_CUDA_TRY(c, launch_shadow(fn_shadow, grid_shadow, st, c->dev, S.pool, q, wc));
-        PTB_PROF(3, 1);
-        c->stats.kernel_launches += 1;
-      }
-      // pinned mirrors + events, a ring of four
-      const int r = (int)(iter & 3u);
-      PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + r, wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
-      PTB_CUDA_TRY(c, cudaEventRecord(c->ev_ring[r], st));
-      if (depth > 4096) return set_error(c, PTB_ERR_INVALID, "wavefront did not terminate");
+    prof_rec(sl, depth, 1, 0);
+    if (depth == 0) {
+      // camera rays of a warp finish together: refilling later (fewer, fuller service passes) suits them
+      // (C3, camera rays only: threshold 8 -> 8105 Mrays/s, 4 -> 8311; bounce rays prefer 8, profiles/r1_sweeps.md)
+      DevScene cam = c->dev;
+      cam.trace_fetch_threshold = cam_fetch;
+      PTB_CUDA_TRY(c, launch_trace(fn_trace_cam, grid_trace_cam, s, cam, S.pool, q, wc, rs.rp, R.first));
+    } else {
+      PTB_CUDA_TRY(c, launch_trace(fn_trace, grid_trace, s, c->dev, S.pool, q, wc, rs.rp, 0ull));
     }
-    // the iterations still in flight are empty or the hand-over itself; the timing build collects their events
-    if (prof)
-      for (uint64_t it = iter > iter0 + kAhead ? iter - kAhead : iter0; it < iter; ++it) {
-        bool keep = over;
-        const int32_t d = drain(it);
-        over = keep || over;
-        if (d != PTB_OK) return d;
+    prof_rec(sl, depth, 1, 1);
+    prof_rec(sl, depth, 2, 0);
+    launch_shade<true>(rs, c, S, grid_shade, TS, s, depth == 0 ? R.first : kNoCamera);
+    prof_rec(sl, depth, 2, 1);
+    c->stats.kernel_launches += depth ? 5 : 4;
+    c->stats.trace_launches += 1;
+    if (mis) {
+      prof_rec(sl, depth, 3, 0);
+      PTB_CUDA_TRY(c, launch_shadow(fn_shadow, grid_shadow, s, c->dev, S.pool, q, wc));
+      prof_rec(sl, depth, 3, 1);
+      c->stats.kernel_launches += 1;
+    }
+    // pinned mirror + event of this iteration, a ring of four per slot
+    const int r = sl * 4 + (int)(depth & 3u);
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + r, wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, s));
+    PTB_CUDA_TRY(c, cudaEventRecord(c->ev_ring[r], s));
+    ++R.depth;
+    ++iterations;
+    if (R.depth > 4096) return set_error(c, PTB_ERR_INVALID, "wavefront did not terminate");
+    return PTB_OK;
+  };
+  // reads the mirror of the oldest undrained iteration (its event must be complete)
+  auto drain_one = [&](int sl) {
+    ChunkRun& R = run[sl];
+    const int r = sl * 4 + (int)(R.drained & 3u);
+    if (prof) prof_collect(c, r, mis);
+    if (c->h_counters[r].mode != 0u) R.over = true;
+    R.rays_ref_seen = c->h_counters[r].rays_reference;
+    ++R.drained;
+  };
+
+  while (rc == PTB_OK) {
+    for (int sl = 0; sl < (two ? 2 : 1); ++sl)
+      if (!run[sl].active && next_first < total) {
+        const int32_t e = start_chunk(sl);
+        if (e != PTB_OK) return e;
       }
-    if (progress && first + n_paths < total && progress(user, (first + n_paths) / npix, rays_ref_seen)) rc = PTB_ERR_ABORTED;
+    if (!run[0].active && !run[1].active) break;
+    bool progress_made = false;
+    for (int sl = 0; sl < 2 && rc == PTB_OK; ++sl) {
+      ChunkRun& R = run[sl];
+      if (!R.active) continue;
+      if (R.depth - R.drained >= kAhead) {
+        const int r = sl * 4 + (int)(R.drained & 3u);
+        if (cudaEventQuery(c->ev_ring[r]) != cudaSuccess) continue;  // still running: look at the other chunk
+        drain_one(sl);
+        progress_made = true;
+      } else if (!R.over) {
+        const int32_t e = enqueue_iteration(sl);
+        if (e != PTB_OK) return e;
+        progress_made = true;
+        continue;
+      }
+      if (R.over) {
+        // the iterations still in flight are empty (or the hand-over itself); the timing build collects their events
+        if (prof)
+          while (R.drained < R.depth) {
+            PTB_CUDA_TRY(c, cudaEventSynchronize(c->ev_ring[sl * 4 + (int)(R.drained & 3u)]));
+            drain_one(sl);
+          }
+        R.active = false;
+        paths_done += R.n_paths;
+        progress_made = true;
+        if (progress && paths_done < total && progress(user, paths_done / npix, R.rays_ref_seen)) rc = PTB_ERR_ABORTED;
+      }
+    }
+    if (!progress_made) {
+      // both chunks are kAhead iterations ahead of the device: wait for the older of the two oldest iterations
+      int sl = run[0].active ? 0 : 1;
+      if (run[0].active && run[1].active && run[1].depth - run[1].drained >= kAhead && run[0].depth - run[0].drained < kAhead) sl = 1;
+      PTB_CUDA_TRY(c, cudaEventSynchronize(c->ev_ring[sl * 4 + (int)(run[sl].drained & 3u)]));
+    }
   }
-  for (int sl = 0; sl < 2; ++sl)
-    if (tail_pending[sl]) PTB_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_tail_done[sl], 0));
-  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + 4, rs.wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
-  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + 5, rs.wc2, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+  // join: everything the second stream and the tail stream still hold comes back to the caller's stream
+  if (two) {
+    PTB_CUDA_TRY(c, cudaEventRecord(c->ev_join, wst[1]));
+    PTB_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_join, 0));
+  }
+  if (tail_paths)
+    for (int sl = 0; sl < 2; ++sl) PTB_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_tail_done[sl], 0));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + 8, rs.wc, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_counters + 9, rs.wc2, sizeof(WaveCounters), cudaMemcpyDeviceToHost, st));
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_b, st));
   PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
   PTB_CUDA_TRY(c, cudaGetLastError());
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
   const uint64_t ref_before = c->stats.rays_reference;
-  fold_counters(c, c->h_counters[4], iter);
-  fold_counters(c, c->h_counters[5], 0);
-  for (int k = 4; k < 6; ++k) {
+  fold_counters(c, c->h_counters[8], iterations);
+  fold_counters(c, c->h_counters[9], 0);
+  for (int k = 8; k < 10; ++k) {
     const WaveCounters& h = c->h_counters[k];
     c->stats.ms_tail += 1e-6 * (double)(h.tail_ns + (h.tail_t0 != ~0ull && h.tail_t1 > h.tail_t0 ? h.tail_t1 - h.tail_t0 : 0ull));
   }

@@ -18,7 +18,7 @@ def test_traversal_counts_match_lbvh_oracle(ptb, orc, gpu_ctx):
     s = ptb.meshgen.c3_scene(0.1)
     rays = random_rays(ptb, 200_000, 21, centre=(0, 4, 1), radius=5.0)
     gpu_ctx.upload(s)
-    gpu_ctx.commit()
+    gpu_ctx.commit(ptb._lib.BUILD_BINARY)   # the binary walk's counts (the wide tree's are EQUAL to its own CPU statement: test_gpu_wide.py)
     gpu_ctx.set_option(ptb._lib.OPT_COUNT_TRAVERSAL, 1)
     gpu_ctx.stats_reset()
     g = gpu_ctx.closest_hit(rays)

@@ -67,6 +67,7 @@ struct WaveCounters {  // lives in device memory; mirrored to pinned host memory
   // 2 chunk finished, 3 handed over earlier — in every state but 0 the wavefront kernels find n_trace == 0 and return
   uint32_t mode;
   uint32_t n_tail, tail_iter;  // set ONCE per chunk: live paths handed over, and the iteration whose k_tail launch takes them
+  uint32_t tail_head, _pad2;   // k_tail's work cursor (its lanes pull paths one by one)
   // k_shade's queue cursors, packed so that one warp needs ONE returning atomic per pair (the kernel used to spend 40 % of
   // its stall samples waiting for three serial same-address atomics): push_pair = finished-slot cursor << 32 | next-active
   // cursor, shadow_pair = sky NEE rays << 32 | shadow-queue cursor. k_prepare unpacks them between iterations.

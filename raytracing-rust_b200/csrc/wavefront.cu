@@ -970,7 +970,7 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
 __global__ void __launch_bounds__(256) k_win_init(Queues q, WaveCounters* wc, uint32_t n_paths) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w == 0u) {
-    wc->mode = 0u; wc->n_tail = 0u; wc->tail_iter = 0xFFFFFFFFu; wc->n_trace = 0u;
+    wc->mode = 0u; wc->n_tail = 0u; wc->tail_iter = 0xFFFFFFFFu; wc->n_trace = 0u; wc->tail_head = 0u;
     if (wc->tail_t0 != ~0ull && wc->tail_t1 > wc->tail_t0) wc->tail_ns += wc->tail_t1 - wc->tail_t0;  // the slot's previous hand-over
     wc->tail_t0 = ~0ull;
     wc->tail_t1 = 0ull;
@@ -1194,7 +1194,13 @@ k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, 
   if (threadIdx.x == 0u) atomicMin(&wc->tail_t0, global_timer_ns());
   typename TR::Scratch scratch;
   unsigned long long c_bounce = 0, c_sky = 0, c_light = 0, c_ref = 0, c_paths = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  // Few threads on purpose (one block per SM by default): the launch lives for milliseconds beside the next chunk's
+  // persistent kernels, and every register it holds is one those cannot use (a 512-block tail held 65 % of the register
+  // file and cost k_trace two thirds of its occupancy). A lane pulls the next live path when its own has ended, so the
+  // launch still lasts about as long as the longest path.
+  for (;;) {
+    const uint32_t i = atomicAdd(&wc->tail_head, 1u);
+    if (i >= n) break;
     const uint32_t slot = q.active[0][i];
     for (;;) {
       // ---- closest hit (k_trace): the hit goes into the ray record, where shade_path reads it
@@ -1734,10 +1740,16 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
   if (prof) cudaEventRecord(c->ev_prof[(int)(iter & 3u) * 8 + 2 * (k) + (which)], st)
 static void prof_collect(Ctx* c, int half, bool mis) {  // half = ring position (+ 4 for the second slot's ring)
   double* prof_ms[4] = {&c->stats.ms_generate, &c->stats.ms_trace, &c->stats.ms_shade, &c->stats.ms_shadow};
+  static const bool timeline = getenv("PTB_TIMELINE") != nullptr;  // tuning aid: where each iteration sits inside the render
   for (int k = 0; k < (mis ? 4 : 3); ++k) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev_prof[half * 8 + 2 * k], c->ev_prof[half * 8 + 2 * k + 1]) == cudaSuccess)
       *prof_ms[k] += ms;
+    if (timeline) {
+      float t0 = 0.f;
+      cudaEventElapsedTime(&t0, c->ev_a, c->ev_prof[half * 8 + 2 * k]);
+      fprintf(stderr, "timeline ring %d class %d start %.3f ms dur %.3f ms\n", half, k, t0, ms);
+    }
   }
 }
 static void dump_lane_stats() {
@@ -1826,7 +1838,7 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   if (const char* e = getenv("PTB_TRACE_FETCH_CAMERA")) { int v = atoi(e); if (v >= 1 && v <= 32) cam_fetch = v; }
   // hand-over point: live paths of a chunk at or below which the fused tail takes it (0: never; the traversal statistics
   // build counts in k_trace only, so it keeps the wavefront to the end)
-  uint32_t tail_paths = 65536u;
+  uint32_t tail_paths = 32768u;
   if (const char* e = getenv("PTB_TAIL_PATHS")) { long v = atol(e); if (v >= 0 && v <= (1l << 24)) tail_paths = (uint32_t)v; }
   if (count) tail_paths = 0u;
   if (tail_paths) {
@@ -1845,8 +1857,17 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   if (!c->ev_fork) PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   if (!c->ev_join) PTB_CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   const bool two = rs.n_chunks > 1;
-  if (two && !c->s_work2) PTB_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_work2, cudaStreamNonBlocking));
-  const uint32_t grid_tail = (tail_paths + 127u) / 128u;
+  // How many chunks run their wide iterations at the same time. Two (each on its own stream) fill each other's kernel
+  // drains, but their rays compete for L1 / L2: measured on B200 (profiles/r2_sweeps.md) it loses 4 - 13 % on the 1 M-triangle
+  // mesh and gains 5 % on the two-sphere / 14-primitive scenes, whose geometry lives in L1 whatever happens. One chunk at a
+  // time still alternates between the two slots, so its fused tail overlaps the next chunk's iterations.
+  int chunk_streams = c->n_prims < 4096 ? 2 : 1;
+  if (const char* e = getenv("PTB_CHUNK_STREAMS")) { int v = atoi(e); if (v == 1 || v == 2) chunk_streams = v; }
+  if (!two) chunk_streams = 1;
+  if (chunk_streams == 2 && !c->s_work2) PTB_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_work2, cudaStreamNonBlocking));
+  uint32_t grid_tail = (uint32_t)c->sm_count;  // blocks of 128 threads (PTB_TAIL_BLOCKS)
+  if (const char* e = getenv("PTB_TAIL_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= 65535) grid_tail = (uint32_t)v; }
+  if (grid_tail > (tail_paths + 127u) / 128u) grid_tail = (tail_paths + 127u) / 128u;
   // Two chunks are in flight at any time, one per slot, each on its own stream: the block scheduler fills the drain of
   // one chunk's persistent kernel (its last long rays) and its small late iterations with the other chunk's blocks. The
   // FIRST chunk is half as long as the others, so the two streams stay half a chunk out of phase — while one is in its
@@ -1866,13 +1887,13 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
     uint64_t rays_ref_seen = 0;
   };
   ChunkRun run[2];
-  cudaStream_t wst[2] = {st, two ? c->s_work2 : st};
+  cudaStream_t wst[2] = {st, chunk_streams == 2 ? c->s_work2 : st};
 
   PTB_CUDA_TRY(c, cudaEventRecord(c->ev_a, st));
   k_init_pool<<<1, 32, 0, st>>>(rs.q.active[0], 0u, rs.wc, total);   // counters only
   k_init_pool<<<1, 32, 0, st>>>(rs.q2.active[0], 0u, rs.wc2, total);
   c->stats.kernel_launches += 2;
-  if (two) {  // the second stream starts after whatever the caller queued before this render
+  if (chunk_streams == 2) {  // the second stream starts after whatever the caller queued before this render
     PTB_CUDA_TRY(c, cudaEventRecord(c->ev_fork, st));
     PTB_CUDA_TRY(c, cudaStreamWaitEvent(wst[1], c->ev_fork, 0));
   }
@@ -1890,7 +1911,7 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
     const SlotRefs& S = slots[sl];
     // chunk 0 is half a chunk long (see above); the others P, the last one what is left
     unsigned long long len = P;
-    if (two && chunks_started == 0 && total > (unsigned long long)P) len = (P / 2 + kWindow - 1) / kWindow * kWindow;
+    if (chunk_streams == 2 && chunks_started == 0 && total > (unsigned long long)P) len = (P / 2 + kWindow - 1) / kWindow * kWindow;
     if (len > total - next_first) len = total - next_first;
     R = ChunkRun();
     R.active = true;
@@ -1974,11 +1995,12 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   };
 
   while (rc == PTB_OK) {
-    for (int sl = 0; sl < (two ? 2 : 1); ++sl)
-      if (!run[sl].active && next_first < total) {
-        const int32_t e = start_chunk(sl);
-        if (e != PTB_OK) return e;
-      }
+    while (next_first < total && (int)run[0].active + (int)run[1].active < chunk_streams) {
+      const int sl = two ? (int)(chunks_started & 1u) : 0;  // slots alternate: chunk k's tail may still be running in slot k & 1
+      if (run[sl].active) break;
+      const int32_t e = start_chunk(sl);
+      if (e != PTB_OK) return e;
+    }
     if (!run[0].active && !run[1].active) break;
     bool progress_made = false;
     for (int sl = 0; sl < 2 && rc == PTB_OK; ++sl) {
@@ -2016,7 +2038,7 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
     }
   }
   // join: everything the second stream and the tail stream still hold comes back to the caller's stream
-  if (two) {
+  if (chunk_streams == 2) {
     PTB_CUDA_TRY(c, cudaEventRecord(c->ev_join, wst[1]));
     PTB_CUDA_TRY(c, cudaStreamWaitEvent(st, c->ev_join, 0));
   }

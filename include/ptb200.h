@@ -246,11 +246,11 @@ int32_t ptb_closest_hit_device(ptb_ctx* ctx, const void* d_rays, size_t n, void*
 /* --------------------------------------------------------------- render -- */
 /* Replaces Sampler::sample_image (samplers/mod.rs:7-20, random_sampler.rs:10-99) + the running mean of
  * src/main.rs:175-191: adds opts->samples_per_pixel samples per pixel into the device accumulator (sums).
- * Device memory: the path state of a call lives in two chunk slots of together at most 8 GiB (PTB_POOL_BYTES=<bytes>
- * changes the budget; 69 B per path, 133 B with MIS, i.e. 2 x 62 Mi / 2 x 32 Mi paths), never more than half of the memory
- * that was free at the context's first large render. A call larger than one slot runs chunk by chunk, the wide iterations
- * of chunk k+1 overlapping the latency-bound tail of chunk k. PTB_POOL_PATHS=<paths> sets the slot size directly,
- * PTB_TAIL_PATHS=<paths> the live-path count (default 32 768) below which a chunk is handed to the fused tail kernel (0: never),
+ * Device memory: the path state of a call takes at most 8 GiB (PTB_POOL_BYTES=<bytes> changes the budget; 69 B per path,
+ * 133 B with MIS), never more than half of the memory that was free at the context's first large render. A call that fits
+ * (124 Mi paths, 64 Mi with MIS) runs as one chunk; a larger one runs chunk by chunk in two slots of half the budget each,
+ * the wide iterations of chunk k+1 overlapping the latency-bound tail of chunk k. PTB_POOL_PATHS=<paths> sets the slot size directly,
+ * PTB_TAIL_PATHS=<paths> the live-path count (default 65 536) below which a chunk is handed to the fused tail kernel (0: never),
  * PTB_WAVEFRONT=queue selects the small-pool regenerating mode. The
  * image is a pure function of (scene, opts): pool size, chunking and GPU count only change the f32 summation order
  * (finished paths are added with float atomics, so two runs of the same call agree to ~1e-6 relative, not bit for bit).

@@ -1543,8 +1543,8 @@ void free_render_state(Ctx* c) {
 // Paths in flight. Round 1 kept EVERY camera path of a call resident (36 GB for 1080p x 256 spp) to amortise the ~45
 // nearly empty iterations at the end of a wavefront; the fused tail kernel on a side stream removes that cost instead, so
 // the path state is bounded: two chunk slots of together PTB_POOL_BYTES (default 8 GiB), never more than half of the
-// device memory that was free at the context's first large render. A call is cut into equal chunks of at most one slot —
-// and into at least four once it has more than 8 Mi paths, so that only the LAST chunk's tail is exposed.
+// device memory that was free at the context's first large render. A call is cut into equal chunks of at most one slot;
+// all tails but the last chunk's are hidden under the next chunk.
 // PTB_POOL_PATHS sets the slot size directly (tests; the queue mode's pool).
 struct PoolPlan {
   uint32_t slot_paths;  // capacity of one slot (multiple of kWindow)
@@ -1569,7 +1569,11 @@ static PoolPlan plan_pool(Ctx* c, unsigned long long total, bool mis, bool windo
       }
       if (budget > c->pool_budget_bytes) budget = c->pool_budget_bytes;
     }
-    cap = budget / (windows ? 2ull : 1ull) / per_path;
+    // a call that fits the whole budget runs as ONE chunk in one slot (its only tail is exposed either way, and every
+    // extra chunk adds the drain of five more persistent launches: measured, profiles/r2_sweeps.md); a larger one
+    // alternates between two slots of half the budget each
+    cap = budget / per_path;
+    if (windows && total > cap) cap = budget / 2ull / per_path;
     if (cap > (1ull << 29)) cap = 1ull << 29;
     if (cap < (1ull << 20)) cap = 1ull << 20;
   }
@@ -1577,7 +1581,6 @@ static PoolPlan plan_pool(Ctx* c, unsigned long long total, bool mis, bool windo
   cap = cap / gran * gran;
   if (cap < gran) cap = gran;
   unsigned long long n_chunks = (total + cap - 1ull) / cap;
-  if (windows && n_chunks < 4ull && total > (1ull << 23)) n_chunks = 4ull;  // overlap the tails of all chunks but the last
   unsigned long long chunk = (total + n_chunks - 1ull) / n_chunks;
   chunk = (chunk + gran - 1ull) / gran * gran;
   if (chunk > cap) chunk = cap;
@@ -1838,7 +1841,7 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   if (const char* e = getenv("PTB_TRACE_FETCH_CAMERA")) { int v = atoi(e); if (v >= 1 && v <= 32) cam_fetch = v; }
   // hand-over point: live paths of a chunk at or below which the fused tail takes it (0: never; the traversal statistics
   // build counts in k_trace only, so it keeps the wavefront to the end)
-  uint32_t tail_paths = 32768u;
+  uint32_t tail_paths = 65536u;
   if (const char* e = getenv("PTB_TAIL_PATHS")) { long v = atol(e); if (v >= 0 && v <= (1l << 24)) tail_paths = (uint32_t)v; }
   if (count) tail_paths = 0u;
   if (tail_paths) {

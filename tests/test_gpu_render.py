@@ -351,7 +351,7 @@ def test_render_multi_fewer_samples_than_gpus(ptb, gpu_ctx, rtweekend1):
 def test_fused_tail_hand_over_does_not_change_the_result(ptb, gpu_ctx, overshadowed, method, monkeypatch):
     """The last live paths of a chunk are finished by ONE k_tail launch on a side stream (closest hit -> shade -> NEE per
     lane) instead of ~45 nearly empty wavefront iterations. Same functions, same records, same RNG counters: the image and
-    every ray counter are independent of where the hand-over happens (PTB_TAIL_PATHS: 0 = never, default 32 768, and a
+    every ray counter are independent of where the hand-over happens (PTB_TAIL_PATHS: 0 = never, default 65 536, and a
     hand-over forced right after the first bounce)."""
     scenes = [overshadowed, ptb.meshgen.c3_scene(0.05)] if method == 0 else [overshadowed]
     for scene in scenes:
@@ -367,7 +367,7 @@ def test_fused_tail_hand_over_does_not_change_the_result(ptb, gpu_ctx, overshado
         monkeypatch.setenv("PTB_TAIL_PATHS", "0")
         a, ca = run()
         monkeypatch.delenv("PTB_TAIL_PATHS")
-        b, cb = run()                                      # 230 400 paths: handed over once <= 32 768 are alive
+        b, cb = run()                                      # 230 400 paths: handed over once <= 65 536 are alive
         monkeypatch.setenv("PTB_TAIL_PATHS", str(1 << 24))
         c, cc = run()                                      # handed over after the first bounce
         monkeypatch.setenv("PTB_WAVEFRONT", "window")

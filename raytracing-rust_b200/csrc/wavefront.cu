@@ -1888,6 +1888,7 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
     bool over = false;
     bool tail_pending = false;  // a k_tail launch of this slot may still be running
     uint64_t rays_ref_seen = 0;
+    bool last = false;          // the call's last chunk: its tail runs alone and may take the whole machine
   };
   ChunkRun run[2];
   cudaStream_t wst[2] = {st, chunk_streams == 2 ? c->s_work2 : st};
@@ -1921,6 +1922,7 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
     R.first = next_first;
     R.n_paths = (uint32_t)len;
     next_first += len;
+    R.last = next_first >= total;
     ++chunks_started;
     cudaStream_t s = wst[sl];
     if (tail_paths)  // the slot's previous chunk has left it (a no-op while the event has never been recorded)
@@ -1951,7 +1953,8 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
       // everything left of the chunk is then ONE launch on the side stream
       PTB_CUDA_TRY(c, cudaEventRecord(c->ev_head_done[sl], s));
       PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_tail, c->ev_head_done[sl], 0));
-      launch_tail(rs, c, S, grid_tail, c->s_tail, (uint32_t)depth);
+      // (the last chunk's tail has nothing beside it: one lane per path instead of one block per SM)
+      launch_tail(rs, c, S, R.last ? (tail_paths + 127u) / 128u : grid_tail, c->s_tail, (uint32_t)depth);
       PTB_CUDA_TRY(c, cudaEventRecord(c->ev_tail_done[sl], c->s_tail));
       R.tail_pending = true;
       c->stats.kernel_launches += 1;

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (raw page) into a small markdown table for profiles/. Usage: ncu_summary.py rep [title]"""
+"""Summarise an .ncu-rep — or the CSV of its raw page (`ncu -i rep --page raw --csv`) — into a small markdown table for
+profiles/. Usage: ncu_summary.py rep|csv [title]"""
 import csv
 import subprocess
 import sys
@@ -25,13 +26,23 @@ KEYS = [
     ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected / issue"),
     ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall branch_resolving / issue"),
     ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_pipe_throttle / issue"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 data-pipe wavefronts % of peak"),
+    ("l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum", "global-load wavefronts"),
+    ("l1tex__t_output_wavefronts_pipe_lsu_mem_local_op_ld.sum", "local-load wavefronts"),
+    ("l1tex__t_output_wavefronts_pipe_lsu_mem_local_op_st.sum", "local-store wavefronts"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+    ("sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "FMA-heavy pipe %"),
+    ("smsp__inst_executed_pipe_fp64.sum", "FP64 instructions"),
 ]
 
 
 def main():
     rep = sys.argv[1]
     title = sys.argv[2] if len(sys.argv) > 2 else rep
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     H, units, data = rows[0], rows[1], rows[2:]
     ki = H.index("Kernel Name")

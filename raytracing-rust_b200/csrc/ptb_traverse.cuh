@@ -20,6 +20,7 @@
 //     lanes refilled from the global ray queue with one warp-aggregated atomicAdd.
 // Node fetches are four 16-byte loads of one 64-byte node that carries BOTH children's boxes.
 #pragma once
+#include "ptb_coop.cuh"
 #include "ptb_cwbvh.cuh"
 #include "ptb_intersect.cuh"
 
@@ -207,6 +208,7 @@ PTB_DEV TraceResult trav_result(const TravState& s) {
 // ---- the two trees behind one interface: what persistent_trace / trace_lane need from a traversal
 struct BinTrav {  // binary LBVH, one primitive per leaf (this file)
   static constexpr int kTraceMinBlocks = PTB_TRACE_MIN_BLOCKS, kApiMinBlocks = PTB_API_MIN_BLOCKS;
+  static constexpr bool kCoop = true;   // ptb_coop.cuh walks this tree warp-cooperatively
   typedef TravState State;
   typedef SlabRay RayCtx;
   struct Scratch {
@@ -231,6 +233,7 @@ struct BinTrav {  // binary LBVH, one primitive per leaf (this file)
 };
 struct CwTrav {  // compressed 8-wide tree, leaf groups of up to 3 primitives (ptb_cwbvh.cuh)
   static constexpr int kTraceMinBlocks = PTB_CW_TRACE_MIN_BLOCKS, kApiMinBlocks = PTB_CW_API_MIN_BLOCKS;
+  static constexpr bool kCoop = false;
   typedef CwState State;
   typedef CwRay RayCtx;
   struct Scratch {

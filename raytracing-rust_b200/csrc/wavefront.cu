@@ -1186,61 +1186,170 @@ PTB_DEV unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// One bounce of the path in `slot` whose closest hit `tr` has just been found: the hit goes into the ray record, where
+// shade_path reads it; then the shading step of k_shade. Returns the shading outcome; the NEE visibility test (MIS) is the
+// caller's (a lane walk or a cooperative walk).
+template <int METHOD, bool FULL>
+PTB_DEV void tail_shade(const DevScene& sc, const PathPool& pool, const RenderParams& rp, uint32_t slot, const Ray& ray,
+                        const TraceResult& tr, ShadeOut& so) {
+  stg256(pool.ray + 4u * (size_t)slot, make_float4(ray.o.x, ray.o.y, ray.o.z, tr.t),
+         make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(tr.ref)));
+  so.fin_L = mk(0.0f, 0.0f, 0.0f);
+  shade_path<METHOD, FULL>(sc, pool, rp, slot, false, kNoCamera, so);
+}
+PTB_DEV void tail_add_nee(const PathPool& pool, uint32_t slot, const ShadeOut& so) {  // unoccluded NEE joins the path's radiance
+  float4 ra = pool.col[4u * (size_t)slot + 1u];
+  ra.x += so.sh_c.x; ra.y += so.sh_c.y; ra.z += so.sh_c.z;
+  pool.col[4u * (size_t)slot + 1u] = ra;
+}
+PTB_DEV void tail_finish(float* __restrict__ accum, const Queues& q, uint32_t slot, const ShadeOut& so) {
+  if (so.contributes) {
+    atomicAdd(accum + 3u * (size_t)so.fin_pixel + 0, so.fin_L.x);
+    atomicAdd(accum + 3u * (size_t)so.fin_pixel + 1, so.fin_L.y);
+    atomicAdd(accum + 3u * (size_t)so.fin_pixel + 2, so.fin_L.z);
+  }
+  q.bin[slot] = (uint8_t)kBinDead;
+}
+
+// Binary tree: the warp advances its (up to 32) paths one bounce at a time, in lock step, and traverses their rays
+// TOGETHER (ptb_coop.cuh: the rays of up to kCoopRays paths share one frontier, all 32 lanes work on it); shading stays with
+// the lane that owns the path, and a lane whose path has ended takes the next one from the queue. A lane that walks its ray
+// alone pays one dependent memory round trip per node (~150 for a ray inside the glass sphere of C3: 60 us per bounce, and
+// the launch used to last as long as its longest path — 3.5 ms exposed at the end of a C3 render at 5 of 32 lanes); the
+// cooperative walk pays about the depth of the tree, and as the warp's paths die its lanes move over to the survivors.
+// Every step of the loop is warp-convergent on purpose: a lane that leaves a divergent loop early waits at the compiler's
+// reconvergence point until the others arrive, so "a lane pulls the next path when its own has ended" did not do what it
+// says (measured: hand-over tests that relied on idle lanes making progress never fired).
+// Wide tree, and scenes of a handful of primitives (a two-level tree: nothing to share, the rounds' bookkeeping would be
+// most of the work — rtweekend1 measured 3 % slower cooperatively): the lane walk (one lane per path, trace_lane).
+constexpr uint32_t kCoopMinPrims = 4096u;
 template <class TR, int METHOD, bool FULL>
 __global__ void __launch_bounds__(128)
 k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum, uint32_t depth) {
   if (wc->tail_iter != depth) return;  // launched after every iteration >= 2; only the hand-over iteration's launch has work
   const uint32_t n = wc->n_tail;   // live paths, listed in q.active[0] by k_win_fill
   if (threadIdx.x == 0u) atomicMin(&wc->tail_t0, global_timer_ns());
-  typename TR::Scratch scratch;
+#ifdef PTB_TAIL_STATS
+  if (threadIdx.x == 0u) atomicMin(&g_tail_stats[9], global_timer_ns());
+#endif
+  constexpr bool COOP = TR::kCoop;
+  __shared__ CoopWarp s_coop[COOP ? 4 : 1];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   unsigned long long c_bounce = 0, c_sky = 0, c_light = 0, c_ref = 0, c_paths = 0;
-  // Few threads on purpose (one block per SM by default): the launch lives for milliseconds beside the next chunk's
-  // persistent kernels, and every register it holds is one those cannot use (a 512-block tail held 65 % of the register
-  // file and cost k_trace two thirds of its occupancy). A lane pulls the next live path when its own has ended, so the
-  // launch still lasts about as long as the longest path.
-  for (;;) {
-    const uint32_t i = atomicAdd(&wc->tail_head, 1u);
-    if (i >= n) break;
-    const uint32_t slot = q.active[0][i];
+  // Ticket t -> path: cycle walking over x -> (x * odd) mod 2^k, a bijection of [0, n) that sends the 32 consecutive
+  // tickets of a warp to paths ~0.618 * 2^k apart (Fibonacci hashing): neighbouring paths — the same glass pixels, the long
+  // ones — land in different warps.
+  const uint32_t mask = n <= 1u ? 0u : (1u << (32 - __clz(n - 1u))) - 1u;
+  if (COOP && sc.n_prims >= kCoopMinPrims) {
+    CoopWarp& cw = s_coop[warp];
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t slot = kNone;
+    bool exhausted = false;
     for (;;) {
-      // ---- closest hit (k_trace): the hit goes into the ray record, where shade_path reads it
-      float4 o4, d4;
-      ldg256_rw(pool.ray + 4u * (size_t)slot, o4, d4);
-      const Ray ray = make_ray(from4(o4), from4(d4));
-      const TraceResult tr = trace_lane<TR, false>(sc, ray, __int_as_float(0x7f800000), kNone, scratch);
-      stg256(pool.ray + 4u * (size_t)slot, make_float4(ray.o.x, ray.o.y, ray.o.z, tr.t),
-             make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(tr.ref)));
-      ++c_bounce;
-      // ---- shade (k_shade)
-      ShadeOut so;
-      so.fin_L = mk(0.0f, 0.0f, 0.0f);
-      shade_path<METHOD, FULL>(sc, pool, rp, slot, false, kNoCamera, so);
-      if (METHOD == PTB_METHOD_NAIVE) ++c_ref;            // Q7: naive counts every check_hit ...
-      else if (so.alive) ++c_ref;                         // ... MIS every bounce iteration that continues
-      // ---- NEE visibility (k_shadow): unoccluded contributions join the path's radiance
-      if (METHOD == PTB_METHOD_MIS && so.shadow) {
-        if (so.shadow_is_sky) ++c_sky; else ++c_light;
-        const Ray sray = make_ray(from4(so.sh_o), from4(so.sh_d));
-        const TraceResult ss = trace_lane<TR, true>(sc, sray, so.sh_o.w, __float_as_uint(so.sh_d.w), scratch);
-        if (ss.ref == kNone) {
-          float4 ra = pool.col[4u * (size_t)slot + 1u];
-          ra.x += so.sh_c.x; ra.y += so.sh_c.y; ra.z += so.sh_c.z;
-          pool.col[4u * (size_t)slot + 1u] = ra;
+      if (slot == kNone && !exhausted) {
+        const uint32_t t = atomicAdd(&wc->tail_head, 1u);
+        if (t < n) {
+          uint32_t i = t;
+          do { i = (i * 0x9E3779B1u) & mask; } while (i >= n);
+          slot = q.active[0][i];
+        } else {
+          exhausted = true;
         }
       }
-      if (so.finished) {
-        ++c_paths;
-        if (so.contributes) {
-          atomicAdd(accum + 3u * (size_t)so.fin_pixel + 0, so.fin_L.x);
-          atomicAdd(accum + 3u * (size_t)so.fin_pixel + 1, so.fin_L.y);
-          atomicAdd(accum + 3u * (size_t)so.fin_pixel + 2, so.fin_L.z);
+      const uint32_t live = __ballot_sync(0xffffffffu, slot != kNone);
+      if (!live) break;
+      const bool active = slot != kNone;
+      // ---- closest hit (k_trace), kCoopRays rays at a time
+      Ray ray;
+      TraceResult tr;
+      tr.t = 0.0f;
+      tr.ref = kNone;
+      if (active) {
+        float4 o4, d4;
+        ldg256_rw(pool.ray + 4u * (size_t)slot, o4, d4);
+        ray = make_ray(from4(o4), from4(d4));
+      }
+      for (uint32_t todo = live; todo;) {
+        const bool mine = ((todo >> lane) & 1u) && (uint32_t)__popc(todo & lt) < kCoopRays;
+        const uint32_t bm = __ballot_sync(0xffffffffu, mine);
+        const uint32_t r = (uint32_t)__popc(bm & lt);
+        if (mine) coop_set_ray(cw, r, ray, __int_as_float(0x7f800000), kNone);
+        __syncwarp();
+        coop_trace<false>(sc, cw, (uint32_t)__popc(bm));
+        if (mine) {
+          tr.ref = cw.ref[r];
+          tr.t = tr.ref == kNone ? 0.0f : __uint_as_float((uint32_t)(cw.best[r] >> 32));
         }
-        q.bin[slot] = (uint8_t)kBinDead;
-        break;
+        __syncwarp();  // answers read before the next batch overwrites them
+        todo &= ~bm;
+      }
+      // ---- shade (k_shade)
+      ShadeOut so;
+      if (active) {
+        ++c_bounce;
+        tail_shade<METHOD, FULL>(sc, pool, rp, slot, ray, tr, so);
+        if (METHOD == PTB_METHOD_NAIVE) ++c_ref;            // Q7: naive counts every check_hit ...
+        else if (so.alive) ++c_ref;                         // ... MIS every bounce iteration that continues
+      }
+      // ---- NEE visibility (k_shadow): unoccluded contributions join the path's radiance
+      if (METHOD == PTB_METHOD_MIS) {
+        const bool sh = active && so.shadow;
+        if (sh) { if (so.shadow_is_sky) ++c_sky; else ++c_light; }
+        for (uint32_t todo = __ballot_sync(0xffffffffu, sh); todo;) {
+          const bool mine = ((todo >> lane) & 1u) && (uint32_t)__popc(todo & lt) < kCoopRays;
+          const uint32_t bm = __ballot_sync(0xffffffffu, mine);
+          const uint32_t r = (uint32_t)__popc(bm & lt);
+          if (mine) coop_set_ray(cw, r, make_ray(from4(so.sh_o), from4(so.sh_d)), so.sh_o.w, __float_as_uint(so.sh_d.w));
+          __syncwarp();
+          coop_trace<true>(sc, cw, (uint32_t)__popc(bm));
+          if (mine && cw.ref[r] == kNone) tail_add_nee(pool, slot, so);
+          __syncwarp();
+          todo &= ~bm;
+        }
+      }
+      if (active && so.finished) {
+        ++c_paths;
+        tail_finish(accum, q, slot, so);
+        slot = kNone;
+      }
+    }
+  } else {
+    typename TR::Scratch scratch;
+    for (;;) {
+      const uint32_t i = atomicAdd(&wc->tail_head, 1u);
+      if (i >= n) break;
+      const uint32_t s = q.active[0][i];
+      for (;;) {
+        float4 o4, d4;
+        ldg256_rw(pool.ray + 4u * (size_t)s, o4, d4);
+        const Ray ray = make_ray(from4(o4), from4(d4));
+        const TraceResult tr = trace_lane<TR, false>(sc, ray, __int_as_float(0x7f800000), kNone, scratch);
+        ++c_bounce;
+        ShadeOut so;
+        tail_shade<METHOD, FULL>(sc, pool, rp, s, ray, tr, so);
+        if (METHOD == PTB_METHOD_NAIVE) ++c_ref;
+        else if (so.alive) ++c_ref;
+        if (METHOD == PTB_METHOD_MIS && so.shadow) {
+          if (so.shadow_is_sky) ++c_sky; else ++c_light;
+          const Ray sray = make_ray(from4(so.sh_o), from4(so.sh_d));
+          const TraceResult ss = trace_lane<TR, true>(sc, sray, so.sh_o.w, __float_as_uint(so.sh_d.w), scratch);
+          if (ss.ref == kNone) tail_add_nee(pool, s, so);
+        }
+        if (so.finished) {
+          ++c_paths;
+          tail_finish(accum, q, s, so);
+          break;
+        }
       }
     }
   }
   // statistics: one set of atomics per warp
+  __syncwarp();
+#ifdef PTB_TAIL_STATS
+  PTB_TS(4, c_bounce);
+  if (threadIdx.x == 0u && blockIdx.x == 0u) { PTB_TS(0, 1); PTB_TS(1, n); }
+  if (lane == 0u) atomicMax(&g_tail_stats[10], global_timer_ns());
+#endif
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     c_bounce += __shfl_xor_sync(0xffffffffu, c_bounce, o);
@@ -1756,6 +1865,18 @@ static void prof_collect(Ctx* c, int half, bool mis) {  // half = ring position 
   }
 }
 static void dump_lane_stats() {
+#ifdef PTB_TAIL_STATS  // tuning builds: what the fused tail's two phases did (per ptb_render call)
+  {
+    unsigned long long ts[16];
+    cudaMemcpyFromSymbol(ts, g_tail_stats, sizeof(ts));
+    fprintf(stderr, "tail_stats launches %llu paths %llu bounces %llu | cooperative traces %llu, rounds %llu (%.1f per trace, %.2f us each), "
+            "entries %llu (%.1f per round), culled at pop %llu | all warps done after %.3f ms\n", ts[0], ts[1], ts[4], ts[5], ts[6],
+            (double)ts[6] / (ts[5] ? ts[5] : 1), 1e-3 * (double)ts[13] / (ts[6] ? ts[6] : 1), ts[7], (double)ts[7] / (ts[6] ? ts[6] : 1), ts[12],
+            1e-6 * (double)(ts[10] - ts[9]));
+    unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, ~0ull, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_tail_stats, z, sizeof(z));
+  }
+#endif
 #ifdef PTB_LANE_STATS  // tuning builds (scripts/lane_stats.sh): where the lanes of persistent_trace spent their iterations
   unsigned long long ls[8];
   cudaMemcpyFromSymbol(ls, g_lane_stats, sizeof(ls));
@@ -1795,8 +1916,11 @@ static void launch_shade(const RenderSetup& rs, Ctx* c, const SlotRefs& sl, uint
     else k_shade<PTB_METHOD_NAIVE, false, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first);
   }
 }
+static const void* tail_fn(const RenderSetup& rs, Ctx* c) {
+  return c->wide ? tail_kernel_of<CwTrav>(rs.mis, rs.full) : tail_kernel_of<BinTrav>(rs.mis, rs.full);
+}
 static void launch_tail(const RenderSetup& rs, Ctx* c, const SlotRefs& sl, uint32_t grid, cudaStream_t st, uint32_t depth) {
-  const void* fn = c->wide ? tail_kernel_of<CwTrav>(rs.mis, rs.full) : tail_kernel_of<BinTrav>(rs.mis, rs.full);
+  const void* fn = tail_fn(rs, c);
   WaveCounters* wc = sl.wc;
   float* accum = rs.accum;
   void* args[] = {(void*)&c->dev, (void*)&sl.pool, (void*)&sl.q, (void*)&wc, (void*)&rs.rp, (void*)&accum, (void*)&depth};
@@ -1871,6 +1995,16 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   uint32_t grid_tail = (uint32_t)c->sm_count;  // blocks of 128 threads (PTB_TAIL_BLOCKS)
   if (const char* e = getenv("PTB_TAIL_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= 65535) grid_tail = (uint32_t)v; }
   if (grid_tail > (tail_paths + 127u) / 128u) grid_tail = (tail_paths + 127u) / 128u;
+  // The call's last tail has the machine to itself: one lane per path, but never more blocks than are resident at once
+  // (45 KB of shared memory each) — a block that starts only when another has finished would keep the work queue from
+  // running empty, which is what lets a warp go cooperative.
+  uint32_t grid_tail_last = (tail_paths + 127u) / 128u;
+  if (tail_paths) {
+    cudaFuncSetAttribute(tail_fn(rs, c), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const uint32_t resident = (uint32_t)persistent_grid(c, tail_fn(rs, c), 128);
+    if (grid_tail_last > resident) grid_tail_last = resident;
+    if (grid_tail > resident) grid_tail = resident;
+  }
   // Two chunks are in flight at any time, one per slot, each on its own stream: the block scheduler fills the drain of
   // one chunk's persistent kernel (its last long rays) and its small late iterations with the other chunk's blocks. The
   // FIRST chunk is half as long as the others, so the two streams stay half a chunk out of phase — while one is in its
@@ -1954,7 +2088,7 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
       PTB_CUDA_TRY(c, cudaEventRecord(c->ev_head_done[sl], s));
       PTB_CUDA_TRY(c, cudaStreamWaitEvent(c->s_tail, c->ev_head_done[sl], 0));
       // (the last chunk's tail has nothing beside it: one lane per path instead of one block per SM)
-      launch_tail(rs, c, S, R.last ? (tail_paths + 127u) / 128u : grid_tail, c->s_tail, (uint32_t)depth);
+      launch_tail(rs, c, S, R.last ? grid_tail_last : grid_tail, c->s_tail, (uint32_t)depth);
       PTB_CUDA_TRY(c, cudaEventRecord(c->ev_tail_done[sl], c->s_tail));
       R.tail_pending = true;
       c->stats.kernel_launches += 1;

@@ -353,7 +353,9 @@ def test_fused_tail_hand_over_does_not_change_the_result(ptb, gpu_ctx, overshado
     lane) instead of ~45 nearly empty wavefront iterations. Same functions, same records, same RNG counters: the image and
     every ray counter are independent of where the hand-over happens (PTB_TAIL_PATHS: 0 = never, default 65 536, and a
     hand-over forced right after the first bounce)."""
-    scenes = [overshadowed, ptb.meshgen.c3_scene(0.05)] if method == 0 else [overshadowed]
+    # overshadowed (14 primitives) takes the tail's lane walk, the 50 000-triangle mesh its warp-cooperative walk
+    # (closest hit for both methods, any-hit for the NEE rays of MIS)
+    scenes = [overshadowed, ptb.meshgen.c3_scene(0.05)]
     for scene in scenes:
         sc = ptb.Scene(scene, ctx=gpu_ctx)
         o = ptb.RenderOptions(samples_per_pixel=16, render_method=method, width=160, height=90, seed=4)

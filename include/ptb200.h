@@ -228,6 +228,12 @@ int32_t ptb_scene_commit(ptb_ctx* ctx, uint32_t build_flags);
  * (1 node when n_prims == 1). Any pointer may be NULL. */
 int32_t ptb_bvh_info(ptb_ctx* ctx, uint64_t* n_prims, uint64_t* n_nodes);
 int32_t ptb_bvh_export(ptb_ctx* ctx, uint32_t* morton_sorted, uint32_t* prim_sorted, ptb_bvh_node* nodes);
+/* The same binary tree as the traversal kernels read it (bit-exact test hook): 32 bytes per node, both children's boxes
+ * snapped outwards onto a 65536^3 grid over the scene box — eight 32-bit words {left box x, y, z, right box x, y, z (each:
+ * low half = min, high half = max grid coordinate), left, right}; frame = grid origin xyz, grid step xyz
+ * (plane = origin + q * step). nodes32 receives nothing when the committed scene uses the wide tree. CPU definition:
+ * oracle/lbvh_ref.hpp. Any pointer may be NULL. */
+int32_t ptb_bvh_export_quantised(ptb_ctx* ctx, float frame[6], void* nodes32);
 
 /* The compressed 8-wide tree, for bit-exact tests: *n_nodes = 0 when the committed scene uses the binary tree. Nodes are
  * 96 bytes each (layout: raytracing-rust_b200/csrc/ptb_common.cuh CwNode == oracle/cwbvh_ref.hpp CwNode), slot_prim maps

@@ -144,6 +144,52 @@ struct Lbvh {
     }
   }
 
+  // The 32-byte nodes the device's traversal kernels read (lbvh_build.cu: k_qframe / k_quantise_nodes), restated: grid over
+  // the scene box (union of the root's child boxes), q_step = (float)(extent / 65535) moved up until the grid reaches the
+  // far side, boxes snapped outwards in f64. Words per node: left box x, y, z, right box x, y, z (low half min, high
+  // half max), left, right. frame = origin xyz, step xyz.
+  static uint32_t q_floor(float v, float mn, float step) {
+    if (!(step > 0.0f)) return 0u;
+    double q = std::floor(((double)v - (double)mn) / (double)step);
+    q = q < 0.0 ? 0.0 : (q > 65535.0 ? 65535.0 : q);
+    while (q > 0.0 && (double)mn + q * (double)step > (double)v) q -= 1.0;
+    return (uint32_t)q;
+  }
+  static uint32_t q_ceil(float v, float mn, float step) {
+    if (!(step > 0.0f)) return 0u;
+    double q = std::ceil(((double)v - (double)mn) / (double)step);
+    q = q < 0.0 ? 0.0 : (q > 65535.0 ? 65535.0 : q);
+    while (q < 65535.0 && (double)mn + q * (double)step < (double)v) q += 1.0;
+    return (uint32_t)q;
+  }
+  void quantise(float frame[6], std::vector<uint32_t>& words) const {
+    words.assign(nodes.size() * 8, 0u);
+    for (int k = 0; k < 6; ++k) frame[k] = 0.0f;
+    if (nodes.empty()) return;
+    const ptb_bvh_node& r = nodes[0];
+    for (int k = 0; k < 3; ++k) {
+      const float mn = fmin_(r.lmin[k], r.rmin[k]), mx = fmax_(r.lmax[k], r.rmax[k]);
+      const double ext = (double)mx - (double)mn;
+      float step = (float)(ext / 65535.0);
+      if (ext > 0.0)
+        while ((double)mn + 65535.0 * (double)step < (double)mx) step = std::nextafterf(step, INF_F);
+      else
+        step = 0.0f;
+      frame[k] = mn;
+      frame[3 + k] = step;
+    }
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      const ptb_bvh_node& nd = nodes[i];
+      uint32_t* w = &words[8 * i];
+      for (int k = 0; k < 3; ++k) {
+        w[k] = q_floor(nd.lmin[k], frame[k], frame[3 + k]) | (q_ceil(nd.lmax[k], frame[k], frame[3 + k]) << 16);
+        w[3 + k] = q_floor(nd.rmin[k], frame[k], frame[3 + k]) | (q_ceil(nd.rmax[k], frame[k], frame[3 + k]) << 16);
+      }
+      w[6] = nd.left;
+      w[7] = nd.right;
+    }
+  }
+
   // The device's slab test (ptb_intersect.cuh box_entry), restated operation for operation: aabb.rs:22-57 with one fma
   // per plane (plane * dinv - o * dinv, the product hoisted per ray), near / far plane chosen by the direction's sign,
   // near distances moved down / far distances moved up by e_i = 2 eps |o_i dinv_i|, far side widened by 1 + 4 gamma(3).

@@ -59,6 +59,10 @@ def _load():
     lib.orc_render.argtypes = [P, C.POINTER(RenderOpts), P, C.c_int, P]
     lib.orc_radiance.argtypes = [P, P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, P]
     lib.orc_lbvh_build.argtypes = [P]
+    lib.orc_lbvh_ploc.argtypes = [P, C.c_int]
+    lib.orc_lbvh_snap16.argtypes = [P, C.c_float]
+    lib.orc_lbvh_quantise.argtypes = [P, P, P]
+    lib.orc_lbvh_ploc.restype = C.c_int
     lib.orc_lbvh_export.argtypes = [P, P, P, P]
     lib.orc_lbvh_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_lbvh_node_counts.argtypes = [P, P, C.c_size_t, P, C.c_int]
@@ -247,6 +251,25 @@ class OracleScene:
     def lbvh_build(self):
         lib.orc_lbvh_build(self._h)
         self._lbvh = True
+
+    def lbvh_ploc(self, radius=16):
+        """Replaces the LBVH's hierarchy by the PLOC hierarchy over the same Morton order (ploc_ref.hpp); returns the rounds."""
+        self._lbvh = True
+        return lib.orc_lbvh_ploc(self._h, radius)
+
+    def lbvh_quantise(self):
+        """(frame, (m, 8) uint32 words): the 32-byte traversal nodes of the LBVH, CPU definition (lbvh_ref.hpp quantise)."""
+        if not self._lbvh:
+            self.lbvh_build()
+        m = lib.orc_lbvh_num_nodes(self._h)
+        frame = np.zeros(6, np.float32)
+        words = np.zeros((m, 8), np.uint32)
+        lib.orc_lbvh_quantise(self._h, _p(frame), _p(words))
+        return frame, words
+
+    def lbvh_snap16(self, extra=0.0):
+        """Experiment: child boxes snapped outwards onto a 65536^3 grid over the scene box, plus `extra` steps per side."""
+        lib.orc_lbvh_snap16(self._h, extra)
 
     def lbvh_export(self):
         if not self._lbvh:

@@ -10,6 +10,7 @@
 
 #include "cwbvh_ref.hpp"
 #include "lbvh_ref.hpp"
+#include "ploc_ref.hpp"
 #include "ref_integrators.hpp"
 
 namespace ref {
@@ -312,6 +313,37 @@ int orc_lbvh_build(orc_scene* s) {
   return 0;
 }
 size_t orc_lbvh_num_nodes(const orc_scene* s) { return s->lbvh.nodes.size(); }
+void orc_lbvh_quantise(const orc_scene* s, float frame[6], uint32_t* words) {
+  std::vector<uint32_t> w;
+  s->lbvh.quantise(frame, w);
+  if (words) for (size_t i = 0; i < w.size(); ++i) words[i] = w[i];
+}
+// experiment: snaps every child box of the LBVH outwards onto a 65536^3 grid over the scene box, plus `extra` grid steps
+// per side (what a 16-bit quantised node would let the traversal see)
+void orc_lbvh_snap16(orc_scene* s, float extra) {
+  Lbvh& l = s->lbvh;
+  if (l.nodes.empty()) return;
+  float mn[3], mx[3];
+  const ptb_bvh_node& r = l.nodes[0];
+  for (int k = 0; k < 3; ++k) { mn[k] = std::fmin(r.lmin[k], r.rmin[k]); mx[k] = std::fmax(r.lmax[k], r.rmax[k]); }
+  for (ptb_bvh_node& nd : l.nodes) {
+    float* lo[2] = {nd.lmin, nd.rmin};
+    float* hi[2] = {nd.lmax, nd.rmax};
+    for (int c = 0; c < 2; ++c)
+      for (int k = 0; k < 3; ++k) {
+        const double step = ((double)mx[k] - (double)mn[k]) / 65535.0;
+        if (!(step > 0.0)) continue;
+        const double ql = std::floor(((double)lo[c][k] - mn[k]) / step) - extra, qh = std::ceil(((double)hi[c][k] - mn[k]) / step) + extra;
+        lo[c][k] = (float)(mn[k] + ql * step);
+        hi[c][k] = (float)(mn[k] + qh * step);
+      }
+  }
+}
+// replaces the LBVH's Karras hierarchy by the PLOC hierarchy over the same Morton order (ploc_ref.hpp); returns the rounds
+int orc_lbvh_ploc(orc_scene* s, int radius) {
+  if (!s->lbvh_built) orc_lbvh_build(s);
+  return ploc_rebuild(s->lbvh, radius);
+}
 void orc_lbvh_export(const orc_scene* s, uint32_t* morton, uint32_t* prim_sorted, ptb_bvh_node* nodes) {
   const Lbvh& l = s->lbvh;
   if (morton) for (size_t i = 0; i < l.morton.size(); ++i) morton[i] = l.morton[i];

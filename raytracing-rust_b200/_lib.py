@@ -103,6 +103,7 @@ SYMBOLS = [
     ("ptb_scene_commit", C.c_int32, [_P, C.c_uint32]),
     ("ptb_bvh_info", C.c_int32, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("ptb_bvh_export", C.c_int32, [_P, _P, _P, _P]),
+    ("ptb_bvh_export_quantised", C.c_int32, [_P, _P, _P]),
     ("ptb_bvh_wide_info", C.c_int32, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
     ("ptb_bvh_wide_export", C.c_int32, [_P, _P, _P]),
     ("ptb_closest_hit", C.c_int32, [_P, _P, C.c_size_t, _P]),

@@ -113,6 +113,14 @@ class Context:
         _check(self._h, L.lib.ptb_bvh_export(self._h, L.ptr(morton), L.ptr(prims), L.ptr(nodes)))
         return morton, prims, nodes
 
+    def bvh_export_quantised(self):
+        """(frame: grid origin xyz + grid step xyz, nodes (m, 8) uint32: the 32-byte nodes the traversal kernels read)."""
+        _, m = self.bvh_info()
+        frame = np.zeros(6, np.float32)
+        nodes = np.zeros((m, 8), np.uint32)
+        _check(self._h, L.lib.ptb_bvh_export_quantised(self._h, L.ptr(frame), L.ptr(nodes)))
+        return frame, nodes
+
     def bvh_wide_info(self):
         """(number of 96-byte nodes of the compressed 8-wide tree — 0 when the scene uses the binary tree, max leaf size)."""
         n, m = C.c_uint64(), C.c_uint32()

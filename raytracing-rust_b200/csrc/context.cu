@@ -296,6 +296,22 @@ int32_t ptb_bvh_export(ptb_ctx* ctx, uint32_t* morton_sorted, uint32_t* prim_sor
   return PTB_OK;
 }
 
+int32_t ptb_bvh_export_quantised(ptb_ctx* ctx, float frame[6], void* nodes32) {
+  CTX_OR_FAIL(ctx);
+  if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
+  if (!PTB_QNODES) return set_error(c, PTB_ERR_UNSUPPORTED, "this build walks the 64-byte nodes (compile with -DPTB_QNODES=1)");
+  if (frame)
+    for (int k = 0; k < 3; ++k) { frame[k] = c->dev.q_min[k]; frame[3 + k] = c->dev.q_step[k]; }
+  if (c->n_prims == 0 || c->wide || !nodes32) return PTB_OK;
+  PTB_CUDA_TRY(c, cudaMemcpyAsync(nodes32, c->d_qnodes.p, c->n_nodes * 32, cudaMemcpyDeviceToHost, c->stream));
+  PTB_CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+  uint32_t* w = static_cast<uint32_t*>(nodes32);  // the sphere flag of leaf references is device-internal
+  for (uint64_t i = 0; i < c->n_nodes; ++i)
+    for (int k = 6; k < 8; ++k)
+      if (w[8 * i + k] & PTB_LEAF_BIT) w[8 * i + k] &= ~kSphereBit;
+  return PTB_OK;
+}
+
 int32_t ptb_bvh_wide_info(ptb_ctx* ctx, uint64_t* n_nodes, uint32_t* max_leaf) {
   CTX_OR_FAIL(ctx);
   if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");

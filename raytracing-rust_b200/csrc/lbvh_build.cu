@@ -344,6 +344,58 @@ __global__ void k_single_node(const uint32_t* __restrict__ prim_sorted, uint32_t
   nodes[0].n3 = make_uint4(ref, ref, kNone, 0u);
 }
 
+// ------------------------------------------------------------------------------------------ 16-bit traversal nodes
+// The traversal kernels read 32-byte nodes (ptb_intersect.cuh: 16-bit boxes); CPU definition: oracle/lbvh_ref.hpp
+// quantise(). Grid: the scene box = union of the root's two child boxes; per axis q_step = (float)(extent / 65535), moved
+// up until q_min + 65535 * q_step reaches the far side (f64), 0 for a flat axis. A box is snapped OUTWARDS in f64:
+// q_lo = floor((lo - q_min) / q_step) stepped down while q_min + q_lo * q_step > lo, q_hi the mirror image.
+__global__ void k_qframe(const BvhNode* __restrict__ nodes, float* __restrict__ frame) {
+  const BvhNode r = nodes[0];
+  const float mn[3] = {fminf(r.n0.x, r.n1.z), fminf(r.n0.y, r.n1.w), fminf(r.n0.z, r.n2.x)};
+  const float mx[3] = {fmaxf(r.n0.w, r.n2.y), fmaxf(r.n1.x, r.n2.z), fmaxf(r.n1.y, r.n2.w)};
+  for (int k = 0; k < 3; ++k) {
+    const double ext = (double)mx[k] - (double)mn[k];
+    float step = (float)(ext / 65535.0);
+    if (ext > 0.0)
+      while ((double)mn[k] + 65535.0 * (double)step < (double)mx[k]) step = __uint_as_float(__float_as_uint(step) + 1u);
+    else
+      step = 0.0f;
+    frame[k] = mn[k];
+    frame[3 + k] = step;
+  }
+}
+PTB_DEV uint32_t q_floor(float v, float mn, float step) {
+  if (!(step > 0.0f)) return 0u;
+  double q = floor(((double)v - (double)mn) / (double)step);
+  q = q < 0.0 ? 0.0 : (q > 65535.0 ? 65535.0 : q);
+  while (q > 0.0 && (double)mn + q * (double)step > (double)v) q -= 1.0;
+  return (uint32_t)q;
+}
+PTB_DEV uint32_t q_ceil(float v, float mn, float step) {
+  if (!(step > 0.0f)) return 0u;
+  double q = ceil(((double)v - (double)mn) / (double)step);
+  q = q < 0.0 ? 0.0 : (q > 65535.0 ? 65535.0 : q);
+  while (q < 65535.0 && (double)mn + q * (double)step < (double)v) q += 1.0;
+  return (uint32_t)q;
+}
+__global__ void __launch_bounds__(256)
+k_quantise_nodes(const BvhNode* __restrict__ nodes, uint32_t n_nodes, const float* __restrict__ frame, uint4* __restrict__ qnodes) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const BvhNode nd = nodes[i];
+  const float mn[3] = {frame[0], frame[1], frame[2]}, st[3] = {frame[3], frame[4], frame[5]};
+  const float llo[3] = {nd.n0.x, nd.n0.y, nd.n0.z}, lhi[3] = {nd.n0.w, nd.n1.x, nd.n1.y};
+  const float rlo[3] = {nd.n1.z, nd.n1.w, nd.n2.x}, rhi[3] = {nd.n2.y, nd.n2.z, nd.n2.w};
+  uint32_t l[3], r[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    l[k] = q_floor(llo[k], mn[k], st[k]) | (q_ceil(lhi[k], mn[k], st[k]) << 16);
+    r[k] = q_floor(rlo[k], mn[k], st[k]) | (q_ceil(rhi[k], mn[k], st[k]) << 16);
+  }
+  qnodes[2u * (size_t)i] = make_uint4(l[0], l[1], l[2], r[0]);
+  qnodes[2u * (size_t)i + 1u] = make_uint4(r[1], r[2], nd.n3.x, nd.n3.y);
+}
+
 // ------------------------------------------------------------------------------------------ gather into slot order
 __global__ void k_gather(const ptb_sphere* __restrict__ spheres, uint32_t n_spheres, const ptb_triangle* __restrict__ tris,
                          uint32_t n_prims, const uint32_t* __restrict__ prim_sorted, const DevMaterial* __restrict__ mats,
@@ -548,7 +600,7 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
   c->dev.n_prims = (uint32_t)n;
   c->dev.n_lights = 0;
   c->dev.geom = nullptr; c->dev.normals = nullptr; c->dev.slot_prim = nullptr; c->dev.slot_mat = nullptr;
-  c->dev.nodes = nullptr; c->dev.lights = nullptr; c->dev.cw_nodes = nullptr;
+  c->dev.nodes = nullptr; c->dev.qnodes = nullptr; c->dev.lights = nullptr; c->dev.cw_nodes = nullptr;
   c->wide = false;
   if (n == 0) {
     c->committed = true;
@@ -562,7 +614,7 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
   DevBuf &bmin = c->scratch[0], &bmax = c->scratch[1], &bounds = c->scratch[2], &keys_a = c->scratch[3], &keys_b = c->scratch[4],
          &vals_a = c->scratch[5], &vals_b = c->scratch[6], &hist = c->scratch[7], &leaf_parent = c->scratch[8],
          &nbmin = c->scratch[9], &nbmax = c->scratch[10], &flags = c->scratch[11], &prim_slot = c->scratch[12],
-         &d_light_prims = c->scratch[13], &d_light_tmp = c->scratch[14], &d_light_out = c->scratch[15];
+         &d_light_prims = c->scratch[13], &d_light_tmp = c->scratch[14], &d_light_out = c->scratch[15], &d_qframe = c->scratch[16];
   const uint32_t n32 = (uint32_t)n, ns32 = (uint32_t)ns, nt32 = (uint32_t)nt;
   PTB_CUDA_TRY(c, bmin.reserve(n * 16));
   PTB_CUDA_TRY(c, bmax.reserve(n * 16));
@@ -581,6 +633,8 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
   PTB_CUDA_TRY(c, d_light_tmp.reserve(n * 4));
   PTB_CUDA_TRY(c, d_light_out.reserve(8));
   PTB_CUDA_TRY(c, c->d_nodes.reserve(c->n_nodes * sizeof(BvhNode)));
+  if (PTB_QNODES) PTB_CUDA_TRY(c, c->d_qnodes.reserve(c->n_nodes * 32));
+  PTB_CUDA_TRY(c, d_qframe.reserve(6 * 4));
   PTB_CUDA_TRY(c, c->d_geom.reserve(n * 48));
   PTB_CUDA_TRY(c, c->d_normals.reserve(n * 48));
   PTB_CUDA_TRY(c, c->d_slot_mat.reserve(n * 4));
@@ -634,6 +688,15 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
                               c->d_nodes.as<BvhNode>(), nbmin.as<float4>(), nbmax.as<float4>(), flags.as<uint32_t>());
     c->stats.kernel_launches += 2;
   }
+  // the 32-byte nodes the traversal kernels read, and their grid (6 floats, read back with the light count below)
+  float h_qframe[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (!wide && PTB_QNODES) {
+    k_qframe<<<1, 1, 0, st>>>(c->d_nodes.as<BvhNode>(), d_qframe.as<float>());
+    k_quantise_nodes<<<((uint32_t)c->n_nodes + T - 1) / T, T, 0, st>>>(c->d_nodes.as<BvhNode>(), (uint32_t)c->n_nodes, d_qframe.as<float>(),
+                                                                     c->d_qnodes.as<uint4>());
+    PTB_CUDA_TRY(c, cudaMemcpyAsync(h_qframe, d_qframe.p, sizeof h_qframe, cudaMemcpyDeviceToHost, st));
+    c->stats.kernel_launches += 2;
+  }
   // slot order of the geometry: Morton order for the binary tree, the wide tree's own primitive order otherwise
   const uint32_t* slot_order = va;
   if (wide) {
@@ -681,6 +744,8 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
   c->dev.slot_prim = c->d_slot_prim.as<uint32_t>();
   c->dev.slot_mat = c->d_slot_mat.as<uint32_t>();
   c->dev.nodes = c->d_nodes.as<BvhNode>();
+  c->dev.qnodes = (wide || !PTB_QNODES) ? nullptr : c->d_qnodes.as<uint4>();
+  for (int k = 0; k < 3; ++k) { c->dev.q_min[k] = h_qframe[k]; c->dev.q_step[k] = h_qframe[3 + k]; }
   c->dev.cw_nodes = wide ? c->d_cw_nodes.as<CwNode>() : nullptr;
   c->wide = wide;
   if (!wide) c->n_cw_nodes = 0;

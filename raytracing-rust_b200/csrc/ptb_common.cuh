@@ -19,6 +19,9 @@ constexpr float kPi = 3.14159265358979323846f;
 constexpr float kTau = 6.28318530717958647692f;
 constexpr float kEpsRt = 3.0e-4f;          // rt_core/src/lib.rs:28  EPSILON
 constexpr float kF32Eps = 1.1920929e-7f;   // f32::EPSILON
+#ifndef PTB_QNODES
+#define PTB_QNODES 0  // 1: the binary tree's traversal kernels read 32-byte nodes with 16-bit boxes (ptb_intersect.cuh)
+#endif
 constexpr uint32_t kSphereBit = 0x40000000u;  // device-internal: leaf reference points at a sphere slot
 constexpr uint32_t kSlotMask = 0x3FFFFFFFu;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
@@ -295,7 +298,9 @@ struct DevScene {
   const float4* normals;      // 3 x float4 per slot (triangles only): n0, n1, n2
   const uint32_t* slot_prim;  // slot -> original primitive id (loader order)
   const uint32_t* slot_mat;   // slot -> (material kind << 24) | material index
-  const BvhNode* nodes;       // binary LBVH (leaf references: Morton position; traversed when `cw_nodes` is null)
+  const BvhNode* nodes;       // binary LBVH (leaf references: Morton position), f32 boxes: the build's product, exported as is
+  const uint4* qnodes;        // the same tree as the traversal kernels read it: 32-byte nodes, 16-bit boxes (2 x uint4 per node)
+  float q_min[3], q_step[3];  // their grid: plane(q) = q_min + q * q_step, exactly
   const CwNode* cw_nodes;     // compressed 8-wide tree over the same primitives; geometry is then in ITS primitive order
   const DevMaterial* materials;
   const DevTexture* textures;

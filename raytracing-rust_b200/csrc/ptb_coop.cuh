@@ -24,7 +24,10 @@ namespace ptb {
 
 constexpr uint32_t kCoopRays = 16;    // rays that may share a warp's frontier (tag in the cull key's low 5 bits)
 constexpr uint32_t kCoopTagMask = 31u;
-constexpr uint32_t kCoopCap = 1024;   // stack entries per warp
+#ifndef PTB_COOP_CAP
+#define PTB_COOP_CAP 1024
+#endif
+constexpr uint32_t kCoopCap = PTB_COOP_CAP;   // stack entries per warp
 constexpr uint32_t kCoopSoft = kCoopCap - 96u;  // above it: one entry per round (<= +1 entry per tree level, depth <= 62)
 
 #ifdef PTB_TAIL_STATS  // tuning builds: [0] launches with work [1] paths [2] lane-walk bounces [3] paths handed to the cooperative
@@ -38,8 +41,8 @@ __device__ unsigned long long g_tail_stats[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, ~0u
 
 struct CoopRay {  // what a node test and a primitive test need of a ray, 80 bytes
   float ox, oy, oz, dx, dy, dz, shx, shy, shz;
-  uint32_t swap_xz;
-  float ix, iy, iz, lx, ly, lz, hx, hy, hz;  // SlabRay: dinv, c_lo, c_hi
+  uint32_t swap_xz;  // bit 0: Ray::swap_xz (PTB_QNODES: bits 1-3 = the direction is negative along x / y / z)
+  float ax, ay, az, lx, ly, lz, hx, hy, hz;  // the slab constants: SlabRay dinv, c_lo, c_hi (PTB_QNODES: QSlabRay a, b_lo, b_hi)
   uint32_t exclude;                           // any-hit: slot that does not block (the surface the ray leaves), else kNone
 };
 struct CoopWarp {
@@ -49,16 +52,23 @@ struct CoopWarp {
   uint2 stack[kCoopCap];
 };
 
-PTB_DEV void coop_set_ray(CoopWarp& cw, uint32_t j, const Ray& ray, float tmax, uint32_t exclude) {
-  const SlabRay s = make_slab_ray(ray);
+PTB_DEV void coop_set_ray(const DevScene& sc, CoopWarp& cw, uint32_t j, const Ray& ray, float tmax, uint32_t exclude) {
+  const BinRayCtx s = make_bin_ray(sc, ray);
   CoopRay& r = cw.ray[j];
   r.ox = ray.o.x; r.oy = ray.o.y; r.oz = ray.o.z;
   r.dx = ray.d.x; r.dy = ray.d.y; r.dz = ray.d.z;
   r.shx = ray.shear.x; r.shy = ray.shear.y; r.shz = ray.shear.z;
-  r.swap_xz = ray.swap_xz ? 1u : 0u;
-  r.ix = s.dinv.x; r.iy = s.dinv.y; r.iz = s.dinv.z;
+#if PTB_QNODES
+  r.ax = s.a.x; r.ay = s.a.y; r.az = s.a.z;
+  r.lx = s.b_lo.x; r.ly = s.b_lo.y; r.lz = s.b_lo.z;
+  r.hx = s.b_hi.x; r.hy = s.b_hi.y; r.hz = s.b_hi.z;
+  r.swap_xz = (ray.swap_xz ? 1u : 0u) | (s.sn_x == kSelHigh ? 2u : 0u) | (s.sn_y == kSelHigh ? 4u : 0u) | (s.sn_z == kSelHigh ? 8u : 0u);
+#else
+  r.ax = s.dinv.x; r.ay = s.dinv.y; r.az = s.dinv.z;
   r.lx = s.c_lo.x; r.ly = s.c_lo.y; r.lz = s.c_lo.z;
   r.hx = s.c_hi.x; r.hy = s.c_hi.y; r.hz = s.c_hi.z;
+  r.swap_xz = ray.swap_xz ? 1u : 0u;
+#endif
   r.exclude = exclude;
   cw.best[j] = ((unsigned long long)__float_as_uint(tmax) << 32) | 0xFFFFFFFFull;
   cw.ref[j] = kNone;
@@ -110,11 +120,21 @@ PTB_DEV void coop_trace(const DevScene& sc, CoopWarp& cw, uint32_t n_rays) {
     const bool leaf = has && (e.x & PTB_LEAF_BIT);
     const bool node = has && !leaf;
     // ---- loads of both kinds first, so that their latencies overlap
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a, d = a;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+    uint4 qa = make_uint4(0u, 0u, 0u, 0u), qb = qa;
+    uint32_t orig = 0u;
     if (node) {
+#if PTB_QNODES
+      ldg256u(sc.qnodes + 2u * (size_t)e.x, qa, qb);
+#else
+      float4 d;
       ldg256(sc.nodes + e.x, a, b);
       ldg256(reinterpret_cast<const float4*>(sc.nodes + e.x) + 2, c, d);
+      qb.z = __float_as_uint(d.x);
+      qb.w = __float_as_uint(d.y);
+#endif
     } else if (leaf) {
+      orig = __ldg(sc.slot_prim + (e.x & kSlotMask));  // tie-break id, fetched beside the geometry rather than after the test
       const float4* g = sc.geom + 3u * (size_t)(e.x & kSlotMask);
       a = __ldg(g);
       if (!(e.x & kSphereBit)) { b = __ldg(g + 1); c = __ldg(g + 2); }
@@ -125,14 +145,26 @@ PTB_DEV void coop_trace(const DevScene& sc, CoopWarp& cw, uint32_t n_rays) {
     unsigned long long packed = 0ull;
     bool candidate = false;
     if (node) {
+      float tl, tr;
+#if PTB_QNODES
+      QSlabRay s;
+      s.a = mk(r.ax, r.ay, r.az);
+      s.b_lo = mk(r.lx, r.ly, r.lz);
+      s.b_hi = mk(r.hx, r.hy, r.hz);
+      s.sn_x = (r.swap_xz & 2u) ? kSelHigh : kSelLow;
+      s.sn_y = (r.swap_xz & 4u) ? kSelHigh : kSelLow;
+      s.sn_z = (r.swap_xz & 8u) ? kSelHigh : kSelLow;
+      const bool hl = box_entry_q(qa.x, qa.y, qa.z, s, bt, tl);
+      const bool hr = box_entry_q(qa.w, qb.x, qb.y, s, bt, tr);
+#else
       SlabRay s;
-      s.dinv = mk(r.ix, r.iy, r.iz);
+      s.dinv = mk(r.ax, r.ay, r.az);
       s.c_lo = mk(r.lx, r.ly, r.lz);
       s.c_hi = mk(r.hx, r.hy, r.hz);
-      float tl, tr;
       const bool hl = box_entry(a.x, a.y, a.z, a.w, b.x, b.y, s, bt, tl);
       const bool hr = box_entry(b.z, b.w, c.x, c.y, c.z, c.w, s, bt, tr);
-      const uint32_t cl = __float_as_uint(d.x), cr = __float_as_uint(d.y);
+#endif
+      const uint32_t cl = qb.z, cr = qb.w;
       if (hl && hr) {
         const bool right_first = tr < tl;
         p0 = right_first ? make_uint2(cl, coop_key(tl, j)) : make_uint2(cr, coop_key(tr, j));  // far child: below
@@ -150,10 +182,10 @@ PTB_DEV void coop_trace(const DevScene& sc, CoopWarp& cw, uint32_t n_rays) {
         ray.d = mk(r.dx, r.dy, r.dz);
         ray.shear = mk(r.shx, r.shy, r.shz);
         ray.dinv = mk(0.0f, 0.0f, 0.0f);
-        ray.swap_xz = r.swap_xz != 0u;
+        ray.swap_xz = (r.swap_xz & 1u) != 0u;
         const float t = (e.x & kSphereBit) ? sphere_t(ray, from4(a), a.w) : triangle_t(ray, from4(a), from4(b), from4(c));
         if (t > 0.0f && (ANYHIT ? t < bt : t <= bt)) {
-          packed = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)__ldg(sc.slot_prim + slot);
+          packed = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned long long)orig;
           candidate = packed < atomicMin(&cw.best[j], packed);
         }
       }

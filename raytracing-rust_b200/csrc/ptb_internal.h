@@ -93,7 +93,7 @@ struct Ctx {
   // are kept on the host until commit
   DevBuf d_raw_spheres, d_raw_tris;
   size_t n_spheres = 0, n_tris = 0;
-  DevBuf scratch[16];  // LBVH build temporaries, grow-only (lbvh_build.cu)
+  DevBuf scratch[17];  // LBVH build temporaries, grow-only (lbvh_build.cu)
   std::vector<ptb_material> materials;
   std::vector<ptb_texture> textures;
   struct TexData { uint32_t width = 0, height = 0; std::vector<float> data; };
@@ -106,7 +106,7 @@ struct Ctx {
 
   // device scene
   DevScene dev{};
-  DevBuf d_geom, d_normals, d_slot_prim, d_slot_mat, d_nodes, d_cw_nodes, d_prim_sorted, d_morton, d_materials, d_textures, d_tex_data, d_lights;
+  DevBuf d_geom, d_normals, d_slot_prim, d_slot_mat, d_nodes, d_qnodes, d_cw_nodes, d_prim_sorted, d_morton, d_materials, d_textures, d_tex_data, d_lights;
   DevBuf d_sky_ycdf, d_sky_ypdf, d_sky_xcdf, d_sky_xpdf;
   uint64_t n_prims = 0, n_nodes = 0, n_cw_nodes = 0;
   bool wide = false;          // the committed scene is traversed through the compressed 8-wide tree (d_cw_nodes)

@@ -206,6 +206,87 @@ PTB_HD bool box_entry(float mnx, float mny, float mnz, float mxx, float mxy, flo
   return hmin * k > fmaxf(tmin, 0.0f) && tkey <= best_t;
 }
 
+// ---- 16-bit boxes ---------------------------------------------------------------------------------------------------------
+// The traversal kernels read 32-byte nodes: both children's boxes as 16-bit grid coordinates over the scene box
+// (plane(q) = q_min + q * q_step, a box snapped OUTWARDS by lbvh_build.cu: k_quantise_nodes) and the two child
+// references — ONE 32-byte load per node visit instead of two (ncu, round 2: the bounce launches of k_trace sit at 87 %
+// of the L1 data-pipe wavefront peak, node loads being most of it; the node array shrinks from 64 to 32 MB per million
+// primitives). On the CPU statement of the walk the snapped boxes cost +0.7 % node visits and +5 % primitive tests.
+// Decoding costs nothing: a word holds one axis of one box (low half = min, high half = max); ONE byte permute places
+// the half chosen by the direction's sign (the selector is a per-ray constant) under the exponent of 2^23, which makes
+// the float f = 2^23 + q exactly, and the plane distance is ONE fma, f * A + B, with A = q_step * dinv and
+// B = (q_min - o) * dinv - 2^23 * A hoisted per ray — the byte permute replaces the sign select of the f32 test.
+// Error budget (eps = 2^-23). Exact: t* = (q_min - o) * dinv + q * a, a = q_step * dinv. Computed: A = a (1 + d1);
+// f * A + B cancels the 2^23 * A term exactly (B was made from the same rounded A), leaving q * a * d1 <= |a| / 256;
+// B itself is rounded at magnitude ~2^23 |A|: |A| / 2; X = (q_min - o) * dinv carries two roundings: eps |X|. Near
+// distances are therefore moved down and far distances up by e = 0.51 |A| + 4 eps |X| (about half a grid step),
+// the final rounding of the fma is covered as before by the far side's 1 + 4 gamma(3) and by the cull slack.
+// |dinv| is clamped to 1e24 here (f * A stays finite for scenes up to 1e12 across).
+constexpr float kDinvMaxQ = 1.0e24f;
+constexpr uint32_t kSelLow = 0x7610u, kSelHigh = 0x7632u, kSelFlip = 0x0022u;  // prmt(word, 0x4B000000, sel) = 2^23 + half
+struct QSlabRay {
+  v3 a;       // q_step * dinv
+  v3 b_lo;    // addend of the near planes
+  v3 b_hi;    // addend of the far planes
+  uint32_t sn_x, sn_y, sn_z;  // selector of the NEAR plane's half per axis (far = sn ^ kSelFlip)
+};
+PTB_HD QSlabRay make_qslab_ray(const float q_min[3], const float q_step[3], const Ray& ray) {
+  QSlabRay r;
+  const v3 dinv = mk(fmaxf(fminf(ray.dinv.x, kDinvMaxQ), -kDinvMaxQ), fmaxf(fminf(ray.dinv.y, kDinvMaxQ), -kDinvMaxQ),
+                     fmaxf(fminf(ray.dinv.z, kDinvMaxQ), -kDinvMaxQ));
+  r.a = mk(q_step[0] * dinv.x, q_step[1] * dinv.y, q_step[2] * dinv.z);
+  const v3 x = mk((q_min[0] - ray.o.x) * dinv.x, (q_min[1] - ray.o.y) * dinv.y, (q_min[2] - ray.o.z) * dinv.z);
+  const v3 b = mk(x.x - 8388608.0f * r.a.x, x.y - 8388608.0f * r.a.y, x.z - 8388608.0f * r.a.z);
+  const v3 e = 0.51f * vabs(r.a) + (4.0f * kF32Eps) * vabs(x);
+  r.b_lo = b - e;
+  r.b_hi = b + e;
+  r.sn_x = dinv.x < 0.0f ? kSelHigh : kSelLow;
+  r.sn_y = dinv.y < 0.0f ? kSelHigh : kSelLow;
+  r.sn_z = dinv.z < 0.0f ? kSelHigh : kSelLow;
+  return r;
+}
+#ifdef __CUDACC__
+// wx / wy / wz: the three axis words of one child box
+// 2^23 + (the half of `w` named by `sel`), as a float: prmt straight from PTX (__byte_perm masks its selector first)
+PTB_DEV float q_plane(uint32_t w, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0x4B000000u), "r"(sel));
+  return __uint_as_float(d);
+}
+PTB_DEV bool box_entry_q(uint32_t wx, uint32_t wy, uint32_t wz, const QSlabRay& r, float best_t, float& tkey) {
+  const float k = 1.0f + 4.0f * gamma_n(3);
+  const float lox = __fmaf_rn(q_plane(wx, r.sn_x), r.a.x, r.b_lo.x), hix = __fmaf_rn(q_plane(wx, r.sn_x ^ kSelFlip), r.a.x, r.b_hi.x);
+  const float loy = __fmaf_rn(q_plane(wy, r.sn_y), r.a.y, r.b_lo.y), hiy = __fmaf_rn(q_plane(wy, r.sn_y ^ kSelFlip), r.a.y, r.b_hi.y);
+  const float loz = __fmaf_rn(q_plane(wz, r.sn_z), r.a.z, r.b_lo.z), hiz = __fmaf_rn(q_plane(wz, r.sn_z ^ kSelFlip), r.a.z, r.b_hi.z);
+  const float tmin = fmaxf(fmaxf(lox, loy), loz);
+  const float hmin = fminf(fminf(hix, hiy), hiz);
+  tkey = __fmaf_rn(-kCullSlack, fmaxf(fabsf(tmin), fabsf(hmin)), tmin);
+  return hmin * k > fmaxf(tmin, 0.0f) && tkey <= best_t;
+}
+PTB_DEV void ldg256u(const void* p, uint4& a, uint4& b) {
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+      : "l"(p));
+}
+#endif
+
+// Which node format the binary tree's traversal kernels read. Measured on B200 (profiles/r2_sweeps.md §6): the 32-byte
+// nodes take the bounce launches of k_trace from 87 % to 60 % of the L1 data-pipe peak and make them 4 - 6 % faster, the
+// (ALU / issue bound) camera launch 8 % slower — the C3 step and the C5 rate end up within 1 % of the 64-byte nodes, for 32 MB
+// more per million primitives (the f32 nodes stay: export, wide collapse). Built, bit-exact, parity-green, not the default.
+#if PTB_QNODES  // (the switch itself: ptb_common.cuh)
+typedef QSlabRay BinRayCtx;
+#else
+typedef SlabRay BinRayCtx;
+#endif
+PTB_HD BinRayCtx make_bin_ray(const DevScene& sc, const Ray& ray) {
+#if PTB_QNODES
+  return make_qslab_ray(sc.q_min, sc.q_step, ray);
+#else
+  return make_slab_ray(ray);
+#endif
+}
+
 #ifdef PTB_BOX_V1  // experiment: the previous sub+mul slab test with the per-box slack
 PTB_DEV bool box_entry_v1(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Ray& ray, float best_t,
                           float& tkey) {

@@ -18,7 +18,7 @@
 //     meanwhile fallen behind the best hit are dropped without a test;
 //   * dynamic fetch: when fewer than `trace_fetch_threshold` lanes still have work, finished rays are retired and idle
 //     lanes refilled from the global ray queue with one warp-aggregated atomicAdd.
-// Node fetches are four 16-byte loads of one 64-byte node that carries BOTH children's boxes.
+// A node fetch is ONE 32-byte load: both children's boxes (16-bit grid coordinates) and both child references.
 #pragma once
 #include "ptb_coop.cuh"
 #include "ptb_cwbvh.cuh"
@@ -26,6 +26,10 @@
 
 namespace ptb {
 
+#ifndef PTB_PREFETCH
+#define PTB_PREFETCH 0  // 1: a node step requests both child nodes into L1 before testing their boxes; 2: leaf geometry too
+#endif
+PTB_DEV void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 constexpr int kStackDepth = 64;  // LBVH depth <= 30 Morton bits + 32 index tie-break bits: one push per binary level
 #ifndef PTB_LEAF_QUEUE
 #define PTB_LEAF_QUEUE 1         // postponed leaves per lane (power of two). Measured on C3: 1 -> 1911-1927 Mrays/s,
@@ -109,8 +113,19 @@ PTB_DEV void trav_pop(TravState& s, const TravStack& stack, uint2* lq) {
 // One internal-node step of the lane: fetch the 64-byte node, test both child boxes, descend into the nearer hit child
 // (deferring the other on the stack); a leaf child is queued and the walk continues from the stack.
 template <bool COUNT>
-PTB_DEV void trav_node_step(const DevScene& sc, const SlabRay& ray, TravState& s, const TravStack& stack, uint2* lq,
+PTB_DEV void trav_node_step(const DevScene& sc, const BinRayCtx& ray, TravState& s, const TravStack& stack, uint2* lq,
                             uint32_t& n_nodes) {
+#if PTB_QNODES
+  // 32-byte node: {left box x, y, z, right box x} {right box y, z, left child, right child} (ptb_intersect.cuh: 16-bit boxes)
+  uint4 qa, n3;
+  ldg256u(sc.qnodes + 2u * (size_t)s.cur, qa, n3);
+  if (COUNT) ++n_nodes;
+  float tl, tr;
+  const bool hl = box_entry_q(qa.x, qa.y, qa.z, ray, s.best_t, tl);
+  const bool hr = box_entry_q(qa.w, n3.x, n3.y, ray, s.best_t, tr);
+  n3.x = n3.z;  // left, right
+  n3.y = n3.w;
+#else
   float4 n0, n1, n2;
   uint4 n3;
   load_node(sc.nodes, s.cur, n0, n1, n2, n3);
@@ -118,11 +133,26 @@ PTB_DEV void trav_node_step(const DevScene& sc, const SlabRay& ray, TravState& s
   float tl, tr;
   const bool hl = box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, ray, s.best_t, tl);
   const bool hr = box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, ray, s.best_t, tr);
+#endif
+#if PTB_PREFETCH >= 1 && PTB_QNODES
+  // (measured: 13 - 17 % SLOWER on C3 — the walk is bound by LSU / issue throughput, not by latency)
+  // The walk is a chain of dependent fetches (ncu: long-scoreboard is 58 % of a warp's time on the bounce launches). Both
+  // children are requested into L1 the moment their references arrive, before the box tests decide which one is
+  // entered: the next step's load then finds its line on the way or there. With 32-byte nodes the two requests cost the
+  // bytes ONE 64-byte node used to.
+  if (!(n3.x & PTB_LEAF_BIT)) prefetch_l1(sc.qnodes + 2u * (size_t)n3.x);
+#if PTB_PREFETCH >= 2
+  else prefetch_l1(sc.geom + 3u * (size_t)(n3.x & kSlotMask));
+#endif
+  if (!(n3.y & PTB_LEAF_BIT)) prefetch_l1(sc.qnodes + 2u * (size_t)n3.y);
+#if PTB_PREFETCH >= 2
+  else prefetch_l1(sc.geom + 3u * (size_t)(n3.y & kSlotMask));
+#endif
+#endif
   bool want_pop = !(hl || hr);
   if (!want_pop) {
-    const bool both = hl && hr;
-    const bool right_first = both ? (tr < tl) : hr;
-    if (both) stack_push(s, stack, make_uint2(right_first ? n3.x : n3.y, __float_as_uint(right_first ? tl : tr)));
+    const bool right_first = hr & (!hl | (tr < tl));  // (no short circuit: it compiles to a divergent branch)
+    if (hl & hr) stack_push(s, stack, make_uint2(right_first ? n3.x : n3.y, __float_as_uint(right_first ? tl : tr)));
     s.cur = right_first ? n3.y : n3.x;
     if (s.cur & PTB_LEAF_BIT) {
       const float key = right_first ? tr : tl;
@@ -210,13 +240,22 @@ struct BinTrav {  // binary LBVH, one primitive per leaf (this file)
   static constexpr int kTraceMinBlocks = PTB_TRACE_MIN_BLOCKS, kApiMinBlocks = PTB_API_MIN_BLOCKS;
   static constexpr bool kCoop = true;   // ptb_coop.cuh walks this tree warp-cooperatively
   typedef TravState State;
-  typedef SlabRay RayCtx;
+  typedef BinRayCtx RayCtx;
   struct Scratch {
     uint2 stack[kStackDepth];
     uint2 lq[kLeafQueue];
   };
-  PTB_DEV static RayCtx make(const Ray& ray) { return make_slab_ray(ray); }
-  PTB_DEV static RayCtx idle() { RayCtx r; r.dinv = r.c_lo = r.c_hi = mk(0.0f, 0.0f, 0.0f); return r; }
+  PTB_DEV static RayCtx make(const DevScene& sc, const Ray& ray) { return make_bin_ray(sc, ray); }
+  PTB_DEV static RayCtx idle() {
+    RayCtx r;
+#if PTB_QNODES
+    r.a = r.b_lo = r.b_hi = mk(0.0f, 0.0f, 0.0f);
+    r.sn_x = r.sn_y = r.sn_z = kSelLow;
+#else
+    r.dinv = r.c_lo = r.c_hi = mk(0.0f, 0.0f, 0.0f);
+#endif
+    return r;
+  }
   PTB_DEV static void init(State& s, const RayCtx&, uint32_t n_prims, float tmax) { trav_init(s, n_prims, tmax); }
   PTB_DEV static bool node_ready(const State& s) { return !(s.cur & PTB_LEAF_BIT); }
   PTB_DEV static bool leaf_ready(const State& s) { return s.lq_count != 0u; }
@@ -239,7 +278,7 @@ struct CwTrav {  // compressed 8-wide tree, leaf groups of up to 3 primitives (p
   struct Scratch {
     uint2 stack[kCwStackDepth];
   };
-  PTB_DEV static RayCtx make(const Ray& ray) { return make_cw_ray(ray); }
+  PTB_DEV static RayCtx make(const DevScene&, const Ray& ray) { return make_cw_ray(ray); }
   PTB_DEV static RayCtx idle() {
     RayCtx r;
     r.dinv = r.neg_od = r.ed = r.eo = mk(0.0f, 0.0f, 0.0f);
@@ -268,6 +307,16 @@ struct CwTrav {  // compressed 8-wide tree, leaf groups of up to 3 primitives (p
   }
 };
 
+#ifdef PTB_DRAIN_STATS  // tuning builds only: how long does a persistent launch run after its queue is empty?
+// [0] first warp finds the queue empty (ns, abs; ~0 = not yet) [1] last warp leaves [2] first warp starts
+// [3] sum of drains [4] sum of launch durations [5] launches folded (k_win_prepare folds and resets)
+__device__ unsigned long long g_drain[6] = {~0ull, 0ull, ~0ull, 0ull, 0ull, 0ull};
+PTB_DEV unsigned long long drain_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
 #ifdef PTB_LANE_STATS  // tuning builds only: where do the lanes of a warp spend their iterations?
 // [0] loop iterations  [1] lanes with work (sum)  [2] node phases  [3] node-ready lanes in them  [4] primitive phases
 // [5] leaf-ready lanes in them  [6] service passes  [7] node steps executed (lane level)
@@ -303,6 +352,9 @@ PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fe
 #ifdef PTB_LANE_STATS
   unsigned long long ls[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
+#ifdef PTB_DRAIN_STATS
+  if (threadIdx.x == 0u) atomicMin(&g_drain[2], drain_now());
+#endif
   for (;;) {
     // a lane with work can take a node step, a primitive step, or (binary tree: queued leaf while walking) both
     bool node_ready = has_ray && TR::node_ready(st);
@@ -337,12 +389,15 @@ PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fe
         if (((idle >> lane) & 1u) && mine < n) {
           float tmax = __int_as_float(0x7f800000);
           fetch(mine, ray, tmax, exclude);
-          rc = TR::make(ray);
+          rc = TR::make(sc, ray);
           TR::init(st, rc, sc.n_prims, tmax);
           has_ray = true;
           if (COUNT) ++cnt_rays;
         }
         if (base + want >= n) exhausted = true;
+#ifdef PTB_DRAIN_STATS
+        if (lane == leader && base + want >= n) atomicMin(&g_drain[0], drain_now());
+#endif
       }
       continue;
     }
@@ -372,13 +427,16 @@ PTB_DEV void persistent_trace(const DevScene& sc, uint32_t n, uint32_t* head, Fe
   if (lane == 0u)
     for (int i = 0; i < 7; ++i) atomicAdd(&g_lane_stats[i], ls[i]);
 #endif
+#ifdef PTB_DRAIN_STATS
+  if (lane == 0u) atomicMax(&g_drain[1], drain_now());
+#endif
 }
 
 // One ray, one lane, start to finish (the fused tail kernel): the same steps without the warp-level scheduling.
 template <class TR, bool ANYHIT>
 PTB_DEV TraceResult trace_lane(const DevScene& sc, const Ray& ray, float tmax, uint32_t exclude, typename TR::Scratch& scratch) {
   typename TR::State st;
-  const typename TR::RayCtx rc = TR::make(ray);
+  const typename TR::RayCtx rc = TR::make(sc, ray);
   TR::init(st, rc, sc.n_prims, tmax);
   uint32_t unused = 0;
   while (!TR::done(st)) {

@@ -1023,6 +1023,14 @@ __global__ void __launch_bounds__(1024) k_win_scan(Queues q) {
 // kernels of an iteration in any state but 0 find n_trace == 0, so the host may enqueue iterations without waiting.
 __global__ void k_win_prepare(WaveCounters* wc, Queues q, uint32_t n_segments, uint32_t method, uint32_t prev, uint32_t depth,
                               uint32_t tail_paths) {
+#ifdef PTB_DRAIN_STATS
+  if (threadIdx.x == 0u && g_drain[0] != ~0ull && g_drain[2] != ~0ull) {  // fold the previous persistent launch
+    if (g_drain[1] > g_drain[0]) g_drain[3] += g_drain[1] - g_drain[0];
+    if (g_drain[1] > g_drain[2]) g_drain[4] += g_drain[1] - g_drain[2];
+    if (g_drain[1] > g_drain[2] + 200000ull) g_drain[5] += 1ull;  // launches longer than 0.2 ms
+    g_drain[0] = ~0ull; g_drain[1] = 0ull; g_drain[2] = ~0ull;
+  }
+#endif
   const uint32_t lane = threadIdx.x;
   uint32_t total = 0;
   for (uint32_t s = lane; s < n_segments; s += 32u) total += q.seg_total[s];
@@ -1223,8 +1231,12 @@ PTB_DEV void tail_finish(float* __restrict__ accum, const Queues& q, uint32_t sl
 // Wide tree, and scenes of a handful of primitives (a two-level tree: nothing to share, the rounds' bookkeeping would be
 // most of the work — rtweekend1 measured 3 % slower cooperatively): the lane walk (one lane per path, trace_lane).
 constexpr uint32_t kCoopMinPrims = 4096u;
+#ifndef PTB_TAIL_WARPS
+#define PTB_TAIL_WARPS 4  // warps per k_tail block (each owns one cooperative frontier in shared memory)
+#endif
+constexpr int kTailThreads = 32 * PTB_TAIL_WARPS;
 template <class TR, int METHOD, bool FULL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kTailThreads)
 k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum, uint32_t depth) {
   if (wc->tail_iter != depth) return;  // launched after every iteration >= 2; only the hand-over iteration's launch has work
   const uint32_t n = wc->n_tail;   // live paths, listed in q.active[0] by k_win_fill
@@ -1233,7 +1245,7 @@ k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, 
   if (threadIdx.x == 0u) atomicMin(&g_tail_stats[9], global_timer_ns());
 #endif
   constexpr bool COOP = TR::kCoop;
-  __shared__ CoopWarp s_coop[COOP ? 4 : 1];
+  __shared__ CoopWarp s_coop[COOP ? PTB_TAIL_WARPS : 1];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   unsigned long long c_bounce = 0, c_sky = 0, c_light = 0, c_ref = 0, c_paths = 0;
   // Ticket t -> path: cycle walking over x -> (x * odd) mod 2^k, a bijection of [0, n) that sends the 32 consecutive
@@ -1273,7 +1285,7 @@ k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, 
         const bool mine = ((todo >> lane) & 1u) && (uint32_t)__popc(todo & lt) < kCoopRays;
         const uint32_t bm = __ballot_sync(0xffffffffu, mine);
         const uint32_t r = (uint32_t)__popc(bm & lt);
-        if (mine) coop_set_ray(cw, r, ray, __int_as_float(0x7f800000), kNone);
+        if (mine) coop_set_ray(sc, cw, r, ray, __int_as_float(0x7f800000), kNone);
         __syncwarp();
         coop_trace<false>(sc, cw, (uint32_t)__popc(bm));
         if (mine) {
@@ -1299,7 +1311,7 @@ k_tail(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, 
           const bool mine = ((todo >> lane) & 1u) && (uint32_t)__popc(todo & lt) < kCoopRays;
           const uint32_t bm = __ballot_sync(0xffffffffu, mine);
           const uint32_t r = (uint32_t)__popc(bm & lt);
-          if (mine) coop_set_ray(cw, r, make_ray(from4(so.sh_o), from4(so.sh_d)), so.sh_o.w, __float_as_uint(so.sh_d.w));
+          if (mine) coop_set_ray(sc, cw, r, make_ray(from4(so.sh_o), from4(so.sh_d)), so.sh_o.w, __float_as_uint(so.sh_d.w));
           __syncwarp();
           coop_trace<true>(sc, cw, (uint32_t)__popc(bm));
           if (mine && cw.ref[r] == kNone) tail_add_nee(pool, slot, so);
@@ -1865,6 +1877,17 @@ static void prof_collect(Ctx* c, int half, bool mis) {  // half = ring position 
   }
 }
 static void dump_lane_stats() {
+#ifdef PTB_DRAIN_STATS
+  {
+    unsigned long long d[6];
+    cudaMemcpyFromSymbol(d, g_drain, sizeof(d));
+    if (d[5])
+      fprintf(stderr, "drain_stats launches %llu: %.3f ms of %.3f ms ran after the queue was empty (%.1f us per launch)\n", d[5],
+              1e-6 * (double)d[3], 1e-6 * (double)d[4], 1e-3 * (double)d[3] / (double)d[5]);
+    unsigned long long z[6] = {~0ull, 0ull, ~0ull, 0ull, 0ull, 0ull};
+    cudaMemcpyToSymbol(g_drain, z, sizeof(z));
+  }
+#endif
 #ifdef PTB_TAIL_STATS  // tuning builds: what the fused tail's two phases did (per ptb_render call)
   {
     unsigned long long ts[16];
@@ -1924,7 +1947,7 @@ static void launch_tail(const RenderSetup& rs, Ctx* c, const SlotRefs& sl, uint3
   WaveCounters* wc = sl.wc;
   float* accum = rs.accum;
   void* args[] = {(void*)&c->dev, (void*)&sl.pool, (void*)&sl.q, (void*)&wc, (void*)&rs.rp, (void*)&accum, (void*)&depth};
-  cudaLaunchKernel(fn, dim3(grid), dim3(128), args, 0, st);
+  cudaLaunchKernel(fn, dim3(grid), dim3(kTailThreads), args, 0, st);
 }
 template <bool DENSE>
 static const void* shade_fn(const RenderSetup& rs) {
@@ -1992,16 +2015,19 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   if (const char* e = getenv("PTB_CHUNK_STREAMS")) { int v = atoi(e); if (v == 1 || v == 2) chunk_streams = v; }
   if (!two) chunk_streams = 1;
   if (chunk_streams == 2 && !c->s_work2) PTB_CUDA_TRY(c, cudaStreamCreateWithFlags(&c->s_work2, cudaStreamNonBlocking));
-  uint32_t grid_tail = (uint32_t)c->sm_count;  // blocks of 128 threads (PTB_TAIL_BLOCKS)
+  uint32_t grid_tail = (uint32_t)c->sm_count * (4u / PTB_TAIL_WARPS);  // four warps per SM beside the next chunk (PTB_TAIL_BLOCKS)
   if (const char* e = getenv("PTB_TAIL_BLOCKS")) { int v = atoi(e); if (v >= 1 && v <= 65535) grid_tail = (uint32_t)v; }
-  if (grid_tail > (tail_paths + 127u) / 128u) grid_tail = (tail_paths + 127u) / 128u;
+  const uint32_t tail_blocks_max = (tail_paths + (uint32_t)kTailThreads - 1u) / (uint32_t)kTailThreads;  // one lane per path
+  if (grid_tail > tail_blocks_max) grid_tail = tail_blocks_max;
   // The call's last tail has the machine to itself: one lane per path, but never more blocks than are resident at once
   // (45 KB of shared memory each) — a block that starts only when another has finished would keep the work queue from
   // running empty, which is what lets a warp go cooperative.
-  uint32_t grid_tail_last = (tail_paths + 127u) / 128u;
+  uint32_t grid_tail_last = tail_blocks_max;
   if (tail_paths) {
+#ifdef PTB_TAIL_CARVEOUT
     cudaFuncSetAttribute(tail_fn(rs, c), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    const uint32_t resident = (uint32_t)persistent_grid(c, tail_fn(rs, c), 128);
+#endif
+    const uint32_t resident = (uint32_t)persistent_grid(c, tail_fn(rs, c), kTailThreads);
     if (grid_tail_last > resident) grid_tail_last = resident;
     if (grid_tail > resident) grid_tail = resident;
   }

@@ -21,6 +21,37 @@ def _compare(ptb, orc, gpu_ctx, scene):
     # sortedness + permutation (size-independent properties)
     assert np.all(np.diff(gm.astype(np.int64)) >= 0)
     assert np.array_equal(np.sort(gp), np.arange(scene.n_primitives, dtype=np.uint32))
+    # the 32-byte nodes the traversal kernels read: grid and 16-bit boxes bit-exact, and every box contains its f32 box
+    if not has_quantised_nodes(ptb, gpu_ctx):
+        return
+    gf, gq = gpu_ctx.bvh_export_quantised()
+    of, oq = o.lbvh_quantise()
+    assert np.array_equal(gf.view(np.uint32), of.view(np.uint32)), "quantisation grid differs"
+    assert np.array_equal(gq, oq), "quantised nodes differ"
+    check_quantised_contains(gn, gf, gq)
+
+
+def has_quantised_nodes(ptb, ctx):
+    """The 32-byte traversal nodes are a compile-time option of the library (-DPTB_QNODES=1; scripts/gpu_suite.sh runs the
+    suite under that build too): the default build answers PTB_ERR_UNSUPPORTED."""
+    try:
+        ctx.bvh_export_quantised()
+        return True
+    except ptb.PtbError as e:
+        assert e.code == 8  # PTB_ERR_UNSUPPORTED
+        return False
+
+
+def check_quantised_contains(nodes, frame, q):
+    org, step = frame[:3].astype(np.float64), frame[3:].astype(np.float64)
+    for side, mn, mx in ((0, "lmin", "lmax"), (3, "rmin", "rmax")):
+        w = q[:, side:side + 3]
+        lo = org + (w & 0xFFFF).astype(np.float64) * step
+        hi = org + (w >> 16).astype(np.float64) * step
+        assert np.all(lo <= nodes[mn].astype(np.float64)) and np.all(hi >= nodes[mx].astype(np.float64))
+        flat = step == 0
+        assert np.all((nodes[mn].astype(np.float64) - lo)[:, ~flat] < step[~flat]) and np.all((hi - nodes[mx].astype(np.float64))[:, ~flat] < step[~flat])
+    assert np.array_equal(q[:, 6], nodes["left"]) and np.array_equal(q[:, 7], nodes["right"])
 
 
 def test_rtweekend1(ptb, orc, gpu_ctx, rtweekend1):
@@ -79,3 +110,5 @@ def test_full_size_properties(ptb, gpu_ctx):
         cmin = np.minimum(c["lmin"], c["rmin"])
         cmax = np.maximum(c["lmax"], c["rmax"])
         assert np.array_equal(gn[mn][m], cmin) and np.array_equal(gn[mx][m], cmax)
+    if has_quantised_nodes(ptb, gpu_ctx):
+        check_quantised_contains(gn, *gpu_ctx.bvh_export_quantised())

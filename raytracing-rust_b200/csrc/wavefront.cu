@@ -18,6 +18,7 @@
 // the image is a pure function of (scene, seed, sample range) — independent of pool size, scheduling and GPU count.
 #include "ptb_internal.h"
 #include "ptb_traverse.cuh"
+#include "ptb_packet.cuh"
 
 namespace ptb {
 
@@ -397,6 +398,55 @@ k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
   TraceFetch<CAMERA> fetch{pool, q.active[DENSE ? 0u : wc->cur], 0u, sc, rp, first};
   TraceRetire<DENSE, CAMERA> retire{sc, pool, q, wc, fetch};
   persistent_trace<TR, false, COUNT>(sc, wc->n_trace, &wc->trace_head, fetch, retire, cnt_nodes, cnt_prims, cnt_rays);
+  if (COUNT) {
+    for (int off = 16; off > 0; off >>= 1) {
+      cnt_nodes += __shfl_xor_sync(0xffffffffu, cnt_nodes, off);
+      cnt_prims += __shfl_xor_sync(0xffffffffu, cnt_prims, off);
+      cnt_rays += __shfl_xor_sync(0xffffffffu, cnt_rays, off);
+    }
+    if (lane == 0 && cnt_rays) {
+      atomicAdd(&wc->nodes_fetched, (unsigned long long)cnt_nodes);
+      atomicAdd(&wc->prims_tested, (unsigned long long)cnt_prims);
+      atomicAdd(&wc->rays_counted, (unsigned long long)cnt_rays);
+    }
+  }
+}
+
+// K1 + K8 for the first iteration of a window-mode chunk on the binary tree: packets (ptb_packet.cuh). Work item i is slot i
+// and its ray is the camera ray of path first + i, computed here; a warp takes 32 consecutive slots — samples of one pixel
+// (or of one 8 x 4 pixel tile when the call has fewer samples) — and walks the tree once for all of them.
+#ifndef PTB_CAMERA_MIN_BLOCKS
+#define PTB_CAMERA_MIN_BLOCKS 3  // 71 registers; at 4 blocks (64) the slab constants are rematerialised per node: 4252 vs 4344 Mrays/s on C3
+#endif
+template <bool COUNT>
+__global__ void __launch_bounds__(256, PTB_CAMERA_MIN_BLOCKS)
+k_trace_camera(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, unsigned long long first) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n = wc->n_trace;
+  uint32_t cnt_nodes = 0, cnt_prims = 0, cnt_rays = 0;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0u) base = atomicAdd(&wc->trace_head, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n) break;
+    const uint32_t i = base + lane;
+    const bool valid = i < n;
+    Ray ray;
+    if (valid) {
+      uint32_t x, y, sample;
+      camera_pixel_sample(rp, first + i, x, y, sample);
+      ray = make_ray(sc.cam_origin, camera_direction(sc, rp, x, y, sample));
+      if (COUNT) ++cnt_rays;
+    } else {
+      ray = make_ray(sc.cam_origin, mk(0.0f, 0.0f, 1.0f));
+    }
+    float best_t;
+    uint32_t best_ref;
+    packet_trace<COUNT>(sc, ray, valid, best_t, best_ref, cnt_nodes, cnt_prims);
+    if (valid)
+      stg256(pool.ray + 4u * (size_t)i, make_float4(ray.o.x, ray.o.y, ray.o.z, best_ref == kNone ? 0.0f : best_t),
+             make_float4(ray.d.x, ray.d.y, ray.d.z, __uint_as_float(best_ref == kNone ? kNone : (best_ref & ~PTB_LEAF_BIT))));
+  }
   if (COUNT) {
     for (int off = 16; off > 0; off >>= 1) {
       cnt_nodes += __shfl_xor_sync(0xffffffffu, cnt_nodes, off);
@@ -1979,7 +2029,13 @@ static int32_t render_window_mode(Ctx* c, const ptb_render_opts& o, const Render
   uint32_t grid_shade = (uint32_t)persistent_grid(c, shade_fn<true>(rs), TS);
   if (grid_shade > (P + TS - 1) / TS) grid_shade = (P + TS - 1) / TS;
   const void* fn_trace = trace_kernel(c, count, true, false);
-  const void* fn_trace_cam = trace_kernel(c, count, true, true);
+  // camera rays of the binary tree walk it in packets (PTB_CAMERA_PACKET=0: the persistent kernel, as the wide tree does)
+  // — when a warp's 32 work items are samples of ONE pixel (group a multiple of 32). C3 on B200: 256 spp 4256 -> 4344 Mrays/s;
+  // with 4 samples per pixel a warp spans eight pixels and the packet loses (7.32 vs 6.75 ms per 4-spp step).
+  bool cam_packet = !c->wide && rs.rp.group % 32u == 0u;
+  if (const char* e = getenv("PTB_CAMERA_PACKET")) cam_packet = !c->wide && atoi(e) != 0;
+  const void* fn_trace_cam = cam_packet ? (count ? (const void*)k_trace_camera<true> : (const void*)k_trace_camera<false>)
+                                        : trace_kernel(c, count, true, true);
   const void* fn_shadow = shadow_kernel(c);
   const int grid_trace = persistent_grid(c, fn_trace, T);
   const int grid_trace_cam = persistent_grid(c, fn_trace_cam, T);

@@ -382,3 +382,23 @@ def test_fused_tail_hand_over_does_not_change_the_result(ptb, gpu_ctx, overshado
         assert ca[5] == 160 * 90 * 16
         for other in (b, c, d):
             assert np.allclose(a, other, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("spp", [4, 32])
+def test_camera_packets_are_the_same_rays(ptb, gpu_ctx, spp, monkeypatch):
+    """The first iteration of a window-mode chunk walks the binary tree in packets (32 camera rays of a warp, one shared
+    stack, per-lane participation masks — ptb_packet.cuh) when a warp's work items are samples of one pixel; forced on and
+    off here, with one pixel per warp (32 spp) and eight (4 spp): same image, same ray counters, and the same hits as the
+    per-ray walk down to the traversal statistics' primitive ids (the image is a function of the hits)."""
+    sc = ptb.Scene(ptb.meshgen.c3_scene(0.05), ctx=gpu_ctx)
+    o = ptb.RenderOptions(samples_per_pixel=spp, render_method=0, width=160, height=96, seed=9)
+    out = []
+    for packet in ("0", "1"):
+        monkeypatch.setenv("PTB_CAMERA_PACKET", packet)
+        gpu_ctx.stats_reset()
+        img = sc.render(o)
+        st = gpu_ctx.stats()
+        out.append((img, (st.rays_camera, st.rays_bounce, st.rays_reference, st.paths)))
+    monkeypatch.delenv("PTB_CAMERA_PACKET")
+    assert out[0][1] == out[1][1]
+    assert np.allclose(out[0][0], out[1][0], rtol=1e-5, atol=1e-5)

@@ -550,6 +550,11 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
   c->scene_needs_full_shade = false;
   for (const auto& t : c->textures) c->scene_needs_full_shade |= t.kind == PTB_TEX_IMAGE || t.kind == PTB_TEX_PERLIN;
   for (const auto& m : c->materials) c->scene_needs_full_shade |= m.kind == PTB_MAT_TROWBRIDGE_REITZ;
+  {
+    uint32_t kinds = 0;
+    for (const auto& m : c->materials) kinds |= 1u << (m.kind & 31u);
+    c->scene_material_kinds = (uint32_t)__builtin_popcount(kinds);
+  }
 
   // materials / textures / camera
   std::vector<DevMaterial> dm(c->materials.size());

@@ -102,6 +102,7 @@ struct Ctx {
   ptb_sky sky{};
   bool have_camera = false, have_sky = false;
   bool committed = false;
+  uint32_t scene_material_kinds = 0;    // distinct PTB_MAT_* kinds among the scene's materials (k_shade's block-level sort)
   bool scene_needs_full_shade = false;  // any Trowbridge-Reitz material or image / perlin texture (k_shade<.., FULL>)
 
   // device scene

@@ -911,7 +911,7 @@ PTB_DEV void shade_path(const DevScene& sc, const PathPool& pool, const RenderPa
 template <int METHOD, bool FULL, bool DENSE>
 __global__ void __launch_bounds__(256, PTB_SHADE_MIN_BLOCKS + (METHOD == PTB_METHOD_MIS ? 1 : 0))
 k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp, float* __restrict__ accum,
-        unsigned long long camera_first) {
+        unsigned long long camera_first, uint32_t sort_kinds) {
   // window mode, first iteration of a chunk (camera_first != kNoCamera): work item i is slot i, every slot is live and its
   // colour record is the camera path's initial state, derived from the path index instead of read from memory
   const bool depth0 = DENSE && camera_first != kNoCamera;
@@ -947,10 +947,42 @@ k_shade(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
   ShadeOut so;
   so.fin_L = mk(0.0f, 0.0f, 0.0f);
 
-  if (active) {
-    slot = DENSE ? (depth0 ? i : q.active[0][i]) : q.kind[kq][off];
-    shade_path<METHOD, FULL>(sc, pool, rp, slot, depth0, camera_first, so);
+  if (active) slot = DENSE ? (depth0 ? i : q.active[0][i]) : q.kind[kq][off];
+  if (DENSE && sort_kinds) {
+    // Window mode orders a window's rays by direction, so the hits a block shades arrive with their materials mixed. A
+    // scene with more than two material kinds (sort_kinds, decided at commit) has its block's work items counting-sorted
+    // by the kind of the surface hit (0 = sky, 1 + PTB_MAT_*) before they are shaded: warps then run one material's code
+    // instead of all of them one after the other. Costs one extra 16-byte read per path (the hit reference) and two
+    // block barriers; scenes with one or two kinds (C1 - C5) skip it.
+    __shared__ uint32_t s_slot[256];
+    __shared__ uint32_t s_cnt[(kNumKinds + 1) * 8];  // [kind][warp], kind kNumKinds = no work item
+    const uint32_t warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    uint32_t kind = (uint32_t)kNumKinds;
+    if (active) {
+      const uint32_t ref = __float_as_uint(pool.ray[4u * (size_t)slot + 1u].w);
+      kind = ref == kNone ? 0u : 1u + (__ldg(sc.slot_mat + (ref & kSlotMask)) >> 24);
+    }
+    uint32_t rank = 0;
+#pragma unroll
+    for (uint32_t k = 0; k <= (uint32_t)kNumKinds; ++k) {
+      const uint32_t m = __ballot_sync(0xffffffffu, kind == k);
+      if (kind == k) rank = (uint32_t)__popc(m & ((1u << lane) - 1u));
+      if (lane == 0u) s_cnt[k * 8u + warp] = (uint32_t)__popc(m);
+    }
+    __syncthreads();
+    uint32_t pos = rank;
+    for (uint32_t e = 0; e < kind * 8u + warp; ++e)
+      if ((e & 7u) < n_warps) pos += s_cnt[e];
+    s_slot[pos] = slot;
+    __syncthreads();
+    uint32_t n_here = 0;
+    for (uint32_t e = 0; e < (uint32_t)kNumKinds * 8u; ++e)
+      if ((e & 7u) < n_warps) n_here += s_cnt[e];
+    active = threadIdx.x < n_here;
+    slot = s_slot[threadIdx.x];
+    __syncthreads();  // the tables are reused by the block's next batch
   }
+  if (active) shade_path<METHOD, FULL>(sc, pool, rp, slot, depth0, camera_first, so);
   finish_paths(accum, so.contributes, so.fin_pixel, so.fin_L);
 
   if (DENSE) {
@@ -1773,6 +1805,7 @@ struct RenderSetup {
   uint32_t P;          // slot capacity in paths
   uint32_t chunk_paths, n_chunks;
   bool mis, full, count, prof;
+  bool sort_kinds = false;  // window mode: k_shade sorts each block's hits by material kind
 };
 
 static int32_t render_queue_mode(Ctx* c, const ptb_render_opts& o, const RenderSetup& rs, ptb_progress_fn progress, void* user);
@@ -1900,6 +1933,11 @@ int32_t render_wavefront(Ctx* c, const ptb_render_opts& o, ptb_progress_fn progr
 
   rs.accum = c->accum_target ? c->accum_target : c->d_accum.as<float>();
   rs.full = c->scene_needs_full_shade;
+  // k_shade sorts a block's hits by material kind (PTB_SHADE_SORT=0|1 overrides). Measured on the five-sphere showcase scene
+  // (three kinds, 1080p x 64 spp, profiles/r2_sweeps.md §11): MIS 4370 -> 4494 Mrays/s (k_shade 107 -> 101 ms), naive 9376 ->
+  // 8538 (its shading is too short to pay for the sort): on for MIS.
+  rs.sort_kinds = c->scene_material_kinds > 2 && rs.mis;
+  if (const char* e = getenv("PTB_SHADE_SORT")) rs.sort_kinds = atoi(e) != 0;
   rs.count = c->opt_count_traversal;
   rs.prof = c->opt_time_kernels;
   if (rs.prof) {
@@ -1981,12 +2019,13 @@ struct SlotRefs {  // the device state one chunk runs in
 template <bool DENSE>
 static void launch_shade(const RenderSetup& rs, Ctx* c, const SlotRefs& sl, uint32_t grid, int threads, cudaStream_t st,
                          unsigned long long camera_first = kNoCamera) {
+  const uint32_t sort = DENSE && rs.sort_kinds ? 1u : 0u;
   if (rs.mis) {
-    if (rs.full) k_shade<PTB_METHOD_MIS, true, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first);
-    else k_shade<PTB_METHOD_MIS, false, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first);
+    if (rs.full) k_shade<PTB_METHOD_MIS, true, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first, sort);
+    else k_shade<PTB_METHOD_MIS, false, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first, sort);
   } else {
-    if (rs.full) k_shade<PTB_METHOD_NAIVE, true, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first);
-    else k_shade<PTB_METHOD_NAIVE, false, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first);
+    if (rs.full) k_shade<PTB_METHOD_NAIVE, true, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first, sort);
+    else k_shade<PTB_METHOD_NAIVE, false, DENSE><<<grid, threads, 0, st>>>(c->dev, sl.pool, sl.q, sl.wc, rs.rp, rs.accum, camera_first, sort);
   }
 }
 static const void* tail_fn(const RenderSetup& rs, Ctx* c) {

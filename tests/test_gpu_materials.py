@@ -87,3 +87,25 @@ def test_texture_data_errors(ptb, gpu_ctx):
     c.upload(s)
     c.commit()
     c.close()
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_material_sorted_shading_is_the_same_image(ptb, gpu_ctx, method, monkeypatch):
+    """Window mode: a scene with more than two material kinds has each block of k_shade sort its hits by the kind of the
+    surface hit before shading them (north_star: "shading on sorted ray queues"). Only the ORDER inside a block changes:
+    same image, same counters with the sort forced off and on (the showcase scene enables it by itself: three kinds)."""
+    s = showcase_scene(ptb, sky="image")
+    sc = ptb.Scene(s, ctx=gpu_ctx)
+    o = ptb.RenderOptions(samples_per_pixel=16, render_method=method, width=200, height=120, seed=12)
+    out = []
+    for flag in ("0", "1", None):
+        if flag is None:
+            monkeypatch.delenv("PTB_SHADE_SORT")
+        else:
+            monkeypatch.setenv("PTB_SHADE_SORT", flag)
+        gpu_ctx.stats_reset()
+        img = sc.render(o)
+        st = gpu_ctx.stats()
+        out.append((img, (st.rays_camera, st.rays_bounce, st.rays_shadow_light, st.rays_shadow_sky, st.rays_reference, st.paths)))
+    assert out[0][1] == out[1][1] == out[2][1]
+    assert np.allclose(out[0][0], out[1][0], rtol=1e-5, atol=1e-5) and np.allclose(out[0][0], out[2][0], rtol=1e-5, atol=1e-5)

@@ -452,26 +452,42 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
+        phase = [0.0, 0.0, 0.0, 0.0, 0.0]  # host wall clock per phase (no extra synchronisation: a phase ends where its call returns)
         for i in range(k2):
+            ta = time.perf_counter()
             ctx.stats_reset()
             ctx.upload(hscene)   # same context: ptb_scene_set_* + commit rebuild everything device-side
+            tb = time.perf_counter()
             ctx.commit()
+            tc = time.perf_counter()
             step(W + K + 1 + i)
             if rank == 0:
+                td = time.perf_counter()
                 ctx.accum_read(w, h, normalise=False, out=himg)
             else:
                 ctx.synchronize()
-            rays2 += ctx.stats().rays_total
+                td = time.perf_counter()
+            te = time.perf_counter()
+            st2 = ctx.stats()
+            rays2 += st2.rays_total
+            for k_, (a_, b_) in enumerate(((ta, tb), (tb, tc), (tc, td), (td, te))):
+                phase[k_] += b_ - a_
+            phase[4] += 1e-3 * st2.render_ms   # ptb_render alone, CUDA events inside the library
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt, float(rays2)], dtype=torch.float64, device="cuda")
-        tm = tt.clone()
+        tm = torch.tensor([dt] + phase, dtype=torch.float64, device="cuda")
+        t_rank0 = tm.clone()
         if world > 1:
+            dist.broadcast(t_rank0, src=0)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             dist.all_reduce(tt, op=dist.ReduceOp.SUM)
         e2e = {"value": float(tt[1]) / float(tm[0]) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": scene.nbytes(),
                "d2h_bytes_per_step": w * h * 3 * 4, "steps": k2,
-               "includes": "ptb_scene_set_* (pinned host arrays) + ptb_scene_commit (BVH build) + ptb_render + reduce + ptb_accum_read"}
+               "includes": "ptb_scene_set_* (pinned host arrays) + ptb_scene_commit (BVH build) + ptb_render + reduce + ptb_accum_read",
+               "ms_per_step_by_phase": {n_: {"rank0": 1e3 * float(t_rank0[1 + k_]) / k2, "max_over_ranks": 1e3 * float(tm[1 + k_]) / k2}
+                                        for k_, n_ in enumerate(("scene_set", "commit", "render_and_reduce" if world > 1 else "render",
+                                                                 "accum_read_or_sync", "ptb_render_device"))}}
 
     ctx.close()
     del ctx

@@ -53,6 +53,7 @@ extern "C" {
     pub fn ptb_scene_set_camera(ctx: *mut ptb_ctx, cam: *const ptb_camera) -> i32;
     pub fn ptb_scene_set_sky(ctx: *mut ptb_ctx, sky: *const ptb_sky) -> i32;
     pub fn ptb_scene_commit(ctx: *mut ptb_ctx, build_flags: u32) -> i32;
+    pub fn ptb_bvh_export_quantised(ctx: *mut ptb_ctx, frame: *mut f32, nodes32: *mut c_void) -> i32;
     pub fn ptb_bvh_wide_info(ctx: *mut ptb_ctx, n_nodes: *mut u64, max_leaf: *mut u32) -> i32;
     pub fn ptb_bvh_wide_export(ctx: *mut ptb_ctx, nodes96: *mut c_void, slot_prim: *mut u32) -> i32;
     pub fn ptb_closest_hit(ctx: *mut ptb_ctx, rays: *const ptb_ray, n: usize, hits: *mut ptb_hit) -> i32;

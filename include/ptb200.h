@@ -232,7 +232,8 @@ int32_t ptb_bvh_export(ptb_ctx* ctx, uint32_t* morton_sorted, uint32_t* prim_sor
  * snapped outwards onto a 65536^3 grid over the scene box — eight 32-bit words {left box x, y, z, right box x, y, z (each:
  * low half = min, high half = max grid coordinate), left, right}; frame = grid origin xyz, grid step xyz
  * (plane = origin + q * step). nodes32 receives nothing when the committed scene uses the wide tree. CPU definition:
- * oracle/lbvh_ref.hpp. Any pointer may be NULL. */
+ * oracle/lbvh_ref.hpp. Any pointer may be NULL. The 32-byte nodes are a compile-time option of the library
+ * (-DPTB_QNODES=1): the default build answers PTB_ERR_UNSUPPORTED. */
 int32_t ptb_bvh_export_quantised(ptb_ctx* ctx, float frame[6], void* nodes32);
 
 /* The compressed 8-wide tree, for bit-exact tests: *n_nodes = 0 when the committed scene uses the binary tree. Nodes are

@@ -287,6 +287,22 @@ PTB_HD BinRayCtx make_bin_ray(const DevScene& sc, const Ray& ray) {
 #endif
 }
 
+// box_entry with the direction's signs known at compile time (camera packets: the 32 rays of a pixel share an octant):
+// the six near / far selects disappear. OCT bit 0 / 1 / 2 = the direction is negative along x / y / z.
+template <int OCT>
+PTB_HD bool box_entry_oct(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const SlabRay& r, float best_t,
+                          float& tkey) {
+  const float k = 1.0f + 4.0f * gamma_n(3);
+  constexpr bool sx = (OCT & 1) != 0, sy = (OCT & 2) != 0, sz = (OCT & 4) != 0;
+  const float lox = fma_rn(sx ? mxx : mnx, r.dinv.x, r.c_lo.x), hix = fma_rn(sx ? mnx : mxx, r.dinv.x, r.c_hi.x);
+  const float loy = fma_rn(sy ? mxy : mny, r.dinv.y, r.c_lo.y), hiy = fma_rn(sy ? mny : mxy, r.dinv.y, r.c_hi.y);
+  const float loz = fma_rn(sz ? mxz : mnz, r.dinv.z, r.c_lo.z), hiz = fma_rn(sz ? mnz : mxz, r.dinv.z, r.c_hi.z);
+  const float tmin = fmaxf(fmaxf(lox, loy), loz);
+  const float hmin = fminf(fminf(hix, hiy), hiz);
+  tkey = fma_rn(-kCullSlack, fmaxf(fabsf(tmin), fabsf(hmin)), tmin);
+  return hmin * k > fmaxf(tmin, 0.0f) && tkey <= best_t;
+}
+
 #ifdef PTB_BOX_V1  // experiment: the previous sub+mul slab test with the per-box slack
 PTB_DEV bool box_entry_v1(float mnx, float mny, float mnz, float mxx, float mxy, float mxz, const Ray& ray, float best_t,
                           float& tkey) {

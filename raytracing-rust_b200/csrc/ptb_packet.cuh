@@ -38,11 +38,12 @@ PTB_DEV uint32_t packet_key(float t) { return __float_as_uint(fmaxf(t, 0.0f)); }
 
 // All 32 lanes call this together. `valid` lanes hold a ray; on return best_t / best_ref hold each lane's closest hit
 // (best_ref == kNone: miss). n_nodes / n_prims count what the lane took part in (COUNT).
-template <bool COUNT>
-PTB_DEV void packet_trace(const DevScene& sc, const Ray& ray, bool valid, float& best_t, uint32_t& best_ref, uint32_t& n_nodes,
-                          uint32_t& n_prims) {
+// OCT = the octant all valid lanes' directions lie in (bit 0 / 1 / 2: negative along x / y / z: the slab test then needs no
+// sign selects), or -1 when they do not share one.
+template <bool COUNT, int OCT>
+PTB_DEV void packet_trace_oct(const DevScene& sc, const Ray& ray, const SlabRay& sr, bool valid, float& best_t, uint32_t& best_ref,
+                              uint32_t& n_nodes, uint32_t& n_prims) {
   const uint32_t lane = threadIdx.x & 31u;
-  const SlabRay sr = make_slab_ray(ray);
   best_t = __int_as_float(0x7f800000);
   best_ref = kNone;
   PacketStack st;
@@ -78,8 +79,10 @@ PTB_DEV void packet_trace(const DevScene& sc, const Ray& ray, bool valid, float&
       const uint32_t cl = __float_as_uint(n3f.x), cr = __float_as_uint(n3f.y);
       if (COUNT && in) ++n_nodes;
       float tl = 0.0f, tr = 0.0f;
-      const bool hl = in && box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, sr, best_t, tl);
-      const bool hr = in && box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, sr, best_t, tr);
+      const bool hl = in && (OCT < 0 ? box_entry(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, sr, best_t, tl)
+                                     : box_entry_oct<(OCT < 0 ? 0 : OCT)>(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, sr, best_t, tl));
+      const bool hr = in && (OCT < 0 ? box_entry(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, sr, best_t, tr)
+                                     : box_entry_oct<(OCT < 0 ? 0 : OCT)>(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, sr, best_t, tr));
       const uint32_t ml = __ballot_sync(0xffffffffu, hl), mr = __ballot_sync(0xffffffffu, hr);
       if (ml | mr) {
         pop = false;
@@ -107,6 +110,30 @@ PTB_DEV void packet_trace(const DevScene& sc, const Ray& ray, bool valid, float&
       const uint32_t m = __shfl_sync(0xffffffffu, sp < 32 ? st.mask0 : st.mask1, src);
       if (k <= best_max) { cur = r; mask = m; pop = false; }
     }
+  }
+}
+
+template <bool COUNT>
+PTB_DEV void packet_trace(const DevScene& sc, const Ray& ray, bool valid, float& best_t, uint32_t& best_ref, uint32_t& n_nodes,
+                          uint32_t& n_prims) {
+  const SlabRay sr = make_slab_ray(ray);
+  // do the valid lanes share a direction octant? (the signs box_entry selects by: dinv < 0 after the clamp)
+  const uint32_t all = __ballot_sync(0xffffffffu, valid);
+  const uint32_t mx = __ballot_sync(0xffffffffu, valid && sr.dinv.x < 0.0f), my = __ballot_sync(0xffffffffu, valid && sr.dinv.y < 0.0f),
+                 mz = __ballot_sync(0xffffffffu, valid && sr.dinv.z < 0.0f);
+  int oct = -1;
+  if ((mx == 0u || mx == all) && (my == 0u || my == all) && (mz == 0u || mz == all))
+    oct = (mx ? 1 : 0) | (my ? 2 : 0) | (mz ? 4 : 0);
+  switch (oct) {
+    case 0: packet_trace_oct<COUNT, 0>(sc, ray, sr, valid, best_t, best_ref, n_nodes, n_prims); break;
+    case 1: packet_trace_oct<COUNT, 1>(sc, ray, sr, valid, best_t, best_ref, n_nodes, n_prims); break;
+    case 2: packet_trace_oct<COUNT, 2>(sc, ray, sr, valid, best_t, best_ref, n_nodes, n_prims); break;
+    case 3: packet_trace_oct<COUNT, 3>(sc, ray, sr, valid, best_t, best_ref, n_nodes, n_prims); break;
+    case 4: packet_trace_oct<COUNT, 4>(sc, ray, sr, valid, best_t, best_ref, n_nodes, n_prims); break;
+    case 5: packet_trace_oct<COUNT, 5>(sc, ray, sr, valid, best_t, best_ref, n_nodes, n_prims); break;
+    case 6: packet_trace_oct<COUNT, 6>(sc, ray, sr, valid, best_t, best_ref, n_nodes, n_prims); break;
+    case 7: packet_trace_oct<COUNT, 7>(sc, ray, sr, valid, best_t, best_ref, n_nodes, n_prims); break;
+    default: packet_trace_oct<COUNT, -1>(sc, ray, sr, valid, best_t, best_ref, n_nodes, n_prims); break;
   }
 }
 

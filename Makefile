@@ -6,7 +6,7 @@ NVCC     ?= nvcc
 # -fmad=false: the reference (rustc) never contracts a*b+c; hit/miss decisions must match the oracle bit for bit.
 NVFLAGS  ?= -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false \
             -Xcompiler -fPIC,-Wall,-Wextra,-Wno-unused-parameter -Xptxas -v
-CU_SRCS  := $(PKG)/csrc/context.cu $(PKG)/csrc/lbvh_build.cu $(PKG)/csrc/cwbvh_build.cu $(PKG)/csrc/wavefront.cu $(PKG)/csrc/multi.cu
+CU_SRCS  := $(PKG)/csrc/context.cu $(PKG)/csrc/lbvh_build.cu $(PKG)/csrc/cwbvh_build.cu $(PKG)/csrc/sah_build.cu $(PKG)/csrc/wavefront.cu $(PKG)/csrc/multi.cu
 CPP_SRCS := $(PKG)/host/ssml_loader.cpp $(PKG)/host/image_out.cpp $(PKG)/host/image_in.cpp
 HDRS     := include/ptb200.h $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h)
 OBJS     := $(CU_SRCS:.cu=.o) $(CPP_SRCS:.cpp=.o)

@@ -220,12 +220,17 @@ int32_t ptb_scene_set_sky(ptb_ctx* ctx, const ptb_sky* sky);
 /* Replaces Bvh::new (acceleration/mod.rs:58-93): builds the acceleration structure on the device — always the LBVH
  * (Morton sort, Karras hierarchy, refit), and on top of it, when the wide tree is selected, its SAH-driven collapse into
  * a compressed 8-wide BVH (quantised 96-byte nodes, leaf groups of up to 3 primitives) which the traversal kernels then
- * walk instead. PTB_BUILD_DEFAULT follows the environment (PTB_BVH=binary|wide) and otherwise the library's default. */
-enum { PTB_BUILD_DEFAULT = 0, PTB_BUILD_BINARY = 1, PTB_BUILD_WIDE = 2 };
+ * walk instead. PTB_BUILD_SAH makes the binary tree with the device's top-down SAH builder instead of the Karras
+ * hierarchy (8 bins on each axis of a node's box, exact sweep for subtrees of <= 32 primitives, one primitive per leaf;
+ * the replacement for the QUALITY of build_bvh + Split::Sah, acceleration/mod.rs:97-160, split.rs:78-187; CPU definition
+ * oracle/sah_ref.hpp; 2..2^24 primitives, otherwise the LBVH is built). Same hits, fewer nodes per ray, a slower commit.
+ * PTB_BUILD_DEFAULT follows the environment (PTB_BVH=binary|lbvh|sah|wide) and otherwise the library's default. */
+enum { PTB_BUILD_DEFAULT = 0, PTB_BUILD_BINARY = 1, PTB_BUILD_WIDE = 2, PTB_BUILD_SAH = 4 };
 int32_t ptb_scene_commit(ptb_ctx* ctx, uint32_t build_flags);
 
 /* Bit-exact test hooks: n_prims Morton codes and primitive ids in sorted order, n_prims-1 nodes
- * (1 node when n_prims == 1). Any pointer may be NULL. */
+ * (1 node when n_prims == 1). Any pointer may be NULL. After an SAH build prim_sorted is the SAH tree's own primitive
+ * order (what its leaf references index) while morton_sorted still holds the sorted codes of the order it started from. */
 int32_t ptb_bvh_info(ptb_ctx* ctx, uint64_t* n_prims, uint64_t* n_nodes);
 int32_t ptb_bvh_export(ptb_ctx* ctx, uint32_t* morton_sorted, uint32_t* prim_sorted, ptb_bvh_node* nodes);
 /* The same binary tree as the traversal kernels read it (bit-exact test hook): 32 bytes per node, both children's boxes
@@ -240,6 +245,9 @@ int32_t ptb_bvh_export_quantised(ptb_ctx* ctx, float frame[6], void* nodes32);
  * 96 bytes each (layout: raytracing-rust_b200/csrc/ptb_common.cuh CwNode == oracle/cwbvh_ref.hpp CwNode), slot_prim maps
  * the tree's primitive order to original primitive ids (n_prims entries). Any pointer may be NULL. */
 int32_t ptb_bvh_wide_info(ptb_ctx* ctx, uint64_t* n_nodes, uint32_t* max_leaf);
+/* Which builder made the committed tree: *builder = PTB_BUILD_BINARY (Karras LBVH), PTB_BUILD_SAH or PTB_BUILD_WIDE;
+ * *sah_levels = levels of large tasks the SAH build took (0 otherwise). Either pointer may be NULL. */
+int32_t ptb_bvh_builder(ptb_ctx* ctx, uint32_t* builder, uint32_t* sah_levels);
 int32_t ptb_bvh_wide_export(ptb_ctx* ctx, void* nodes96, uint32_t* slot_prim);
 
 /* ---------------------------------------------------------- closest hit -- */

@@ -63,6 +63,8 @@ def _load():
     lib.orc_lbvh_snap16.argtypes = [P, C.c_float]
     lib.orc_lbvh_quantise.argtypes = [P, P, P]
     lib.orc_lbvh_ploc.restype = C.c_int
+    lib.orc_lbvh_sah.argtypes = [P, C.c_int, P]
+    lib.orc_lbvh_sah.restype = C.c_int
     lib.orc_lbvh_export.argtypes = [P, P, P, P]
     lib.orc_lbvh_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
     lib.orc_lbvh_node_counts.argtypes = [P, P, C.c_size_t, P, C.c_int]
@@ -256,6 +258,14 @@ class OracleScene:
         """Replaces the LBVH's hierarchy by the PLOC hierarchy over the same Morton order (ploc_ref.hpp); returns the rounds."""
         self._lbvh = True
         return lib.orc_lbvh_ploc(self._h, radius)
+
+    def lbvh_sah(self, nbins=8):
+        """Replaces the LBVH's hierarchy and primitive order by the SAH tree of sah_ref.hpp (CPU statement of the device's
+        SAH builder). Returns (levels of large tasks, most large tasks in a level, small tasks, fallback splits)."""
+        self._lbvh = True
+        st = np.zeros(4, np.uint32)
+        lib.orc_lbvh_sah(self._h, nbins, _p(st))
+        return tuple(int(x) for x in st)
 
     def lbvh_quantise(self):
         """(frame, (m, 8) uint32 words): the 32-byte traversal nodes of the LBVH, CPU definition (lbvh_ref.hpp quantise)."""

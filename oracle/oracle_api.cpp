@@ -11,6 +11,7 @@
 #include "cwbvh_ref.hpp"
 #include "lbvh_ref.hpp"
 #include "ploc_ref.hpp"
+#include "sah_ref.hpp"
 #include "ref_integrators.hpp"
 
 namespace ref {
@@ -343,6 +344,14 @@ void orc_lbvh_snap16(orc_scene* s, float extra) {
 int orc_lbvh_ploc(orc_scene* s, int radius) {
   if (!s->lbvh_built) orc_lbvh_build(s);
   return ploc_rebuild(s->lbvh, radius);
+}
+// replaces the LBVH's hierarchy AND primitive order by the binned / swept SAH tree of sah_ref.hpp (the CPU statement of
+// csrc/sah_build.cu); stats4: levels of large tasks, most large tasks in a level, small tasks, fallback splits
+int orc_lbvh_sah(orc_scene* s, int nbins, uint32_t* stats4) {
+  if (!s->lbvh_built) orc_lbvh_build(s);
+  const SahStats st = sah_rebuild(s->lbvh, nbins);
+  if (stats4) { stats4[0] = st.levels; stats4[1] = st.max_tasks; stats4[2] = st.small_tasks; stats4[3] = st.fallbacks; }
+  return 0;
 }
 void orc_lbvh_export(const orc_scene* s, uint32_t* morton, uint32_t* prim_sorted, ptb_bvh_node* nodes) {
   const Lbvh& l = s->lbvh;

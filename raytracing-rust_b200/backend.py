@@ -96,8 +96,9 @@ class Context:
         _check(h, L.lib.ptb_scene_set_sky(h, L.ptr(s.sky)))
 
     def commit(self, flags: int = 0):
-        """Bvh::new: device LBVH build (+ its collapse into the compressed 8-wide tree when selected: L.BUILD_WIDE, or
-        L.BUILD_DEFAULT with PTB_BVH=wide / the library default)."""
+        """Bvh::new: device build of the acceleration structure. L.BUILD_BINARY: Karras LBVH; L.BUILD_SAH: top-down SAH
+        builder (sah_build.cu); L.BUILD_WIDE: the LBVH collapsed into the compressed 8-wide tree; L.BUILD_DEFAULT follows
+        PTB_BVH=binary|lbvh|sah|wide, else the library default."""
         _check(self._h, L.lib.ptb_scene_commit(self._h, flags))
 
     def bvh_info(self):
@@ -120,6 +121,12 @@ class Context:
         nodes = np.zeros((m, 8), np.uint32)
         _check(self._h, L.lib.ptb_bvh_export_quantised(self._h, L.ptr(frame), L.ptr(nodes)))
         return frame, nodes
+
+    def bvh_builder(self):
+        """(L.BUILD_BINARY | L.BUILD_SAH | L.BUILD_WIDE: which builder made the committed tree, levels the SAH build took)."""
+        a, b = C.c_uint32(), C.c_uint32()
+        _check(self._h, L.lib.ptb_bvh_builder(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def bvh_wide_info(self):
         """(number of 96-byte nodes of the compressed 8-wide tree — 0 when the scene uses the binary tree, max leaf size)."""

@@ -105,6 +105,7 @@ int32_t ptb_destroy(ptb_ctx* ctx) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->h_sah) cudaFreeHost(c->h_sah);
   for (float* h : c->h_pass)
     if (h) cudaFreeHost(h);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -274,6 +275,14 @@ int32_t ptb_bvh_info(ptb_ctx* ctx, uint64_t* n_prims, uint64_t* n_nodes) {
   if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
   if (n_prims) *n_prims = c->n_prims;
   if (n_nodes) *n_nodes = c->n_nodes;
+  return PTB_OK;
+}
+
+int32_t ptb_bvh_builder(ptb_ctx* ctx, uint32_t* builder, uint32_t* sah_levels) {
+  CTX_OR_FAIL(ctx);
+  if (!c->committed) return set_error(c, PTB_ERR_INVALID, "scene not committed");
+  if (builder) *builder = c->wide ? PTB_BUILD_WIDE : (c->sah ? PTB_BUILD_SAH : PTB_BUILD_BINARY);
+  if (sah_levels) *sah_levels = c->sah ? c->sah_levels : 0u;
   return PTB_OK;
 }
 

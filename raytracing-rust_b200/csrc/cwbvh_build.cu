@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_add(uint32_t* __restrict__ 
   for (int k = 0; k < kScanItems; ++k)
     if (base + k < n) data[base + k] += add;
 }
-static int32_t exclusive_scan(Ctx* c, uint32_t* data, uint32_t n, uint32_t* block_sum, uint32_t* total_out) {
+int32_t exclusive_scan(Ctx* c, uint32_t* data, uint32_t n, uint32_t* block_sum, uint32_t* total_out) {
   const uint32_t n_blocks = (n + kScanTile - 1) / kScanTile;
   if (n_blocks > (uint32_t)kScanTile) return set_error(c, PTB_ERR_INVALID, "scan of %u elements needs a third level", n);
   k_scan_local<<<n_blocks, kScanBlock, 0, c->stream>>>(data, n, block_sum);

@@ -529,6 +529,12 @@ __global__ void k_collect_lights(const ptb_sphere* __restrict__ spheres, uint32_
 #ifndef PTB_DEFAULT_WIDE
 #define PTB_DEFAULT_WIDE 0  // tree behind PTB_BUILD_DEFAULT (see the comment at its use); decided by measurement, DESIGN.md
 #endif
+#ifndef PTB_DEFAULT_SAH
+// builder of the binary tree behind PTB_BUILD_DEFAULT: 0 Karras LBVH, 1 SAH (sah_build.cu). Measured on B200: C3 4335 -> 4850
+// Mrays/s (256 spp per step), 4010 -> 4467 (32 spp), C5 4625 -> 4918, for a commit of 4.3 instead of 0.55 ms at 1 M
+// triangles and 38.8 instead of 4.2 ms at 10 M (profiles/r2_sweeps.md section 12); the reference's own default is its SAH split
+#define PTB_DEFAULT_SAH 1
+#endif
 int32_t build_scene(Ctx* c, uint32_t build_flags) {
   const size_t ns = c->n_spheres, nt = c->n_tris;
   const size_t n = ns + nt;
@@ -650,8 +656,17 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
   // (cwbvh_build.cu). build_flags picks; PTB_BUILD_DEFAULT follows PTB_BVH=binary|wide, else the measured default.
   bool wide = PTB_DEFAULT_WIDE != 0;
   if (const char* e = getenv("PTB_BVH")) wide = strcmp(e, "wide") == 0 ? true : (strcmp(e, "binary") == 0 ? false : wide);
-  if (build_flags & PTB_BUILD_BINARY) wide = false;
-  if (build_flags & PTB_BUILD_WIDE) wide = true;
+  // ... and which builder makes the binary tree: the Karras hierarchy over the Morton order, or the SAH builder
+  // (sah_build.cu) started from that order. The wide tree is always collapsed from the Karras hierarchy.
+  bool sah = PTB_DEFAULT_SAH != 0;
+  if (const char* e = getenv("PTB_BVH")) {
+    if (strcmp(e, "sah") == 0) { sah = true; wide = false; }
+    else if (strcmp(e, "binary") == 0 || strcmp(e, "lbvh") == 0 || strcmp(e, "wide") == 0) sah = false;
+  }
+  if (build_flags & PTB_BUILD_BINARY) { wide = false; sah = false; }
+  if (build_flags & PTB_BUILD_WIDE) { wide = true; sah = false; }
+  if (build_flags & PTB_BUILD_SAH) { wide = false; sah = true; }
+  if (wide || n < 2 || n > (1u << 24)) sah = false;
   c->cw_max_leaf = 3u;
   if (const char* e = getenv("PTB_WIDE_LEAF")) { int v = atoi(e); if (v >= 1 && v <= 3) c->cw_max_leaf = (uint32_t)v; }
   DevBuf &range = c->cw_scratch[8], &final_prim = c->cw_scratch[9];
@@ -659,6 +674,10 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
     PTB_CUDA_TRY(c, range.reserve(c->n_nodes * 8));
     PTB_CUDA_TRY(c, final_prim.reserve(n * 4));
     PTB_CUDA_TRY(c, c->d_prim_sorted.reserve(n * 4));
+  }
+  if (sah) {
+    const int32_t rcs = reserve_sah(c, n32);
+    if (rcs != PTB_OK) return rcs;
   }
   const int T = 256;
   const uint32_t gn = (n32 + T - 1) / T;
@@ -687,11 +706,20 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
     c->stats.kernel_launches += 1;
   } else {
     PTB_CUDA_TRY(c, cudaMemsetAsync(flags.p, 0, c->n_nodes * 4, st));
-    k_hierarchy<<<(n32 - 1 + T - 1) / T, T, 0, st>>>(ka, va, n32, ns32, c->d_nodes.as<BvhNode>(), leaf_parent.as<uint32_t>(),
-                                                     wide ? range.as<uint2>() : nullptr);
+    if (sah) {
+      SahBuildInputs si{bmin.as<float4>(), bmax.as<float4>(), va, vb, c->d_nodes.as<BvhNode>(), leaf_parent.as<uint32_t>(), n32, ns32};
+      const uint32_t* order = nullptr;
+      const int32_t rcs = build_sah(c, si, &order);
+      if (rcs != PTB_OK) return rcs;
+      va = const_cast<uint32_t*>(order);  // the tree's own primitive order from here on
+    } else {
+      k_hierarchy<<<(n32 - 1 + T - 1) / T, T, 0, st>>>(ka, va, n32, ns32, c->d_nodes.as<BvhNode>(), leaf_parent.as<uint32_t>(),
+                                                       wide ? range.as<uint2>() : nullptr);
+      c->stats.kernel_launches += 1;
+    }
     k_refit<<<gn, T, 0, st>>>(n32, va, leaf_parent.as<uint32_t>(), bmin.as<float4>(), bmax.as<float4>(),
                               c->d_nodes.as<BvhNode>(), nbmin.as<float4>(), nbmax.as<float4>(), flags.as<uint32_t>());
-    c->stats.kernel_launches += 2;
+    c->stats.kernel_launches += 1;
   }
   // the 32-byte nodes the traversal kernels read, and their grid (6 floats, read back with the light count below)
   float h_qframe[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -753,6 +781,7 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
   for (int k = 0; k < 3; ++k) { c->dev.q_min[k] = h_qframe[k]; c->dev.q_step[k] = h_qframe[3 + k]; }
   c->dev.cw_nodes = wide ? c->d_cw_nodes.as<CwNode>() : nullptr;
   c->wide = wide;
+  c->sah = sah;
   if (!wide) c->n_cw_nodes = 0;
   c->dev.lights = c->d_lights.as<uint32_t>();
   c->dev.n_lights = nl;

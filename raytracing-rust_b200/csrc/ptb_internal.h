@@ -113,6 +113,10 @@ struct Ctx {
   bool wide = false;          // the committed scene is traversed through the compressed 8-wide tree (d_cw_nodes)
   uint32_t cw_max_leaf = 3;   // primitives per leaf group of the wide tree (1..3)
   DevBuf cw_scratch[10];      // wide-tree build temporaries, grow-only (cwbvh_build.cu; [8] LBVH ranges, [9] final order)
+  bool sah = false;           // the committed scene's binary tree was built by the SAH builder (sah_build.cu)
+  uint32_t sah_levels = 0;    // levels of large tasks the last SAH build took
+  DevBuf sah_scratch[12];     // SAH build temporaries, grow-only
+  uint32_t* h_sah = nullptr;  // pinned: the per-level counters of the SAH build
 
   // render state
   DevBuf d_accum;
@@ -164,6 +168,18 @@ struct CwBuildInputs {
   uint32_t n_prims;
 };
 int32_t build_wide(Ctx* c, const CwBuildInputs& in, uint32_t* final_prim);
+// in-place exclusive prefix sum of n <= 2^24 words (block_sum: 4096 words of scratch; *total_out receives the sum)
+int32_t exclusive_scan(Ctx* c, uint32_t* data, uint32_t n, uint32_t* block_sum, uint32_t* total_out);
+// sah_build.cu — top-down SAH hierarchy in the LBVH's node format (links in nodes[].n3 + leaf_parent; k_refit fills the boxes)
+struct SahBuildInputs {
+  const float4 *bmin, *bmax;      // box of every primitive (original order)
+  uint32_t *order_a, *order_b;    // order_a: Morton position -> original primitive id (the starting order); order_b: scratch
+  BvhNode* nodes;                 // n - 1 nodes
+  uint32_t* leaf_parent;          // n words
+  uint32_t n_prims, n_spheres;
+};
+int32_t build_sah(Ctx* c, const SahBuildInputs& in, const uint32_t** order_out);
+int32_t reserve_sah(Ctx* c, uint32_t n_prims);
 void radix_sort_pairs(Ctx* c, uint32_t*& ka, uint32_t*& va, uint32_t*& kb, uint32_t*& vb, uint32_t n, int passes, uint32_t* hist);
 size_t radix_sort_hist_words(uint32_t n);
 // wavefront.cu

@@ -73,12 +73,19 @@ def report(label):
 
 orc.lbvh_build()
 report("Karras LBVH")
-for radius in (int(x) for x in os.environ.get("RADII", "8,16,32").split(",")):
+for radius in (int(x) for x in os.environ.get("RADII", "8,16,32").split(",") if x):
     t0 = time.time()
     rounds = orc.lbvh_ploc(radius)
     report(f"PLOC r={radius} ({rounds} rounds, {time.time() - t0:.1f}s)")
     orc.lbvh_build()
+for nb in (int(x) for x in os.environ.get("SAH_BINS", "8,16").split(",") if x):
+    orc.lbvh_build()
+    t0 = time.time()
+    st = orc.lbvh_sah(nb)
+    report(f"SAH {nb} bins (levels {st[0]}, tasks <= {st[1]}, small {st[2]}, fallbacks {st[3]}; {time.time() - t0:.1f}s)")
 for extra in (0.0, 1.0, 2.0):
+    if os.environ.get("SNAP", "1") == "0":
+        break
     orc.lbvh_build()
     orc.lbvh_snap16(extra)
     report(f"LBVH, 16-bit boxes +{extra:g}")

@@ -7,7 +7,7 @@ pytestmark = pytest.mark.gpu
 
 def _compare(ptb, orc, gpu_ctx, scene):
     gpu_ctx.upload(scene)
-    gpu_ctx.commit()
+    gpu_ctx.commit(ptb._lib.BUILD_BINARY)
     gm, gp, gn = gpu_ctx.bvh_export()
     o = orc.OracleScene(scene, split_type=-1)
     om, op, on = o.lbvh_export()
@@ -91,7 +91,7 @@ def test_full_size_properties(ptb, gpu_ctx):
     s = ptb.meshgen.c3_scene(1.0)
     assert len(s.triangles) == 1_000_000
     gpu_ctx.upload(s)
-    gpu_ctx.commit()
+    gpu_ctx.commit(ptb._lib.BUILD_BINARY)
     gm, gp, gn = gpu_ctx.bvh_export()
     assert np.all(np.diff(gm.astype(np.int64)) >= 0)
     assert np.array_equal(np.sort(gp), np.arange(1_000_000, dtype=np.uint32))

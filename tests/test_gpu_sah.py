@@ -1,0 +1,180 @@
+"""The device SAH builder (csrc/sah_build.cu, PTB_BUILD_SAH; VERDICT r1 item 5: the QUALITY of the reference's build_bvh +
+Split::Sah, acceleration/mod.rs:97-160, split.rs:78-187) through the C ABI.
+
+  * build: primitive order, child / parent links and boxes are BIT-EXACT against the CPU definition (oracle/sah_ref.hpp),
+    including the degenerate inputs (2, 3, 32, 33 primitives; thousands of identical centroids: the halving fallback);
+  * traversal: identical hits (primitive id, t, u, v bit for bit) to the LBVH tree's and to the reference-semantics oracle,
+    with FEWER nodes fetched per ray; the device's counts stay within the speculation margin of the CPU walk's;
+  * render: the image and every ray counter do not depend on the builder.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import random_rays
+
+pytestmark = pytest.mark.gpu
+
+MISS = 0xFFFFFFFF
+LEAF = 0x80000000
+
+
+@pytest.fixture()
+def sah_ctx(ptb):
+    c = ptb.Context(0)
+    yield c
+    c.close()
+
+
+def commit_sah(ptb, ctx, scene):
+    ctx.upload(scene)
+    ctx.commit(ptb._lib.BUILD_SAH)
+
+
+def check_tree(nodes, prims, n):
+    assert np.array_equal(np.sort(prims), np.arange(n, dtype=np.uint32))
+    refs = np.concatenate([nodes["left"], nodes["right"]])
+    assert np.array_equal(np.sort(refs[refs >= LEAF] & 0x3FFFFFFF), np.arange(n, dtype=np.uint32))   # every leaf once
+    assert np.array_equal(np.sort(refs[refs < LEAF]), np.arange(1, len(nodes), dtype=np.uint32))     # every inner node once
+    assert nodes["parent"][0] == MISS
+    for side, mn, mx in (("left", "lmin", "lmax"), ("right", "rmin", "rmax")):
+        ch = nodes[side]
+        m = ch < LEAF
+        assert np.array_equal(nodes["parent"][ch[m]], np.nonzero(m)[0].astype(np.uint32))
+        c = nodes[ch[m]]
+        assert np.array_equal(nodes[mn][m], np.minimum(c["lmin"], c["rmin"])) and np.array_equal(nodes[mx][m], np.maximum(c["lmax"], c["rmax"]))
+
+
+def compare_with_definition(ptb, orc, ctx, scene):
+    commit_sah(ptb, ctx, scene)
+    _, gp, gn = ctx.bvh_export()
+    o = orc.OracleScene(scene, split_type=-1)
+    o.lbvh_sah()
+    _, op, on = o.lbvh_export()
+    assert np.array_equal(gp, op), "primitive order differs"
+    assert len(gn) == len(on)
+    sphere_bit = np.uint32(0x40000000)   # device-internal flag of a leaf reference (ptb_bvh_export strips nothing)
+    for f in ("left", "right"):
+        assert np.array_equal(gn[f] & ~sphere_bit, on[f]), f"node field {f} differs"
+    assert np.array_equal(gn["parent"], on["parent"])
+    for f in ("lmin", "lmax", "rmin", "rmax"):
+        assert np.array_equal(gn[f].view(np.uint32), on[f].view(np.uint32)), f"node boxes {f} differ (bitwise)"
+    check_tree(gn, gp, scene.n_primitives)
+
+
+def spheres_scene(ptb, rtweekend1, centres, radii):
+    s = copy.deepcopy(rtweekend1)
+    sp = np.zeros(len(centres), ptb._lib.sphere_dtype)
+    sp["center"] = np.asarray(centres, np.float32)
+    sp["radius"] = np.asarray(radii, np.float32)
+    sp["material"] = 0
+    s.spheres = sp
+    return s
+
+
+@pytest.mark.parametrize("which", ["rtweekend1", "overshadowed", "c3_small", "c3_mid"])
+def test_sah_tree_is_bit_exact(ptb, orc, sah_ctx, rtweekend1, overshadowed, which):
+    scene = {"rtweekend1": rtweekend1, "overshadowed": overshadowed}.get(which) or ptb.meshgen.c3_scene(0.05 if which == "c3_small" else 0.3)
+    compare_with_definition(ptb, orc, sah_ctx, scene)
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 31, 32, 33, 64, 65, 1000])
+def test_sah_small_counts(ptb, orc, sah_ctx, rtweekend1, n):
+    rng = np.random.default_rng(n)
+    compare_with_definition(ptb, orc, sah_ctx, spheres_scene(ptb, rtweekend1, rng.uniform(-3, 3, (n, 3)), rng.uniform(0.01, 0.4, n)))
+
+
+def test_sah_mixed_spheres_and_triangles(ptb, orc, sah_ctx, rtweekend1):
+    s = ptb.meshgen.c3_scene(0.05)
+    rng = np.random.default_rng(5)
+    t = spheres_scene(ptb, rtweekend1, rng.uniform(-4, 4, (300, 3)) + np.array([0, 4, 0]), rng.uniform(0.01, 0.3, 300))
+    s.spheres = t.spheres
+    s.spheres["material"] = 0
+    compare_with_definition(ptb, orc, sah_ctx, s)
+    rays = random_rays(ptb, 100_000, 9, centre=(0, 4, 1), radius=5.0)
+    g = sah_ctx.closest_hit(rays)
+    r = orc.OracleScene(s).closest_hit(rays)
+    tie = (g["prim"] != r["prim"]) & (g["t"] == r["t"])
+    assert tie.mean() < 1e-3 and np.array_equal(g["prim"][~tie], r["prim"][~tie])
+    assert np.array_equal(g["t"][~tie].view(np.uint32), r["t"][~tie].view(np.uint32))
+    assert (g["prim"] < len(s.spheres)).any() and (g["prim"][g["prim"] != MISS] >= len(s.spheres)).any()
+
+
+def test_sah_identical_centroids(ptb, orc, sah_ctx, rtweekend1):
+    """Thousands of primitives sharing a centroid: no plane separates them, the task is halved in its current order."""
+    centres = np.repeat(np.array([[0, 1, 0], [1, 1, 0], [0, 2, 0], [0, 1, 0.5], [3, 3, 3]], np.float32), 1000, axis=0)
+    compare_with_definition(ptb, orc, sah_ctx, spheres_scene(ptb, rtweekend1, centres, np.tile(np.linspace(0.01, 0.5, 1000, dtype=np.float32), 5)))
+    compare_with_definition(ptb, orc, sah_ctx, spheres_scene(ptb, rtweekend1, np.zeros((700, 3)), np.linspace(0.1, 2.0, 700)))
+
+
+@pytest.mark.parametrize("which", ["rtweekend1", "overshadowed", "c3"])
+def test_sah_traversal_matches_lbvh_and_oracle(ptb, orc, gpu_ctx, sah_ctx, rtweekend1, overshadowed, which):
+    scene, centre, radius = {"rtweekend1": (rtweekend1, (0, 1, 0), 3.0), "overshadowed": (overshadowed, (-0.3, 0.3, -0.3), 1.5),
+                             "c3": (ptb.meshgen.c3_scene(0.3), (0, 4, 1), 5.0)}[which]
+    rays = random_rays(ptb, 300_000, 52, centre=centre, radius=radius)
+    counts = {}
+    hits = {}
+    for name, ctx, flag in (("lbvh", gpu_ctx, ptb._lib.BUILD_BINARY), ("sah", sah_ctx, ptb._lib.BUILD_SAH)):
+        ctx.upload(scene)
+        ctx.commit(flag)
+        ctx.set_option(ptb._lib.OPT_COUNT_TRAVERSAL, 1)
+        ctx.stats_reset()
+        hits[name] = ctx.closest_hit(rays)
+        st = ctx.stats()
+        ctx.set_option(ptb._lib.OPT_COUNT_TRAVERSAL, 0)
+        assert st.rays_counted == len(rays)
+        counts[name] = (st.nodes_fetched / len(rays), st.prims_tested / len(rays))
+    for f in ("prim", "t", "u", "v"):
+        assert np.array_equal(hits["sah"][f].view(np.uint32), hits["lbvh"][f].view(np.uint32)), f
+    o = orc.OracleScene(scene)                      # the reference's own SAH tree and test-all walk
+    r = o.closest_hit(rays)
+    w = hits["sah"]
+    tie = (w["prim"] != r["prim"]) & (w["t"] == r["t"])
+    assert tie.mean() < 1e-3 and np.array_equal(w["prim"][~tie], r["prim"][~tie])
+    assert np.array_equal(w["t"][~tie].view(np.uint32), r["t"][~tie].view(np.uint32))
+    # CPU statement of the same walk over the same (bit-exact) tree: the device speculates a few percent more
+    o2 = orc.OracleScene(scene, split_type=-1)
+    o2.lbvh_sah()
+    h, nodes, prims = o2.lbvh_closest_hit(rays)
+    assert np.array_equal(h["prim"], w["prim"])
+    v_cpu, t_cpu = nodes / len(rays), prims / len(rays)
+    assert v_cpu <= counts["sah"][0] <= 1.10 * v_cpu + 0.05, (counts, v_cpu)
+    assert t_cpu <= counts["sah"][1] <= 1.25 * t_cpu + 0.05, (counts, t_cpu)
+    if which == "c3":
+        assert counts["sah"][0] < 0.95 * counts["lbvh"][0], counts      # what the builder is for
+
+
+def test_sah_full_size_c3(ptb, orc, sah_ctx):
+    """BASELINE config C3 at full size: tree consistency, hits against the LBVH oracle, and the build's time."""
+    s = ptb.meshgen.c3_scene(1.0)
+    commit_sah(ptb, sah_ctx, s)
+    commit_sah(ptb, sah_ctx, s)                     # second commit: no allocation in the timed build
+    build_ms = sah_ctx.stats().build_ms
+    _, gp, gn = sah_ctx.bvh_export()
+    check_tree(gn, gp, 1_000_000)
+    rays = random_rays(ptb, 1 << 19, 78, centre=(0, 4, 1), radius=6.0)
+    g = sah_ctx.closest_hit(rays)
+    h, _, _ = orc.OracleScene(s, split_type=-1).lbvh_closest_hit(rays)
+    assert np.array_equal(g["prim"], h["prim"]) and np.array_equal(g["t"].view(np.uint32), h["t"].view(np.uint32))
+    print(f"SAH build of 1 M triangles: {build_ms:.2f} ms")
+    assert build_ms < 60.0
+
+
+@pytest.mark.parametrize("method", [0, 1])
+def test_render_does_not_depend_on_the_builder(ptb, gpu_ctx, sah_ctx, overshadowed, method):
+    scenes = [overshadowed, ptb.meshgen.c3_scene(0.05)] if method == 0 else [overshadowed]
+    for scene in scenes:
+        o = ptb.RenderOptions(samples_per_pixel=16, render_method=method, width=160, height=90, seed=4)
+        res = []
+        for ctx, flag in ((gpu_ctx, ptb._lib.BUILD_BINARY), (sah_ctx, ptb._lib.BUILD_SAH)):
+            ctx.upload(scene)
+            ctx.commit(flag)
+            ctx.accum_clear()
+            ctx.stats_reset()
+            ctx.render(o)
+            st = ctx.stats()
+            res.append((ctx.accum_read(160, 90).copy(),
+                        (st.rays_camera, st.rays_bounce, st.rays_shadow_light, st.rays_shadow_sky, st.rays_reference, st.paths)))
+        assert np.allclose(res[0][0], res[1][0], rtol=1e-5, atol=1e-5)
+        assert res[0][1] == res[1][1]

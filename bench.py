@@ -540,7 +540,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": e2e, "gpu_launches": int(st.kernel_launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "run": {"spp_this_rank": my_spp, "bvh": (f"compressed 8-wide, {n_wide} nodes x 96 B, leaf groups <= {wide_leaf}" if n_wide
-                                                     else f"binary LBVH, {n_nodes} nodes x 64 B"),
+                                                     else f"binary, {binary_tree_label(ctx)}, {n_nodes} nodes x 64 B"),
                     "bvh_nodes": n_wide or n_nodes, "node_bytes": node_bytes, "bvh_build_ms": build_ms, "rays_reference_style": st.rays_reference,
                     "wall_s": t_wall, "wavefront_iterations": int(st.wavefront_iterations)},
         }
@@ -552,6 +552,12 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def binary_tree_label(ctx):
+    """Which builder made the committed binary tree (ptb_bvh_builder): the device SAH builder or the Karras LBVH."""
+    builder, levels = ctx.bvh_builder()
+    return f"device SAH builder ({levels} levels of binned splits + per-warp sweeps)" if builder == 4 else "Karras LBVH"
 
 
 def run_closest_hit(args, rank, world, local, n_tris, n_rays, cpu=True, steps=None, warmup=None):
@@ -668,7 +674,7 @@ def run_closest_hit(args, rank, world, local, n_tris, n_rays, cpu=True, steps=No
                      "limiter": ev.get("limiter")},
         "cpu_baseline": cpu_b,
         "run": {"rays_per_step_per_gpu": batch, "rays_timed": batch * K * world, "bvh_nodes": n_wide or n_nodes, "node_bytes": node_bytes,
-                "bvh": "compressed 8-wide" if n_wide else "binary LBVH", "build_ms": ctx_build_ms, "hit_fraction": hit_frac,
+                "bvh": "compressed 8-wide" if n_wide else "binary, " + binary_tree_label(ctx), "build_ms": ctx_build_ms, "hit_fraction": hit_frac,
                 "ray_stream_max_abs_dev_vs_numpy": stream_err},
     }
 

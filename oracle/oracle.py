@@ -63,7 +63,7 @@ def _load():
     lib.orc_lbvh_snap16.argtypes = [P, C.c_float]
     lib.orc_lbvh_quantise.argtypes = [P, P, P]
     lib.orc_lbvh_ploc.restype = C.c_int
-    lib.orc_lbvh_sah.argtypes = [P, C.c_int, P]
+    lib.orc_lbvh_sah.argtypes = [P, C.c_int, C.c_uint32, P]
     lib.orc_lbvh_sah.restype = C.c_int
     lib.orc_lbvh_export.argtypes = [P, P, P, P]
     lib.orc_lbvh_closest_hit.argtypes = [P, P, C.c_size_t, P, C.c_int, P]
@@ -259,12 +259,13 @@ class OracleScene:
         self._lbvh = True
         return lib.orc_lbvh_ploc(self._h, radius)
 
-    def lbvh_sah(self, nbins=8):
+    def lbvh_sah(self, nbins=8, max_depth=60):
         """Replaces the LBVH's hierarchy and primitive order by the SAH tree of sah_ref.hpp (CPU statement of the device's
-        SAH builder). Returns (levels of large tasks, most large tasks in a level, small tasks, fallback splits)."""
+        SAH builder). Returns (levels of large tasks, most large tasks in a level, small tasks, halving splits, depth of the
+        deepest leaf, splits replaced by halving because of the depth bound)."""
         self._lbvh = True
-        st = np.zeros(4, np.uint32)
-        lib.orc_lbvh_sah(self._h, nbins, _p(st))
+        st = np.zeros(6, np.uint32)
+        lib.orc_lbvh_sah(self._h, nbins, max_depth, _p(st))
         return tuple(int(x) for x in st)
 
     def lbvh_quantise(self):

@@ -346,11 +346,12 @@ int orc_lbvh_ploc(orc_scene* s, int radius) {
   return ploc_rebuild(s->lbvh, radius);
 }
 // replaces the LBVH's hierarchy AND primitive order by the binned / swept SAH tree of sah_ref.hpp (the CPU statement of
-// csrc/sah_build.cu); stats4: levels of large tasks, most large tasks in a level, small tasks, fallback splits
-int orc_lbvh_sah(orc_scene* s, int nbins, uint32_t* stats4) {
+// csrc/sah_build.cu); stats6: levels of large tasks, most large tasks in a level, small tasks, halving splits, depth of the
+// deepest leaf, splits replaced by halving because of the depth bound
+int orc_lbvh_sah(orc_scene* s, int nbins, uint32_t max_depth, uint32_t* stats4) {
   if (!s->lbvh_built) orc_lbvh_build(s);
-  const SahStats st = sah_rebuild(s->lbvh, nbins);
-  if (stats4) { stats4[0] = st.levels; stats4[1] = st.max_tasks; stats4[2] = st.small_tasks; stats4[3] = st.fallbacks; }
+  const SahStats st = sah_rebuild(s->lbvh, nbins, max_depth);
+  if (stats4) { stats4[0] = st.levels; stats4[1] = st.max_tasks; stats4[2] = st.small_tasks; stats4[3] = st.fallbacks; stats4[4] = st.max_depth; stats4[5] = st.depth_limited; }
   return 0;
 }
 void orc_lbvh_export(const orc_scene* s, uint32_t* morton, uint32_t* prim_sorted, ptb_bvh_node* nodes) {

@@ -20,6 +20,10 @@
 //     or more positions: candidate (i, a) sends to the left every member j whose (c_a[j], j) is lexicographically
 //     <= (c_a[i], i); candidates that send everything to the left are skipped; cost as above; the minimum by
 //     (cost, i, a) wins; stable partition. No candidate with a comparable cost (NaN): halved in order.
+//   depth bound: the traversal kernels' stacks hold 64 entries (ptb_traverse.cuh kStackDepth; the Karras tree is at most
+//     62 levels deep). A split — in either regime — whose children could not both be finished by halving within
+//     kSahMaxDepth levels (child depth + ceil(log2(child size)) > kSahMaxDepth) is replaced by the halving split, which
+//     keeps that invariant; no leaf lies deeper than kSahMaxDepth.
 //   node numbering: a node is named after the gap it splits at (the last position of its left child), which is unique in
 //     a binary tree over a sequence — except that the root is node 0 and the node of gap 0 takes the root's gap.
 #pragma once
@@ -32,6 +36,10 @@ namespace ref {
 
 static const uint32_t kSahSmall = 32;
 static const uint32_t kSahNone = 0xFFFFFFFFu;
+static const uint32_t kSahMaxDepth = 60;
+static inline uint32_t sah_ceil_log2(uint32_t n) { return n <= 1u ? 0u : 32u - (uint32_t)__builtin_clz(n - 1u); }
+// can a subtree of n positions whose root sits at `depth` be finished by halving without exceeding max_depth?
+static inline bool sah_fits(uint32_t depth, uint32_t n, uint32_t max_depth) { return depth + sah_ceil_log2(n) <= max_depth; }
 
 struct SahBox {
   float mn[3], mx[3];
@@ -45,10 +53,11 @@ struct SahBox {
 struct SahTask {
   uint32_t lo, hi;  // positions [lo, hi)
   uint32_t parent, side;
+  uint32_t depth;   // of the task's node (root: 0)
   SahBox box;
 };
 struct SahStats {
-  uint32_t levels = 0, max_tasks = 0, small_tasks = 0, fallbacks = 0;
+  uint32_t levels = 0, max_tasks = 0, small_tasks = 0, fallbacks = 0, max_depth = 0, depth_limited = 0;
 };
 
 struct SahBuilder {
@@ -58,7 +67,8 @@ struct SahBuilder {
   std::vector<uint32_t> order;  // position -> original primitive
   uint32_t root_gap = kSahNone;
   SahStats stats;
-  SahBuilder(Lbvh& l_, int nbins) : l(l_), nb(nbins) {}
+  uint32_t max_depth;  // kSahMaxDepth, or lower (test hook; never below what halving alone needs)
+  SahBuilder(Lbvh& l_, int nbins, uint32_t max_depth_) : l(l_), nb(nbins), max_depth(max_depth_) {}
 
   uint32_t node_id(uint32_t gap) {
     if (root_gap == kSahNone) { root_gap = gap; return 0u; }
@@ -128,6 +138,10 @@ struct SahBuilder {
             if (cost < best) { best = cost; best_axis = a; best_bin = i; best_cl = c; }
           }
         }
+        if (best_axis >= 0 && !(sah_fits(t.depth + 1u, best_cl, max_depth) && sah_fits(t.depth + 1u, len - best_cl, max_depth))) {
+          best_axis = -1;
+          ++stats.depth_limited;
+        }
         SahTask L, R;
         uint32_t cl;
         if (best_axis < 0) {
@@ -152,9 +166,10 @@ struct SahBuilder {
         const uint32_t id = make_node(t.lo, cl, t.parent, t.side);
         L.lo = t.lo; L.hi = t.lo + cl; L.parent = id; L.side = 0;
         R.lo = t.lo + cl; R.hi = t.hi; R.parent = id; R.side = 1;
+        L.depth = R.depth = t.depth + 1u;
         for (const SahTask* c : {&L, &R}) {
           const uint32_t cn = c->hi - c->lo;
-          if (cn == 1) link(id, c->side, PTB_LEAF_BIT | c->lo);
+          if (cn == 1) { link(id, c->side, PTB_LEAF_BIT | c->lo); if (c->depth > stats.max_depth) stats.max_depth = c->depth; }
           else if (cn <= kSahSmall) small.push_back(*c);
           else next.push_back(*c);
         }
@@ -166,8 +181,8 @@ struct SahBuilder {
   void run_small(const SahTask& t) {
     ++stats.small_tasks;
     // segments of the task, processed until every one is a single position; a segment's split depends on its members only
-    struct Seg { uint32_t lo, hi, parent, side; };
-    std::vector<Seg> segs{Seg{t.lo, t.hi, t.parent, t.side}}, nxt;
+    struct Seg { uint32_t lo, hi, parent, side, depth; };
+    std::vector<Seg> segs{Seg{t.lo, t.hi, t.parent, t.side, t.depth}}, nxt;
     std::vector<uint32_t> tmp;
     while (!segs.empty()) {
       nxt.clear();
@@ -192,6 +207,10 @@ struct SahBuilder {
             const float cost = L.half_area() * (float)cl + R.half_area() * (float)(len - cl);
             if (cost < best) { best = cost; best_a = a; best_i = i; best_cl = cl; }
           }
+        if (best_a >= 0 && !(sah_fits(s.depth + 1u, best_cl, max_depth) && sah_fits(s.depth + 1u, len - best_cl, max_depth))) {
+          best_a = -1;
+          ++stats.depth_limited;
+        }
         uint32_t cl;
         if (best_a < 0) {
           ++stats.fallbacks;
@@ -209,10 +228,11 @@ struct SahBuilder {
           for (uint32_t k = 0; k < len; ++k) order[s.lo + k] = tmp[k];
         }
         const uint32_t id = make_node(s.lo, cl, s.parent, s.side);
+        if (s.depth + 1u > stats.max_depth) stats.max_depth = s.depth + 1u;
         if (cl == 1) link(id, 0, PTB_LEAF_BIT | s.lo);
-        else nxt.push_back(Seg{s.lo, s.lo + cl, id, 0});
+        else nxt.push_back(Seg{s.lo, s.lo + cl, id, 0, s.depth + 1u});
         if (len - cl == 1) link(id, 1, PTB_LEAF_BIT | (s.hi - 1u));
-        else nxt.push_back(Seg{s.lo + cl, s.hi, id, 1});
+        else nxt.push_back(Seg{s.lo + cl, s.hi, id, 1, s.depth + 1u});
       }
       segs.swap(nxt);
     }
@@ -231,10 +251,12 @@ struct SahBuilder {
   void run() {
     const size_t n = l.prim_sorted.size();
     if (n < 2) return;  // 0 / 1 primitive: the LBVH's own single node stands
+    if (max_depth == 0u || max_depth > kSahMaxDepth) max_depth = kSahMaxDepth;
+    if (max_depth < sah_ceil_log2((uint32_t)n)) max_depth = sah_ceil_log2((uint32_t)n);
     pbox.resize(n);
     order = l.prim_sorted;
     SahTask root;
-    root.lo = 0; root.hi = (uint32_t)n; root.parent = kSahNone; root.side = 0;
+    root.lo = 0; root.hi = (uint32_t)n; root.parent = kSahNone; root.side = 0; root.depth = 0;
     root.box.reset();
     for (size_t i = 0; i < n; ++i) {
       Vec3 a, b;
@@ -252,8 +274,8 @@ struct SahBuilder {
   }
 };
 
-static inline SahStats sah_rebuild(Lbvh& l, int nbins) {
-  SahBuilder b(l, nbins);
+static inline SahStats sah_rebuild(Lbvh& l, int nbins, uint32_t max_depth = kSahMaxDepth) {
+  SahBuilder b(l, nbins, max_depth);
   b.run();
   return b.stats;
 }

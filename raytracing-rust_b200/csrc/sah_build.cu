@@ -28,6 +28,9 @@ namespace {
 
 constexpr int kSahBins = 8;
 constexpr uint32_t kSahSmall = 32;
+// The traversal kernels' stacks hold 64 entries (ptb_traverse.cuh kStackDepth, ptb_packet.cuh): a split whose children could
+// not both be finished by halving within kSahMaxDepth levels is replaced by the halving split (oracle/sah_ref.hpp).
+constexpr uint32_t kSahMaxDepth = 60;
 constexpr int kBinWords = 7;                          // min xyz, max xyz (order-preserving uint), count
 constexpr int kTaskBinWords = 3 * kSahBins * kBinWords;  // 168
 
@@ -35,7 +38,8 @@ struct SahTask {  // 48 bytes
   uint32_t lo, hi;  // positions [lo, hi)
   uint32_t parent, side;
   float mn[3], mx[3];
-  uint32_t _pad[2];
+  uint32_t depth;  // of the task's node (root: 0)
+  uint32_t _pad;
 };
 struct SahSplit {  // per task of the current level, written by k_sah_eval / k_sah_emit
   int32_t axis;    // -1: halved in its current order
@@ -66,6 +70,14 @@ __device__ __forceinline__ bool axis_scale(float mn, float mx, float& scale) {
   return scale < 1.0e30f;
 }
 __device__ __forceinline__ int bin_of(float c, float mn, float scale) { return (int)fminf((c - mn) * scale, (float)(kSahBins - 1)); }
+__host__ __device__ __forceinline__ uint32_t sah_ceil_log2(uint32_t n) {
+  uint32_t k = 0u;
+  while (k < 32u && (1ull << k) < (unsigned long long)n) ++k;
+  return k;
+}
+__device__ __forceinline__ bool sah_fits(uint32_t depth, uint32_t n, uint32_t max_depth) {
+  return depth + (n <= 1u ? 0u : 32u - (uint32_t)__clz(n - 1u)) <= max_depth;
+}
 __device__ __forceinline__ uint32_t node_id(uint32_t gap, uint32_t root_gap) {
   return gap == root_gap ? 0u : (gap == 0u ? root_gap : gap);
 }
@@ -100,7 +112,8 @@ __global__ void k_sah_root(const uint32_t* __restrict__ box6, uint32_t n, SahTas
   SahTask t;
   t.lo = 0u; t.hi = n; t.parent = kNone; t.side = 0u;
   for (int k = 0; k < 3; ++k) { t.mn[k] = sah_unflip(box6[k]); t.mx[k] = sah_unflip(box6[3 + k]); }
-  t._pad[0] = t._pad[1] = 0u;
+  t.depth = 0u;
+  t._pad = 0u;
   *task = t;
   counters[0] = 0u;
   counters[1] = kNone;
@@ -186,7 +199,7 @@ k_sah_bin(uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __rest
 __global__ void __launch_bounds__(128)
 k_sah_eval(uint32_t n_tasks, const SahTask* __restrict__ tasks, const uint32_t* __restrict__ bins, SahSplit* __restrict__ splits,
            SahTask* __restrict__ child_tasks, uint32_t* __restrict__ n_large, BvhNode* nodes, uint32_t* __restrict__ leaf_parent,
-           SahTask* __restrict__ small, uint32_t* counters) {
+           SahTask* __restrict__ small, uint32_t* counters, uint32_t max_depth) {
   const uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
   if (ti >= n_tasks) return;
   const SahTask t = tasks[ti];
@@ -228,6 +241,7 @@ k_sah_eval(uint32_t n_tasks, const SahTask* __restrict__ tasks, const uint32_t* 
       if (cost < best) { best = cost; best_axis = a; best_bin = i; best_cl = c; best_scale = scale; }
     }
   }
+  if (best_axis >= 0 && !(sah_fits(t.depth + 1u, best_cl, max_depth) && sah_fits(t.depth + 1u, len - best_cl, max_depth))) best_axis = -1;
   SahTask L, R;
   uint32_t cl;
   if (best_axis < 0) {
@@ -259,7 +273,8 @@ k_sah_eval(uint32_t n_tasks, const SahTask* __restrict__ tasks, const uint32_t* 
   link_child(nodes, t.parent, t.side, id);
   L.lo = t.lo; L.hi = t.lo + cl; L.parent = id; L.side = 0u;
   R.lo = t.lo + cl; R.hi = t.hi; R.parent = id; R.side = 1u;
-  L._pad[0] = L._pad[1] = R._pad[0] = R._pad[1] = 0u;
+  L.depth = R.depth = t.depth + 1u;
+  L._pad = R._pad = 0u;
   SahSplit sp;
   sp.axis = best_axis;
   sp.bin = best_bin;
@@ -378,10 +393,10 @@ k_sah_scatter(uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __
 
 // ------------------------------------------------------------------------------------------ S6
 constexpr int kSmallWarps = 4;
-constexpr int kSmallWords = 14;  // primitive, box (6), centroid (3), segment lo / hi, parent, side
+constexpr int kSmallWords = 15;  // primitive, box (6), centroid (3), segment lo / hi, parent, side, depth
 __global__ void __launch_bounds__(32 * kSmallWarps)
 k_sah_small(uint32_t n_small, const SahTask* __restrict__ small, uint32_t* __restrict__ order, const float4* __restrict__ bmin,
-            const float4* __restrict__ bmax, BvhNode* nodes, uint32_t* __restrict__ leaf_parent, uint32_t* counters) {
+            const float4* __restrict__ bmax, BvhNode* nodes, uint32_t* __restrict__ leaf_parent, uint32_t* counters, uint32_t max_depth) {
   __shared__ uint32_t sm[kSmallWarps][kSmallWords][32];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t ti = blockIdx.x * kSmallWarps + warp;
@@ -398,7 +413,7 @@ k_sah_small(uint32_t n_small, const SahTask* __restrict__ small, uint32_t* __res
 #pragma unroll
     for (int k = 0; k < 3; ++k) c[k] = 0.5f * (bx[k] + bx[3 + k]);
   }
-  uint32_t seg_lo = active ? 0u : lane, seg_hi = active ? m : lane, par = t.parent, side = t.side;
+  uint32_t seg_lo = active ? 0u : lane, seg_hi = active ? m : lane, par = t.parent, side = t.side, depth = t.depth;
   uint32_t root_gap = t.parent == kNone ? kNone : counters[1];
   const float inf = __int_as_float(0x7f800000);
   for (;;) {
@@ -457,6 +472,7 @@ k_sah_small(uint32_t n_small, const SahTask* __restrict__ small, uint32_t* __res
     const int pa = __shfl_sync(0xffffffffu, best_a, src);
     const float pc = __shfl_sync(0xffffffffu, my_pivot_c, src);
     uint32_t scl = __shfl_sync(0xffffffffu, best_cl, src);
+    if (pl != kNone && !(sah_fits(depth + 1u, scl, max_depth) && sah_fits(depth + 1u, len - scl, max_depth))) pl = kNone;  // depth bound: halve
     bool mine;
     if (pl == kNone) {
       scl = len >> 1;
@@ -466,7 +482,7 @@ k_sah_small(uint32_t n_small, const SahTask* __restrict__ small, uint32_t* __res
       mine = mc < pc || (mc == pc && lane <= pl);
     }
     const uint32_t leftmask = __ballot_sync(0xffffffffu, need && mine);
-    uint32_t newpos = lane, nlo = seg_lo, nhi = seg_hi, npar = par, nside = side;
+    uint32_t newpos = lane, nlo = seg_lo, nhi = seg_hi, npar = par, nside = side, ndepth = depth;
     if (need) {
       const uint32_t below = leftmask & ((1u << lane) - 1u) & ~((1u << seg_lo) - 1u);
       const uint32_t rank_left = (uint32_t)__popc(below);
@@ -485,6 +501,7 @@ k_sah_small(uint32_t n_small, const SahTask* __restrict__ small, uint32_t* __res
         link_child(nodes, par, side, id);
       }
       npar = id;
+      ndepth = depth + 1u;
       if (mine) { nhi = seg_lo + scl; nside = 0u; } else { nlo = seg_lo + scl; nside = 1u; }
     }
     root_gap = __shfl_sync(0xffffffffu, root_gap, 0);  // (root task: one segment at its first split, lane 0 is a member)
@@ -499,6 +516,7 @@ k_sah_small(uint32_t n_small, const SahTask* __restrict__ small, uint32_t* __res
     s[11 * 32 + newpos] = nhi;
     s[12 * 32 + newpos] = npar;
     s[13 * 32 + newpos] = nside;
+    s[14 * 32 + newpos] = ndepth;
     const uint32_t was_need = __ballot_sync(0xffffffffu, need);
     __syncwarp();
     p = s[0 * 32 + lane];
@@ -510,6 +528,7 @@ k_sah_small(uint32_t n_small, const SahTask* __restrict__ small, uint32_t* __res
     seg_hi = s[11 * 32 + lane];
     par = s[12 * 32 + lane];
     side = s[13 * 32 + lane];
+    depth = s[14 * 32 + lane];
     __syncwarp();
     // an item whose segment has just become a single position is a leaf (a segment is split as a whole, so the lanes of
     // a segment that needed a split are exactly the lanes that hold its items afterwards)
@@ -570,6 +589,13 @@ int32_t build_sah(Ctx* c, const SahBuildInputs& in, const uint32_t** order_out) 
          &tasks_b = c->sah_scratch[4], &bins = c->sah_scratch[5], &splits = c->sah_scratch[6], &child_tasks = c->sah_scratch[7],
          &n_large = c->sah_scratch[8], &small = c->sah_scratch[9], &counters = c->sah_scratch[10], &block_sum = c->sah_scratch[11];
 
+  // depth bound (test hook: PTB_SAH_MAX_DEPTH lowers it, never below what halving alone needs)
+  uint32_t max_depth = kSahMaxDepth;
+  if (const char* e = getenv("PTB_SAH_MAX_DEPTH")) {
+    const int v = atoi(e);
+    if (v > 0 && (uint32_t)v < kSahMaxDepth) max_depth = (uint32_t)v;
+  }
+  if (max_depth < sah_ceil_log2(n)) max_depth = sah_ceil_log2(n);
   const int T = 256;
   const uint32_t gn = (n + T - 1) / T;
   uint32_t* cnt = counters.as<uint32_t>();
@@ -596,7 +622,7 @@ int32_t build_sah(Ctx* c, const SahBuildInputs& in, const uint32_t** order_out) 
     k_sah_clear<<<(n_tasks * kTaskBinWords + T - 1) / T, T, 0, st>>>(bins.as<uint32_t>(), n_tasks);
     k_sah_bin<<<gn, T, 0, st>>>(n, order, stask, cur, in.bmin, in.bmax, bins.as<uint32_t>());
     k_sah_eval<<<(n_tasks + 127) / 128, 128, 0, st>>>(n_tasks, cur, bins.as<uint32_t>(), splits.as<SahSplit>(), child_tasks.as<SahTask>(),
-                                                      n_large.as<uint32_t>(), in.nodes, in.leaf_parent, small.as<SahTask>(), cnt);
+                                                      n_large.as<uint32_t>(), in.nodes, in.leaf_parent, small.as<SahTask>(), cnt, max_depth);
     k_sah_task_scan<<<1, 1024, 0, st>>>(n_large.as<uint32_t>(), n_tasks, cnt);
     k_sah_emit<<<(n_tasks + 127) / 128, 128, 0, st>>>(n_tasks, n_large.as<uint32_t>(), child_tasks.as<SahTask>(), splits.as<SahSplit>(), nxt);
     k_sah_flag<<<gn, T, 0, st>>>(n, order, stask, splits.as<SahSplit>(), in.bmin, in.bmax, prefix.as<uint32_t>());
@@ -618,7 +644,7 @@ int32_t build_sah(Ctx* c, const SahBuildInputs& in, const uint32_t** order_out) 
   }
   if (n_small) {
     k_sah_small<<<(n_small + kSmallWarps - 1) / kSmallWarps, 32 * kSmallWarps, 0, st>>>(n_small, small.as<SahTask>(), order, in.bmin, in.bmax,
-                                                                                        in.nodes, in.leaf_parent, cnt);
+                                                                                        in.nodes, in.leaf_parent, cnt, max_depth);
     c->stats.kernel_launches += 1;
   }
   k_sah_finish<<<gn, T, 0, st>>>(n, in.n_spheres, order, in.leaf_parent, in.nodes);

@@ -82,7 +82,7 @@ for nb in (int(x) for x in os.environ.get("SAH_BINS", "8,16").split(",") if x):
     orc.lbvh_build()
     t0 = time.time()
     st = orc.lbvh_sah(nb)
-    report(f"SAH {nb} bins (levels {st[0]}, tasks <= {st[1]}, small {st[2]}, fallbacks {st[3]}; {time.time() - t0:.1f}s)")
+    report(f"SAH {nb} bins (levels {st[0]}, tasks <= {st[1]}, small {st[2]}, halvings {st[3]}, deepest leaf {st[4]}, depth-limited {st[5]}; {time.time() - t0:.1f}s)")
 for extra in (0.0, 1.0, 2.0):
     if os.environ.get("SNAP", "1") == "0":
         break

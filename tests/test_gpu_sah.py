@@ -46,11 +46,11 @@ def check_tree(nodes, prims, n):
         assert np.array_equal(nodes[mn][m], np.minimum(c["lmin"], c["rmin"])) and np.array_equal(nodes[mx][m], np.maximum(c["lmax"], c["rmax"]))
 
 
-def compare_with_definition(ptb, orc, ctx, scene):
+def compare_with_definition(ptb, orc, ctx, scene, max_depth=60):
     commit_sah(ptb, ctx, scene)
     _, gp, gn = ctx.bvh_export()
     o = orc.OracleScene(scene, split_type=-1)
-    o.lbvh_sah()
+    o.lbvh_sah(8, max_depth)
     _, op, on = o.lbvh_export()
     assert np.array_equal(gp, op), "primitive order differs"
     assert len(gn) == len(on)
@@ -106,6 +106,31 @@ def test_sah_identical_centroids(ptb, orc, sah_ctx, rtweekend1):
     centres = np.repeat(np.array([[0, 1, 0], [1, 1, 0], [0, 2, 0], [0, 1, 0.5], [3, 3, 3]], np.float32), 1000, axis=0)
     compare_with_definition(ptb, orc, sah_ctx, spheres_scene(ptb, rtweekend1, centres, np.tile(np.linspace(0.01, 0.5, 1000, dtype=np.float32), 5)))
     compare_with_definition(ptb, orc, sah_ctx, spheres_scene(ptb, rtweekend1, np.zeros((700, 3)), np.linspace(0.1, 2.0, 700)))
+
+
+@pytest.mark.parametrize("bound", [15, 14])
+def test_sah_depth_bound(ptb, orc, sah_ctx, bound, monkeypatch):
+    """The traversal stacks hold 64 entries, so no leaf may lie deeper than 60 levels: a split that would leave no room to
+    finish by halving is replaced by the halving split. PTB_SAH_MAX_DEPTH lowers the bound to exercise the rule (the C3 mesh
+    is 17 levels deep without it); device tree == CPU definition, hits unchanged."""
+    s = ptb.meshgen.c3_scene(0.1)
+    monkeypatch.setenv("PTB_SAH_MAX_DEPTH", str(bound))
+    compare_with_definition(ptb, orc, sah_ctx, s, bound)
+    monkeypatch.delenv("PTB_SAH_MAX_DEPTH")
+    rays = random_rays(ptb, 100_000, 53, centre=(0, 4, 1), radius=5.0)
+    g = sah_ctx.closest_hit(rays)
+    h, _, _ = orc.OracleScene(s, split_type=-1).lbvh_closest_hit(rays)
+    assert np.array_equal(g["prim"], h["prim"]) and np.array_equal(g["t"].view(np.uint32), h["t"].view(np.uint32))
+    _, _, gn = sah_ctx.bvh_export()
+    depth = np.zeros(len(gn), np.int64)                      # parents have smaller depth: walk down level by level
+    frontier = np.array([0])
+    d = 0
+    while len(frontier):
+        depth[frontier] = d
+        ch = np.concatenate([gn["left"][frontier], gn["right"][frontier]])
+        frontier = ch[ch < LEAF]
+        d += 1
+    assert depth.max() + 1 <= bound
 
 
 @pytest.mark.parametrize("which", ["rtweekend1", "overshadowed", "c3"])

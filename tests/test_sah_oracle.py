@@ -27,8 +27,8 @@ def test_sah_definition_on_the_c3_mesh(ptb, orc):
     rays = random_rays(ptb, 50_000, 31, centre=(0, 4, 1), radius=5.0)
     o = orc.OracleScene(s, split_type=-1)
     h0, v0, t0 = o.lbvh_closest_hit(rays)
-    levels, max_tasks, small, fallbacks = o.lbvh_sah()
-    assert levels > 5 and max_tasks > 10 and small > 100 and fallbacks == 0
+    levels, max_tasks, small, fallbacks, max_depth, limited = o.lbvh_sah()
+    assert levels > 5 and max_tasks > 10 and small > 100 and fallbacks == 0 and max_depth <= 60 and limited == 0
     _, prims, nodes = o.lbvh_export()
     _check_tree(nodes, prims, s.n_primitives)
     h1, v1, t1 = o.lbvh_closest_hit(rays)
@@ -57,3 +57,20 @@ def test_sah_definition_small_and_degenerate(ptb, orc, rtweekend1, overshadowed)
         _, prims, nodes = o.lbvh_export()
         _check_tree(nodes, prims, n)
         assert st[3] > 0 or n <= 3
+
+
+def test_sah_definition_depth_bound(ptb, orc):
+    """The traversal stacks hold 64 entries: a split that would leave no room to finish by halving is replaced by the
+    halving split. Lowering the bound (the test hook) exercises the rule; the tree stays valid and no leaf lies deeper."""
+    s = ptb.meshgen.c3_scene(0.1)
+    rays = random_rays(ptb, 20_000, 33, centre=(0, 4, 1), radius=5.0)
+    o = orc.OracleScene(s, split_type=-1)
+    h0, _, _ = o.lbvh_closest_hit(rays)
+    for bound in (15, 14):
+        st = o.lbvh_sah(8, bound)
+        assert st[4] <= bound and st[5] > 0, st
+        _, prims, nodes = o.lbvh_export()
+        _check_tree(nodes, prims, s.n_primitives)
+        h1, _, _ = o.lbvh_closest_hit(rays)
+        assert np.array_equal(h0["prim"], h1["prim"]) and np.array_equal(h0["t"].view(np.uint32), h1["t"].view(np.uint32))
+        o.lbvh_build()

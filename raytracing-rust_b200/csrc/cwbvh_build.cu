@@ -207,6 +207,11 @@ __global__ void __launch_bounds__(kScanBlock) k_scan_add(uint32_t* __restrict__ 
   for (int k = 0; k < kScanItems; ++k)
     if (base + k < n) data[base + k] += add;
 }
+// the middle step alone: exclusive scan of n_blocks <= 4096 block totals in place (the caller scanned its blocks itself)
+void scan_block_sums(Ctx* c, uint32_t* block_sum, uint32_t n_blocks, uint32_t* total_out) {
+  k_scan_sums<<<1, kScanBlock, 0, c->stream>>>(block_sum, n_blocks, total_out);
+  c->stats.kernel_launches += 1;
+}
 int32_t exclusive_scan(Ctx* c, uint32_t* data, uint32_t n, uint32_t* block_sum, uint32_t* total_out) {
   const uint32_t n_blocks = (n + kScanTile - 1) / kScanTile;
   if (n_blocks > (uint32_t)kScanTile) return set_error(c, PTB_ERR_INVALID, "scan of %u elements needs a third level", n);

@@ -39,7 +39,8 @@ __device__ __forceinline__ uint32_t quantise10(float c, float cmin, float ext) {
 }
 
 // ------------------------------------------------------------------------------------------ K2
-// bounds[0..2] = flipped min of centroids, bounds[3..5] = flipped max
+// bounds[0..2] = flipped min of centroids, bounds[3..5] = flipped max; bounds[6..8] / [9..11] = the same of the boxes
+// themselves (the root box of the SAH builder)
 __global__ void k_prim_bounds(const ptb_sphere* __restrict__ spheres, uint32_t n_spheres,
                               const ptb_triangle* __restrict__ tris, uint32_t n_tris, float4* __restrict__ bmin,
                               float4* __restrict__ bmax, uint32_t* __restrict__ bounds) {
@@ -47,6 +48,7 @@ __global__ void k_prim_bounds(const ptb_sphere* __restrict__ spheres, uint32_t n
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const float inf = __int_as_float(0x7f800000);
   v3 cmin = mk(inf, inf, inf), cmax = mk(-inf, -inf, -inf);
+  uint32_t bx[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
   if (i < n) {
     v3 mn, mx;
     if (i < n_spheres) {
@@ -66,7 +68,13 @@ __global__ void k_prim_bounds(const ptb_sphere* __restrict__ spheres, uint32_t n
     const v3 c = 0.5f * (mn + mx);
     cmin = c;
     cmax = c;
+    bx[0] = float_flip(mn.x); bx[1] = float_flip(mn.y); bx[2] = float_flip(mn.z);
+    bx[3] = float_flip(mx.x); bx[4] = float_flip(mx.y); bx[5] = float_flip(mx.z);
   }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) bx[k] = __reduce_min_sync(0xffffffffu, bx[k]);
+#pragma unroll
+  for (int k = 3; k < 6; ++k) bx[k] = __reduce_max_sync(0xffffffffu, bx[k]);
   // warp reduce then one atomic per warp per component
   for (int off = 16; off > 0; off >>= 1) {
     cmin.x = fminf(cmin.x, __shfl_xor_sync(0xffffffffu, cmin.x, off));
@@ -76,13 +84,23 @@ __global__ void k_prim_bounds(const ptb_sphere* __restrict__ spheres, uint32_t n
     cmax.y = fmaxf(cmax.y, __shfl_xor_sync(0xffffffffu, cmax.y, off));
     cmax.z = fmaxf(cmax.z, __shfl_xor_sync(0xffffffffu, cmax.z, off));
   }
-  if ((threadIdx.x & 31) == 0 && cmin.x <= cmax.x) {
-    atomicMin(bounds + 0, float_flip(cmin.x));
-    atomicMin(bounds + 1, float_flip(cmin.y));
-    atomicMin(bounds + 2, float_flip(cmin.z));
-    atomicMax(bounds + 3, float_flip(cmax.x));
-    atomicMax(bounds + 4, float_flip(cmax.y));
-    atomicMax(bounds + 5, float_flip(cmax.z));
+  // block reduce (12 words x warps), then ONE atomic per word per block: at 10 M primitives the per-warp atomics on twelve
+  // addresses were a quarter of the kernel. Warps without a primitive contribute the identities (+inf / -inf).
+  __shared__ uint32_t red[12][32];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31u) >> 5;
+  if (lane == 0u) {
+    red[0][warp] = float_flip(cmin.x); red[1][warp] = float_flip(cmin.y); red[2][warp] = float_flip(cmin.z);
+    red[3][warp] = float_flip(cmax.x); red[4][warp] = float_flip(cmax.y); red[5][warp] = float_flip(cmax.z);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) red[6 + k][warp] = bx[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 12u) {
+    const bool is_min = threadIdx.x < 3u || (threadIdx.x >= 6u && threadIdx.x < 9u);
+    uint32_t v = red[threadIdx.x][0];
+    for (uint32_t w = 1; w < n_warps; ++w) v = is_min ? min(v, red[threadIdx.x][w]) : max(v, red[threadIdx.x][w]);
+    if (is_min) atomicMin(bounds + threadIdx.x, v);
+    else atomicMax(bounds + threadIdx.x, v);
   }
 }
 
@@ -629,7 +647,7 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
   const uint32_t n32 = (uint32_t)n, ns32 = (uint32_t)ns, nt32 = (uint32_t)nt;
   PTB_CUDA_TRY(c, bmin.reserve(n * 16));
   PTB_CUDA_TRY(c, bmax.reserve(n * 16));
-  PTB_CUDA_TRY(c, bounds.reserve(6 * 4));
+  PTB_CUDA_TRY(c, bounds.reserve(12 * 4));
   PTB_CUDA_TRY(c, keys_a.reserve(n * 4));
   PTB_CUDA_TRY(c, keys_b.reserve(n * 4));
   PTB_CUDA_TRY(c, vals_a.reserve(n * 4));
@@ -690,7 +708,7 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
                                      d_light_prims.as<uint32_t>());
   c->stats.kernel_launches += 1;
   {
-    const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+    const uint32_t init[12] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
     PTB_CUDA_TRY(c, cudaMemcpyAsync(bounds.p, init, sizeof init, cudaMemcpyHostToDevice, st));
   }
   k_prim_bounds<<<gn, T, 0, st>>>(raw_spheres.as<ptb_sphere>(), ns32, raw_tris.as<ptb_triangle>(), nt32, bmin.as<float4>(),
@@ -707,7 +725,7 @@ int32_t build_scene(Ctx* c, uint32_t build_flags) {
   } else {
     PTB_CUDA_TRY(c, cudaMemsetAsync(flags.p, 0, c->n_nodes * 4, st));
     if (sah) {
-      SahBuildInputs si{bmin.as<float4>(), bmax.as<float4>(), va, vb, c->d_nodes.as<BvhNode>(), leaf_parent.as<uint32_t>(), n32, ns32};
+      SahBuildInputs si{bmin.as<float4>(), bmax.as<float4>(), bounds.as<uint32_t>() + 6, va, vb, c->d_nodes.as<BvhNode>(), leaf_parent.as<uint32_t>(), n32, ns32};
       const uint32_t* order = nullptr;
       const int32_t rcs = build_sah(c, si, &order);
       if (rcs != PTB_OK) return rcs;

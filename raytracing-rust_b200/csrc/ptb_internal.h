@@ -170,9 +170,11 @@ struct CwBuildInputs {
 int32_t build_wide(Ctx* c, const CwBuildInputs& in, uint32_t* final_prim);
 // in-place exclusive prefix sum of n <= 2^24 words (block_sum: 4096 words of scratch; *total_out receives the sum)
 int32_t exclusive_scan(Ctx* c, uint32_t* data, uint32_t n, uint32_t* block_sum, uint32_t* total_out);
+void scan_block_sums(Ctx* c, uint32_t* block_sum, uint32_t n_blocks, uint32_t* total_out);
 // sah_build.cu — top-down SAH hierarchy in the LBVH's node format (links in nodes[].n3 + leaf_parent; k_refit fills the boxes)
 struct SahBuildInputs {
   const float4 *bmin, *bmax;      // box of every primitive (original order)
+  const uint32_t* box6;           // union of those boxes: min xyz, max xyz as order-preserving uints (k_prim_bounds)
   uint32_t *order_a, *order_b;    // order_a: Morton position -> original primitive id (the starting order); order_b: scratch
   BvhNode* nodes;                 // n - 1 nodes
   uint32_t* leaf_parent;          // n words

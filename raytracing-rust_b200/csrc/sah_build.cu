@@ -5,13 +5,13 @@
 // bit for bit (tests/test_gpu_sah.py). Everything here is deterministic: bins are min / max / integer counts (order
 // independent atomics), partitions are stable (prefix sums), nodes are named after the gap they split at.
 //
-//   S1  k_sah_root        root task: all positions of the Morton order, box = union of the primitive boxes
+//   S1  k_sah_root        root task: all positions of the Morton order, box = union of the primitive boxes (k_prim_bounds)
 //   per level of LARGE tasks (more than 32 positions), tasks in position order:
 //   S2  k_sah_clear / k_sah_bin    8 bins on each axis of the task's box: union of boxes + count (warp-aggregated atomics)
 //   S3  k_sah_eval        one thread per task: first minimum of the cost over axes x planes; names and links the node; the
 //                         children become leaves, SMALL tasks (appended to a list) or next-level large tasks
 //   S4  k_sah_task_scan / k_sah_emit   next level's task list, in position order
-//   S5  k_sah_flag + exclusive scan + k_sah_scatter   stable partition of every task's positions, all tasks at once
+//   S5  k_sah_flag_scan + scan_block_sums + k_sah_scatter   stable partition of every task's positions, all tasks at once
 //   S6  k_sah_small       one WARP per small task: exact sweep over every (member, axis) candidate, the whole subtree in
 //                         registers / shuffles, a stable partition per split through shared memory
 //   S7  k_sah_finish      sphere bits of the leaf references
@@ -88,26 +88,6 @@ __device__ __forceinline__ void link_child(BvhNode* nodes, uint32_t parent, uint
 }
 
 // ------------------------------------------------------------------------------------------ S1
-__global__ void __launch_bounds__(256) k_sah_box(const float4* __restrict__ bmin, const float4* __restrict__ bmax, uint32_t n,
-                                                  uint32_t* __restrict__ box6) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t v[6] = {kFlipPosInf, kFlipPosInf, kFlipPosInf, kFlipNegInf, kFlipNegInf, kFlipNegInf};
-  if (i < n) {
-    const float4 a = bmin[i], b = bmax[i];
-    v[0] = sah_flip(a.x); v[1] = sah_flip(a.y); v[2] = sah_flip(a.z);
-    v[3] = sah_flip(b.x); v[4] = sah_flip(b.y); v[5] = sah_flip(b.z);
-  }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) v[k] = __reduce_min_sync(0xffffffffu, v[k]);
-#pragma unroll
-  for (int k = 3; k < 6; ++k) v[k] = __reduce_max_sync(0xffffffffu, v[k]);
-  if ((threadIdx.x & 31u) == 0u) {
-#pragma unroll
-    for (int k = 0; k < 3; ++k) atomicMin(box6 + k, v[k]);
-#pragma unroll
-    for (int k = 3; k < 6; ++k) atomicMax(box6 + k, v[k]);
-  }
-}
 __global__ void k_sah_root(const uint32_t* __restrict__ box6, uint32_t n, SahTask* __restrict__ task, uint32_t* __restrict__ counters) {
   SahTask t;
   t.lo = 0u; t.hi = n; t.parent = kNone; t.side = 0u;
@@ -131,15 +111,40 @@ __global__ void __launch_bounds__(256) k_sah_clear(uint32_t* __restrict__ bins, 
   const uint32_t w = i % (uint32_t)kBinWords;
   bins[i] = w < 3u ? kFlipPosInf : (w < 6u ? kFlipNegInf : 0u);
 }
+// One thread per position. A block whose positions all belong to ONE task (the upper levels: tasks of thousands of
+// positions) folds its bins in shared memory and sends 168 atomics at most; other warps aggregate per (axis, bin) group when
+// the warp's positions share a task, and fall back to one set of atomics per lane otherwise.
+template <class Atom>
+__device__ __forceinline__ void bin_warp(bool active, const int* bi, const uint32_t* v, uint32_t lane, Atom atom) {
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    for (int b = 0; b < kSahBins; ++b) {
+      const bool in = active && bi[a] == b;
+      const uint32_t m = __ballot_sync(0xffffffffu, in);
+      if (!m) continue;
+      uint32_t r[6];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) r[k] = __reduce_min_sync(0xffffffffu, in ? v[k] : kFlipPosInf);
+#pragma unroll
+      for (int k = 3; k < 6; ++k) r[k] = __reduce_max_sync(0xffffffffu, in ? v[k] : kFlipNegInf);
+      if (lane == (uint32_t)(__ffs(m) - 1)) atom((a * kSahBins + b) * kBinWords, r, (uint32_t)__popc(m));
+    }
+  }
+}
 __global__ void __launch_bounds__(256)
 k_sah_bin(uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ slot_task, const SahTask* __restrict__ tasks,
           const float4* __restrict__ bmin, const float4* __restrict__ bmax, uint32_t* __restrict__ bins) {
+  __shared__ uint32_t sb[kTaskBinWords];
+  __shared__ uint32_t s_t0;
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t t = slot < n ? slot_task[slot] : kNone;
   const bool active = t != kNone;
-  const uint32_t any = __ballot_sync(0xffffffffu, active);
-  if (!any) return;
+  if (threadIdx.x == 0u) s_t0 = t;
+  if (threadIdx.x < (uint32_t)kTaskBinWords) {
+    const uint32_t w = threadIdx.x % (uint32_t)kBinWords;
+    sb[threadIdx.x] = w < 3u ? kFlipPosInf : (w < 6u ? kFlipNegInf : 0u);
+  }
   uint32_t v[6] = {kFlipPosInf, kFlipPosInf, kFlipPosInf, kFlipNegInf, kFlipNegInf, kFlipNegInf};
   int bi[3] = {0, 0, 0};
   if (active) {
@@ -156,31 +161,38 @@ k_sah_bin(uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __rest
       if (axis_scale(mn, tk.mx[k], scale)) bi[k] = bin_of(0.5f * (lo3[k] + hi3[k]), mn, scale);
     }
   }
-  const uint32_t t0 = __shfl_sync(0xffffffffu, t, __ffs(any) - 1);
-  if (__all_sync(0xffffffffu, !active || t == t0)) {
-    // the warp's positions belong to one task: one set of atomics per (axis, bin) group
-    uint32_t* tb = bins + (size_t)t0 * kTaskBinWords;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      for (int b = 0; b < kSahBins; ++b) {
-        const bool in = active && bi[a] == b;
-        const uint32_t m = __ballot_sync(0xffffffffu, in);
-        if (!m) continue;
-        uint32_t r[6];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) r[k] = __reduce_min_sync(0xffffffffu, in ? v[k] : kFlipPosInf);
-#pragma unroll
-        for (int k = 3; k < 6; ++k) r[k] = __reduce_max_sync(0xffffffffu, in ? v[k] : kFlipNegInf);
-        if (lane == (uint32_t)(__ffs(m) - 1)) {
-          uint32_t* w = tb + (a * kSahBins + b) * kBinWords;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) atomicMin(w + k, r[k]);
-#pragma unroll
-          for (int k = 3; k < 6; ++k) atomicMax(w + k, r[k]);
-          atomicAdd(w + 6, (uint32_t)__popc(m));
-        }
+  __syncthreads();
+  const uint32_t bt = s_t0;
+  const bool block_uniform = __syncthreads_and(!active || t == bt) != 0;
+  if (block_uniform) {
+    if (bt == kNone) return;  // nothing active in this block
+    bin_warp(active, bi, v, lane, [&](int w0, const uint32_t* r, uint32_t c) {
+      for (int k = 0; k < 3; ++k) atomicMin(sb + w0 + k, r[k]);
+      for (int k = 3; k < 6; ++k) atomicMax(sb + w0 + k, r[k]);
+      atomicAdd(sb + w0 + 6, c);
+    });
+    __syncthreads();
+    if (threadIdx.x < (uint32_t)kTaskBinWords) {
+      const uint32_t w = threadIdx.x % (uint32_t)kBinWords;
+      if (sb[threadIdx.x - w + 6u] != 0u) {
+        uint32_t* g = bins + (size_t)bt * kTaskBinWords + threadIdx.x;
+        if (w < 3u) atomicMin(g, sb[threadIdx.x]);
+        else if (w < 6u) atomicMax(g, sb[threadIdx.x]);
+        else atomicAdd(g, sb[threadIdx.x]);
       }
     }
+    return;
+  }
+  const uint32_t any = __ballot_sync(0xffffffffu, active);
+  if (!any) return;
+  const uint32_t t0 = __shfl_sync(0xffffffffu, t, __ffs(any) - 1);
+  if (__all_sync(0xffffffffu, !active || t == t0)) {
+    uint32_t* tb = bins + (size_t)t0 * kTaskBinWords;
+    bin_warp(active, bi, v, lane, [&](int w0, const uint32_t* r, uint32_t c) {
+      for (int k = 0; k < 3; ++k) atomicMin(tb + w0 + k, r[k]);
+      for (int k = 3; k < 6; ++k) atomicMax(tb + w0 + k, r[k]);
+      atomicAdd(tb + w0 + 6, c);
+    });
   } else if (active) {
     uint32_t* tb = bins + (size_t)t * kTaskBinWords;
 #pragma unroll
@@ -361,19 +373,60 @@ __device__ __forceinline__ bool goes_left(const SahSplit& sp, uint32_t slot, uin
   const float lo = sp.axis == 0 ? a.x : (sp.axis == 1 ? a.y : a.z), hi = sp.axis == 0 ? b.x : (sp.axis == 1 ? b.y : b.z);
   return bin_of(0.5f * (lo + hi), sp.mn, sp.scale) <= sp.bin;
 }
-__global__ void __launch_bounds__(256)
-k_sah_flag(uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ slot_task, const SahSplit* __restrict__ splits,
-           const float4* __restrict__ bmin, const float4* __restrict__ bmax, uint32_t* __restrict__ flag) {
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= n) return;
-  const uint32_t t = slot_task[slot];
-  flag[slot] = t != kNone && goes_left(splits[t], slot, order[slot], bmin, bmax) ? 1u : 0u;
+// left flags and their exclusive prefix sums in one pass: 4096 positions per block, prefix[] = the sum inside the block,
+// block_sum[] = the block's total (scanned by scan_block_sums; k_sah_scatter adds it back)
+constexpr int kFlagBlock = 1024, kFlagItems = 4, kFlagTile = kFlagBlock * kFlagItems;
+__global__ void __launch_bounds__(kFlagBlock)
+k_sah_flag_scan(uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ slot_task, const SahSplit* __restrict__ splits,
+                const float4* __restrict__ bmin, const float4* __restrict__ bmax, uint32_t* __restrict__ prefix, uint32_t* __restrict__ block_sum) {
+  __shared__ uint32_t warp_sum[33];
+  const uint32_t base = blockIdx.x * kFlagTile + threadIdx.x * kFlagItems;
+  uint32_t f[kFlagItems], mine = 0u;
+#pragma unroll
+  for (int k = 0; k < kFlagItems; ++k) {
+    const uint32_t slot = base + k;
+    f[k] = 0u;
+    if (slot < n) {
+      const uint32_t t = slot_task[slot];
+      if (t != kNone && goes_left(splits[t], slot, order[slot], bmin, bmax)) f[k] = 1u;
+    }
+    mine += f[k];
+  }
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += u;
+  }
+  if (lane == 31u) warp_sum[warp] = inc;
+  __syncthreads();
+  if (warp == 0u) {
+    const uint32_t v = warp_sum[lane];
+    uint32_t winc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= (uint32_t)o) winc += u;
+    }
+    warp_sum[lane] = winc - v;
+    if (lane == 31u) warp_sum[32] = winc;
+  }
+  __syncthreads();
+  uint32_t run = warp_sum[warp] + inc - mine;
+#pragma unroll
+  for (int k = 0; k < kFlagItems; ++k) {
+    if (base + k < n) prefix[base + k] = run;
+    run += f[k];
+  }
+  if (threadIdx.x == 0u) block_sum[blockIdx.x] = warp_sum[32];
 }
-// prefix[slot] = positions going left before `slot` (whole array): the rank inside a task is the difference to its start
+// global prefix of a position = positions going left before it (whole array): the rank inside a task is the difference to
+// the prefix of the task's first position
 __global__ void __launch_bounds__(256)
 k_sah_scatter(uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __restrict__ slot_task, const SahSplit* __restrict__ splits,
               const float4* __restrict__ bmin, const float4* __restrict__ bmax, const uint32_t* __restrict__ prefix,
-              uint32_t* __restrict__ order_out, uint32_t* __restrict__ slot_task_out) {
+              const uint32_t* __restrict__ block_sum, uint32_t* __restrict__ order_out, uint32_t* __restrict__ slot_task_out) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n) return;
   const uint32_t t = slot_task[slot];
@@ -385,7 +438,7 @@ k_sah_scatter(uint32_t n, const uint32_t* __restrict__ order, const uint32_t* __
   }
   const SahSplit sp = splits[t];
   const bool left = goes_left(sp, slot, p, bmin, bmax);
-  const uint32_t rank_left = prefix[slot] - prefix[sp.lo];
+  const uint32_t rank_left = (prefix[slot] + block_sum[slot / kFlagTile]) - (prefix[sp.lo] + block_sum[sp.lo / kFlagTile]);
   const uint32_t dest = left ? sp.lo + rank_left : sp.lo + sp.cl + ((slot - sp.lo) - rank_left);
   order_out[dest] = p;
   slot_task_out[dest] = sp.child[left ? 0 : 1];
@@ -427,14 +480,17 @@ k_sah_small(uint32_t n_small, const SahTask* __restrict__ small, uint32_t* __res
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int k = 0; k < 3; ++k) { Lmn[a][k] = Rmn[a][k] = inf; Lmx[a][k] = Rmx[a][k] = -inf; }
-    for (uint32_t j = 0; j < m; ++j) {
+    // every lane walks the members of ITS OWN segment (source lane seg_lo + i): the trip count is the longest segment of the
+    // warp, which halves from level to level, not the size of the task
+    const uint32_t max_len = __reduce_max_sync(0xffffffffu, need ? len : 0u);
+    for (uint32_t i = 0; i < max_len; ++i) {
+      const uint32_t j = min(seg_lo + i, 31u);
       float jb[6], jc[3];
 #pragma unroll
       for (int k = 0; k < 6; ++k) jb[k] = __shfl_sync(0xffffffffu, bx[k], j);
 #pragma unroll
       for (int k = 0; k < 3; ++k) jc[k] = __shfl_sync(0xffffffffu, c[k], j);
-      const uint32_t jlo = __shfl_sync(0xffffffffu, seg_lo, j);
-      const bool same = need && jlo == seg_lo;
+      const bool same = need && i < len;
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         const bool left = same && (jc[a] < c[a] || (jc[a] == c[a] && j <= lane));
@@ -463,10 +519,10 @@ k_sah_small(uint32_t n_small, const SahTask* __restrict__ small, uint32_t* __res
     // the segment's winner: smallest (cost, lane)
     float seg_best = inf;
     uint32_t pl = kNone;
-    for (uint32_t j = 0; j < m; ++j) {
+    for (uint32_t i = 0; i < max_len; ++i) {
+      const uint32_t j = min(seg_lo + i, 31u);
       const float k = __shfl_sync(0xffffffffu, best, j);
-      const uint32_t jlo = __shfl_sync(0xffffffffu, seg_lo, j);
-      if (need && jlo == seg_lo && k < seg_best) { seg_best = k; pl = j; }
+      if (need && i < len && k < seg_best) { seg_best = k; pl = j; }
     }
     const uint32_t src = pl == kNone ? lane : pl;
     const int pa = __shfl_sync(0xffffffffu, best_a, src);
@@ -599,16 +655,11 @@ int32_t build_sah(Ctx* c, const SahBuildInputs& in, const uint32_t** order_out) 
   const int T = 256;
   const uint32_t gn = (n + T - 1) / T;
   uint32_t* cnt = counters.as<uint32_t>();
-  uint32_t* box6 = cnt + 8;
-  {
-    const uint32_t init[6] = {kFlipPosInf, kFlipPosInf, kFlipPosInf, kFlipNegInf, kFlipNegInf, kFlipNegInf};
-    PTB_CUDA_TRY(c, cudaMemcpyAsync(box6, init, sizeof init, cudaMemcpyHostToDevice, st));
-  }
-  k_sah_box<<<gn, T, 0, st>>>(in.bmin, in.bmax, n, box6);
+  const uint32_t* box6 = in.box6;  // union of the primitive boxes, left by k_prim_bounds
   SahTask *cur = tasks_a.as<SahTask>(), *nxt = tasks_b.as<SahTask>();
   const bool root_small = n <= kSahSmall;
   k_sah_root<<<1, 1, 0, st>>>(box6, n, root_small ? small.as<SahTask>() : cur, cnt);
-  c->stats.kernel_launches += 2;
+  c->stats.kernel_launches += 1;
   uint32_t *order = in.order_a, *order2 = in.order_b;
   uint32_t *stask = slot_task_a.as<uint32_t>(), *stask2 = slot_task_b.as<uint32_t>();
   uint32_t n_tasks = root_small ? 0u : 1u, n_small = root_small ? 1u : 0u;
@@ -625,14 +676,13 @@ int32_t build_sah(Ctx* c, const SahBuildInputs& in, const uint32_t** order_out) 
                                                       n_large.as<uint32_t>(), in.nodes, in.leaf_parent, small.as<SahTask>(), cnt, max_depth);
     k_sah_task_scan<<<1, 1024, 0, st>>>(n_large.as<uint32_t>(), n_tasks, cnt);
     k_sah_emit<<<(n_tasks + 127) / 128, 128, 0, st>>>(n_tasks, n_large.as<uint32_t>(), child_tasks.as<SahTask>(), splits.as<SahSplit>(), nxt);
-    k_sah_flag<<<gn, T, 0, st>>>(n, order, stask, splits.as<SahSplit>(), in.bmin, in.bmax, prefix.as<uint32_t>());
-    c->stats.kernel_launches += 6;
-    {
-      const int32_t rc = exclusive_scan(c, prefix.as<uint32_t>(), n, block_sum.as<uint32_t>(), cnt + 3);
-      if (rc != PTB_OK) return rc;
-    }
-    k_sah_scatter<<<gn, T, 0, st>>>(n, order, stask, splits.as<SahSplit>(), in.bmin, in.bmax, prefix.as<uint32_t>(), order2, stask2);
-    c->stats.kernel_launches += 1;
+    const uint32_t n_tiles = (n + kFlagTile - 1) / kFlagTile;
+    k_sah_flag_scan<<<n_tiles, kFlagBlock, 0, st>>>(n, order, stask, splits.as<SahSplit>(), in.bmin, in.bmax, prefix.as<uint32_t>(),
+                                                    block_sum.as<uint32_t>());
+    scan_block_sums(c, block_sum.as<uint32_t>(), n_tiles, cnt + 3);
+    k_sah_scatter<<<gn, T, 0, st>>>(n, order, stask, splits.as<SahSplit>(), in.bmin, in.bmax, prefix.as<uint32_t>(),
+                                    block_sum.as<uint32_t>(), order2, stask2);
+    c->stats.kernel_launches += 7;
     PTB_CUDA_TRY(c, cudaMemcpyAsync(c->h_sah, cnt, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PTB_CUDA_TRY(c, cudaStreamSynchronize(st));
     n_small = c->h_sah[0];

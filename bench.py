@@ -344,6 +344,7 @@ def run_ours(args):
     build_ms = ctx.stats().build_ms
     n_prims, n_nodes = ctx.bvh_info()
     n_wide, wide_leaf = ctx.bvh_wide_info()
+    tree_label = binary_tree_label(ctx)
     if strong:
         my_off, my_spp = ptb200.shard_samples(S, rank, world)
         step_span = S
@@ -540,7 +541,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": cfg,
             "e2e": e2e, "gpu_launches": int(st.kernel_launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "run": {"spp_this_rank": my_spp, "bvh": (f"compressed 8-wide, {n_wide} nodes x 96 B, leaf groups <= {wide_leaf}" if n_wide
-                                                     else f"binary, {binary_tree_label(ctx)}, {n_nodes} nodes x 64 B"),
+                                                     else f"binary, {tree_label}, {n_nodes} nodes x 64 B"),
                     "bvh_nodes": n_wide or n_nodes, "node_bytes": node_bytes, "bvh_build_ms": build_ms, "rays_reference_style": st.rays_reference,
                     "wall_s": t_wall, "wavefront_iterations": int(st.wavefront_iterations)},
         }
@@ -578,6 +579,7 @@ def run_closest_hit(args, rank, world, local, n_tris, n_rays, cpu=True, steps=No
     ctx.commit()
     n_prims, n_nodes = ctx.bvh_info()
     n_wide, wide_leaf = ctx.bvh_wide_info()
+    tree_label = binary_tree_label(ctx)
     node_bytes = 96.0 if n_wide else 64.0
     ctx_build_ms = ctx.stats().build_ms
     K = steps if steps is not None else args.steps
@@ -674,7 +676,7 @@ def run_closest_hit(args, rank, world, local, n_tris, n_rays, cpu=True, steps=No
                      "limiter": ev.get("limiter")},
         "cpu_baseline": cpu_b,
         "run": {"rays_per_step_per_gpu": batch, "rays_timed": batch * K * world, "bvh_nodes": n_wide or n_nodes, "node_bytes": node_bytes,
-                "bvh": "compressed 8-wide" if n_wide else "binary, " + binary_tree_label(ctx), "build_ms": ctx_build_ms, "hit_fraction": hit_frac,
+                "bvh": "compressed 8-wide" if n_wide else "binary, " + tree_label, "build_ms": ctx_build_ms, "hit_fraction": hit_frac,
                 "ray_stream_max_abs_dev_vs_numpy": stream_err},
     }
 

@@ -416,7 +416,9 @@ k_trace(DevScene sc, PathPool pool, Queues q, WaveCounters* wc, RenderParams rp,
 // and its ray is the camera ray of path first + i, computed here; a warp takes 32 consecutive slots — samples of one pixel
 // (or of one 8 x 4 pixel tile when the call has fewer samples) — and walks the tree once for all of them.
 #ifndef PTB_CAMERA_MIN_BLOCKS
-#define PTB_CAMERA_MIN_BLOCKS 3  // 71 registers; at 4 blocks (64) the slab constants are rematerialised per node: 4252 vs 4344 Mrays/s on C3
+// 4 blocks per SM = 62 registers, no spills. (Before the octant-specialised slab test the kernel needed 71 registers and
+// lost at 4 blocks: 4252 vs 4344 Mrays/s on C3; with it, 3 -> 4 blocks: 4849 -> 4925 at 256 spp, 4475 -> 4570 at 32 spp.)
+#define PTB_CAMERA_MIN_BLOCKS 4
 #endif
 template <bool COUNT>
 __global__ void __launch_bounds__(256, PTB_CAMERA_MIN_BLOCKS)

@@ -39,6 +39,11 @@ pub type ptb_progress_fn = Option<unsafe extern "C" fn(user: *mut c_void, sample
 /// per-pass presentation closure (random_sampler.rs:82-98): single-sample image of a finished pass, 1-based pass number
 pub type ptb_pass_fn = Option<unsafe extern "C" fn(user: *mut c_void, pass_image: *const f32, n_floats: usize, pass_number: u64, rays_shot: u64) -> i32>;
 pub const PTB_PERLIN_TABLE_WORDS: usize = 1024;
+// ptb_scene_commit build flags: which builder / tree (PTB_BUILD_DEFAULT: the device SAH builder, or what PTB_BVH says)
+pub const PTB_BUILD_DEFAULT: u32 = 0;
+pub const PTB_BUILD_BINARY: u32 = 1; // Karras LBVH
+pub const PTB_BUILD_WIDE: u32 = 2;   // LBVH collapsed into the compressed 8-wide tree
+pub const PTB_BUILD_SAH: u32 = 4;    // top-down SAH builder (Bvh::new with Split::Sah, acceleration/mod.rs:58-160)
 
 extern "C" {
     pub fn ptb_abi_version() -> u32;
@@ -55,6 +60,7 @@ extern "C" {
     pub fn ptb_scene_commit(ctx: *mut ptb_ctx, build_flags: u32) -> i32;
     pub fn ptb_bvh_export_quantised(ctx: *mut ptb_ctx, frame: *mut f32, nodes32: *mut c_void) -> i32;
     pub fn ptb_bvh_wide_info(ctx: *mut ptb_ctx, n_nodes: *mut u64, max_leaf: *mut u32) -> i32;
+    pub fn ptb_bvh_builder(ctx: *mut ptb_ctx, builder: *mut u32, sah_levels: *mut u32) -> i32;
     pub fn ptb_bvh_wide_export(ctx: *mut ptb_ctx, nodes96: *mut c_void, slot_prim: *mut u32) -> i32;
     pub fn ptb_closest_hit(ctx: *mut ptb_ctx, rays: *const ptb_ray, n: usize, hits: *mut ptb_hit) -> i32;
     pub fn ptb_render(ctx: *mut ptb_ctx, opts: *const ptb_render_opts, progress: ptb_progress_fn, user: *mut c_void) -> i32;

@@ -163,20 +163,25 @@ int main(int argc, char** argv) {
     destroy_all();
     return 1;
   };
+  // --bvh-type (parameters.rs:35-36, split.rs SplitType): `sah` = the device's SAH builder (or what PTB_BVH says); `middle`
+  // = the Karras LBVH, whose nodes split at the spatial middle of their Morton cell; `equal-counts` has no device builder
+  // and gets the LBVH too. Every tree returns the same hits, so the image does not depend on the choice.
+  const uint32_t build_flags = cli.bvh_type == "sah" ? (uint32_t)PTB_BUILD_DEFAULT : (uint32_t)PTB_BUILD_BINARY;
   {
     std::vector<int32_t> rcs((size_t)cli.gpus, PTB_OK);
     std::vector<std::thread> th;
     for (int g = 0; g < cli.gpus; ++g)
       th.emplace_back([&, g]() {
         int32_t r = ptb_scene_upload(ctxs[(size_t)g], scene);
-        if (r == PTB_OK) r = ptb_scene_commit(ctxs[(size_t)g], PTB_BUILD_DEFAULT);  // Bvh::new (parameters.rs:60)
+        if (r == PTB_OK) r = ptb_scene_commit(ctxs[(size_t)g], build_flags);  // Bvh::new(primitives, sky, cli.bvh_type) (parameters.rs:61)
         rcs[(size_t)g] = r;
       });
     for (auto& t : th) t.join();
     for (int g = 0; g < cli.gpus; ++g)
       if (rcs[(size_t)g] != PTB_OK) return fail("scene upload / bvh build", ctxs[(size_t)g]);
   }
-  if (cli.bvh_type != "sah") log_line("WARN", "frontend", "--bvh-type is ignored by the cuda backend (it builds its own tree)");
+  if (cli.bvh_type == "equal-counts")
+    log_line("WARN", "frontend", "--bvh-type equal-counts: the cuda backend has no equal-counts builder, using its spatial-middle tree (same image)");
 
   // output/src/lib.rs:126-136
   {

@@ -94,3 +94,22 @@ def test_cli_gpus_flag_and_exr_output(ptb, gpu_ctx, root, tmp_path):
     ref = sc.render(ptb.RenderOptions(samples_per_pixel=6, render_method=1, width=96, height=54, seed=9))
     assert np.max(np.abs(img - ref)) < 1e-5
     assert subprocess.run([cli, "-f", scene_path, "--gpus", "0"], capture_output=True).returncode != 0
+
+
+def test_cli_bvh_type(ptb, root, tmp_path):
+    """`-b / --bvh-type` (parameters.rs:35-36): sah = the device SAH builder, middle = the Karras LBVH (spatial-middle splits),
+    equal-counts = the LBVH with a warning. The image does not depend on the tree; an unknown value is a usage error."""
+    cli = os.path.join(root, "raytracing-rust_b200", "ptb200-cli")
+    scene_path = os.path.join(root, "scenes", "overshadowed.ssml")
+    imgs = {}
+    for bvh in ("sah", "middle", "equal-counts"):
+        out = tmp_path / f"img_{bvh}.pfm"
+        r = subprocess.run([cli, "-f", scene_path, "-s", "4", "-x", "64", "-y", "36", "-r", "mis", "-o", str(out), "--seed", "3", "-b", bvh],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert ("no equal-counts builder" in r.stderr) == (bvh == "equal-counts")
+        raw = out.read_bytes()
+        imgs[bvh] = np.frombuffer(raw[raw.index(b"-1.0\n") + 5:], np.float32)
+    # (two renders agree to the f32 summation order of the accumulator's atomic adds, not bit for bit: ptb200.h)
+    assert np.allclose(imgs["sah"], imgs["middle"], rtol=1e-5, atol=1e-5) and np.allclose(imgs["middle"], imgs["equal-counts"], rtol=1e-5, atol=1e-5)
+    assert subprocess.run([cli, "-f", scene_path, "-b", "octree"], capture_output=True).returncode != 0

@@ -658,6 +658,78 @@ struct ShadeOut {
   float4 sh_o, sh_d, sh_c;  // NEE ray: o.xyz|tmax, d.xyz|exclude slot, contribution.rgb|path slot
   v3 fin_L;
 };
+// Next-event estimation of one departing path (integrators/mis.rs:36-43, 95-157): one light or the sky, sampled, its
+// shadow ray and weighted contribution left in `o`. Out of line (PTB_NEE_NOINLINE): its sampling code — sky tables, cone
+// sampling, the light's own hit record, two Philox blocks — then holds registers only while it runs.
+#ifndef PTB_NEE_NOINLINE
+#define PTB_NEE_NOINLINE 0
+#endif
+#if PTB_NEE_NOINLINE
+#define PTB_NEE_ATTR __device__ __noinline__
+#else
+#define PTB_NEE_ATTR PTB_DEV
+#endif
+template <bool FULL>
+PTB_NEE_ATTR void nee_sample(const DevScene& sc, const RenderParams& rp, const Surface& s, v3 wo, v3 T, uint32_t pixel, uint32_t sample,
+                             uint32_t depth, uint32_t slot, ShadeOut& o) {
+  bool& shadow = o.shadow;
+  uint32_t& shadow_is_sky = o.shadow_is_sky;
+  float4 &sh_o = o.sh_o, &sh_d = o.sh_d, &sh_c = o.sh_c;
+    const uint32_t n_l = sc.n_lights;
+    const bool sky_s = (sc.sky_rx | sc.sky_ry) != 0u;
+    if (n_l != 0u || sky_s) {
+      const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_NEE, 0u, rp.k0, rp.k1);
+      bool do_sky;
+      float mult;
+      uint32_t li = 0;
+      if (n_l == 0u) { do_sky = true; mult = 1.0f; }
+      else if (!sky_s) { do_sky = false; mult = 1.0f / (float)n_l; li = rng_below(r.x, n_l); }
+      else { mult = 1.0f / (float)(n_l + 1u); li = rng_below(r.x, n_l + 1u); do_sky = li == n_l; }
+      const v3 so = s.h.point + 0.0001f * s.h.normal;  // mis.rs:106,124
+      v3 l_wi, le;
+      float l_pdf = 0.0f, tmax = __int_as_float(0x7f800000);
+      uint32_t exclude = kNone;
+      bool usable = false;
+      if (do_sky) {
+        const uint4 r2 = philox4x32_10(pixel, sample, (depth << 8) | RNG_NEE, 1u, rp.k0, rp.k1);
+        l_wi = sky_sample(sc, u32_to_unit(r.y), u32_to_unit(r.z), u32_to_unit(r.w), u32_to_unit(r2.x));
+        const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);
+        le = 1.0f * texture_colour<FULL>(sc, sc.sky_tex, l_wi, point);
+        l_pdf = sky_pdf(sc, l_wi) * mult;
+        usable = true;
+        shadow_is_sky = 1u;
+      } else {
+        const uint32_t lref = __ldg(sc.lights + li);
+        l_wi = light_sample_dir(sc, lref, s.h.point, u32_to_unit(r.y), u32_to_unit(r.z));
+        const Ray sray = make_ray_from_raw(so, l_wi);
+        HitRec si;
+        if (prim_hit(sc, sray, lref, si) && si.t > 0.0f) {  // acceleration/mod.rs:231-243
+          const float pdf = light_pdf(sc, lref, s.h.point, l_wi, si.point, si.normal);
+          if (pdf > 0.0f) {
+            const uint32_t lmi = __ldg(sc.slot_mat + (lref & kSlotMask)) & 0x00FFFFFFu;
+            const DevMaterial* lm = sc.materials + lmi;
+            const v3 lpoint = offset_ray(si.point, si.normal, si.error, true);
+            le = __ldg(&lm->param) * texture_colour<FULL>(sc, __ldg(&lm->tex), l_wi, lpoint);
+            l_pdf = pdf * mult;
+            tmax = si.t;
+            exclude = lref & kSlotMask;
+            usable = true;
+          }
+        }
+      }
+      if (usable) {
+        const float mp = mat_scattering_pdf<FULL>(s, wo, l_wi);
+        const float w = power_heuristic(l_pdf, mp);
+        const v3 contrib = T * mat_eval<FULL>(sc, s, wo, l_wi) * w * le / l_pdf;  // mis.rs:42
+        const v3 sd = l_wi / mag(l_wi);  // Ray::new normalises (ray.rs:14)
+        sh_o = make_float4(so.x, so.y, so.z, tmax);
+        sh_d = make_float4(sd.x, sd.y, sd.z, __uint_as_float(exclude));
+        sh_c = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(slot));
+        shadow = true;
+      }
+    }
+}
+
 template <int METHOD, bool FULL>
 PTB_DEV void shade_path(const DevScene& sc, const PathPool& pool, const RenderParams& rp, uint32_t slot, bool depth0,
                         unsigned long long camera_first, ShadeOut& o) {
@@ -768,61 +840,7 @@ PTB_DEV void shade_path(const DevScene& sc, const PathPool& pool, const RenderPa
   if (depart) {
     float m_pdf = 0.0f;
     // ---- next-event estimation (MIS only): integrators/mis.rs:36-43, 95-157
-    if (METHOD == PTB_METHOD_MIS) {
-      const uint32_t n_l = sc.n_lights;
-      const bool sky_s = (sc.sky_rx | sc.sky_ry) != 0u;
-      if (n_l != 0u || sky_s) {
-        const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_NEE, 0u, rp.k0, rp.k1);
-        bool do_sky;
-        float mult;
-        uint32_t li = 0;
-        if (n_l == 0u) { do_sky = true; mult = 1.0f; }
-        else if (!sky_s) { do_sky = false; mult = 1.0f / (float)n_l; li = rng_below(r.x, n_l); }
-        else { mult = 1.0f / (float)(n_l + 1u); li = rng_below(r.x, n_l + 1u); do_sky = li == n_l; }
-        const v3 so = s.h.point + 0.0001f * s.h.normal;  // mis.rs:106,124
-        v3 l_wi, le;
-        float l_pdf = 0.0f, tmax = __int_as_float(0x7f800000);
-        uint32_t exclude = kNone;
-        bool usable = false;
-        if (do_sky) {
-          const uint4 r2 = philox4x32_10(pixel, sample, (depth << 8) | RNG_NEE, 1u, rp.k0, rp.k1);
-          l_wi = sky_sample(sc, u32_to_unit(r.y), u32_to_unit(r.z), u32_to_unit(r.w), u32_to_unit(r2.x));
-          const v3 point = offset_ray(s.h.point, s.h.normal, s.h.error, true);
-          le = 1.0f * texture_colour<FULL>(sc, sc.sky_tex, l_wi, point);
-          l_pdf = sky_pdf(sc, l_wi) * mult;
-          usable = true;
-          shadow_is_sky = 1u;
-        } else {
-          const uint32_t lref = __ldg(sc.lights + li);
-          l_wi = light_sample_dir(sc, lref, s.h.point, u32_to_unit(r.y), u32_to_unit(r.z));
-          const Ray sray = make_ray_from_raw(so, l_wi);
-          HitRec si;
-          if (prim_hit(sc, sray, lref, si) && si.t > 0.0f) {  // acceleration/mod.rs:231-243
-            const float pdf = light_pdf(sc, lref, s.h.point, l_wi, si.point, si.normal);
-            if (pdf > 0.0f) {
-              const uint32_t lmi = __ldg(sc.slot_mat + (lref & kSlotMask)) & 0x00FFFFFFu;
-              const DevMaterial* lm = sc.materials + lmi;
-              const v3 lpoint = offset_ray(si.point, si.normal, si.error, true);
-              le = __ldg(&lm->param) * texture_colour<FULL>(sc, __ldg(&lm->tex), l_wi, lpoint);
-              l_pdf = pdf * mult;
-              tmax = si.t;
-              exclude = lref & kSlotMask;
-              usable = true;
-            }
-          }
-        }
-        if (usable) {
-          const float mp = mat_scattering_pdf<FULL>(s, wo, l_wi);
-          const float w = power_heuristic(l_pdf, mp);
-          const v3 contrib = T * mat_eval<FULL>(sc, s, wo, l_wi) * w * le / l_pdf;  // mis.rs:42
-          const v3 sd = l_wi / mag(l_wi);  // Ray::new normalises (ray.rs:14)
-          sh_o = make_float4(so.x, so.y, so.z, tmax);
-          sh_d = make_float4(sd.x, sd.y, sd.z, __uint_as_float(exclude));
-          sh_c = make_float4(contrib.x, contrib.y, contrib.z, __uint_as_float(slot));
-          shadow = true;
-        }
-      }
-    }
+    if (METHOD == PTB_METHOD_MIS) nee_sample<FULL>(sc, rp, s, wo, T, pixel, sample, depth, slot, o);
     // ---- BSDF sample -> next ray
     const uint4 r = philox4x32_10(pixel, sample, (depth << 8) | RNG_SCATTER, 0u, rp.k0, rp.k1);
     v3 new_o, new_dir;

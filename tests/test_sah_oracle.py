@@ -74,3 +74,44 @@ def test_sah_definition_depth_bound(ptb, orc):
         h1, _, _ = o.lbvh_closest_hit(rays)
         assert np.array_equal(h0["prim"], h1["prim"]) and np.array_equal(h0["t"].view(np.uint32), h1["t"].view(np.uint32))
         o.lbvh_build()
+
+
+import pytest
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_sah_definition_random_scenes(ptb, orc, rtweekend1, seed):
+    """Random mixed scenes (spheres of very different sizes, slivers, duplicates, one flat axis): the tree is valid and its
+    ordered walk finds the hits of the brute-force scan over every primitive."""
+    import copy
+    rng = np.random.default_rng(100 + seed)
+    s = copy.deepcopy(rtweekend1)
+    ns, nt = int(rng.integers(1, 200)), int(rng.integers(0, 400))
+    sp = np.zeros(ns, ptb._lib.sphere_dtype)
+    sp["center"] = rng.uniform(-3, 3, (ns, 3))
+    sp["radius"] = 10.0 ** rng.uniform(-3, 0, ns)
+    if seed % 2:
+        sp["center"][:, 1] = 0.5                      # every centroid on one plane
+        sp["center"][ns // 2:] = sp["center"][0]      # and half of them identical
+    s.spheres = sp
+    tri = np.zeros(nt, ptb._lib.triangle_dtype)
+    if nt:
+        base = rng.uniform(-3, 3, (nt, 1, 3))
+        ext = 10.0 ** rng.uniform(-3, 0.3, (nt, 1, 1))
+        tri["p"] = base + ext * rng.uniform(-1, 1, (nt, 3, 3)) * np.array([1.0, 1.0, 0.02 if seed % 3 == 0 else 1.0])
+        n = np.cross(tri["p"][:, 1] - tri["p"][:, 0], tri["p"][:, 2] - tri["p"][:, 0])
+        n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-30)
+        tri["n"] = n[:, None, :]
+    s.triangles = tri
+    o = orc.OracleScene(s, split_type=-1)
+    o.lbvh_sah()
+    _, prims, nodes = o.lbvh_export()
+    if s.n_primitives >= 2:
+        _check_tree(nodes, prims, s.n_primitives)
+    rays = random_rays(ptb, 20_000, 200 + seed, centre=(0, 0, 0), radius=4.0)
+    h, _, _ = o.lbvh_closest_hit(rays)
+    b = o.closest_hit_brute(rays)
+    same = (h["prim"] == b["prim"]) | ((h["t"] == b["t"]) & (h["prim"] != MISS) & (b["prim"] != MISS))
+    assert same.all(), np.nonzero(~same)[0][:5]
+    m = h["prim"] != MISS
+    assert np.array_equal(h["t"][m].view(np.uint32), b["t"][m].view(np.uint32))

@@ -7,7 +7,7 @@
 //
 //   S1  k_sah_root        root task: all positions of the Morton order, box = union of the primitive boxes (k_prim_bounds)
 //   per level of LARGE tasks (more than 32 positions), tasks in position order:
-//   S2  k_sah_clear / k_sah_bin    8 bins on each axis of the task's box: union of boxes + count (warp-aggregated atomics)
+//   S2  k_sah_clear / k_sah_bin    8 bins on each axis of the task's box: union of boxes + count (block- / warp-aggregated atomics)
 //   S3  k_sah_eval        one thread per task: first minimum of the cost over axes x planes; names and links the node; the
 //                         children become leaves, SMALL tasks (appended to a list) or next-level large tasks
 //   S4  k_sah_task_scan / k_sah_emit   next level's task list, in position order

@@ -7,6 +7,7 @@ tests/test_oracle_kats.py and tests/test_materials_textures.py — so that (a) a
 its answers is caught on CPU and (b) the device is compared against committed numbers as well as against a live oracle.
 
     python tests/golden/make_golden.py        # rewrites *.npz next to this file
+    python tests/golden/make_golden.py sah    # only the sah_*.npz fixtures (the SAH builder's tree)
 """
 import os
 import sys
@@ -32,7 +33,22 @@ def scenes():
     yield "c3_small", ptb200.meshgen.c3_scene(0.03), (0.0, 4.0, 1.0), 5.0
 
 
+def sah_fixture(scene):
+    """The CPU definition of the device SAH builder (oracle/sah_ref.hpp): primitive order, topology, a checksum of the boxes."""
+    o = orc.OracleScene(scene, split_type=-1)
+    o.lbvh_sah()
+    _, order, nodes = o.lbvh_export()
+    return {"order": order, "node_children": np.stack([nodes["left"], nodes["right"], nodes["parent"]], 1),
+            "node_box_sum": np.array([nodes[k].astype(np.float64).sum() for k in ("lmin", "lmax", "rmin", "rmax")])}
+
+
+def main_sah():
+    for name, scene, _, _ in scenes():
+        np.savez_compressed(os.path.join(HERE, f"sah_{name}.npz"), **sah_fixture(scene))
+
+
 def main():
+    main_sah()
     for name, scene, centre, radius in scenes():
         o = orc.OracleScene(scene)
         rays = golden_rays(centre, radius)
@@ -57,4 +73,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main_sah() if sys.argv[1:] == ["sah"] else main()

@@ -59,6 +59,35 @@ def test_device_reproduces_golden(ptb, gpu_ctx, name):
     _check_lbvh(g, *gpu_ctx.bvh_export())                                        # Morton sort + topology + boxes bit-exact
 
 
+def _check_sah(g, order, nodes):
+    assert np.array_equal(order, g["order"])
+    leaf, sphere_bit = 0x80000000, np.uint32(0x40000000)
+    kids = np.stack([nodes["left"], nodes["right"], nodes["parent"]], 1)
+    kids[:, :2] = np.where(kids[:, :2] >= leaf, kids[:, :2] & ~sphere_bit, kids[:, :2])
+    assert np.array_equal(kids, g["node_children"])
+    sums = np.array([nodes[k].astype(np.float64).sum() for k in ("lmin", "lmax", "rmin", "rmax")])
+    assert np.array_equal(sums, g["node_box_sum"])
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_oracle_reproduces_golden_sah_tree(orc, name):
+    g = np.load(os.path.join(GOLDEN, f"sah_{name}.npz"))
+    f = G.sah_fixture(SCENES[name][0])
+    for k in ("order", "node_children", "node_box_sum"):
+        assert np.array_equal(f[k], g[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_device_reproduces_golden_sah_tree(ptb, gpu_ctx, name):
+    """The device SAH builder against the committed tree of its CPU definition (order, links; boxes by checksum)."""
+    g = np.load(os.path.join(GOLDEN, f"sah_{name}.npz"))
+    gpu_ctx.upload(SCENES[name][0])
+    gpu_ctx.commit(ptb._lib.BUILD_SAH)
+    _, order, nodes = gpu_ctx.bvh_export()
+    _check_sah(g, order, nodes)
+
+
 @pytest.mark.gpu
 def test_device_reproduces_golden_images(ptb, gpu_ctx, rtweekend1):
     g = np.load(os.path.join(GOLDEN, "render_rtweekend1_48x27x8.npz"))

@@ -510,6 +510,15 @@ def run_ours(args):
         except Exception as exc:  # the leg must not take the headline down with it
             extra["c5"] = {"error": repr(exc)}
 
+    # ---- extra.c1_mis / extra.c2_mis (N = 1, default workload): BASELINE configs[0] and [1], the MIS integrator on the two
+    # shipped scenes, bounded (a fraction of a second each) so that they are driver-run beside the headline
+    if world == 1 and args.workload == "c3" and not args.no_c5_leg:
+        for key, leg in (("c1_mis", ("rtweekend1", 800, 450, 64, 1)), ("c2_mis", ("overshadowed", 1920, 1080, 256, 1))):
+            try:
+                extra[key] = run_render_leg(local, *leg)
+            except Exception as exc:  # a leg must not take the headline down with it
+                extra[key] = {"error": repr(exc)}
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         # Algorithmic bytes of a closest-hit traversal: 32 B ray in + 16 B hit out + V nodes + T primitives
@@ -553,6 +562,56 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_render_leg(local, workload, w, h, spp, method, steps=3, warmup=3):
+    """A bounded device-timed leg of another BASELINE render config inside the default run (extra.c1_mis / extra.c2_mis):
+    the same measurement as the headline (CUDA events around `steps` renders of `spp` samples per pixel, inputs resident),
+    with the roofline block of ITS dominant kernel. N = 1 only; no CPU leg, no e2e."""
+    import torch
+    import ptb200
+    path = os.path.join(ROOT, "scenes", workload + ".ssml")
+    scene = ptb200.load_file(path)
+    ctx = ptb200.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.upload(scene)
+    ctx.commit()
+
+    def step(i):
+        ctx.accum_clear()
+        ctx.render(ptb200.RenderOptions(samples_per_pixel=spp, sample_offset=i * spp, render_method=method, width=w, height=h, seed=0))
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    ctx.set_option(ptb200._lib.OPT_TIME_KERNELS, 1)
+    ctx.stats_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(steps):
+        step(warmup + i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1)
+    st = ctx.stats()
+    ctx.set_option(ptb200._lib.OPT_TIME_KERNELS, 0)
+    ms_by_kernel = {"k_trace": st.ms_trace, "k_shade": st.ms_shade, "k_shadow": st.ms_shadow, "bookkeeping": st.ms_generate,
+                    "k_tail": st.ms_tail}
+    dominant = max(("k_trace", "k_shade", "k_shadow"), key=lambda k: ms_by_kernel[k])
+    ev = ncu_evidence(f"rtweekend1:{dominant}") or {}   # the sphere scenes share one capture (rtweekend1 3840x2160 MIS)
+    out = {"metric": "Mrays/s", "value": st.rays_total / (dev_ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": 1, "steps": steps,
+           "warmup": warmup, "ms_per_step": dev_ms / steps, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{workload}.ssml, {w}x{h}, {'mis' if method == 1 else 'naive'}, depth 50", "width": w, "height": h,
+                      "spp_per_step": spp, "primitives": int(scene.n_primitives)},
+           "gpu_launches": int(st.kernel_launches),
+           "roofline": {"kernel": dominant, "bound": ev.get("bound", "unprofiled"), "achieved": ev.get("achieved"), "peak": ev.get("peak"),
+                        "unit": ev.get("unit"), "frac": ev.get("frac"),
+                        "frac_source": ev.get("source", "no ncu capture committed for this kernel"),
+                        "traffic": ev.get("dram_bytes_per_launch"), "traffic_source": ev.get("traffic_source"),
+                        "ms_by_kernel": ms_by_kernel, "dominant_kernel_share_of_step": ms_by_kernel[dominant] / dev_ms if dev_ms else None}}
+    ctx.close()
+    return out
 
 
 def binary_tree_label(ctx):
